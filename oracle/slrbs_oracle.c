@@ -1,0 +1,1373 @@
+/*
+ * slrbs_oracle.c -- CPU ORACLE (test infrastructure, NOT the product).
+ * See slrbs_oracle.h for status ("parity unpinned by reference tests"), conventions
+ * and the Eigen 3.4 operation orders restated here.  All citations are relative
+ * to the reference tree (sheldona/slrbs).
+ *
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared (see oracle/Makefile).
+ */
+#include "slrbs_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ------------------------------------------------------------------ */
+/* Eigen 3.4 arithmetic restated                */
+/* ------------------------------------------------------------------ */
+typedef struct { float x, y, z; } v3;
+typedef struct { float x, y, z, w; } quat;     /* Eigen coeffs() order */
+typedef struct { float m[3][3]; } m3;          /* m[row][col]          */
+
+static inline v3 V3(float x, float y, float z) { v3 r = { x, y, z }; return r; }
+static inline v3 v3_add(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 v3_sub(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 v3_neg(v3 a) { return V3(-a.x, -a.y, -a.z); }
+static inline v3 v3_scale(float s, v3 a) { return V3(s * a.x, s * a.y, s * a.z); }
+static inline v3 v3_div(v3 a, float s) { return V3(a.x / s, a.y / s, a.z / s); }
+/* fixed-size 3-term reduction: Eigen redux_novec_unroller tree a0 + (a1 + a2) */
+static inline float sum3(float a0, float a1, float a2) { return a0 + (a1 + a2); }
+static inline float v3_dot(v3 a, v3 b) { return sum3(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline float v3_sqnorm(v3 a) { return sum3(a.x * a.x, a.y * a.y, a.z * a.z); }
+static inline float v3_norm(v3 a) { return sqrtf(v3_sqnorm(a)); }
+/* MatrixBase::cross (Geometry/OrthoMethods.h) */
+static inline v3 v3_cross(v3 a, v3 b)
+{
+    return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+/* MatrixBase::normalize: z = squaredNorm(); if (z > 0) *this /= sqrt(z) */
+static inline v3 v3_normalized(v3 a)
+{
+    float z = v3_sqnorm(a);
+    if (z > 0.0f) return v3_div(a, sqrtf(z));
+    return a;
+}
+static inline float get3(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+/* 4-term reduction on quaternion coeffs: SSE2 predux (a0 + a2) + (a1 + a3) */
+static inline float q_sqnorm(quat q) { return (q.x * q.x + q.z * q.z) + (q.y * q.y + q.w * q.w); }
+/* QuaternionBase::_transformVector */
+static inline v3 q_rot(quat q, v3 v)
+{
+    v3 qv = V3(q.x, q.y, q.z);
+    v3 uv = v3_cross(qv, v);
+    uv = v3_add(uv, uv);
+    return v3_add(v3_add(v, v3_scale(q.w, uv)), v3_cross(qv, uv));
+}
+/* QuaternionBase::inverse: conjugate / squaredNorm (true divides), zero if n2 == 0 */
+static inline quat q_inverse(quat q)
+{
+    float n2 = q_sqnorm(q);
+    quat r;
+    if (n2 > 0.0f) { r.x = -q.x / n2; r.y = -q.y / n2; r.z = -q.z / n2; r.w = q.w / n2; }
+    else { r.x = r.y = r.z = r.w = 0.0f; }
+    return r;
+}
+/* quaternion product, SSE2 specialisation add order (Geometry_SIMD.h):
+ * res = (a * b.wwww - a.zxyx * b.yzxx) + (+-)(a.yzxz * b.zxyz + a.wwwy * b.xyzy), sign - on w */
+static inline quat q_mul(quat a, quat b)
+{
+    quat r;
+    r.x = (a.x * b.w - a.z * b.y) + (a.y * b.z + a.w * b.x);
+    r.y = (a.y * b.w - a.x * b.z) + (a.z * b.x + a.w * b.y);
+    r.z = (a.z * b.w - a.y * b.x) + (a.x * b.y + a.w * b.z);
+    r.w = (a.w * b.w - a.x * b.x) + (-(a.z * b.z + a.y * b.y));
+    return r;
+}
+/* QuaternionBase::normalize -> coeffs().normalize() */
+static inline quat q_normalized(quat q)
+{
+    float z = q_sqnorm(q);
+    if (z > 0.0f) {
+        float s = sqrtf(z);
+        q.x /= s; q.y /= s; q.z /= s; q.w /= s;
+    }
+    return q;
+}
+/* QuaternionBase::toRotationMatrix */
+static inline m3 q_to_matrix(quat q)
+{
+    m3 R;
+    const float tx = 2.0f * q.x, ty = 2.0f * q.y, tz = 2.0f * q.z;
+    const float twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    const float txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    const float tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    R.m[0][0] = 1.0f - (tyy + tzz); R.m[0][1] = txy - twz;          R.m[0][2] = txz + twy;
+    R.m[1][0] = txy + twz;          R.m[1][1] = 1.0f - (txx + tzz); R.m[1][2] = tyz - twx;
+    R.m[2][0] = txz - twy;          R.m[2][1] = tyz + twx;          R.m[2][2] = 1.0f - (txx + tyy);
+    return R;
+}
+/* AngleAxis -> Quaternion (Geometry/Quaternion.h operator=(AngleAxis)) */
+static inline quat q_from_angle_axis(float angle, v3 axis)
+{
+    const float ha = 0.5f * angle;
+    const float s = sinf(ha);
+    quat q; q.w = cosf(ha); q.x = s * axis.x; q.y = s * axis.y; q.z = s * axis.z;
+    return q;
+}
+static inline quat q_identity(void) { quat q = { 0.f, 0.f, 0.f, 1.f }; return q; }
+
+static inline m3 m3_zero(void) { m3 r; memset(&r, 0, sizeof r); return r; }
+static inline m3 m3_mul(const m3* A, const m3* B)
+{
+    m3 C;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            C.m[i][j] = sum3(A->m[i][0] * B->m[0][j], A->m[i][1] * B->m[1][j], A->m[i][2] * B->m[2][j]);
+    return C;
+}
+static inline v3 m3_mulv(const m3* A, v3 v)
+{
+    return V3(sum3(A->m[0][0] * v.x, A->m[0][1] * v.y, A->m[0][2] * v.z),
+              sum3(A->m[1][0] * v.x, A->m[1][1] * v.y, A->m[1][2] * v.z),
+              sum3(A->m[2][0] * v.x, A->m[2][1] * v.y, A->m[2][2] * v.z));
+}
+/* Matrix3f::inverse (LU/InverseImpl.h compute_inverse_size3_helper: cofactors * (1/det)) */
+static inline float cof3(const m3* A, int i, int j)
+{
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return A->m[i1][j1] * A->m[i2][j2] - A->m[i1][j2] * A->m[i2][j1];
+}
+static inline m3 m3_inverse(const m3* A)
+{
+    m3 R;
+    const float c00 = cof3(A, 0, 0), c10 = cof3(A, 1, 0), c20 = cof3(A, 2, 0);
+    const float det = sum3(c00 * A->m[0][0], c10 * A->m[1][0], c20 * A->m[2][0]);
+    const float invdet = 1.0f / det;
+    /* result(r,c) = cofactor(c,r) * invdet */
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            R.m[r][c] = cof3(A, c, r) * invdet;
+    return R;
+}
+
+/* ------------------------------------------------------------------ */
+/* data model (RigidBody.h:38-57, Joint.h:24-39, Contact.h:20-42)      */
+/* ------------------------------------------------------------------ */
+typedef struct { int kind; int idx; } cref;   /* kind 0 = contact, 1 = joint */
+
+typedef struct {
+    int   fixed;
+    float mass;
+    m3    I, Iinv, Ibody, IbodyInv;
+    v3    x; quat q;
+    v3    xdot, omega, f, tau, fc, tauc;
+    int   geom_type;
+    float radius;          /* sphere, cylinder */
+    v3    dim;             /* box */
+    float height;          /* cylinder */
+    v3    plane_p, plane_n;
+    int  *contacts; int n_contacts, cap_contacts;   /* indices into sys->contacts, detection order */
+    int  *joints;   int n_joints,   cap_joints;     /* indices into sys->joints, insertion order   */
+    /* RigidBodyState snapshot */
+    v3 sx, sxdot, somega; quat sq;
+} body_t;
+
+typedef struct {
+    int   type;            /* ORC_CONTACT / ORC_SPHERICAL / ORC_HINGE */
+    int   body0, body1;
+    int   dim;
+    float J0[5][6], J1[5][6], J0Minv[5][6], J1Minv[5][6];
+    float phi[5], lambda[5];
+    unsigned idx;
+    v3    r0, r1; quat q0, q1;
+    v3    p, n, t, b; float pene;    /* contact only */
+} con_t;
+
+struct orc_system {
+    body_t *bodies;   int n_bodies,   cap_bodies;
+    con_t  *joints;   int n_joints,   cap_joints;
+    con_t  *contacts; int n_contacts, cap_contacts;
+    float mu;               /* Contact::mu, Contact.cpp:4 */
+    int   solverId;         /* RigidBodySystem.cpp:23 */
+    int   solverIter;       /* RigidBodySystem.cpp:22 */
+    int   collisions;       /* m_collisionsEnabled, :26 */
+    long long pairs_tested;
+};
+
+static void push_int(int **arr, int *n, int *cap, int v)
+{
+    if (*n == *cap) { *cap = *cap ? *cap * 2 : 8; *arr = (int*)realloc(*arr, (size_t)*cap * sizeof(int)); }
+    (*arr)[(*n)++] = v;
+}
+
+orc_system* orc_create(void)
+{
+    orc_system* s = (orc_system*)calloc(1, sizeof *s);
+    s->mu = 0.8f; s->solverId = 0; s->solverIter = 10; s->collisions = 1;
+    return s;
+}
+
+/* RigidBodySystem::clear, RigidBodySystem.cpp:123-146 */
+void orc_clear(orc_system* s)
+{
+    for (int i = 0; i < s->n_bodies; ++i) { free(s->bodies[i].contacts); free(s->bodies[i].joints); }
+    s->n_bodies = s->n_joints = s->n_contacts = 0;
+}
+
+void orc_destroy(orc_system* s)
+{
+    if (!s) return;
+    orc_clear(s);
+    free(s->bodies); free(s->joints); free(s->contacts);
+    free(s);
+}
+
+void orc_set_params(orc_system* s, float mu, int solver_id, int solver_iter, int collisions)
+{
+    s->mu = mu; s->solverId = solver_id; s->solverIter = solver_iter; s->collisions = collisions;
+}
+
+/* Geometry::computeInertia, include/collision/Geometry.h:38-43,63-70,91-102,120-124 */
+static m3 compute_inertia(const body_t* b, float mass)
+{
+    m3 I = m3_zero();
+    switch (b->geom_type) {
+    case ORC_SPHERE:
+        I.m[0][0] = I.m[1][1] = I.m[2][2] = (2.0f / 5.0f) * mass * b->radius * b->radius;
+        break;
+    case ORC_BOX:
+        I.m[0][0] = (1.0f / 12.0f) * mass * (b->dim.y * b->dim.y + b->dim.z * b->dim.z);
+        I.m[1][1] = (1.0f / 12.0f) * mass * (b->dim.x * b->dim.x + b->dim.z * b->dim.z);
+        I.m[2][2] = (1.0f / 12.0f) * mass * (b->dim.x * b->dim.x + b->dim.y * b->dim.y);
+        break;
+    case ORC_CYLINDER: {
+        const float s12 = 1.0f / 12.0f;
+        const float h2 = b->height * b->height;
+        const float r2 = b->radius * b->radius;
+        const float r2_h2_3 = (3.0f * r2 + h2);
+        I.m[0][0] = s12 * mass * r2_h2_3;
+        I.m[1][1] = 0.5f * mass * r2;
+        I.m[2][2] = s12 * mass * r2_h2_3;
+        break; }
+    default: /* plane: zero inertia, Geometry.h:120-124 */
+        break;
+    }
+    return I;
+}
+
+/* RigidBody::RigidBody, src/rigidbody/RigidBody.cpp:9-45 (mesh registration omitted: render-only) */
+int orc_add_body(orc_system* s, float mass, int geom_type, const float* g, int fixed,
+                 const float* x3, const float* q, const float* v, const float* w)
+{
+    if (s->n_bodies == s->cap_bodies) {
+        s->cap_bodies = s->cap_bodies ? s->cap_bodies * 2 : 64;
+        s->bodies = (body_t*)realloc(s->bodies, (size_t)s->cap_bodies * sizeof(body_t));
+    }
+    body_t* b = &s->bodies[s->n_bodies];
+    memset(b, 0, sizeof *b);
+    b->fixed = fixed; b->mass = mass;
+    b->geom_type = geom_type;
+    switch (geom_type) {
+    case ORC_SPHERE:   b->radius = g[0]; break;
+    case ORC_BOX:      b->dim = V3(g[0], g[1], g[2]); break;
+    case ORC_PLANE:    b->plane_p = V3(g[0], g[1], g[2]); b->plane_n = V3(g[3], g[4], g[5]); break;
+    case ORC_CYLINDER: b->height = g[0]; b->radius = g[1]; break;
+    }
+    b->x = x3 ? V3(x3[0], x3[1], x3[2]) : V3(0, 0, 0);
+    if (q) { b->q.x = q[0]; b->q.y = q[1]; b->q.z = q[2]; b->q.w = q[3]; } else b->q = q_identity();
+    b->xdot  = v ? V3(v[0], v[1], v[2]) : V3(0, 0, 0);
+    b->omega = w ? V3(w[0], w[1], w[2]) : V3(0, 0, 0);
+    b->Iinv = m3_zero();               /* RigidBody.cpp:18 (I is left uninitialised there; zero here) */
+    b->I = m3_zero();
+    b->Ibody = compute_inertia(b, mass);   /* :27 */
+    b->IbodyInv = m3_inverse(&b->Ibody);   /* :28 */
+    return s->n_bodies++;
+}
+
+static con_t* new_joint(orc_system* s)
+{
+    if (s->n_joints == s->cap_joints) {
+        s->cap_joints = s->cap_joints ? s->cap_joints * 2 : 16;
+        s->joints = (con_t*)realloc(s->joints, (size_t)s->cap_joints * sizeof(con_t));
+    }
+    con_t* j = &s->joints[s->n_joints];
+    memset(j, 0, sizeof *j);
+    return j;
+}
+
+/* RigidBodySystem::addJoint, RigidBodySystem.cpp:44-50 */
+static int register_joint(orc_system* s)
+{
+    const int id = s->n_joints++;
+    con_t* j = &s->joints[id];
+    body_t* b0 = &s->bodies[j->body0];
+    body_t* b1 = &s->bodies[j->body1];
+    push_int(&b0->joints, &b0->n_joints, &b0->cap_joints, id);
+    push_int(&b1->joints, &b1->n_joints, &b1->cap_joints, id);
+    return id;
+}
+
+/* Hinge::Hinge, src/joint/Hinge.cpp:21-31 */
+int orc_add_hinge(orc_system* s, int b0, int b1, const float* r0, const float* q0,
+                  const float* r1, const float* q1)
+{
+    con_t* j = new_joint(s);
+    j->type = ORC_HINGE; j->dim = 5; j->body0 = b0; j->body1 = b1;
+    j->r0 = V3(r0[0], r0[1], r0[2]); j->r1 = V3(r1[0], r1[1], r1[2]);
+    j->q0.x = q0[0]; j->q0.y = q0[1]; j->q0.z = q0[2]; j->q0.w = q0[3];
+    j->q1.x = q1[0]; j->q1.y = q1[1]; j->q1.z = q1[2]; j->q1.w = q1[3];
+    return register_joint(s);
+}
+
+/* Spherical::Spherical, src/joint/Spherical.cpp:22-32 */
+int orc_add_spherical(orc_system* s, int b0, int b1, const float* r0, const float* r1)
+{
+    con_t* j = new_joint(s);
+    j->type = ORC_SPHERICAL; j->dim = 3; j->body0 = b0; j->body1 = b1;
+    j->r0 = V3(r0[0], r0[1], r0[2]); j->r1 = V3(r1[0], r1[1], r1[2]);
+    j->q0 = q_identity(); j->q1 = q_identity();
+    return register_joint(s);
+}
+
+/* ------------------------------------------------------------------ */
+/* S1/S2/S4: reset, inertia update, contact clear                      */
+/* ------------------------------------------------------------------ */
+/* RigidBody::updateInertiaMatrix, src/rigidbody/RigidBody.cpp:78-89
+ * I = q * Ibody * q.inverse()  ==  (R(q) * Ibody) * R(q^-1) */
+static void update_inertia(body_t* b)
+{
+    if (!b->fixed) {
+        const m3 R = q_to_matrix(b->q);
+        const m3 Rinv = q_to_matrix(q_inverse(b->q));
+        m3 T = m3_mul(&R, &b->Ibody);
+        b->I = m3_mul(&T, &Rinv);
+        T = m3_mul(&R, &b->IbodyInv);
+        b->Iinv = m3_mul(&T, &Rinv);
+    } else {
+        b->Iinv = m3_zero();
+    }
+}
+
+/* RigidBodySystem.cpp:58-65, :68 (computeInertias :148-154), :75 (CollisionDetect::clear, CollisionDetect.cpp:87-100) */
+void orc_stage_prepare(orc_system* s)
+{
+    for (int i = 0; i < s->n_bodies; ++i) {
+        body_t* b = &s->bodies[i];
+        b->f = v3_scale(b->mass, V3(0.f, -9.81f, 0.f));
+        b->tau = V3(0, 0, 0); b->fc = V3(0, 0, 0); b->tauc = V3(0, 0, 0);
+        b->n_contacts = 0;
+    }
+    for (int i = 0; i < s->n_bodies; ++i) update_inertia(&s->bodies[i]);
+    s->n_contacts = 0;
+    for (int i = 0; i < s->n_bodies; ++i) s->bodies[i].n_contacts = 0;
+}
+
+/* RigidBody::addForceAtPos, src/rigidbody/RigidBody.cpp:91-96 */
+void orc_add_force_at_pos(orc_system* s, int body, const float* pos, const float* force)
+{
+    body_t* b = &s->bodies[body];
+    const v3 F = V3(force[0], force[1], force[2]);
+    const v3 r = v3_sub(V3(pos[0], pos[1], pos[2]), b->x);
+    b->f = v3_add(b->f, F);
+    b->tau = v3_add(b->tau, v3_cross(r, F));
+}
+
+void orc_add_force(orc_system* s, int body, const float* f3, const float* tau3)
+{
+    body_t* b = &s->bodies[body];
+    if (f3)   b->f   = v3_add(b->f,   V3(f3[0], f3[1], f3[2]));
+    if (tau3) b->tau = v3_add(b->tau, V3(tau3[0], tau3[1], tau3[2]));
+}
+
+/* ------------------------------------------------------------------ */
+/* S5-S9: collision detection                                          */
+/* ------------------------------------------------------------------ */
+/* Contact::Contact, src/contact/Contact.cpp:11-26 */
+static void new_contact(orc_system* s, int body0, int body1, v3 p, v3 n, float pene)
+{
+    if (s->n_contacts == s->cap_contacts) {
+        s->cap_contacts = s->cap_contacts ? s->cap_contacts * 2 : 256;
+        s->contacts = (con_t*)realloc(s->contacts, (size_t)s->cap_contacts * sizeof(con_t));
+    }
+    const int id = s->n_contacts++;
+    con_t* c = &s->contacts[id];
+    memset(c, 0, sizeof *c);
+    c->type = ORC_CONTACT; c->dim = 3;
+    c->body0 = body0; c->body1 = body1;
+    c->p = p; c->n = n; c->pene = pene;
+    c->phi[0] = pene;
+    c->q0 = q_identity(); c->q1 = q_identity();
+    body_t* b0 = &s->bodies[body0];
+    body_t* b1 = &s->bodies[body1];
+    push_int(&b0->contacts, &b0->n_contacts, &b0->cap_contacts, id);   /* :24 */
+    push_int(&b1->contacts, &b1->n_contacts, &b1->cap_contacts, id);   /* :25 */
+}
+
+/* distancePointPlane, CollisionDetect.cpp:12-17 */
+static inline float distance_point_plane(v3 p, v3 plane_p, v3 plane_n)
+{
+    return v3_dot(v3_sub(p, plane_p), plane_n);
+}
+
+/* collisionDetectSphereSphere, CollisionDetect.cpp:102-123 */
+static void detect_sphere_sphere(orc_system* s, int i0, int i1)
+{
+    const body_t* body0 = &s->bodies[i0];
+    const body_t* body1 = &s->bodies[i1];
+    const v3 vec = v3_sub(body0->x, body1->x);
+    const float rsum = (body0->radius + body1->radius);
+    const float dist = v3_norm(vec);
+    if (dist < (rsum + 1e-3f)) {
+        const v3 n = v3_div(vec, dist);
+        const v3 p = v3_scale(0.5f, v3_add(v3_sub(body0->x, v3_scale(body0->radius, n)),
+                                           v3_add(body1->x, v3_scale(body1->radius, n))));
+        const float phi = fminf(0.0f, dist - rsum);
+        new_contact(s, i0, i1, p, n, phi);
+    }
+}
+
+/* collisionDetectSphereBox, CollisionDetect.cpp:125-150 (body0 = sphere, body1 = box) */
+static void detect_sphere_box(orc_system* s, int i0, int i1)
+{
+    const body_t* body0 = &s->bodies[i0];
+    const body_t* body1 = &s->bodies[i1];
+    const v3 clocal = q_rot(q_inverse(body1->q), v3_sub(body0->x, body1->x));
+    float c[3] = { clocal.x, clocal.y, clocal.z };
+    float d[3] = { body1->dim.x, body1->dim.y, body1->dim.z };
+    float q[3] = { 0.f, 0.f, 0.f };
+    for (int i = 0; i < 3; ++i) {
+        q[i] = c[i];
+        if (q[i] < (-d[i] / 2.0f)) q[i] = -d[i] / 2.0f;
+        else if (q[i] > (d[i] / 2.0f)) q[i] = (d[i] / 2.0f);
+    }
+    const v3 qv = V3(q[0], q[1], q[2]);
+    const v3 dx = v3_sub(clocal, qv);
+    const float dist = v3_norm(dx);
+    if (dist < (body0->radius + 1e-3f)) {
+        const v3 n = q_rot(body1->q, v3_div(dx, dist));
+        const v3 p = v3_add(q_rot(body1->q, qv), body1->x);
+        const float phi = fminf(0.0f, dist - body0->radius);
+        new_contact(s, i0, i1, p, n, phi);
+    }
+}
+
+/* collisionDetectCylinderPlane, CollisionDetect.cpp:152-274 (body0 = cylinder, body1 = plane) */
+static void detect_cylinder_plane(orc_system* s, int i0, int i1)
+{
+    const body_t* body0 = &s->bodies[i0];
+    const body_t* body1 = &s->bodies[i1];
+    const float cyl_h = body0->height, cyl_r = body0->radius;
+
+    const v3 cyldir = q_rot(body0->q, V3(0, 1, 0));                          /* :158 */
+    const v3 planen = q_rot(body1->q, body1->plane_n);                       /* :159 */
+    const v3 planep = v3_add(q_rot(body1->q, body1->plane_p), body1->x);     /* :160 */
+    const float dp = v3_dot(cyldir, planen);
+
+    if (fabsf(dp) > 0.995f) {                                                /* :164 cap face */
+        v3 w = (dp < 0.0f) ? cyldir : v3_neg(cyldir);
+        v3 u, v;
+        if (fabsf(v3_dot(w, V3(1, 0, 0))) > 0.01f) u = v3_cross(w, V3(1, 0, 0));
+        else                                        u = v3_cross(w, V3(0, 0, 1));
+        u = v3_normalized(u);
+        v = v3_cross(w, u);
+        v = v3_normalized(v);
+        const v3 a = v3_add(body0->x, v3_scale(0.5f * cyl_h, w));            /* :189 (0.5f*h)*w */
+        const float dist = distance_point_plane(a, planep, planen);
+        if (dist < 1e-3f) {
+            const v3 n = planen;
+            const v3 pA = v3_add(a, v3_scale(cyl_r, u));
+            const v3 pB = v3_sub(a, v3_scale(cyl_r, u));
+            const v3 pC = v3_add(a, v3_scale(cyl_r, v));
+            const v3 pD = v3_sub(a, v3_scale(cyl_r, v));
+            const float phiA = distance_point_plane(pA, planep, planen);
+            const float phiB = distance_point_plane(pB, planep, planen);
+            const float phiC = distance_point_plane(pC, planep, planen);
+            const float phiD = distance_point_plane(pD, planep, planen);
+            if (phiA < 1e-3f) new_contact(s, i0, i1, pA, n, fminf(0.0f, phiA));
+            if (phiB < 1e-3f) new_contact(s, i0, i1, pB, n, fminf(0.0f, phiB));
+            if (phiC < 1e-3f) new_contact(s, i0, i1, pC, n, fminf(0.0f, phiC));
+            if (phiD < 1e-3f) new_contact(s, i0, i1, pD, n, fminf(0.0f, phiD));
+        }
+    } else if (fabsf(dp) < 1e-2f) {                                          /* :215 side */
+        const v3 w = cyldir;
+        v3 u = v3_cross(v3_cross(planen, w), w);
+        if (v3_dot(u, planen) > 0.0f) u = v3_neg(u);
+        u = v3_normalized(u);
+        const v3 cylpos = body0->x;
+        const float dist = distance_point_plane(cylpos, planep, planen) - cyl_r;
+        if (dist < 0.01f) {                                                   /* :227 */
+            const v3 n = planen;
+            /* cylpos + 0.5f*h*cyldir + r*u : ((cylpos + (0.5f*h)*cyldir) + r*u) */
+            const v3 hw = v3_scale(0.5f * cyl_h, cyldir);
+            const v3 ru = v3_scale(cyl_r, u);
+            const v3 pA = v3_add(v3_add(cylpos, hw), ru);
+            const v3 pB = v3_add(v3_sub(cylpos, hw), ru);
+            const float phiA = distance_point_plane(pA, planep, planen);
+            const float phiB = distance_point_plane(pB, planep, planen);
+            if (phiA < 1e-3f) new_contact(s, i0, i1, pA, n, fminf(0.0f, phiA));
+            if (phiB < 1e-3f) new_contact(s, i0, i1, pB, n, fminf(0.0f, phiB));
+        }
+    } else {                                                                  /* :241 general */
+        v3 w = (dp < 0.0f) ? cyldir : v3_neg(cyldir);
+        w = v3_normalized(w);
+        v3 u = v3_cross(v3_cross(planen, w), w);
+        u = v3_normalized(u);
+        if (v3_dot(u, planen) > 0.0f) u = v3_neg(u);
+        u = v3_normalized(u);
+        const v3 a = v3_add(v3_add(body0->x, v3_scale(0.5f * cyl_h, w)), v3_scale(cyl_r, u));
+        const float dist = distance_point_plane(a, planep, planen);
+        if (dist < 1e-3f) {
+            new_contact(s, i0, i1, a, planen, fminf(0.0f, dist));
+        }
+    }
+}
+
+/* CollisionDetect::detectCollisions, CollisionDetect.cpp:27-76 */
+void orc_stage_detect(orc_system* s)
+{
+    s->pairs_tested = 0;
+    if (!s->collisions) return;                         /* RigidBodySystem.cpp:77 */
+    const int n = s->n_bodies;
+    for (int i = 0; i < n; ++i) {
+        for (int j = i + 1; j < n; ++j) {
+            const body_t* body0 = &s->bodies[i];
+            const body_t* body1 = &s->bodies[j];
+            if (body0->fixed && body1->fixed) continue;
+            s->pairs_tested++;
+            const int t0 = body0->geom_type, t1 = body1->geom_type;
+            if (t0 == ORC_SPHERE && t1 == ORC_SPHERE)        detect_sphere_sphere(s, i, j);
+            else if (t0 == ORC_SPHERE && t1 == ORC_BOX)      detect_sphere_box(s, i, j);
+            else if (t1 == ORC_SPHERE && t0 == ORC_BOX)      detect_sphere_box(s, j, i);
+            else if (t0 == ORC_CYLINDER && t1 == ORC_PLANE)  detect_cylinder_plane(s, i, j);
+            else if (t1 == ORC_CYLINDER && t0 == ORC_PLANE)  detect_cylinder_plane(s, j, i);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* S10-S13: frames and Jacobians                                       */
+/* ------------------------------------------------------------------ */
+/* Contact::computeContactFrame, Contact.cpp:33-53 */
+static void contact_frame(con_t* c)
+{
+    c->t = v3_cross(c->n, V3(1, 0, 0));
+    if (v3_norm(c->t) < 1e-5f) c->t = v3_cross(c->n, V3(0, 1, 0));
+    c->t = v3_normalized(c->t);
+    c->b = v3_cross(c->n, c->t);
+    c->b = v3_normalized(c->b);
+}
+
+static inline void set_row(float* row, v3 lin, v3 ang)
+{
+    row[0] = lin.x; row[1] = lin.y; row[2] = lin.z; row[3] = ang.x; row[4] = ang.y; row[5] = ang.z;
+}
+
+/* J*Minv blocks: linear = (1/mass) * J_lin ; angular = J_ang * Iinv (Contact.cpp:90-93, Hinge.cpp:59-62) */
+static void compute_JMinv(int dim, float J[5][6], float JM[5][6], const body_t* b)
+{
+    const float im = 1.0f / b->mass;
+    for (int r = 0; r < dim; ++r) {
+        for (int c = 0; c < 3; ++c) JM[r][c] = im * J[r][c];
+        for (int c = 0; c < 3; ++c)
+            JM[r][3 + c] = sum3(J[r][3] * b->Iinv.m[0][c], J[r][4] * b->Iinv.m[1][c], J[r][5] * b->Iinv.m[2][c]);
+    }
+}
+
+/* Contact::computeJacobian, Contact.cpp:55-94 */
+static void contact_jacobian(orc_system* s, con_t* c)
+{
+    const body_t* body0 = &s->bodies[c->body0];
+    const body_t* body1 = &s->bodies[c->body1];
+    const v3 rr0 = v3_sub(c->p, body0->x);
+    const v3 rr1 = v3_sub(c->p, body1->x);
+    memset(c->J0, 0, sizeof c->J0); memset(c->J1, 0, sizeof c->J1);
+    memset(c->J0Minv, 0, sizeof c->J0Minv); memset(c->J1Minv, 0, sizeof c->J1Minv);
+    memset(c->lambda, 0, sizeof c->lambda); memset(c->phi, 0, sizeof c->phi);
+    c->phi[0] = c->pene;
+    const v3 d[3] = { c->n, c->t, c->b };
+    for (int k = 0; k < 3; ++k) {
+        set_row(c->J0[k], d[k], v3_cross(rr0, d[k]));
+        set_row(c->J1[k], v3_neg(d[k]), v3_neg(v3_cross(rr1, d[k])));
+    }
+    compute_JMinv(3, c->J0, c->J0Minv, body0);
+    compute_JMinv(3, c->J1, c->J1Minv, body1);
+}
+
+/* hat(), Hinge.cpp:6-13 */
+static void set_hat(float J[5][6], v3 v)
+{
+    J[0][3] = 0.f;   J[0][4] = -v.z; J[0][5] = v.y;
+    J[1][3] = v.z;   J[1][4] = 0.f;  J[1][5] = -v.x;
+    J[2][3] = -v.y;  J[2][4] = v.x;  J[2][5] = 0.f;
+}
+
+/* Hinge::computeJacobian, Hinge.cpp:33-63 ; Spherical::computeJacobian, Spherical.cpp:34-52 */
+static void joint_jacobian(orc_system* s, con_t* j)
+{
+    const body_t* body0 = &s->bodies[j->body0];
+    const body_t* body1 = &s->bodies[j->body1];
+    const v3 rr0 = q_rot(body0->q, j->r0);
+    const v3 rr1 = q_rot(body1->q, j->r1);
+    /* phi(0:3) = x0 + rr0 - x1 - rr1 (left to right) */
+    const v3 e = v3_sub(v3_sub(v3_add(body0->x, rr0), body1->x), rr1);
+    j->phi[0] = e.x; j->phi[1] = e.y; j->phi[2] = e.z;
+    /* Rows are rewritten in place each step; entries never written stay 0 from construction. */
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+        j->J0[r][c] = (r == c) ? 1.f : 0.f;
+        j->J1[r][c] = (r == c) ? -1.f : 0.f;
+    }
+    set_hat(j->J0, v3_neg(rr0));
+    set_hat(j->J1, rr1);
+    if (j->type == ORC_HINGE) {
+        const v3 nn = q_rot(body0->q, q_rot(j->q0, V3(1, 0, 0)));
+        const v3 uu = q_rot(body1->q, q_rot(j->q1, V3(0, 1, 0)));
+        const v3 vv = q_rot(body1->q, q_rot(j->q1, V3(0, 0, 1)));
+        const v3 nxu = v3_cross(nn, uu);
+        const v3 nxv = v3_cross(nn, vv);
+        j->phi[3] = v3_dot(nn, uu);
+        j->phi[4] = v3_dot(nn, vv);
+        set_row(j->J0[3], V3(0, 0, 0), nxu);
+        set_row(j->J0[4], V3(0, 0, 0), nxv);
+        set_row(j->J1[3], V3(0, 0, 0), v3_neg(nxu));
+        set_row(j->J1[4], V3(0, 0, 0), v3_neg(nxv));
+    }
+    compute_JMinv(j->dim, j->J0, j->J0Minv, body0);
+    compute_JMinv(j->dim, j->J1, j->J1Minv, body1);
+}
+
+/* CollisionDetect::computeContactJacobians (CollisionDetect.cpp:78-85), joints (RigidBodySystem.cpp:83-86),
+ * zero fc/tauc (:88-92) */
+void orc_stage_jacobians(orc_system* s)
+{
+    if (s->collisions) {
+        for (int i = 0; i < s->n_contacts; ++i) {
+            contact_frame(&s->contacts[i]);
+            contact_jacobian(s, &s->contacts[i]);
+        }
+    }
+    for (int i = 0; i < s->n_joints; ++i) joint_jacobian(s, &s->joints[i]);
+    for (int i = 0; i < s->n_bodies; ++i) { s->bodies[i].fc = V3(0, 0, 0); s->bodies[i].tauc = V3(0, 0, 0); }
+}
+
+/* ------------------------------------------------------------------ */
+/* S14-S18: Box-PGS (src/solvers/SolverBoxPGS.cpp)                     */
+/* ------------------------------------------------------------------ */
+/* multAndSub, SolverBoxPGS.cpp:13-21: b -= (a * G.col(k)) * x(k) */
+static void mult_and_sub(int dim, float G[5][6], v3 x, v3 y, float a, float* b)
+{
+    const float xs[6] = { x.x, x.y, x.z, y.x, y.y, y.z };
+    for (int k = 0; k < 6; ++k)
+        for (int r = 0; r < dim; ++r)
+            b[r] -= (a * G[r][k]) * xs[k];
+}
+
+/* buildRHS, SolverBoxPGS.cpp:27-44 */
+static void build_rhs(const orc_system* s, con_t* j, float h, float* b)
+{
+    const float hinv = 1.0f / h;
+    const float gamma = 0.3f;
+    const body_t* body0 = &s->bodies[j->body0];
+    const body_t* body1 = &s->bodies[j->body1];
+    for (int r = 0; r < j->dim; ++r) b[r] = (-hinv * gamma) * j->phi[r];
+    if (!body0->fixed) {
+        mult_and_sub(j->dim, j->J0Minv, body0->f, body0->tau, h, b);
+        mult_and_sub(j->dim, j->J0, body0->xdot, body0->omega, 1.0f, b);
+    }
+    if (!body1->fixed) {
+        mult_and_sub(j->dim, j->J1Minv, body1->f, body1->tau, h, b);
+        mult_and_sub(j->dim, j->J1, body1->xdot, body1->omega, 1.0f, b);
+    }
+}
+
+/* b -= JMinv * (Jother^T * lambda_other) */
+static void sub_coupling(int dim, float JMinv[5][6], const con_t* o, float Jo[5][6], float* b)
+{
+    float t[6];
+    for (int c = 0; c < 6; ++c) {
+        float acc = 0.f;
+        for (int k = 0; k < o->dim; ++k) acc += Jo[k][c] * o->lambda[k];
+        t[c] = acc;
+    }
+    for (int r = 0; r < dim; ++r) {
+        float acc = 0.f;
+        for (int c = 0; c < 6; ++c) acc += JMinv[r][c] * t[c];
+        b[r] -= acc;
+    }
+}
+
+/* accumulateCoupledContactsAndJoints, SolverBoxPGS.cpp:49-82 */
+static void accumulate_coupled(orc_system* s, int self_kind, int self_idx, int dim,
+                               float JMinv[5][6], int body, float* b)
+{
+    body_t* bd = &s->bodies[body];
+    if (bd->fixed) return;
+    for (int k = 0; k < bd->n_contacts; ++k) {
+        const int ci = bd->contacts[k];
+        if (self_kind == 0 && ci == self_idx) continue;
+        con_t* cc = &s->contacts[ci];
+        if (body == cc->body0) sub_coupling(dim, JMinv, cc, cc->J0, b);
+        else                   sub_coupling(dim, JMinv, cc, cc->J1, b);
+    }
+    for (int k = 0; k < bd->n_joints; ++k) {
+        const int ji = bd->joints[k];
+        if (self_kind == 1 && ji == self_idx) continue;
+        con_t* jj = &s->joints[ji];
+        if (body == jj->body0) sub_coupling(dim, JMinv, jj, jj->J0, b);
+        else                   sub_coupling(dim, JMinv, jj, jj->J1, b);
+    }
+}
+
+/* solveContact, SolverBoxPGS.cpp:94-113 */
+static void solve_contact(const float A[3][3], const float* b, float* x, float mu)
+{
+    x[0] = (b[0] - A[0][1] * x[1] - A[0][2] * x[2]) / (A[0][0] + 1e-3f);
+    if (x[0] < 0.0f) x[0] = 0.0f;
+    const float lowerx = -mu * x[0];
+    const float upperx = mu * x[0];
+    x[1] = (b[1] - A[1][0] * x[0] - A[1][2] * x[2]) / A[1][1];
+    if (x[1] < lowerx) x[1] = lowerx; else if (x[1] > upperx) x[1] = upperx;
+    x[2] = (b[2] - A[2][0] * x[0] - A[2][1] * x[1]) / A[2][2];
+    if (x[2] < lowerx) x[2] = lowerx; else if (x[2] > upperx) x[2] = upperx;
+}
+
+/* Eigen::LDLT<MatrixXf> restated (Cholesky/LDLT.h): symmetric diagonal pivoting on the
+ * largest |diagonal| entry, in-place lower factorisation; solve = P^T L^-T D^-1 L^-1 P b
+ * with Eigen's pseudo-inverse tolerance on D. */
+typedef struct { int n; float m[5][5]; int tr[5]; } ldlt_t;
+
+static void ldlt_factor(ldlt_t* F, int n, float A[5][5])
+{
+    F->n = n;
+    memcpy(F->m, A, sizeof F->m);
+    float (*M)[5] = F->m;
+    for (int k = 0; k < n; ++k) {
+        int piv = k; float big = fabsf(M[k][k]);
+        for (int i = k + 1; i < n; ++i) if (fabsf(M[i][i]) > big) { big = fabsf(M[i][i]); piv = i; }
+        F->tr[k] = piv;
+        if (piv != k) {
+            /* symmetric swap of rows/cols k and piv in the lower triangle */
+            for (int c = 0; c < k; ++c) { float t = M[k][c]; M[k][c] = M[piv][c]; M[piv][c] = t; }
+            for (int r = piv + 1; r < n; ++r) { float t = M[r][k]; M[r][k] = M[r][piv]; M[r][piv] = t; }
+            { float t = M[k][k]; M[k][k] = M[piv][piv]; M[piv][piv] = t; }
+            for (int i = k + 1; i < piv; ++i) { float t = M[i][k]; M[i][k] = M[piv][i]; M[piv][i] = t; }
+        }
+        /* A10 = M[k][0:k], A20 = M[k+1:n][0:k], A21 = M[k+1:n][k] */
+        if (k > 0) {
+            float temp[5];
+            for (int c = 0; c < k; ++c) temp[c] = M[c][c] * M[k][c];
+            float acc = 0.f;
+            for (int c = 0; c < k; ++c) acc += M[k][c] * temp[c];
+            M[k][k] -= acc;
+            for (int r = k + 1; r < n; ++r) {
+                float a2 = 0.f;
+                for (int c = 0; c < k; ++c) a2 += M[r][c] * temp[c];
+                M[r][k] -= a2;
+            }
+        }
+        const float piv_val = M[k][k];
+        if (fabsf(piv_val) > 0.0f)
+            for (int r = k + 1; r < n; ++r) M[r][k] /= piv_val;
+    }
+}
+
+static void ldlt_solve(const ldlt_t* F, const float* b, float* x)
+{
+    const int n = F->n;
+    float y[5];
+    for (int i = 0; i < n; ++i) y[i] = b[i];
+    for (int k = 0; k < n; ++k) { const int p = F->tr[k]; if (p != k) { float t = y[k]; y[k] = y[p]; y[p] = t; } }
+    for (int i = 0; i < n; ++i) { float acc = y[i]; for (int c = 0; c < i; ++c) acc -= F->m[i][c] * y[c]; y[i] = acc; }
+    const float tol = 1.17549435e-38f;   /* (std::numeric_limits<float>::min)() */
+    for (int i = 0; i < n; ++i) { if (fabsf(F->m[i][i]) > tol) y[i] /= F->m[i][i]; else y[i] = 0.f; }
+    for (int i = n - 1; i >= 0; --i) { float acc = y[i]; for (int r = i + 1; r < n; ++r) acc -= F->m[r][i] * y[r]; y[i] = acc; }
+    for (int k = n - 1; k >= 0; --k) { const int p = F->tr[k]; if (p != k) { float t = y[k]; y[k] = y[p]; y[p] = t; } }
+    for (int i = 0; i < n; ++i) x[i] = y[i];
+}
+
+/* A += JMinv * J^T  (dim x dim) */
+static void add_JMinvJT(int dim, float JM[5][6], float J[5][6], float A[5][5])
+{
+    for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) {
+            float acc = 0.f;
+            for (int k = 0; k < 6; ++k) acc += JM[r][k] * J[c][k];
+            A[r][c] += acc;
+        }
+}
+
+/* SolverBoxPGS::solve, SolverBoxPGS.cpp:126-250 */
+static void solve_box_pgs(orc_system* s, float h)
+{
+    const int numContacts = s->n_contacts;
+    const int numJoints = s->n_joints;
+    const int N = numJoints + numContacts;
+    ldlt_t* LLT = numJoints ? (ldlt_t*)malloc((size_t)numJoints * sizeof(ldlt_t)) : NULL;
+    float (*Acc)[3][3] = numContacts ? (float (*)[3][3])malloc((size_t)numContacts * sizeof(float[3][3])) : NULL;
+
+    for (int i = 0; i < numJoints; ++i) {                                   /* :134-163 */
+        con_t* j = &s->joints[i];
+        float A[5][5]; memset(A, 0, sizeof A);
+        for (int d = 0; d < j->dim; ++d) A[d][d] = 1e-5f;
+        if (!s->bodies[j->body0].fixed) add_JMinvJT(j->dim, j->J0Minv, j->J0, A);
+        if (!s->bodies[j->body1].fixed) add_JMinvJT(j->dim, j->J1Minv, j->J1, A);
+        ldlt_factor(&LLT[i], j->dim, A);
+    }
+    for (int i = 0; i < numContacts; ++i) {                                 /* :165-189 */
+        con_t* c = &s->contacts[i];
+        float A[5][5]; memset(A, 0, sizeof A);
+        if (!s->bodies[c->body0].fixed) add_JMinvJT(3, c->J0Minv, c->J0, A);
+        if (!s->bodies[c->body1].fixed) add_JMinvJT(3, c->J1Minv, c->J1, A);
+        for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) Acc[i][r][cc] = A[r][cc];
+    }
+    if (N > 0) {
+        float (*b)[5] = (float (*)[5])calloc((size_t)N, sizeof(float[5]));
+        for (int i = 0; i < numJoints; ++i) build_rhs(s, &s->joints[i], h, b[i]);          /* :200-204 */
+        for (int i = 0; i < numContacts; ++i) {                                              /* :206-211 */
+            build_rhs(s, &s->contacts[i], h, b[i + numJoints]);
+            s->contacts[i].lambda[0] = s->contacts[i].lambda[1] = s->contacts[i].lambda[2] = 0.f;
+        }
+        for (int iter = 0; iter < s->solverIter; ++iter) {                                   /* :217-248 */
+            for (int i = 0; i < numJoints; ++i) {
+                con_t* j = &s->joints[i];
+                float x[5];
+                for (int r = 0; r < j->dim; ++r) x[r] = b[i][r];
+                accumulate_coupled(s, 1, i, j->dim, j->J0Minv, j->body0, x);
+                accumulate_coupled(s, 1, i, j->dim, j->J1Minv, j->body1, x);
+                ldlt_solve(&LLT[i], x, j->lambda);
+            }
+            for (int i = 0; i < numContacts; ++i) {
+                con_t* c = &s->contacts[i];
+                float x[5];
+                for (int r = 0; r < 3; ++r) x[r] = b[i + numJoints][r];
+                accumulate_coupled(s, 0, i, 3, c->J0Minv, c->body0, x);
+                accumulate_coupled(s, 0, i, 3, c->J1Minv, c->body1, x);
+                solve_contact(Acc[i], x, c->lambda, s->mu);
+            }
+        }
+        free(b);
+    }
+    free(LLT); free(Acc);
+}
+
+/* ------------------------------------------------------------------ */
+/* S23: CG / CR joint-only solvers                                     */
+/* ------------------------------------------------------------------ */
+static int assign_joint_idx(orc_system* s)
+{
+    unsigned idx = 0;
+    for (int i = 0; i < s->n_joints; ++i) { s->joints[i].idx = idx; idx += (unsigned)s->joints[i].dim; }
+    return (int)idx;
+}
+
+/* buildRHS, SolverConjGradient.cpp:26-47 / SolverConjResidual.cpp:25-46 */
+static void krylov_build_rhs(orc_system* s, float h, float* b)
+{
+    for (int i = 0; i < s->n_joints; ++i) build_rhs(s, &s->joints[i], h, b + s->joints[i].idx);
+}
+
+/* Ax.segment(j) += JMinv * (Jo^T * x.segment(o)) */
+static void add_coupling(con_t* j, float JMinv[5][6], con_t* o, float Jo[5][6], const float* x, float* Ax)
+{
+    float t[6];
+    for (int c = 0; c < 6; ++c) {
+        float acc = 0.f;
+        for (int k = 0; k < o->dim; ++k) acc += Jo[k][c] * x[o->idx + k];
+        t[c] = acc;
+    }
+    for (int r = 0; r < j->dim; ++r) {
+        float acc = 0.f;
+        for (int c = 0; c < 6; ++c) acc += JMinv[r][c] * t[c];
+        Ax[j->idx + r] += acc;
+    }
+}
+
+/* computeAx, SolverConjGradient.cpp:49-100 (eps = 0) and SolverConjResidual.cpp:68-92 (eps = 1e-9) */
+static void krylov_compute_Ax(orc_system* s, const float* x, float* Ax, int n, float eps, int use_eps)
+{
+    for (int i = 0; i < n; ++i) Ax[i] = 0.f;
+    for (int i = 0; i < s->n_joints; ++i) {
+        con_t* j = &s->joints[i];
+        body_t* body0 = &s->bodies[j->body0];
+        body_t* body1 = &s->bodies[j->body1];
+        if (use_eps) for (int r = 0; r < j->dim; ++r) Ax[j->idx + r] += eps * x[j->idx + r];
+        if (!body0->fixed) {
+            add_coupling(j, j->J0Minv, j, j->J0, x, Ax);
+            for (int k = 0; k < body0->n_joints; ++k) {
+                const int ji = body0->joints[k];
+                if (ji == i) continue;
+                con_t* jj = &s->joints[ji];
+                add_coupling(j, j->J0Minv, jj, (j->body0 == jj->body0) ? jj->J0 : jj->J1, x, Ax);
+            }
+        }
+        if (!body1->fixed) {
+            add_coupling(j, j->J1Minv, j, j->J1, x, Ax);
+            for (int k = 0; k < body1->n_joints; ++k) {
+                const int ji = body1->joints[k];
+                if (ji == i) continue;
+                con_t* jj = &s->joints[ji];
+                add_coupling(j, j->J1Minv, jj, (j->body1 == jj->body0) ? jj->J0 : jj->J1, x, Ax);
+            }
+        }
+    }
+}
+
+static float dotn(const float* a, const float* b, int n) { float acc = 0.f; for (int i = 0; i < n; ++i) acc += a[i] * b[i]; return acc; }
+
+/* SolverConjGradient::solve, SolverConjGradient.cpp:109-162 (keeps p = r - beta*p, :150) */
+static void solve_conj_gradient(orc_system* s, float h)
+{
+    const int n = assign_joint_idx(s);
+    if (n == 0) return;
+    float* buf = (float*)calloc((size_t)n * 6, sizeof(float));
+    float *x = buf, *r = buf + n, *p = buf + 2 * n, *b = buf + 3 * n, *Ax = buf + 4 * n, *Ap = buf + 5 * n;
+    krylov_build_rhs(s, h, b);
+    krylov_compute_Ax(s, x, Ax, n, 0.f, 0);
+    for (int i = 0; i < n; ++i) { r[i] = b[i] - Ax[i]; p[i] = r[i]; }
+    float rTr = dotn(r, r, n);
+    krylov_compute_Ax(s, p, Ap, n, 0.f, 0);
+    float pAp = dotn(p, Ap, n);
+    for (int it = 0; it < s->solverIter; ++it) {
+        if (rTr < 1e-12f) break;
+        if (pAp < 1e-12f) break;
+        const float alpha = rTr / pAp;
+        for (int i = 0; i < n; ++i) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; }
+        const float rTr_next = dotn(r, r, n);
+        const float beta = rTr_next / rTr;
+        for (int i = 0; i < n; ++i) p[i] = r[i] - beta * p[i];
+        krylov_compute_Ax(s, p, Ap, n, 0.f, 0);
+        pAp = dotn(p, Ap, n);
+        rTr = rTr_next;
+    }
+    for (int i = 0; i < s->n_joints; ++i)
+        for (int k = 0; k < s->joints[i].dim; ++k) s->joints[i].lambda[k] = x[s->joints[i].idx + k];
+    free(buf);
+}
+
+/* SolverConjResidual::solve, SolverConjResidual.cpp:100-158 */
+static void solve_conj_residual(orc_system* s, float h)
+{
+    const int n = assign_joint_idx(s);
+    if (n == 0) return;
+    float* buf = (float*)calloc((size_t)n * 7, sizeof(float));
+    float *x = buf, *r = buf + n, *p = buf + 2 * n, *b = buf + 3 * n, *Ax = buf + 4 * n, *Ap = buf + 5 * n, *Ar = buf + 6 * n;
+    const float eps = 1e-9f;
+    krylov_build_rhs(s, h, b);
+    krylov_compute_Ax(s, x, Ax, n, eps, 1);
+    for (int i = 0; i < n; ++i) { r[i] = b[i] - Ax[i]; p[i] = r[i]; }
+    krylov_compute_Ax(s, p, Ap, n, eps, 1);
+    krylov_compute_Ax(s, r, Ar, n, eps, 1);
+    float rAr = dotn(r, Ar, n);
+    float pATAp = dotn(Ap, Ap, n);
+    for (int it = 0; it < s->solverIter; ++it) {
+        if (rAr < 1e-12f) break;
+        if (pATAp < 1e-12f) break;
+        const float alpha = rAr / pATAp;
+        for (int i = 0; i < n; ++i) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; }
+        krylov_compute_Ax(s, r, Ar, n, eps, 1);
+        const float rAr_next = dotn(r, Ar, n);
+        const float beta = rAr_next / rAr;
+        for (int i = 0; i < n; ++i) { p[i] = r[i] + beta * p[i]; Ap[i] = Ar[i] + beta * Ap[i]; }
+        rAr = rAr_next;
+        pATAp = dotn(Ap, Ap, n);
+    }
+    for (int i = 0; i < s->n_joints; ++i)
+        for (int k = 0; k < s->joints[i].dim; ++k) s->joints[i].lambda[k] = x[s->joints[i].idx + k];
+    free(buf);
+}
+
+/* calcConstraintForces head, RigidBodySystem.cpp:181-182 */
+void orc_stage_solve(orc_system* s, float dt)
+{
+    switch (s->solverId) {
+    case 1:  solve_conj_gradient(s, dt); break;
+    case 2:  solve_conj_residual(s, dt); break;
+    default: solve_box_pgs(s, dt); break;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* S19: constraint-force scatter, RigidBodySystem.cpp:185-220          */
+/* ------------------------------------------------------------------ */
+static void jt_lambda_over_dt(const con_t* c, float J[5][6], float dt, float* f6)
+{
+    for (int k = 0; k < 6; ++k) {
+        float acc = 0.f;
+        for (int r = 0; r < c->dim; ++r) acc += J[r][k] * c->lambda[r];
+        f6[k] = acc / dt;
+    }
+}
+
+void orc_stage_scatter(orc_system* s, float dt)
+{
+    for (int i = 0; i < s->n_joints; ++i) {
+        con_t* j = &s->joints[i];
+        float f0[6], f1[6];
+        jt_lambda_over_dt(j, j->J0, dt, f0);
+        jt_lambda_over_dt(j, j->J1, dt, f1);
+        body_t* b0 = &s->bodies[j->body0];
+        body_t* b1 = &s->bodies[j->body1];
+        b0->fc = v3_add(b0->fc, V3(f0[0], f0[1], f0[2])); b0->tauc = v3_add(b0->tauc, V3(f0[3], f0[4], f0[5]));
+        b1->fc = v3_add(b1->fc, V3(f1[0], f1[1], f1[2])); b1->tauc = v3_add(b1->tauc, V3(f1[3], f1[4], f1[5]));
+    }
+    for (int i = 0; i < s->n_contacts; ++i) {
+        con_t* c = &s->contacts[i];
+        float f0[6], f1[6];
+        jt_lambda_over_dt(c, c->J0, dt, f0);
+        jt_lambda_over_dt(c, c->J1, dt, f1);
+        body_t* b0 = &s->bodies[c->body0];
+        body_t* b1 = &s->bodies[c->body1];
+        if (!b0->fixed) { b0->fc = v3_add(b0->fc, V3(f0[0], f0[1], f0[2])); b0->tauc = v3_add(b0->tauc, V3(f0[3], f0[4], f0[5])); }
+        if (!b1->fixed) { b1->fc = v3_add(b1->fc, V3(f1[0], f1[1], f1[2])); b1->tauc = v3_add(b1->tauc, V3(f1[3], f1[4], f1[5])); }
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* S20: integration, RigidBodySystem.cpp:99-120                        */
+/* ------------------------------------------------------------------ */
+void orc_stage_integrate(orc_system* s, float dt)
+{
+    for (int i = 0; i < s->n_bodies; ++i) {
+        body_t* b = &s->bodies[i];
+        if (!b->fixed) {
+            b->xdot = v3_add(b->xdot, v3_scale(dt * (1.0f / b->mass), v3_add(b->f, b->fc)));
+            const v3 Iw = m3_mulv(&b->I, b->omega);
+            const v3 rhs = v3_sub(v3_add(b->tau, b->tauc), v3_cross(b->omega, Iw));
+            /* (dt * Iinv) * v evaluated as dt * (Iinv * v)   */
+            b->omega = v3_add(b->omega, v3_scale(dt, m3_mulv(&b->Iinv, rhs)));
+            b->x = v3_add(b->x, v3_scale(dt, b->xdot));
+            /* q = q + (0.5*dt) * Quaternionf(0, omega) * q ; helpers RigidBodySystem.h:78-88 */
+            const float hdt = 0.5f * dt;
+            quat wq; wq.w = hdt * 0.0f; wq.x = hdt * b->omega.x; wq.y = hdt * b->omega.y; wq.z = hdt * b->omega.z;
+            const quat dq = q_mul(wq, b->q);
+            quat qn; qn.w = b->q.w + dq.w; qn.x = b->q.x + dq.x; qn.y = b->q.y + dq.y; qn.z = b->q.z + dq.z;
+            b->q = q_normalized(qn);
+        } else {
+            b->xdot = V3(0, 0, 0);
+            b->omega = V3(0, 0, 0);
+        }
+    }
+}
+
+/* RigidBodySystem::step, RigidBodySystem.cpp:52-121 (pre-step callback :70-73 is the caller's
+ * business: run orc_stage_prepare, mutate, then the remaining stages) */
+void orc_step(orc_system* s, float dt)
+{
+    orc_stage_prepare(s);
+    orc_stage_detect(s);
+    orc_stage_jacobians(s);
+    orc_stage_solve(s, dt);
+    orc_stage_scatter(s, dt);
+    orc_stage_integrate(s, dt);
+}
+
+double orc_time_steps(orc_system* s, float dt, int n)
+{
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < n; ++i) orc_step(s, dt);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+/* ------------------------------------------------------------------ */
+/* accessors                                                           */
+/* ------------------------------------------------------------------ */
+int orc_num_bodies(const orc_system* s) { return s->n_bodies; }
+int orc_num_joints(const orc_system* s) { return s->n_joints; }
+int orc_num_contacts(const orc_system* s) { return s->n_contacts; }
+int orc_num_joint_rows(const orc_system* s) { int n = 0; for (int i = 0; i < s->n_joints; ++i) n += s->joints[i].dim; return n; }
+long long orc_pairs_tested(const orc_system* s) { return s->pairs_tested; }
+
+static void put3(float* dst, int i, v3 v) { if (dst) { dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z; } }
+static void putq(float* dst, int i, quat q) { if (dst) { dst[4 * i] = q.x; dst[4 * i + 1] = q.y; dst[4 * i + 2] = q.z; dst[4 * i + 3] = q.w; } }
+static void putm(float* dst, int i, const m3* m) { if (dst) memcpy(dst + 9 * i, m->m, 9 * sizeof(float)); }
+
+void orc_get_state(const orc_system* s, float* x3, float* q, float* v3_, float* w3)
+{
+    for (int i = 0; i < s->n_bodies; ++i) {
+        const body_t* b = &s->bodies[i];
+        put3(x3, i, b->x); putq(q, i, b->q); put3(v3_, i, b->xdot); put3(w3, i, b->omega);
+    }
+}
+
+void orc_set_state(orc_system* s, const float* x3, const float* q, const float* v, const float* w)
+{
+    for (int i = 0; i < s->n_bodies; ++i) {
+        body_t* b = &s->bodies[i];
+        if (x3) b->x = V3(x3[3 * i], x3[3 * i + 1], x3[3 * i + 2]);
+        if (q) { b->q.x = q[4 * i]; b->q.y = q[4 * i + 1]; b->q.z = q[4 * i + 2]; b->q.w = q[4 * i + 3]; }
+        if (v) b->xdot = V3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        if (w) b->omega = V3(w[3 * i], w[3 * i + 1], w[3 * i + 2]);
+    }
+}
+
+void orc_get_body_params(const orc_system* s, float* mass, float* ibody9, float* ibodyinv9,
+                         int* fixed, int* geom_type, float* g)
+{
+    for (int i = 0; i < s->n_bodies; ++i) {
+        const body_t* b = &s->bodies[i];
+        if (mass) mass[i] = b->mass;
+        putm(ibody9, i, &b->Ibody); putm(ibodyinv9, i, &b->IbodyInv);
+        if (fixed) fixed[i] = b->fixed;
+        if (geom_type) geom_type[i] = b->geom_type;
+        if (g) {
+            float* o = g + 6 * i;
+            for (int k = 0; k < 6; ++k) o[k] = 0.f;
+            switch (b->geom_type) {
+            case ORC_SPHERE:   o[0] = b->radius; break;
+            case ORC_BOX:      o[0] = b->dim.x; o[1] = b->dim.y; o[2] = b->dim.z; break;
+            case ORC_PLANE:    o[0] = b->plane_p.x; o[1] = b->plane_p.y; o[2] = b->plane_p.z;
+                               o[3] = b->plane_n.x; o[4] = b->plane_n.y; o[5] = b->plane_n.z; break;
+            case ORC_CYLINDER: o[0] = b->height; o[1] = b->radius; break;
+            }
+        }
+    }
+}
+
+void orc_get_body_dyn(const orc_system* s, float* f3, float* tau3, float* fc3, float* tauc3, float* I9, float* Iinv9)
+{
+    for (int i = 0; i < s->n_bodies; ++i) {
+        const body_t* b = &s->bodies[i];
+        put3(f3, i, b->f); put3(tau3, i, b->tau); put3(fc3, i, b->fc); put3(tauc3, i, b->tauc);
+        putm(I9, i, &b->I); putm(Iinv9, i, &b->Iinv);
+    }
+}
+
+void orc_get_contacts(const orc_system* s, int* body0, int* body1, float* p3, float* n3,
+                      float* t3, float* b3, float* phi, float* lambda3)
+{
+    for (int i = 0; i < s->n_contacts; ++i) {
+        const con_t* c = &s->contacts[i];
+        if (body0) body0[i] = c->body0;
+        if (body1) body1[i] = c->body1;
+        put3(p3, i, c->p); put3(n3, i, c->n); put3(t3, i, c->t); put3(b3, i, c->b);
+        if (phi) phi[i] = c->pene;
+        if (lambda3) { lambda3[3 * i] = c->lambda[0]; lambda3[3 * i + 1] = c->lambda[1]; lambda3[3 * i + 2] = c->lambda[2]; }
+    }
+}
+
+void orc_get_contact_rows(const orc_system* s, float* J0, float* J1, float* J0M, float* J1M)
+{
+    for (int i = 0; i < s->n_contacts; ++i) {
+        const con_t* c = &s->contacts[i];
+        for (int r = 0; r < 3; ++r) for (int k = 0; k < 6; ++k) {
+            const int o = 18 * i + 6 * r + k;
+            if (J0) J0[o] = c->J0[r][k];
+            if (J1) J1[o] = c->J1[r][k];
+            if (J0M) J0M[o] = c->J0Minv[r][k];
+            if (J1M) J1M[o] = c->J1Minv[r][k];
+        }
+    }
+}
+
+void orc_get_joints(const orc_system* s, int* type, int* body0, int* body1, float* r0, float* q0,
+                    float* r1, float* q1)
+{
+    for (int i = 0; i < s->n_joints; ++i) {
+        const con_t* j = &s->joints[i];
+        if (type) type[i] = j->type;
+        if (body0) body0[i] = j->body0;
+        if (body1) body1[i] = j->body1;
+        put3(r0, i, j->r0); put3(r1, i, j->r1); putq(q0, i, j->q0); putq(q1, i, j->q1);
+    }
+}
+
+void orc_get_joint_rows(const orc_system* s, float* J0, float* J1, float* J0M, float* J1M, float* phi5, float* lambda5)
+{
+    for (int i = 0; i < s->n_joints; ++i) {
+        const con_t* j = &s->joints[i];
+        for (int r = 0; r < 5; ++r) {
+            for (int k = 0; k < 6; ++k) {
+                const int o = 30 * i + 6 * r + k;
+                const int live = r < j->dim;
+                if (J0) J0[o] = live ? j->J0[r][k] : 0.f;
+                if (J1) J1[o] = live ? j->J1[r][k] : 0.f;
+                if (J0M) J0M[o] = live ? j->J0Minv[r][k] : 0.f;
+                if (J1M) J1M[o] = live ? j->J1Minv[r][k] : 0.f;
+            }
+            if (phi5) phi5[5 * i + r] = r < j->dim ? j->phi[r] : 0.f;
+            if (lambda5) lambda5[5 * i + r] = r < j->dim ? j->lambda[r] : 0.f;
+        }
+    }
+}
+
+void orc_set_joint_lambda(orc_system* s, const float* lambda5)
+{
+    for (int i = 0; i < s->n_joints; ++i)
+        for (int r = 0; r < s->joints[i].dim; ++r) s->joints[i].lambda[r] = lambda5[5 * i + r];
+}
+
+/* RigidBodySystemState::save / restore, RigidBodyState.cpp:18-72 (joint lambda is NOT reset) */
+void orc_save_state(orc_system* s)
+{
+    for (int i = 0; i < s->n_bodies; ++i) {
+        body_t* b = &s->bodies[i];
+        b->sx = b->x; b->sxdot = b->xdot; b->sq = b->q; b->somega = b->omega;
+    }
+}
+
+void orc_restore_state(orc_system* s)
+{
+    for (int i = 0; i < s->n_bodies; ++i) {
+        body_t* b = &s->bodies[i];
+        b->x = b->sx; b->xdot = b->sxdot; b->q = b->sq; b->omega = b->somega;
+        b->f = V3(0, 0, 0); b->fc = V3(0, 0, 0);
+        b->n_contacts = 0;
+    }
+    s->n_contacts = 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Scenarios.h scene data (include/rigidbody/Scenarios.h)              */
+/* ------------------------------------------------------------------ */
+static int add_simple(orc_system* s, float mass, int type, float g0, float g1, float g2, float g3, float g4, float g5)
+{
+    const float g[6] = { g0, g1, g2, g3, g4, g5 };
+    return orc_add_body(s, mass, type, g, 0, NULL, NULL, NULL, NULL);
+}
+
+/* createMarbleBox, Scenarios.h:18-80 */
+void orc_scene_marble_box(orc_system* s)
+{
+    orc_clear(s);
+    const float radius = 0.5f;
+    for (int i = 0; i < 9; ++i) {
+        for (int j = 0; j < 9; ++j) {
+            int b1 = add_simple(s, 1.0f, ORC_SPHERE, radius, 0, 0, 0, 0, 0);
+            s->bodies[b1].x.x = -4.0f + (float)i * 1.0f;
+            s->bodies[b1].x.z = -4.0f + (float)j * 1.0f;
+            s->bodies[b1].x.y = 2.0f;
+            int b2 = add_simple(s, 1.0f, ORC_SPHERE, radius, 0, 0, 0, 0, 0);
+            s->bodies[b2].x.x = -4.0f + (float)i * 1.0f;
+            s->bodies[b2].x.z = -4.0f + (float)j * 1.0f;
+            s->bodies[b2].x.y = 3.0f;
+        }
+    }
+    const int s0 = add_simple(s, 1.0f, ORC_BOX, 0.4f, 4.0f, 10.0f, 0, 0, 0);
+    const int s1 = add_simple(s, 1.0f, ORC_BOX, 0.4f, 4.0f, 10.0f, 0, 0, 0);
+    const int s2 = add_simple(s, 1.0f, ORC_BOX, 0.4f, 4.0f, 10.0f, 0, 0, 0);
+    const int s3 = add_simple(s, 1.0f, ORC_BOX, 0.4f, 4.0f, 10.0f, 0, 0, 0);
+    const int s4 = add_simple(s, 1.0f, ORC_BOX, 10.0f, 0.4f, 10.0f, 0, 0, 0);
+    body_t* B = s->bodies;
+    B[s0].fixed = B[s1].fixed = B[s2].fixed = B[s3].fixed = B[s4].fixed = 1;
+    B[s0].x = V3(4.75f, 2.0f, 0.0f);
+    B[s1].x = V3(-4.75f, 2.0f, 0.0f);
+    B[s2].x = V3(0.0f, 2.0f, 4.75f);
+    B[s2].q = q_from_angle_axis(1.57f, V3(0, 1, 0));
+    B[s3].x = V3(0.0f, 2.0f, -4.75f);
+    B[s3].q = q_from_angle_axis(1.57f, V3(0, 1, 0));
+    B[s4].x = V3(0.0f, 0.0f, 0.0f);
+}
+
+/* createSphereOnBox, Scenarios.h:84-108 */
+void orc_scene_sphere_on_box(orc_system* s)
+{
+    orc_clear(s);
+    const int sp = add_simple(s, 1.0f, ORC_SPHERE, 0.5f, 0, 0, 0, 0, 0);
+    s->bodies[sp].x.y = 4.0f;
+    s->bodies[sp].omega = V3(10.0f, 0.0f, 0.0f);
+    const int bx = add_simple(s, 1.0f, ORC_BOX, 10.0f, 0.4f, 10.0f, 0, 0, 0);
+    s->bodies[bx].fixed = 1;
+}
+
+/* createSwingingBoxes, Scenarios.h:112-148 */
+void orc_scene_swinging_boxes(orc_system* s)
+{
+    orc_clear(s);
+    const int N = 20;
+    const int top = add_simple(s, 1.0f, ORC_BOX, 1.0f, 1.0f, 1.0f, 0, 0, 0);
+    s->bodies[top].x = V3(0.0f, 1.5f * (float)N, 0.0f);
+    s->bodies[top].fixed = 1;
+    const v3 dx = V3(0.0f, 1.5f, 0.0f);
+    int parent = top;
+    const float qi[4] = { 0.f, 0.f, 0.f, 1.f };
+    for (int i = 0; i < N - 1; ++i) {
+        const float mass = (i == (N - 2)) ? 100.0f : 1.0f;
+        const int next = add_simple(s, mass, ORC_BOX, 1.0f, 1.0f, 1.0f, 0, 0, 0);
+        s->bodies[next].x = v3_sub(s->bodies[parent].x, dx);
+        const v3 a0 = v3_scale(-0.5f, dx), a1 = v3_scale(0.5f, dx);
+        const float r0[3] = { a0.x, a0.y, a0.z }, r1[3] = { a1.x, a1.y, a1.z };
+        orc_add_hinge(s, parent, next, r0, qi, r1, qi);
+        parent = next;
+    }
+    s->bodies[parent].xdot = V3(0.0f, 0.0f, 10.0f);
+}
+
+/* createCylinderOnPlane, Scenarios.h:153-174 */
+void orc_scene_cylinder_on_plane(orc_system* s)
+{
+    orc_clear(s);
+    const int cyl = add_simple(s, 1.0f, ORC_CYLINDER, 2.0f, 1.0f, 0, 0, 0, 0);
+    s->bodies[cyl].x = V3(0.0f, 2.0f, 0.0f);
+    s->bodies[cyl].q = q_from_angle_axis(0.57f, V3(0.0f, 0.0f, 1.0f));
+    const int pl = add_simple(s, 1.0f, ORC_PLANE, 0, 0, 0, 0, 1.0f, 0);
+    s->bodies[pl].x = V3(0, 0, 0);
+    s->bodies[pl].fixed = 1;
+}
+
+/* createCarScene, Scenarios.h:178-247 */
+void orc_scene_car(orc_system* s)
+{
+    orc_clear(s);
+    const int chassis = add_simple(s, 5.0f, ORC_BOX, 2.0f, 0.5f, 3.0f, 0, 0, 0);
+    int wheel[4];
+    for (int k = 0; k < 4; ++k) wheel[k] = add_simple(s, 1.0f, ORC_CYLINDER, 0.2f, 0.5f, 0, 0, 0, 0);
+    body_t* B = s->bodies;
+    B[chassis].x = V3(0.0f, 0.5f, 0.0f);
+    B[chassis].xdot = V3(0.0f, 0.0f, -10.0f);
+    const float wx[4] = { 1.0f, -1.0f, 1.0f, -1.0f };
+    const float wz[4] = { 1.5f, 1.5f, -1.5f, -1.5f };
+    for (int k = 0; k < 4; ++k) {
+        B[wheel[k]].x = V3(wx[k], 0.5f, wz[k]);
+        B[wheel[k]].q = q_from_angle_axis(1.57079f, V3(0.0f, 0.0f, 1.0f));
+    }
+    const int plane = add_simple(s, 1.0f, ORC_PLANE, 0, 0, 0, 0, 1.0f, 0);
+    s->bodies[plane].x = V3(0, 0, 0);
+    s->bodies[plane].fixed = 1;
+    const quat hq = q_from_angle_axis(1.57f, V3(0, 0, 1));
+    const float q0[4] = { 0.f, 0.f, 0.f, 1.f };
+    const float q1[4] = { hq.x, hq.y, hq.z, hq.w };
+    const float r1[3] = { 0.f, 0.f, 0.f };
+    for (int k = 0; k < 4; ++k) {
+        const float r0[3] = { wx[k], 0.0f, wz[k] };
+        orc_add_hinge(s, chassis, wheel[k], r0, q0, r1, q1);
+    }
+}
+
+/* K spheres (r = 0.5, m = 1) stacked at y = 0.7 + k on the fixed
+ * 10 x 0.4 x 10 box of createSphereOnBox (Scenarios.h:99-101). Spheres first, then the box. */
+void orc_scene_sphere_stack(orc_system* s, int k)
+{
+    orc_clear(s);
+    for (int i = 0; i < k; ++i) {
+        const int sp = add_simple(s, 1.0f, ORC_SPHERE, 0.5f, 0, 0, 0, 0, 0);
+        s->bodies[sp].x = V3(0.0f, 0.7f + (float)i * 1.0f, 0.0f);
+    }
+    const int bx = add_simple(s, 1.0f, ORC_BOX, 10.0f, 0.4f, 10.0f, 0, 0, 0);
+    s->bodies[bx].fixed = 1;
+}
+
+/* SURVEY.md 8(d) MB1k family: createMarbleBox's construction scaled to nx x nz x ny spheres
+ * (r = 0.5, spacing 1, lowest layer y = 2), container = 4 fixed side boxes + floor sized to fit.
+ * Body order: for i, for j, for k (layers interleaved like the reference's lower/upper pair). */
+void orc_scene_marble_box_n(orc_system* s, int nx, int nz, int ny)
+{
+    orc_clear(s);
+    const float radius = 0.5f;
+    const float x0 = -0.5f * (float)(nx - 1), z0 = -0.5f * (float)(nz - 1);
+    for (int i = 0; i < nx; ++i)
+        for (int j = 0; j < nz; ++j)
+            for (int k = 0; k < ny; ++k) {
+                const int b = add_simple(s, 1.0f, ORC_SPHERE, radius, 0, 0, 0, 0, 0);
+                s->bodies[b].x = V3(x0 + (float)i * 1.0f, 2.0f + (float)k * 1.0f, z0 + (float)j * 1.0f);
+            }
+    const float ex = (float)nx + 1.0f, ez = (float)nz + 1.0f;     /* inner clearance like 10 for 9 spheres */
+    const float hy = (float)ny + 2.0f;
+    const float wallx = 0.5f * ex - 0.25f, wallz = 0.5f * ez - 0.25f;
+    const int s0 = add_simple(s, 1.0f, ORC_BOX, 0.4f, hy, ez, 0, 0, 0);
+    const int s1 = add_simple(s, 1.0f, ORC_BOX, 0.4f, hy, ez, 0, 0, 0);
+    const int s2 = add_simple(s, 1.0f, ORC_BOX, 0.4f, hy, ex, 0, 0, 0);
+    const int s3 = add_simple(s, 1.0f, ORC_BOX, 0.4f, hy, ex, 0, 0, 0);
+    const int s4 = add_simple(s, 1.0f, ORC_BOX, ex, 0.4f, ez, 0, 0, 0);
+    body_t* B = s->bodies;
+    B[s0].fixed = B[s1].fixed = B[s2].fixed = B[s3].fixed = B[s4].fixed = 1;
+    B[s0].x = V3(wallx, 0.5f * hy, 0.0f);
+    B[s1].x = V3(-wallx, 0.5f * hy, 0.0f);
+    B[s2].x = V3(0.0f, 0.5f * hy, wallz);
+    B[s2].q = q_from_angle_axis(1.57f, V3(0, 1, 0));
+    B[s3].x = V3(0.0f, 0.5f * hy, -wallz);
+    B[s3].q = q_from_angle_axis(1.57f, V3(0, 1, 0));
+    B[s4].x = V3(0.0f, 0.0f, 0.0f);
+}
