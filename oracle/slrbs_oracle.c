@@ -967,6 +967,38 @@ static void solve_conj_residual(orc_system* s, float h)
     free(buf);
 }
 
+
+/* The solver's per-constraint diagonal blocks and right-hand sides as SolverBoxPGS::solve builds
+ * them before its main loop (SolverBoxPGS.cpp:134-211); exported for per-stage parity tests. */
+void orc_get_solver_blocks(orc_system* s, float h, float* Acontact9, float* rhs_contact3, float* Ajoint25, float* rhs_joint5)
+{
+    for (int i = 0; i < s->n_contacts; ++i) {
+        con_t* c = &s->contacts[i];
+        float A[5][5]; memset(A, 0, sizeof A);
+        if (!s->bodies[c->body0].fixed) add_JMinvJT(3, c->J0Minv, c->J0, A);
+        if (!s->bodies[c->body1].fixed) add_JMinvJT(3, c->J1Minv, c->J1, A);
+        float b[5] = { 0, 0, 0, 0, 0 };
+        build_rhs(s, c, h, b);
+        for (int r = 0; r < 3; ++r) {
+            for (int k = 0; k < 3; ++k) if (Acontact9) Acontact9[9 * i + 3 * r + k] = A[r][k];
+            if (rhs_contact3) rhs_contact3[3 * i + r] = b[r];
+        }
+    }
+    for (int i = 0; i < s->n_joints; ++i) {
+        con_t* j = &s->joints[i];
+        float A[5][5]; memset(A, 0, sizeof A);
+        for (int d = 0; d < j->dim; ++d) A[d][d] = 1e-5f;
+        if (!s->bodies[j->body0].fixed) add_JMinvJT(j->dim, j->J0Minv, j->J0, A);
+        if (!s->bodies[j->body1].fixed) add_JMinvJT(j->dim, j->J1Minv, j->J1, A);
+        float b[5] = { 0, 0, 0, 0, 0 };
+        build_rhs(s, j, h, b);
+        for (int r = 0; r < 5; ++r) {
+            for (int k = 0; k < 5; ++k) if (Ajoint25) Ajoint25[25 * i + 5 * r + k] = A[r][k];
+            if (rhs_joint5) rhs_joint5[5 * i + r] = r < j->dim ? b[r] : 0.f;
+        }
+    }
+}
+
 /* calcConstraintForces head, RigidBodySystem.cpp:181-182 */
 void orc_stage_solve(orc_system* s, float dt)
 {

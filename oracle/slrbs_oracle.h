@@ -92,6 +92,8 @@ void orc_get_joints(const orc_system* s, int* type, int* body0, int* body1, floa
 void orc_get_joint_rows(const orc_system* s, float* J0_30, float* J1_30, float* J0Minv_30, float* J1Minv_30,
                         float* phi5, float* lambda5);
 void orc_set_joint_lambda(orc_system* s, const float* lambda5);
+/* solver diagonal blocks and RHS as built before the PGS loop (SolverBoxPGS.cpp:134-211); needs jacobians */
+void orc_get_solver_blocks(orc_system* s, float h, float* Acontact9, float* rhs_contact3, float* Ajoint25, float* rhs_joint5);
 
 /* RigidBodySystemState save/restore (src/rigidbody/RigidBodyState.cpp:18-72) */
 void orc_save_state(orc_system* s);

@@ -1,0 +1,286 @@
+"""ctypes binding of include/slrbs_b200.h (libslrbs_b200.so).
+
+Fails loudly when the CUDA library is missing or when no sm_100 device is usable; there is
+no CPU path in the product.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SPHERE, BOX, PLANE, CYLINDER = 0, 1, 2, 3
+SPHERICAL, HINGE = 1, 2
+
+# every symbol include/slrbs_b200.h declares
+SYMBOLS = [
+    "slrbs_last_error", "slrbs_version", "slrbs_create", "slrbs_destroy", "slrbs_set_params",
+    "slrbs_upload_bodies", "slrbs_upload_joints", "slrbs_upload_state", "slrbs_download_state",
+    "slrbs_set_external_forces", "slrbs_step", "slrbs_sync", "slrbs_stage_prepare", "slrbs_stage_detect",
+    "slrbs_stage_jacobians", "slrbs_stage_solve", "slrbs_stage_integrate", "slrbs_download_contact_counts",
+    "slrbs_download_contacts", "slrbs_download_contact_rows", "slrbs_download_joint_rows",
+    "slrbs_download_joint_lambda", "slrbs_upload_joint_lambda", "slrbs_download_body_dyn",
+    "slrbs_save_state", "slrbs_restore_state", "slrbs_profile_enable", "slrbs_profile_read",
+]
+
+
+class SlrbsError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libslrbs_b200.so")
+
+
+def load_library():
+    """dlopen the C ABI library; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise SlrbsError(f"{p} is missing: build it with `make -C slrbs_b200/csrc` "
+                         "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(p)
+    fp, ip, vp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_void_p
+    L.slrbs_last_error.restype = C.c_char_p
+    L.slrbs_version.restype = C.c_char_p
+    L.slrbs_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.slrbs_destroy.argtypes = [vp]
+    L.slrbs_destroy.restype = None
+    L.slrbs_set_params.argtypes = [vp, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.slrbs_upload_bodies.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, fp, fp, fp, fp, fp, fp, fp, ip, ip, fp]
+    L.slrbs_upload_joints.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, fp, fp, fp, fp]
+    L.slrbs_upload_state.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]
+    L.slrbs_download_state.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]
+    L.slrbs_set_external_forces.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp]
+    L.slrbs_step.argtypes = [vp, C.c_float, C.c_int]
+    L.slrbs_sync.argtypes = [vp]
+    L.slrbs_stage_prepare.argtypes = [vp]
+    L.slrbs_stage_detect.argtypes = [vp]
+    L.slrbs_stage_jacobians.argtypes = [vp, C.c_float]
+    L.slrbs_stage_solve.argtypes = [vp, C.c_float]
+    L.slrbs_stage_integrate.argtypes = [vp, C.c_float]
+    L.slrbs_download_contact_counts.argtypes = [vp, C.c_int, C.c_int, ip]
+    L.slrbs_download_contacts.argtypes = [vp, C.c_int, C.c_int, ip, ip, fp, fp, fp, fp, fp, fp]
+    L.slrbs_download_contact_rows.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp]
+    L.slrbs_download_joint_rows.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, fp, fp]
+    L.slrbs_download_joint_lambda.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
+    L.slrbs_upload_joint_lambda.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
+    L.slrbs_download_body_dyn.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp]
+    L.slrbs_save_state.argtypes = [vp]
+    L.slrbs_restore_state.argtypes = [vp, C.c_int, C.c_int]
+    L.slrbs_profile_enable.argtypes = [vp, C.c_int]
+    L.slrbs_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    _LIB = L
+    return L
+
+
+def _f(a):
+    return None if a is None else C.cast(a.ctypes.data, C.POINTER(C.c_float))
+
+
+def _i(a):
+    return None if a is None else C.cast(a.ctypes.data, C.POINTER(C.c_int32))
+
+
+def _arr(a, dtype, shape):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(np.asarray(a, dtype=dtype))
+    if a.shape != tuple(shape):
+        a = np.ascontiguousarray(np.broadcast_to(a.reshape((-1,) + tuple(shape[1:])) if a.ndim == len(shape) - 1 else a, shape))
+    return a
+
+
+class Context:
+    """A batch of n_scenes independent RigidBodySystems resident on one B200."""
+
+    def __init__(self, n_scenes, max_bodies, max_joints=0, max_contacts=0, device=0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        self.n_scenes, self.max_bodies, self.max_joints, self.max_contacts = n_scenes, max_bodies, max_joints, max_contacts
+        self.n_bodies = max_bodies
+        self.n_joints = 0
+        self._ck(self.L.slrbs_create(C.byref(self.h), device, n_scenes, max_bodies, max_joints, max_contacts))
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise SlrbsError(f"slrbs error {rc}: {self.L.slrbs_last_error().decode()}")
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.slrbs_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setup ---------------------------------------------------------------------
+    def set_params(self, mu=0.8, solver_id=0, solver_iters=10, collisions=True):
+        self._ck(self.L.slrbs_set_params(self.h, float(mu), int(solver_id), int(solver_iters), int(bool(collisions))))
+
+    def upload_bodies(self, x, q, v, w, mass, ibody, ibodyinv, fixed, geom_type, geom, scene0=0, counts=None):
+        """Arrays are [n_scenes, n_bodies, K] (or [n_bodies, K], replicated to every scene)."""
+        x = np.asarray(x, np.float32)
+        ns = self.n_scenes - scene0 if x.ndim == 2 else x.shape[0]
+        n = x.shape[-2]
+
+        def rep(a, dt, k):
+            a = np.asarray(a, dt)
+            tgt = (ns, n) + ((k,) if k else ())
+            if a.shape != tgt:
+                a = np.broadcast_to(a.reshape((1, n) + ((k,) if k else ())), tgt)
+            return np.ascontiguousarray(a)
+
+        a = [rep(x, np.float32, 3), rep(q, np.float32, 4), rep(v, np.float32, 3), rep(w, np.float32, 3),
+             rep(mass, np.float32, 0), rep(ibody, np.float32, 9), rep(ibodyinv, np.float32, 9)]
+        fx, gt, g = rep(fixed, np.int32, 0), rep(geom_type, np.int32, 0), rep(geom, np.float32, 6)
+        cnt = None if counts is None else np.ascontiguousarray(np.asarray(counts, np.int32))
+        self._ck(self.L.slrbs_upload_bodies(self.h, scene0, ns, n, _i(cnt), *[_f(t) for t in a], _i(fx), _i(gt), _f(g)))
+        self.n_bodies = n
+
+    def upload_joints(self, jtype, body0, body1, r0, q0, r1, q1, scene0=0, counts=None):
+        jtype = np.asarray(jtype, np.int32)
+        ns = self.n_scenes - scene0 if jtype.ndim == 1 else jtype.shape[0]
+        n = jtype.shape[-1]
+        if n == 0:
+            self._ck(self.L.slrbs_upload_joints(self.h, scene0, ns, 0, None, None, None, None, None, None, None, None))
+            self.n_joints = 0
+            return
+
+        def rep(a, dt, k):
+            a = np.asarray(a, dt)
+            tgt = (ns, n) + ((k,) if k else ())
+            if a.shape != tgt:
+                a = np.broadcast_to(a.reshape((1, n) + ((k,) if k else ())), tgt)
+            return np.ascontiguousarray(a)
+
+        ty, b0, b1 = rep(jtype, np.int32, 0), rep(body0, np.int32, 0), rep(body1, np.int32, 0)
+        a = [rep(r0, np.float32, 3), rep(q0, np.float32, 4), rep(r1, np.float32, 3), rep(q1, np.float32, 4)]
+        cnt = None if counts is None else np.ascontiguousarray(np.asarray(counts, np.int32))
+        self._ck(self.L.slrbs_upload_joints(self.h, scene0, ns, n, _i(cnt), _i(ty), _i(b0), _i(b1), *[_f(t) for t in a]))
+        self.n_joints = n
+
+    def upload_state(self, x=None, q=None, v=None, w=None, scene0=0, n_scenes=None, n_bodies=None):
+        ns = n_scenes or (self.n_scenes - scene0)
+        n = n_bodies or self.n_bodies
+        a = [None if t is None else np.ascontiguousarray(np.asarray(t, np.float32).reshape(ns, n, k))
+             for t, k in ((x, 3), (q, 4), (v, 3), (w, 3))]
+        self._ck(self.L.slrbs_upload_state(self.h, scene0, ns, n, *[_f(t) for t in a]))
+
+    def upload_state_raw(self, ns, n, px, pq, pv, pw, scene0=0):
+        """Raw host pointers (ints), e.g. pinned torch tensors' data_ptr()."""
+        cast = lambda p: None if not p else C.cast(p, C.POINTER(C.c_float))
+        self._ck(self.L.slrbs_upload_state(self.h, scene0, ns, n, cast(px), cast(pq), cast(pv), cast(pw)))
+
+    def download_state_raw(self, ns, n, px, pq, pv, pw, scene0=0):
+        cast = lambda p: None if not p else C.cast(p, C.POINTER(C.c_float))
+        self._ck(self.L.slrbs_download_state(self.h, scene0, ns, n, cast(px), cast(pq), cast(pv), cast(pw)))
+
+    def download_state(self, scene0=0, n_scenes=None, n_bodies=None):
+        ns = n_scenes or (self.n_scenes - scene0)
+        n = n_bodies or self.n_bodies
+        x = np.zeros((ns, n, 3), np.float32); q = np.zeros((ns, n, 4), np.float32)
+        v = np.zeros((ns, n, 3), np.float32); w = np.zeros((ns, n, 3), np.float32)
+        self._ck(self.L.slrbs_download_state(self.h, scene0, ns, n, _f(x), _f(q), _f(v), _f(w)))
+        return dict(x=x, q=q, v=v, w=w)
+
+    def set_external_forces(self, f=None, tau=None, scene0=0, n_scenes=None, n_bodies=None):
+        ns = n_scenes or (self.n_scenes - scene0)
+        n = n_bodies or self.n_bodies
+        a = [None if t is None else np.ascontiguousarray(np.broadcast_to(np.asarray(t, np.float32).reshape(-1, n, 3), (ns, n, 3)))
+             for t in (f, tau)]
+        self._ck(self.L.slrbs_set_external_forces(self.h, scene0, ns, n, _f(a[0]), _f(a[1])))
+
+    # -- stepping ------------------------------------------------------------------
+    def step(self, dt=0.01, n=1):
+        self._ck(self.L.slrbs_step(self.h, float(dt), int(n)))
+
+    def sync(self):
+        self._ck(self.L.slrbs_sync(self.h))
+
+    def stage_prepare(self): self._ck(self.L.slrbs_stage_prepare(self.h))
+    def stage_detect(self): self._ck(self.L.slrbs_stage_detect(self.h))
+    def stage_jacobians(self, dt): self._ck(self.L.slrbs_stage_jacobians(self.h, float(dt)))
+    def stage_solve(self, dt): self._ck(self.L.slrbs_stage_solve(self.h, float(dt)))
+    def stage_integrate(self, dt): self._ck(self.L.slrbs_stage_integrate(self.h, float(dt)))
+    def save_state(self): self._ck(self.L.slrbs_save_state(self.h))
+
+    def restore_state(self, scene0=0, n_scenes=None):
+        self._ck(self.L.slrbs_restore_state(self.h, scene0, n_scenes or (self.n_scenes - scene0)))
+
+    # -- read back -----------------------------------------------------------------
+    def contact_counts(self, scene0=0, n_scenes=None):
+        ns = n_scenes or (self.n_scenes - scene0)
+        c = np.zeros(ns, np.int32)
+        self._ck(self.L.slrbs_download_contact_counts(self.h, scene0, ns, _i(c)))
+        return c
+
+    def contacts(self, scene=0):
+        m = max(int(self.contact_counts(scene, 1)[0]), 1)
+        b0 = np.zeros(m, np.int32); b1 = np.zeros(m, np.int32)
+        o = {k: np.zeros((m, 3), np.float32) for k in ("p", "n", "t", "b", "lam")}
+        phi = np.zeros(m, np.float32)
+        cnt = self._ck(self.L.slrbs_download_contacts(self.h, scene, m, _i(b0), _i(b1), _f(o["p"]), _f(o["n"]),
+                                                      _f(o["t"]), _f(o["b"]), _f(phi), _f(o["lam"])))
+        out = dict(body0=b0[:cnt], body1=b1[:cnt], phi=phi[:cnt])
+        out.update({k: a[:cnt] for k, a in o.items()})
+        return out
+
+    def contact_rows(self, scene=0):
+        m = max(int(self.contact_counts(scene, 1)[0]), 1)
+        o = {k: np.zeros((m, 3, 6), np.float32) for k in ("J0", "J1", "J0Minv", "J1Minv")}
+        A = np.zeros((m, 3, 3), np.float32); rhs = np.zeros((m, 3), np.float32)
+        cnt = self._ck(self.L.slrbs_download_contact_rows(self.h, scene, m, _f(o["J0"]), _f(o["J1"]), _f(o["J0Minv"]),
+                                                          _f(o["J1Minv"]), _f(A), _f(rhs)))
+        out = {k: a[:cnt] for k, a in o.items()}
+        out["A"] = A[:cnt]; out["rhs"] = rhs[:cnt]
+        return out
+
+    def joint_rows(self, scene=0):
+        m = max(self.n_joints, 1)
+        o = {k: np.zeros((m, 5, 6), np.float32) for k in ("J0", "J1", "J0Minv", "J1Minv")}
+        rhs = np.zeros((m, 5), np.float32)
+        cnt = self._ck(self.L.slrbs_download_joint_rows(self.h, scene, m, _f(o["J0"]), _f(o["J1"]), _f(o["J0Minv"]),
+                                                        _f(o["J1Minv"]), _f(rhs)))
+        out = {k: a[:cnt] for k, a in o.items()}
+        out["rhs"] = rhs[:cnt]
+        return out
+
+    def joint_lambda(self, scene0=0, n_scenes=None):
+        ns = n_scenes or (self.n_scenes - scene0)
+        lam = np.zeros((ns, self.n_joints, 5), np.float32)
+        if self.n_joints:
+            self._ck(self.L.slrbs_download_joint_lambda(self.h, scene0, ns, self.n_joints, _f(lam)))
+        return lam
+
+    def set_joint_lambda(self, lam, scene0=0):
+        lam = np.ascontiguousarray(np.asarray(lam, np.float32).reshape(-1, self.n_joints, 5))
+        self._ck(self.L.slrbs_upload_joint_lambda(self.h, scene0, lam.shape[0], self.n_joints, _f(lam)))
+
+    def body_dyn(self, scene=0):
+        n = self.n_bodies
+        o = {k: np.zeros((n, 3), np.float32) for k in ("f", "tau", "fc", "tauc")}
+        o["I"] = np.zeros((n, 9), np.float32); o["Iinv"] = np.zeros((n, 9), np.float32)
+        self._ck(self.L.slrbs_download_body_dyn(self.h, scene, n, _f(o["f"]), _f(o["tau"]), _f(o["fc"]), _f(o["tauc"]),
+                                                _f(o["I"]), _f(o["Iinv"])))
+        return o
+
+    # -- measurement ---------------------------------------------------------------
+    def profile_enable(self, on=True):
+        self._ck(self.L.slrbs_profile_enable(self.h, int(bool(on))))
+
+    def profile_read(self, reset=True):
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        ms = C.c_double()
+        self._ck(self.L.slrbs_profile_read(self.h, int(bool(reset)), C.byref(a), C.byref(ms), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(solve_launches=a.value, solve_ms=ms.value, contact_visits=b.value, joint_visits=c.value,
+                    total_launches=d.value)

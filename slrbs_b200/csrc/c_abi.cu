@@ -1,0 +1,539 @@
+// c_abi.cu -- the C ABI of include/slrbs_b200.h: context, HBM allocation, staging of
+// caller-owned host buffers, stage launches, CUDA-event profiling.  No CPU fallback: every
+// entry point fails with SLRBS_E_CUDA if the device is not usable.
+#include "../../include/slrbs_b200.h"
+#include "kernels.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace slrbs;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(SLRBS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+}  // namespace
+
+struct slrbs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    View v{};
+    float mu = 0.8f;
+    int solver_id = 0, solver_iters = 10, collisions = 1;
+    std::vector<void*> allocs;
+    char* stage = nullptr; size_t stage_cap = 0, stage_off = 0;
+    int* h_flag = nullptr;                      // pinned copy of the overflow flag
+    // profiling
+    int profiling = 0;
+    std::vector<cudaEvent_t> ev; size_t ev_used = 0;
+    double solve_ms = 0.0; int64_t solve_launches = 0, total_launches = 0;
+};
+
+namespace {
+
+template <typename T>
+int dalloc(slrbs_ctx* c, T** p, size_t n)
+{
+    void* q = nullptr;
+    const size_t bytes = (n ? n : 1) * sizeof(T);
+    CU(cudaMalloc(&q, bytes));
+    CU(cudaMemsetAsync(q, 0, bytes, c->stream));
+    c->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+// bump allocator over one device staging buffer; reset at the start of every staging call
+int stage_reserve(slrbs_ctx* c, size_t bytes)
+{
+    c->stage_off = 0;
+    if (bytes <= c->stage_cap) return 0;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->stage) CU(cudaFree(c->stage));
+    c->stage = nullptr; c->stage_cap = 0;
+    const size_t cap = bytes + bytes / 4 + 4096;
+    CU(cudaMalloc((void**)&c->stage, cap));
+    c->stage_cap = cap;
+    return 0;
+}
+template <typename T>
+T* stage_take(slrbs_ctx* c, size_t n)
+{
+    const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    T* p = (T*)(c->stage + c->stage_off);
+    c->stage_off += bytes;
+    return p;
+}
+inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+template <typename T>
+int stage_in(slrbs_ctx* c, const T* host, size_t n, const T** dev)
+{
+    if (!host) { *dev = nullptr; return 0; }
+    T* d = stage_take<T>(c, n);
+    CU(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *dev = d;
+    return 0;
+}
+
+int check_launch(slrbs_ctx* c, int n = 1)
+{
+    c->total_launches += n;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int range_ok(const slrbs_ctx* c, int scene0, int ns)
+{
+    return c && scene0 >= 0 && ns > 0 && scene0 + ns <= c->v.B;
+}
+
+int fold_events(slrbs_ctx* c)
+{
+    if (c->ev_used == 0) return 0;
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+        c->solve_ms += ms;
+    }
+    c->ev_used = 0;
+    return 0;
+}
+
+int solve_launch(slrbs_ctx* c, float dt)
+{
+    if (c->solver_id != 0)
+        return fail(SLRBS_E_UNSUPPORTED, "solver_id 1/2 (CG/CR) not implemented on the device yet");
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profiling) {
+        if (c->ev_used + 2 > 8192) { int r = fold_events(c); if (r) return r; }
+        while (c->ev.size() < c->ev_used + 2) { cudaEvent_t e; CU(cudaEventCreate(&e)); c->ev.push_back(e); }
+        e0 = c->ev[c->ev_used]; e1 = c->ev[c->ev_used + 1]; c->ev_used += 2;
+        CU(cudaEventRecord(e0, c->stream));
+    }
+    launch_pgs(c->v, dt, c->solver_iters, c->mu, c->stream);
+    if (c->profiling) { CU(cudaEventRecord(e1, c->stream)); c->solve_launches++; }
+    return check_launch(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* slrbs_last_error(void) { return g_err.c_str(); }
+const char* slrbs_version(void) { return "slrbs_b200 0.1 (sm_100a)"; }
+
+int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int max_joints, int max_contacts)
+{
+    if (!out || n_scenes <= 0 || max_bodies <= 0 || max_joints < 0 || max_contacts < 0)
+        return fail(SLRBS_E_ARG, "slrbs_create: bad sizes");
+    *out = nullptr;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SLRBS_E_CUDA, "slrbs_create: no such CUDA device (no CPU fallback)");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(SLRBS_E_CUDA, std::string("slrbs_create: device is ") + prop.name + ", kernels are built for sm_100a only");
+    CU(cudaSetDevice(device));
+    slrbs_ctx* c = new slrbs_ctx();
+    c->device = device;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    View& v = c->v;
+    v.B = n_scenes; v.NB = max_bodies; v.NJ = max_joints; v.NC = max_contacts;
+    const size_t nb = (size_t)v.NB * v.B, nj = (size_t)v.NJ * v.B, nc = (size_t)v.NC * v.B;
+    int r = 0;
+#define A(p, n) if ((r = dalloc(c, &p, n))) { slrbs_destroy(c); return r; }
+    A(v.nbodies, v.B) A(v.njoints, v.B) A(v.ncontacts, v.B) A(v.overflow, 1) A(v.visit_counters, 2)
+    A(v.pos, nb) A(v.quat, nb) A(v.vel, nb) A(v.omg, nb) A(v.flags, nb) A(v.geomA, nb) A(v.geomB, nb)
+    A(v.ibody, 9 * nb) A(v.ibodyinv, 9 * nb) A(v.cproxy, nb) A(v.force, nb) A(v.torque, nb)
+    A(v.extf, nb) A(v.extt, nb) A(v.Iw, 9 * nb) A(v.Iinvw, 9 * nb) A(v.wl, nb) A(v.wa, nb)
+    A(v.s_pos, nb) A(v.s_quat, nb) A(v.s_vel, nb) A(v.s_omg, nb)
+    A(v.jdef, nj) A(v.jr0, nj) A(v.jq0, nj) A(v.jr1, nj) A(v.jq1, nj) A(v.jlam, nj) A(v.jlam4, nj)
+    A(v.jrow, (size_t)JROW_FIELDS * nj)
+    A(v.cids, nc) A(v.cp, nc) A(v.cn, nc) A(v.crow, (size_t)CROW_FIELDS * nc)
+#undef A
+    CU(cudaMallocHost((void**)&c->h_flag, sizeof(int)));
+    *c->h_flag = 0;
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+void slrbs_destroy(slrbs_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->stage) cudaFree(c->stage);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int slrbs_set_params(slrbs_ctx* c, float mu, int solver_id, int solver_iters, int collisions_enabled)
+{
+    if (!c || solver_id < 0 || solver_id > 2 || solver_iters < 0) return fail(SLRBS_E_ARG, "slrbs_set_params: bad argument");
+    c->mu = mu; c->solver_id = solver_id; c->solver_iters = solver_iters; c->collisions = collisions_enabled ? 1 : 0;
+    return 0;
+}
+
+int slrbs_upload_bodies(slrbs_ctx* c, int scene0, int ns, int n, const int32_t* counts,
+                        const float* x3, const float* q4, const float* v3, const float* w3,
+                        const float* mass, const float* ibody9, const float* ibodyinv9,
+                        const int32_t* fixed, const int32_t* geom_type, const float* geom6)
+{
+    if (!range_ok(c, scene0, ns) || n <= 0 || n > c->v.NB) return fail(SLRBS_E_ARG, "slrbs_upload_bodies: bad range");
+    if (!x3 || !q4 || !v3 || !w3 || !mass || !ibody9 || !ibodyinv9 || !fixed || !geom_type || !geom6)
+        return fail(SLRBS_E_ARG, "slrbs_upload_bodies: all body arrays are required");
+    CU(cudaSetDevice(c->device));
+    const size_t m = (size_t)ns * n;
+    int r = stage_reserve(c, pad256(m * 4) * (3 + 4 + 3 + 3 + 1 + 9 + 9 + 1 + 1 + 6) + pad256((size_t)ns * 4) + 4096);
+    if (r) return r;
+    BodyStage st{};
+    const int* dcounts = nullptr;
+    if ((r = stage_in(c, x3, 3 * m, &st.x)) || (r = stage_in(c, q4, 4 * m, &st.q)) || (r = stage_in(c, v3, 3 * m, &st.v)) ||
+        (r = stage_in(c, w3, 3 * m, &st.w)) || (r = stage_in(c, mass, m, &st.mass)) || (r = stage_in(c, ibody9, 9 * m, &st.ibody)) ||
+        (r = stage_in(c, ibodyinv9, 9 * m, &st.ibodyinv)) || (r = stage_in(c, fixed, m, &st.fixed)) ||
+        (r = stage_in(c, geom_type, m, &st.geom_type)) || (r = stage_in(c, geom6, 6 * m, &st.geom)) ||
+        (r = stage_in(c, counts, (size_t)ns, &dcounts)))
+        return r;
+    launch_upload_bodies(c->v, scene0, ns, n, dcounts, st, c->stream);
+    if ((r = check_launch(c))) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slrbs_upload_joints(slrbs_ctx* c, int scene0, int ns, int n, const int32_t* counts,
+                        const int32_t* type, const int32_t* body0, const int32_t* body1,
+                        const float* r0, const float* q0, const float* r1, const float* q1)
+{
+    if (!range_ok(c, scene0, ns) || n < 0 || n > c->v.NJ) return fail(SLRBS_E_ARG, "slrbs_upload_joints: bad range");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) {
+        CU(cudaMemsetAsync(c->v.njoints + scene0, 0, sizeof(int) * ns, c->stream));
+        return 0;
+    }
+    if (!type || !body0 || !body1 || !r0 || !r1) return fail(SLRBS_E_ARG, "slrbs_upload_joints: type/body/r arrays are required");
+    const size_t m = (size_t)ns * n;
+    for (size_t i = 0; i < m; ++i) {
+        if (type[i] != 1 && type[i] != 2) return fail(SLRBS_E_ARG, "slrbs_upload_joints: type must be 1 (spherical) or 2 (hinge)");
+        if (body0[i] < 0 || body0[i] >= c->v.NB || body1[i] < 0 || body1[i] >= c->v.NB)
+            return fail(SLRBS_E_ARG, "slrbs_upload_joints: body index out of range");
+    }
+    int r = stage_reserve(c, pad256(m * 4) * (3 + 3 + 4 + 3 + 4) + pad256((size_t)ns * 4) + 4096);
+    if (r) return r;
+    JointStage st{};
+    const int* dcounts = nullptr;
+    if ((r = stage_in(c, type, m, &st.type)) || (r = stage_in(c, body0, m, &st.body0)) || (r = stage_in(c, body1, m, &st.body1)) ||
+        (r = stage_in(c, r0, 3 * m, &st.r0)) || (r = stage_in(c, q0, 4 * m, &st.q0)) || (r = stage_in(c, r1, 3 * m, &st.r1)) ||
+        (r = stage_in(c, q1, 4 * m, &st.q1)) || (r = stage_in(c, counts, (size_t)ns, &dcounts)))
+        return r;
+    launch_upload_joints(c->v, scene0, ns, n, dcounts, st, c->stream);
+    if ((r = check_launch(c))) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slrbs_upload_state(slrbs_ctx* c, int scene0, int ns, int n, const float* x3, const float* q4, const float* v3, const float* w3)
+{
+    if (!range_ok(c, scene0, ns) || n <= 0 || n > c->v.NB) return fail(SLRBS_E_ARG, "slrbs_upload_state: bad range");
+    CU(cudaSetDevice(c->device));
+    const size_t m = (size_t)ns * n;
+    int r = stage_reserve(c, pad256(m * 4) * 13 + 4096);
+    if (r) return r;
+    BodyStage st{};
+    if ((r = stage_in(c, x3, 3 * m, &st.x)) || (r = stage_in(c, q4, 4 * m, &st.q)) || (r = stage_in(c, v3, 3 * m, &st.v)) ||
+        (r = stage_in(c, w3, 3 * m, &st.w)))
+        return r;
+    // counts unchanged: pass the live counts back to themselves
+    launch_upload_bodies(c->v, scene0, ns, n, c->v.nbodies + scene0, st, c->stream);
+    if ((r = check_launch(c))) return r;
+    CU(cudaStreamSynchronize(c->stream));      // the caller may reuse its (possibly pinned) buffers on return
+    return 0;
+}
+
+int slrbs_download_state(slrbs_ctx* c, int scene0, int ns, int n, float* x3, float* q4, float* v3, float* w3)
+{
+    if (!range_ok(c, scene0, ns) || n <= 0 || n > c->v.NB) return fail(SLRBS_E_ARG, "slrbs_download_state: bad range");
+    CU(cudaSetDevice(c->device));
+    const size_t m = (size_t)ns * n;
+    int r = stage_reserve(c, pad256(m * 4) * 13 + 4096);
+    if (r) return r;
+    BodyStage st{};
+    float *dx = x3 ? stage_take<float>(c, 3 * m) : nullptr, *dq = q4 ? stage_take<float>(c, 4 * m) : nullptr;
+    float *dv = v3 ? stage_take<float>(c, 3 * m) : nullptr, *dw = w3 ? stage_take<float>(c, 3 * m) : nullptr;
+    st.x = dx; st.q = dq; st.v = dv; st.w = dw;
+    launch_download_state(c->v, scene0, ns, n, st, c->stream);
+    if ((r = check_launch(c))) return r;
+    if (x3) CU(cudaMemcpyAsync(x3, dx, 3 * m * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (q4) CU(cudaMemcpyAsync(q4, dq, 4 * m * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (v3) CU(cudaMemcpyAsync(v3, dv, 3 * m * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (w3) CU(cudaMemcpyAsync(w3, dw, 3 * m * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slrbs_set_external_forces(slrbs_ctx* c, int scene0, int ns, int n, const float* f3, const float* tau3)
+{
+    if (!range_ok(c, scene0, ns) || n <= 0 || n > c->v.NB) return fail(SLRBS_E_ARG, "slrbs_set_external_forces: bad range");
+    CU(cudaSetDevice(c->device));
+    const size_t m = (size_t)ns * n;
+    int r = stage_reserve(c, pad256(m * 4) * 6 + 4096);
+    if (r) return r;
+    const float *df = nullptr, *dt = nullptr;
+    if ((r = stage_in(c, f3, 3 * m, &df)) || (r = stage_in(c, tau3, 3 * m, &dt))) return r;
+    launch_set_ext(c->v, scene0, ns, n, df, dt, c->stream);
+    if ((r = check_launch(c))) return r;
+    if (f3 || tau3) c->v.has_ext = 1;
+    else if (scene0 == 0 && ns == c->v.B) c->v.has_ext = 0;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slrbs_stage_prepare(slrbs_ctx* c)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    launch_prepare(c->v, c->stream);
+    return check_launch(c);
+}
+int slrbs_stage_detect(slrbs_ctx* c)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    if (!c->collisions || c->v.NC == 0) return 0;               // RigidBodySystem.cpp:77
+    launch_detect(c->v, c->stream);
+    return check_launch(c);
+}
+int slrbs_stage_jacobians(slrbs_ctx* c, float dt)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    int n = 0;
+    if (c->collisions && c->v.NC > 0) { launch_contact_rows(c->v, dt, c->stream); ++n; }
+    if (c->v.NJ > 0) { launch_joint_rows(c->v, dt, c->stream); ++n; }
+    return check_launch(c, n);
+}
+int slrbs_stage_solve(slrbs_ctx* c, float dt)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    return solve_launch(c, dt);
+}
+int slrbs_stage_integrate(slrbs_ctx* c, float dt)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    launch_integrate(c->v, dt, c->stream);
+    return check_launch(c);
+}
+
+int slrbs_step(slrbs_ctx* c, float dt, int n_steps)
+{
+    if (!c || n_steps < 0) return fail(SLRBS_E_ARG, "slrbs_step: bad argument");
+    CU(cudaSetDevice(c->device));
+    int r;
+    for (int i = 0; i < n_steps; ++i) {
+        if ((r = slrbs_stage_prepare(c)) || (r = slrbs_stage_detect(c)) || (r = slrbs_stage_jacobians(c, dt)) ||
+            (r = slrbs_stage_solve(c, dt)) || (r = slrbs_stage_integrate(c, dt)))
+            return r;
+    }
+    return 0;
+}
+
+int slrbs_sync(slrbs_ctx* c)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->h_flag, c->v.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (*c->h_flag) return fail(SLRBS_E_CAPACITY, "a scene produced more contacts than max_contacts; extra contacts were dropped");
+    return 0;
+}
+
+int slrbs_download_contact_counts(slrbs_ctx* c, int scene0, int ns, int32_t* counts)
+{
+    if (!range_ok(c, scene0, ns) || !counts) return fail(SLRBS_E_ARG, "slrbs_download_contact_counts: bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(counts, c->v.ncontacts + scene0, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int scene_count(slrbs_ctx* c, const int* dev_counts, int scene, int* out)
+{
+    CU(cudaMemcpyAsync(out, dev_counts + scene, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slrbs_download_contacts(slrbs_ctx* c, int scene, int max_out, int32_t* body0, int32_t* body1,
+                            float* p3, float* n3, float* t3, float* b3, float* phi, float* lambda3)
+{
+    if (!range_ok(c, scene, 1) || max_out < 0) return fail(SLRBS_E_ARG, "slrbs_download_contacts: bad argument");
+    CU(cudaSetDevice(c->device));
+    int total = 0, r;
+    if ((r = scene_count(c, c->v.ncontacts, scene, &total))) return r;
+    const int n = total < max_out ? total : max_out;
+    if (n == 0) return total;
+    if ((r = stage_reserve(c, pad256((size_t)n * 4) * (2 + 3 * 4 + 1 + 3) + 4096))) return r;
+    int *d0 = stage_take<int>(c, n), *d1 = stage_take<int>(c, n);
+    float *dp = stage_take<float>(c, 3 * n), *dn = stage_take<float>(c, 3 * n), *dt = stage_take<float>(c, 3 * n);
+    float *db = stage_take<float>(c, 3 * n), *dphi = stage_take<float>(c, n), *dl = stage_take<float>(c, 3 * n);
+    launch_export_contacts(c->v, scene, n, d0, d1, dp, dn, dt, db, dphi, dl, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c->stream);
+    if ((r = check_launch(c))) return r;
+#define D2H(h, d, cnt) if (h) CU(cudaMemcpyAsync(h, d, (size_t)(cnt) * 4, cudaMemcpyDeviceToHost, c->stream));
+    D2H(body0, d0, n) D2H(body1, d1, n) D2H(p3, dp, 3 * n) D2H(n3, dn, 3 * n) D2H(t3, dt, 3 * n) D2H(b3, db, 3 * n)
+    D2H(phi, dphi, n) D2H(lambda3, dl, 3 * n)
+    CU(cudaStreamSynchronize(c->stream));
+    return total;
+}
+
+int slrbs_download_contact_rows(slrbs_ctx* c, int scene, int max_out, float* J0, float* J1, float* M0, float* M1, float* A9, float* rhs3)
+{
+    if (!range_ok(c, scene, 1) || max_out < 0) return fail(SLRBS_E_ARG, "slrbs_download_contact_rows: bad argument");
+    CU(cudaSetDevice(c->device));
+    int total = 0, r;
+    if ((r = scene_count(c, c->v.ncontacts, scene, &total))) return r;
+    const int n = total < max_out ? total : max_out;
+    if (n == 0) return total;
+    if ((r = stage_reserve(c, pad256((size_t)n * 4) * (18 * 4 + 9 + 3) + 4096))) return r;
+    float *d0 = stage_take<float>(c, 18 * n), *d1 = stage_take<float>(c, 18 * n), *m0 = stage_take<float>(c, 18 * n);
+    float *m1 = stage_take<float>(c, 18 * n), *dA = stage_take<float>(c, 9 * n), *db = stage_take<float>(c, 3 * n);
+    launch_export_contacts(c->v, scene, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d0, d1, m0, m1, dA, db, c->stream);
+    if ((r = check_launch(c))) return r;
+    D2H(J0, d0, 18 * n) D2H(J1, d1, 18 * n) D2H(M0, m0, 18 * n) D2H(M1, m1, 18 * n) D2H(A9, dA, 9 * n) D2H(rhs3, db, 3 * n)
+    CU(cudaStreamSynchronize(c->stream));
+    return total;
+}
+
+int slrbs_download_joint_rows(slrbs_ctx* c, int scene, int max_out, float* J0, float* J1, float* M0, float* M1, float* rhs5)
+{
+    if (!range_ok(c, scene, 1) || max_out < 0) return fail(SLRBS_E_ARG, "slrbs_download_joint_rows: bad argument");
+    CU(cudaSetDevice(c->device));
+    int total = 0, r;
+    if ((r = scene_count(c, c->v.njoints, scene, &total))) return r;
+    const int n = total < max_out ? total : max_out;
+    if (n == 0) return total;
+    if ((r = stage_reserve(c, pad256((size_t)n * 4) * (30 * 4 + 5) + 4096))) return r;
+    float *d0 = stage_take<float>(c, 30 * n), *d1 = stage_take<float>(c, 30 * n), *m0 = stage_take<float>(c, 30 * n);
+    float *m1 = stage_take<float>(c, 30 * n), *db = stage_take<float>(c, 5 * n);
+    launch_export_joints(c->v, scene, n, d0, d1, m0, m1, db, c->stream);
+    if ((r = check_launch(c))) return r;
+    D2H(J0, d0, 30 * n) D2H(J1, d1, 30 * n) D2H(M0, m0, 30 * n) D2H(M1, m1, 30 * n) D2H(rhs5, db, 5 * n)
+    CU(cudaStreamSynchronize(c->stream));
+    return total;
+}
+
+int slrbs_download_joint_lambda(slrbs_ctx* c, int scene0, int ns, int n, float* lambda5)
+{
+    if (!range_ok(c, scene0, ns) || n <= 0 || n > c->v.NJ || !lambda5) return fail(SLRBS_E_ARG, "slrbs_download_joint_lambda: bad argument");
+    CU(cudaSetDevice(c->device));
+    const size_t m = (size_t)ns * n;
+    int r = stage_reserve(c, pad256(m * 20) + 4096);
+    if (r) return r;
+    float* d = stage_take<float>(c, 5 * m);
+    launch_joint_lambda(c->v, scene0, ns, n, d, 0, c->stream);
+    if ((r = check_launch(c))) return r;
+    CU(cudaMemcpyAsync(lambda5, d, 5 * m * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slrbs_upload_joint_lambda(slrbs_ctx* c, int scene0, int ns, int n, const float* lambda5)
+{
+    if (!range_ok(c, scene0, ns) || n <= 0 || n > c->v.NJ || !lambda5) return fail(SLRBS_E_ARG, "slrbs_upload_joint_lambda: bad argument");
+    CU(cudaSetDevice(c->device));
+    const size_t m = (size_t)ns * n;
+    int r = stage_reserve(c, pad256(m * 20) + 4096);
+    if (r) return r;
+    const float* d = nullptr;
+    if ((r = stage_in(c, lambda5, 5 * m, &d))) return r;
+    launch_joint_lambda(c->v, scene0, ns, n, (float*)d, 1, c->stream);
+    if ((r = check_launch(c))) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slrbs_download_body_dyn(slrbs_ctx* c, int scene, int n, float* f3, float* tau3, float* fc3, float* tauc3, float* I9, float* Iinv9)
+{
+    if (!range_ok(c, scene, 1) || n <= 0 || n > c->v.NB) return fail(SLRBS_E_ARG, "slrbs_download_body_dyn: bad argument");
+    CU(cudaSetDevice(c->device));
+    int r = stage_reserve(c, pad256((size_t)n * 4) * (12 + 18) + 4096);
+    if (r) return r;
+    float *df = stage_take<float>(c, 3 * n), *dt = stage_take<float>(c, 3 * n), *dfc = stage_take<float>(c, 3 * n);
+    float *dtc = stage_take<float>(c, 3 * n), *dI = stage_take<float>(c, 9 * n), *dIi = stage_take<float>(c, 9 * n);
+    launch_export_body_dyn(c->v, scene, n, df, dt, dfc, dtc, dI, dIi, c->stream);
+    if ((r = check_launch(c))) return r;
+    D2H(f3, df, 3 * n) D2H(tau3, dt, 3 * n) D2H(fc3, dfc, 3 * n) D2H(tauc3, dtc, 3 * n) D2H(I9, dI, 9 * n) D2H(Iinv9, dIi, 9 * n)
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+#undef D2H
+
+int slrbs_save_state(slrbs_ctx* c)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    launch_snapshot(c->v, 0, c->v.B, 0, c->stream);
+    return check_launch(c);
+}
+
+int slrbs_restore_state(slrbs_ctx* c, int scene0, int ns)
+{
+    if (!range_ok(c, scene0, ns)) return fail(SLRBS_E_ARG, "slrbs_restore_state: bad range");
+    CU(cudaSetDevice(c->device));
+    launch_snapshot(c->v, scene0, ns, 1, c->stream);
+    return check_launch(c);
+}
+
+int slrbs_profile_enable(slrbs_ctx* c, int on)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    if (!on) { int r = fold_events(c); if (r) return r; }
+    c->profiling = on ? 1 : 0;
+    c->v.profiling = c->profiling;
+    return 0;
+}
+
+int slrbs_profile_read(slrbs_ctx* c, int reset, int64_t* solve_launches, double* solve_ms,
+                       int64_t* contact_visits, int64_t* joint_visits, int64_t* total_launches)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    int r = fold_events(c);
+    if (r) return r;
+    unsigned long long h[2] = { 0, 0 };
+    CU(cudaMemcpyAsync(h, c->v.visit_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (solve_launches) *solve_launches = c->solve_launches;
+    if (solve_ms) *solve_ms = c->solve_ms;
+    if (contact_visits) *contact_visits = (int64_t)h[0];
+    if (joint_visits) *joint_visits = (int64_t)h[1];
+    if (total_launches) *total_launches = c->total_launches;
+    if (reset) {
+        c->solve_launches = 0; c->solve_ms = 0.0; c->total_launches = 0;
+        CU(cudaMemsetAsync(c->v.visit_counters, 0, sizeof h, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+}  // extern "C"

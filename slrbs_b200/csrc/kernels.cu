@@ -1,0 +1,975 @@
+// kernels.cu -- hand-written sm_100a kernels of the per-step rigid-body pipeline.
+//
+// Compiled with -fmad=false: the narrow phase, the Jacobian/RHS assembly, the force scatter
+// and the integrator reproduce the reference's fp32 arithmetic operation by operation (see
+// vecmath.cuh); only the PGS sweep uses (explicit) fused multiply-adds.
+//
+// Kernel            replaces (reference file:line)                                   mapping
+// k_prepare         RigidBodySystem.cpp:58-65, RigidBody.cpp:78-89                    thread / (body, scene)
+// k_detect          CollisionDetect.cpp:27-76,102-274, Contact.cpp:11-26              thread / scene (ordered emit)
+// k_contact_rows    Contact.cpp:33-94, SolverBoxPGS.cpp:27-44,165-189,206-211         thread / (contact, scene)
+// k_joint_rows      Hinge.cpp:33-63, Spherical.cpp:34-52, SolverBoxPGS.cpp:134-163    thread / (joint, scene)
+// k_pgs             SolverBoxPGS.cpp:217-248, RigidBodySystem.cpp:185-220             thread / scene (sequential rows)
+// k_integrate       RigidBodySystem.cpp:99-120                                        thread / (body, scene)
+#include "kernels.cuh"
+#include "vecmath.cuh"
+
+namespace slrbs {
+
+// ------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ M3 load_m3(const float* base, const View& v, int slot, int scene)
+{
+    M3 A;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) A.m[k / 3][k % 3] = base[at_b9(v, k, slot, scene)];
+    return A;
+}
+__device__ __forceinline__ void store_m3(float* base, const View& v, int slot, int scene, const M3& A)
+{
+#pragma unroll
+    for (int k = 0; k < 9; ++k) base[at_b9(v, k, slot, scene)] = A.m[k / 3][k % 3];
+}
+
+// ------------------------------------------------------------------------------------
+// K1  force reset + world inertia
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prepare(View v)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)v.NB * v.B) return;
+    const int scene = (int)(tid % v.B), slot = (int)(tid / v.B);
+    if (slot == 0) v.ncontacts[scene] = 0;                       // CollisionDetect::clear, RigidBodySystem.cpp:75
+    if (slot >= v.nbodies[scene]) return;
+    const size_t i = at(v, slot, scene);
+    const float4 px = v.pos[i];
+    const float mass = px.w;
+    // b->f = b->mass * Vector3f(0, -9.81, 0); tau = 0  (RigidBodySystem.cpp:60-61)
+    V3 f = mass * mk3(0.f, -9.81f, 0.f);
+    V3 tau = mk3(0.f, 0.f, 0.f);
+    if (v.has_ext) {                                             // pre-step callback contribution (:70-73)
+        f = f + mk3(v.extf[i]);
+        tau = tau + mk3(v.extt[i]);
+    }
+    v.force[i] = mk4(f, 0.f);
+    v.torque[i] = mk4(tau, 0.f);
+    const int fl = v.flags[i];
+    const float4 ga = v.geomA[i];
+    v.cproxy[i] = make_float4(px.x, px.y, px.z, ((fl & FLAG_TYPE_MASK) == GEOM_SPHERE) ? ga.x : 0.f);
+    // RigidBody::updateInertiaMatrix (RigidBody.cpp:78-89)
+    if (!(fl & FLAG_FIXED)) {
+        const Q4 q = mkq(v.quat[i]);
+        const M3 R = rotation_matrix(q);
+        const M3 Rinv = rotation_matrix(qinverse(q));
+        const M3 Ib = load_m3(v.ibody, v, slot, scene);
+        const M3 Ibi = load_m3(v.ibodyinv, v, slot, scene);
+        store_m3(v.Iw, v, slot, scene, matmul(matmul(R, Ib), Rinv));
+        store_m3(v.Iinvw, v, slot, scene, matmul(matmul(R, Ibi), Rinv));
+    } else {
+        M3 Z;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Z.m[k / 3][k % 3] = 0.f;
+        store_m3(v.Iinvw, v, slot, scene, Z);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K3  narrow phase, one thread per scene walking the reference's i<j pair order
+// ------------------------------------------------------------------------------------
+struct Emit {
+    const View& v; int scene; int count;
+    __device__ __forceinline__ void put(int b0, int b1, const V3& p, const V3& n, float pene)
+    {
+        if (count < v.NC) {
+            const size_t c = at(v, count, scene);
+            v.cids[c] = make_int2(b0, b1);
+            v.cp[c] = mk4(p, pene);
+            v.cn[c] = mk4(n, 0.f);
+        } else {
+            *v.overflow = 1;
+        }
+        ++count;
+    }
+};
+
+__device__ __forceinline__ float plane_dist(const V3& p, const V3& plane_p, const V3& plane_n)
+{
+    return dot(p - plane_p, plane_n);                            // CollisionDetect.cpp:12-17
+}
+
+// CollisionDetect.cpp:125-150 (body0 = sphere, body1 = box)
+__device__ __noinline__ void sphere_box(Emit& e, int is, int ib, const V3& xs, float r)
+{
+    const View& v = e.v;
+    const size_t bi = at(v, ib, e.scene);
+    const V3 xb = mk3(v.pos[bi]);
+    const Q4 qb = mkq(v.quat[bi]);
+    const float4 dim = v.geomA[bi];
+    const V3 cl = rotate(qinverse(qb), xs - xb);
+    V3 q;
+    q.x = cl.x; if (q.x < (-dim.x / 2.0f)) q.x = -dim.x / 2.0f; else if (q.x > (dim.x / 2.0f)) q.x = dim.x / 2.0f;
+    q.y = cl.y; if (q.y < (-dim.y / 2.0f)) q.y = -dim.y / 2.0f; else if (q.y > (dim.y / 2.0f)) q.y = dim.y / 2.0f;
+    q.z = cl.z; if (q.z < (-dim.z / 2.0f)) q.z = -dim.z / 2.0f; else if (q.z > (dim.z / 2.0f)) q.z = dim.z / 2.0f;
+    const V3 dx = cl - q;
+    const float dist = norm(dx);
+    if (dist < (r + 1e-3f)) {
+        const V3 n = rotate(qb, dx / dist);
+        const V3 p = rotate(qb, q) + xb;
+        e.put(is, ib, p, n, fminf(0.0f, dist - r));
+    }
+}
+
+// CollisionDetect.cpp:152-274 (body0 = cylinder, body1 = plane)
+__device__ __noinline__ void cylinder_plane(Emit& e, int ic, int ip)
+{
+    const View& v = e.v;
+    const size_t ci = at(v, ic, e.scene), pi = at(v, ip, e.scene);
+    const V3 xc = mk3(v.pos[ci]);
+    const Q4 qc = mkq(v.quat[ci]);
+    const float4 cg = v.geomA[ci];
+    const float h = cg.x, r = cg.y;
+    const V3 xp = mk3(v.pos[pi]);
+    const Q4 qp = mkq(v.quat[pi]);
+    const V3 cyldir = rotate(qc, mk3(0.f, 1.f, 0.f));
+    const V3 planen = rotate(qp, mk3(v.geomB[pi]));
+    const V3 planep = rotate(qp, mk3(v.geomA[pi])) + xp;
+    const float dp = dot(cyldir, planen);
+
+    if (fabsf(dp) > 0.995f) {                                    // :164 cap face on the plane
+        const V3 w = (dp < 0.0f) ? cyldir : -cyldir;
+        V3 u = (fabsf(dot(w, mk3(1.f, 0.f, 0.f))) > 0.01f) ? cross(w, mk3(1.f, 0.f, 0.f)) : cross(w, mk3(0.f, 0.f, 1.f));
+        u = normalized(u);
+        V3 vv = normalized(cross(w, u));
+        const V3 a = xc + (0.5f * h) * w;
+        if (plane_dist(a, planep, planen) < 1e-3f) {
+            const V3 pA = a + r * u, pB = a - r * u, pC = a + r * vv, pD = a - r * vv;
+            const float fA = plane_dist(pA, planep, planen), fB = plane_dist(pB, planep, planen);
+            const float fC = plane_dist(pC, planep, planen), fD = plane_dist(pD, planep, planen);
+            if (fA < 1e-3f) e.put(ic, ip, pA, planen, fminf(0.0f, fA));
+            if (fB < 1e-3f) e.put(ic, ip, pB, planen, fminf(0.0f, fB));
+            if (fC < 1e-3f) e.put(ic, ip, pC, planen, fminf(0.0f, fC));
+            if (fD < 1e-3f) e.put(ic, ip, pD, planen, fminf(0.0f, fD));
+        }
+    } else if (fabsf(dp) < 1e-2f) {                              // :215 lying on its side
+        V3 u = cross(cross(planen, cyldir), cyldir);
+        if (dot(u, planen) > 0.0f) u = -u;
+        u = normalized(u);
+        const float dist = plane_dist(xc, planep, planen) - r;
+        if (dist < 0.01f) {                                      // :227
+            const V3 hw = (0.5f * h) * cyldir, ru = r * u;
+            const V3 pA = (xc + hw) + ru, pB = (xc - hw) + ru;
+            const float fA = plane_dist(pA, planep, planen), fB = plane_dist(pB, planep, planen);
+            if (fA < 1e-3f) e.put(ic, ip, pA, planen, fminf(0.0f, fA));
+            if (fB < 1e-3f) e.put(ic, ip, pB, planen, fminf(0.0f, fB));
+        }
+    } else {                                                     // :241 single lowest rim point
+        V3 w = (dp < 0.0f) ? cyldir : -cyldir;
+        w = normalized(w);
+        V3 u = normalized(cross(cross(planen, w), w));
+        if (dot(u, planen) > 0.0f) u = -u;
+        u = normalized(u);
+        const V3 a = (xc + (0.5f * h) * w) + r * u;
+        const float dist = plane_dist(a, planep, planen);
+        if (dist < 1e-3f) e.put(ic, ip, a, planen, fminf(0.0f, dist));
+    }
+}
+
+__global__ void __launch_bounds__(128) k_detect(View v)
+{
+    const int scene = blockIdx.x * blockDim.x + threadIdx.x;
+    if (scene >= v.B) return;
+    const int n = v.nbodies[scene];
+    Emit e{ v, scene, 0 };
+    for (int i = 0; i < n; ++i) {
+        const size_t ii = at(v, i, scene);
+        const float4 ci = v.cproxy[ii];
+        const int fi = v.flags[ii];
+        const int ti = fi & FLAG_TYPE_MASK;
+        const V3 xi = mk3(ci);
+        for (int j = i + 1; j < n; ++j) {
+            const size_t jj = at(v, j, scene);
+            const int fj = v.flags[jj];
+            if ((fi & fj) & FLAG_FIXED) continue;                // CollisionDetect.cpp:41-42
+            const int tj = fj & FLAG_TYPE_MASK;
+            if (ti == GEOM_SPHERE && tj == GEOM_SPHERE) {        // :102-123
+                const float4 cj = v.cproxy[jj];
+                const V3 xj = mk3(cj);
+                const V3 vec = xi - xj;
+                const float rsum = (ci.w + cj.w);
+                const float dist = norm(vec);
+                if (dist < (rsum + 1e-3f)) {
+                    const V3 nn = vec / dist;
+                    const V3 p = 0.5f * ((xi - ci.w * nn) + (xj + cj.w * nn));
+                    e.put(i, j, p, nn, fminf(0.0f, dist - rsum));
+                }
+            } else if (ti == GEOM_SPHERE && tj == GEOM_BOX) {
+                sphere_box(e, i, j, xi, ci.w);
+            } else if (tj == GEOM_SPHERE && ti == GEOM_BOX) {
+                const float4 cj = v.cproxy[jj];
+                sphere_box(e, j, i, mk3(cj), cj.w);
+            } else if (ti == GEOM_CYLINDER && tj == GEOM_PLANE) {
+                cylinder_plane(e, i, j);
+            } else if (tj == GEOM_CYLINDER && ti == GEOM_PLANE) {
+                cylinder_plane(e, j, i);
+            }
+        }
+    }
+    v.ncontacts[scene] = e.count < v.NC ? e.count : v.NC;
+}
+
+// ------------------------------------------------------------------------------------
+// K4  contact frame, Jacobian blocks, J M^-1, 3x3 diagonal block, RHS
+// ------------------------------------------------------------------------------------
+struct BodyDyn { V3 x, xdot, omega, f, tau; float mass; M3 Iinv; bool fixed; };
+
+__device__ __forceinline__ BodyDyn load_body_dyn(const View& v, int slot, int scene)
+{
+    BodyDyn b;
+    const size_t i = at(v, slot, scene);
+    const float4 px = v.pos[i];
+    b.x = mk3(px); b.mass = px.w;
+    b.xdot = mk3(v.vel[i]); b.omega = mk3(v.omg[i]);
+    b.f = mk3(v.force[i]); b.tau = mk3(v.torque[i]);
+    b.Iinv = load_m3(v.Iinvw, v, slot, scene);
+    b.fixed = (v.flags[i] & FLAG_FIXED) != 0;
+    return b;
+}
+
+// multAndSub (SolverBoxPGS.cpp:13-21) on one row: b -= (a * G[k]) * x[k], k = 0..5
+__device__ __forceinline__ float mult_and_sub_row(float b, const float* G, const V3& x, const V3& y, float a)
+{
+    b -= (a * G[0]) * x.x; b -= (a * G[1]) * x.y; b -= (a * G[2]) * x.z;
+    b -= (a * G[3]) * y.x; b -= (a * G[4]) * y.y; b -= (a * G[5]) * y.z;
+    return b;
+}
+
+__device__ __forceinline__ void set_row(float* row, const V3& lin, const V3& ang)
+{
+    row[0] = lin.x; row[1] = lin.y; row[2] = lin.z; row[3] = ang.x; row[4] = ang.y; row[5] = ang.z;
+}
+
+// J M^-1 row: linear (1/mass) * J_lin, angular J_ang * Iinv   (Contact.cpp:90-93, Hinge.cpp:59-62)
+__device__ __forceinline__ void jminv_row(const float* J, float* JM, const BodyDyn& b)
+{
+    const float im = 1.0f / b.mass;
+    JM[0] = im * J[0]; JM[1] = im * J[1]; JM[2] = im * J[2];
+    const V3 a = vecmat(mk3(J[3], J[4], J[5]), b.Iinv);
+    JM[3] = a.x; JM[4] = a.y; JM[5] = a.z;
+}
+
+__device__ __forceinline__ float dot6_seq(const float* a, const float* b)
+{
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc += a[k] * b[k];
+    return acc;
+}
+
+__global__ void __launch_bounds__(128) k_contact_rows(View v, float h)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)v.NC * v.B) return;
+    const int scene = (int)(tid % v.B), slot = (int)(tid / v.B);
+    if (slot >= v.ncontacts[scene]) return;
+    const size_t c = at(v, slot, scene);
+    const int2 ids = v.cids[c];
+    const float4 pp = v.cp[c];
+    const V3 p = mk3(pp), n = mk3(v.cn[c]);
+    const float pene = pp.w;
+    const BodyDyn b0 = load_body_dyn(v, ids.x, scene);
+    const BodyDyn b1 = load_body_dyn(v, ids.y, scene);
+
+    // Contact::computeContactFrame (Contact.cpp:33-53)
+    V3 t = cross(n, mk3(1.f, 0.f, 0.f));
+    if (norm(t) < 1e-5f) t = cross(n, mk3(0.f, 1.f, 0.f));
+    t = normalized(t);
+    const V3 bb = normalized(cross(n, t));
+
+    // Contact::computeJacobian (Contact.cpp:55-94)
+    const V3 rr0 = p - b0.x, rr1 = p - b1.x;
+    float J0[3][6], J1[3][6], M0[3][6], M1[3][6];
+    const V3 d[3] = { n, t, bb };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        set_row(J0[k], d[k], cross(rr0, d[k]));
+        set_row(J1[k], -d[k], -cross(rr1, d[k]));
+        jminv_row(J0[k], M0[k], b0);
+        jminv_row(J1[k], M1[k], b1);
+    }
+    // diagonal block (SolverBoxPGS.cpp:165-189) and RHS (buildRHS :27-44)
+    float A[3][3], rhs[3];
+    const float hinv = 1.0f / h;
+    const float phi[3] = { pene, 0.f, 0.f };
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+            float a = 0.f;
+            if (!b0.fixed) a += dot6_seq(M0[r], J0[cc]);
+            if (!b1.fixed) a += dot6_seq(M1[r], J1[cc]);
+            A[r][cc] = a;
+        }
+        float b = (-hinv * 0.3f) * phi[r];
+        if (!b0.fixed) { b = mult_and_sub_row(b, M0[r], b0.f, b0.tau, h); b = mult_and_sub_row(b, J0[r], b0.xdot, b0.omega, 1.0f); }
+        if (!b1.fixed) { b = mult_and_sub_row(b, M1[r], b1.f, b1.tau, h); b = mult_and_sub_row(b, J1[r], b1.xdot, b1.omega, 1.0f); }
+        rhs[r] = b;
+    }
+    const int id0 = ids.x | (b0.fixed ? BODY_FIXED_BIT : 0);
+    const int id1 = ids.y | (b1.fixed ? BODY_FIXED_BIT : 0);
+    float4* R = v.crow;
+#define CROW(f) R[at_crow(v, f, slot, scene)]
+    CROW(0)  = mk4(n, 1.0f / b0.mass);
+    CROW(1)  = mk4(t, 1.0f / b1.mass);
+    CROW(2)  = mk4(bb, __int_as_float(id0));
+    CROW(3)  = make_float4(J0[0][3], J0[0][4], J0[0][5], __int_as_float(id1));
+    CROW(4)  = make_float4(J0[1][3], J0[1][4], J0[1][5], rhs[0]);
+    CROW(5)  = make_float4(J0[2][3], J0[2][4], J0[2][5], rhs[1]);
+    CROW(6)  = make_float4(J1[0][3], J1[0][4], J1[0][5], rhs[2]);
+    CROW(7)  = make_float4(J1[1][3], J1[1][4], J1[1][5], A[0][0]);
+    CROW(8)  = make_float4(J1[2][3], J1[2][4], J1[2][5], A[1][1]);
+    CROW(9)  = make_float4(M0[0][3], M0[0][4], M0[0][5], A[2][2]);
+    CROW(10) = make_float4(M0[1][3], M0[1][4], M0[1][5], A[0][1]);
+    CROW(11) = make_float4(M0[2][3], M0[2][4], M0[2][5], A[0][2]);
+    CROW(12) = make_float4(M1[0][3], M1[0][4], M1[0][5], A[1][0]);
+    CROW(13) = make_float4(M1[1][3], M1[1][4], M1[1][5], A[1][2]);
+    CROW(14) = make_float4(M1[2][3], M1[2][4], M1[2][5], A[2][0]);
+    CROW(15) = make_float4(0.f, 0.f, 0.f, A[2][1]);          // lambda = 0 (Contact.cpp:66, SolverBoxPGS.cpp:210)
+#undef CROW
+}
+
+// ------------------------------------------------------------------------------------
+// K5  joint Jacobians, J M^-1, dim x dim diagonal block + LDL^T, RHS
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void set_hat(float J[5][6], const V3& a)
+{
+    J[0][3] = 0.f;   J[0][4] = -a.z; J[0][5] = a.y;
+    J[1][3] = a.z;   J[1][4] = 0.f;  J[1][5] = -a.x;
+    J[2][3] = -a.y;  J[2][4] = a.x;  J[2][5] = 0.f;
+}
+
+__global__ void __launch_bounds__(128) k_joint_rows(View v, float h)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)v.NJ * v.B) return;
+    const int scene = (int)(tid % v.B), slot = (int)(tid / v.B);
+    if (slot >= v.njoints[scene]) return;
+    const size_t j = at(v, slot, scene);
+    const int4 def = v.jdef[j];                                  // type, body0, body1, dim
+    const int dim = def.w;
+    const BodyDyn b0 = load_body_dyn(v, def.y, scene);
+    const BodyDyn b1 = load_body_dyn(v, def.z, scene);
+    const Q4 qb0 = mkq(v.quat[at(v, def.y, scene)]);
+    const Q4 qb1 = mkq(v.quat[at(v, def.z, scene)]);
+
+    // Hinge::computeJacobian (Hinge.cpp:33-63) / Spherical::computeJacobian (Spherical.cpp:34-52)
+    const V3 rr0 = rotate(qb0, mk3(v.jr0[j]));
+    const V3 rr1 = rotate(qb1, mk3(v.jr1[j]));
+    float phi[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
+    const V3 e = ((b0.x + rr0) - b1.x) - rr1;
+    phi[0] = e.x; phi[1] = e.y; phi[2] = e.z;
+    float J0[5][6], J1[5][6], M0[5][6], M1[5][6];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { J0[r][k] = 0.f; J1[r][k] = 0.f; }
+    J0[0][0] = J0[1][1] = J0[2][2] = 1.f;
+    J1[0][0] = J1[1][1] = J1[2][2] = -1.f;
+    set_hat(J0, -rr0);
+    set_hat(J1, rr1);
+    V3 nxu = mk3(0.f, 0.f, 0.f), nxv = mk3(0.f, 0.f, 0.f);
+    if (dim == 5) {
+        const V3 nn = rotate(qb0, rotate(mkq(v.jq0[j]), mk3(1.f, 0.f, 0.f)));
+        const Q4 q1 = mkq(v.jq1[j]);
+        const V3 uu = rotate(qb1, rotate(q1, mk3(0.f, 1.f, 0.f)));
+        const V3 vv = rotate(qb1, rotate(q1, mk3(0.f, 0.f, 1.f)));
+        nxu = cross(nn, uu); nxv = cross(nn, vv);
+        phi[3] = dot(nn, uu); phi[4] = dot(nn, vv);
+        set_row(J0[3], mk3(0.f, 0.f, 0.f), nxu); set_row(J0[4], mk3(0.f, 0.f, 0.f), nxv);
+        set_row(J1[3], mk3(0.f, 0.f, 0.f), -nxu); set_row(J1[4], mk3(0.f, 0.f, 0.f), -nxv);
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r) { jminv_row(J0[r], M0[r], b0); jminv_row(J1[r], M1[r], b1); }
+
+    // A = eps*I + sum_{non-fixed} JMinv J^T  (SolverBoxPGS.cpp:140-159); RHS (:27-44)
+    float A[5][5], rhs[5];
+    const float hinv = 1.0f / h;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            float a = (r == c) ? 1e-5f : 0.f;
+            if (!b0.fixed) a += dot6_seq(M0[r], J0[c]);
+            if (!b1.fixed) a += dot6_seq(M1[r], J1[c]);
+            A[r][c] = a;
+        }
+        float b = (-hinv * 0.3f) * phi[r];
+        if (!b0.fixed) { b = mult_and_sub_row(b, M0[r], b0.f, b0.tau, h); b = mult_and_sub_row(b, J0[r], b0.xdot, b0.omega, 1.0f); }
+        if (!b1.fixed) { b = mult_and_sub_row(b, M1[r], b1.f, b1.tau, h); b = mult_and_sub_row(b, J1[r], b1.xdot, b1.omega, 1.0f); }
+        rhs[r] = b;
+    }
+    if (dim < 5) {   // spherical: rows 3,4 are inert (lambda stays 0)
+        for (int r = 3; r < 5; ++r) { for (int c = 0; c < 5; ++c) { A[r][c] = 0.f; A[c][r] = 0.f; } A[r][r] = 1.f; rhs[r] = 0.f; }
+    }
+    // LDL^T of the SPD block (Eigen::LDLT in the reference, SolverBoxPGS.cpp:161; the block is
+    // J M^-1 J^T + 1e-5 I so no pivoting is needed for accuracy)
+    float L[5][5], D[5], Dinv[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        float dsum = A[c][c];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) if (k < c) dsum -= (L[c][k] * L[c][k]) * D[k];
+        D[c] = dsum;
+        Dinv[c] = 1.0f / dsum;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) if (r > c) {
+            float s = A[r][c];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) if (k < c) s -= (L[r][k] * L[c][k]) * D[k];
+            L[r][c] = s / dsum;
+        }
+    }
+    const int id0 = def.y | (b0.fixed ? BODY_FIXED_BIT : 0);
+    const int id1 = def.z | (b1.fixed ? BODY_FIXED_BIT : 0);
+    float4* R = v.jrow;
+#define JROW(f) R[at_jrow(v, f, slot, scene)]
+    JROW(0) = mk4(rr0, 1.0f / b0.mass);
+    JROW(1) = mk4(rr1, 1.0f / b1.mass);
+    JROW(2) = mk4(nxu, __int_as_float(id0));
+    JROW(3) = mk4(nxv, __int_as_float(id1));
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        JROW(4 + r) = make_float4(M0[r][3], M0[r][4], M0[r][5], rhs[r]);
+        JROW(9 + r) = make_float4(M1[r][3], M1[r][4], M1[r][5], Dinv[r]);
+    }
+    JROW(14) = make_float4(L[1][0], L[2][0], L[2][1], L[3][0]);
+    JROW(15) = make_float4(L[3][1], L[3][2], L[4][0], L[4][1]);
+    JROW(16) = make_float4(L[4][2], L[4][3], __int_as_float(dim), 0.f);
+#undef JROW
+}
+
+// ------------------------------------------------------------------------------------
+// K6  Box-PGS sweep: one thread per scene, rows in the reference's sequential order
+// ------------------------------------------------------------------------------------
+// The reference recomputes, for every row block i, x = b_i - sum_{k != i} JMinv_i (J_k^T lambda_k)
+// over all constraints sharing a non-fixed body (SolverBoxPGS.cpp:49-82). Here each non-fixed
+// body carries w_body = sum_k J_k,body^T lambda_k, so the same x is
+//   b_i - JMinv_i0 (w_0 - J_i0^T lambda_i) - JMinv_i1 (w_1 - J_i1^T lambda_i)
+// and after the block solve w += J^T (lambda_new - lambda_old). Gauss-Seidel order, the
+// solveContact projection (:94-113) and the joint block solve (:115-118) are unchanged.
+__device__ __forceinline__ V3 fma3(float s, const V3& a, const V3& acc)
+{
+    return mk3(fmaf(s, a.x, acc.x), fmaf(s, a.y, acc.y), fmaf(s, a.z, acc.z));
+}
+__device__ __forceinline__ float dotf(const V3& a, const V3& b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ V3 lin3(const V3& a, float s0, const V3& b, float s1, const V3& c, float s2)
+{
+    return fma3(s2, c, fma3(s1, b, s0 * a));
+}
+
+__device__ __forceinline__ void contact_visit(const View& v, int slot, int scene, float mu)
+{
+    float4 F[CROW_FIELDS];
+#pragma unroll
+    for (int f = 0; f < CROW_FIELDS; ++f) F[f] = __ldg(&v.crow[at_crow(v, f, slot, scene)]);
+    // lambda is read-modify-write; field 15 is re-read without the read-only path
+    F[15] = v.crow[at_crow(v, 15, slot, scene)];
+    const V3 n = mk3(F[0]), t = mk3(F[1]), b = mk3(F[2]);
+    const float im0 = F[0].w, im1 = F[1].w;
+    const int id0 = __float_as_int(F[2].w), id1 = __float_as_int(F[3].w);
+    const bool dyn0 = id0 >= 0, dyn1 = id1 >= 0;
+    const V3 a0n = mk3(F[3]), a0t = mk3(F[4]), a0b = mk3(F[5]);
+    const V3 a1n = mk3(F[6]), a1t = mk3(F[7]), a1b = mk3(F[8]);
+    float x0 = F[4].w, x1 = F[5].w, x2 = F[6].w;
+    const float l0 = F[15].x, l1 = F[15].y, l2 = F[15].z;
+    const V3 dl = lin3(n, l0, t, l1, b, l2);                     // J0_lin^T lambda ( = -J1_lin^T lambda)
+    size_t w0i = 0, w1i = 0;
+    V3 w0l, w0a, w1l, w1a;
+    if (dyn0) {
+        w0i = at(v, id0, scene);
+        w0l = mk3(v.wl[w0i]); w0a = mk3(v.wa[w0i]);
+        const V3 tl = w0l - dl;
+        const V3 ta = w0a - lin3(a0n, l0, a0t, l1, a0b, l2);
+        x0 -= fmaf(im0, dotf(n, tl), dotf(mk3(F[9]), ta));
+        x1 -= fmaf(im0, dotf(t, tl), dotf(mk3(F[10]), ta));
+        x2 -= fmaf(im0, dotf(b, tl), dotf(mk3(F[11]), ta));
+    }
+    if (dyn1) {
+        w1i = at(v, id1 & 0x7fffffff, scene);
+        w1l = mk3(v.wl[w1i]); w1a = mk3(v.wa[w1i]);
+        const V3 tl = w1l + dl;
+        const V3 ta = w1a - lin3(a1n, l0, a1t, l1, a1b, l2);
+        x0 -= fmaf(-im1, dotf(n, tl), dotf(mk3(F[12]), ta));
+        x1 -= fmaf(-im1, dotf(t, tl), dotf(mk3(F[13]), ta));
+        x2 -= fmaf(-im1, dotf(b, tl), dotf(mk3(F[14]), ta));
+    }
+    // solveContact (SolverBoxPGS.cpp:94-113); x aliases lambda, so l1,l2 on the first line are last sweep's
+    const float A00 = F[7].w, A11 = F[8].w, A22 = F[9].w, A01 = F[10].w, A02 = F[11].w;
+    const float A10 = F[12].w, A12 = F[13].w, A20 = F[14].w, A21 = F[15].w;
+    float y0 = (x0 - A01 * l1 - A02 * l2) / (A00 + 1e-3f);
+    if (y0 < 0.0f) y0 = 0.0f;
+    const float lo = -mu * y0, hi = mu * y0;
+    float y1 = (x1 - A10 * y0 - A12 * l2) / A11;
+    if (y1 < lo) y1 = lo; else if (y1 > hi) y1 = hi;
+    float y2 = (x2 - A20 * y0 - A21 * y1) / A22;
+    if (y2 < lo) y2 = lo; else if (y2 > hi) y2 = hi;
+    const float d0 = y0 - l0, d1 = y1 - l1, d2 = y2 - l2;
+    const V3 ddl = lin3(n, d0, t, d1, b, d2);
+    if (dyn0) {
+        v.wl[w0i] = mk4(w0l + ddl, 0.f);
+        v.wa[w0i] = mk4(w0a + lin3(a0n, d0, a0t, d1, a0b, d2), 0.f);
+    }
+    if (dyn1) {
+        v.wl[w1i] = mk4(w1l - ddl, 0.f);
+        v.wa[w1i] = mk4(w1a + lin3(a1n, d0, a1t, d1, a1b, d2), 0.f);
+    }
+    v.crow[at_crow(v, 15, slot, scene)] = make_float4(y0, y1, y2, A21);
+}
+
+struct JointRow {
+    V3 rr0, rr1, nxu, nxv; float im0, im1; int id0, id1;
+};
+__device__ __forceinline__ JointRow load_joint_head(const View& v, int slot, int scene)
+{
+    JointRow j;
+    const float4 g0 = __ldg(&v.jrow[at_jrow(v, 0, slot, scene)]);
+    const float4 g1 = __ldg(&v.jrow[at_jrow(v, 1, slot, scene)]);
+    const float4 g2 = __ldg(&v.jrow[at_jrow(v, 2, slot, scene)]);
+    const float4 g3 = __ldg(&v.jrow[at_jrow(v, 3, slot, scene)]);
+    j.rr0 = mk3(g0); j.im0 = g0.w; j.rr1 = mk3(g1); j.im1 = g1.w;
+    j.nxu = mk3(g2); j.id0 = __float_as_int(g2.w); j.nxv = mk3(g3); j.id1 = __float_as_int(g3.w);
+    return j;
+}
+// J0^T lambda: linear (l0,l1,l2), angular rr0 x l_lin + l3 nxu + l4 nxv ; J1^T lambda is minus the
+// same with rr1 (J0 = [I hat(-rr0); 0 nxu; 0 nxv], J1 = [-I hat(rr1); 0 -nxu; 0 -nxv])
+__device__ __forceinline__ V3 joint_jt_ang(const V3& rr, const V3& nxu, const V3& nxv, const float* l)
+{
+    const V3 ll = mk3(l[0], l[1], l[2]);
+    return fma3(l[4], nxv, fma3(l[3], nxu, cross(rr, ll)));
+}
+
+__device__ __forceinline__ void joint_visit(const View& v, int slot, int scene)
+{
+    const JointRow j = load_joint_head(v, slot, scene);
+    float4 M0[5], M1[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        M0[r] = __ldg(&v.jrow[at_jrow(v, 4 + r, slot, scene)]);
+        M1[r] = __ldg(&v.jrow[at_jrow(v, 9 + r, slot, scene)]);
+    }
+    const float4 La = __ldg(&v.jrow[at_jrow(v, 14, slot, scene)]);
+    const float4 Lb = __ldg(&v.jrow[at_jrow(v, 15, slot, scene)]);
+    const float4 Lc = __ldg(&v.jrow[at_jrow(v, 16, slot, scene)]);
+    const size_t ji = at(v, slot, scene);
+    const float4 lam03 = v.jlam[ji];
+    float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
+    float x[5] = { M0[0].w, M0[1].w, M0[2].w, M0[3].w, M0[4].w };
+    const bool dyn0 = j.id0 >= 0, dyn1 = j.id1 >= 0;
+    const V3 ll = mk3(l[0], l[1], l[2]);
+    size_t w0i = 0, w1i = 0;
+    V3 w0l, w0a, w1l, w1a;
+    if (dyn0) {
+        w0i = at(v, j.id0, scene);
+        w0l = mk3(v.wl[w0i]); w0a = mk3(v.wa[w0i]);
+        const V3 tl = w0l - ll;
+        const V3 ta = w0a - joint_jt_ang(j.rr0, j.nxu, j.nxv, l);
+        x[0] -= fmaf(j.im0, tl.x, dotf(mk3(M0[0]), ta));
+        x[1] -= fmaf(j.im0, tl.y, dotf(mk3(M0[1]), ta));
+        x[2] -= fmaf(j.im0, tl.z, dotf(mk3(M0[2]), ta));
+        x[3] -= dotf(mk3(M0[3]), ta);
+        x[4] -= dotf(mk3(M0[4]), ta);
+    }
+    if (dyn1) {
+        w1i = at(v, j.id1 & 0x7fffffff, scene);
+        w1l = mk3(v.wl[w1i]); w1a = mk3(v.wa[w1i]);
+        const V3 tl = w1l + ll;
+        const V3 ta = w1a + joint_jt_ang(j.rr1, j.nxu, j.nxv, l);
+        x[0] -= fmaf(-j.im1, tl.x, dotf(mk3(M1[0]), ta));
+        x[1] -= fmaf(-j.im1, tl.y, dotf(mk3(M1[1]), ta));
+        x[2] -= fmaf(-j.im1, tl.z, dotf(mk3(M1[2]), ta));
+        x[3] -= dotf(mk3(M1[3]), ta);
+        x[4] -= dotf(mk3(M1[4]), ta);
+    }
+    // lambda = LDLT.solve(x)  (SolverBoxPGS.cpp:115-118,231)
+    const float L10 = La.x, L20 = La.y, L21 = La.z, L30 = La.w, L31 = Lb.x, L32 = Lb.y, L40 = Lb.z, L41 = Lb.w, L42 = Lc.x, L43 = Lc.y;
+    float y0 = x[0];
+    float y1 = fmaf(-L10, y0, x[1]);
+    float y2 = fmaf(-L21, y1, fmaf(-L20, y0, x[2]));
+    float y3 = fmaf(-L32, y2, fmaf(-L31, y1, fmaf(-L30, y0, x[3])));
+    float y4 = fmaf(-L43, y3, fmaf(-L42, y2, fmaf(-L41, y1, fmaf(-L40, y0, x[4]))));
+    y0 *= M1[0].w; y1 *= M1[1].w; y2 *= M1[2].w; y3 *= M1[3].w; y4 *= M1[4].w;
+    float n[5];
+    n[4] = y4;
+    n[3] = fmaf(-L43, n[4], y3);
+    n[2] = fmaf(-L42, n[4], fmaf(-L32, n[3], y2));
+    n[1] = fmaf(-L41, n[4], fmaf(-L31, n[3], fmaf(-L21, n[2], y1)));
+    n[0] = fmaf(-L40, n[4], fmaf(-L30, n[3], fmaf(-L20, n[2], fmaf(-L10, n[1], y0))));
+    float d[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) d[r] = n[r] - l[r];
+    const V3 dl = mk3(d[0], d[1], d[2]);
+    if (dyn0) {
+        v.wl[w0i] = mk4(w0l + dl, 0.f);
+        v.wa[w0i] = mk4(w0a + joint_jt_ang(j.rr0, j.nxu, j.nxv, d), 0.f);
+    }
+    if (dyn1) {
+        v.wl[w1i] = mk4(w1l - dl, 0.f);
+        v.wa[w1i] = mk4(w1a - joint_jt_ang(j.rr1, j.nxu, j.nxv, d), 0.f);
+    }
+    v.jlam[ji] = make_float4(n[0], n[1], n[2], n[3]);
+    v.jlam4[ji] = n[4];
+}
+
+// calcConstraintForces tail (RigidBodySystem.cpp:185-220): f = (J^T lambda) / dt with the
+// reference's left-to-right row sum, no fused multiply-adds.
+__device__ __forceinline__ V3 seq3(const V3& a, float s0, const V3& b, float s1, const V3& c, float s2)
+{
+    return mk3(((0.f + a.x * s0) + b.x * s1) + c.x * s2, ((0.f + a.y * s0) + b.y * s1) + c.y * s2,
+               ((0.f + a.z * s0) + b.z * s1) + c.z * s2);
+}
+__device__ __forceinline__ void add_force(const View& v, int body, int scene, const V3& fl, const V3& fa)
+{
+    const size_t i = at(v, body, scene);
+    v.wl[i] = mk4(mk3(v.wl[i]) + fl, 0.f);
+    v.wa[i] = mk4(mk3(v.wa[i]) + fa, 0.f);
+}
+
+__global__ void __launch_bounds__(128) k_pgs(View v, float dt, int iters, float mu)
+{
+    const int scene = blockIdx.x * blockDim.x + threadIdx.x;
+    if (scene >= v.B) return;
+    const int nb = v.nbodies[scene], nj = v.njoints[scene], nc = v.ncontacts[scene];
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < nb; ++i) { v.wl[at(v, i, scene)] = z4; v.wa[at(v, i, scene)] = z4; }
+    // joints keep last step's lambda (Hinge.cpp:33-63 never zeroes it): seed w with it
+    for (int s = 0; s < nj; ++s) {
+        const JointRow j = load_joint_head(v, s, scene);
+        const size_t ji = at(v, s, scene);
+        const float4 lam03 = v.jlam[ji];
+        const float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
+        const V3 ll = mk3(l[0], l[1], l[2]);
+        if (j.id0 >= 0) {
+            const size_t wi = at(v, j.id0, scene);
+            v.wl[wi] = mk4(mk3(v.wl[wi]) + ll, 0.f);
+            v.wa[wi] = mk4(mk3(v.wa[wi]) + joint_jt_ang(j.rr0, j.nxu, j.nxv, l), 0.f);
+        }
+        if (j.id1 >= 0) {
+            const size_t wi = at(v, j.id1 & 0x7fffffff, scene);
+            v.wl[wi] = mk4(mk3(v.wl[wi]) - ll, 0.f);
+            v.wa[wi] = mk4(mk3(v.wa[wi]) - joint_jt_ang(j.rr1, j.nxu, j.nxv, l), 0.f);
+        }
+    }
+    for (int it = 0; it < iters; ++it) {                          // SolverBoxPGS.cpp:217-248
+        for (int s = 0; s < nj; ++s) joint_visit(v, s, scene);
+        for (int s = 0; s < nc; ++s) contact_visit(v, s, scene, mu);
+    }
+    // constraint forces (RigidBodySystem.cpp:185-220): wl/wa become fc/tauc
+    for (int i = 0; i < nb; ++i) { v.wl[at(v, i, scene)] = z4; v.wa[at(v, i, scene)] = z4; }
+    for (int s = 0; s < nj; ++s) {
+        const JointRow j = load_joint_head(v, s, scene);
+        const size_t ji = at(v, s, scene);
+        const float4 lam03 = v.jlam[ji];
+        const float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
+        float J0[5][6], J1[5][6];
+        for (int r = 0; r < 5; ++r) for (int k = 0; k < 6; ++k) { J0[r][k] = 0.f; J1[r][k] = 0.f; }
+        J0[0][0] = J0[1][1] = J0[2][2] = 1.f; J1[0][0] = J1[1][1] = J1[2][2] = -1.f;
+        set_hat(J0, -j.rr0); set_hat(J1, j.rr1);
+        set_row(J0[3], mk3(0.f, 0.f, 0.f), j.nxu); set_row(J0[4], mk3(0.f, 0.f, 0.f), j.nxv);
+        set_row(J1[3], mk3(0.f, 0.f, 0.f), -j.nxu); set_row(J1[4], mk3(0.f, 0.f, 0.f), -j.nxv);
+        const int dim = __float_as_int(__ldg(&v.jrow[at_jrow(v, 16, s, scene)]).z);
+        float f0[6], f1[6];
+        for (int k = 0; k < 6; ++k) {
+            float a0 = 0.f, a1 = 0.f;
+            for (int r = 0; r < 5; ++r) if (r < dim) { a0 += J0[r][k] * l[r]; a1 += J1[r][k] * l[r]; }
+            f0[k] = a0 / dt; f1[k] = a1 / dt;
+        }
+        add_force(v, j.id0 & 0x7fffffff, scene, mk3(f0[0], f0[1], f0[2]), mk3(f0[3], f0[4], f0[5]));   // unconditional (:189-192)
+        add_force(v, j.id1 & 0x7fffffff, scene, mk3(f1[0], f1[1], f1[2]), mk3(f1[3], f1[4], f1[5]));
+    }
+    for (int s = 0; s < nc; ++s) {
+        float4 F[9];
+#pragma unroll
+        for (int f = 0; f < 9; ++f) F[f] = __ldg(&v.crow[at_crow(v, f, s, scene)]);
+        const float4 lam = v.crow[at_crow(v, 15, s, scene)];
+        const int id0 = __float_as_int(F[2].w), id1 = __float_as_int(F[3].w);
+        const V3 n = mk3(F[0]), t = mk3(F[1]), b = mk3(F[2]);
+        if (id0 >= 0)
+            add_force(v, id0, scene, seq3(n, lam.x, t, lam.y, b, lam.z) / dt,
+                      seq3(mk3(F[3]), lam.x, mk3(F[4]), lam.y, mk3(F[5]), lam.z) / dt);
+        if (id1 >= 0)
+            add_force(v, id1, scene, seq3(-n, lam.x, -t, lam.y, -b, lam.z) / dt,
+                      seq3(mk3(F[6]), lam.x, mk3(F[7]), lam.y, mk3(F[8]), lam.z) / dt);
+    }
+    if (v.profiling) {
+        atomicAdd(&v.visit_counters[0], (unsigned long long)nc * iters);
+        atomicAdd(&v.visit_counters[1], (unsigned long long)nj * iters);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K7  symplectic Euler + quaternion update (RigidBodySystem.cpp:99-120)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_integrate(View v, float dt)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)v.NB * v.B) return;
+    const int scene = (int)(tid % v.B), slot = (int)(tid / v.B);
+    if (slot >= v.nbodies[scene]) return;
+    const size_t i = at(v, slot, scene);
+    const int fl = v.flags[i];
+    float4 vv = v.vel[i], ww = v.omg[i];
+    if (!(fl & FLAG_FIXED)) {
+        float4 px = v.pos[i];
+        const float mass = px.w;
+        const V3 f = mk3(v.force[i]), tau = mk3(v.torque[i]);
+        const V3 fc = mk3(v.wl[i]), tauc = mk3(v.wa[i]);
+        V3 xdot = mk3(vv), omega = mk3(ww), x = mk3(px);
+        Q4 q = mkq(v.quat[i]);
+        const M3 I = load_m3(v.Iw, v, slot, scene);
+        const M3 Iinv = load_m3(v.Iinvw, v, slot, scene);
+        xdot = xdot + (dt * (1.0f / mass)) * (f + fc);
+        omega = omega + dt * matvec(Iinv, (tau + tauc) - cross(omega, matvec(I, omega)));
+        x = x + dt * xdot;
+        const float hdt = 0.5f * dt;
+        Q4 wq; wq.w = hdt * 0.0f; wq.x = hdt * omega.x; wq.y = hdt * omega.y; wq.z = hdt * omega.z;
+        const Q4 dq = qmul(wq, q);
+        Q4 qn; qn.x = q.x + dq.x; qn.y = q.y + dq.y; qn.z = q.z + dq.z; qn.w = q.w + dq.w;
+        qn = qnormalized(qn);
+        v.pos[i] = make_float4(x.x, x.y, x.z, mass);
+        v.quat[i] = make_float4(qn.x, qn.y, qn.z, qn.w);
+        v.vel[i] = make_float4(xdot.x, xdot.y, xdot.z, vv.w);
+        v.omg[i] = make_float4(omega.x, omega.y, omega.z, ww.w);
+    } else {
+        v.vel[i] = make_float4(0.f, 0.f, 0.f, vv.w);
+        v.omg[i] = make_float4(0.f, 0.f, 0.f, ww.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host <-> device repacking (scene-major host arrays <-> slot-major device arrays)
+// ------------------------------------------------------------------------------------
+__global__ void k_upload_bodies(View v, int scene0, int ns, int n, const int* counts, BodyStage st)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)ns * n) return;
+    const int ls = (int)(tid % ns), slot = (int)(tid / ns);
+    const int scene = scene0 + ls;
+    if (slot == 0) v.nbodies[scene] = counts ? counts[ls] : n;
+    const size_t h = (size_t)ls * n + slot;
+    const size_t i = at(v, slot, scene);
+    float4 px = v.pos[i];
+    if (st.x) { px.x = st.x[3 * h]; px.y = st.x[3 * h + 1]; px.z = st.x[3 * h + 2]; }
+    if (st.mass) px.w = st.mass[h];
+    v.pos[i] = px;
+    if (st.q) v.quat[i] = make_float4(st.q[4 * h], st.q[4 * h + 1], st.q[4 * h + 2], st.q[4 * h + 3]);
+    if (st.v) v.vel[i] = make_float4(st.v[3 * h], st.v[3 * h + 1], st.v[3 * h + 2], 0.f);
+    if (st.w) v.omg[i] = make_float4(st.w[3 * h], st.w[3 * h + 1], st.w[3 * h + 2], 0.f);
+    if (st.geom_type) v.flags[i] = (st.geom_type[h] & FLAG_TYPE_MASK) | ((st.fixed && st.fixed[h]) ? FLAG_FIXED : 0);
+    if (st.geom) {
+        const float* g = st.geom + 6 * h;
+        v.geomA[i] = make_float4(g[0], g[1], g[2], 0.f);
+        v.geomB[i] = make_float4(g[3], g[4], g[5], 0.f);
+    }
+    if (st.ibody) for (int k = 0; k < 9; ++k) v.ibody[at_b9(v, k, slot, scene)] = st.ibody[9 * h + k];
+    if (st.ibodyinv) for (int k = 0; k < 9; ++k) v.ibodyinv[at_b9(v, k, slot, scene)] = st.ibodyinv[9 * h + k];
+}
+
+__global__ void k_download_state(View v, int scene0, int ns, int n, BodyStage st)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)ns * n) return;
+    const int ls = (int)(tid % ns), slot = (int)(tid / ns);
+    const int scene = scene0 + ls;
+    const size_t h = (size_t)ls * n + slot;
+    const size_t i = at(v, slot, scene);
+    float* x = (float*)st.x; float* q = (float*)st.q; float* vv = (float*)st.v; float* w = (float*)st.w;
+    if (x) { const float4 a = v.pos[i]; x[3 * h] = a.x; x[3 * h + 1] = a.y; x[3 * h + 2] = a.z; }
+    if (q) { const float4 a = v.quat[i]; q[4 * h] = a.x; q[4 * h + 1] = a.y; q[4 * h + 2] = a.z; q[4 * h + 3] = a.w; }
+    if (vv) { const float4 a = v.vel[i]; vv[3 * h] = a.x; vv[3 * h + 1] = a.y; vv[3 * h + 2] = a.z; }
+    if (w) { const float4 a = v.omg[i]; w[3 * h] = a.x; w[3 * h + 1] = a.y; w[3 * h + 2] = a.z; }
+}
+
+__global__ void k_upload_joints(View v, int scene0, int ns, int n, const int* counts, JointStage st)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)ns * n) return;
+    const int ls = (int)(tid % ns), slot = (int)(tid / ns);
+    const int scene = scene0 + ls;
+    if (slot == 0) v.njoints[scene] = counts ? counts[ls] : n;
+    const size_t h = (size_t)ls * n + slot;
+    const size_t j = at(v, slot, scene);
+    const int type = st.type[h];
+    v.jdef[j] = make_int4(type, st.body0[h], st.body1[h], type == 2 ? 5 : 3);
+    v.jr0[j] = make_float4(st.r0[3 * h], st.r0[3 * h + 1], st.r0[3 * h + 2], 0.f);
+    v.jr1[j] = make_float4(st.r1[3 * h], st.r1[3 * h + 1], st.r1[3 * h + 2], 0.f);
+    v.jq0[j] = st.q0 ? make_float4(st.q0[4 * h], st.q0[4 * h + 1], st.q0[4 * h + 2], st.q0[4 * h + 3]) : make_float4(0.f, 0.f, 0.f, 1.f);
+    v.jq1[j] = st.q1 ? make_float4(st.q1[4 * h], st.q1[4 * h + 1], st.q1[4 * h + 2], st.q1[4 * h + 3]) : make_float4(0.f, 0.f, 0.f, 1.f);
+    v.jlam[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.jlam4[j] = 0.f;
+}
+
+__global__ void k_joint_lambda(View v, int scene0, int ns, int n, float* lam5, int upload)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)ns * n) return;
+    const int ls = (int)(tid % ns), slot = (int)(tid / ns);
+    const size_t h = (size_t)ls * n + slot;
+    const size_t j = at(v, slot, scene0 + ls);
+    if (upload) {
+        v.jlam[j] = make_float4(lam5[5 * h], lam5[5 * h + 1], lam5[5 * h + 2], lam5[5 * h + 3]);
+        v.jlam4[j] = lam5[5 * h + 4];
+    } else {
+        const float4 a = v.jlam[j];
+        lam5[5 * h] = a.x; lam5[5 * h + 1] = a.y; lam5[5 * h + 2] = a.z; lam5[5 * h + 3] = a.w; lam5[5 * h + 4] = v.jlam4[j];
+    }
+}
+
+__global__ void k_set_ext(View v, int scene0, int ns, int n, const float* f3, const float* t3)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)ns * n) return;
+    const int ls = (int)(tid % ns), slot = (int)(tid / ns);
+    const size_t h = (size_t)ls * n + slot;
+    const size_t i = at(v, slot, scene0 + ls);
+    v.extf[i] = f3 ? make_float4(f3[3 * h], f3[3 * h + 1], f3[3 * h + 2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v.extt[i] = t3 ? make_float4(t3[3 * h], t3[3 * h + 1], t3[3 * h + 2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void k_snapshot(View v, int scene0, int ns, int restore)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)ns * v.NB) return;
+    const int ls = (int)(tid % ns), slot = (int)(tid / ns);
+    const int scene = scene0 + ls;
+    if (restore && slot == 0) v.ncontacts[scene] = 0;            // RigidBodyState.cpp:71
+    if (slot >= v.nbodies[scene]) return;
+    const size_t i = at(v, slot, scene);
+    if (restore) {
+        const float4 sp = v.s_pos[i];
+        const float4 p = v.pos[i];
+        v.pos[i] = make_float4(sp.x, sp.y, sp.z, p.w);
+        v.quat[i] = v.s_quat[i]; v.vel[i] = v.s_vel[i]; v.omg[i] = v.s_omg[i];
+        v.force[i] = make_float4(0.f, 0.f, 0.f, 0.f);            // RigidBodyState.cpp:35-36
+        v.wl[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        v.s_pos[i] = v.pos[i]; v.s_quat[i] = v.quat[i]; v.s_vel[i] = v.vel[i]; v.s_omg[i] = v.omg[i];
+    }
+}
+
+// dense exports of one scene for parity tests / getContacts()
+__global__ void k_export_contacts(View v, int scene, int n, int* body0, int* body1, float* p3, float* n3,
+                                  float* t3, float* b3, float* phi, float* lam3, float* J0, float* J1,
+                                  float* M0, float* M1, float* A9, float* rhs3)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const size_t ci = at(v, c, scene);
+    const int2 ids = v.cids[ci];
+    if (body0) body0[c] = ids.x;
+    if (body1) body1[c] = ids.y;
+    const float4 pp = v.cp[ci], nn = v.cn[ci];
+    if (p3) { p3[3 * c] = pp.x; p3[3 * c + 1] = pp.y; p3[3 * c + 2] = pp.z; }
+    if (n3) { n3[3 * c] = nn.x; n3[3 * c + 1] = nn.y; n3[3 * c + 2] = nn.z; }
+    if (phi) phi[c] = pp.w;
+    float4 F[CROW_FIELDS];
+    for (int f = 0; f < CROW_FIELDS; ++f) F[f] = v.crow[at_crow(v, f, c, scene)];
+    if (t3) { t3[3 * c] = F[1].x; t3[3 * c + 1] = F[1].y; t3[3 * c + 2] = F[1].z; }
+    if (b3) { b3[3 * c] = F[2].x; b3[3 * c + 1] = F[2].y; b3[3 * c + 2] = F[2].z; }
+    if (lam3) { lam3[3 * c] = F[15].x; lam3[3 * c + 1] = F[15].y; lam3[3 * c + 2] = F[15].z; }
+    const float im0 = F[0].w, im1 = F[1].w;
+    for (int r = 0; r < 3; ++r) {
+        const float4 d = F[r], a0 = F[3 + r], a1 = F[6 + r], m0 = F[9 + r], m1 = F[12 + r];
+        const int o = 18 * c + 6 * r;
+        if (J0) { J0[o] = d.x; J0[o + 1] = d.y; J0[o + 2] = d.z; J0[o + 3] = a0.x; J0[o + 4] = a0.y; J0[o + 5] = a0.z; }
+        if (J1) { J1[o] = -d.x; J1[o + 1] = -d.y; J1[o + 2] = -d.z; J1[o + 3] = a1.x; J1[o + 4] = a1.y; J1[o + 5] = a1.z; }
+        if (M0) { M0[o] = im0 * d.x; M0[o + 1] = im0 * d.y; M0[o + 2] = im0 * d.z; M0[o + 3] = m0.x; M0[o + 4] = m0.y; M0[o + 5] = m0.z; }
+        if (M1) { M1[o] = im1 * -d.x; M1[o + 1] = im1 * -d.y; M1[o + 2] = im1 * -d.z; M1[o + 3] = m1.x; M1[o + 4] = m1.y; M1[o + 5] = m1.z; }
+    }
+    if (A9) {
+        float* A = A9 + 9 * c;
+        A[0] = F[7].w; A[1] = F[10].w; A[2] = F[11].w; A[3] = F[12].w; A[4] = F[8].w; A[5] = F[13].w;
+        A[6] = F[14].w; A[7] = F[15].w; A[8] = F[9].w;
+    }
+    if (rhs3) { rhs3[3 * c] = F[4].w; rhs3[3 * c + 1] = F[5].w; rhs3[3 * c + 2] = F[6].w; }
+}
+
+__global__ void k_export_joints(View v, int scene, int n, float* J0, float* J1, float* M0, float* M1, float* rhs5)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    float4 G[JROW_FIELDS];
+    for (int f = 0; f < JROW_FIELDS; ++f) G[f] = v.jrow[at_jrow(v, f, s, scene)];
+    const V3 rr0 = mk3(G[0]), rr1 = mk3(G[1]), nxu = mk3(G[2]), nxv = mk3(G[3]);
+    const float im0 = G[0].w, im1 = G[1].w;
+    const int dim = __float_as_int(G[16].z);
+    float A0[5][6], A1[5][6];
+    for (int r = 0; r < 5; ++r) for (int k = 0; k < 6; ++k) { A0[r][k] = 0.f; A1[r][k] = 0.f; }
+    A0[0][0] = A0[1][1] = A0[2][2] = 1.f; A1[0][0] = A1[1][1] = A1[2][2] = -1.f;
+    set_hat(A0, -rr0); set_hat(A1, rr1);
+    if (dim == 5) {
+        set_row(A0[3], mk3(0.f, 0.f, 0.f), nxu); set_row(A0[4], mk3(0.f, 0.f, 0.f), nxv);
+        set_row(A1[3], mk3(0.f, 0.f, 0.f), -nxu); set_row(A1[4], mk3(0.f, 0.f, 0.f), -nxv);
+    }
+    for (int r = 0; r < 5; ++r) {
+        const bool live = r < dim;
+        for (int k = 0; k < 6; ++k) {
+            const int o = 30 * s + 6 * r + k;
+            if (J0) J0[o] = live ? A0[r][k] : 0.f;
+            if (J1) J1[o] = live ? A1[r][k] : 0.f;
+            if (M0) M0[o] = !live ? 0.f : (k < 3 ? im0 * A0[r][k] : (k == 3 ? G[4 + r].x : (k == 4 ? G[4 + r].y : G[4 + r].z)));
+            if (M1) M1[o] = !live ? 0.f : (k < 3 ? im1 * A1[r][k] : (k == 3 ? G[9 + r].x : (k == 4 ? G[9 + r].y : G[9 + r].z)));
+        }
+        if (rhs5) rhs5[5 * s + r] = live ? G[4 + r].w : 0.f;
+    }
+}
+
+__global__ void k_export_body_dyn(View v, int scene, int n, float* f3, float* tau3, float* fc3, float* tauc3, float* I9, float* Iinv9)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const size_t i = at(v, b, scene);
+    const float4 f = v.force[i], t = v.torque[i], fc = v.wl[i], tc = v.wa[i];
+    if (f3) { f3[3 * b] = f.x; f3[3 * b + 1] = f.y; f3[3 * b + 2] = f.z; }
+    if (tau3) { tau3[3 * b] = t.x; tau3[3 * b + 1] = t.y; tau3[3 * b + 2] = t.z; }
+    if (fc3) { fc3[3 * b] = fc.x; fc3[3 * b + 1] = fc.y; fc3[3 * b + 2] = fc.z; }
+    if (tauc3) { tauc3[3 * b] = tc.x; tauc3[3 * b + 1] = tc.y; tauc3[3 * b + 2] = tc.z; }
+    for (int k = 0; k < 9; ++k) {
+        if (I9) I9[9 * b + k] = v.Iw[at_b9(v, k, b, scene)];
+        if (Iinv9) Iinv9[9 * b + k] = v.Iinvw[at_b9(v, k, b, scene)];
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------
+static inline unsigned blocks_for(size_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+void launch_prepare(const View& v, cudaStream_t s) { k_prepare<<<blocks_for((size_t)v.NB * v.B, 256), 256, 0, s>>>(v); }
+void launch_detect(const View& v, cudaStream_t s) { k_detect<<<blocks_for(v.B, 128), 128, 0, s>>>(v); }
+void launch_contact_rows(const View& v, float h, cudaStream_t s) { k_contact_rows<<<blocks_for((size_t)v.NC * v.B, 128), 128, 0, s>>>(v, h); }
+void launch_joint_rows(const View& v, float h, cudaStream_t s) { if (v.NJ > 0) k_joint_rows<<<blocks_for((size_t)v.NJ * v.B, 128), 128, 0, s>>>(v, h); }
+void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s) { k_pgs<<<blocks_for(v.B, 128), 128, 0, s>>>(v, dt, iters, mu); }
+void launch_integrate(const View& v, float dt, cudaStream_t s) { k_integrate<<<blocks_for((size_t)v.NB * v.B, 256), 256, 0, s>>>(v, dt); }
+
+void launch_upload_bodies(const View& v, int scene0, int ns, int n, const int* counts, const BodyStage& st, cudaStream_t s)
+{ k_upload_bodies<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, counts, st); }
+void launch_download_state(const View& v, int scene0, int ns, int n, const BodyStage& st, cudaStream_t s)
+{ k_download_state<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, st); }
+void launch_upload_joints(const View& v, int scene0, int ns, int n, const int* counts, const JointStage& st, cudaStream_t s)
+{ k_upload_joints<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, counts, st); }
+void launch_joint_lambda(const View& v, int scene0, int ns, int n, float* lam5, int upload, cudaStream_t s)
+{ k_joint_lambda<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, lam5, upload); }
+void launch_set_ext(const View& v, int scene0, int ns, int n, const float* f3, const float* t3, cudaStream_t s)
+{ k_set_ext<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, f3, t3); }
+void launch_snapshot(const View& v, int scene0, int ns, int restore, cudaStream_t s)
+{ k_snapshot<<<blocks_for((size_t)ns * v.NB, 256), 256, 0, s>>>(v, scene0, ns, restore); }
+void launch_export_contacts(const View& v, int scene, int n, int* body0, int* body1, float* p3, float* n3, float* t3,
+                            float* b3, float* phi, float* lam3, float* J0, float* J1, float* M0, float* M1,
+                            float* A9, float* rhs3, cudaStream_t s)
+{ if (n > 0) k_export_contacts<<<blocks_for(n, 128), 128, 0, s>>>(v, scene, n, body0, body1, p3, n3, t3, b3, phi, lam3, J0, J1, M0, M1, A9, rhs3); }
+void launch_export_joints(const View& v, int scene, int n, float* J0, float* J1, float* M0, float* M1, float* rhs5, cudaStream_t s)
+{ if (n > 0) k_export_joints<<<blocks_for(n, 128), 128, 0, s>>>(v, scene, n, J0, J1, M0, M1, rhs5); }
+void launch_export_body_dyn(const View& v, int scene, int n, float* f3, float* tau3, float* fc3, float* tauc3, float* I9, float* Iinv9, cudaStream_t s)
+{ if (n > 0) k_export_body_dyn<<<blocks_for(n, 128), 128, 0, s>>>(v, scene, n, f3, tau3, fc3, tauc3, I9, Iinv9); }
+
+}  // namespace slrbs

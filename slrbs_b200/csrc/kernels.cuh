@@ -1,0 +1,37 @@
+// kernels.cuh -- launcher declarations shared by kernels.cu and c_abi.cu
+#pragma once
+#include "layout.cuh"
+
+namespace slrbs {
+
+// device-side staging views of the scene-major host arrays (all pointers are device pointers)
+struct BodyStage {
+    const float *x, *q, *v, *w, *mass, *ibody, *ibodyinv, *geom;
+    const int *fixed, *geom_type;
+};
+struct JointStage {
+    const int *type, *body0, *body1;
+    const float *r0, *q0, *r1, *q1;
+};
+
+void launch_prepare(const View& v, cudaStream_t s);
+void launch_detect(const View& v, cudaStream_t s);
+void launch_contact_rows(const View& v, float h, cudaStream_t s);
+void launch_joint_rows(const View& v, float h, cudaStream_t s);
+void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s);
+void launch_integrate(const View& v, float dt, cudaStream_t s);
+
+void launch_upload_bodies(const View& v, int scene0, int ns, int n, const int* counts, const BodyStage& st, cudaStream_t s);
+void launch_download_state(const View& v, int scene0, int ns, int n, const BodyStage& st, cudaStream_t s);
+void launch_upload_joints(const View& v, int scene0, int ns, int n, const int* counts, const JointStage& st, cudaStream_t s);
+void launch_joint_lambda(const View& v, int scene0, int ns, int n, float* lam5, int upload, cudaStream_t s);
+void launch_set_ext(const View& v, int scene0, int ns, int n, const float* f3, const float* t3, cudaStream_t s);
+void launch_snapshot(const View& v, int scene0, int ns, int restore, cudaStream_t s);
+void launch_export_contacts(const View& v, int scene, int n, int* body0, int* body1, float* p3, float* n3, float* t3,
+                            float* b3, float* phi, float* lam3, float* J0, float* J1, float* M0, float* M1,
+                            float* A9, float* rhs3, cudaStream_t s);
+void launch_export_joints(const View& v, int scene, int n, float* J0, float* J1, float* M0, float* M1, float* rhs5, cudaStream_t s);
+void launch_export_body_dyn(const View& v, int scene, int n, float* f3, float* tau3, float* fc3, float* tauc3,
+                            float* I9, float* Iinv9, cudaStream_t s);
+
+}  // namespace slrbs

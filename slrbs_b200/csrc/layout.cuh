@@ -1,0 +1,76 @@
+// layout.cuh -- device data layout of a batch of scenes in HBM.
+//
+// Every per-item array is "slot-major, scene-minor": element (slot i, scene s) lives at
+// i * B + s, so the 32 lanes of a warp that work on 32 consecutive scenes read one
+// contiguous 128 B / 512 B segment per field (coalesced float / float4 streams), whatever
+// the item index is.  Multi-field records (constraint rows) add a field index in front:
+// (f * CAP + i) * B + s.  With B = 1 this degenerates to plain SoA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace slrbs {
+
+enum { GEOM_SPHERE = 0, GEOM_BOX = 1, GEOM_PLANE = 2, GEOM_CYLINDER = 3 };
+enum { FLAG_TYPE_MASK = 0xF, FLAG_FIXED = 0x10 };
+enum { CROW_FIELDS = 16, JROW_FIELDS = 17 };
+enum { BODY_FIXED_BIT = (int)0x80000000 };
+
+// Contact row record (CROW_FIELDS float4 per contact; see k_contact_rows):
+//  0 n   | im0      4 a0t | rhs0     8 a1b | A11     12 m1n | A10
+//  1 t   | im1      5 a0b | rhs1     9 m0n | A22     13 m1t | A12
+//  2 b   | body0    6 a1n | rhs2    10 m0t | A01     14 m1b | A20
+//  3 a0n | body1    7 a1t | A00     11 m0b | A02     15 lam | A21
+// d in {n,t,b}: J0 row = [d, a0d], J1 row = [-d, a1d], J0Minv row = [im0*d, m0d],
+// J1Minv row = [-im1*d, m1d]; body ids carry BODY_FIXED_BIT when the body is fixed.
+//
+// Joint row record (JROW_FIELDS float4 per joint; see k_joint_rows):
+//  0 rr0 | im0     2 nxu | body0     4..8  J0Minv angular rows 0..4 | rhs[r]
+//  1 rr1 | im1     3 nxv | body1     9..13 J1Minv angular rows 0..4 | 1/D[r]
+//  14 (L10 L20 L21 L30)  15 (L31 L32 L40 L41)  16 (L42 L43 dim -)
+// J0 = [I hat(-rr0); 0 nxu; 0 nxv], J1 = [-I hat(rr1); 0 -nxu; 0 -nxv] (Hinge.cpp:50-57).
+
+struct View {
+    int B, NB, NJ, NC;
+    int *nbodies, *njoints, *ncontacts;   // [B]
+    int *overflow;                        // [1] set when a scene exceeded NC
+    unsigned long long *visit_counters;   // [2] contact visits, joint visits (profiling)
+    int profiling;
+    // bodies, [NB][B]
+    float4 *pos;        // x y z | mass
+    float4 *quat;       // x y z w
+    float4 *vel;        // xdot | -
+    float4 *omg;        // omega | -
+    int    *flags;      // geometry type | FLAG_FIXED
+    float4 *geomA;      // sphere r,-,-,- | box dim | cylinder h,r | plane p
+    float4 *geomB;      // plane n
+    float  *ibody;      // [9][NB][B]
+    float  *ibodyinv;   // [9][NB][B]
+    float4 *cproxy;     // x y z | sphere radius (0 for other shapes): narrow-phase inner-loop stream
+    float4 *force;      // f | -
+    float4 *torque;     // tau | -
+    float4 *extf, *extt;
+    int     has_ext;
+    float  *Iw;         // [9][NB][B] world inertia
+    float  *Iinvw;      // [9][NB][B]
+    float4 *wl, *wa;    // PGS body accumulators sum(J^T lambda); after solve: fc, tauc
+    float4 *s_pos, *s_quat, *s_vel, *s_omg;   // RigidBodySystemState snapshot
+    // joints, [NJ][B]
+    int4   *jdef;       // type, body0, body1, dim
+    float4 *jr0, *jq0, *jr1, *jq1;
+    float4 *jlam;       // lambda 0..3
+    float  *jlam4;      // lambda 4
+    float4 *jrow;       // [JROW_FIELDS][NJ][B]
+    // contacts, [NC][B]
+    int2   *cids;       // body0, body1 (role ordered: sphere/box, cylinder/plane)
+    float4 *cp;         // p | pene
+    float4 *cn;         // n | -
+    float4 *crow;       // [CROW_FIELDS][NC][B]
+};
+
+__host__ __device__ __forceinline__ size_t at(const View& v, int slot, int scene) { return (size_t)slot * v.B + scene; }
+__host__ __device__ __forceinline__ size_t at_b9(const View& v, int k, int slot, int scene) { return ((size_t)k * v.NB + slot) * v.B + scene; }
+__host__ __device__ __forceinline__ size_t at_crow(const View& v, int f, int slot, int scene) { return ((size_t)f * v.NC + slot) * v.B + scene; }
+__host__ __device__ __forceinline__ size_t at_jrow(const View& v, int f, int slot, int scene) { return ((size_t)f * v.NJ + slot) * v.B + scene; }
+
+}  // namespace slrbs

@@ -67,6 +67,7 @@ def lib():
     L.orc_get_joints.argtypes = [vp, ip, ip, ip, fp, fp, fp, fp]
     L.orc_get_joint_rows.argtypes = [vp, fp, fp, fp, fp, fp, fp]
     L.orc_set_joint_lambda.argtypes = [vp, fp]
+    L.orc_get_solver_blocks.argtypes = [vp, C.c_float, fp, fp, fp, fp]
     for name in ("orc_scene_marble_box", "orc_scene_sphere_on_box", "orc_scene_swinging_boxes",
                  "orc_scene_cylinder_on_plane", "orc_scene_car"):
         getattr(L, name).argtypes = [vp]
@@ -246,6 +247,13 @@ class Oracle:
         self.L.orc_get_joint_rows(self.h, _f(out["J0"]), _f(out["J1"]), _f(out["J0Minv"]), _f(out["J1Minv"]),
                                   _f(out["phi"]), _f(out["lam"]))
         return out
+
+    def solver_blocks(self, dt):
+        m, nj = self.n_contacts, self.n_joints
+        A = np.zeros((m, 3, 3), np.float32); rhs = np.zeros((m, 3), np.float32)
+        Aj = np.zeros((nj, 5, 5), np.float32); rhsj = np.zeros((nj, 5), np.float32)
+        self.L.orc_get_solver_blocks(self.h, float(dt), _f(A), _f(rhs), _f(Aj), _f(rhsj))
+        return dict(A=A, rhs=rhs, Aj=Aj, rhsj=rhsj)
 
     def set_joint_lambda(self, lam):
         a = np.ascontiguousarray(np.asarray(lam, np.float32).reshape(self.n_joints, 5))
