@@ -23,6 +23,7 @@ SYMBOLS = [
     "slrbs_download_contacts", "slrbs_download_contact_rows", "slrbs_download_joint_rows",
     "slrbs_download_joint_lambda", "slrbs_upload_joint_lambda", "slrbs_download_body_dyn",
     "slrbs_save_state", "slrbs_restore_state", "slrbs_profile_enable", "slrbs_profile_read",
+    "slrbs_timer_start", "slrbs_timer_stop",
 ]
 
 
@@ -55,7 +56,7 @@ def load_library():
     L.slrbs_upload_joints.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, fp, fp, fp, fp]
     L.slrbs_upload_state.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]
     L.slrbs_download_state.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]
-    L.slrbs_set_external_forces.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp]
+    L.slrbs_set_external_forces.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_int]
     L.slrbs_step.argtypes = [vp, C.c_float, C.c_int]
     L.slrbs_sync.argtypes = [vp]
     L.slrbs_stage_prepare.argtypes = [vp]
@@ -73,6 +74,8 @@ def load_library():
     L.slrbs_save_state.argtypes = [vp]
     L.slrbs_restore_state.argtypes = [vp, C.c_int, C.c_int]
     L.slrbs_profile_enable.argtypes = [vp, C.c_int]
+    L.slrbs_timer_start.argtypes = [vp]
+    L.slrbs_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.slrbs_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     _LIB = L
@@ -193,12 +196,12 @@ class Context:
         self._ck(self.L.slrbs_download_state(self.h, scene0, ns, n, _f(x), _f(q), _f(v), _f(w)))
         return dict(x=x, q=q, v=v, w=w)
 
-    def set_external_forces(self, f=None, tau=None, scene0=0, n_scenes=None, n_bodies=None):
+    def set_external_forces(self, f=None, tau=None, scene0=0, n_scenes=None, n_bodies=None, absolute=False):
         ns = n_scenes or (self.n_scenes - scene0)
         n = n_bodies or self.n_bodies
         a = [None if t is None else np.ascontiguousarray(np.broadcast_to(np.asarray(t, np.float32).reshape(-1, n, 3), (ns, n, 3)))
              for t in (f, tau)]
-        self._ck(self.L.slrbs_set_external_forces(self.h, scene0, ns, n, _f(a[0]), _f(a[1])))
+        self._ck(self.L.slrbs_set_external_forces(self.h, scene0, ns, n, _f(a[0]), _f(a[1]), int(bool(absolute))))
 
     # -- stepping ------------------------------------------------------------------
     def step(self, dt=0.01, n=1):
@@ -277,6 +280,14 @@ class Context:
     # -- measurement ---------------------------------------------------------------
     def profile_enable(self, on=True):
         self._ck(self.L.slrbs_profile_enable(self.h, int(bool(on))))
+
+    def timer_start(self):
+        self._ck(self.L.slrbs_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.L.slrbs_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def profile_read(self, reset=True):
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()

@@ -39,6 +39,7 @@ struct slrbs_ctx {
     int profiling = 0;
     std::vector<cudaEvent_t> ev; size_t ev_used = 0;
     double solve_ms = 0.0; int64_t solve_launches = 0, total_launches = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 namespace {
@@ -182,6 +183,8 @@ void slrbs_destroy(slrbs_ctx* c)
     if (c->stage) cudaFree(c->stage);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -289,8 +292,9 @@ int slrbs_download_state(slrbs_ctx* c, int scene0, int ns, int n, float* x3, flo
     return 0;
 }
 
-int slrbs_set_external_forces(slrbs_ctx* c, int scene0, int ns, int n, const float* f3, const float* tau3)
+int slrbs_set_external_forces(slrbs_ctx* c, int scene0, int ns, int n, const float* f3, const float* tau3, int mode)
 {
+    if (mode != 0 && mode != 1) return fail(SLRBS_E_ARG, "slrbs_set_external_forces: mode must be 0 or 1");
     if (!range_ok(c, scene0, ns) || n <= 0 || n > c->v.NB) return fail(SLRBS_E_ARG, "slrbs_set_external_forces: bad range");
     CU(cudaSetDevice(c->device));
     const size_t m = (size_t)ns * n;
@@ -300,7 +304,7 @@ int slrbs_set_external_forces(slrbs_ctx* c, int scene0, int ns, int n, const flo
     if ((r = stage_in(c, f3, 3 * m, &df)) || (r = stage_in(c, tau3, 3 * m, &dt))) return r;
     launch_set_ext(c->v, scene0, ns, n, df, dt, c->stream);
     if ((r = check_launch(c))) return r;
-    if (f3 || tau3) c->v.has_ext = 1;
+    if (f3 || tau3) c->v.has_ext = 1 + mode;
     else if (scene0 == 0 && ns == c->v.B) c->v.has_ext = 0;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -510,6 +514,25 @@ int slrbs_profile_enable(slrbs_ctx* c, int on)
     if (!on) { int r = fold_events(c); if (r) return r; }
     c->profiling = on ? 1 : 0;
     c->v.profiling = c->profiling;
+    return 0;
+}
+
+int slrbs_timer_start(slrbs_ctx* c)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    if (!c->t0) { CU(cudaEventCreate(&c->t0)); CU(cudaEventCreate(&c->t1)); }
+    CU(cudaEventRecord(c->t0, c->stream));
+    return 0;
+}
+
+int slrbs_timer_stop(slrbs_ctx* c, float* ms)
+{
+    if (!c || !ms || !c->t0) return fail(SLRBS_E_ARG, "slrbs_timer_stop: timer not started");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->t1, c->stream));
+    CU(cudaEventSynchronize(c->t1));
+    CU(cudaEventElapsedTime(ms, c->t0, c->t1));
     return 0;
 }
 

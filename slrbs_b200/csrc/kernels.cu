@@ -48,9 +48,12 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
     // b->f = b->mass * Vector3f(0, -9.81, 0); tau = 0  (RigidBodySystem.cpp:60-61)
     V3 f = mass * mk3(0.f, -9.81f, 0.f);
     V3 tau = mk3(0.f, 0.f, 0.f);
-    if (v.has_ext) {                                             // pre-step callback contribution (:70-73)
+    if (v.has_ext == 1) {                                        // pre-step callback contribution (:70-73)
         f = f + mk3(v.extf[i]);
         tau = tau + mk3(v.extt[i]);
+    } else if (v.has_ext == 2) {                                 // callback result given absolutely
+        f = mk3(v.extf[i]);
+        tau = mk3(v.extt[i]);
     }
     v.force[i] = mk4(f, 0.f);
     v.torque[i] = mk4(tau, 0.f);

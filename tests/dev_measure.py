@@ -1,0 +1,34 @@
+"""Developer measurement tool (not the bench): batched copies of an oracle-built scene on the GPU."""
+import argparse, time, sys, os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from oracle_lib import Oracle
+from gpu_helpers import scene_arrays
+from slrbs_b200 import Context
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scene", default="marble_box"); ap.add_argument("--B", type=int, default=4096)
+ap.add_argument("--nc", type=int, default=1024); ap.add_argument("--settle", type=int, default=200)
+ap.add_argument("--steps", type=int, default=20); ap.add_argument("--k", type=int, default=8)
+a = ap.parse_args()
+o = Oracle(a.scene, k=a.k) if a.scene == "sphere_stack" else Oracle(a.scene)
+s = scene_arrays(o)
+B, nb, nj = a.B, o.n_bodies, o.n_joints
+ctx = Context(B, nb, nj, a.nc)
+rng = np.random.default_rng(1234)
+x = np.broadcast_to(s["x"], (B, nb, 3)).copy()
+dyn = s["fixed"] == 0
+x[:, dyn, 0] += rng.uniform(-0.01, 0.01, (B, dyn.sum())).astype(np.float32)
+x[:, dyn, 2] += rng.uniform(-0.01, 0.01, (B, dyn.sum())).astype(np.float32)
+ctx.upload_bodies(x, s["q"], s["v"], s["w"], s["mass"], s["ibody"], s["ibodyinv"], s["fixed"], s["geom_type"], s["geom"])
+if nj: ctx.upload_joints(s["jtype"], s["jb0"], s["jb1"], s["r0"], s["q0"], s["r1"], s["q1"])
+t0 = time.time(); ctx.step(0.01, a.settle); ctx.sync(); t1 = time.time()
+print(f"settle {a.settle} steps: {t1-t0:.3f}s  contacts/scene mean {ctx.contact_counts().mean():.1f} max {ctx.contact_counts().max()}")
+ctx.profile_enable(True); ctx.profile_read(True)
+t0 = time.time(); ctx.step(0.01, a.steps); ctx.sync(); t1 = time.time()
+p = ctx.profile_read(True)
+dt = (t1 - t0) / a.steps
+alg = 464 * p["contact_visits"] + 744 * p["joint_visits"]
+print(f"{a.scene} B={B}: {dt*1e3:.3f} ms/step  {B*nb/dt/1e6:.1f} M body-steps/s | pgs {p['solve_ms']/p['solve_launches']:.3f} ms/launch "
+      f"share {p['solve_ms']/1e3/(t1-t0):.2f}  alg {alg/ (p['solve_ms']/1e3)/1e9:.1f} GB/s  visits/launch c={p['contact_visits']/p['solve_launches']:.0f} j={p['joint_visits']/p['solve_launches']:.0f}")
