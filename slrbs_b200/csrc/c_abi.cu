@@ -139,8 +139,8 @@ const char* slrbs_version(void) { return "slrbs_b200 0.1 (sm_100a)"; }
 
 int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int max_joints, int max_contacts)
 {
-    if (!out || n_scenes <= 0 || max_bodies <= 0 || max_joints < 0 || max_contacts < 0)
-        return fail(SLRBS_E_ARG, "slrbs_create: bad sizes");
+    if (!out || n_scenes <= 0 || max_bodies <= 0 || max_bodies > MAX_BODIES_PER_SCENE || max_joints < 0 || max_contacts < 0)
+        return fail(SLRBS_E_ARG, "slrbs_create: bad sizes (max_bodies must be 1..32767)");
     *out = nullptr;
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -156,6 +156,7 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     View& v = c->v;
     v.B = n_scenes; v.NB = max_bodies; v.NJ = max_joints; v.NC = max_contacts;
     const size_t nb = (size_t)v.NB * v.B, nj = (size_t)v.NJ * v.B, nc = (size_t)v.NC * v.B;
+    const size_t bpad = ((size_t)v.B + 31) / 32 * 32;      // row records are blocked 32 scenes at a time
     int r = 0;
 #define A(p, n) if ((r = dalloc(c, &p, n))) { slrbs_destroy(c); return r; }
     A(v.nbodies, v.B) A(v.njoints, v.B) A(v.ncontacts, v.B) A(v.overflow, 1) A(v.visit_counters, 2)
@@ -164,8 +165,8 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     A(v.extf, nb) A(v.extt, nb) A(v.Iw, 9 * nb) A(v.Iinvw, 9 * nb) A(v.wl, nb) A(v.wa, nb)
     A(v.s_pos, nb) A(v.s_quat, nb) A(v.s_vel, nb) A(v.s_omg, nb)
     A(v.jdef, nj) A(v.jr0, nj) A(v.jq0, nj) A(v.jr1, nj) A(v.jq1, nj) A(v.jlam, nj) A(v.jlam4, nj)
-    A(v.jrow, (size_t)JROW_FIELDS * nj)
-    A(v.cids, nc) A(v.cp, nc) A(v.cn, nc) A(v.crow, (size_t)CROW_FIELDS * nc)
+    A(v.jrow, (size_t)JROW_FIELDS * v.NJ * bpad)
+    A(v.cids, nc) A(v.cp, nc) A(v.cn, nc) A(v.crow, (size_t)CROW_FIELDS * v.NC * bpad)
 #undef A
     CU(cudaMallocHost((void**)&c->h_flag, sizeof(int)));
     *c->h_flag = 0;

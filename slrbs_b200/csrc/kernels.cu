@@ -6,7 +6,7 @@
 //
 // Kernel            replaces (reference file:line)                                   mapping
 // k_prepare         RigidBodySystem.cpp:58-65, RigidBody.cpp:78-89                    thread / (body, scene)
-// k_detect          CollisionDetect.cpp:27-76,102-274, Contact.cpp:11-26              thread / scene (ordered emit)
+// k_detect_warp     CollisionDetect.cpp:27-76,102-274, Contact.cpp:11-26              warp / scene (ballot-ordered emit)
 // k_contact_rows    Contact.cpp:33-94, SolverBoxPGS.cpp:27-44,165-189,206-211         thread / (contact, scene)
 // k_joint_rows      Hinge.cpp:33-63, Spherical.cpp:34-52, SolverBoxPGS.cpp:134-163    thread / (joint, scene)
 // k_pgs             SolverBoxPGS.cpp:217-248, RigidBodySystem.cpp:185-220             thread / scene (sequential rows)
@@ -78,22 +78,16 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
 }
 
 // ------------------------------------------------------------------------------------
-// K3  narrow phase, one thread per scene walking the reference's i<j pair order
+// K3  narrow phase: one WARP per scene. The scene's body proxies are staged in shared memory;
+// for each i the lanes test 32 consecutive j > i, and contacts are appended in the reference's
+// lexicographic (i, j) order by a warp-ballot prefix sum (up to 4 per pair, fixed A,B,C,D order).
 // ------------------------------------------------------------------------------------
-struct Emit {
-    const View& v; int scene; int count;
-    __device__ __forceinline__ void put(int b0, int b1, const V3& p, const V3& n, float pene)
-    {
-        if (count < v.NC) {
-            const size_t c = at(v, count, scene);
-            v.cids[c] = make_int2(b0, b1);
-            v.cp[c] = mk4(p, pene);
-            v.cn[c] = mk4(n, 0.f);
-        } else {
-            *v.overflow = 1;
-        }
-        ++count;
-    }
+struct PairOut {
+    int b0, b1, cnt;        // role-ordered body indices (sphere/box, cylinder/plane), contacts of this pair
+    V3 n;
+    V3 p[4];
+    float phi[4];
+    __device__ __forceinline__ void add(const V3& pp, float f) { p[cnt] = pp; phi[cnt] = f; ++cnt; }
 };
 
 __device__ __forceinline__ float plane_dist(const V3& p, const V3& plane_p, const V3& plane_n)
@@ -101,14 +95,28 @@ __device__ __forceinline__ float plane_dist(const V3& p, const V3& plane_p, cons
     return dot(p - plane_p, plane_n);                            // CollisionDetect.cpp:12-17
 }
 
-// CollisionDetect.cpp:125-150 (body0 = sphere, body1 = box)
-__device__ __noinline__ void sphere_box(Emit& e, int is, int ib, const V3& xs, float r)
+// CollisionDetect.cpp:102-123
+__device__ __forceinline__ void sphere_sphere(PairOut& o, int i0, int i1, const float4& c0, const float4& c1)
 {
-    const View& v = e.v;
-    const size_t bi = at(v, ib, e.scene);
-    const V3 xb = mk3(v.pos[bi]);
-    const Q4 qb = mkq(v.quat[bi]);
-    const float4 dim = v.geomA[bi];
+    const V3 x0 = mk3(c0), x1 = mk3(c1);
+    const V3 vec = x0 - x1;
+    const float rsum = (c0.w + c1.w);
+    const float dist = norm(vec);
+    if (dist < (rsum + 1e-3f)) {
+        o.b0 = i0; o.b1 = i1;
+        o.n = vec / dist;
+        o.add(0.5f * ((x0 - c0.w * o.n) + (x1 + c1.w * o.n)), fminf(0.0f, dist - rsum));
+    }
+}
+
+// CollisionDetect.cpp:125-150 (body0 = sphere, body1 = box)
+__device__ __noinline__ void sphere_box(PairOut& o, const float4* __restrict__ quat, const float4* __restrict__ geomA, size_t bi,
+                                       int is, int ib, const float4& cs, const float4& cb)
+{
+    const V3 xs = mk3(cs), xb = mk3(cb);
+    const float r = cs.w;
+    const Q4 qb = mkq(__ldg(&quat[bi]));
+    const float4 dim = __ldg(&geomA[bi]);
     const V3 cl = rotate(qinverse(qb), xs - xb);
     V3 q;
     q.x = cl.x; if (q.x < (-dim.x / 2.0f)) q.x = -dim.x / 2.0f; else if (q.x > (dim.x / 2.0f)) q.x = dim.x / 2.0f;
@@ -117,42 +125,42 @@ __device__ __noinline__ void sphere_box(Emit& e, int is, int ib, const V3& xs, f
     const V3 dx = cl - q;
     const float dist = norm(dx);
     if (dist < (r + 1e-3f)) {
-        const V3 n = rotate(qb, dx / dist);
-        const V3 p = rotate(qb, q) + xb;
-        e.put(is, ib, p, n, fminf(0.0f, dist - r));
+        o.b0 = is; o.b1 = ib;
+        o.n = rotate(qb, dx / dist);
+        o.add(rotate(qb, q) + xb, fminf(0.0f, dist - r));
     }
 }
 
 // CollisionDetect.cpp:152-274 (body0 = cylinder, body1 = plane)
-__device__ __noinline__ void cylinder_plane(Emit& e, int ic, int ip)
+__device__ __noinline__ void cylinder_plane(PairOut& o, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+                                           const float4* __restrict__ geomB, size_t ci, size_t pi, int ic, int ip,
+                                           const float4& cc, const float4& cpl)
 {
-    const View& v = e.v;
-    const size_t ci = at(v, ic, e.scene), pi = at(v, ip, e.scene);
-    const V3 xc = mk3(v.pos[ci]);
-    const Q4 qc = mkq(v.quat[ci]);
-    const float4 cg = v.geomA[ci];
+    const V3 xc = mk3(cc), xp = mk3(cpl);
+    const Q4 qc = mkq(__ldg(&quat[ci]));
+    const float4 cg = __ldg(&geomA[ci]);
     const float h = cg.x, r = cg.y;
-    const V3 xp = mk3(v.pos[pi]);
-    const Q4 qp = mkq(v.quat[pi]);
+    const Q4 qp = mkq(__ldg(&quat[pi]));
     const V3 cyldir = rotate(qc, mk3(0.f, 1.f, 0.f));
-    const V3 planen = rotate(qp, mk3(v.geomB[pi]));
-    const V3 planep = rotate(qp, mk3(v.geomA[pi])) + xp;
+    const V3 planen = rotate(qp, mk3(__ldg(&geomB[pi])));
+    const V3 planep = rotate(qp, mk3(__ldg(&geomA[pi]))) + xp;
     const float dp = dot(cyldir, planen);
+    o.b0 = ic; o.b1 = ip; o.n = planen;
 
     if (fabsf(dp) > 0.995f) {                                    // :164 cap face on the plane
         const V3 w = (dp < 0.0f) ? cyldir : -cyldir;
         V3 u = (fabsf(dot(w, mk3(1.f, 0.f, 0.f))) > 0.01f) ? cross(w, mk3(1.f, 0.f, 0.f)) : cross(w, mk3(0.f, 0.f, 1.f));
         u = normalized(u);
-        V3 vv = normalized(cross(w, u));
+        const V3 vv = normalized(cross(w, u));
         const V3 a = xc + (0.5f * h) * w;
         if (plane_dist(a, planep, planen) < 1e-3f) {
             const V3 pA = a + r * u, pB = a - r * u, pC = a + r * vv, pD = a - r * vv;
             const float fA = plane_dist(pA, planep, planen), fB = plane_dist(pB, planep, planen);
             const float fC = plane_dist(pC, planep, planen), fD = plane_dist(pD, planep, planen);
-            if (fA < 1e-3f) e.put(ic, ip, pA, planen, fminf(0.0f, fA));
-            if (fB < 1e-3f) e.put(ic, ip, pB, planen, fminf(0.0f, fB));
-            if (fC < 1e-3f) e.put(ic, ip, pC, planen, fminf(0.0f, fC));
-            if (fD < 1e-3f) e.put(ic, ip, pD, planen, fminf(0.0f, fD));
+            if (fA < 1e-3f) o.add(pA, fminf(0.0f, fA));
+            if (fB < 1e-3f) o.add(pB, fminf(0.0f, fB));
+            if (fC < 1e-3f) o.add(pC, fminf(0.0f, fC));
+            if (fD < 1e-3f) o.add(pD, fminf(0.0f, fD));
         }
     } else if (fabsf(dp) < 1e-2f) {                              // :215 lying on its side
         V3 u = cross(cross(planen, cyldir), cyldir);
@@ -163,8 +171,8 @@ __device__ __noinline__ void cylinder_plane(Emit& e, int ic, int ip)
             const V3 hw = (0.5f * h) * cyldir, ru = r * u;
             const V3 pA = (xc + hw) + ru, pB = (xc - hw) + ru;
             const float fA = plane_dist(pA, planep, planen), fB = plane_dist(pB, planep, planen);
-            if (fA < 1e-3f) e.put(ic, ip, pA, planen, fminf(0.0f, fA));
-            if (fB < 1e-3f) e.put(ic, ip, pB, planen, fminf(0.0f, fB));
+            if (fA < 1e-3f) o.add(pA, fminf(0.0f, fA));
+            if (fB < 1e-3f) o.add(pB, fminf(0.0f, fB));
         }
     } else {                                                     // :241 single lowest rim point
         V3 w = (dp < 0.0f) ? cyldir : -cyldir;
@@ -174,51 +182,110 @@ __device__ __noinline__ void cylinder_plane(Emit& e, int ic, int ip)
         u = normalized(u);
         const V3 a = (xc + (0.5f * h) * w) + r * u;
         const float dist = plane_dist(a, planep, planen);
-        if (dist < 1e-3f) e.put(ic, ip, a, planen, fminf(0.0f, dist));
+        if (dist < 1e-3f) o.add(a, fminf(0.0f, dist));
     }
 }
 
-__global__ void __launch_bounds__(128) k_detect(View v)
+// the reference's dispatch chain for the ordered pair (i < j), CollisionDetect.cpp:41-73
+__device__ __forceinline__ void test_pair(PairOut& o, const View& v, int scene, int i, int j,
+                                          const float4& ci, int fi, const float4& cj, int fj)
+{
+    o.cnt = 0;
+    if ((fi & fj) & FLAG_FIXED) return;
+    const int ti = fi & FLAG_TYPE_MASK, tj = fj & FLAG_TYPE_MASK;
+    if (ti == GEOM_SPHERE && tj == GEOM_SPHERE)          sphere_sphere(o, i, j, ci, cj);
+    else if (ti == GEOM_SPHERE && tj == GEOM_BOX)        sphere_box(o, v.quat, v.geomA, at(v, j, scene), i, j, ci, cj);
+    else if (tj == GEOM_SPHERE && ti == GEOM_BOX)        sphere_box(o, v.quat, v.geomA, at(v, i, scene), j, i, cj, ci);
+    else if (ti == GEOM_CYLINDER && tj == GEOM_PLANE)    cylinder_plane(o, v.quat, v.geomA, v.geomB, at(v, i, scene), at(v, j, scene), i, j, ci, cj);
+    else if (tj == GEOM_CYLINDER && ti == GEOM_PLANE)    cylinder_plane(o, v.quat, v.geomA, v.geomB, at(v, j, scene), at(v, i, scene), j, i, cj, ci);
+}
+
+__device__ __forceinline__ void write_contacts(const View& v, int scene, int base, const PairOut& o)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < o.cnt) {
+            if (base + k < v.NC) {
+                const size_t c = at(v, base + k, scene);
+                v.cids[c] = make_int2(o.b0, o.b1);
+                v.cp[c] = mk4(o.p[k], o.phi[k]);
+                v.cn[c] = mk4(o.n, 0.f);
+            } else {
+                *v.overflow = 1;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta)
+{
+    extern __shared__ float4 smem4[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int scene = blockIdx.x * warps_per_cta + warp;
+    if (scene >= v.B) return;
+    float4* sp = smem4 + (size_t)warp * v.NB;                                 // proxies of this warp's scene
+    int* sf = reinterpret_cast<int*>(smem4 + (size_t)warps_per_cta * v.NB) + (size_t)warp * v.NB;
+    const int n = v.nbodies[scene];
+    for (int b = lane; b < n; b += 32) {
+        const size_t i = at(v, b, scene);
+        sp[b] = v.cproxy[i];
+        sf[b] = v.flags[i];
+    }
+    __syncwarp();
+    int count = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = 0; i < n; ++i) {
+        const float4 ci = sp[i];
+        const int fi = sf[i];
+        for (int j0 = i + 1; j0 < n; j0 += 32) {
+            const int j = j0 + lane;
+            PairOut o;
+            o.cnt = 0;
+            if (j < n) test_pair(o, v, scene, i, j, ci, fi, sp[j], sf[j]);
+            const unsigned any = __ballot_sync(0xffffffffu, o.cnt > 0);
+            if (any == 0) continue;
+            const unsigned multi = __ballot_sync(0xffffffffu, o.cnt > 1);
+            int before, total;
+            if (multi == 0) {                                    // common case: at most one contact per pair
+                before = __popc(any & lt);
+                total = __popc(any);
+            } else {                                             // up to 4 per pair: shuffle prefix sum
+                int incl = o.cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                before = incl - o.cnt;
+                total = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            write_contacts(v, scene, count + before, o);
+            count += total;
+        }
+    }
+    if (lane == 0) v.ncontacts[scene] = count < v.NC ? count : v.NC;
+}
+
+// fallback for scenes whose proxies do not fit in shared memory: one thread per scene
+__global__ void __launch_bounds__(128) k_detect_serial(View v)
 {
     const int scene = blockIdx.x * blockDim.x + threadIdx.x;
     if (scene >= v.B) return;
     const int n = v.nbodies[scene];
-    Emit e{ v, scene, 0 };
+    int count = 0;
     for (int i = 0; i < n; ++i) {
         const size_t ii = at(v, i, scene);
         const float4 ci = v.cproxy[ii];
         const int fi = v.flags[ii];
-        const int ti = fi & FLAG_TYPE_MASK;
-        const V3 xi = mk3(ci);
         for (int j = i + 1; j < n; ++j) {
             const size_t jj = at(v, j, scene);
-            const int fj = v.flags[jj];
-            if ((fi & fj) & FLAG_FIXED) continue;                // CollisionDetect.cpp:41-42
-            const int tj = fj & FLAG_TYPE_MASK;
-            if (ti == GEOM_SPHERE && tj == GEOM_SPHERE) {        // :102-123
-                const float4 cj = v.cproxy[jj];
-                const V3 xj = mk3(cj);
-                const V3 vec = xi - xj;
-                const float rsum = (ci.w + cj.w);
-                const float dist = norm(vec);
-                if (dist < (rsum + 1e-3f)) {
-                    const V3 nn = vec / dist;
-                    const V3 p = 0.5f * ((xi - ci.w * nn) + (xj + cj.w * nn));
-                    e.put(i, j, p, nn, fminf(0.0f, dist - rsum));
-                }
-            } else if (ti == GEOM_SPHERE && tj == GEOM_BOX) {
-                sphere_box(e, i, j, xi, ci.w);
-            } else if (tj == GEOM_SPHERE && ti == GEOM_BOX) {
-                const float4 cj = v.cproxy[jj];
-                sphere_box(e, j, i, mk3(cj), cj.w);
-            } else if (ti == GEOM_CYLINDER && tj == GEOM_PLANE) {
-                cylinder_plane(e, i, j);
-            } else if (tj == GEOM_CYLINDER && ti == GEOM_PLANE) {
-                cylinder_plane(e, j, i);
-            }
+            PairOut o;
+            test_pair(o, v, scene, i, j, ci, fi, v.cproxy[jj], v.flags[jj]);
+            write_contacts(v, scene, count, o);
+            count += o.cnt;
         }
     }
-    v.ncontacts[scene] = e.count < v.NC ? e.count : v.NC;
+    v.ncontacts[scene] = count < v.NC ? count : v.NC;
 }
 
 // ------------------------------------------------------------------------------------
@@ -318,26 +385,25 @@ __global__ void __launch_bounds__(128) k_contact_rows(View v, float h)
         if (!b1.fixed) { b = mult_and_sub_row(b, M1[r], b1.f, b1.tau, h); b = mult_and_sub_row(b, J1[r], b1.xdot, b1.omega, 1.0f); }
         rhs[r] = b;
     }
-    const int id0 = ids.x | (b0.fixed ? BODY_FIXED_BIT : 0);
-    const int id1 = ids.y | (b1.fixed ? BODY_FIXED_BIT : 0);
+    const int packed = (ids.x | (b0.fixed ? 0x8000 : 0)) | ((ids.y | (b1.fixed ? 0x8000 : 0)) << 16);
     float4* R = v.crow;
 #define CROW(f) R[at_crow(v, f, slot, scene)]
     CROW(0)  = mk4(n, 1.0f / b0.mass);
     CROW(1)  = mk4(t, 1.0f / b1.mass);
-    CROW(2)  = mk4(bb, __int_as_float(id0));
-    CROW(3)  = make_float4(J0[0][3], J0[0][4], J0[0][5], __int_as_float(id1));
-    CROW(4)  = make_float4(J0[1][3], J0[1][4], J0[1][5], rhs[0]);
-    CROW(5)  = make_float4(J0[2][3], J0[2][4], J0[2][5], rhs[1]);
-    CROW(6)  = make_float4(J1[0][3], J1[0][4], J1[0][5], rhs[2]);
-    CROW(7)  = make_float4(J1[1][3], J1[1][4], J1[1][5], A[0][0]);
-    CROW(8)  = make_float4(J1[2][3], J1[2][4], J1[2][5], A[1][1]);
-    CROW(9)  = make_float4(M0[0][3], M0[0][4], M0[0][5], A[2][2]);
-    CROW(10) = make_float4(M0[1][3], M0[1][4], M0[1][5], A[0][1]);
-    CROW(11) = make_float4(M0[2][3], M0[2][4], M0[2][5], A[0][2]);
-    CROW(12) = make_float4(M1[0][3], M1[0][4], M1[0][5], A[1][0]);
-    CROW(13) = make_float4(M1[1][3], M1[1][4], M1[1][5], A[1][2]);
-    CROW(14) = make_float4(M1[2][3], M1[2][4], M1[2][5], A[2][0]);
-    CROW(15) = make_float4(0.f, 0.f, 0.f, A[2][1]);          // lambda = 0 (Contact.cpp:66, SolverBoxPGS.cpp:210)
+    CROW(2)  = mk4(bb, __int_as_float(packed));
+    CROW(3)  = make_float4(J0[0][3], J0[0][4], J0[0][5], rhs[0]);
+    CROW(4)  = make_float4(J0[1][3], J0[1][4], J0[1][5], rhs[1]);
+    CROW(5)  = make_float4(J0[2][3], J0[2][4], J0[2][5], rhs[2]);
+    CROW(6)  = make_float4(J1[0][3], J1[0][4], J1[0][5], A[0][0]);
+    CROW(7)  = make_float4(J1[1][3], J1[1][4], J1[1][5], A[1][1]);
+    CROW(8)  = make_float4(J1[2][3], J1[2][4], J1[2][5], A[2][2]);
+    CROW(9)  = make_float4(M0[0][3], M0[0][4], M0[0][5], A[0][1]);
+    CROW(10) = make_float4(M0[1][3], M0[1][4], M0[1][5], A[0][2]);
+    CROW(11) = make_float4(M0[2][3], M0[2][4], M0[2][5], A[1][0]);
+    CROW(12) = make_float4(M1[0][3], M1[0][4], M1[0][5], A[1][2]);
+    CROW(13) = make_float4(M1[1][3], M1[1][4], M1[1][5], A[2][0]);
+    CROW(14) = make_float4(M1[2][3], M1[2][4], M1[2][5], A[2][1]);
+    CROW(CROW_LAMBDA) = make_float4(0.f, 0.f, 0.f, 0.f);       // lambda = 0 (Contact.cpp:66, SolverBoxPGS.cpp:210)
 #undef CROW
 }
 
@@ -470,45 +536,80 @@ __device__ __forceinline__ V3 lin3(const V3& a, float s0, const V3& b, float s1,
     return fma3(s2, c, fma3(s1, b, s0 * a));
 }
 
-__device__ __forceinline__ void contact_visit(const View& v, int slot, int scene, float mu)
+// One-entry write-back register cache of a body accumulator. Rows are visited in (i, j) order, so
+// body0 of consecutive rows is almost always the same body (all contacts of body i, all hinges of a
+// chassis): it stays in registers instead of making a dependent HBM round trip per row.
+struct WCache {
+    int id;          // cached body index, -1 = empty
+    V3 l, a;
+};
+__device__ __forceinline__ void wc_flush(const View& v, int scene, WCache& c)
 {
-    float4 F[CROW_FIELDS];
-#pragma unroll
-    for (int f = 0; f < CROW_FIELDS; ++f) F[f] = __ldg(&v.crow[at_crow(v, f, slot, scene)]);
-    // lambda is read-modify-write; field 15 is re-read without the read-only path
-    F[15] = v.crow[at_crow(v, 15, slot, scene)];
+    if (c.id >= 0) {
+        const size_t i = at(v, c.id, scene);
+        v.wl[i] = mk4(c.l, 0.f);
+        v.wa[i] = mk4(c.a, 0.f);
+    }
+}
+__device__ __forceinline__ void wc_acquire(const View& v, int scene, WCache& c, int id)
+{
+    if (c.id != id) {
+        wc_flush(v, scene, c);
+        const size_t i = at(v, id, scene);
+        c.l = mk3(v.wl[i]); c.a = mk3(v.wa[i]);
+        c.id = id;
+    }
+}
+
+// cp.async (LDGSTS) 16-byte global -> shared copy and group bookkeeping
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// solveContact (SolverBoxPGS.cpp:94-113) on a row record F (CROW_FIELDS float4, layout.cuh).
+__device__ __forceinline__ void contact_visit(const View& v, int slot, int scene, float mu, const float4* F, const float4& lam, WCache& wc)
+{
     const V3 n = mk3(F[0]), t = mk3(F[1]), b = mk3(F[2]);
     const float im0 = F[0].w, im1 = F[1].w;
-    const int id0 = __float_as_int(F[2].w), id1 = __float_as_int(F[3].w);
-    const bool dyn0 = id0 >= 0, dyn1 = id1 >= 0;
+    const int ids = __float_as_int(F[2].w);
+    const int id0 = ids & 0x7fff, id1 = (ids >> 16) & 0x7fff;
+    const bool dyn0 = !(ids & 0x8000), dyn1 = !(ids & 0x80000000);
     const V3 a0n = mk3(F[3]), a0t = mk3(F[4]), a0b = mk3(F[5]);
     const V3 a1n = mk3(F[6]), a1t = mk3(F[7]), a1b = mk3(F[8]);
-    float x0 = F[4].w, x1 = F[5].w, x2 = F[6].w;
-    const float l0 = F[15].x, l1 = F[15].y, l2 = F[15].z;
+    float x0 = F[3].w, x1 = F[4].w, x2 = F[5].w;
+    const float l0 = lam.x, l1 = lam.y, l2 = lam.z;
     const V3 dl = lin3(n, l0, t, l1, b, l2);                     // J0_lin^T lambda ( = -J1_lin^T lambda)
-    size_t w0i = 0, w1i = 0;
-    V3 w0l, w0a, w1l, w1a;
+    // body1 first: its accumulator usually comes from HBM, issue the load before the body0 math
+    size_t w1i = 0;
+    V3 w1l, w1a;
+    const bool hit1 = dyn1 && (id1 == wc.id) && !(dyn0 && id0 != wc.id);
+    if (dyn0) wc_acquire(v, scene, wc, id0);
+    if (dyn1) {
+        if (hit1) { w1l = wc.l; w1a = wc.a; }
+        else { w1i = at(v, id1, scene); w1l = mk3(v.wl[w1i]); w1a = mk3(v.wa[w1i]); }
+    }
     if (dyn0) {
-        w0i = at(v, id0, scene);
-        w0l = mk3(v.wl[w0i]); w0a = mk3(v.wa[w0i]);
-        const V3 tl = w0l - dl;
-        const V3 ta = w0a - lin3(a0n, l0, a0t, l1, a0b, l2);
+        const V3 tl = wc.l - dl;
+        const V3 ta = wc.a - lin3(a0n, l0, a0t, l1, a0b, l2);
         x0 -= fmaf(im0, dotf(n, tl), dotf(mk3(F[9]), ta));
         x1 -= fmaf(im0, dotf(t, tl), dotf(mk3(F[10]), ta));
         x2 -= fmaf(im0, dotf(b, tl), dotf(mk3(F[11]), ta));
     }
     if (dyn1) {
-        w1i = at(v, id1 & 0x7fffffff, scene);
-        w1l = mk3(v.wl[w1i]); w1a = mk3(v.wa[w1i]);
         const V3 tl = w1l + dl;
         const V3 ta = w1a - lin3(a1n, l0, a1t, l1, a1b, l2);
         x0 -= fmaf(-im1, dotf(n, tl), dotf(mk3(F[12]), ta));
         x1 -= fmaf(-im1, dotf(t, tl), dotf(mk3(F[13]), ta));
         x2 -= fmaf(-im1, dotf(b, tl), dotf(mk3(F[14]), ta));
     }
-    // solveContact (SolverBoxPGS.cpp:94-113); x aliases lambda, so l1,l2 on the first line are last sweep's
-    const float A00 = F[7].w, A11 = F[8].w, A22 = F[9].w, A01 = F[10].w, A02 = F[11].w;
-    const float A10 = F[12].w, A12 = F[13].w, A20 = F[14].w, A21 = F[15].w;
+    // x aliases lambda in the reference, so l1, l2 on the first line are last sweep's values
+    const float A00 = F[6].w, A11 = F[7].w, A22 = F[8].w, A01 = F[9].w, A02 = F[10].w;
+    const float A10 = F[11].w, A12 = F[12].w, A20 = F[13].w, A21 = F[14].w;
     float y0 = (x0 - A01 * l1 - A02 * l2) / (A00 + 1e-3f);
     if (y0 < 0.0f) y0 = 0.0f;
     const float lo = -mu * y0, hi = mu * y0;
@@ -519,14 +620,15 @@ __device__ __forceinline__ void contact_visit(const View& v, int slot, int scene
     const float d0 = y0 - l0, d1 = y1 - l1, d2 = y2 - l2;
     const V3 ddl = lin3(n, d0, t, d1, b, d2);
     if (dyn0) {
-        v.wl[w0i] = mk4(w0l + ddl, 0.f);
-        v.wa[w0i] = mk4(w0a + lin3(a0n, d0, a0t, d1, a0b, d2), 0.f);
+        wc.l = wc.l + ddl;
+        wc.a = wc.a + lin3(a0n, d0, a0t, d1, a0b, d2);
     }
     if (dyn1) {
-        v.wl[w1i] = mk4(w1l - ddl, 0.f);
-        v.wa[w1i] = mk4(w1a + lin3(a1n, d0, a1t, d1, a1b, d2), 0.f);
+        const V3 nl = w1l - ddl, na = w1a + lin3(a1n, d0, a1t, d1, a1b, d2);
+        if (hit1) { wc.l = nl; wc.a = na; }
+        else { v.wl[w1i] = mk4(nl, 0.f); v.wa[w1i] = mk4(na, 0.f); }
     }
-    v.crow[at_crow(v, 15, slot, scene)] = make_float4(y0, y1, y2, A21);
+    v.crow[at_crow(v, CROW_LAMBDA, slot, scene)] = make_float4(y0, y1, y2, 0.f);
 }
 
 struct JointRow {
@@ -551,7 +653,7 @@ __device__ __forceinline__ V3 joint_jt_ang(const V3& rr, const V3& nxu, const V3
     return fma3(l[4], nxv, fma3(l[3], nxu, cross(rr, ll)));
 }
 
-__device__ __forceinline__ void joint_visit(const View& v, int slot, int scene)
+__device__ __forceinline__ void joint_visit(const View& v, int slot, int scene, WCache& wc)
 {
     const JointRow j = load_joint_head(v, slot, scene);
     float4 M0[5], M1[5];
@@ -568,14 +670,19 @@ __device__ __forceinline__ void joint_visit(const View& v, int slot, int scene)
     float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
     float x[5] = { M0[0].w, M0[1].w, M0[2].w, M0[3].w, M0[4].w };
     const bool dyn0 = j.id0 >= 0, dyn1 = j.id1 >= 0;
+    const int id0 = j.id0 & 0x7fffffff, id1 = j.id1 & 0x7fffffff;
     const V3 ll = mk3(l[0], l[1], l[2]);
-    size_t w0i = 0, w1i = 0;
-    V3 w0l, w0a, w1l, w1a;
+    size_t w1i = 0;
+    V3 w1l, w1a;
+    const bool hit1 = dyn1 && (id1 == wc.id) && !(dyn0 && id0 != wc.id);
+    if (dyn0) wc_acquire(v, scene, wc, id0);
+    if (dyn1) {
+        if (hit1) { w1l = wc.l; w1a = wc.a; }
+        else { w1i = at(v, id1, scene); w1l = mk3(v.wl[w1i]); w1a = mk3(v.wa[w1i]); }
+    }
     if (dyn0) {
-        w0i = at(v, j.id0, scene);
-        w0l = mk3(v.wl[w0i]); w0a = mk3(v.wa[w0i]);
-        const V3 tl = w0l - ll;
-        const V3 ta = w0a - joint_jt_ang(j.rr0, j.nxu, j.nxv, l);
+        const V3 tl = wc.l - ll;
+        const V3 ta = wc.a - joint_jt_ang(j.rr0, j.nxu, j.nxv, l);
         x[0] -= fmaf(j.im0, tl.x, dotf(mk3(M0[0]), ta));
         x[1] -= fmaf(j.im0, tl.y, dotf(mk3(M0[1]), ta));
         x[2] -= fmaf(j.im0, tl.z, dotf(mk3(M0[2]), ta));
@@ -583,8 +690,6 @@ __device__ __forceinline__ void joint_visit(const View& v, int slot, int scene)
         x[4] -= dotf(mk3(M0[4]), ta);
     }
     if (dyn1) {
-        w1i = at(v, j.id1 & 0x7fffffff, scene);
-        w1l = mk3(v.wl[w1i]); w1a = mk3(v.wa[w1i]);
         const V3 tl = w1l + ll;
         const V3 ta = w1a + joint_jt_ang(j.rr1, j.nxu, j.nxv, l);
         x[0] -= fmaf(-j.im1, tl.x, dotf(mk3(M1[0]), ta));
@@ -612,12 +717,13 @@ __device__ __forceinline__ void joint_visit(const View& v, int slot, int scene)
     for (int r = 0; r < 5; ++r) d[r] = n[r] - l[r];
     const V3 dl = mk3(d[0], d[1], d[2]);
     if (dyn0) {
-        v.wl[w0i] = mk4(w0l + dl, 0.f);
-        v.wa[w0i] = mk4(w0a + joint_jt_ang(j.rr0, j.nxu, j.nxv, d), 0.f);
+        wc.l = wc.l + dl;
+        wc.a = wc.a + joint_jt_ang(j.rr0, j.nxu, j.nxv, d);
     }
     if (dyn1) {
-        v.wl[w1i] = mk4(w1l - dl, 0.f);
-        v.wa[w1i] = mk4(w1a - joint_jt_ang(j.rr1, j.nxu, j.nxv, d), 0.f);
+        const V3 nl = w1l - dl, na = w1a - joint_jt_ang(j.rr1, j.nxu, j.nxv, d);
+        if (hit1) { wc.l = nl; wc.a = na; }
+        else { v.wl[w1i] = mk4(nl, 0.f); v.wa[w1i] = mk4(na, 0.f); }
     }
     v.jlam[ji] = make_float4(n[0], n[1], n[2], n[3]);
     v.jlam4[ji] = n[4];
@@ -637,9 +743,14 @@ __device__ __forceinline__ void add_force(const View& v, int body, int scene, co
     v.wa[i] = mk4(mk3(v.wa[i]) + fa, 0.f);
 }
 
-__global__ void __launch_bounds__(128) k_pgs(View v, float dt, int iters, float mu)
+enum { PGS_THREADS = 32, PGS_STAGES = 2, PGS_MIN_CTAS = 12 };
+
+__global__ void __launch_bounds__(PGS_THREADS, PGS_MIN_CTAS) k_pgs(View v, float dt, int iters, float mu)
 {
-    const int scene = blockIdx.x * blockDim.x + threadIdx.x;
+    // thread-private staging ring for the contact row stream: [stage][field][thread] float4;
+    __shared__ float4 ring[PGS_STAGES][CROW_FIELDS][PGS_THREADS];
+    const int tid = threadIdx.x;
+    const int scene = blockIdx.x * PGS_THREADS + tid;
     if (scene >= v.B) return;
     const int nb = v.nbodies[scene], nj = v.njoints[scene], nc = v.ncontacts[scene];
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -662,10 +773,45 @@ __global__ void __launch_bounds__(128) k_pgs(View v, float dt, int iters, float 
             v.wa[wi] = mk4(mk3(v.wa[wi]) - joint_jt_ang(j.rr1, j.nxu, j.nxv, l), 0.f);
         }
     }
+    WCache wc; wc.id = -1; wc.l = mk3(0.f, 0.f, 0.f); wc.a = wc.l;
+
+    // The contact rows are static during the solve: stream them (and each row's lambda, which was
+    // last written a whole sweep earlier) through shared memory with cp.async, PGS_STAGES - 1 rows
+    // ahead of the row being solved, across sweep boundaries. With fewer rows than stages the
+    // prefetched lambda could be stale, so it is then re-read directly.
+    const int total = nc * iters;
+    const bool lam_direct = nc < PGS_STAGES + 1;
+    int fetch_row = 0, fetched = 0;
+    auto fetch = [&]() {
+        if (fetched < total) {
+            const int st = fetched % PGS_STAGES;
+#pragma unroll
+            const float4* src = &v.crow[at_crow(v, 0, fetch_row, scene)];       // one contiguous 8 KB tile per warp
+#pragma unroll
+            for (int f = 0; f < CROW_FIELDS; ++f) cp_async16(&ring[st][f][tid], src + f * 32);
+            ++fetched;
+            if (++fetch_row == nc) fetch_row = 0;
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int k = 0; k < PGS_STAGES - 1; ++k) fetch();
+    int g = 0;
     for (int it = 0; it < iters; ++it) {                          // SolverBoxPGS.cpp:217-248
-        for (int s = 0; s < nj; ++s) joint_visit(v, s, scene);
-        for (int s = 0; s < nc; ++s) contact_visit(v, s, scene, mu);
+        for (int s = 0; s < nj; ++s) joint_visit(v, s, scene, wc);
+        for (int s = 0; s < nc; ++s, ++g) {
+            fetch();
+            cp_async_wait<PGS_STAGES - 1>();
+            const int st = g % PGS_STAGES;
+            float4 F[CROW_FIELDS];
+#pragma unroll
+            for (int f = 0; f < CROW_FIELDS; ++f) F[f] = ring[st][f][tid];
+            float4 lam = F[CROW_LAMBDA];
+            if (lam_direct) lam = v.crow[at_crow(v, CROW_LAMBDA, s, scene)];
+            contact_visit(v, s, scene, mu, F, lam, wc);
+        }
     }
+    cp_async_wait<0>();
     // constraint forces (RigidBodySystem.cpp:185-220): wl/wa become fc/tauc
     for (int i = 0; i < nb; ++i) { v.wl[at(v, i, scene)] = z4; v.wa[at(v, i, scene)] = z4; }
     for (int s = 0; s < nj; ++s) {
@@ -693,14 +839,14 @@ __global__ void __launch_bounds__(128) k_pgs(View v, float dt, int iters, float 
         float4 F[9];
 #pragma unroll
         for (int f = 0; f < 9; ++f) F[f] = __ldg(&v.crow[at_crow(v, f, s, scene)]);
-        const float4 lam = v.crow[at_crow(v, 15, s, scene)];
-        const int id0 = __float_as_int(F[2].w), id1 = __float_as_int(F[3].w);
+        const float4 lam = v.crow[at_crow(v, CROW_LAMBDA, s, scene)];
+        const int ids = __float_as_int(F[2].w);
         const V3 n = mk3(F[0]), t = mk3(F[1]), b = mk3(F[2]);
-        if (id0 >= 0)
-            add_force(v, id0, scene, seq3(n, lam.x, t, lam.y, b, lam.z) / dt,
+        if (!(ids & 0x8000))
+            add_force(v, ids & 0x7fff, scene, seq3(n, lam.x, t, lam.y, b, lam.z) / dt,
                       seq3(mk3(F[3]), lam.x, mk3(F[4]), lam.y, mk3(F[5]), lam.z) / dt);
-        if (id1 >= 0)
-            add_force(v, id1, scene, seq3(-n, lam.x, -t, lam.y, -b, lam.z) / dt,
+        if (!(ids & 0x80000000))
+            add_force(v, (ids >> 16) & 0x7fff, scene, seq3(-n, lam.x, -t, lam.y, -b, lam.z) / dt,
                       seq3(mk3(F[6]), lam.x, mk3(F[7]), lam.y, mk3(F[8]), lam.z) / dt);
     }
     if (v.profiling) {
@@ -878,7 +1024,7 @@ __global__ void k_export_contacts(View v, int scene, int n, int* body0, int* bod
     for (int f = 0; f < CROW_FIELDS; ++f) F[f] = v.crow[at_crow(v, f, c, scene)];
     if (t3) { t3[3 * c] = F[1].x; t3[3 * c + 1] = F[1].y; t3[3 * c + 2] = F[1].z; }
     if (b3) { b3[3 * c] = F[2].x; b3[3 * c + 1] = F[2].y; b3[3 * c + 2] = F[2].z; }
-    if (lam3) { lam3[3 * c] = F[15].x; lam3[3 * c + 1] = F[15].y; lam3[3 * c + 2] = F[15].z; }
+    if (lam3) { const float4 l = F[CROW_LAMBDA]; lam3[3 * c] = l.x; lam3[3 * c + 1] = l.y; lam3[3 * c + 2] = l.z; }
     const float im0 = F[0].w, im1 = F[1].w;
     for (int r = 0; r < 3; ++r) {
         const float4 d = F[r], a0 = F[3 + r], a1 = F[6 + r], m0 = F[9 + r], m1 = F[12 + r];
@@ -890,10 +1036,10 @@ __global__ void k_export_contacts(View v, int scene, int n, int* body0, int* bod
     }
     if (A9) {
         float* A = A9 + 9 * c;
-        A[0] = F[7].w; A[1] = F[10].w; A[2] = F[11].w; A[3] = F[12].w; A[4] = F[8].w; A[5] = F[13].w;
-        A[6] = F[14].w; A[7] = F[15].w; A[8] = F[9].w;
+        A[0] = F[6].w; A[1] = F[9].w; A[2] = F[10].w; A[3] = F[11].w; A[4] = F[7].w; A[5] = F[12].w;
+        A[6] = F[13].w; A[7] = F[14].w; A[8] = F[8].w;
     }
-    if (rhs3) { rhs3[3 * c] = F[4].w; rhs3[3 * c + 1] = F[5].w; rhs3[3 * c + 2] = F[6].w; }
+    if (rhs3) { rhs3[3 * c] = F[3].w; rhs3[3 * c + 1] = F[4].w; rhs3[3 * c + 2] = F[5].w; }
 }
 
 __global__ void k_export_joints(View v, int scene, int n, float* J0, float* J1, float* M0, float* M1, float* rhs5)
@@ -948,10 +1094,22 @@ __global__ void k_export_body_dyn(View v, int scene, int n, float* f3, float* ta
 static inline unsigned blocks_for(size_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 void launch_prepare(const View& v, cudaStream_t s) { k_prepare<<<blocks_for((size_t)v.NB * v.B, 256), 256, 0, s>>>(v); }
-void launch_detect(const View& v, cudaStream_t s) { k_detect<<<blocks_for(v.B, 128), 128, 0, s>>>(v); }
+void launch_detect(const View& v, cudaStream_t s)
+{
+    // warps per CTA: as many as fit ~96 KB of staged proxies (20 B / body / warp), at most 8
+    const size_t per_warp = (size_t)v.NB * 20;
+    int warps = 8;
+    while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+    const size_t smem = per_warp * warps;
+    // tiny scenes (car: 15 pairs) leave a warp idle: one thread per scene is faster there; huge ones do not fit
+    if (v.NB < 24 || smem > 200 * 1024) { k_detect_serial<<<blocks_for(v.B, 128), 128, 0, s>>>(v); return; }
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_detect_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    k_detect_warp<<<blocks_for(v.B, warps), warps * 32, smem, s>>>(v, warps);
+}
 void launch_contact_rows(const View& v, float h, cudaStream_t s) { k_contact_rows<<<blocks_for((size_t)v.NC * v.B, 128), 128, 0, s>>>(v, h); }
 void launch_joint_rows(const View& v, float h, cudaStream_t s) { if (v.NJ > 0) k_joint_rows<<<blocks_for((size_t)v.NJ * v.B, 128), 128, 0, s>>>(v, h); }
-void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s) { k_pgs<<<blocks_for(v.B, 128), 128, 0, s>>>(v, dt, iters, mu); }
+void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s) { k_pgs<<<blocks_for(v.B, PGS_THREADS), PGS_THREADS, 0, s>>>(v, dt, iters, mu); }
 void launch_integrate(const View& v, float dt, cudaStream_t s) { k_integrate<<<blocks_for((size_t)v.NB * v.B, 256), 256, 0, s>>>(v, dt); }
 
 void launch_upload_bodies(const View& v, int scene0, int ns, int n, const int* counts, const BodyStage& st, cudaStream_t s)

@@ -3,8 +3,14 @@
 // Every per-item array is "slot-major, scene-minor": element (slot i, scene s) lives at
 // i * B + s, so the 32 lanes of a warp that work on 32 consecutive scenes read one
 // contiguous 128 B / 512 B segment per field (coalesced float / float4 streams), whatever
-// the item index is.  Multi-field records (constraint rows) add a field index in front:
-// (f * CAP + i) * B + s.  With B = 1 this degenerates to plain SoA.
+// the item index is.  With B = 1 this degenerates to plain SoA.
+//
+// Constraint ROW records (the stream the PGS sweep re-reads every iteration) are blocked by
+// warp instead: scenes are grouped 32 at a time, and the rows of a group are laid out
+// [group][slot][field][lane], i.e. one row of one group is a contiguous 16-field x 32-lane x 16 B
+// = 8 KB tile and consecutive rows follow each other. A warp sweeping its 32 scenes therefore
+// streams one private, contiguous HBM region front to back (DRAM-page and TLB friendly; one
+// tile is what a stage of the shared-memory ring holds).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,16 +19,18 @@ namespace slrbs {
 
 enum { GEOM_SPHERE = 0, GEOM_BOX = 1, GEOM_PLANE = 2, GEOM_CYLINDER = 3 };
 enum { FLAG_TYPE_MASK = 0xF, FLAG_FIXED = 0x10 };
-enum { CROW_FIELDS = 16, JROW_FIELDS = 17 };
+enum { CROW_FIELDS = 16, JROW_FIELDS = 17, CROW_LAMBDA = 15 };
+enum { MAX_BODIES_PER_SCENE = 32767 };   // body ids are packed 2 x 16 bit in the contact row record
 enum { BODY_FIXED_BIT = (int)0x80000000 };
 
-// Contact row record (CROW_FIELDS float4 per contact; see k_contact_rows):
-//  0 n   | im0      4 a0t | rhs0     8 a1b | A11     12 m1n | A10
-//  1 t   | im1      5 a0b | rhs1     9 m0n | A22     13 m1t | A12
-//  2 b   | body0    6 a1n | rhs2    10 m0t | A01     14 m1b | A20
-//  3 a0n | body1    7 a1t | A00     11 m0b | A02     15 lam | A21
+// Contact row record (CROW_FIELDS float4 per contact, written by k_contact_rows, streamed by k_pgs):
+//  0 n   | im0      3 a0n | rhs0     6 a1n | A00      9 m0n | A01     12 m1n | A12
+//  1 t   | im1      4 a0t | rhs1     7 a1t | A11     10 m0t | A02     13 m1t | A20
+//  2 b   | ids      5 a0b | rhs2     8 a1b | A22     11 m0b | A10     14 m1b | A21
+//  15 lambda | -   (the only field the sweep writes)
 // d in {n,t,b}: J0 row = [d, a0d], J1 row = [-d, a1d], J0Minv row = [im0*d, m0d],
-// J1Minv row = [-im1*d, m1d]; body ids carry BODY_FIXED_BIT when the body is fixed.
+// J1Minv row = [-im1*d, m1d]; ids = body0 | body1 << 16, each 15-bit index with bit 15 set
+// when the body is fixed.
 //
 // Joint row record (JROW_FIELDS float4 per joint; see k_joint_rows):
 //  0 rr0 | im0     2 nxu | body0     4..8  J0Minv angular rows 0..4 | rhs[r]
@@ -60,17 +68,23 @@ struct View {
     float4 *jr0, *jq0, *jr1, *jq1;
     float4 *jlam;       // lambda 0..3
     float  *jlam4;      // lambda 4
-    float4 *jrow;       // [JROW_FIELDS][NJ][B]
+    float4 *jrow;       // [B/32][NJ][JROW_FIELDS][32]
     // contacts, [NC][B]
     int2   *cids;       // body0, body1 (role ordered: sphere/box, cylinder/plane)
     float4 *cp;         // p | pene
     float4 *cn;         // n | -
-    float4 *crow;       // [CROW_FIELDS][NC][B]
+    float4 *crow;       // [B/32][NC][CROW_FIELDS][32]
 };
 
 __host__ __device__ __forceinline__ size_t at(const View& v, int slot, int scene) { return (size_t)slot * v.B + scene; }
 __host__ __device__ __forceinline__ size_t at_b9(const View& v, int k, int slot, int scene) { return ((size_t)k * v.NB + slot) * v.B + scene; }
-__host__ __device__ __forceinline__ size_t at_crow(const View& v, int f, int slot, int scene) { return ((size_t)f * v.NC + slot) * v.B + scene; }
-__host__ __device__ __forceinline__ size_t at_jrow(const View& v, int f, int slot, int scene) { return ((size_t)f * v.NJ + slot) * v.B + scene; }
+__host__ __device__ __forceinline__ size_t at_crow(const View& v, int f, int slot, int scene)
+{
+    return ((((size_t)(scene >> 5) * v.NC + slot) * CROW_FIELDS + f) << 5) + (scene & 31);
+}
+__host__ __device__ __forceinline__ size_t at_jrow(const View& v, int f, int slot, int scene)
+{
+    return ((((size_t)(scene >> 5) * v.NJ + slot) * JROW_FIELDS + f) << 5) + (scene & 31);
+}
 
 }  // namespace slrbs
