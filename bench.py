@@ -103,18 +103,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_batch(workload, B, seed):
-    """Synthetic batch: B copies of a Scenarios.h scene, dynamic bodies jittered in x,z per scene."""
-    from slrbs_b200 import host_api
+def build_batch(workload, B, rank):
+    """Synthetic batch: this rank's contiguous block of B scenes (global indices rank*B ..), each a copy of
+    a Scenarios.h scene whose dynamic bodies are jittered in x,z by a generator keyed on the GLOBAL scene
+    index (the data does not depend on the number of ranks)."""
+    from slrbs_b200 import host_api, sharding
     scene, abc, nc, _, settle, jitter = WORKLOADS[workload]
     s = host_api.scene_arrays(scene, *abc)
     nb = s["x"].shape[0]
     x = np.broadcast_to(s["x"], (B, nb, 3)).copy()
     if jitter > 0:
-        rng = np.random.default_rng(seed)
         dyn = s["fixed"] == 0
-        x[:, dyn, 0] += rng.uniform(-jitter, jitter, (B, int(dyn.sum()))).astype(np.float32)
-        x[:, dyn, 2] += rng.uniform(-jitter, jitter, (B, int(dyn.sum()))).astype(np.float32)
+        j = sharding.jitter_for_scenes(rank * B, B, nb, jitter)
+        x[:, dyn, 0] += j[:, dyn, 0]
+        x[:, dyn, 2] += j[:, dyn, 1]
     return s, x, nb, s["jtype"].shape[0], nc, settle
 
 
@@ -129,7 +131,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.scenes or WORKLOADS[args.workload][3]
-    s, x, nb, nj, nc, settle = build_batch(args.workload, B, 1234 + rank)
+    s, x, nb, nj, nc, settle = build_batch(args.workload, B, rank)
 
     ctx = Context(B, nb, nj, nc, device=local)
     ctx.set_params(MU, 0, SOLVER_ITERS, True)
@@ -177,19 +179,16 @@ def run_ours(args):
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
 
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
-    agg = torch.tensor([prof["solve_ms"], float(prof["solve_launches"]), float(prof["contact_visits"]), float(prof["joint_visits"]),
-                        float(prof["total_launches"])], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    from slrbs_b200 import sharding
+    ms, e2e_ms = sharding.reduce_over_ranks([ms, e2e_ms], "max")           # device time: max over ranks
+    agg = [prof["solve_ms"], float(prof["solve_launches"]), float(prof["contact_visits"]), float(prof["joint_visits"]),
+           float(prof["total_launches"])]                                    # roofline / launches: rank 0's GPU
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    body_steps = float(B) * nb * world
-    value = body_steps * args.steps / (ms * 1e-3)
-    e2e_value = body_steps * e2e_steps / (e2e_ms * 1e-3)
+    value = sharding.job_throughput(float(B) * nb * args.steps, world, ms)
+    e2e_value = sharding.job_throughput(float(B) * nb * e2e_steps, world, e2e_ms)
     peak, peak_src = load_peaks()
     solve_ms, launches = float(agg[0]), max(float(agg[1]), 1.0)
     alg_bytes = BYTES_PER_CONTACT_VISIT * float(agg[2]) + BYTES_PER_HINGE_VISIT * float(agg[3])
