@@ -116,8 +116,16 @@ int fold_events(slrbs_ctx* c)
 
 int solve_launch(slrbs_ctx* c, float dt)
 {
-    if (c->solver_id != 0)
-        return fail(SLRBS_E_UNSUPPORTED, "solver_id 1/2 (CG/CR) not implemented on the device yet");
+    if (c->solver_id != 0) {
+        // joint-only Krylov solve, then the PGS kernel with zero sweeps for the force scatter
+        if (c->v.NJ > 0 && !c->v.kry) {
+            int r = dalloc(c, &c->v.kry, (size_t)7 * 5 * c->v.NJ * c->v.B);
+            if (r) return r;
+        }
+        launch_krylov(c->v, c->solver_id, c->solver_iters, c->stream);
+        launch_pgs(c->v, dt, 0, c->mu, c->stream);
+        return check_launch(c, 2);
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profiling) {
         if (c->ev_used + 2 > 8192) { int r = fold_events(c); if (r) return r; }

@@ -856,6 +856,170 @@ __global__ void __launch_bounds__(PGS_THREADS, PGS_MIN_CTAS) k_pgs(View v, float
 }
 
 // ------------------------------------------------------------------------------------
+// K6c  joint-only Krylov solvers (solverId 1 = CG, 2 = CR): SolverConjGradient.cpp:109-162,
+// SolverConjResidual.cpp:100-158. One thread per scene; contacts are ignored (lambda stays 0).
+// A x is evaluated body-wise: u_body = sum_{joints on body} J^T x, then (A x)_j = J0Minv_j u_b0 +
+// J1Minv_j u_b1 over the non-fixed bodies, which is the reference's self + neighbour sum
+// (SolverConjGradient.cpp:49-100) regrouped. The reference's quirks are kept: CG updates
+// p = r - beta p (:150), CR adds 1e-9 x to A x (SolverConjResidual.cpp:71,78), both stop at 1e-12.
+// ------------------------------------------------------------------------------------
+enum { KV_X = 0, KV_R = 1, KV_P = 2, KV_B = 3, KV_AP = 4, KV_AR = 5, KV_AX = 6 };
+
+__device__ __forceinline__ void kry_load(const View& v, int vec, int s, int scene, float* x)
+{
+#pragma unroll
+    for (int k = 0; k < 5; ++k) x[k] = v.kry[at_kry(v, vec, k, s, scene)];
+}
+__device__ __forceinline__ void kry_store(const View& v, int vec, int s, int scene, const float* x)
+{
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v.kry[at_kry(v, vec, k, s, scene)] = x[k];
+}
+
+// out = A * in   (vectors live in v.kry); wl/wa are used as the per-body u accumulators
+__device__ void kry_apply(const View& v, int scene, int nb, int nj, int vin, int vout, float eps)
+{
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < nb; ++i) { v.wl[at(v, i, scene)] = z4; v.wa[at(v, i, scene)] = z4; }
+    for (int s = 0; s < nj; ++s) {
+        const JointRow j = load_joint_head(v, s, scene);
+        float x[5]; kry_load(v, vin, s, scene, x);
+        const V3 ll = mk3(x[0], x[1], x[2]);
+        if (j.id0 >= 0) {
+            const size_t wi = at(v, j.id0, scene);
+            v.wl[wi] = mk4(mk3(v.wl[wi]) + ll, 0.f);
+            v.wa[wi] = mk4(mk3(v.wa[wi]) + joint_jt_ang(j.rr0, j.nxu, j.nxv, x), 0.f);
+        }
+        if (j.id1 >= 0) {
+            const size_t wi = at(v, j.id1 & 0x7fffffff, scene);
+            v.wl[wi] = mk4(mk3(v.wl[wi]) - ll, 0.f);
+            v.wa[wi] = mk4(mk3(v.wa[wi]) - joint_jt_ang(j.rr1, j.nxu, j.nxv, x), 0.f);
+        }
+    }
+    for (int s = 0; s < nj; ++s) {
+        const JointRow j = load_joint_head(v, s, scene);
+        const int dim = __float_as_int(__ldg(&v.jrow[at_jrow(v, 16, s, scene)]).z);
+        float x[5]; kry_load(v, vin, s, scene, x);
+        float y[5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) y[r] = eps * x[r];
+        if (j.id0 >= 0) {
+            const size_t wi = at(v, j.id0, scene);
+            const V3 ul = mk3(v.wl[wi]), ua = mk3(v.wa[wi]);
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                const V3 m = mk3(__ldg(&v.jrow[at_jrow(v, 4 + r, s, scene)]));
+                y[r] += (r < 3 ? j.im0 * (r == 0 ? ul.x : (r == 1 ? ul.y : ul.z)) : 0.f) + dotf(m, ua);
+            }
+        }
+        if (j.id1 >= 0) {
+            const size_t wi = at(v, j.id1 & 0x7fffffff, scene);
+            const V3 ul = mk3(v.wl[wi]), ua = mk3(v.wa[wi]);
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                const V3 m = mk3(__ldg(&v.jrow[at_jrow(v, 9 + r, s, scene)]));
+                y[r] += (r < 3 ? -j.im1 * (r == 0 ? ul.x : (r == 1 ? ul.y : ul.z)) : 0.f) + dotf(m, ua);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 5; ++r) if (r >= dim) y[r] = 0.f;
+        kry_store(v, vout, s, scene, y);
+    }
+}
+
+__device__ float kry_dot(const View& v, int scene, int nj, int va, int vb)
+{
+    float acc = 0.f;
+    for (int s = 0; s < nj; ++s) {
+        float a[5], b[5]; kry_load(v, va, s, scene, a); kry_load(v, vb, s, scene, b);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc += a[k] * b[k];
+    }
+    return acc;
+}
+
+template <bool CR>
+__global__ void __launch_bounds__(64) k_krylov(View v, int iters)
+{
+    const int scene = blockIdx.x * blockDim.x + threadIdx.x;
+    if (scene >= v.B) return;
+    const int nb = v.nbodies[scene], nj = v.njoints[scene];
+    if (nj == 0) return;
+    const float eps = CR ? 1e-9f : 0.f;
+    // x = 0, b = rhs from the row records, r = b - A x = b, p = r
+    for (int s = 0; s < nj; ++s) {
+        float b[5], z[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
+#pragma unroll
+        for (int r = 0; r < 5; ++r) b[r] = __ldg(&v.jrow[at_jrow(v, 4 + r, s, scene)]).w;
+        kry_store(v, KV_X, s, scene, z); kry_store(v, KV_B, s, scene, b);
+        kry_store(v, KV_R, s, scene, b); kry_store(v, KV_P, s, scene, b);
+    }
+    kry_apply(v, scene, nb, nj, KV_P, KV_AP, eps);
+    if (!CR) {
+        float rTr = kry_dot(v, scene, nj, KV_R, KV_R);
+        float pAp = kry_dot(v, scene, nj, KV_P, KV_AP);
+        for (int it = 0; it < iters; ++it) {
+            if (rTr < 1e-12f) break;
+            if (pAp < 1e-12f) break;
+            const float alpha = rTr / pAp;
+            for (int s = 0; s < nj; ++s) {
+                float x[5], r[5], p[5], ap[5];
+                kry_load(v, KV_X, s, scene, x); kry_load(v, KV_R, s, scene, r); kry_load(v, KV_P, s, scene, p); kry_load(v, KV_AP, s, scene, ap);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { x[k] += alpha * p[k]; r[k] -= alpha * ap[k]; }
+                kry_store(v, KV_X, s, scene, x); kry_store(v, KV_R, s, scene, r);
+            }
+            const float rTr_next = kry_dot(v, scene, nj, KV_R, KV_R);
+            const float beta = rTr_next / rTr;
+            for (int s = 0; s < nj; ++s) {
+                float r[5], p[5];
+                kry_load(v, KV_R, s, scene, r); kry_load(v, KV_P, s, scene, p);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) p[k] = r[k] - beta * p[k];          // sic (SolverConjGradient.cpp:150)
+                kry_store(v, KV_P, s, scene, p);
+            }
+            kry_apply(v, scene, nb, nj, KV_P, KV_AP, eps);
+            pAp = kry_dot(v, scene, nj, KV_P, KV_AP);
+            rTr = rTr_next;
+        }
+    } else {
+        kry_apply(v, scene, nb, nj, KV_R, KV_AR, eps);
+        float rAr = kry_dot(v, scene, nj, KV_R, KV_AR);
+        float pATAp = kry_dot(v, scene, nj, KV_AP, KV_AP);
+        for (int it = 0; it < iters; ++it) {
+            if (rAr < 1e-12f) break;
+            if (pATAp < 1e-12f) break;
+            const float alpha = rAr / pATAp;
+            for (int s = 0; s < nj; ++s) {
+                float x[5], r[5], p[5], ap[5];
+                kry_load(v, KV_X, s, scene, x); kry_load(v, KV_R, s, scene, r); kry_load(v, KV_P, s, scene, p); kry_load(v, KV_AP, s, scene, ap);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { x[k] += alpha * p[k]; r[k] -= alpha * ap[k]; }
+                kry_store(v, KV_X, s, scene, x); kry_store(v, KV_R, s, scene, r);
+            }
+            kry_apply(v, scene, nb, nj, KV_R, KV_AR, eps);
+            const float rAr_next = kry_dot(v, scene, nj, KV_R, KV_AR);
+            const float beta = rAr_next / rAr;
+            for (int s = 0; s < nj; ++s) {
+                float r[5], p[5], ap[5], ar[5];
+                kry_load(v, KV_R, s, scene, r); kry_load(v, KV_P, s, scene, p); kry_load(v, KV_AP, s, scene, ap); kry_load(v, KV_AR, s, scene, ar);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { p[k] = r[k] + beta * p[k]; ap[k] = ar[k] + beta * ap[k]; }
+                kry_store(v, KV_P, s, scene, p); kry_store(v, KV_AP, s, scene, ap);
+            }
+            rAr = rAr_next;
+            pATAp = kry_dot(v, scene, nj, KV_AP, KV_AP);
+        }
+    }
+    for (int s = 0; s < nj; ++s) {                               // j->lambda = x.segment(j->idx, j->dim)
+        float x[5]; kry_load(v, KV_X, s, scene, x);
+        const size_t ji = at(v, s, scene);
+        v.jlam[ji] = make_float4(x[0], x[1], x[2], x[3]);
+        v.jlam4[ji] = x[4];
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // K7  symplectic Euler + quaternion update (RigidBodySystem.cpp:99-120)
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_integrate(View v, float dt)
@@ -1110,6 +1274,12 @@ void launch_detect(const View& v, cudaStream_t s)
 void launch_contact_rows(const View& v, float h, cudaStream_t s) { k_contact_rows<<<blocks_for((size_t)v.NC * v.B, 128), 128, 0, s>>>(v, h); }
 void launch_joint_rows(const View& v, float h, cudaStream_t s) { if (v.NJ > 0) k_joint_rows<<<blocks_for((size_t)v.NJ * v.B, 128), 128, 0, s>>>(v, h); }
 void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s) { k_pgs<<<blocks_for(v.B, PGS_THREADS), PGS_THREADS, 0, s>>>(v, dt, iters, mu); }
+void launch_krylov(const View& v, int solver_id, int iters, cudaStream_t s)
+{
+    if (v.NJ == 0) return;
+    if (solver_id == 2) k_krylov<true><<<blocks_for(v.B, 64), 64, 0, s>>>(v, iters);
+    else k_krylov<false><<<blocks_for(v.B, 64), 64, 0, s>>>(v, iters);
+}
 void launch_integrate(const View& v, float dt, cudaStream_t s) { k_integrate<<<blocks_for((size_t)v.NB * v.B, 256), 256, 0, s>>>(v, dt); }
 
 void launch_upload_bodies(const View& v, int scene0, int ns, int n, const int* counts, const BodyStage& st, cudaStream_t s)

@@ -19,6 +19,7 @@ void launch_detect(const View& v, cudaStream_t s);
 void launch_contact_rows(const View& v, float h, cudaStream_t s);
 void launch_joint_rows(const View& v, float h, cudaStream_t s);
 void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s);
+void launch_krylov(const View& v, int solver_id, int iters, cudaStream_t s);
 void launch_integrate(const View& v, float dt, cudaStream_t s);
 
 void launch_upload_bodies(const View& v, int scene0, int ns, int n, const int* counts, const BodyStage& st, cudaStream_t s);

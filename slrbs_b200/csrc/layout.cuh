@@ -69,6 +69,7 @@ struct View {
     float4 *jlam;       // lambda 0..3
     float  *jlam4;      // lambda 4
     float4 *jrow;       // [B/32][NJ][JROW_FIELDS][32]
+    float  *kry;        // [7][5][NJ][B] Krylov work vectors x, r, p, b, Ap, Ar, Ax (allocated on first CG/CR solve)
     // contacts, [NC][B]
     int2   *cids;       // body0, body1 (role ordered: sphere/box, cylinder/plane)
     float4 *cp;         // p | pene
@@ -77,6 +78,7 @@ struct View {
 };
 
 __host__ __device__ __forceinline__ size_t at(const View& v, int slot, int scene) { return (size_t)slot * v.B + scene; }
+__host__ __device__ __forceinline__ size_t at_kry(const View& v, int vec, int k, int slot, int scene) { return (((size_t)vec * 5 + k) * v.NJ + slot) * v.B + scene; }
 __host__ __device__ __forceinline__ size_t at_b9(const View& v, int k, int slot, int scene) { return ((size_t)k * v.NB + slot) * v.B + scene; }
 __host__ __device__ __forceinline__ size_t at_crow(const View& v, int f, int slot, int scene)
 {

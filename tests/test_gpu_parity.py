@@ -255,3 +255,46 @@ def test_save_restore_scene_range():
         assert_bit_equal(s1[k][1:3], s0[k][1:3], k)
     assert np.abs(s1["x"][0] - s0["x"][0]).max() > 1e-3 and np.abs(s1["x"][3] - s0["x"][3]).max() > 1e-3
     ctx.close()
+
+
+@pytest.mark.parametrize("solver_id", [1, 2])
+@pytest.mark.parametrize("scene,steps", [("swinging_boxes", [0, 5, 40]), ("car", [0, 3, 30])])
+def test_krylov_solvers_match_oracle(solver_id, scene, steps):
+    """solverId 1 (CG, with the reference's p = r - beta p) and 2 (CR) on the joint-only system: one
+    step from identical states; lambda within 2e-3 of the largest impulse, state within 1e-4."""
+    o0 = Oracle(scene); o0.set_params(solver_id=solver_id, solver_iter=20)
+    oracles, done = [], 0
+    for s in steps:
+        o0.step(DT, s - done); done = s
+        c = Oracle(scene); c.set_params(solver_id=solver_id, solver_iter=20)
+        c.set_state(**o0.state()); c.set_joint_lambda(o0.joint_rows()["lam"])
+        oracles.append(c)
+    ctx = context_from_oracles(oracles, max_contacts=32)
+    ctx.set_params(solver_id=solver_id, solver_iters=20)
+    push_state(ctx, oracles)
+    ctx.step(DT, 1); ctx.sync()
+    lam, st = ctx.joint_lambda(), ctx.download_state()
+    for k, o in enumerate(oracles):
+        o.step(DT, 1)
+        ol = o.joint_rows()["lam"]
+        np.testing.assert_allclose(lam[k], ol, rtol=0, atol=2e-3 * max(np.abs(ol).max(), 1e-3), err_msg=f"{scene}@{steps[k]}")
+        np.testing.assert_allclose(st["x"][k], o.state()["x"], rtol=0, atol=1e-4)
+        assert (ctx.contacts(k)["lam"] == 0).all() if ctx.contact_counts()[k] else True     # contacts are ignored
+    ctx.close()
+
+
+def test_krylov_trajectory_swinging_boxes():
+    """The reference's CG (p = r - beta p, SolverConjGradient.cpp:150) and CR iterations amplify last-bit
+    differences by orders of magnitude per step on this scene (mass ratio 100): a 1-ulp change of one input
+    moves the ORACLE's own result by ~1e-2 m within a few steps. The tolerance is therefore a small multiple
+    (20x) of the oracle's measured 1-ulp self-sensitivity over the same horizon, not an absolute number."""
+    for solver_id, n in ((1, 6), (2, 40)):
+        o = Oracle("swinging_boxes"); o.set_params(solver_id=solver_id, solver_iter=30)
+        p = Oracle("swinging_boxes"); p.set_params(solver_id=solver_id, solver_iter=30)
+        st = p.state(); st["v"][19, 2] = np.nextafter(np.float32(10.0), np.float32(11.0)); p.set_state(**st)
+        ctx = context_from_oracles([o], max_contacts=8); ctx.set_params(solver_id=solver_id, solver_iters=30)
+        ctx.step(DT, n); o.step(DT, n); p.step(DT, n); ctx.sync()
+        self_sens = np.abs(p.state()["x"] - o.state()["x"]).max()
+        d = np.abs(ctx.download_state()["x"][0] - o.state()["x"]).max()
+        assert np.isfinite(d) and d < 20 * max(self_sens, 1e-4), (solver_id, n, d, self_sens)
+        ctx.close()
