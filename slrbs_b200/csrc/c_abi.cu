@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -32,6 +33,8 @@ struct slrbs_ctx {
     View v{};
     float mu = 0.8f;
     int solver_id = 0, solver_iters = 10, collisions = 1;
+    int level_group = 8;                        // lanes per scene of the level-scheduled solver
+    bool joints_dirty = true;                   // joint levels must be recomputed (bodies / joints uploaded)
     std::vector<void*> allocs;
     char* stage = nullptr; size_t stage_cap = 0, stage_off = 0;
     int* h_flag = nullptr;                      // pinned copy of the overflow flag
@@ -123,7 +126,8 @@ int solve_launch(slrbs_ctx* c, float dt)
             if (r) return r;
         }
         launch_krylov(c->v, c->solver_id, c->solver_iters, c->stream);
-        launch_pgs(c->v, dt, 0, c->mu, c->stream);
+        if (c->v.level_mode) launch_pgs_level(c->v, dt, 0, c->mu, c->level_group, c->stream);
+        else launch_pgs(c->v, dt, 0, c->mu, c->stream);
         return check_launch(c, 2);
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -133,7 +137,8 @@ int solve_launch(slrbs_ctx* c, float dt)
         e0 = c->ev[c->ev_used]; e1 = c->ev[c->ev_used + 1]; c->ev_used += 2;
         CU(cudaEventRecord(e0, c->stream));
     }
-    launch_pgs(c->v, dt, c->solver_iters, c->mu, c->stream);
+    if (c->v.level_mode) launch_pgs_level(c->v, dt, c->solver_iters, c->mu, c->level_group, c->stream);
+    else launch_pgs(c->v, dt, c->solver_iters, c->mu, c->stream);
     if (c->profiling) { CU(cudaEventRecord(e1, c->stream)); c->solve_launches++; }
     return check_launch(c);
 }
@@ -163,6 +168,21 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     View& v = c->v;
     v.B = n_scenes; v.NB = max_bodies; v.NJ = max_joints; v.NC = max_contacts;
+    // Solver variant. Small and medium batches of scenes with enough bodies to expose row-level
+    // parallelism use the level-scheduled kernel (pgs_level.cu: G lanes per scene, measured 2-30x faster
+    // up to ~8k marble-box scenes); very large batches and tiny scenes (a car: 12 rows, chains) use one
+    // thread per scene, which then has the whole GPU's worth of independent scenes to hide latency. Both
+    // give the same impulses bit for bit; SLRBS_PGS_MODE=thread|level and SLRBS_LEVEL_GROUP=4|8|16|32 override.
+    {
+        const char* m = std::getenv("SLRBS_PGS_MODE");
+        const bool fits = level_mode_fits(max_bodies) &&
+                          ((size_t)max_bodies * 20 + ((size_t)max_bodies + max_contacts + 2) * 4) <= 200 * 1024;   // k_detect_warp tables
+        if (m && std::strcmp(m, "thread") == 0) v.level_mode = 0;
+        else if (m && std::strcmp(m, "level") == 0) v.level_mode = fits ? 1 : 0;
+        else v.level_mode = (max_bodies >= 24 && n_scenes <= 8192 && fits) ? 1 : 0;
+        const char* g = std::getenv("SLRBS_LEVEL_GROUP");
+        c->level_group = level_group_size(v, g ? std::atoi(g) : 0);
+    }
     const size_t nb = (size_t)v.NB * v.B, nj = (size_t)v.NJ * v.B, nc = (size_t)v.NC * v.B;
     const size_t bpad = ((size_t)v.B + 31) / 32 * 32;      // row records are blocked 32 scenes at a time
     int r = 0;
@@ -175,6 +195,10 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     A(v.jdef, nj) A(v.jr0, nj) A(v.jq0, nj) A(v.jr1, nj) A(v.jq1, nj) A(v.jlam, nj) A(v.jlam4, nj)
     A(v.jrow, (size_t)JROW_FIELDS * v.NJ * bpad)
     A(v.cids, nc) A(v.cp, nc) A(v.cn, nc) A(v.crow, (size_t)CROW_FIELDS * v.NC * bpad)
+    if (v.level_mode) {
+        A(v.cpos, nc) A(v.clev_end, nc + v.B) A(v.nclev, v.B) A(v.lv_last, nb)
+        A(v.jpos, nj) A(v.jlev_end, nj + v.B) A(v.njlev, v.B)
+    }
 #undef A
     CU(cudaMallocHost((void**)&c->h_flag, sizeof(int)));
     *c->h_flag = 0;
@@ -227,6 +251,7 @@ int slrbs_upload_bodies(slrbs_ctx* c, int scene0, int ns, int n, const int32_t* 
         return r;
     launch_upload_bodies(c->v, scene0, ns, n, dcounts, st, c->stream);
     if ((r = check_launch(c))) return r;
+    c->joints_dirty = true;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -258,6 +283,7 @@ int slrbs_upload_joints(slrbs_ctx* c, int scene0, int ns, int n, const int32_t* 
         return r;
     launch_upload_joints(c->v, scene0, ns, n, dcounts, st, c->stream);
     if ((r = check_launch(c))) return r;
+    c->joints_dirty = true;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -339,6 +365,7 @@ int slrbs_stage_jacobians(slrbs_ctx* c, float dt)
     if (!c) return fail(SLRBS_E_ARG, "null context");
     CU(cudaSetDevice(c->device));
     int n = 0;
+    if (c->v.level_mode && c->joints_dirty) { launch_joint_levels(c->v, c->stream); c->joints_dirty = false; ++n; }
     if (c->collisions && c->v.NC > 0) { launch_contact_rows(c->v, dt, c->stream); ++n; }
     if (c->v.NJ > 0) { launch_joint_rows(c->v, dt, c->stream); ++n; }
     return check_launch(c, n);

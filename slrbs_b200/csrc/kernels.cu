@@ -12,6 +12,7 @@
 // k_pgs             SolverBoxPGS.cpp:217-248, RigidBodySystem.cpp:185-220             thread / scene (sequential rows)
 // k_integrate       RigidBodySystem.cpp:99-120                                        thread / (body, scene)
 #include "kernels.cuh"
+#include "pgs_math.cuh"
 #include "vecmath.cuh"
 
 namespace slrbs {
@@ -217,6 +218,9 @@ __device__ __forceinline__ void write_contacts(const View& v, int scene, int bas
     }
 }
 
+// In level mode (layout.cuh) the warp also assigns every contact its dependency level as it is emitted
+// (sequential in emission order, tables in shared memory) and counting-sorts the contacts by level:
+// cpos[c] = position of contact c in the level-ordered row stream, clev_end[l] = end of level l.
 __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta)
 {
     extern __shared__ float4 smem4[];
@@ -225,14 +229,21 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta)
     if (scene >= v.B) return;
     float4* sp = smem4 + (size_t)warp * v.NB;                                 // proxies of this warp's scene
     int* sf = reinterpret_cast<int*>(smem4 + (size_t)warps_per_cta * v.NB) + (size_t)warp * v.NB;
+    // level tables (level mode only): last level per body, contacts per level
+    int* ibase = reinterpret_cast<int*>(smem4 + (size_t)warps_per_cta * v.NB) + (size_t)warps_per_cta * v.NB;
+    int* last = ibase + (size_t)warp * (v.NB + v.NC + 2);
+    int* hist = last + v.NB;
+    const bool lv = v.level_mode != 0;
     const int n = v.nbodies[scene];
     for (int b = lane; b < n; b += 32) {
         const size_t i = at(v, b, scene);
         sp[b] = v.cproxy[i];
         sf[b] = v.flags[i];
+        if (lv) last[b] = 0;
     }
+    if (lv) for (int l = lane; l <= v.NC; l += 32) hist[l] = 0;
     __syncwarp();
-    int count = 0;
+    int count = 0, nlev = 0;
     const unsigned lt = (1u << lane) - 1u;
     for (int i = 0; i < n; ++i) {
         const float4 ci = sp[i];
@@ -260,10 +271,66 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta)
                 total = __shfl_sync(0xffffffffu, incl, 31);
             }
             write_contacts(v, scene, count + before, o);
+            if (lv) {
+                // levels in emission order: every lane follows the same sequence, the emitting lane records
+                unsigned m = any;
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int b0 = __shfl_sync(0xffffffffu, o.b0, src), b1 = __shfl_sync(0xffffffffu, o.b1, src);
+                    const int c = __shfl_sync(0xffffffffu, o.cnt, src), base = __shfl_sync(0xffffffffu, before, src);
+                    const bool dyn0 = !(sf[b0] & FLAG_FIXED), dyn1 = !(sf[b1] & FLAG_FIXED);
+                    int L = 0;
+                    if (dyn0) L = max(L, last[b0]);
+                    if (dyn1) L = max(L, last[b1]);
+                    __syncwarp();
+                    for (int k = 0; k < c; ++k) {                // contacts of one pair share both bodies: consecutive levels
+                        if (count + base + k >= v.NC) break;     // dropped (capacity overflow is reported by slrbs_sync)
+                        ++L;
+                        const int rank = hist[L];
+                        __syncwarp();
+                        if (lane == src) {
+                            hist[L] = rank + 1;
+                            v.cpos[at(v, count + base + k, scene)] = (L << 16) | rank;
+                        }
+                    }
+                    if (lane == src) { if (dyn0) last[b0] = L; if (dyn1) last[b1] = L; }
+                    nlev = max(nlev, L);
+                    __syncwarp();
+                }
+            }
             count += total;
         }
     }
-    if (lane == 0) v.ncontacts[scene] = count < v.NC ? count : v.NC;
+    const int nc = count < v.NC ? count : v.NC;
+    if (lane == 0) v.ncontacts[scene] = nc;
+    if (lv) {
+        nlev = min(nlev, v.NC);
+        // exclusive prefix of the per-level counts -> level starts (in place), level ends to global
+        int carry = 0;
+        for (int l0 = 1; l0 <= nlev; l0 += 32) {
+            const int l = l0 + lane;
+            const int c = l <= nlev ? hist[l] : 0;
+            int incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (l <= nlev) {
+                hist[l] = carry + incl - c;
+                v.clev_end[at(v, l, scene)] = min(carry + incl, nc);
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        for (int c = lane; c < nc; c += 32) {
+            const size_t ci = at(v, c, scene);
+            const int packed = v.cpos[ci];
+            v.cpos[ci] = hist[packed >> 16] + (packed & 0xffff);
+        }
+        if (lane == 0) v.nclev[scene] = nlev;
+    }
 }
 
 // fallback for scenes whose proxies do not fit in shared memory: one thread per scene
@@ -312,11 +379,6 @@ __device__ __forceinline__ float mult_and_sub_row(float b, const float* G, const
     b -= (a * G[0]) * x.x; b -= (a * G[1]) * x.y; b -= (a * G[2]) * x.z;
     b -= (a * G[3]) * y.x; b -= (a * G[4]) * y.y; b -= (a * G[5]) * y.z;
     return b;
-}
-
-__device__ __forceinline__ void set_row(float* row, const V3& lin, const V3& ang)
-{
-    row[0] = lin.x; row[1] = lin.y; row[2] = lin.z; row[3] = ang.x; row[4] = ang.y; row[5] = ang.z;
 }
 
 // J M^-1 row: linear (1/mass) * J_lin, angular J_ang * Iinv   (Contact.cpp:90-93, Hinge.cpp:59-62)
@@ -387,7 +449,8 @@ __global__ void __launch_bounds__(128) k_contact_rows(View v, float h)
     }
     const int packed = (ids.x | (b0.fixed ? 0x8000 : 0)) | ((ids.y | (b1.fixed ? 0x8000 : 0)) << 16);
     float4* R = v.crow;
-#define CROW(f) R[at_crow(v, f, slot, scene)]
+    const int pos = contact_pos(v, slot, scene);                 // slot, or its place in the level-ordered stream
+#define CROW(f) R[at_crow(v, f, pos, scene)]
     CROW(0)  = mk4(n, 1.0f / b0.mass);
     CROW(1)  = mk4(t, 1.0f / b1.mass);
     CROW(2)  = mk4(bb, __int_as_float(packed));
@@ -410,13 +473,6 @@ __global__ void __launch_bounds__(128) k_contact_rows(View v, float h)
 // ------------------------------------------------------------------------------------
 // K5  joint Jacobians, J M^-1, dim x dim diagonal block + LDL^T, RHS
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void set_hat(float J[5][6], const V3& a)
-{
-    J[0][3] = 0.f;   J[0][4] = -a.z; J[0][5] = a.y;
-    J[1][3] = a.z;   J[1][4] = 0.f;  J[1][5] = -a.x;
-    J[2][3] = -a.y;  J[2][4] = a.x;  J[2][5] = 0.f;
-}
-
 __global__ void __launch_bounds__(128) k_joint_rows(View v, float h)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -501,7 +557,8 @@ __global__ void __launch_bounds__(128) k_joint_rows(View v, float h)
     const int id0 = def.y | (b0.fixed ? BODY_FIXED_BIT : 0);
     const int id1 = def.z | (b1.fixed ? BODY_FIXED_BIT : 0);
     float4* R = v.jrow;
-#define JROW(f) R[at_jrow(v, f, slot, scene)]
+    const int pos = joint_pos(v, slot, scene);
+#define JROW(f) R[at_jrow(v, f, pos, scene)]
     JROW(0) = mk4(rr0, 1.0f / b0.mass);
     JROW(1) = mk4(rr1, 1.0f / b1.mass);
     JROW(2) = mk4(nxu, __int_as_float(id0));
@@ -513,29 +570,14 @@ __global__ void __launch_bounds__(128) k_joint_rows(View v, float h)
     }
     JROW(14) = make_float4(L[1][0], L[2][0], L[2][1], L[3][0]);
     JROW(15) = make_float4(L[3][1], L[3][2], L[4][0], L[4][1]);
-    JROW(16) = make_float4(L[4][2], L[4][3], __int_as_float(dim), 0.f);
+    JROW(16) = make_float4(L[4][2], L[4][3], __int_as_float(dim), __int_as_float(slot));
 #undef JROW
 }
 
 // ------------------------------------------------------------------------------------
-// K6  Box-PGS sweep: one thread per scene, rows in the reference's sequential order
+// K6  Box-PGS sweep, thread-per-scene variant: rows in the reference's sequential order
+// (row arithmetic in pgs_math.cuh)
 // ------------------------------------------------------------------------------------
-// The reference recomputes, for every row block i, x = b_i - sum_{k != i} JMinv_i (J_k^T lambda_k)
-// over all constraints sharing a non-fixed body (SolverBoxPGS.cpp:49-82). Here each non-fixed
-// body carries w_body = sum_k J_k,body^T lambda_k, so the same x is
-//   b_i - JMinv_i0 (w_0 - J_i0^T lambda_i) - JMinv_i1 (w_1 - J_i1^T lambda_i)
-// and after the block solve w += J^T (lambda_new - lambda_old). Gauss-Seidel order, the
-// solveContact projection (:94-113) and the joint block solve (:115-118) are unchanged.
-__device__ __forceinline__ V3 fma3(float s, const V3& a, const V3& acc)
-{
-    return mk3(fmaf(s, a.x, acc.x), fmaf(s, a.y, acc.y), fmaf(s, a.z, acc.z));
-}
-__device__ __forceinline__ float dotf(const V3& a, const V3& b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
-__device__ __forceinline__ V3 lin3(const V3& a, float s0, const V3& b, float s1, const V3& c, float s2)
-{
-    return fma3(s2, c, fma3(s1, b, s0 * a));
-}
-
 // One-entry write-back register cache of a body accumulator. Rows are visited in (i, j) order, so
 // body0 of consecutive rows is almost always the same body (all contacts of body i, all hinges of a
 // chassis): it stays in registers instead of making a dependent HBM round trip per row.
@@ -571,171 +613,53 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// solveContact (SolverBoxPGS.cpp:94-113) on a row record F (CROW_FIELDS float4, layout.cuh).
-__device__ __forceinline__ void contact_visit(const View& v, int slot, int scene, float mu, const float4* F, const float4& lam, WCache& wc)
+// fetch the accumulators of a row's two bodies (body0 through the register cache), solve, write back
+template <class Solve>
+__device__ __forceinline__ void with_bodies(const View& v, int scene, WCache& wc, int id0, int id1, bool dyn0, bool dyn1, Solve solve)
 {
-    const V3 n = mk3(F[0]), t = mk3(F[1]), b = mk3(F[2]);
-    const float im0 = F[0].w, im1 = F[1].w;
-    const int ids = __float_as_int(F[2].w);
-    const int id0 = ids & 0x7fff, id1 = (ids >> 16) & 0x7fff;
-    const bool dyn0 = !(ids & 0x8000), dyn1 = !(ids & 0x80000000);
-    const V3 a0n = mk3(F[3]), a0t = mk3(F[4]), a0b = mk3(F[5]);
-    const V3 a1n = mk3(F[6]), a1t = mk3(F[7]), a1b = mk3(F[8]);
-    float x0 = F[3].w, x1 = F[4].w, x2 = F[5].w;
-    const float l0 = lam.x, l1 = lam.y, l2 = lam.z;
-    const V3 dl = lin3(n, l0, t, l1, b, l2);                     // J0_lin^T lambda ( = -J1_lin^T lambda)
-    // body1 first: its accumulator usually comes from HBM, issue the load before the body0 math
     size_t w1i = 0;
-    V3 w1l, w1a;
+    V3 w1l = mk3(0.f, 0.f, 0.f), w1a = w1l;
     const bool hit1 = dyn1 && (id1 == wc.id) && !(dyn0 && id0 != wc.id);
     if (dyn0) wc_acquire(v, scene, wc, id0);
     if (dyn1) {
         if (hit1) { w1l = wc.l; w1a = wc.a; }
         else { w1i = at(v, id1, scene); w1l = mk3(v.wl[w1i]); w1a = mk3(v.wa[w1i]); }
     }
-    if (dyn0) {
-        const V3 tl = wc.l - dl;
-        const V3 ta = wc.a - lin3(a0n, l0, a0t, l1, a0b, l2);
-        x0 -= fmaf(im0, dotf(n, tl), dotf(mk3(F[9]), ta));
-        x1 -= fmaf(im0, dotf(t, tl), dotf(mk3(F[10]), ta));
-        x2 -= fmaf(im0, dotf(b, tl), dotf(mk3(F[11]), ta));
+    if (hit1) {                                  // body0 is fixed here, the cache line is body1's
+        V3 dl = mk3(0.f, 0.f, 0.f), da = dl;
+        solve(dl, da, w1l, w1a);
+        wc.l = w1l; wc.a = w1a;
+    } else {
+        solve(wc.l, wc.a, w1l, w1a);
+        if (dyn1) { v.wl[w1i] = mk4(w1l, 0.f); v.wa[w1i] = mk4(w1a, 0.f); }
     }
-    if (dyn1) {
-        const V3 tl = w1l + dl;
-        const V3 ta = w1a - lin3(a1n, l0, a1t, l1, a1b, l2);
-        x0 -= fmaf(-im1, dotf(n, tl), dotf(mk3(F[12]), ta));
-        x1 -= fmaf(-im1, dotf(t, tl), dotf(mk3(F[13]), ta));
-        x2 -= fmaf(-im1, dotf(b, tl), dotf(mk3(F[14]), ta));
-    }
-    // x aliases lambda in the reference, so l1, l2 on the first line are last sweep's values
-    const float A00 = F[6].w, A11 = F[7].w, A22 = F[8].w, A01 = F[9].w, A02 = F[10].w;
-    const float A10 = F[11].w, A12 = F[12].w, A20 = F[13].w, A21 = F[14].w;
-    float y0 = (x0 - A01 * l1 - A02 * l2) / (A00 + 1e-3f);
-    if (y0 < 0.0f) y0 = 0.0f;
-    const float lo = -mu * y0, hi = mu * y0;
-    float y1 = (x1 - A10 * y0 - A12 * l2) / A11;
-    if (y1 < lo) y1 = lo; else if (y1 > hi) y1 = hi;
-    float y2 = (x2 - A20 * y0 - A21 * y1) / A22;
-    if (y2 < lo) y2 = lo; else if (y2 > hi) y2 = hi;
-    const float d0 = y0 - l0, d1 = y1 - l1, d2 = y2 - l2;
-    const V3 ddl = lin3(n, d0, t, d1, b, d2);
-    if (dyn0) {
-        wc.l = wc.l + ddl;
-        wc.a = wc.a + lin3(a0n, d0, a0t, d1, a0b, d2);
-    }
-    if (dyn1) {
-        const V3 nl = w1l - ddl, na = w1a + lin3(a1n, d0, a1t, d1, a1b, d2);
-        if (hit1) { wc.l = nl; wc.a = na; }
-        else { v.wl[w1i] = mk4(nl, 0.f); v.wa[w1i] = mk4(na, 0.f); }
-    }
-    v.crow[at_crow(v, CROW_LAMBDA, slot, scene)] = make_float4(y0, y1, y2, 0.f);
 }
 
-struct JointRow {
-    V3 rr0, rr1, nxu, nxv; float im0, im1; int id0, id1;
-};
-__device__ __forceinline__ JointRow load_joint_head(const View& v, int slot, int scene)
+__device__ __forceinline__ void contact_visit(const View& v, int slot, int scene, float mu, const float4* F, const float4& lam, WCache& wc)
 {
-    JointRow j;
-    const float4 g0 = __ldg(&v.jrow[at_jrow(v, 0, slot, scene)]);
-    const float4 g1 = __ldg(&v.jrow[at_jrow(v, 1, slot, scene)]);
-    const float4 g2 = __ldg(&v.jrow[at_jrow(v, 2, slot, scene)]);
-    const float4 g3 = __ldg(&v.jrow[at_jrow(v, 3, slot, scene)]);
-    j.rr0 = mk3(g0); j.im0 = g0.w; j.rr1 = mk3(g1); j.im1 = g1.w;
-    j.nxu = mk3(g2); j.id0 = __float_as_int(g2.w); j.nxv = mk3(g3); j.id1 = __float_as_int(g3.w);
-    return j;
-}
-// J0^T lambda: linear (l0,l1,l2), angular rr0 x l_lin + l3 nxu + l4 nxv ; J1^T lambda is minus the
-// same with rr1 (J0 = [I hat(-rr0); 0 nxu; 0 nxv], J1 = [-I hat(rr1); 0 -nxu; 0 -nxv])
-__device__ __forceinline__ V3 joint_jt_ang(const V3& rr, const V3& nxu, const V3& nxv, const float* l)
-{
-    const V3 ll = mk3(l[0], l[1], l[2]);
-    return fma3(l[4], nxv, fma3(l[3], nxu, cross(rr, ll)));
+    const ContactIds c = contact_ids(F);
+    float4 out;
+    with_bodies(v, scene, wc, c.id0, c.id1, c.dyn0, c.dyn1, [&](V3& w0l, V3& w0a, V3& w1l, V3& w1a) {
+        out = contact_solve(F, lam, mu, c.dyn0, c.dyn1, w0l, w0a, w1l, w1a);
+    });
+    v.crow[at_crow(v, CROW_LAMBDA, slot, scene)] = out;
 }
 
 __device__ __forceinline__ void joint_visit(const View& v, int slot, int scene, WCache& wc)
 {
-    const JointRow j = load_joint_head(v, slot, scene);
-    float4 M0[5], M1[5];
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {
-        M0[r] = __ldg(&v.jrow[at_jrow(v, 4 + r, slot, scene)]);
-        M1[r] = __ldg(&v.jrow[at_jrow(v, 9 + r, slot, scene)]);
-    }
-    const float4 La = __ldg(&v.jrow[at_jrow(v, 14, slot, scene)]);
-    const float4 Lb = __ldg(&v.jrow[at_jrow(v, 15, slot, scene)]);
-    const float4 Lc = __ldg(&v.jrow[at_jrow(v, 16, slot, scene)]);
+    JointRec r;
+    load_joint_rec(v, slot, scene, r);
     const size_t ji = at(v, slot, scene);
     const float4 lam03 = v.jlam[ji];
     float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
-    float x[5] = { M0[0].w, M0[1].w, M0[2].w, M0[3].w, M0[4].w };
-    const bool dyn0 = j.id0 >= 0, dyn1 = j.id1 >= 0;
-    const int id0 = j.id0 & 0x7fffffff, id1 = j.id1 & 0x7fffffff;
-    const V3 ll = mk3(l[0], l[1], l[2]);
-    size_t w1i = 0;
-    V3 w1l, w1a;
-    const bool hit1 = dyn1 && (id1 == wc.id) && !(dyn0 && id0 != wc.id);
-    if (dyn0) wc_acquire(v, scene, wc, id0);
-    if (dyn1) {
-        if (hit1) { w1l = wc.l; w1a = wc.a; }
-        else { w1i = at(v, id1, scene); w1l = mk3(v.wl[w1i]); w1a = mk3(v.wa[w1i]); }
-    }
-    if (dyn0) {
-        const V3 tl = wc.l - ll;
-        const V3 ta = wc.a - joint_jt_ang(j.rr0, j.nxu, j.nxv, l);
-        x[0] -= fmaf(j.im0, tl.x, dotf(mk3(M0[0]), ta));
-        x[1] -= fmaf(j.im0, tl.y, dotf(mk3(M0[1]), ta));
-        x[2] -= fmaf(j.im0, tl.z, dotf(mk3(M0[2]), ta));
-        x[3] -= dotf(mk3(M0[3]), ta);
-        x[4] -= dotf(mk3(M0[4]), ta);
-    }
-    if (dyn1) {
-        const V3 tl = w1l + ll;
-        const V3 ta = w1a + joint_jt_ang(j.rr1, j.nxu, j.nxv, l);
-        x[0] -= fmaf(-j.im1, tl.x, dotf(mk3(M1[0]), ta));
-        x[1] -= fmaf(-j.im1, tl.y, dotf(mk3(M1[1]), ta));
-        x[2] -= fmaf(-j.im1, tl.z, dotf(mk3(M1[2]), ta));
-        x[3] -= dotf(mk3(M1[3]), ta);
-        x[4] -= dotf(mk3(M1[4]), ta);
-    }
-    // lambda = LDLT.solve(x)  (SolverBoxPGS.cpp:115-118,231)
-    const float L10 = La.x, L20 = La.y, L21 = La.z, L30 = La.w, L31 = Lb.x, L32 = Lb.y, L40 = Lb.z, L41 = Lb.w, L42 = Lc.x, L43 = Lc.y;
-    float y0 = x[0];
-    float y1 = fmaf(-L10, y0, x[1]);
-    float y2 = fmaf(-L21, y1, fmaf(-L20, y0, x[2]));
-    float y3 = fmaf(-L32, y2, fmaf(-L31, y1, fmaf(-L30, y0, x[3])));
-    float y4 = fmaf(-L43, y3, fmaf(-L42, y2, fmaf(-L41, y1, fmaf(-L40, y0, x[4]))));
-    y0 *= M1[0].w; y1 *= M1[1].w; y2 *= M1[2].w; y3 *= M1[3].w; y4 *= M1[4].w;
-    float n[5];
-    n[4] = y4;
-    n[3] = fmaf(-L43, n[4], y3);
-    n[2] = fmaf(-L42, n[4], fmaf(-L32, n[3], y2));
-    n[1] = fmaf(-L41, n[4], fmaf(-L31, n[3], fmaf(-L21, n[2], y1)));
-    n[0] = fmaf(-L40, n[4], fmaf(-L30, n[3], fmaf(-L20, n[2], fmaf(-L10, n[1], y0))));
-    float d[5];
-#pragma unroll
-    for (int r = 0; r < 5; ++r) d[r] = n[r] - l[r];
-    const V3 dl = mk3(d[0], d[1], d[2]);
-    if (dyn0) {
-        wc.l = wc.l + dl;
-        wc.a = wc.a + joint_jt_ang(j.rr0, j.nxu, j.nxv, d);
-    }
-    if (dyn1) {
-        const V3 nl = w1l - dl, na = w1a - joint_jt_ang(j.rr1, j.nxu, j.nxv, d);
-        if (hit1) { wc.l = nl; wc.a = na; }
-        else { v.wl[w1i] = mk4(nl, 0.f); v.wa[w1i] = mk4(na, 0.f); }
-    }
-    v.jlam[ji] = make_float4(n[0], n[1], n[2], n[3]);
-    v.jlam4[ji] = n[4];
+    const bool dyn0 = r.h.id0 >= 0, dyn1 = r.h.id1 >= 0;
+    with_bodies(v, scene, wc, r.h.id0 & 0x7fffffff, r.h.id1 & 0x7fffffff, dyn0, dyn1, [&](V3& w0l, V3& w0a, V3& w1l, V3& w1a) {
+        joint_solve(r, l, dyn0, dyn1, w0l, w0a, w1l, w1a);
+    });
+    v.jlam[ji] = make_float4(l[0], l[1], l[2], l[3]);
+    v.jlam4[ji] = l[4];
 }
 
-// calcConstraintForces tail (RigidBodySystem.cpp:185-220): f = (J^T lambda) / dt with the
-// reference's left-to-right row sum, no fused multiply-adds.
-__device__ __forceinline__ V3 seq3(const V3& a, float s0, const V3& b, float s1, const V3& c, float s2)
-{
-    return mk3(((0.f + a.x * s0) + b.x * s1) + c.x * s2, ((0.f + a.y * s0) + b.y * s1) + c.y * s2,
-               ((0.f + a.z * s0) + b.z * s1) + c.z * s2);
-}
 __device__ __forceinline__ void add_force(const View& v, int body, int scene, const V3& fl, const V3& fa)
 {
     const size_t i = at(v, body, scene);
@@ -747,7 +671,7 @@ enum { PGS_THREADS = 32, PGS_STAGES = 2, PGS_MIN_CTAS = 12 };
 
 __global__ void __launch_bounds__(PGS_THREADS, PGS_MIN_CTAS) k_pgs(View v, float dt, int iters, float mu)
 {
-    // thread-private staging ring for the contact row stream: [stage][field][thread] float4;
+    // thread-private staging ring for the contact row stream: [stage][field][thread] float4
     __shared__ float4 ring[PGS_STAGES][CROW_FIELDS][PGS_THREADS];
     const int tid = threadIdx.x;
     const int scene = blockIdx.x * PGS_THREADS + tid;
@@ -761,16 +685,17 @@ __global__ void __launch_bounds__(PGS_THREADS, PGS_MIN_CTAS) k_pgs(View v, float
         const size_t ji = at(v, s, scene);
         const float4 lam03 = v.jlam[ji];
         const float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
-        const V3 ll = mk3(l[0], l[1], l[2]);
         if (j.id0 >= 0) {
             const size_t wi = at(v, j.id0, scene);
-            v.wl[wi] = mk4(mk3(v.wl[wi]) + ll, 0.f);
-            v.wa[wi] = mk4(mk3(v.wa[wi]) + joint_jt_ang(j.rr0, j.nxu, j.nxv, l), 0.f);
+            V3 wl = mk3(v.wl[wi]), wa = mk3(v.wa[wi]);
+            joint_seed(j, l, 0, wl, wa);
+            v.wl[wi] = mk4(wl, 0.f); v.wa[wi] = mk4(wa, 0.f);
         }
         if (j.id1 >= 0) {
             const size_t wi = at(v, j.id1 & 0x7fffffff, scene);
-            v.wl[wi] = mk4(mk3(v.wl[wi]) - ll, 0.f);
-            v.wa[wi] = mk4(mk3(v.wa[wi]) - joint_jt_ang(j.rr1, j.nxu, j.nxv, l), 0.f);
+            V3 wl = mk3(v.wl[wi]), wa = mk3(v.wa[wi]);
+            joint_seed(j, l, 1, wl, wa);
+            v.wl[wi] = mk4(wl, 0.f); v.wa[wi] = mk4(wa, 0.f);
         }
     }
     WCache wc; wc.id = -1; wc.l = mk3(0.f, 0.f, 0.f); wc.a = wc.l;
@@ -785,7 +710,6 @@ __global__ void __launch_bounds__(PGS_THREADS, PGS_MIN_CTAS) k_pgs(View v, float
     auto fetch = [&]() {
         if (fetched < total) {
             const int st = fetched % PGS_STAGES;
-#pragma unroll
             const float4* src = &v.crow[at_crow(v, 0, fetch_row, scene)];       // one contiguous 8 KB tile per warp
 #pragma unroll
             for (int f = 0; f < CROW_FIELDS; ++f) cp_async16(&ring[st][f][tid], src + f * 32);
@@ -819,19 +743,9 @@ __global__ void __launch_bounds__(PGS_THREADS, PGS_MIN_CTAS) k_pgs(View v, float
         const size_t ji = at(v, s, scene);
         const float4 lam03 = v.jlam[ji];
         const float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
-        float J0[5][6], J1[5][6];
-        for (int r = 0; r < 5; ++r) for (int k = 0; k < 6; ++k) { J0[r][k] = 0.f; J1[r][k] = 0.f; }
-        J0[0][0] = J0[1][1] = J0[2][2] = 1.f; J1[0][0] = J1[1][1] = J1[2][2] = -1.f;
-        set_hat(J0, -j.rr0); set_hat(J1, j.rr1);
-        set_row(J0[3], mk3(0.f, 0.f, 0.f), j.nxu); set_row(J0[4], mk3(0.f, 0.f, 0.f), j.nxv);
-        set_row(J1[3], mk3(0.f, 0.f, 0.f), -j.nxu); set_row(J1[4], mk3(0.f, 0.f, 0.f), -j.nxv);
         const int dim = __float_as_int(__ldg(&v.jrow[at_jrow(v, 16, s, scene)]).z);
         float f0[6], f1[6];
-        for (int k = 0; k < 6; ++k) {
-            float a0 = 0.f, a1 = 0.f;
-            for (int r = 0; r < 5; ++r) if (r < dim) { a0 += J0[r][k] * l[r]; a1 += J1[r][k] * l[r]; }
-            f0[k] = a0 / dt; f1[k] = a1 / dt;
-        }
+        joint_force(j, dim, l, dt, f0, f1);
         add_force(v, j.id0 & 0x7fffffff, scene, mk3(f0[0], f0[1], f0[2]), mk3(f0[3], f0[4], f0[5]));   // unconditional (:189-192)
         add_force(v, j.id1 & 0x7fffffff, scene, mk3(f1[0], f1[1], f1[2]), mk3(f1[3], f1[4], f1[5]));
     }
@@ -840,14 +754,10 @@ __global__ void __launch_bounds__(PGS_THREADS, PGS_MIN_CTAS) k_pgs(View v, float
 #pragma unroll
         for (int f = 0; f < 9; ++f) F[f] = __ldg(&v.crow[at_crow(v, f, s, scene)]);
         const float4 lam = v.crow[at_crow(v, CROW_LAMBDA, s, scene)];
-        const int ids = __float_as_int(F[2].w);
-        const V3 n = mk3(F[0]), t = mk3(F[1]), b = mk3(F[2]);
-        if (!(ids & 0x8000))
-            add_force(v, ids & 0x7fff, scene, seq3(n, lam.x, t, lam.y, b, lam.z) / dt,
-                      seq3(mk3(F[3]), lam.x, mk3(F[4]), lam.y, mk3(F[5]), lam.z) / dt);
-        if (!(ids & 0x80000000))
-            add_force(v, (ids >> 16) & 0x7fff, scene, seq3(-n, lam.x, -t, lam.y, -b, lam.z) / dt,
-                      seq3(mk3(F[6]), lam.x, mk3(F[7]), lam.y, mk3(F[8]), lam.z) / dt);
+        const ContactIds c = contact_ids(F);
+        V3 fl, fa;
+        if (c.dyn0) { contact_force(F, lam, dt, 0, fl, fa); add_force(v, c.id0, scene, fl, fa); }
+        if (c.dyn1) { contact_force(F, lam, dt, 1, fl, fa); add_force(v, c.id1, scene, fl, fa); }
     }
     if (v.profiling) {
         atomicAdd(&v.visit_counters[0], (unsigned long long)nc * iters);
@@ -882,7 +792,7 @@ __device__ void kry_apply(const View& v, int scene, int nb, int nj, int vin, int
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = 0; i < nb; ++i) { v.wl[at(v, i, scene)] = z4; v.wa[at(v, i, scene)] = z4; }
     for (int s = 0; s < nj; ++s) {
-        const JointRow j = load_joint_head(v, s, scene);
+        const JointRow j = load_joint_head(v, joint_pos(v, s, scene), scene);
         float x[5]; kry_load(v, vin, s, scene, x);
         const V3 ll = mk3(x[0], x[1], x[2]);
         if (j.id0 >= 0) {
@@ -897,8 +807,9 @@ __device__ void kry_apply(const View& v, int scene, int nb, int nj, int vin, int
         }
     }
     for (int s = 0; s < nj; ++s) {
-        const JointRow j = load_joint_head(v, s, scene);
-        const int dim = __float_as_int(__ldg(&v.jrow[at_jrow(v, 16, s, scene)]).z);
+        const int jp = joint_pos(v, s, scene);
+        const JointRow j = load_joint_head(v, jp, scene);
+        const int dim = __float_as_int(__ldg(&v.jrow[at_jrow(v, 16, jp, scene)]).z);
         float x[5]; kry_load(v, vin, s, scene, x);
         float y[5];
 #pragma unroll
@@ -908,7 +819,7 @@ __device__ void kry_apply(const View& v, int scene, int nb, int nj, int vin, int
             const V3 ul = mk3(v.wl[wi]), ua = mk3(v.wa[wi]);
 #pragma unroll
             for (int r = 0; r < 5; ++r) {
-                const V3 m = mk3(__ldg(&v.jrow[at_jrow(v, 4 + r, s, scene)]));
+                const V3 m = mk3(__ldg(&v.jrow[at_jrow(v, 4 + r, jp, scene)]));
                 y[r] += (r < 3 ? j.im0 * (r == 0 ? ul.x : (r == 1 ? ul.y : ul.z)) : 0.f) + dotf(m, ua);
             }
         }
@@ -917,7 +828,7 @@ __device__ void kry_apply(const View& v, int scene, int nb, int nj, int vin, int
             const V3 ul = mk3(v.wl[wi]), ua = mk3(v.wa[wi]);
 #pragma unroll
             for (int r = 0; r < 5; ++r) {
-                const V3 m = mk3(__ldg(&v.jrow[at_jrow(v, 9 + r, s, scene)]));
+                const V3 m = mk3(__ldg(&v.jrow[at_jrow(v, 9 + r, jp, scene)]));
                 y[r] += (r < 3 ? -j.im1 * (r == 0 ? ul.x : (r == 1 ? ul.y : ul.z)) : 0.f) + dotf(m, ua);
             }
         }
@@ -950,7 +861,7 @@ __global__ void __launch_bounds__(64) k_krylov(View v, int iters)
     for (int s = 0; s < nj; ++s) {
         float b[5], z[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
 #pragma unroll
-        for (int r = 0; r < 5; ++r) b[r] = __ldg(&v.jrow[at_jrow(v, 4 + r, s, scene)]).w;
+        for (int r = 0; r < 5; ++r) b[r] = __ldg(&v.jrow[at_jrow(v, 4 + r, joint_pos(v, s, scene), scene)]).w;
         kry_store(v, KV_X, s, scene, z); kry_store(v, KV_B, s, scene, b);
         kry_store(v, KV_R, s, scene, b); kry_store(v, KV_P, s, scene, b);
     }
@@ -1185,7 +1096,8 @@ __global__ void k_export_contacts(View v, int scene, int n, int* body0, int* bod
     if (n3) { n3[3 * c] = nn.x; n3[3 * c + 1] = nn.y; n3[3 * c + 2] = nn.z; }
     if (phi) phi[c] = pp.w;
     float4 F[CROW_FIELDS];
-    for (int f = 0; f < CROW_FIELDS; ++f) F[f] = v.crow[at_crow(v, f, c, scene)];
+    const int cp_ = contact_pos(v, c, scene);
+    for (int f = 0; f < CROW_FIELDS; ++f) F[f] = v.crow[at_crow(v, f, cp_, scene)];
     if (t3) { t3[3 * c] = F[1].x; t3[3 * c + 1] = F[1].y; t3[3 * c + 2] = F[1].z; }
     if (b3) { b3[3 * c] = F[2].x; b3[3 * c + 1] = F[2].y; b3[3 * c + 2] = F[2].z; }
     if (lam3) { const float4 l = F[CROW_LAMBDA]; lam3[3 * c] = l.x; lam3[3 * c + 1] = l.y; lam3[3 * c + 2] = l.z; }
@@ -1211,7 +1123,8 @@ __global__ void k_export_joints(View v, int scene, int n, float* J0, float* J1, 
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     float4 G[JROW_FIELDS];
-    for (int f = 0; f < JROW_FIELDS; ++f) G[f] = v.jrow[at_jrow(v, f, s, scene)];
+    const int jp_ = joint_pos(v, s, scene);
+    for (int f = 0; f < JROW_FIELDS; ++f) G[f] = v.jrow[at_jrow(v, f, jp_, scene)];
     const V3 rr0 = mk3(G[0]), rr1 = mk3(G[1]), nxu = mk3(G[2]), nxv = mk3(G[3]);
     const float im0 = G[0].w, im1 = G[1].w;
     const int dim = __float_as_int(G[16].z);
@@ -1260,13 +1173,14 @@ static inline unsigned blocks_for(size_t n, int bs) { return (unsigned)((n + bs 
 void launch_prepare(const View& v, cudaStream_t s) { k_prepare<<<blocks_for((size_t)v.NB * v.B, 256), 256, 0, s>>>(v); }
 void launch_detect(const View& v, cudaStream_t s)
 {
-    // warps per CTA: as many as fit ~96 KB of staged proxies (20 B / body / warp), at most 8
-    const size_t per_warp = (size_t)v.NB * 20;
+    // warps per CTA: as many as fit ~96 KB of staged proxies (20 B / body / warp) and, in level mode, the
+    // level tables (4 B / body + 4 B / contact slot / warp), at most 8
+    const size_t per_warp = (size_t)v.NB * 20 + (v.level_mode ? ((size_t)v.NB + v.NC + 2) * 4 : 0);
     int warps = 8;
     while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
     const size_t smem = per_warp * warps;
     // tiny scenes (car: 15 pairs) leave a warp idle: one thread per scene is faster there; huge ones do not fit
-    if (v.NB < 24 || smem > 200 * 1024) { k_detect_serial<<<blocks_for(v.B, 128), 128, 0, s>>>(v); return; }
+    if ((v.NB < 24 && !v.level_mode) || smem > 200 * 1024) { k_detect_serial<<<blocks_for(v.B, 128), 128, 0, s>>>(v); return; }
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_detect_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
     k_detect_warp<<<blocks_for(v.B, warps), warps * 32, smem, s>>>(v, warps);

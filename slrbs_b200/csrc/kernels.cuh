@@ -20,6 +20,11 @@ void launch_contact_rows(const View& v, float h, cudaStream_t s);
 void launch_joint_rows(const View& v, float h, cudaStream_t s);
 void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s);
 void launch_krylov(const View& v, int solver_id, int iters, cudaStream_t s);
+// level-scheduled solver (pgs_level.cu)
+void launch_joint_levels(const View& v, cudaStream_t s);
+void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, cudaStream_t s);
+int  level_group_size(const View& v, int requested);
+bool level_mode_fits(int max_bodies);
 void launch_integrate(const View& v, float dt, cudaStream_t s);
 
 void launch_upload_bodies(const View& v, int scene0, int ns, int n, const int* counts, const BodyStage& st, cudaStream_t s);

@@ -35,11 +35,13 @@ enum { BODY_FIXED_BIT = (int)0x80000000 };
 // Joint row record (JROW_FIELDS float4 per joint; see k_joint_rows):
 //  0 rr0 | im0     2 nxu | body0     4..8  J0Minv angular rows 0..4 | rhs[r]
 //  1 rr1 | im1     3 nxv | body1     9..13 J1Minv angular rows 0..4 | 1/D[r]
-//  14 (L10 L20 L21 L30)  15 (L31 L32 L40 L41)  16 (L42 L43 dim -)
+//  14 (L10 L20 L21 L30)  15 (L31 L32 L40 L41)  16 (L42 L43 dim slot)
 // J0 = [I hat(-rr0); 0 nxu; 0 nxv], J1 = [-I hat(rr1); 0 -nxu; 0 -nxv] (Hinge.cpp:50-57).
 
 struct View {
     int B, NB, NJ, NC;
+    int level_mode;                       // 0: rows as warp-blocked tiles in slot order (k_pgs)
+                                          // 1: rows scene-major in dependency-level order (k_pgs_lv)
     int *nbodies, *njoints, *ncontacts;   // [B]
     int *overflow;                        // [1] set when a scene exceeded NC
     unsigned long long *visit_counters;   // [2] contact visits, joint visits (profiling)
@@ -68,25 +70,38 @@ struct View {
     float4 *jr0, *jq0, *jr1, *jq1;
     float4 *jlam;       // lambda 0..3
     float  *jlam4;      // lambda 4
-    float4 *jrow;       // [B/32][NJ][JROW_FIELDS][32]
+    float4 *jrow;       // mode 0: [B/32][NJ][JROW_FIELDS][32]; mode 1: [B][JROW_FIELDS][NJ]
+    int    *jpos;       // [NJ][B] position of joint slot in the level-ordered row stream (level mode)
+    int    *jlev_end;   // [NJ+1][B] end offset of joint level l (1-based; entry 0 is 0)
+    int    *njlev;      // [B] number of joint levels
     float  *kry;        // [7][5][NJ][B] Krylov work vectors x, r, p, b, Ap, Ar, Ax (allocated on first CG/CR solve)
     // contacts, [NC][B]
     int2   *cids;       // body0, body1 (role ordered: sphere/box, cylinder/plane)
     float4 *cp;         // p | pene
     float4 *cn;         // n | -
-    float4 *crow;       // [B/32][NC][CROW_FIELDS][32]
+    float4 *crow;       // mode 0: [B/32][NC][CROW_FIELDS][32]; mode 1: [B][CROW_FIELDS][NC]
+    int    *cpos;       // [NC][B] position of contact slot in the level-ordered row stream (level mode)
+    int    *clev_end;   // [NC+1][B] end offset of contact level l (1-based; entry 0 is 0)
+    int    *nclev;      // [B] number of contact levels
+    int    *lv_last;    // [NB][B] scratch: last level that touched a body
 };
 
 __host__ __device__ __forceinline__ size_t at(const View& v, int slot, int scene) { return (size_t)slot * v.B + scene; }
 __host__ __device__ __forceinline__ size_t at_kry(const View& v, int vec, int k, int slot, int scene) { return (((size_t)vec * 5 + k) * v.NJ + slot) * v.B + scene; }
 __host__ __device__ __forceinline__ size_t at_b9(const View& v, int k, int slot, int scene) { return ((size_t)k * v.NB + slot) * v.B + scene; }
-__host__ __device__ __forceinline__ size_t at_crow(const View& v, int f, int slot, int scene)
+// row record addressing: `pos` is the contact / joint slot in mode 0 and the position in the
+// level-ordered stream (cpos / jpos of the slot) in mode 1
+__host__ __device__ __forceinline__ size_t at_crow(const View& v, int f, int pos, int scene)
 {
-    return ((((size_t)(scene >> 5) * v.NC + slot) * CROW_FIELDS + f) << 5) + (scene & 31);
+    if (v.level_mode) return ((size_t)scene * CROW_FIELDS + f) * v.NC + pos;
+    return ((((size_t)(scene >> 5) * v.NC + pos) * CROW_FIELDS + f) << 5) + (scene & 31);
 }
-__host__ __device__ __forceinline__ size_t at_jrow(const View& v, int f, int slot, int scene)
+__host__ __device__ __forceinline__ size_t at_jrow(const View& v, int f, int pos, int scene)
 {
-    return ((((size_t)(scene >> 5) * v.NJ + slot) * JROW_FIELDS + f) << 5) + (scene & 31);
+    if (v.level_mode) return ((size_t)scene * JROW_FIELDS + f) * v.NJ + pos;
+    return ((((size_t)(scene >> 5) * v.NJ + pos) * JROW_FIELDS + f) << 5) + (scene & 31);
 }
+__host__ __device__ __forceinline__ int contact_pos(const View& v, int slot, int scene) { return v.level_mode ? v.cpos[at(v, slot, scene)] : slot; }
+__host__ __device__ __forceinline__ int joint_pos(const View& v, int slot, int scene) { return v.level_mode ? v.jpos[at(v, slot, scene)] : slot; }
 
 }  // namespace slrbs

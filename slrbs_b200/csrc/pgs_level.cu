@@ -1,0 +1,298 @@
+// pgs_level.cu -- level-scheduled Box-PGS: the reference's sequential Gauss-Seidel order, run in parallel.
+//
+// SolverBoxPGS.cpp:217-248 visits the row blocks strictly one after another. A row only reads and
+// writes the accumulators of its own (non-fixed) bodies, so the result of the sequential sweep is
+// fully determined by, for every body, the ORDER of the rows that touch it. k_levels gives every row
+// the level  L(row) = 1 + max(L of the previous row on each of its non-fixed bodies): rows of one
+// level share no dynamic body, every body still sees its rows in the original order, and processing
+// level after level therefore reproduces the sequential sweep exactly (bit for bit, the row maths
+// being the same functions of pgs_math.cuh that the thread-per-scene kernel uses). The marble box's
+// ~450 rows fall into ~50 levels, a 1000-sphere pile's ~2800 rows into ~80.
+//
+// k_joint_levels  thread / scene  joint levels + stable counting sort -> jpos (row position in the level-
+//                                 ordered stream) and jlev_end (level boundaries); joints are static, so this
+//                                 runs only after an upload. Contact levels are assigned by the narrow-phase
+//                                 warp as it emits the contacts (k_detect_warp in kernels.cu).
+// k_pgs_lv   G lanes / scene  body accumulators of the scene in shared memory, row records streamed
+//                             from HBM in level order (scene-major [field][pos] so the lanes of a level
+//                             read consecutive records), group barrier between levels
+#include "kernels.cuh"
+#include "pgs_math.cuh"
+
+namespace slrbs {
+
+// ------------------------------------------------------------------------------------
+// joint levels (joints and contacts form two separate level sequences: every sweep runs all joint
+// levels, then all contact levels, which is what "all joints, then all contacts" means for a body)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_joint_levels(View v)
+{
+    const int scene = blockIdx.x * blockDim.x + threadIdx.x;
+    if (scene >= v.B) return;
+    const int nb = v.nbodies[scene], nj = v.njoints[scene];
+    for (int i = 0; i < nb; ++i) v.lv_last[at(v, i, scene)] = 0;
+    for (int l = 0; l <= nj; ++l) v.jlev_end[at(v, l, scene)] = 0;
+    int nl = 0;
+    for (int s = 0; s < nj; ++s) {
+        const int4 def = v.jdef[at(v, s, scene)];
+        const bool dyn0 = !(v.flags[at(v, def.y, scene)] & FLAG_FIXED), dyn1 = !(v.flags[at(v, def.z, scene)] & FLAG_FIXED);
+        int L = 0;
+        if (dyn0) L = max(L, v.lv_last[at(v, def.y, scene)]);
+        if (dyn1) L = max(L, v.lv_last[at(v, def.z, scene)]);
+        ++L;
+        if (dyn0) v.lv_last[at(v, def.y, scene)] = L;
+        if (dyn1) v.lv_last[at(v, def.z, scene)] = L;
+        v.jpos[at(v, s, scene)] = L;
+        v.jlev_end[at(v, L, scene)] += 1;
+        nl = max(nl, L);
+    }
+    int start = 0;
+    for (int l = 1; l <= nl; ++l) { const int c = v.jlev_end[at(v, l, scene)]; v.jlev_end[at(v, l, scene)] = start; start += c; }
+    for (int s = 0; s < nj; ++s) {
+        const int L = v.jpos[at(v, s, scene)];
+        v.jpos[at(v, s, scene)] = v.jlev_end[at(v, L, scene)]++;       // afterwards jlev_end[L] is the end of level L
+    }
+    v.njlev[scene] = nl;
+}
+
+// ------------------------------------------------------------------------------------
+// solve
+// ------------------------------------------------------------------------------------
+enum { LV_THREADS = 128 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+struct BodyW { float4* w; };     // shared-memory accumulators of one scene: [body][2] (linear, angular)
+__device__ __forceinline__ void ld_w(const float4* w, int body, V3& l, V3& a) { l = mk3(w[2 * body]); a = mk3(w[2 * body + 1]); }
+__device__ __forceinline__ void st_w(float4* w, int body, const V3& l, const V3& a) { w[2 * body] = mk4(l, 0.f); w[2 * body + 1] = mk4(a, 0.f); }
+
+template <int G>
+__device__ __forceinline__ void group_sync(unsigned mask)
+{
+    if (G >= 32) __syncwarp(); else __syncwarp(mask);
+}
+
+template <int G>
+__global__ void __launch_bounds__(LV_THREADS) k_pgs_lv(View v, float dt, int iters, float mu)
+{
+    extern __shared__ float4 smem_w[];
+    constexpr int SPC = LV_THREADS / G;                          // scenes per CTA
+    const int grp = threadIdx.x / G, gl = threadIdx.x % G;
+    const int scene = blockIdx.x * SPC + grp;
+    const unsigned mask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
+    if (scene >= v.B) return;                                    // whole groups leave together
+    float4* w = smem_w + (size_t)grp * v.NB * 2;
+    const int nb = v.nbodies[scene], nj = v.njoints[scene], nc = v.ncontacts[scene];
+    const int njl = v.njlev[scene], ncl = v.nclev[scene];
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int i = gl; i < 2 * nb; i += G) w[i] = z4;
+    group_sync<G>(mask);
+    // joints keep last step's lambda (Hinge.cpp:33-63 never zeroes it): seed w with it, level by level
+    for (int lev = 1, p0 = 0; lev <= njl; ++lev) {
+        const int p1 = v.jlev_end[at(v, lev, scene)];
+        for (int p = p0 + gl; p < p1; p += G) {
+            const JointRow j = load_joint_head(v, p, scene);
+            const int slot = __float_as_int(__ldg(&v.jrow[at_jrow(v, 16, p, scene)]).w);
+            const size_t ji = at(v, slot, scene);
+            const float4 lam03 = v.jlam[ji];
+            const float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
+            V3 wl, wa;
+            if (j.id0 >= 0) { ld_w(w, j.id0, wl, wa); joint_seed(j, l, 0, wl, wa); st_w(w, j.id0, wl, wa); }
+            if (j.id1 >= 0) { const int b = j.id1 & 0x7fffffff; ld_w(w, b, wl, wa); joint_seed(j, l, 1, wl, wa); st_w(w, b, wl, wa); }
+        }
+        p0 = p1;
+        group_sync<G>(mask);
+    }
+
+    // thread-private ring [stage][field][thread] behind the scenes' accumulators
+    float4* ring = smem_w + (size_t)SPC * v.NB * 2;
+    const bool lam_direct = nc <= 2 * G;                       // too few chunks: a prefetched lambda could be stale
+    int it_stage = 0;
+    auto issue = [&](int p0, int cnt, int st) {
+        if (gl < cnt) {
+#pragma unroll
+            for (int f = 0; f < CROW_FIELDS; ++f)
+                cp_async16(&ring[(st * CROW_FIELDS + f) * LV_THREADS + threadIdx.x], &v.crow[at_crow(v, f, p0 + gl, scene)]);
+        }
+        cp_async_commit();
+    };
+
+    for (int it = 0; it < iters; ++it) {                          // SolverBoxPGS.cpp:217-248
+        for (int lev = 1, p0 = 0; lev <= njl; ++lev) {
+            const int p1 = v.jlev_end[at(v, lev, scene)];
+            for (int p = p0 + gl; p < p1; p += G) {
+                JointRec r;
+                load_joint_rec(v, p, scene, r);
+                const size_t ji = at(v, joint_slot(r), scene);
+                const float4 lam03 = v.jlam[ji];
+                float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
+                const bool dyn0 = r.h.id0 >= 0, dyn1 = r.h.id1 >= 0;
+                const int b0 = r.h.id0 & 0x7fffffff, b1 = r.h.id1 & 0x7fffffff;
+                V3 w0l = mk3(0.f, 0.f, 0.f), w0a = w0l, w1l = w0l, w1a = w0l;
+                if (dyn0) ld_w(w, b0, w0l, w0a);
+                if (dyn1) ld_w(w, b1, w1l, w1a);
+                joint_solve(r, l, dyn0, dyn1, w0l, w0a, w1l, w1a);
+                if (dyn0) st_w(w, b0, w0l, w0a);
+                if (dyn1) st_w(w, b1, w1l, w1a);
+                v.jlam[ji] = make_float4(l[0], l[1], l[2], l[3]);
+                v.jlam4[ji] = l[4];
+            }
+            p0 = p1;
+            group_sync<G>(mask);
+        }
+        // contact levels: the rows of the NEXT chunk (up to G rows of one level) are copied into the lanes'
+        // private ring slots with cp.async while the current chunk is solved
+        if (nc > 0) {
+            int lev = 1, p0 = 0, end = v.clev_end[at(v, 1, scene)];
+            if (it == 0) { issue(p0, min(G, end - p0), 0); }
+            int st = it_stage;
+            while (true) {
+                const int cnt = min(G, end - p0);
+                // next chunk: same level, next level, or the first chunk of the next sweep
+                int nlev = lev, np0 = p0 + cnt, nend = end;
+                bool more = true;
+                if (np0 >= end) {
+                    if (lev < ncl) { nlev = lev + 1; nend = v.clev_end[at(v, nlev, scene)]; }
+                    else { nlev = 1; np0 = 0; nend = v.clev_end[at(v, 1, scene)]; more = false; }
+                }
+                if (more || it + 1 < iters) issue(np0, min(G, nend - np0), st ^ 1); else cp_async_commit();
+                cp_async_wait<1>();
+                if (gl < cnt) {
+                    const int p = p0 + gl;
+                    float4 F[CROW_FIELDS];
+#pragma unroll
+                    for (int f = 0; f < CROW_FIELDS; ++f) F[f] = ring[(st * CROW_FIELDS + f) * LV_THREADS + threadIdx.x];
+                    const size_t li = at_crow(v, CROW_LAMBDA, p, scene);
+                    const float4 lam = lam_direct ? v.crow[li] : F[CROW_LAMBDA];
+                    const ContactIds c = contact_ids(F);
+                    V3 w0l = mk3(0.f, 0.f, 0.f), w0a = w0l, w1l = w0l, w1a = w0l;
+                    if (c.dyn0) ld_w(w, c.id0, w0l, w0a);
+                    if (c.dyn1) ld_w(w, c.id1, w1l, w1a);
+                    const float4 out = contact_solve(F, lam, mu, c.dyn0, c.dyn1, w0l, w0a, w1l, w1a);
+                    if (c.dyn0) st_w(w, c.id0, w0l, w0a);
+                    if (c.dyn1) st_w(w, c.id1, w1l, w1a);
+                    v.crow[li] = out;
+                }
+                st ^= 1;
+                if (nlev != lev || !more) group_sync<G>(mask);
+                if (!more) break;
+                lev = nlev; p0 = np0; end = nend;
+            }
+            it_stage = st;
+        }
+    }
+    cp_async_wait<0>();
+
+    // constraint forces (RigidBodySystem.cpp:185-220) in the same per-body order: w becomes fc / tauc
+    for (int i = gl; i < 2 * nb; i += G) w[i] = z4;
+    group_sync<G>(mask);
+    for (int lev = 1, p0 = 0; lev <= njl; ++lev) {
+        const int p1 = v.jlev_end[at(v, lev, scene)];
+        for (int p = p0 + gl; p < p1; p += G) {
+            const JointRow j = load_joint_head(v, p, scene);
+            const float4 tail = __ldg(&v.jrow[at_jrow(v, 16, p, scene)]);
+            const size_t ji = at(v, __float_as_int(tail.w), scene);
+            const float4 lam03 = v.jlam[ji];
+            const float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
+            float f0[6], f1[6];
+            joint_force(j, __float_as_int(tail.z), l, dt, f0, f1);
+            V3 wl, wa;
+            if (j.id0 >= 0) { ld_w(w, j.id0, wl, wa); st_w(w, j.id0, wl + mk3(f0[0], f0[1], f0[2]), wa + mk3(f0[3], f0[4], f0[5])); }
+            if (j.id1 >= 0) { const int b = j.id1 & 0x7fffffff; ld_w(w, b, wl, wa); st_w(w, b, wl + mk3(f1[0], f1[1], f1[2]), wa + mk3(f1[3], f1[4], f1[5])); }
+        }
+        p0 = p1;
+        group_sync<G>(mask);
+    }
+    // the reference also adds joint forces to FIXED bodies (:189-192, harmless: they do not integrate).
+    // Levels do not separate rows that share a fixed body, so one lane adds those in joint order.
+    if (gl == 0) {
+        for (int s = 0; s < nj; ++s) {
+            const int4 def = v.jdef[at(v, s, scene)];
+            const bool fix0 = v.flags[at(v, def.y, scene)] & FLAG_FIXED, fix1 = v.flags[at(v, def.z, scene)] & FLAG_FIXED;
+            if (!fix0 && !fix1) continue;
+            const int p = v.jpos[at(v, s, scene)];
+            const JointRow j = load_joint_head(v, p, scene);
+            const size_t ji = at(v, s, scene);
+            const float4 lam03 = v.jlam[ji];
+            const float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
+            float f0[6], f1[6];
+            joint_force(j, def.w, l, dt, f0, f1);
+            V3 wl, wa;
+            if (fix0) { ld_w(w, def.y, wl, wa); st_w(w, def.y, wl + mk3(f0[0], f0[1], f0[2]), wa + mk3(f0[3], f0[4], f0[5])); }
+            if (fix1) { ld_w(w, def.z, wl, wa); st_w(w, def.z, wl + mk3(f1[0], f1[1], f1[2]), wa + mk3(f1[3], f1[4], f1[5])); }
+        }
+    }
+    group_sync<G>(mask);
+    for (int lev = 1, p0 = 0; lev <= ncl; ++lev) {
+        const int p1 = v.clev_end[at(v, lev, scene)];
+        for (int p = p0 + gl; p < p1; p += G) {
+            float4 F[9];
+#pragma unroll
+            for (int f = 0; f < 9; ++f) F[f] = __ldg(&v.crow[at_crow(v, f, p, scene)]);
+            const float4 lam = v.crow[at_crow(v, CROW_LAMBDA, p, scene)];
+            const ContactIds c = contact_ids(F);
+            V3 fl, fa, wl, wa;
+            if (c.dyn0) { contact_force(F, lam, dt, 0, fl, fa); ld_w(w, c.id0, wl, wa); st_w(w, c.id0, wl + fl, wa + fa); }
+            if (c.dyn1) { contact_force(F, lam, dt, 1, fl, fa); ld_w(w, c.id1, wl, wa); st_w(w, c.id1, wl + fl, wa + fa); }
+        }
+        p0 = p1;
+        group_sync<G>(mask);
+    }
+    for (int i = gl; i < nb; i += G) {
+        v.wl[at(v, i, scene)] = w[2 * i];
+        v.wa[at(v, i, scene)] = w[2 * i + 1];
+    }
+    if (v.profiling && gl == 0) {
+        atomicAdd(&v.visit_counters[0], (unsigned long long)nc * iters);
+        atomicAdd(&v.visit_counters[1], (unsigned long long)nj * iters);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------
+void launch_joint_levels(const View& v, cudaStream_t s)
+{
+    k_joint_levels<<<(unsigned)((v.B + 127) / 128), 128, 0, s>>>(v);
+}
+
+template <int G>
+static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t s)
+{
+    const int spc = LV_THREADS / G;
+    const size_t smem = (size_t)spc * v.NB * 2 * sizeof(float4) + (size_t)2 * CROW_FIELDS * LV_THREADS * sizeof(float4);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_pgs_lv<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
+    k_pgs_lv<G><<<(unsigned)((v.B + spc - 1) / spc), LV_THREADS, smem, s>>>(v, dt, iters, mu);
+}
+
+int level_group_size(const View& v, int requested)
+{
+    int g = requested;
+    if (g != 4 && g != 8 && g != 16 && g != 32) g = v.NB <= 256 ? 8 : (v.NB <= 512 ? 16 : 32);
+    // the accumulators of LV_THREADS / g scenes must fit in shared memory
+    while (g < 32 && (size_t)(LV_THREADS / g) * v.NB * 32 > 150 * 1024) g <<= 1;
+    return g;
+}
+
+bool level_mode_fits(int max_bodies) { return (size_t)(LV_THREADS / 32) * max_bodies * 32 <= 150 * 1024; }
+
+void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, cudaStream_t s)
+{
+    switch (group) {
+    case 4:  launch_lv<4>(v, dt, iters, mu, s); break;
+    case 8:  launch_lv<8>(v, dt, iters, mu, s); break;
+    case 16: launch_lv<16>(v, dt, iters, mu, s); break;
+    default: launch_lv<32>(v, dt, iters, mu, s); break;
+    }
+}
+
+}  // namespace slrbs

@@ -11,8 +11,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scene", default="marble_box"); ap.add_argument("--B", type=int, default=4096)
 ap.add_argument("--nc", type=int, default=1024); ap.add_argument("--settle", type=int, default=200)
 ap.add_argument("--steps", type=int, default=20); ap.add_argument("--k", type=int, default=8)
+ap.add_argument("--mode", default=""); ap.add_argument("--group", default="")
 a = ap.parse_args()
-o = Oracle(a.scene, k=a.k) if a.scene == "sphere_stack" else Oracle(a.scene)
+if a.mode: os.environ["SLRBS_PGS_MODE"] = a.mode
+if a.group: os.environ["SLRBS_LEVEL_GROUP"] = a.group
+o = Oracle(a.scene, k=a.k) if a.scene == "sphere_stack" else (Oracle("marble_box_n", nx=10, nz=10, ny=10) if a.scene == "mb1k" else Oracle(a.scene))
 s = scene_arrays(o)
 B, nb, nj = a.B, o.n_bodies, o.n_joints
 ctx = Context(B, nb, nj, a.nc)
