@@ -32,7 +32,8 @@ class SlrbsError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libslrbs_b200.so")
+    # SLRBS_LIB lets a developer point the binding at an experimental build of the same ABI
+    return os.environ.get("SLRBS_LIB") or os.path.join(_HERE, "libslrbs_b200.so")
 
 
 def load_library():

@@ -60,15 +60,6 @@ __global__ void __launch_bounds__(128) k_joint_levels(View v)
 // ------------------------------------------------------------------------------------
 enum { LV_THREADS = 128 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 struct BodyW { float4* w; };     // shared-memory accumulators of one scene: [body][2] (linear, angular)
 __device__ __forceinline__ void ld_w(const float4* w, int body, V3& l, V3& a) { l = mk3(w[2 * body]); a = mk3(w[2 * body + 1]); }
 __device__ __forceinline__ void st_w(float4* w, int body, const V3& l, const V3& a) { w[2 * body] = mk4(l, 0.f); w[2 * body + 1] = mk4(a, 0.f); }
@@ -80,7 +71,7 @@ __device__ __forceinline__ void group_sync(unsigned mask)
 }
 
 template <int G>
-__global__ void __launch_bounds__(LV_THREADS) k_pgs_lv(View v, float dt, int iters, float mu)
+__global__ void __launch_bounds__(LV_THREADS, 4) k_pgs_lv(View v, float dt, int iters, float mu)
 {
     extern __shared__ float4 smem_w[];
     constexpr int SPC = LV_THREADS / G;                          // scenes per CTA
@@ -112,19 +103,6 @@ __global__ void __launch_bounds__(LV_THREADS) k_pgs_lv(View v, float dt, int ite
         group_sync<G>(mask);
     }
 
-    // thread-private ring [stage][field][thread] behind the scenes' accumulators
-    float4* ring = smem_w + (size_t)SPC * v.NB * 2;
-    const bool lam_direct = nc <= 2 * G;                       // too few chunks: a prefetched lambda could be stale
-    int it_stage = 0;
-    auto issue = [&](int p0, int cnt, int st) {
-        if (gl < cnt) {
-#pragma unroll
-            for (int f = 0; f < CROW_FIELDS; ++f)
-                cp_async16(&ring[(st * CROW_FIELDS + f) * LV_THREADS + threadIdx.x], &v.crow[at_crow(v, f, p0 + gl, scene)]);
-        }
-        cp_async_commit();
-    };
-
     for (int it = 0; it < iters; ++it) {                          // SolverBoxPGS.cpp:217-248
         for (int lev = 1, p0 = 0; lev <= njl; ++lev) {
             const int p1 = v.jlev_end[at(v, lev, scene)];
@@ -148,48 +126,27 @@ __global__ void __launch_bounds__(LV_THREADS) k_pgs_lv(View v, float dt, int ite
             p0 = p1;
             group_sync<G>(mask);
         }
-        // contact levels: the rows of the NEXT chunk (up to G rows of one level) are copied into the lanes'
-        // private ring slots with cp.async while the current chunk is solved
-        if (nc > 0) {
-            int lev = 1, p0 = 0, end = v.clev_end[at(v, 1, scene)];
-            if (it == 0) { issue(p0, min(G, end - p0), 0); }
-            int st = it_stage;
-            while (true) {
-                const int cnt = min(G, end - p0);
-                // next chunk: same level, next level, or the first chunk of the next sweep
-                int nlev = lev, np0 = p0 + cnt, nend = end;
-                bool more = true;
-                if (np0 >= end) {
-                    if (lev < ncl) { nlev = lev + 1; nend = v.clev_end[at(v, nlev, scene)]; }
-                    else { nlev = 1; np0 = 0; nend = v.clev_end[at(v, 1, scene)]; more = false; }
-                }
-                if (more || it + 1 < iters) issue(np0, min(G, nend - np0), st ^ 1); else cp_async_commit();
-                cp_async_wait<1>();
-                if (gl < cnt) {
-                    const int p = p0 + gl;
-                    float4 F[CROW_FIELDS];
+        for (int lev = 1, p0 = 0; lev <= ncl; ++lev) {
+            const int p1 = v.clev_end[at(v, lev, scene)];
+            for (int p = p0 + gl; p < p1; p += G) {
+                float4 F[CROW_FIELDS];
 #pragma unroll
-                    for (int f = 0; f < CROW_FIELDS; ++f) F[f] = ring[(st * CROW_FIELDS + f) * LV_THREADS + threadIdx.x];
-                    const size_t li = at_crow(v, CROW_LAMBDA, p, scene);
-                    const float4 lam = lam_direct ? v.crow[li] : F[CROW_LAMBDA];
-                    const ContactIds c = contact_ids(F);
-                    V3 w0l = mk3(0.f, 0.f, 0.f), w0a = w0l, w1l = w0l, w1a = w0l;
-                    if (c.dyn0) ld_w(w, c.id0, w0l, w0a);
-                    if (c.dyn1) ld_w(w, c.id1, w1l, w1a);
-                    const float4 out = contact_solve(F, lam, mu, c.dyn0, c.dyn1, w0l, w0a, w1l, w1a);
-                    if (c.dyn0) st_w(w, c.id0, w0l, w0a);
-                    if (c.dyn1) st_w(w, c.id1, w1l, w1a);
-                    v.crow[li] = out;
-                }
-                st ^= 1;
-                if (nlev != lev || !more) group_sync<G>(mask);
-                if (!more) break;
-                lev = nlev; p0 = np0; end = nend;
+                for (int f = 0; f < CROW_LAMBDA; ++f) F[f] = __ldg(&v.crow[at_crow(v, f, p, scene)]);
+                const size_t li = at_crow(v, CROW_LAMBDA, p, scene);
+                const float4 lam = v.crow[li];
+                const ContactIds c = contact_ids(F);
+                V3 w0l = mk3(0.f, 0.f, 0.f), w0a = w0l, w1l = w0l, w1a = w0l;
+                if (c.dyn0) ld_w(w, c.id0, w0l, w0a);
+                if (c.dyn1) ld_w(w, c.id1, w1l, w1a);
+                const float4 out = contact_solve(F, lam, mu, c.dyn0, c.dyn1, w0l, w0a, w1l, w1a);
+                if (c.dyn0) st_w(w, c.id0, w0l, w0a);
+                if (c.dyn1) st_w(w, c.id1, w1l, w1a);
+                v.crow[li] = out;
             }
-            it_stage = st;
+            p0 = p1;
+            group_sync<G>(mask);
         }
     }
-    cp_async_wait<0>();
 
     // constraint forces (RigidBodySystem.cpp:185-220) in the same per-body order: w becomes fc / tauc
     for (int i = gl; i < 2 * nb; i += G) w[i] = z4;
@@ -268,7 +225,7 @@ template <int G>
 static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t s)
 {
     const int spc = LV_THREADS / G;
-    const size_t smem = (size_t)spc * v.NB * 2 * sizeof(float4) + (size_t)2 * CROW_FIELDS * LV_THREADS * sizeof(float4);
+    const size_t smem = (size_t)spc * v.NB * 2 * sizeof(float4);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_pgs_lv<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
     k_pgs_lv<G><<<(unsigned)((v.B + spc - 1) / spc), LV_THREADS, smem, s>>>(v, dt, iters, mu);
@@ -279,11 +236,11 @@ int level_group_size(const View& v, int requested)
     int g = requested;
     if (g != 4 && g != 8 && g != 16 && g != 32) g = v.NB <= 256 ? 8 : (v.NB <= 512 ? 16 : 32);
     // the accumulators of LV_THREADS / g scenes must fit in shared memory
-    while (g < 32 && (size_t)(LV_THREADS / g) * v.NB * 32 > 150 * 1024) g <<= 1;
+    while (g < 32 && (size_t)(LV_THREADS / g) * v.NB * 32 > 200 * 1024) g <<= 1;
     return g;
 }
 
-bool level_mode_fits(int max_bodies) { return (size_t)(LV_THREADS / 32) * max_bodies * 32 <= 150 * 1024; }
+bool level_mode_fits(int max_bodies) { return (size_t)(LV_THREADS / 32) * max_bodies * 32 <= 200 * 1024; }
 
 void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, cudaStream_t s)
 {
