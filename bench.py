@@ -43,7 +43,7 @@ WORKLOADS = {
     "car":            ("car", (0, 0, 0), 16, 262144, 50, 0.0),
     "swinging_boxes": ("swinging_boxes", (0, 0, 0), 0, 65536, 50, 0.0),
     "sphere_stack":   ("sphere_stack", (8, 0, 0), 32, 262144, 50, 0.0),
-    "marble_box_1k":  ("marble_box_n", (10, 10, 10), 4096, 1024, 300, 0.01),
+    "marble_box_1k":  ("marble_box_n", (10, 10, 10), 4096, 1024, 200, 0.01),
 }
 
 

@@ -34,6 +34,7 @@ struct slrbs_ctx {
     float mu = 0.8f;
     int solver_id = 0, solver_iters = 10, collisions = 1;
     int level_group = 8;                        // lanes per scene of the level-scheduled solver
+    int broadphase = -1;                        // -1 auto, 0 all pairs, 1 hashed grid (SLRBS_BROADPHASE)
     bool joints_dirty = true;                   // joint levels must be recomputed (bodies / joints uploaded)
     std::vector<void*> allocs;
     char* stage = nullptr; size_t stage_cap = 0, stage_off = 0;
@@ -175,13 +176,14 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     // give the same impulses bit for bit; SLRBS_PGS_MODE=thread|level and SLRBS_LEVEL_GROUP=4|8|16|32 override.
     {
         const char* m = std::getenv("SLRBS_PGS_MODE");
-        const bool fits = level_mode_fits(max_bodies) &&
-                          ((size_t)max_bodies * 20 + ((size_t)max_bodies + max_contacts + 2) * 4) <= 200 * 1024;   // k_detect_warp tables
+        const bool fits = level_mode_fits(max_bodies) && detect_warp_fits(max_bodies, max_contacts, true);
         if (m && std::strcmp(m, "thread") == 0) v.level_mode = 0;
         else if (m && std::strcmp(m, "level") == 0) v.level_mode = fits ? 1 : 0;
         else v.level_mode = (max_bodies >= 24 && n_scenes <= 8192 && fits) ? 1 : 0;
         const char* g = std::getenv("SLRBS_LEVEL_GROUP");
         c->level_group = level_group_size(v, g ? std::atoi(g) : 0);
+        const char* bp = std::getenv("SLRBS_BROADPHASE");
+        if (bp) c->broadphase = std::atoi(bp) ? 1 : 0;
     }
     const size_t nb = (size_t)v.NB * v.B, nj = (size_t)v.NJ * v.B, nc = (size_t)v.NC * v.B;
     const size_t bpad = ((size_t)v.B + 31) / 32 * 32;      // row records are blocked 32 scenes at a time
@@ -357,7 +359,7 @@ int slrbs_stage_detect(slrbs_ctx* c)
     if (!c) return fail(SLRBS_E_ARG, "null context");
     CU(cudaSetDevice(c->device));
     if (!c->collisions || c->v.NC == 0) return 0;               // RigidBodySystem.cpp:77
-    launch_detect(c->v, c->stream);
+    launch_detect(c->v, c->broadphase, c->stream);
     return check_launch(c);
 }
 int slrbs_stage_jacobians(slrbs_ctx* c, float dt)

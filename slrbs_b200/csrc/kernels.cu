@@ -79,283 +79,6 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
 }
 
 // ------------------------------------------------------------------------------------
-// K3  narrow phase: one WARP per scene. The scene's body proxies are staged in shared memory;
-// for each i the lanes test 32 consecutive j > i, and contacts are appended in the reference's
-// lexicographic (i, j) order by a warp-ballot prefix sum (up to 4 per pair, fixed A,B,C,D order).
-// ------------------------------------------------------------------------------------
-struct PairOut {
-    int b0, b1, cnt;        // role-ordered body indices (sphere/box, cylinder/plane), contacts of this pair
-    V3 n;
-    V3 p[4];
-    float phi[4];
-    __device__ __forceinline__ void add(const V3& pp, float f) { p[cnt] = pp; phi[cnt] = f; ++cnt; }
-};
-
-__device__ __forceinline__ float plane_dist(const V3& p, const V3& plane_p, const V3& plane_n)
-{
-    return dot(p - plane_p, plane_n);                            // CollisionDetect.cpp:12-17
-}
-
-// CollisionDetect.cpp:102-123
-__device__ __forceinline__ void sphere_sphere(PairOut& o, int i0, int i1, const float4& c0, const float4& c1)
-{
-    const V3 x0 = mk3(c0), x1 = mk3(c1);
-    const V3 vec = x0 - x1;
-    const float rsum = (c0.w + c1.w);
-    const float dist = norm(vec);
-    if (dist < (rsum + 1e-3f)) {
-        o.b0 = i0; o.b1 = i1;
-        o.n = vec / dist;
-        o.add(0.5f * ((x0 - c0.w * o.n) + (x1 + c1.w * o.n)), fminf(0.0f, dist - rsum));
-    }
-}
-
-// CollisionDetect.cpp:125-150 (body0 = sphere, body1 = box)
-__device__ __noinline__ void sphere_box(PairOut& o, const float4* __restrict__ quat, const float4* __restrict__ geomA, size_t bi,
-                                       int is, int ib, const float4& cs, const float4& cb)
-{
-    const V3 xs = mk3(cs), xb = mk3(cb);
-    const float r = cs.w;
-    const Q4 qb = mkq(__ldg(&quat[bi]));
-    const float4 dim = __ldg(&geomA[bi]);
-    const V3 cl = rotate(qinverse(qb), xs - xb);
-    V3 q;
-    q.x = cl.x; if (q.x < (-dim.x / 2.0f)) q.x = -dim.x / 2.0f; else if (q.x > (dim.x / 2.0f)) q.x = dim.x / 2.0f;
-    q.y = cl.y; if (q.y < (-dim.y / 2.0f)) q.y = -dim.y / 2.0f; else if (q.y > (dim.y / 2.0f)) q.y = dim.y / 2.0f;
-    q.z = cl.z; if (q.z < (-dim.z / 2.0f)) q.z = -dim.z / 2.0f; else if (q.z > (dim.z / 2.0f)) q.z = dim.z / 2.0f;
-    const V3 dx = cl - q;
-    const float dist = norm(dx);
-    if (dist < (r + 1e-3f)) {
-        o.b0 = is; o.b1 = ib;
-        o.n = rotate(qb, dx / dist);
-        o.add(rotate(qb, q) + xb, fminf(0.0f, dist - r));
-    }
-}
-
-// CollisionDetect.cpp:152-274 (body0 = cylinder, body1 = plane)
-__device__ __noinline__ void cylinder_plane(PairOut& o, const float4* __restrict__ quat, const float4* __restrict__ geomA,
-                                           const float4* __restrict__ geomB, size_t ci, size_t pi, int ic, int ip,
-                                           const float4& cc, const float4& cpl)
-{
-    const V3 xc = mk3(cc), xp = mk3(cpl);
-    const Q4 qc = mkq(__ldg(&quat[ci]));
-    const float4 cg = __ldg(&geomA[ci]);
-    const float h = cg.x, r = cg.y;
-    const Q4 qp = mkq(__ldg(&quat[pi]));
-    const V3 cyldir = rotate(qc, mk3(0.f, 1.f, 0.f));
-    const V3 planen = rotate(qp, mk3(__ldg(&geomB[pi])));
-    const V3 planep = rotate(qp, mk3(__ldg(&geomA[pi]))) + xp;
-    const float dp = dot(cyldir, planen);
-    o.b0 = ic; o.b1 = ip; o.n = planen;
-
-    if (fabsf(dp) > 0.995f) {                                    // :164 cap face on the plane
-        const V3 w = (dp < 0.0f) ? cyldir : -cyldir;
-        V3 u = (fabsf(dot(w, mk3(1.f, 0.f, 0.f))) > 0.01f) ? cross(w, mk3(1.f, 0.f, 0.f)) : cross(w, mk3(0.f, 0.f, 1.f));
-        u = normalized(u);
-        const V3 vv = normalized(cross(w, u));
-        const V3 a = xc + (0.5f * h) * w;
-        if (plane_dist(a, planep, planen) < 1e-3f) {
-            const V3 pA = a + r * u, pB = a - r * u, pC = a + r * vv, pD = a - r * vv;
-            const float fA = plane_dist(pA, planep, planen), fB = plane_dist(pB, planep, planen);
-            const float fC = plane_dist(pC, planep, planen), fD = plane_dist(pD, planep, planen);
-            if (fA < 1e-3f) o.add(pA, fminf(0.0f, fA));
-            if (fB < 1e-3f) o.add(pB, fminf(0.0f, fB));
-            if (fC < 1e-3f) o.add(pC, fminf(0.0f, fC));
-            if (fD < 1e-3f) o.add(pD, fminf(0.0f, fD));
-        }
-    } else if (fabsf(dp) < 1e-2f) {                              // :215 lying on its side
-        V3 u = cross(cross(planen, cyldir), cyldir);
-        if (dot(u, planen) > 0.0f) u = -u;
-        u = normalized(u);
-        const float dist = plane_dist(xc, planep, planen) - r;
-        if (dist < 0.01f) {                                      // :227
-            const V3 hw = (0.5f * h) * cyldir, ru = r * u;
-            const V3 pA = (xc + hw) + ru, pB = (xc - hw) + ru;
-            const float fA = plane_dist(pA, planep, planen), fB = plane_dist(pB, planep, planen);
-            if (fA < 1e-3f) o.add(pA, fminf(0.0f, fA));
-            if (fB < 1e-3f) o.add(pB, fminf(0.0f, fB));
-        }
-    } else {                                                     // :241 single lowest rim point
-        V3 w = (dp < 0.0f) ? cyldir : -cyldir;
-        w = normalized(w);
-        V3 u = normalized(cross(cross(planen, w), w));
-        if (dot(u, planen) > 0.0f) u = -u;
-        u = normalized(u);
-        const V3 a = (xc + (0.5f * h) * w) + r * u;
-        const float dist = plane_dist(a, planep, planen);
-        if (dist < 1e-3f) o.add(a, fminf(0.0f, dist));
-    }
-}
-
-// the reference's dispatch chain for the ordered pair (i < j), CollisionDetect.cpp:41-73
-__device__ __forceinline__ void test_pair(PairOut& o, const View& v, int scene, int i, int j,
-                                          const float4& ci, int fi, const float4& cj, int fj)
-{
-    o.cnt = 0;
-    if ((fi & fj) & FLAG_FIXED) return;
-    const int ti = fi & FLAG_TYPE_MASK, tj = fj & FLAG_TYPE_MASK;
-    if (ti == GEOM_SPHERE && tj == GEOM_SPHERE)          sphere_sphere(o, i, j, ci, cj);
-    else if (ti == GEOM_SPHERE && tj == GEOM_BOX)        sphere_box(o, v.quat, v.geomA, at(v, j, scene), i, j, ci, cj);
-    else if (tj == GEOM_SPHERE && ti == GEOM_BOX)        sphere_box(o, v.quat, v.geomA, at(v, i, scene), j, i, cj, ci);
-    else if (ti == GEOM_CYLINDER && tj == GEOM_PLANE)    cylinder_plane(o, v.quat, v.geomA, v.geomB, at(v, i, scene), at(v, j, scene), i, j, ci, cj);
-    else if (tj == GEOM_CYLINDER && ti == GEOM_PLANE)    cylinder_plane(o, v.quat, v.geomA, v.geomB, at(v, j, scene), at(v, i, scene), j, i, cj, ci);
-}
-
-__device__ __forceinline__ void write_contacts(const View& v, int scene, int base, const PairOut& o)
-{
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (k < o.cnt) {
-            if (base + k < v.NC) {
-                const size_t c = at(v, base + k, scene);
-                v.cids[c] = make_int2(o.b0, o.b1);
-                v.cp[c] = mk4(o.p[k], o.phi[k]);
-                v.cn[c] = mk4(o.n, 0.f);
-            } else {
-                *v.overflow = 1;
-            }
-        }
-    }
-}
-
-// In level mode (layout.cuh) the warp also assigns every contact its dependency level as it is emitted
-// (sequential in emission order, tables in shared memory) and counting-sorts the contacts by level:
-// cpos[c] = position of contact c in the level-ordered row stream, clev_end[l] = end of level l.
-__global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta)
-{
-    extern __shared__ float4 smem4[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int scene = blockIdx.x * warps_per_cta + warp;
-    if (scene >= v.B) return;
-    float4* sp = smem4 + (size_t)warp * v.NB;                                 // proxies of this warp's scene
-    int* sf = reinterpret_cast<int*>(smem4 + (size_t)warps_per_cta * v.NB) + (size_t)warp * v.NB;
-    // level tables (level mode only): last level per body, contacts per level
-    int* ibase = reinterpret_cast<int*>(smem4 + (size_t)warps_per_cta * v.NB) + (size_t)warps_per_cta * v.NB;
-    int* last = ibase + (size_t)warp * (v.NB + v.NC + 2);
-    int* hist = last + v.NB;
-    const bool lv = v.level_mode != 0;
-    const int n = v.nbodies[scene];
-    for (int b = lane; b < n; b += 32) {
-        const size_t i = at(v, b, scene);
-        sp[b] = v.cproxy[i];
-        sf[b] = v.flags[i];
-        if (lv) last[b] = 0;
-    }
-    if (lv) for (int l = lane; l <= v.NC; l += 32) hist[l] = 0;
-    __syncwarp();
-    int count = 0, nlev = 0;
-    const unsigned lt = (1u << lane) - 1u;
-    for (int i = 0; i < n; ++i) {
-        const float4 ci = sp[i];
-        const int fi = sf[i];
-        for (int j0 = i + 1; j0 < n; j0 += 32) {
-            const int j = j0 + lane;
-            PairOut o;
-            o.cnt = 0;
-            if (j < n) test_pair(o, v, scene, i, j, ci, fi, sp[j], sf[j]);
-            const unsigned any = __ballot_sync(0xffffffffu, o.cnt > 0);
-            if (any == 0) continue;
-            const unsigned multi = __ballot_sync(0xffffffffu, o.cnt > 1);
-            int before, total;
-            if (multi == 0) {                                    // common case: at most one contact per pair
-                before = __popc(any & lt);
-                total = __popc(any);
-            } else {                                             // up to 4 per pair: shuffle prefix sum
-                int incl = o.cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                before = incl - o.cnt;
-                total = __shfl_sync(0xffffffffu, incl, 31);
-            }
-            write_contacts(v, scene, count + before, o);
-            if (lv) {
-                // levels in emission order: every lane follows the same sequence, the emitting lane records
-                unsigned m = any;
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int b0 = __shfl_sync(0xffffffffu, o.b0, src), b1 = __shfl_sync(0xffffffffu, o.b1, src);
-                    const int c = __shfl_sync(0xffffffffu, o.cnt, src), base = __shfl_sync(0xffffffffu, before, src);
-                    const bool dyn0 = !(sf[b0] & FLAG_FIXED), dyn1 = !(sf[b1] & FLAG_FIXED);
-                    int L = 0;
-                    if (dyn0) L = max(L, last[b0]);
-                    if (dyn1) L = max(L, last[b1]);
-                    __syncwarp();
-                    for (int k = 0; k < c; ++k) {                // contacts of one pair share both bodies: consecutive levels
-                        if (count + base + k >= v.NC) break;     // dropped (capacity overflow is reported by slrbs_sync)
-                        ++L;
-                        const int rank = hist[L];
-                        __syncwarp();
-                        if (lane == src) {
-                            hist[L] = rank + 1;
-                            v.cpos[at(v, count + base + k, scene)] = (L << 16) | rank;
-                        }
-                    }
-                    if (lane == src) { if (dyn0) last[b0] = L; if (dyn1) last[b1] = L; }
-                    nlev = max(nlev, L);
-                    __syncwarp();
-                }
-            }
-            count += total;
-        }
-    }
-    const int nc = count < v.NC ? count : v.NC;
-    if (lane == 0) v.ncontacts[scene] = nc;
-    if (lv) {
-        nlev = min(nlev, v.NC);
-        // exclusive prefix of the per-level counts -> level starts (in place), level ends to global
-        int carry = 0;
-        for (int l0 = 1; l0 <= nlev; l0 += 32) {
-            const int l = l0 + lane;
-            const int c = l <= nlev ? hist[l] : 0;
-            int incl = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            if (l <= nlev) {
-                hist[l] = carry + incl - c;
-                v.clev_end[at(v, l, scene)] = min(carry + incl, nc);
-            }
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        __syncwarp();
-        for (int c = lane; c < nc; c += 32) {
-            const size_t ci = at(v, c, scene);
-            const int packed = v.cpos[ci];
-            v.cpos[ci] = hist[packed >> 16] + (packed & 0xffff);
-        }
-        if (lane == 0) v.nclev[scene] = nlev;
-    }
-}
-
-// fallback for scenes whose proxies do not fit in shared memory: one thread per scene
-__global__ void __launch_bounds__(128) k_detect_serial(View v)
-{
-    const int scene = blockIdx.x * blockDim.x + threadIdx.x;
-    if (scene >= v.B) return;
-    const int n = v.nbodies[scene];
-    int count = 0;
-    for (int i = 0; i < n; ++i) {
-        const size_t ii = at(v, i, scene);
-        const float4 ci = v.cproxy[ii];
-        const int fi = v.flags[ii];
-        for (int j = i + 1; j < n; ++j) {
-            const size_t jj = at(v, j, scene);
-            PairOut o;
-            test_pair(o, v, scene, i, j, ci, fi, v.cproxy[jj], v.flags[jj]);
-            write_contacts(v, scene, count, o);
-            count += o.cnt;
-        }
-    }
-    v.ncontacts[scene] = count < v.NC ? count : v.NC;
-}
-
-// ------------------------------------------------------------------------------------
 // K4  contact frame, Jacobian blocks, J M^-1, 3x3 diagonal block, RHS
 // ------------------------------------------------------------------------------------
 struct BodyDyn { V3 x, xdot, omega, f, tau; float mass; M3 Iinv; bool fixed; };
@@ -1171,20 +894,6 @@ __global__ void k_export_body_dyn(View v, int scene, int n, float* f3, float* ta
 static inline unsigned blocks_for(size_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 void launch_prepare(const View& v, cudaStream_t s) { k_prepare<<<blocks_for((size_t)v.NB * v.B, 256), 256, 0, s>>>(v); }
-void launch_detect(const View& v, cudaStream_t s)
-{
-    // warps per CTA: as many as fit ~96 KB of staged proxies (20 B / body / warp) and, in level mode, the
-    // level tables (4 B / body + 4 B / contact slot / warp), at most 8
-    const size_t per_warp = (size_t)v.NB * 20 + (v.level_mode ? ((size_t)v.NB + v.NC + 2) * 4 : 0);
-    int warps = 8;
-    while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
-    const size_t smem = per_warp * warps;
-    // tiny scenes (car: 15 pairs) leave a warp idle: one thread per scene is faster there; huge ones do not fit
-    if ((v.NB < 24 && !v.level_mode) || smem > 200 * 1024) { k_detect_serial<<<blocks_for(v.B, 128), 128, 0, s>>>(v); return; }
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_detect_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-    k_detect_warp<<<blocks_for(v.B, warps), warps * 32, smem, s>>>(v, warps);
-}
 void launch_contact_rows(const View& v, float h, cudaStream_t s) { k_contact_rows<<<blocks_for((size_t)v.NC * v.B, 128), 128, 0, s>>>(v, h); }
 void launch_joint_rows(const View& v, float h, cudaStream_t s) { if (v.NJ > 0) k_joint_rows<<<blocks_for((size_t)v.NJ * v.B, 128), 128, 0, s>>>(v, h); }
 void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s) { k_pgs<<<blocks_for(v.B, PGS_THREADS), PGS_THREADS, 0, s>>>(v, dt, iters, mu); }

@@ -70,8 +70,10 @@ __device__ __forceinline__ void group_sync(unsigned mask)
     if (G >= 32) __syncwarp(); else __syncwarp(mask);
 }
 
-template <int G>
-__global__ void __launch_bounds__(LV_THREADS, 4) k_pgs_lv(View v, float dt, int iters, float mu)
+// MINB = CTAs per SM the register allocation must allow: 4 (128 registers, a few spills) wins when the batch can
+// fill 16 warps per SM, 3 (162 registers, no spills) when it cannot and single-warp latency is what matters.
+template <int G, int MINB>
+__global__ void __launch_bounds__(LV_THREADS, MINB) k_pgs_lv(View v, float dt, int iters, float mu)
 {
     extern __shared__ float4 smem_w[];
     constexpr int SPC = LV_THREADS / G;                          // scenes per CTA
@@ -227,8 +229,14 @@ static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t
     const int spc = LV_THREADS / G;
     const size_t smem = (size_t)spc * v.NB * 2 * sizeof(float4);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_pgs_lv<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr_set = true; }
-    k_pgs_lv<G><<<(unsigned)((v.B + spc - 1) / spc), LV_THREADS, smem, s>>>(v, dt, iters, mu);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_pgs_lv<G, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(k_pgs_lv<G, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_set = true;
+    }
+    const unsigned blocks = (unsigned)((v.B + spc - 1) / spc);
+    if (blocks >= 148u * 4u) k_pgs_lv<G, 4><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
+    else k_pgs_lv<G, 3><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
 }
 
 int level_group_size(const View& v, int requested)
