@@ -13,6 +13,8 @@
 // k_integrate       RigidBodySystem.cpp:99-120                                        thread / (body, scene)
 #include "kernels.cuh"
 #include "pgs_math.cuh"
+
+#include <cstdlib>
 #include "vecmath.cuh"
 
 namespace slrbs {
@@ -489,6 +491,149 @@ __global__ void __launch_bounds__(PGS_THREADS, PGS_MIN_CTAS) k_pgs(View v, float
 }
 
 // ------------------------------------------------------------------------------------
+// K6 (TMA variant): the same sweep, but the warp's 8 KB row tile is fetched by ONE bulk asynchronous
+// copy (cp.async.bulk global -> shared, completion on an mbarrier) issued by an elected lane instead of
+// 16 x 32 per-lane cp.async: the tile layout [field][lane] in HBM is exactly the ring stage layout.
+// The loop is warp-uniform (trip count = the largest contact count of the 32 scenes; lanes past their
+// own count idle), lambda written through the generic proxy is fenced before the async proxy re-reads it.
+// MEASURED (marble box x 32768): 13.8 ms per launch against 10.7 ms for the per-lane cp.async ring
+// (11.8 ms without the per-visit proxy fence): the warp-wide barrier per row and the cross-proxy fence
+// cost more than the saved LDGSTS issue slots, so this variant is opt-in (SLRBS_PGS_TMA=1) only.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+enum { TMA_STAGES = 3, TILE_BYTES = CROW_FIELDS * 32 * 16 };
+
+__global__ void __launch_bounds__(32, 9) k_pgs_tma(View v, float dt, int iters, float mu)
+{
+    __shared__ __align__(128) float4 ring[TMA_STAGES][CROW_FIELDS][32];
+    __shared__ __align__(8) unsigned long long bars[TMA_STAGES];
+    const int lane = threadIdx.x;
+    const int scene = blockIdx.x * 32 + lane;
+    const bool live = scene < v.B;
+    const int sc = live ? scene : v.B - 1;                       // dead lanes shadow the last scene, read-only
+    const int nb = live ? v.nbodies[sc] : 0, nj = live ? v.njoints[sc] : 0, nc = live ? v.ncontacts[sc] : 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < TMA_STAGES; ++k) mbar_init(&bars[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < nb; ++i) { v.wl[at(v, i, sc)] = z4; v.wa[at(v, i, sc)] = z4; }
+    for (int s = 0; s < nj; ++s) {                                // seed w with last step's joint impulses
+        const JointRow j = load_joint_head(v, s, sc);
+        const size_t ji = at(v, s, sc);
+        const float4 lam03 = v.jlam[ji];
+        const float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
+        if (j.id0 >= 0) {
+            const size_t wi = at(v, j.id0, sc);
+            V3 wl = mk3(v.wl[wi]), wa = mk3(v.wa[wi]);
+            joint_seed(j, l, 0, wl, wa);
+            v.wl[wi] = mk4(wl, 0.f); v.wa[wi] = mk4(wa, 0.f);
+        }
+        if (j.id1 >= 0) {
+            const size_t wi = at(v, j.id1 & 0x7fffffff, sc);
+            V3 wl = mk3(v.wl[wi]), wa = mk3(v.wa[wi]);
+            joint_seed(j, l, 1, wl, wa);
+            v.wl[wi] = mk4(wl, 0.f); v.wa[wi] = mk4(wa, 0.f);
+        }
+    }
+    WCache wc; wc.id = -1; wc.l = mk3(0.f, 0.f, 0.f); wc.a = wc.l;
+
+    int ncmax = nc, njmax = nj;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ncmax = max(ncmax, __shfl_xor_sync(0xffffffffu, ncmax, d));
+        njmax = max(njmax, __shfl_xor_sync(0xffffffffu, njmax, d));
+    }
+    const int total = ncmax * iters;
+    const bool lam_direct = ncmax < TMA_STAGES + 1;
+    const float4* tiles = &v.crow[at_crow(v, 0, 0, blockIdx.x * 32)];       // tile of row r: tiles + r * CROW_FIELDS * 32
+    auto fetch = [&](int k) {                                     // warp-uniform
+        if (k < total && lane == 0) {
+            const int st = k % TMA_STAGES, row = k % ncmax;
+            fence_proxy_async();
+            mbar_expect_tx(&bars[st], TILE_BYTES);
+            bulk_g2s(&ring[st][0][0], tiles + (size_t)row * CROW_FIELDS * 32, TILE_BYTES, &bars[st]);
+        }
+    };
+    for (int k = 0; k < TMA_STAGES - 1; ++k) fetch(k);
+    int g = 0;
+    for (int it = 0; it < iters; ++it) {                          // SolverBoxPGS.cpp:217-248
+        for (int s = 0; s < njmax; ++s) if (s < nj) joint_visit(v, s, sc, wc);
+        for (int s = 0; s < ncmax; ++s, ++g) {
+            __syncwarp();                                         // everyone is done reading the stage about to be refilled
+            fetch(g + TMA_STAGES - 1);
+            const int st = g % TMA_STAGES;
+            mbar_wait(&bars[st], (unsigned)(g / TMA_STAGES) & 1u);
+            if (s < nc) {
+                float4 F[CROW_FIELDS];
+#pragma unroll
+                for (int f = 0; f < CROW_FIELDS; ++f) F[f] = ring[st][f][lane];
+                float4 lam = F[CROW_LAMBDA];
+                if (lam_direct) lam = v.crow[at_crow(v, CROW_LAMBDA, s, sc)];
+                contact_visit(v, s, sc, mu, F, lam, wc);
+                fence_proxy_async();                              // lambda must be visible to the next bulk read of this tile
+            }
+        }
+    }
+    // constraint forces (RigidBodySystem.cpp:185-220): wl/wa become fc/tauc
+    for (int i = 0; i < nb; ++i) { v.wl[at(v, i, sc)] = z4; v.wa[at(v, i, sc)] = z4; }
+    for (int s = 0; s < nj; ++s) {
+        const JointRow j = load_joint_head(v, s, sc);
+        const size_t ji = at(v, s, sc);
+        const float4 lam03 = v.jlam[ji];
+        const float l[5] = { lam03.x, lam03.y, lam03.z, lam03.w, v.jlam4[ji] };
+        const int dim = __float_as_int(__ldg(&v.jrow[at_jrow(v, 16, s, sc)]).z);
+        float f0[6], f1[6];
+        joint_force(j, dim, l, dt, f0, f1);
+        add_force(v, j.id0 & 0x7fffffff, sc, mk3(f0[0], f0[1], f0[2]), mk3(f0[3], f0[4], f0[5]));
+        add_force(v, j.id1 & 0x7fffffff, sc, mk3(f1[0], f1[1], f1[2]), mk3(f1[3], f1[4], f1[5]));
+    }
+    for (int s = 0; s < nc; ++s) {
+        float4 F[9];
+#pragma unroll
+        for (int f = 0; f < 9; ++f) F[f] = __ldg(&v.crow[at_crow(v, f, s, sc)]);
+        const float4 lam = v.crow[at_crow(v, CROW_LAMBDA, s, sc)];
+        const ContactIds c = contact_ids(F);
+        V3 fl, fa;
+        if (c.dyn0) { contact_force(F, lam, dt, 0, fl, fa); add_force(v, c.id0, sc, fl, fa); }
+        if (c.dyn1) { contact_force(F, lam, dt, 1, fl, fa); add_force(v, c.id1, sc, fl, fa); }
+    }
+    if (v.profiling && live) {
+        atomicAdd(&v.visit_counters[0], (unsigned long long)nc * iters);
+        atomicAdd(&v.visit_counters[1], (unsigned long long)nj * iters);
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // K6c  joint-only Krylov solvers (solverId 1 = CG, 2 = CR): SolverConjGradient.cpp:109-162,
 // SolverConjResidual.cpp:100-158. One thread per scene; contacts are ignored (lambda stays 0).
 // A x is evaluated body-wise: u_body = sum_{joints on body} J^T x, then (A x)_j = J0Minv_j u_b0 +
@@ -896,7 +1041,13 @@ static inline unsigned blocks_for(size_t n, int bs) { return (unsigned)((n + bs 
 void launch_prepare(const View& v, cudaStream_t s) { k_prepare<<<blocks_for((size_t)v.NB * v.B, 256), 256, 0, s>>>(v); }
 void launch_contact_rows(const View& v, float h, cudaStream_t s) { k_contact_rows<<<blocks_for((size_t)v.NC * v.B, 128), 128, 0, s>>>(v, h); }
 void launch_joint_rows(const View& v, float h, cudaStream_t s) { if (v.NJ > 0) k_joint_rows<<<blocks_for((size_t)v.NJ * v.B, 128), 128, 0, s>>>(v, h); }
-void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s) { k_pgs<<<blocks_for(v.B, PGS_THREADS), PGS_THREADS, 0, s>>>(v, dt, iters, mu); }
+void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s)
+{
+    static int use_tma = -1;
+    if (use_tma < 0) { const char* e = getenv("SLRBS_PGS_TMA"); use_tma = e ? atoi(e) : 0; }
+    if (use_tma) k_pgs_tma<<<blocks_for(v.B, 32), 32, 0, s>>>(v, dt, iters, mu);
+    else k_pgs<<<blocks_for(v.B, PGS_THREADS), PGS_THREADS, 0, s>>>(v, dt, iters, mu);
+}
 void launch_krylov(const View& v, int solver_id, int iters, cudaStream_t s)
 {
     if (v.NJ == 0) return;
