@@ -298,3 +298,63 @@ def test_krylov_trajectory_swinging_boxes():
         d = np.abs(ctx.download_state()["x"][0] - o.state()["x"]).max()
         assert np.isfinite(d) and d < 20 * max(self_sens, 1e-4), (solver_id, n, d, self_sens)
         ctx.close()
+
+
+def test_spherical_joints_match_oracle():
+    """Spherical (ball) joints have no scene in the reference but are public API (Spherical.cpp:34-52): a chain
+    of spheres hanging from a fixed box, rows bit-exact, trajectory within tolerance."""
+    def build():
+        o = Oracle()
+        o.add_body(1.0, BOX, [1, 1, 1], fixed=True, x=[0, 10, 0])
+        prev = 0
+        for k in range(6):
+            b = o.add_body(1.0 + 0.5 * k, SPHERE, [0.3], x=[0.8 * (k + 1), 10, 0], v=[0, 0, 0.5 * k])
+            o.add_spherical(prev, b, [0.4, 0, 0], [-0.4, 0, 0])
+            prev = b
+        o.set_params(collisions=False)
+        return o
+    o = build()
+    ctx = context_from_oracles([o], max_contacts=8); ctx.set_params(collisions=False)
+    ctx.stage_prepare(); ctx.stage_detect(); ctx.stage_jacobians(DT); ctx.sync()
+    o.stage_prepare(); o.stage_detect(); o.stage_jacobians()
+    gj, oj = ctx.joint_rows(0), o.joint_rows()
+    for k in ("J0", "J1", "J0Minv", "J1Minv"):
+        assert_bit_equal(gj[k], oj[k], k)
+    assert_bit_equal(gj["rhs"], o.solver_blocks(DT)["rhsj"], "rhs")
+    o2 = build()
+    ctx2 = context_from_oracles([o2], max_contacts=8); ctx2.set_params(collisions=False)
+    ctx2.step(DT, 100); o2.step(DT, 100); ctx2.sync()
+    np.testing.assert_allclose(ctx2.download_state()["x"][0], o2.state()["x"], rtol=0, atol=3e-3)
+    assert np.abs(o2.joint_rows()["phi"][:, :3]).max() < 0.05
+    ctx.close(); ctx2.close()
+
+
+def test_ragged_batch_with_per_scene_counts():
+    """Scenes of different sizes in one context (counts argument): each must equal its own oracle run, and
+    unused body / joint slots must be ignored."""
+    from slrbs_b200 import Context
+    from gpu_helpers import scene_arrays
+    specs = [("car", {}), ("sphere_on_box", {}), ("sphere_stack", {"k": 4}), ("swinging_boxes", {}), ("cylinder_on_plane", {})]
+    oracles = [Oracle(s, **kw) for s, kw in specs]
+    NBm = max(o.n_bodies for o in oracles); NJm = max(o.n_joints for o in oracles)
+    B = len(oracles)
+    ctx = Context(B, NBm, NJm, 64)
+    def pad(a, n, fill=0):
+        out = np.full((n,) + a.shape[1:], fill, a.dtype); out[: a.shape[0]] = a; return out
+    arrs = [scene_arrays(o) for o in oracles]
+    st = lambda k, n: np.stack([pad(a[k], n) for a in arrs])
+    q = st("q", NBm); q[..., 3][np.abs(q).sum(-1) == 0] = 1.0          # padding slots: identity quaternion
+    mass = st("mass", NBm); mass[mass == 0] = 1.0
+    ctx.upload_bodies(st("x", NBm), q, st("v", NBm), st("w", NBm), mass, st("ibody", NBm), st("ibodyinv", NBm),
+                      st("fixed", NBm), st("geom_type", NBm), st("geom", NBm), counts=[o.n_bodies for o in oracles])
+    jt = st("jtype", NJm); jt[jt == 0] = 2
+    q0 = st("q0", NJm); q0[..., 3][np.abs(q0).sum(-1) == 0] = 1.0
+    q1 = st("q1", NJm); q1[..., 3][np.abs(q1).sum(-1) == 0] = 1.0
+    ctx.upload_joints(jt, st("jb0", NJm), st("jb1", NJm), st("r0", NJm), q0, st("r1", NJm), q1, counts=[o.n_joints for o in oracles])
+    ctx.step(DT, 60); ctx.sync()
+    g = ctx.download_state(); cnt = ctx.contact_counts()
+    for s, o in enumerate(oracles):
+        o.step(DT, 60)
+        assert cnt[s] == o.n_contacts, specs[s]
+        np.testing.assert_allclose(g["x"][s, : o.n_bodies], o.state()["x"], rtol=0, atol=3e-3, err_msg=str(specs[s]))
+    ctx.close()
