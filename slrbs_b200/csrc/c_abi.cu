@@ -44,6 +44,10 @@ struct slrbs_ctx {
     std::vector<cudaEvent_t> ev; size_t ev_used = 0;
     double solve_ms = 0.0; int64_t solve_launches = 0, total_launches = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // one step captured as a CUDA graph (launch-bound small batches); re-captured when its inputs change
+    cudaGraphExec_t graph = nullptr;
+    struct { float dt, mu; int iters, solver, collisions, has_ext, launches; } gsig = { 0.f, 0.f, 0, 0, 0, 0, 0 };
+    int use_graph = 1;
 };
 
 namespace {
@@ -164,22 +168,24 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     if (prop.major != 10)
         return fail(SLRBS_E_CUDA, std::string("slrbs_create: device is ") + prop.name + ", kernels are built for sm_100a only");
     CU(cudaSetDevice(device));
+    init_detect_kernels();
+    init_level_kernels();
     slrbs_ctx* c = new slrbs_ctx();
+    { const char* g = std::getenv("SLRBS_GRAPH"); if (g) c->use_graph = std::atoi(g); }
     c->device = device;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     View& v = c->v;
     v.B = n_scenes; v.NB = max_bodies; v.NJ = max_joints; v.NC = max_contacts;
-    // Solver variant. Small and medium batches of scenes with enough bodies to expose row-level
-    // parallelism use the level-scheduled kernel (pgs_level.cu: G lanes per scene, measured 2-30x faster
-    // up to ~8k marble-box scenes); very large batches and tiny scenes (a car: 12 rows, chains) use one
-    // thread per scene, which then has the whole GPU's worth of independent scenes to hide latency. Both
+    // Solver variant. Small and medium batches use the level-scheduled kernel (pgs_level.cu: G lanes per
+    // scene; measured 1.4x (cars) to 30x (1000-sphere piles) faster up to ~8k scenes); very large batches
+    // use one thread per scene, which then has a GPU's worth of independent scenes to hide latency. Both
     // give the same impulses bit for bit; SLRBS_PGS_MODE=thread|level and SLRBS_LEVEL_GROUP=4|8|16|32 override.
     {
         const char* m = std::getenv("SLRBS_PGS_MODE");
         const bool fits = level_mode_fits(max_bodies) && detect_warp_fits(max_bodies, max_contacts, true);
         if (m && std::strcmp(m, "thread") == 0) v.level_mode = 0;
         else if (m && std::strcmp(m, "level") == 0) v.level_mode = fits ? 1 : 0;
-        else v.level_mode = (max_bodies >= 24 && n_scenes <= 8192 && fits) ? 1 : 0;
+        else v.level_mode = (n_scenes <= 8192 && fits) ? 1 : 0;
         const char* g = std::getenv("SLRBS_LEVEL_GROUP");
         c->level_group = level_group_size(v, g ? std::atoi(g) : 0);
         const char* bp = std::getenv("SLRBS_BROADPHASE");
@@ -217,6 +223,7 @@ void slrbs_destroy(slrbs_ctx* c)
     for (void* p : c->allocs) cudaFree(p);
     if (c->stage) cudaFree(c->stage);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->graph) cudaGraphExecDestroy(c->graph);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
@@ -386,16 +393,48 @@ int slrbs_stage_integrate(slrbs_ctx* c, float dt)
     return check_launch(c);
 }
 
+static int step_once(slrbs_ctx* c, float dt)
+{
+    int r;
+    if ((r = slrbs_stage_prepare(c)) || (r = slrbs_stage_detect(c)) || (r = slrbs_stage_jacobians(c, dt)) ||
+        (r = slrbs_stage_solve(c, dt)) || (r = slrbs_stage_integrate(c, dt)))
+        return r;
+    return 0;
+}
+
 int slrbs_step(slrbs_ctx* c, float dt, int n_steps)
 {
     if (!c || n_steps < 0) return fail(SLRBS_E_ARG, "slrbs_step: bad argument");
     CU(cudaSetDevice(c->device));
     int r;
-    for (int i = 0; i < n_steps; ++i) {
-        if ((r = slrbs_stage_prepare(c)) || (r = slrbs_stage_detect(c)) || (r = slrbs_stage_jacobians(c, dt)) ||
-            (r = slrbs_stage_solve(c, dt)) || (r = slrbs_stage_integrate(c, dt)))
-            return r;
+    if (!c->use_graph || c->profiling || n_steps == 0) {
+        for (int i = 0; i < n_steps; ++i) if ((r = step_once(c, dt))) return r;
+        return 0;
     }
+    // Replay one captured step n times: a small batch is launch-bound (5-7 kernels of a few microseconds each).
+    // Anything that is not a plain launch on the stream happens before the capture.
+    if (c->v.level_mode && c->joints_dirty) { launch_joint_levels(c->v, c->stream); c->joints_dirty = false; if ((r = check_launch(c))) return r; }
+    if (c->solver_id != 0 && c->v.NJ > 0 && !c->v.kry) { if ((r = dalloc(c, &c->v.kry, (size_t)7 * 5 * c->v.NJ * c->v.B))) return r; }
+    const bool same = c->graph && c->gsig.dt == dt && c->gsig.mu == c->mu && c->gsig.iters == c->solver_iters &&
+                      c->gsig.solver == c->solver_id && c->gsig.collisions == c->collisions && c->gsig.has_ext == c->v.has_ext;
+    if (!same) {
+        if (c->graph) { CU(cudaGraphExecDestroy(c->graph)); c->graph = nullptr; }
+        const int64_t before = c->total_launches;
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        r = step_once(c, dt);
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (r) { if (g) cudaGraphDestroy(g); return r; }
+        if (e != cudaSuccess) return fail(SLRBS_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        CU(cudaGraphInstantiate(&c->graph, g, 0));
+        CU(cudaGraphDestroy(g));
+        c->gsig.launches = (int)(c->total_launches - before);
+        c->total_launches = before;
+        c->gsig.dt = dt; c->gsig.mu = c->mu; c->gsig.iters = c->solver_iters; c->gsig.solver = c->solver_id;
+        c->gsig.collisions = c->collisions; c->gsig.has_ext = c->v.has_ext;
+    }
+    for (int i = 0; i < n_steps; ++i) CU(cudaGraphLaunch(c->graph, c->stream));
+    c->total_launches += (int64_t)n_steps * c->gsig.launches;
     return 0;
 }
 

@@ -550,6 +550,15 @@ bool detect_warp_fits(int NB, int NC, bool level)
     return warp_bytes <= 200 * 1024 || cta_bytes <= 200 * 1024;
 }
 
+// per-device kernel attributes (called from slrbs_create with the device current)
+void init_detect_kernels()
+{
+    cudaFuncSetAttribute(k_detect_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_detect_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_detect_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_detect_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 void launch_detect(const View& v, int broadphase, cudaStream_t s)
 {
     // broadphase: 0 = off (all pairs), 1 = hashed grid, -1 = auto (grid for scenes of >= 512 bodies)
@@ -557,14 +566,6 @@ void launch_detect(const View& v, int broadphase, cudaStream_t s)
     int H = 64;
     while (H < v.NB && H < 4096) H <<= 1;
     const bool lv = v.level_mode != 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_detect_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_detect_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_detect_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_detect_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
     // big scenes in a batch too small to fill the GPU with one warp per scene: one CTA (16 warps) per scene
     const size_t cta_smem = (size_t)v.NB * 16 + detect_cta_smem_ints(v.NB, v.NC, lv, grid, H, DETECT_CTA_THREADS / 32) * 4;
     if (v.NB >= 128 && v.B <= 4096 && cta_smem <= 200 * 1024) {

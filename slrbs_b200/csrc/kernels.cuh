@@ -18,6 +18,8 @@ void launch_prepare(const View& v, cudaStream_t s);
 // detect.cu; broadphase: 0 all pairs, 1 hashed grid, -1 auto (grid for scenes of >= 512 bodies)
 void launch_detect(const View& v, int broadphase, cudaStream_t s);
 bool detect_warp_fits(int NB, int NC, bool level);
+void init_detect_kernels();
+void init_level_kernels();
 void launch_contact_rows(const View& v, float h, cudaStream_t s);
 void launch_joint_rows(const View& v, float h, cudaStream_t s);
 void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s);

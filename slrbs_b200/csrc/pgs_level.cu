@@ -228,21 +228,24 @@ static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t
 {
     const int spc = LV_THREADS / G;
     const size_t smem = (size_t)spc * v.NB * 2 * sizeof(float4);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_pgs_lv<G, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(k_pgs_lv<G, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_set = true;
-    }
     const unsigned blocks = (unsigned)((v.B + spc - 1) / spc);
     if (blocks >= 148u * 4u) k_pgs_lv<G, 4><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
     else k_pgs_lv<G, 3><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
 }
 
+template <int G>
+static void init_lv()
+{
+    cudaFuncSetAttribute(k_pgs_lv<G, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_lv<G, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+}
+// per-device kernel attributes (called from slrbs_create with the device current)
+void init_level_kernels() { init_lv<4>(); init_lv<8>(); init_lv<16>(); init_lv<32>(); }
+
 int level_group_size(const View& v, int requested)
 {
     int g = requested;
-    if (g != 4 && g != 8 && g != 16 && g != 32) g = v.NB <= 256 ? 8 : (v.NB <= 512 ? 16 : 32);
+    if (g != 4 && g != 8 && g != 16 && g != 32) g = v.NB < 24 ? 4 : (v.NB <= 96 ? 8 : (v.NB <= 512 ? 16 : 32));
     // the accumulators of LV_THREADS / g scenes must fit in shared memory
     while (g < 32 && (size_t)(LV_THREADS / g) * v.NB * 32 > 200 * 1024) g <<= 1;
     return g;
