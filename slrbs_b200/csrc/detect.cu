@@ -568,7 +568,7 @@ void launch_detect(const View& v, int broadphase, cudaStream_t s)
     const bool lv = v.level_mode != 0;
     // big scenes in a batch too small to fill the GPU with one warp per scene: one CTA (16 warps) per scene
     const size_t cta_smem = (size_t)v.NB * 16 + detect_cta_smem_ints(v.NB, v.NC, lv, grid, H, DETECT_CTA_THREADS / 32) * 4;
-    if (v.NB >= 128 && v.B <= 4096 && cta_smem <= 200 * 1024) {
+    if (((v.NB >= 512 && v.B <= 4096) || (v.NB >= 128 && v.B <= 512)) && cta_smem <= 200 * 1024) {
         if (grid) k_detect_cta<true><<<(unsigned)v.B, DETECT_CTA_THREADS, cta_smem, s>>>(v, H);
         else k_detect_cta<false><<<(unsigned)v.B, DETECT_CTA_THREADS, cta_smem, s>>>(v, H);
         return;

@@ -306,6 +306,32 @@ __global__ void __launch_bounds__(128) k_joint_rows(View v, float h)
 // One-entry write-back register cache of a body accumulator. Rows are visited in (i, j) order, so
 // body0 of consecutive rows is almost always the same body (all contacts of body i, all hinges of a
 // chassis): it stays in registers instead of making a dependent HBM round trip per row.
+// L2 eviction-priority policies: the row stream is read once per sweep and must not push the body
+// accumulators (re-read every few rows) out of the 126 MB L2
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_hint(const float4* p, unsigned long long pol)
+{
+    float4 r;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_hint(float4* p, const float4& v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 struct WCache {
     int id;          // cached body index, -1 = empty
     V3 l, a;
@@ -314,8 +340,9 @@ __device__ __forceinline__ void wc_flush(const View& v, int scene, WCache& c)
 {
     if (c.id >= 0) {
         const size_t i = at(v, c.id, scene);
-        v.wl[i] = mk4(c.l, 0.f);
-        v.wa[i] = mk4(c.a, 0.f);
+        const unsigned long long keep = l2_policy_evict_last();
+        st_hint(&v.wl[i], mk4(c.l, 0.f), keep);
+        st_hint(&v.wa[i], mk4(c.a, 0.f), keep);
     }
 }
 __device__ __forceinline__ void wc_acquire(const View& v, int scene, WCache& c, int id)
@@ -323,7 +350,8 @@ __device__ __forceinline__ void wc_acquire(const View& v, int scene, WCache& c, 
     if (c.id != id) {
         wc_flush(v, scene, c);
         const size_t i = at(v, id, scene);
-        c.l = mk3(v.wl[i]); c.a = mk3(v.wa[i]);
+        const unsigned long long keep = l2_policy_evict_last();
+        c.l = mk3(ld_hint(&v.wl[i], keep)); c.a = mk3(ld_hint(&v.wa[i], keep));
         c.id = id;
     }
 }
@@ -333,6 +361,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gmem_src, unsigned long long pol)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -344,11 +377,12 @@ __device__ __forceinline__ void with_bodies(const View& v, int scene, WCache& wc
 {
     size_t w1i = 0;
     V3 w1l = mk3(0.f, 0.f, 0.f), w1a = w1l;
+    const unsigned long long keep = l2_policy_evict_last();
     const bool hit1 = dyn1 && (id1 == wc.id) && !(dyn0 && id0 != wc.id);
     if (dyn0) wc_acquire(v, scene, wc, id0);
     if (dyn1) {
         if (hit1) { w1l = wc.l; w1a = wc.a; }
-        else { w1i = at(v, id1, scene); w1l = mk3(v.wl[w1i]); w1a = mk3(v.wa[w1i]); }
+        else { w1i = at(v, id1, scene); w1l = mk3(ld_hint(&v.wl[w1i], keep)); w1a = mk3(ld_hint(&v.wa[w1i], keep)); }
     }
     if (hit1) {                                  // body0 is fixed here, the cache line is body1's
         V3 dl = mk3(0.f, 0.f, 0.f), da = dl;
@@ -356,7 +390,7 @@ __device__ __forceinline__ void with_bodies(const View& v, int scene, WCache& wc
         wc.l = w1l; wc.a = w1a;
     } else {
         solve(wc.l, wc.a, w1l, w1a);
-        if (dyn1) { v.wl[w1i] = mk4(w1l, 0.f); v.wa[w1i] = mk4(w1a, 0.f); }
+        if (dyn1) { st_hint(&v.wl[w1i], mk4(w1l, 0.f), keep); st_hint(&v.wa[w1i], mk4(w1a, 0.f), keep); }
     }
 }
 
@@ -431,13 +465,14 @@ __global__ void __launch_bounds__(PGS_THREADS, PGS_MIN_CTAS) k_pgs(View v, float
     // prefetched lambda could be stale, so it is then re-read directly.
     const int total = nc * iters;
     const bool lam_direct = nc < PGS_STAGES + 1;
+    const unsigned long long pol_stream = l2_policy_evict_first();
     int fetch_row = 0, fetched = 0;
     auto fetch = [&]() {
         if (fetched < total) {
             const int st = fetched % PGS_STAGES;
             const float4* src = &v.crow[at_crow(v, 0, fetch_row, scene)];       // one contiguous 8 KB tile per warp
 #pragma unroll
-            for (int f = 0; f < CROW_FIELDS; ++f) cp_async16(&ring[st][f][tid], src + f * 32);
+            for (int f = 0; f < CROW_FIELDS; ++f) cp_async16_hint(&ring[st][f][tid], src + f * 32, pol_stream);
             ++fetched;
             if (++fetch_row == nc) fetch_row = 0;
         }

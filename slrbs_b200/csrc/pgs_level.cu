@@ -229,7 +229,7 @@ static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t
     const int spc = LV_THREADS / G;
     const size_t smem = (size_t)spc * v.NB * 2 * sizeof(float4);
     const unsigned blocks = (unsigned)((v.B + spc - 1) / spc);
-    if (blocks >= 148u * 4u) k_pgs_lv<G, 4><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
+    if (blocks >= 148u * 2u) k_pgs_lv<G, 4><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
     else k_pgs_lv<G, 3><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
 }
 
