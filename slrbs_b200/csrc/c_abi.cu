@@ -182,7 +182,8 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     // give the same impulses bit for bit; SLRBS_PGS_MODE=thread|level and SLRBS_LEVEL_GROUP=4|8|16|32 override.
     {
         const char* m = std::getenv("SLRBS_PGS_MODE");
-        const bool fits = level_mode_fits(max_bodies) && detect_warp_fits(max_bodies, max_contacts, true);
+        const bool fits = level_mode_fits(max_bodies) && detect_warp_fits(max_bodies) &&
+                          contact_levels_smem(max_bodies, max_contacts) <= 200 * 1024;
         if (m && std::strcmp(m, "thread") == 0) v.level_mode = 0;
         else if (m && std::strcmp(m, "level") == 0) v.level_mode = fits ? 1 : 0;
         else v.level_mode = (n_scenes <= 8192 && fits) ? 1 : 0;
@@ -197,7 +198,7 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
 #define A(p, n) if ((r = dalloc(c, &p, n))) { slrbs_destroy(c); return r; }
     A(v.nbodies, v.B) A(v.njoints, v.B) A(v.ncontacts, v.B) A(v.overflow, 1) A(v.visit_counters, 2)
     A(v.pos, nb) A(v.quat, nb) A(v.vel, nb) A(v.omg, nb) A(v.flags, nb) A(v.geomA, nb) A(v.geomB, nb)
-    A(v.ibody, 9 * nb) A(v.ibodyinv, 9 * nb) A(v.cproxy, nb) A(v.force, nb) A(v.torque, nb)
+    A(v.ibody, 9 * nb) A(v.ibodyinv, 9 * nb) A(v.cproxy, nb) A(v.bext, nb) A(v.force, nb) A(v.torque, nb)
     A(v.extf, nb) A(v.extt, nb) A(v.Iw, 9 * nb) A(v.Iinvw, 9 * nb) A(v.wl, nb) A(v.wa, nb)
     A(v.s_pos, nb) A(v.s_quat, nb) A(v.s_vel, nb) A(v.s_omg, nb)
     A(v.jdef, nj) A(v.jr0, nj) A(v.jq0, nj) A(v.jr1, nj) A(v.jq1, nj) A(v.jlam, nj) A(v.jlam4, nj)
@@ -367,6 +368,7 @@ int slrbs_stage_detect(slrbs_ctx* c)
     CU(cudaSetDevice(c->device));
     if (!c->collisions || c->v.NC == 0) return 0;               // RigidBodySystem.cpp:77
     launch_detect(c->v, c->broadphase, c->stream);
+    if (c->v.level_mode) { launch_contact_levels(c->v, c->stream); return check_launch(c, 2); }
     return check_launch(c);
 }
 int slrbs_stage_jacobians(slrbs_ctx* c, float dt)

@@ -3,8 +3,7 @@
 // k_detect_warp<GRID>  one WARP per scene. The scene's body proxies are staged in shared memory. For
 //   each body i in index order the lanes test up to 32 partners j > i at a time, in ascending j, and
 //   contacts are appended in the reference's lexicographic (i, j) order by a warp-ballot prefix sum
-//   (up to 4 per pair in the fixed A,B,C,D order). In level mode the warp also assigns every contact
-//   its dependency level as it is emitted (pgs_level.cu) and counting-sorts the contacts by level.
+//   (up to 4 per pair in the fixed A,B,C,D order).
 //   GRID = false: partners are all j > i (the reference's O(n^2) loop, CollisionDetect.cpp:32-34).
 //   GRID = true : broad phase. Spheres are binned into a hashed uniform grid of cell size
 //     2 r_max + 2e-3; the partners of sphere i are the spheres of its 27 neighbouring cells plus every
@@ -22,8 +21,6 @@ enum { CAND_CAP = 128 };          // candidate partners of one row in the grid p
 struct DetectSmem {               // per-warp shared-memory arrays
     float4* sp;                   // [NB] proxies x y z | sphere radius
     int* sf;                      // [NB] flags
-    int* last;                    // [NB] level mode: last level that touched a body
-    int* hist;                    // [NC+1] level mode: contacts per level, then level starts
     int* cell_start;              // [H+1] grid: bucket offsets (after the fill: bucket ends)
     int* cell_items;              // [NB] grid: sphere indices grouped by bucket
     int* special;                 // [NB] grid: non-sphere body indices, ascending
@@ -31,10 +28,9 @@ struct DetectSmem {               // per-warp shared-memory arrays
     int* sorted;                  // [CAND_CAP]
 };
 
-__host__ __device__ inline size_t detect_smem_ints(int NB, int NC, bool level, bool grid, int H)
+__host__ __device__ inline size_t detect_smem_ints(int NB, bool grid, int H)
 {
     size_t n = (size_t)NB;                                     // sf
-    if (level) n += (size_t)NB + NC + 2;
     if (grid) n += (size_t)H + 1 + NB + NB + 2 * CAND_CAP;
     return n;
 }
@@ -44,10 +40,10 @@ __device__ __forceinline__ int cell_hash(int ix, int iy, int iz, int Hmask)
     return (int)(((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u)) & Hmask;
 }
 
-// Tests the pair (i, j) on every lane that has a partner (j >= 0), appends the contacts in lane order and,
-// in level mode, assigns their levels. `count` / `nlev` are warp-uniform running totals.
+// Tests the pair (i, j) on every lane that has a partner (j >= 0) and appends the contacts in lane order.
+// `count` is the warp-uniform running total.
 __device__ __forceinline__ void emit_chunk(const View& v, const DetectSmem& sm, int scene, int lane, int i, const float4& ci,
-                                           int fi, int j, bool lv, int& count, int& nlev)
+                                           int fi, int j, int& count)
 {
     PairOut o;
     o.cnt = 0;
@@ -71,34 +67,6 @@ __device__ __forceinline__ void emit_chunk(const View& v, const DetectSmem& sm, 
         total = __shfl_sync(0xffffffffu, incl, 31);
     }
     write_contacts(v, scene, count + before, o);
-    if (lv) {
-        // levels in emission order: every lane follows the same sequence, the emitting lane records
-        unsigned m = any;
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const int b0 = __shfl_sync(0xffffffffu, o.b0, src), b1 = __shfl_sync(0xffffffffu, o.b1, src);
-            const int c = __shfl_sync(0xffffffffu, o.cnt, src), base = __shfl_sync(0xffffffffu, before, src);
-            const bool dyn0 = !(sm.sf[b0] & FLAG_FIXED), dyn1 = !(sm.sf[b1] & FLAG_FIXED);
-            int L = 0;
-            if (dyn0) L = max(L, sm.last[b0]);
-            if (dyn1) L = max(L, sm.last[b1]);
-            __syncwarp();
-            for (int k = 0; k < c; ++k) {                        // contacts of one pair share both bodies: consecutive levels
-                if (count + base + k >= v.NC) break;             // dropped (capacity overflow is reported by slrbs_sync)
-                ++L;
-                const int rank = sm.hist[L];
-                __syncwarp();
-                if (lane == src) {
-                    sm.hist[L] = rank + 1;
-                    v.cpos[at(v, count + base + k, scene)] = (L << 16) | rank;
-                }
-            }
-            if (lane == src) { if (dyn0) sm.last[b0] = L; if (dyn1) sm.last[b1] = L; }
-            nlev = max(nlev, L);
-            __syncwarp();
-        }
-    }
     count += total;
 }
 
@@ -160,13 +128,10 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int scene = blockIdx.x * warps_per_cta + warp;
     if (scene >= v.B) return;
-    const bool lv = v.level_mode != 0;
     DetectSmem sm;
     sm.sp = smem4 + (size_t)warp * v.NB;
-    int* ip = reinterpret_cast<int*>(smem4 + (size_t)warps_per_cta * v.NB) + (size_t)warp * detect_smem_ints(v.NB, v.NC, lv, GRID, H);
+    int* ip = reinterpret_cast<int*>(smem4 + (size_t)warps_per_cta * v.NB) + (size_t)warp * detect_smem_ints(v.NB, GRID, H);
     sm.sf = ip; ip += v.NB;
-    sm.last = ip; sm.hist = ip + v.NB;
-    if (lv) ip += v.NB + v.NC + 2;
     sm.cell_start = ip; sm.cell_items = ip + H + 1; sm.special = sm.cell_items + v.NB;
     sm.cand = sm.special + v.NB; sm.sorted = sm.cand + CAND_CAP;
 
@@ -178,10 +143,8 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta, 
         const int f = v.flags[i];
         sm.sp[b] = c;
         sm.sf[b] = f;
-        if (lv) sm.last[b] = 0;
         if ((f & FLAG_TYPE_MASK) == GEOM_SPHERE) rmax = fmaxf(rmax, c.w);
     }
-    if (lv) for (int l = lane; l <= v.NC; l += 32) sm.hist[l] = 0;
     __syncwarp();
 
     // ---- broad phase: hashed uniform grid over the spheres, side list of the other shapes ----
@@ -242,7 +205,7 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta, 
     int nsph = 0;
     if (GRID) nsph = n - nspecial;
 
-    int count = 0, nlev = 0;
+    int count = 0;
     for (int i = 0; i < n; ++i) {
         const float4 ci = sm.sp[i];
         const int fi = sm.sf[i];
@@ -253,7 +216,7 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta, 
                 dense_row = false;
                 for (int k0 = 0; k0 < nlive; k0 += 32) {
                     const int k = k0 + lane;
-                    emit_chunk(v, sm, scene, lane, i, ci, fi, k < nlive ? sm.sorted[k] : -1, lv, count, nlev);
+                    emit_chunk(v, sm, scene, lane, i, ci, fi, k < nlive ? sm.sorted[k] : -1, count);
                 }
                 __syncwarp();
             }
@@ -261,54 +224,24 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta, 
         if (dense_row) {
             for (int j0 = i + 1; j0 < n; j0 += 32) {
                 const int j = j0 + lane;
-                emit_chunk(v, sm, scene, lane, i, ci, fi, j < n ? j : -1, lv, count, nlev);
+                emit_chunk(v, sm, scene, lane, i, ci, fi, j < n ? j : -1, count);
             }
         }
     }
-    const int nc = count < v.NC ? count : v.NC;
-    if (lane == 0) v.ncontacts[scene] = nc;
-    if (lv) {
-        nlev = min(nlev, v.NC);
-        // exclusive prefix of the per-level counts -> level starts (in place), level ends to global
-        int carry = 0;
-        for (int l0 = 1; l0 <= nlev; l0 += 32) {
-            const int l = l0 + lane;
-            const int c = l <= nlev ? sm.hist[l] : 0;
-            int incl = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            if (l <= nlev) {
-                sm.hist[l] = carry + incl - c;
-                v.clev_end[at(v, l, scene)] = min(carry + incl, nc);
-            }
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        __syncwarp();
-        for (int c = lane; c < nc; c += 32) {
-            const size_t ci2 = at(v, c, scene);
-            const int packed = v.cpos[ci2];
-            v.cpos[ci2] = sm.hist[packed >> 16] + (packed & 0xffff);
-        }
-        if (lane == 0) v.nclev[scene] = nlev;
-    }
+    if (lane == 0) v.ncontacts[scene] = count < v.NC ? count : v.NC;
 }
 
 // ------------------------------------------------------------------------------------
 // k_detect_cta<GRID>  one CTA per scene, for scenes of hundreds or thousands of bodies. Rows i are dealt
 // round-robin to the warps; since the contact list must stay in (i, j) order the rows are walked twice:
 // pass 1 counts the contacts of every row, a scan turns the counts into row offsets, pass 2 repeats the
-// tests and writes each row's contacts at its offset. In level mode one warp then assigns the levels
-// in list order (a cheap sequential pass over the ids) and the block counting-sorts by level.
+// tests and writes each row's contacts at its offset.
 // ------------------------------------------------------------------------------------
 enum { DETECT_CTA_THREADS = 512 };
 
-__host__ __device__ inline size_t detect_cta_smem_ints(int NB, int NC, bool level, bool grid, int H, int warps)
+__host__ __device__ inline size_t detect_cta_smem_ints(int NB, bool grid, int H, int warps)
 {
     size_t n = (size_t)NB + NB + 2;                            // sf, rowcnt
-    if (level) n += (size_t)NB + NC + 2;
     if (grid) n += (size_t)H + 1 + NB + NB + 2 * CAND_CAP * (size_t)warps;
     return n;
 }
@@ -357,14 +290,11 @@ __global__ void __launch_bounds__(DETECT_CTA_THREADS) k_detect_cta(View v, int H
     __shared__ int s_rmax, s_nspecial, s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = DETECT_CTA_THREADS / 32;
     const int scene = blockIdx.x;
-    const bool lv = v.level_mode != 0;
     DetectSmem sm;
     sm.sp = smem4;
     int* ip = reinterpret_cast<int*>(smem4 + v.NB);
     sm.sf = ip; ip += v.NB;
     int* rowcnt = ip; ip += v.NB + 2;
-    sm.last = ip; sm.hist = ip + v.NB;
-    if (lv) ip += v.NB + v.NC + 2;
     sm.cell_start = ip; sm.cell_items = ip + H + 1; sm.special = sm.cell_items + v.NB;
     sm.cand = sm.special + v.NB + (size_t)warp * 2 * CAND_CAP; sm.sorted = sm.cand + CAND_CAP;
 
@@ -377,10 +307,8 @@ __global__ void __launch_bounds__(DETECT_CTA_THREADS) k_detect_cta(View v, int H
         const float4 c = v.cproxy[i];
         const int f = v.flags[i];
         sm.sp[b] = c; sm.sf[b] = f;
-        if (lv) sm.last[b] = 0;
         if ((f & FLAG_TYPE_MASK) == GEOM_SPHERE) rmax = fmaxf(rmax, c.w);
     }
-    if (lv) for (int l = tid; l <= v.NC; l += DETECT_CTA_THREADS) sm.hist[l] = 0;
     if (GRID) {
         for (int c = tid; c <= H; c += DETECT_CTA_THREADS) sm.cell_start[c] = 0;
         atomicMax(&s_rmax, __float_as_int(rmax));              // radii are >= 0: integer order = float order
@@ -461,63 +389,7 @@ __global__ void __launch_bounds__(DETECT_CTA_THREADS) k_detect_cta(View v, int H
     // pass 2: write every row at its offset (write_contacts drops what does not fit and raises the flag)
     for (int i = warp; i < n; i += W) detect_row<GRID, true>(v, sm, scene, lane, i, n, inv_h, H, nsph, nspecial, rowcnt[i]);
     __syncthreads();
-    const int nc = s_total < v.NC ? s_total : v.NC;
-    if (tid == 0) v.ncontacts[scene] = nc;
-    if (!lv) return;
-    // levels in list order (warp 0), then the counting sort by level (block)
-    __shared__ int s_nlev;
-    if (warp == 0) {
-        int nlev = 0;
-        for (int c0 = 0; c0 < nc; c0 += 32) {
-            const int c = c0 + lane;
-            int2 ids = make_int2(0, 0);
-            if (c < nc) ids = v.cids[at(v, c, scene)];
-            int mine = 0;
-            const int m = min(32, nc - c0);
-            for (int k = 0; k < m; ++k) {
-                const int b0 = __shfl_sync(0xffffffffu, ids.x, k), b1 = __shfl_sync(0xffffffffu, ids.y, k);
-                const bool dyn0 = !(sm.sf[b0] & FLAG_FIXED), dyn1 = !(sm.sf[b1] & FLAG_FIXED);
-                int L = 0;
-                if (dyn0) L = max(L, sm.last[b0]);
-                if (dyn1) L = max(L, sm.last[b1]);
-                ++L;
-                const int rank = sm.hist[L];
-                __syncwarp();
-                if (lane == k) {
-                    sm.hist[L] = rank + 1;
-                    if (dyn0) sm.last[b0] = L;
-                    if (dyn1) sm.last[b1] = L;
-                    mine = (L << 16) | rank;
-                }
-                nlev = max(nlev, L);
-                __syncwarp();
-            }
-            if (c < nc) v.cpos[at(v, c, scene)] = mine;
-        }
-        int carry = 0;
-        for (int l0 = 1; l0 <= nlev; l0 += 32) {
-            const int l = l0 + lane;
-            const int c = l <= nlev ? sm.hist[l] : 0;
-            int incl = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            if (l <= nlev) {
-                sm.hist[l] = carry + incl - c;
-                v.clev_end[at(v, l, scene)] = carry + incl;
-            }
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) { s_nlev = nlev; v.nclev[scene] = nlev; }
-    }
-    __syncthreads();
-    for (int c = tid; c < nc; c += DETECT_CTA_THREADS) {
-        const size_t ci = at(v, c, scene);
-        const int packed = v.cpos[ci];
-        v.cpos[ci] = sm.hist[packed >> 16] + (packed & 0xffff);
-    }
+    if (tid == 0) v.ncontacts[scene] = s_total < v.NC ? s_total : v.NC;
 }
 
 // scenes of a few bodies: one thread per scene walks the pairs
@@ -542,11 +414,11 @@ __global__ void __launch_bounds__(128) k_detect_serial(View v)
     v.ncontacts[scene] = count < v.NC ? count : v.NC;
 }
 
-bool detect_warp_fits(int NB, int NC, bool level)
+bool detect_warp_fits(int NB)
 {
     const bool grid = NB >= 512;
-    const size_t warp_bytes = (size_t)NB * 16 + detect_smem_ints(NB, NC, level, grid, 1024) * 4;
-    const size_t cta_bytes = (size_t)NB * 16 + detect_cta_smem_ints(NB, NC, level, grid, 1024, DETECT_CTA_THREADS / 32) * 4;
+    const size_t warp_bytes = (size_t)NB * 16 + detect_smem_ints(NB, grid, 4096) * 4;
+    const size_t cta_bytes = (size_t)NB * 16 + detect_cta_smem_ints(NB, grid, 4096, DETECT_CTA_THREADS / 32) * 4;
     return warp_bytes <= 200 * 1024 || cta_bytes <= 200 * 1024;
 }
 
@@ -565,20 +437,19 @@ void launch_detect(const View& v, int broadphase, cudaStream_t s)
     const bool grid = broadphase > 0 || (broadphase < 0 && v.NB >= 512);
     int H = 64;
     while (H < v.NB && H < 4096) H <<= 1;
-    const bool lv = v.level_mode != 0;
     // big scenes in a batch too small to fill the GPU with one warp per scene: one CTA (16 warps) per scene
-    const size_t cta_smem = (size_t)v.NB * 16 + detect_cta_smem_ints(v.NB, v.NC, lv, grid, H, DETECT_CTA_THREADS / 32) * 4;
+    const size_t cta_smem = (size_t)v.NB * 16 + detect_cta_smem_ints(v.NB, grid, H, DETECT_CTA_THREADS / 32) * 4;
     if (((v.NB >= 512 && v.B <= 4096) || (v.NB >= 128 && v.B <= 512)) && cta_smem <= 200 * 1024) {
         if (grid) k_detect_cta<true><<<(unsigned)v.B, DETECT_CTA_THREADS, cta_smem, s>>>(v, H);
         else k_detect_cta<false><<<(unsigned)v.B, DETECT_CTA_THREADS, cta_smem, s>>>(v, H);
         return;
     }
-    const size_t per_warp = (size_t)v.NB * 16 + detect_smem_ints(v.NB, v.NC, lv, grid, H) * 4;
+    const size_t per_warp = (size_t)v.NB * 16 + detect_smem_ints(v.NB, grid, H) * 4;
     int warps = 8;
     while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
     const size_t smem = per_warp * warps;
     // tiny scenes (car: 15 pairs) leave a warp idle: one thread per scene is faster there; huge ones do not fit
-    if ((v.NB < 24 && !lv) || smem > 200 * 1024) { k_detect_serial<<<(unsigned)((v.B + 127) / 128), 128, 0, s>>>(v); return; }
+    if ((v.NB < 24 && !v.level_mode) || smem > 200 * 1024) { k_detect_serial<<<(unsigned)((v.B + 127) / 128), 128, 0, s>>>(v); return; }
     const unsigned blocks = (unsigned)((v.B + warps - 1) / warps);
     if (grid) k_detect_warp<true><<<blocks, warps * 32, smem, s>>>(v, warps, H);
     else k_detect_warp<false><<<blocks, warps * 32, smem, s>>>(v, warps, H);

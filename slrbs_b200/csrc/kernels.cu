@@ -63,6 +63,14 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
     const int fl = v.flags[i];
     const float4 ga = v.geomA[i];
     v.cproxy[i] = make_float4(px.x, px.y, px.z, ((fl & FLAG_TYPE_MASK) == GEOM_SPHERE) ? ga.x : 0.f);
+    if ((fl & FLAG_TYPE_MASK) == GEOM_BOX) {
+        // half extents of the box's world AABB: |R| * dim/2 (only used to skip sphere-box tests that cannot touch)
+        const M3 R = rotation_matrix(mkq(v.quat[i]));
+        const V3 hd = mk3(0.5f * ga.x, 0.5f * ga.y, 0.5f * ga.z);
+        v.bext[i] = make_float4(fabsf(R.m[0][0]) * hd.x + fabsf(R.m[0][1]) * hd.y + fabsf(R.m[0][2]) * hd.z,
+                                fabsf(R.m[1][0]) * hd.x + fabsf(R.m[1][1]) * hd.y + fabsf(R.m[1][2]) * hd.z,
+                                fabsf(R.m[2][0]) * hd.x + fabsf(R.m[2][1]) * hd.y + fabsf(R.m[2][2]) * hd.z, 0.f);
+    }
     // RigidBody::updateInertiaMatrix (RigidBody.cpp:78-89)
     if (!(fl & FLAG_FIXED)) {
         const Q4 q = mkq(v.quat[i]);

@@ -17,7 +17,7 @@ struct JointStage {
 void launch_prepare(const View& v, cudaStream_t s);
 // detect.cu; broadphase: 0 all pairs, 1 hashed grid, -1 auto (grid for scenes of >= 512 bodies)
 void launch_detect(const View& v, int broadphase, cudaStream_t s);
-bool detect_warp_fits(int NB, int NC, bool level);
+bool detect_warp_fits(int NB);
 void init_detect_kernels();
 void init_level_kernels();
 void launch_contact_rows(const View& v, float h, cudaStream_t s);
@@ -26,6 +26,8 @@ void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s);
 void launch_krylov(const View& v, int solver_id, int iters, cudaStream_t s);
 // level-scheduled solver (pgs_level.cu)
 void launch_joint_levels(const View& v, cudaStream_t s);
+void launch_contact_levels(const View& v, cudaStream_t s);
+size_t contact_levels_smem(int NB, int NC);
 void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, cudaStream_t s);
 int  level_group_size(const View& v, int requested);
 bool level_mode_fits(int max_bodies);

@@ -57,6 +57,7 @@ struct View {
     float  *ibody;      // [9][NB][B]
     float  *ibodyinv;   // [9][NB][B]
     float4 *cproxy;     // x y z | sphere radius (0 for other shapes): narrow-phase inner-loop stream
+    float4 *bext;       // boxes: half extents of the world-axis-aligned bounding box | - (narrow-phase cull)
     float4 *force;      // f | -
     float4 *torque;     // tau | -
     float4 *extf, *extt;

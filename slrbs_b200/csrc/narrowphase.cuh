@@ -111,6 +111,18 @@ __device__ __noinline__ void cylinder_plane(PairOut& o, const float4* __restrict
     }
 }
 
+// Conservative cull for sphere vs box: the sphere centre must lie inside the box's world AABB grown by the
+// radius and the 1e-3 contact margin for the exact test (CollisionDetect.cpp:142) to succeed; the extra
+// slack (1e-3 absolute + a few ulps of the coordinates) covers the rounding of the AABB itself.
+__device__ __forceinline__ bool sphere_box_may_touch(const float4& cs, const float4& cb, const float4& ext)
+{
+    const float r = cs.w + 2e-3f;
+    const float dx = fabsf(cs.x - cb.x), dy = fabsf(cs.y - cb.y), dz = fabsf(cs.z - cb.z);
+    return dx <= ext.x + r + 4e-6f * (fabsf(cs.x) + fabsf(cb.x) + ext.x) &&
+           dy <= ext.y + r + 4e-6f * (fabsf(cs.y) + fabsf(cb.y) + ext.y) &&
+           dz <= ext.z + r + 4e-6f * (fabsf(cs.z) + fabsf(cb.z) + ext.z);
+}
+
 // the reference's dispatch chain for the ordered pair (i < j), CollisionDetect.cpp:41-73
 __device__ __forceinline__ void test_pair(PairOut& o, const View& v, int scene, int i, int j,
                                           const float4& ci, int fi, const float4& cj, int fj)
@@ -119,8 +131,13 @@ __device__ __forceinline__ void test_pair(PairOut& o, const View& v, int scene, 
     if ((fi & fj) & FLAG_FIXED) return;
     const int ti = fi & FLAG_TYPE_MASK, tj = fj & FLAG_TYPE_MASK;
     if (ti == GEOM_SPHERE && tj == GEOM_SPHERE)          sphere_sphere(o, i, j, ci, cj);
-    else if (ti == GEOM_SPHERE && tj == GEOM_BOX)        sphere_box(o, v.quat, v.geomA, at(v, j, scene), i, j, ci, cj);
-    else if (tj == GEOM_SPHERE && ti == GEOM_BOX)        sphere_box(o, v.quat, v.geomA, at(v, i, scene), j, i, cj, ci);
+    else if (ti == GEOM_SPHERE && tj == GEOM_BOX) {
+        const size_t bj = at(v, j, scene);
+        if (sphere_box_may_touch(ci, cj, __ldg(&v.bext[bj]))) sphere_box(o, v.quat, v.geomA, bj, i, j, ci, cj);
+    } else if (tj == GEOM_SPHERE && ti == GEOM_BOX) {
+        const size_t bi = at(v, i, scene);
+        if (sphere_box_may_touch(cj, ci, __ldg(&v.bext[bi]))) sphere_box(o, v.quat, v.geomA, bi, j, i, cj, ci);
+    }
     else if (ti == GEOM_CYLINDER && tj == GEOM_PLANE)    cylinder_plane(o, v.quat, v.geomA, v.geomB, at(v, i, scene), at(v, j, scene), i, j, ci, cj);
     else if (tj == GEOM_CYLINDER && ti == GEOM_PLANE)    cylinder_plane(o, v.quat, v.geomA, v.geomB, at(v, j, scene), at(v, i, scene), j, i, cj, ci);
 }

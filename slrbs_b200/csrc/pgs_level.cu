@@ -56,6 +56,72 @@ __global__ void __launch_bounds__(128) k_joint_levels(View v)
 }
 
 // ------------------------------------------------------------------------------------
+// contact levels: one warp per scene. Lane 0 walks the contact list in order (the level of a contact
+// depends on the levels of all earlier contacts of its bodies, a strictly sequential chain kept short by
+// doing it out of shared-memory tables); the lanes stage the ids in chunks of 32 and do the counting sort.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_contact_levels(View v)
+{
+    extern __shared__ int lsm[];
+    const int lane = threadIdx.x, scene = blockIdx.x;
+    int* last = lsm;                       // [NB] last level that touched a body; -1 marks a fixed body
+    int* hist = last + v.NB;               // [NC + 2]
+    int2* idbuf = reinterpret_cast<int2*>(lsm + (((size_t)v.NB + v.NC + 2 + 1) & ~(size_t)1));   // [32], 8-byte aligned
+    int* outbuf = reinterpret_cast<int*>(idbuf + 32);         // [32]
+    const int nb = v.nbodies[scene], nc = v.ncontacts[scene];
+    for (int b = lane; b < nb; b += 32) last[b] = (v.flags[at(v, b, scene)] & FLAG_FIXED) ? -1 : 0;
+    for (int l = lane; l <= nc + 1; l += 32) hist[l] = 0;
+    __syncwarp();
+    int nlev = 0;
+    for (int c0 = 0; c0 < nc; c0 += 32) {
+        if (c0 + lane < nc) idbuf[lane] = v.cids[at(v, c0 + lane, scene)];
+        __syncwarp();
+        if (lane == 0) {
+            const int m = min(32, nc - c0);
+            for (int k = 0; k < m; ++k) {
+                const int2 ids = idbuf[k];
+                const int l0 = last[ids.x], l1 = last[ids.y];
+                const int L = max(max(l0, l1), 0) + 1;          // fixed bodies (-1) do not order anything
+                if (l0 >= 0) last[ids.x] = L;
+                if (l1 >= 0) last[ids.y] = L;
+                const int rank = hist[L];
+                hist[L] = rank + 1;
+                outbuf[k] = (L << 16) | rank;
+                nlev = max(nlev, L);
+            }
+        }
+        __syncwarp();
+        if (c0 + lane < nc) v.cpos[at(v, c0 + lane, scene)] = outbuf[lane];
+        __syncwarp();
+    }
+    nlev = __shfl_sync(0xffffffffu, nlev, 0);
+    // exclusive prefix of the per-level counts -> level starts (in place), level ends to global
+    int carry = 0;
+    for (int l0 = 1; l0 <= nlev; l0 += 32) {
+        const int l = l0 + lane;
+        const int c = l <= nlev ? hist[l] : 0;
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (l <= nlev) {
+            hist[l] = carry + incl - c;
+            v.clev_end[at(v, l, scene)] = carry + incl;
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    for (int c = lane; c < nc; c += 32) {
+        const size_t ci = at(v, c, scene);
+        const int packed = v.cpos[ci];
+        v.cpos[ci] = hist[packed >> 16] + (packed & 0xffff);
+    }
+    if (lane == 0) v.nclev[scene] = nlev;
+}
+
+// ------------------------------------------------------------------------------------
 // solve
 // ------------------------------------------------------------------------------------
 enum { LV_THREADS = 128 };
@@ -218,6 +284,13 @@ __global__ void __launch_bounds__(LV_THREADS, MINB) k_pgs_lv(View v, float dt, i
 // ------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------
+size_t contact_levels_smem(int NB, int NC) { return ((((size_t)NB + NC + 2 + 1) & ~(size_t)1)) * 4 + 32 * 8 + 32 * 4; }
+
+void launch_contact_levels(const View& v, cudaStream_t s)
+{
+    k_contact_levels<<<(unsigned)v.B, 32, contact_levels_smem(v.NB, v.NC), s>>>(v);
+}
+
 void launch_joint_levels(const View& v, cudaStream_t s)
 {
     k_joint_levels<<<(unsigned)((v.B + 127) / 128), 128, 0, s>>>(v);
@@ -240,7 +313,11 @@ static void init_lv()
     cudaFuncSetAttribute(k_pgs_lv<G, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 // per-device kernel attributes (called from slrbs_create with the device current)
-void init_level_kernels() { init_lv<4>(); init_lv<8>(); init_lv<16>(); init_lv<32>(); }
+void init_level_kernels()
+{
+    init_lv<4>(); init_lv<8>(); init_lv<16>(); init_lv<32>();
+    cudaFuncSetAttribute(k_contact_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
 
 int level_group_size(const View& v, int requested)
 {
