@@ -17,6 +17,7 @@
 namespace slrbs {
 
 enum { CAND_CAP = 128 };          // candidate partners of one row in the grid path; longer rows fall back to all j > i
+enum { HIT_CAP = 32, HIT_WORDS = 24 };   // contacts pairs of one grid row buffered for ordering; more -> all j > i walk
 
 struct DetectSmem {               // per-warp shared-memory arrays
     float4* sp;                   // [NB] proxies x y z | sphere radius
@@ -24,14 +25,15 @@ struct DetectSmem {               // per-warp shared-memory arrays
     int* cell_start;              // [H+1] grid: bucket offsets (after the fill: bucket ends)
     int* cell_items;              // [NB] grid: sphere indices grouped by bucket
     int* special;                 // [NB] grid: non-sphere body indices, ascending
-    int* cand;                    // [CAND_CAP] grid: candidate partners of the current row
-    int* sorted;                  // [CAND_CAP]
+    int* cand;                    // [CAND_CAP] grid: candidate partners of the current row (unordered)
+    int* order;                   // [HIT_CAP] grid: hit slots in ascending-j order
+    int* hits;                    // [HIT_CAP][HIT_WORDS] grid: j, b0, b1, cnt, n, p[4], phi[4] of the pairs that touch
 };
 
 __host__ __device__ inline size_t detect_smem_ints(int NB, bool grid, int H)
 {
     size_t n = (size_t)NB;                                     // sf
-    if (grid) n += (size_t)H + 1 + NB + NB + 2 * CAND_CAP;
+    if (grid) n += (size_t)H + 1 + NB + NB + CAND_CAP + HIT_CAP + HIT_CAP * HIT_WORDS;
     return n;
 }
 
@@ -70,9 +72,9 @@ __device__ __forceinline__ void emit_chunk(const View& v, const DetectSmem& sm, 
     count += total;
 }
 
-// Partners j > i of sphere i from the grid: the spheres of the 27 neighbouring cells (each distinct bucket
-// once) plus every non-sphere body, ascending in sm.sorted. Returns their number, or -1 when the row has more
-// than CAND_CAP candidates (the caller then walks all j > i). Warp-collective.
+// Partners of sphere i from the grid: the spheres of the 27 neighbouring cells (each distinct bucket once) plus
+// every non-sphere body, unordered in sm.cand; entries with j <= i are marked dead (-1). Returns their number,
+// or -1 when the row has more than CAND_CAP candidates (the caller then walks all j > i). Warp-collective.
 __device__ __forceinline__ int gather_candidates(const DetectSmem& sm, int lane, int i, const float4& ci, float inv_h, int H,
                                                  int nsph, int nspecial)
 {
@@ -97,28 +99,80 @@ __device__ __forceinline__ int gather_candidates(const DetectSmem& sm, int lane,
     const int off = incl - cnt;
     for (int k = 0; k < cnt; ++k) {
         const int j = sm.cell_items[beg + k];
-        sm.cand[off + k] = j > i ? j : 0x7fffffff;
+        sm.cand[off + k] = j > i ? j : -1;
     }
     for (int k = lane; k < nspecial; k += 32) {
         const int j = sm.special[k];
-        sm.cand[total + k] = j > i ? j : 0x7fffffff;
+        sm.cand[total + k] = j > i ? j : -1;
     }
-    const int nc_all = total + nspecial;
     __syncwarp();
-    // rank sort (all live candidates are distinct body indices); dead entries are dropped
-    int nlive = 0;
-    for (int k0 = 0; k0 < nc_all; k0 += 32) {
+    return total + nspecial;
+}
+
+// One grid row: tests the unordered candidates, buffers the pairs that touch, orders them by j and (when WRITE)
+// appends their contacts at `base`. Returns the row's contact count, or -1 if more than HIT_CAP pairs touch
+// (the caller then redoes the row with the ordered all-pairs walk). Warp-collective.
+template <bool WRITE>
+__device__ __forceinline__ int grid_row(const View& v, const DetectSmem& sm, int scene, int lane, int i, const float4& ci, int fi,
+                                        int ncand, int base)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    int nh = 0, ncontacts = 0;
+    for (int k0 = 0; k0 < ncand; k0 += 32) {
         const int k = k0 + lane;
-        const int mine = k < nc_all ? sm.cand[k] : 0x7fffffff;
-        if (mine != 0x7fffffff) {
-            int rank = 0;
-            for (int m = 0; m < nc_all; ++m) rank += sm.cand[m] < mine;
-            sm.sorted[rank] = mine;
+        const int j = k < ncand ? sm.cand[k] : -1;
+        PairOut o;
+        o.cnt = 0;
+        if (j >= 0) test_pair(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
+        const unsigned any = __ballot_sync(0xffffffffu, o.cnt > 0);
+        if (any == 0) continue;
+        const int slot = nh + __popc(any & lt);
+        if (WRITE && o.cnt > 0 && slot < HIT_CAP) {
+            int* hrec = sm.hits + slot * HIT_WORDS;
+            float* f = reinterpret_cast<float*>(hrec);
+            hrec[0] = j; hrec[1] = o.b0; hrec[2] = o.b1; hrec[3] = o.cnt;
+            f[4] = o.n.x; f[5] = o.n.y; f[6] = o.n.z;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < o.cnt) { f[7 + 3 * q] = o.p[q].x; f[8 + 3 * q] = o.p[q].y; f[9 + 3 * q] = o.p[q].z; f[19 + q] = o.phi[q]; }
+            }
         }
-        nlive += __popc(__ballot_sync(0xffffffffu, mine != 0x7fffffff));
+        int c = o.cnt;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        ncontacts += c;
+        nh += __popc(any);
+    }
+    if (nh > HIT_CAP) return -1;
+    if (!WRITE || nh == 0) return ncontacts;
+    __syncwarp();
+    // order the touching pairs by partner index (distinct), then append in that order
+    if (lane < nh) {
+        const int myj = sm.hits[lane * HIT_WORDS];
+        int rank = 0;
+        for (int m = 0; m < nh; ++m) rank += sm.hits[m * HIT_WORDS] < myj;
+        sm.order[rank] = lane;
     }
     __syncwarp();
-    return nlive;
+    PairOut o;
+    o.cnt = 0;
+    if (lane < nh) {
+        const int* hrec = sm.hits + sm.order[lane] * HIT_WORDS;
+        const float* f = reinterpret_cast<const float*>(hrec);
+        o.b0 = hrec[1]; o.b1 = hrec[2]; o.cnt = hrec[3];
+        o.n = mk3(f[4], f[5], f[6]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { o.p[q] = mk3(f[7 + 3 * q], f[8 + 3 * q], f[9 + 3 * q]); o.phi[q] = f[19 + q]; }
+    }
+    int incl = o.cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    write_contacts(v, scene, base + incl - o.cnt, o);
+    __syncwarp();
+    return ncontacts;
 }
 
 template <bool GRID>
@@ -133,7 +187,7 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta, 
     int* ip = reinterpret_cast<int*>(smem4 + (size_t)warps_per_cta * v.NB) + (size_t)warp * detect_smem_ints(v.NB, GRID, H);
     sm.sf = ip; ip += v.NB;
     sm.cell_start = ip; sm.cell_items = ip + H + 1; sm.special = sm.cell_items + v.NB;
-    sm.cand = sm.special + v.NB; sm.sorted = sm.cand + CAND_CAP;
+    sm.cand = sm.special + v.NB; sm.order = sm.cand + CAND_CAP; sm.hits = sm.order + HIT_CAP;
 
     const int n = v.nbodies[scene];
     float rmax = 0.f;
@@ -211,14 +265,10 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta, 
         const int fi = sm.sf[i];
         bool dense_row = true;
         if (GRID && (fi & FLAG_TYPE_MASK) == GEOM_SPHERE) {
-            const int nlive = gather_candidates(sm, lane, i, ci, inv_h, H, nsph, nspecial);
-            if (nlive >= 0) {
-                dense_row = false;
-                for (int k0 = 0; k0 < nlive; k0 += 32) {
-                    const int k = k0 + lane;
-                    emit_chunk(v, sm, scene, lane, i, ci, fi, k < nlive ? sm.sorted[k] : -1, count);
-                }
-                __syncwarp();
+            const int ncand = gather_candidates(sm, lane, i, ci, inv_h, H, nsph, nspecial);
+            if (ncand >= 0) {
+                const int c = grid_row<true>(v, sm, scene, lane, i, ci, fi, ncand, count);
+                if (c >= 0) { dense_row = false; count += c; }
             }
         }
         if (dense_row) {
@@ -242,7 +292,7 @@ enum { DETECT_CTA_THREADS = 512 };
 __host__ __device__ inline size_t detect_cta_smem_ints(int NB, bool grid, int H, int warps)
 {
     size_t n = (size_t)NB + NB + 2;                            // sf, rowcnt
-    if (grid) n += (size_t)H + 1 + NB + NB + 2 * CAND_CAP * (size_t)warps;
+    if (grid) n += (size_t)H + 1 + NB + NB + (size_t)(CAND_CAP + HIT_CAP + HIT_CAP * HIT_WORDS) * warps;
     return n;
 }
 
@@ -271,11 +321,10 @@ __device__ __forceinline__ int detect_row(const View& v, const DetectSmem& sm, i
     };
     bool dense_row = true;
     if (GRID && (fi & FLAG_TYPE_MASK) == GEOM_SPHERE) {
-        const int nlive = gather_candidates(sm, lane, i, ci, inv_h, H, nsph, nspecial);
-        if (nlive >= 0) {
-            dense_row = false;
-            for (int k0 = 0; k0 < nlive; k0 += 32) { const int k = k0 + lane; chunk(k < nlive ? sm.sorted[k] : -1); }
-            __syncwarp();
+        const int ncand = gather_candidates(sm, lane, i, ci, inv_h, H, nsph, nspecial);
+        if (ncand >= 0) {
+            const int c = grid_row<WRITE>(v, sm, scene, lane, i, ci, fi, ncand, base);
+            if (c >= 0) return c;
         }
     }
     if (dense_row)
@@ -296,7 +345,8 @@ __global__ void __launch_bounds__(DETECT_CTA_THREADS) k_detect_cta(View v, int H
     sm.sf = ip; ip += v.NB;
     int* rowcnt = ip; ip += v.NB + 2;
     sm.cell_start = ip; sm.cell_items = ip + H + 1; sm.special = sm.cell_items + v.NB;
-    sm.cand = sm.special + v.NB + (size_t)warp * 2 * CAND_CAP; sm.sorted = sm.cand + CAND_CAP;
+    sm.cand = sm.special + v.NB + (size_t)warp * (CAND_CAP + HIT_CAP + HIT_CAP * HIT_WORDS);
+    sm.order = sm.cand + CAND_CAP; sm.hits = sm.order + HIT_CAP;
 
     const int n = v.nbodies[scene];
     if (tid == 0) { s_rmax = 0; s_nspecial = 0; s_total = 0; }

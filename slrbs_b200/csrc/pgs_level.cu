@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
 // ------------------------------------------------------------------------------------
 // solve
 // ------------------------------------------------------------------------------------
-enum { LV_THREADS = 128 };
+enum { LV_THREADS = 32 };       // one warp per CTA: 32 / G scenes; small CTAs pack shared memory tightly (a
+                                // 1000-body scene needs 32 KB of accumulators: 7 scenes per SM instead of 4)
 
 struct BodyW { float4* w; };     // shared-memory accumulators of one scene: [body][2] (linear, angular)
 __device__ __forceinline__ void ld_w(const float4* w, int body, V3& l, V3& a) { l = mk3(w[2 * body]); a = mk3(w[2 * body + 1]); }
@@ -136,8 +137,8 @@ __device__ __forceinline__ void group_sync(unsigned mask)
     if (G >= 32) __syncwarp(); else __syncwarp(mask);
 }
 
-// MINB = CTAs per SM the register allocation must allow: 4 (128 registers, a few spills) wins when the batch can
-// fill 16 warps per SM, 3 (162 registers, no spills) when it cannot and single-warp latency is what matters.
+// MINB = warps per SM the register allocation must allow: 16 (128 registers, a few spills) wins when the batch
+// can fill 16 warps per SM, 12 (162 registers, no spills) when it cannot and single-warp latency is what matters.
 template <int G, int MINB>
 __global__ void __launch_bounds__(LV_THREADS, MINB) k_pgs_lv(View v, float dt, int iters, float mu)
 {
@@ -302,15 +303,15 @@ static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t
     const int spc = LV_THREADS / G;
     const size_t smem = (size_t)spc * v.NB * 2 * sizeof(float4);
     const unsigned blocks = (unsigned)((v.B + spc - 1) / spc);
-    if (blocks >= 148u * 2u) k_pgs_lv<G, 4><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
-    else k_pgs_lv<G, 3><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
+    if (blocks >= 148u * 8u) k_pgs_lv<G, 16><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
+    else k_pgs_lv<G, 12><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
 }
 
 template <int G>
 static void init_lv()
 {
-    cudaFuncSetAttribute(k_pgs_lv<G, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_pgs_lv<G, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_lv<G, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_lv<G, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 // per-device kernel attributes (called from slrbs_create with the device current)
 void init_level_kernels()
