@@ -109,15 +109,15 @@ __device__ __forceinline__ int gather_candidates(const DetectSmem& sm, int lane,
     return total + nspecial;
 }
 
-// One grid row: tests the unordered candidates, buffers the pairs that touch, orders them by j and (when WRITE)
-// appends their contacts at `base`. Returns the row's contact count, or -1 if more than HIT_CAP pairs touch
-// (the caller then redoes the row with the ordered all-pairs walk). Warp-collective.
-template <bool WRITE>
-__device__ __forceinline__ int grid_row(const View& v, const DetectSmem& sm, int scene, int lane, int i, const float4& ci, int fi,
-                                        int ncand, int base)
+// One grid row, step 1: tests the unordered candidates and buffers the pairs that touch in sm.hits. Returns the
+// row's contact count (nh = number of buffered pairs), or -1 if more than HIT_CAP pairs touch (the caller then
+// redoes the row with the ordered all-pairs walk). Warp-collective.
+__device__ __forceinline__ int grid_collect(const View& v, const DetectSmem& sm, int scene, int lane, int i, const float4& ci, int fi,
+                                            int ncand, int& nh)
 {
     const unsigned lt = (1u << lane) - 1u;
-    int nh = 0, ncontacts = 0;
+    int ncontacts = 0;
+    nh = 0;
     for (int k0 = 0; k0 < ncand; k0 += 32) {
         const int k = k0 + lane;
         const int j = k < ncand ? sm.cand[k] : -1;
@@ -127,7 +127,7 @@ __device__ __forceinline__ int grid_row(const View& v, const DetectSmem& sm, int
         const unsigned any = __ballot_sync(0xffffffffu, o.cnt > 0);
         if (any == 0) continue;
         const int slot = nh + __popc(any & lt);
-        if (WRITE && o.cnt > 0 && slot < HIT_CAP) {
+        if (o.cnt > 0 && slot < HIT_CAP) {
             int* hrec = sm.hits + slot * HIT_WORDS;
             float* f = reinterpret_cast<float*>(hrec);
             hrec[0] = j; hrec[1] = o.b0; hrec[2] = o.b1; hrec[3] = o.cnt;
@@ -143,10 +143,14 @@ __device__ __forceinline__ int grid_row(const View& v, const DetectSmem& sm, int
         ncontacts += c;
         nh += __popc(any);
     }
-    if (nh > HIT_CAP) return -1;
-    if (!WRITE || nh == 0) return ncontacts;
     __syncwarp();
-    // order the touching pairs by partner index (distinct), then append in that order
+    return nh > HIT_CAP ? -1 : ncontacts;
+}
+
+// One grid row, step 2: orders the buffered pairs by partner index (distinct) and appends their contacts at `base`.
+__device__ __forceinline__ void grid_flush(const View& v, const DetectSmem& sm, int scene, int lane, int nh, int base)
+{
+    if (nh == 0) return;
     if (lane < nh) {
         const int myj = sm.hits[lane * HIT_WORDS];
         int rank = 0;
@@ -172,7 +176,6 @@ __device__ __forceinline__ int grid_row(const View& v, const DetectSmem& sm, int
     }
     write_contacts(v, scene, base + incl - o.cnt, o);
     __syncwarp();
-    return ncontacts;
 }
 
 template <bool GRID>
@@ -267,8 +270,9 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta, 
         if (GRID && (fi & FLAG_TYPE_MASK) == GEOM_SPHERE) {
             const int ncand = gather_candidates(sm, lane, i, ci, inv_h, H, nsph, nspecial);
             if (ncand >= 0) {
-                const int c = grid_row<true>(v, sm, scene, lane, i, ci, fi, ncand, count);
-                if (c >= 0) { dense_row = false; count += c; }
+                int nh;
+                const int c = grid_collect(v, sm, scene, lane, i, ci, fi, ncand, nh);
+                if (c >= 0) { dense_row = false; grid_flush(v, sm, scene, lane, nh, count); count += c; }
             }
         }
         if (dense_row) {
@@ -283,9 +287,8 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta, 
 
 // ------------------------------------------------------------------------------------
 // k_detect_cta<GRID>  one CTA per scene, for scenes of hundreds or thousands of bodies. Rows i are dealt
-// round-robin to the warps; since the contact list must stay in (i, j) order the rows are walked twice:
-// pass 1 counts the contacts of every row, a scan turns the counts into row offsets, pass 2 repeats the
-// tests and writes each row's contacts at its offset.
+// to the warps in rounds of consecutive rows and tested in parallel; a block barrier per round turns the
+// rows' contact counts into output offsets, so the list stays in (i, j) order with a single pass over the pairs.
 // ------------------------------------------------------------------------------------
 enum { DETECT_CTA_THREADS = 512 };
 
@@ -296,20 +299,20 @@ __host__ __device__ inline size_t detect_cta_smem_ints(int NB, bool grid, int H,
     return n;
 }
 
-// contacts of row i (pairs (i, j), j > i ascending); counts them, and writes them at `base` when WRITE
-template <bool GRID, bool WRITE>
-__device__ __forceinline__ int detect_row(const View& v, const DetectSmem& sm, int scene, int lane, int i, int n, float inv_h, int H,
-                                          int nsph, int nspecial, int base)
+// all-pairs walk of row i (pairs (i, j), j > i ascending): counts the contacts, and writes them at `base` when WRITE
+template <bool WRITE>
+__device__ __forceinline__ int dense_row(const View& v, const DetectSmem& sm, int scene, int lane, int i, int n, int base)
 {
     const float4 ci = sm.sp[i];
     const int fi = sm.sf[i];
     int off = 0;
-    auto chunk = [&](int j) {
+    for (int j0 = i + 1; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
         PairOut o;
         o.cnt = 0;
-        if (j >= 0) test_pair(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
+        if (j < n) test_pair(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
         const unsigned any = __ballot_sync(0xffffffffu, o.cnt > 0);
-        if (any == 0) return;
+        if (any == 0) continue;
         int incl = o.cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -318,22 +321,12 @@ __device__ __forceinline__ int detect_row(const View& v, const DetectSmem& sm, i
         }
         if (WRITE) write_contacts(v, scene, base + off + incl - o.cnt, o);
         off += __shfl_sync(0xffffffffu, incl, 31);
-    };
-    bool dense_row = true;
-    if (GRID && (fi & FLAG_TYPE_MASK) == GEOM_SPHERE) {
-        const int ncand = gather_candidates(sm, lane, i, ci, inv_h, H, nsph, nspecial);
-        if (ncand >= 0) {
-            const int c = grid_row<WRITE>(v, sm, scene, lane, i, ci, fi, ncand, base);
-            if (c >= 0) return c;
-        }
     }
-    if (dense_row)
-        for (int j0 = i + 1; j0 < n; j0 += 32) { const int j = j0 + lane; chunk(j < n ? j : -1); }
     return off;
 }
 
 template <bool GRID>
-__global__ void __launch_bounds__(DETECT_CTA_THREADS) k_detect_cta(View v, int H)
+__global__ void __launch_bounds__(DETECT_CTA_THREADS, 2) k_detect_cta(View v, int H)
 {
     extern __shared__ float4 smem4[];
     __shared__ int s_rmax, s_nspecial, s_total;
@@ -413,31 +406,44 @@ __global__ void __launch_bounds__(DETECT_CTA_THREADS) k_detect_cta(View v, int H
         __syncthreads();
         nspecial = s_nspecial; nsph = n - nspecial;
     }
-    // pass 1: contacts per row
-    for (int i = warp; i < n; i += W) {
-        const int c = detect_row<GRID, false>(v, sm, scene, lane, i, n, inv_h, H, nsph, nspecial, 0);
-        if (lane == 0) rowcnt[i] = c;
-    }
-    __syncthreads();
-    if (warp == 0) {                                             // exclusive scan -> row offsets
-        int carry = 0;
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            const int c = i < n ? rowcnt[i] : 0;
-            int incl = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
+    // Rounds of W consecutive rows, one per warp: every warp tests its row and buffers the pairs that touch, a block
+    // barrier publishes the W counts, each warp derives its output offset and appends. The contact list comes out in
+    // (i, j) order from a single pass over the pairs (rows whose hits do not fit the buffer count first and re-test
+    // when they write).
+    __shared__ int s_cnt[DETECT_CTA_THREADS / 32];
+    int running = 0;
+    for (int i0 = 0; i0 < n; i0 += W) {
+        const int i = i0 + warp;
+        int count = 0, nh = 0;
+        bool buffered = true;
+        if (i < n) {
+            const float4 ci = sm.sp[i];
+            const int fi = sm.sf[i];
+            count = -1;
+            if (GRID && (fi & FLAG_TYPE_MASK) == GEOM_SPHERE) {
+                const int ncand = gather_candidates(sm, lane, i, ci, inv_h, H, nsph, nspecial);
+                if (ncand >= 0) count = grid_collect(v, sm, scene, lane, i, ci, fi, ncand, nh);
             }
-            if (i < n) rowcnt[i] = carry + incl - c;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
+            buffered = count >= 0;
+            if (!buffered) count = dense_row<false>(v, sm, scene, lane, i, n, 0);
         }
-        if (lane == 0) s_total = carry;
+        if (lane == 0) s_cnt[warp] = count;
+        __syncthreads();
+        int base = running, tot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < DETECT_CTA_THREADS / 32; ++w2) {
+            const int c = s_cnt[w2];
+            if (w2 < warp) base += c;
+            tot += c;
+        }
+        if (i < n) {
+            if (buffered) grid_flush(v, sm, scene, lane, nh, base);
+            else dense_row<true>(v, sm, scene, lane, i, n, base);
+        }
+        running += tot;
+        __syncthreads();
     }
-    __syncthreads();
-    // pass 2: write every row at its offset (write_contacts drops what does not fit and raises the flag)
-    for (int i = warp; i < n; i += W) detect_row<GRID, true>(v, sm, scene, lane, i, n, inv_h, H, nsph, nspecial, rowcnt[i]);
+    if (tid == 0) s_total = running;
     __syncthreads();
     if (tid == 0) v.ncontacts[scene] = s_total < v.NC ? s_total : v.NC;
 }
