@@ -23,7 +23,8 @@ SYMBOLS = [
     "slrbs_download_contacts", "slrbs_download_contact_rows", "slrbs_download_joint_rows",
     "slrbs_download_joint_lambda", "slrbs_upload_joint_lambda", "slrbs_download_body_dyn",
     "slrbs_save_state", "slrbs_restore_state", "slrbs_profile_enable", "slrbs_profile_read",
-    "slrbs_timer_start", "slrbs_timer_stop",
+    "slrbs_timer_start", "slrbs_timer_stop", "slrbs_halo_set_local", "slrbs_halo_set_remote", "slrbs_halo_sync_local",
+    "slrbs_halo_pack", "slrbs_halo_unpack",
 ]
 
 
@@ -75,6 +76,11 @@ def load_library():
     L.slrbs_save_state.argtypes = [vp]
     L.slrbs_restore_state.argtypes = [vp, C.c_int, C.c_int]
     L.slrbs_profile_enable.argtypes = [vp, C.c_int]
+    L.slrbs_halo_set_local.argtypes = [vp, C.c_int, ip, ip]
+    L.slrbs_halo_set_remote.argtypes = [vp, C.c_int, ip, C.c_int, ip]
+    L.slrbs_halo_sync_local.argtypes = [vp]
+    L.slrbs_halo_pack.argtypes = [vp, C.c_void_p]
+    L.slrbs_halo_unpack.argtypes = [vp, C.c_void_p]
     L.slrbs_timer_start.argtypes = [vp]
     L.slrbs_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.slrbs_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double),
@@ -277,6 +283,19 @@ class Context:
         self._ck(self.L.slrbs_download_body_dyn(self.h, scene, n, _f(o["f"]), _f(o["tau"]), _f(o["fc"]), _f(o["tauc"]),
                                                 _f(o["I"]), _f(o["Iinv"])))
         return o
+
+    # -- halos of a scene cut into blocks -------------------------------------------
+    def halo_set_local(self, src_flat, dst_flat):
+        a = np.ascontiguousarray(np.asarray(src_flat, np.int32)); b = np.ascontiguousarray(np.asarray(dst_flat, np.int32))
+        self._ck(self.L.slrbs_halo_set_local(self.h, a.size, _i(a), _i(b)))
+
+    def halo_set_remote(self, send_flat, recv_flat):
+        a = np.ascontiguousarray(np.asarray(send_flat, np.int32)); b = np.ascontiguousarray(np.asarray(recv_flat, np.int32))
+        self._ck(self.L.slrbs_halo_set_remote(self.h, a.size, _i(a), b.size, _i(b)))
+
+    def halo_sync_local(self): self._ck(self.L.slrbs_halo_sync_local(self.h))
+    def halo_pack(self, device_ptr): self._ck(self.L.slrbs_halo_pack(self.h, C.c_void_p(device_ptr)))
+    def halo_unpack(self, device_ptr): self._ck(self.L.slrbs_halo_unpack(self.h, C.c_void_p(device_ptr)))
 
     # -- measurement ---------------------------------------------------------------
     def profile_enable(self, on=True):

@@ -48,6 +48,9 @@ struct slrbs_ctx {
     cudaGraphExec_t graph = nullptr;
     struct { float dt, mu; int iters, solver, collisions, has_ext, launches; } gsig = { 0.f, 0.f, 0, 0, 0, 0, 0 };
     int use_graph = 1;
+    // halo maps (device copies of the index lists)
+    int *halo_src = nullptr, *halo_dst = nullptr, *halo_send = nullptr, *halo_recv = nullptr;
+    int n_halo_local = 0, n_halo_send = 0, n_halo_recv = 0;
 };
 
 namespace {
@@ -225,6 +228,7 @@ void slrbs_destroy(slrbs_ctx* c)
     if (c->stage) cudaFree(c->stage);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->graph) cudaGraphExecDestroy(c->graph);
+    cudaFree(c->halo_src); cudaFree(c->halo_dst); cudaFree(c->halo_send); cudaFree(c->halo_recv);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
@@ -583,6 +587,67 @@ int slrbs_restore_state(slrbs_ctx* c, int scene0, int ns)
     if (!range_ok(c, scene0, ns)) return fail(SLRBS_E_ARG, "slrbs_restore_state: bad range");
     CU(cudaSetDevice(c->device));
     launch_snapshot(c->v, scene0, ns, 1, c->stream);
+    return check_launch(c);
+}
+
+static int set_index_list(slrbs_ctx* c, int** dev, int* count, int n, const int32_t* host, const char* what)
+{
+    const int64_t limit = (int64_t)c->v.B * c->v.NB;
+    for (int i = 0; i < n; ++i)
+        if (host[i] < 0 || host[i] >= limit) return fail(SLRBS_E_ARG, std::string(what) + ": flat body index out of range");
+    CU(cudaStreamSynchronize(c->stream));
+    if (*dev) { CU(cudaFree(*dev)); *dev = nullptr; }
+    *count = 0;
+    if (n > 0) {
+        CU(cudaMalloc((void**)dev, sizeof(int) * (size_t)n));
+        CU(cudaMemcpy(*dev, host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+        *count = n;
+    }
+    return 0;
+}
+
+int slrbs_halo_set_local(slrbs_ctx* c, int n, const int32_t* src_flat, const int32_t* dst_flat)
+{
+    if (!c || n < 0 || (n > 0 && (!src_flat || !dst_flat))) return fail(SLRBS_E_ARG, "slrbs_halo_set_local: bad argument");
+    CU(cudaSetDevice(c->device));
+    int r, cnt = 0;
+    if ((r = set_index_list(c, &c->halo_src, &cnt, n, src_flat, "slrbs_halo_set_local"))) return r;
+    if ((r = set_index_list(c, &c->halo_dst, &c->n_halo_local, n, dst_flat, "slrbs_halo_set_local"))) return r;
+    return 0;
+}
+
+int slrbs_halo_set_remote(slrbs_ctx* c, int n_send, const int32_t* send_flat, int n_recv, const int32_t* recv_flat)
+{
+    if (!c || n_send < 0 || n_recv < 0 || (n_send > 0 && !send_flat) || (n_recv > 0 && !recv_flat))
+        return fail(SLRBS_E_ARG, "slrbs_halo_set_remote: bad argument");
+    CU(cudaSetDevice(c->device));
+    int r;
+    if ((r = set_index_list(c, &c->halo_send, &c->n_halo_send, n_send, send_flat, "slrbs_halo_set_remote"))) return r;
+    if ((r = set_index_list(c, &c->halo_recv, &c->n_halo_recv, n_recv, recv_flat, "slrbs_halo_set_remote"))) return r;
+    return 0;
+}
+
+int slrbs_halo_sync_local(slrbs_ctx* c)
+{
+    if (!c) return fail(SLRBS_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    launch_halo_copy(c->v, c->n_halo_local, c->halo_src, c->halo_dst, c->stream);
+    return check_launch(c);
+}
+
+int slrbs_halo_pack(slrbs_ctx* c, void* device_buffer)
+{
+    if (!c || (c->n_halo_send > 0 && !device_buffer)) return fail(SLRBS_E_ARG, "slrbs_halo_pack: bad argument");
+    CU(cudaSetDevice(c->device));
+    launch_halo_pack(c->v, c->n_halo_send, c->halo_send, (float*)device_buffer, c->stream);
+    return check_launch(c);
+}
+
+int slrbs_halo_unpack(slrbs_ctx* c, const void* device_buffer)
+{
+    if (!c || (c->n_halo_recv > 0 && !device_buffer)) return fail(SLRBS_E_ARG, "slrbs_halo_unpack: bad argument");
+    CU(cudaSetDevice(c->device));
+    launch_halo_unpack(c->v, c->n_halo_recv, c->halo_recv, (const float*)device_buffer, c->stream);
     return check_launch(c);
 }
 

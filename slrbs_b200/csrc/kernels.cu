@@ -991,6 +991,42 @@ __global__ void k_snapshot(View v, int scene0, int ns, int restore)
     }
 }
 
+// halo refresh for a scene cut into overlapping blocks: indexed state copies (flat index = scene * NB + slot)
+__device__ __forceinline__ size_t flat_to_at(const View& v, int flat) { return at(v, flat % v.NB, flat / v.NB); }
+
+__global__ void k_halo_copy(View v, int n, const int* __restrict__ src, const int* __restrict__ dst)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t a = flat_to_at(v, src[k]), b = flat_to_at(v, dst[k]);
+    const float4 p = v.pos[a], pd = v.pos[b];
+    v.pos[b] = make_float4(p.x, p.y, p.z, pd.w);                 // keep the copy's own mass field
+    v.quat[b] = v.quat[a]; v.vel[b] = v.vel[a]; v.omg[b] = v.omg[a];
+}
+
+__global__ void k_halo_pack(View v, int n, const int* __restrict__ idx, float* __restrict__ buf)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t a = flat_to_at(v, idx[k]);
+    const float4 p = v.pos[a], q = v.quat[a], l = v.vel[a], w = v.omg[a];
+    float* o = buf + (size_t)13 * k;
+    o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = q.x; o[4] = q.y; o[5] = q.z; o[6] = q.w;
+    o[7] = l.x; o[8] = l.y; o[9] = l.z; o[10] = w.x; o[11] = w.y; o[12] = w.z;
+}
+
+__global__ void k_halo_unpack(View v, int n, const int* __restrict__ idx, const float* __restrict__ buf)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t b = flat_to_at(v, idx[k]);
+    const float* o = buf + (size_t)13 * k;
+    v.pos[b] = make_float4(o[0], o[1], o[2], v.pos[b].w);
+    v.quat[b] = make_float4(o[3], o[4], o[5], o[6]);
+    v.vel[b] = make_float4(o[7], o[8], o[9], 0.f);
+    v.omg[b] = make_float4(o[10], o[11], o[12], 0.f);
+}
+
 // dense exports of one scene for parity tests / getContacts()
 __global__ void k_export_contacts(View v, int scene, int n, int* body0, int* body1, float* p3, float* n3,
                                   float* t3, float* b3, float* phi, float* lam3, float* J0, float* J1,
@@ -1111,6 +1147,12 @@ void launch_set_ext(const View& v, int scene0, int ns, int n, const float* f3, c
 { k_set_ext<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, f3, t3); }
 void launch_snapshot(const View& v, int scene0, int ns, int restore, cudaStream_t s)
 { k_snapshot<<<blocks_for((size_t)ns * v.NB, 256), 256, 0, s>>>(v, scene0, ns, restore); }
+void launch_halo_copy(const View& v, int n, const int* src, const int* dst, cudaStream_t s)
+{ if (n > 0) k_halo_copy<<<blocks_for(n, 256), 256, 0, s>>>(v, n, src, dst); }
+void launch_halo_pack(const View& v, int n, const int* idx, float* buf, cudaStream_t s)
+{ if (n > 0) k_halo_pack<<<blocks_for(n, 256), 256, 0, s>>>(v, n, idx, buf); }
+void launch_halo_unpack(const View& v, int n, const int* idx, const float* buf, cudaStream_t s)
+{ if (n > 0) k_halo_unpack<<<blocks_for(n, 256), 256, 0, s>>>(v, n, idx, buf); }
 void launch_export_contacts(const View& v, int scene, int n, int* body0, int* body1, float* p3, float* n3, float* t3,
                             float* b3, float* phi, float* lam3, float* J0, float* J1, float* M0, float* M1,
                             float* A9, float* rhs3, cudaStream_t s)

@@ -39,6 +39,9 @@ void launch_upload_joints(const View& v, int scene0, int ns, int n, const int* c
 void launch_joint_lambda(const View& v, int scene0, int ns, int n, float* lam5, int upload, cudaStream_t s);
 void launch_set_ext(const View& v, int scene0, int ns, int n, const float* f3, const float* t3, cudaStream_t s);
 void launch_snapshot(const View& v, int scene0, int ns, int restore, cudaStream_t s);
+void launch_halo_copy(const View& v, int n, const int* src, const int* dst, cudaStream_t s);
+void launch_halo_pack(const View& v, int n, const int* idx, float* buf, cudaStream_t s);
+void launch_halo_unpack(const View& v, int n, const int* idx, const float* buf, cudaStream_t s);
 void launch_export_contacts(const View& v, int scene, int n, int* body0, int* body1, float* p3, float* n3, float* t3,
                             float* b3, float* phi, float* lam3, float* J0, float* J1, float* M0, float* M1,
                             float* A9, float* rhs3, cudaStream_t s);

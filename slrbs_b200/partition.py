@@ -1,0 +1,286 @@
+"""One large sphere pile cut into overlapping blocks and spread over the GPUs of a box (SURVEY.md 8(e),
+BASELINE.json config 5). No reference counterpart: the reference is one process with an O(n^2) pair loop.
+
+Space is cut into cubic blocks. Every block is ONE SCENE of the batched pipeline and holds
+  * the bodies whose centre lies in the block ("owned"),
+  * copies of the bodies of the 26 neighbouring blocks that can reach an owned body before the next
+    re-partition ("halo": distance to the block <= 2 r_max + margin + 2 v_max K dt), simulated as ordinary
+    dynamic bodies so that contacts across a block face are solved on both sides,
+  * the fixed container bodies.
+Blocks are dealt to the ranks as contiguous slabs of block-x indices balanced by body count. After every
+step each halo copy is overwritten with its owner's new state: on the same GPU by an indexed device copy
+(slrbs_halo_sync_local), across GPUs by slrbs_halo_pack -> NCCL all_to_all_single over NVLink ->
+slrbs_halo_unpack. Every K steps the owners' state is all-reduced, the partition rebuilt (bodies migrate) and
+the scenes re-uploaded. Inside a block the solver keeps the reference's sequential row order (bodies sorted by
+global index); ACROSS blocks the coupling is block-Jacobi with one layer of overlap, so results are validated
+on penetration / residual against a single-scene run, not on trajectories (north_star).
+
+The partition itself (build_partition) is pure numpy and identical on every rank, so ranks need not
+exchange index lists: each derives its own send / receive lists from the same global picture.
+"""
+import numpy as np
+
+from .capi import Context, SPHERE
+
+STATE_W = 13      # x3 q4 v3 w3
+
+
+def build_partition(x, block, halo_w, world):
+    """Partition N points. Returns a dict with, for every rank, its scenes (arrays of global body ids, sorted,
+    and an owned mask) and, for every body, where it is owned (rank, scene, slot)."""
+    x = np.asarray(x, np.float64)
+    n = x.shape[0]
+    assert halo_w <= block, "halo wider than a block"
+    origin = x.min(axis=0) - 1e-3
+    cell = np.floor((x - origin) / block).astype(np.int64)
+    ncell = cell.max(axis=0) + 1
+    # slabs of block-x indices balanced by body count
+    per_x = np.bincount(cell[:, 0], minlength=ncell[0])
+    before = np.cumsum(per_x) - per_x
+    rank_of_cx = np.minimum(((2 * before + per_x) * world) // max(2 * int(per_x.sum()), 1), world - 1).astype(np.int64)
+    rank_of_cx = np.maximum.accumulate(rank_of_cx)
+    key = (cell[:, 0] * ncell[1] + cell[:, 1]) * ncell[2] + cell[:, 2]
+    ukeys = np.unique(key)                                         # existing blocks, lexicographic
+    block_rank = rank_of_cx[ukeys // (ncell[1] * ncell[2])]
+    # scene index of a block within its rank
+    scene_of_block = np.zeros(len(ukeys), np.int64)
+    for r in range(world):
+        m = block_rank == r
+        scene_of_block[m] = np.arange(m.sum())
+    bidx = np.searchsorted(ukeys, key)                             # block index of every body
+    # halo candidates: (body, neighbour block) pairs within halo_w of the neighbour's box
+    rel = x - origin - cell * block                                # position inside the own cell, in [0, block)
+    pairs_body, pairs_block = [np.arange(n)], [bidx]
+    owned_flag = [np.ones(n, bool)]
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                if dx == dy == dz == 0:
+                    continue
+                d = np.array([dx, dy, dz])
+                gap = np.where(d < 0, rel, np.where(d > 0, block - rel, 0.0))
+                near = np.sqrt((gap * gap).sum(axis=1)) <= halo_w
+                nc = cell[near] + d
+                ok = ((nc >= 0) & (nc < ncell)).all(axis=1)
+                ids = np.nonzero(near)[0][ok]
+                nk = (nc[ok, 0] * ncell[1] + nc[ok, 1]) * ncell[2] + nc[ok, 2]
+                pos = np.searchsorted(ukeys, nk)
+                pos = np.minimum(pos, len(ukeys) - 1)
+                exists = ukeys[pos] == nk
+                pairs_body.append(ids[exists]); pairs_block.append(pos[exists]); owned_flag.append(np.zeros(exists.sum(), bool))
+    pb, pk, po = np.concatenate(pairs_body), np.concatenate(pairs_block), np.concatenate(owned_flag)
+    order = np.lexsort((pb, pk))                                   # by block, then global body id
+    pb, pk, po = pb[order], pk[order], po[order]
+    starts = np.searchsorted(pk, np.arange(len(ukeys)))
+    ends = np.searchsorted(pk, np.arange(len(ukeys)), side="right")
+    slot = np.arange(len(pk)) - starts[pk]
+    owner_rank = block_rank[bidx]
+    owner_scene = scene_of_block[bidx]
+    owner_slot = np.zeros(n, np.int64)
+    owner_slot[pb[po]] = slot[po]
+    ranks = []
+    for r in range(world):
+        blocks = np.nonzero(block_rank == r)[0]
+        scenes = [dict(ids=pb[starts[b]:ends[b]], owned=po[starts[b]:ends[b]]) for b in blocks]
+        ranks.append(scenes)
+    return dict(ranks=ranks, owner_rank=owner_rank, owner_scene=owner_scene, owner_slot=owner_slot,
+                max_bodies=int((ends - starts).max()), n_blocks=len(ukeys))
+
+
+def halo_maps(part, rank, max_bodies):
+    """Index lists of one rank: local (src_flat, dst_flat) copies and, per peer, what to send / where to unpack.
+    Lists towards / from a peer are ordered by (receiving scene, receiving slot), which both sides can compute."""
+    world = len(part["ranks"])
+    loc_src, loc_dst = [], []
+    recv = {p: [] for p in range(world)}          # flat destinations on this rank, by source peer
+    for s, sc in enumerate(part["ranks"][rank]):
+        halo = np.nonzero(~sc["owned"])[0]
+        g = sc["ids"][halo]
+        orank, oscene, oslot = part["owner_rank"][g], part["owner_scene"][g], part["owner_slot"][g]
+        dst = s * max_bodies + halo
+        m = orank == rank
+        loc_src.append(oscene[m] * max_bodies + oslot[m]); loc_dst.append(dst[m])
+        for p in np.unique(orank[~m]):
+            recv[int(p)].append(dst[orank == p])
+    send = {p: [] for p in range(world)}          # flat sources on this rank, by destination peer
+    for p in range(world):
+        if p == rank:
+            continue
+        for s, sc in enumerate(part["ranks"][p]):
+            halo = np.nonzero(~sc["owned"])[0]
+            g = sc["ids"][halo]
+            m = part["owner_rank"][g] == rank
+            send[p].append(part["owner_scene"][g[m]] * max_bodies + part["owner_slot"][g[m]])
+    cat = lambda L: np.concatenate(L).astype(np.int32) if L else np.zeros(0, np.int32)
+    return dict(local_src=cat(loc_src), local_dst=cat(loc_dst),
+                send={p: cat(v) for p, v in send.items()}, recv={p: cat(v) for p, v in recv.items()})
+
+
+class PartitionedPile:
+    """Driver of one rank. `comm` is None (single process, world 1) or a torch.distributed-like object used through
+    all_reduce_sum(tensor) and all_to_all(out, inp, out_splits, in_splits) (see TorchComm)."""
+
+    def __init__(self, x, radius, mass, fixed_bodies, block=8.0, rebuild_every=10, vmax=6.0, dt=0.01, rank=0, world=1,
+                 device=0, comm=None, contact_factor=4, mu=0.8, iters=10):
+        self.n = x.shape[0]
+        self.radius = np.asarray(radius, np.float32); self.mass = np.asarray(mass, np.float32)
+        self.fixed = fixed_bodies                                 # list of dict(x, q, dim)
+        self.block, self.K, self.vmax, self.dt = float(block), int(rebuild_every), float(vmax), float(dt)
+        self.rank, self.world, self.device, self.comm = rank, world, device, comm
+        self.contact_factor, self.mu, self.iters = contact_factor, mu, iters
+        self.halo_w = 2.0 * float(self.radius.max()) + 2e-3 + 2.0 * self.vmax * self.K * self.dt
+        self.state = np.zeros((self.n, STATE_W), np.float32)
+        self.state[:, :3] = x
+        self.state[:, 6] = 1.0
+        self.ctx = None
+        self.steps_since_rebuild = 0
+        self.stats = dict(rebuilds=0, halo_bodies=0, owned_bodies=0, scenes=0, remote_halos=0)
+        self.rebuild()
+
+    # ---- partition + upload ------------------------------------------------------------------------------------
+    def rebuild(self):
+        part = build_partition(self.state[:, :3], self.block, min(self.halo_w, self.block), self.world)
+        if part["n_blocks"] > 1 and self.halo_w > self.block:
+            raise ValueError(f"halo width {self.halo_w:.2f} exceeds the block size {self.block}: rebuild more often or use larger blocks")
+        nf = len(self.fixed)
+        NBd = part["max_bodies"]
+        NB = NBd + nf
+        scenes = part["ranks"][self.rank]
+        B = max(len(scenes), 1)
+        if self.ctx is None or B != self.ctx.n_scenes or NB > self.ctx.max_bodies:
+            if self.ctx is not None:
+                self.ctx.close()
+            NBcap = int(NB * 1.15) + 8
+            self.ctx = Context(B, NBcap, 0, self.contact_factor * NBcap, device=self.device)
+            self.ctx.set_params(self.mu, 0, self.iters, True)
+        NBc = self.ctx.max_bodies
+        xs = np.zeros((B, NBc, 3), np.float32); q = np.zeros((B, NBc, 4), np.float32); q[..., 3] = 1
+        v = np.zeros((B, NBc, 3), np.float32); w = np.zeros((B, NBc, 3), np.float32)
+        mass = np.ones((B, NBc), np.float32); fixed = np.zeros((B, NBc), np.int32); gtype = np.zeros((B, NBc), np.int32)
+        geom = np.zeros((B, NBc, 6), np.float32); geom[..., 0] = 0.5
+        ib = np.zeros((B, NBc, 9), np.float32); ibi = np.zeros((B, NBc, 9), np.float32)
+        counts = np.zeros(B, np.int32)
+        self.scene_ids, self.scene_owned = [], []
+        for s, sc in enumerate(scenes):
+            g = sc["ids"]; k = len(g)
+            st = self.state[g]
+            xs[s, :k] = st[:, 0:3]; q[s, :k] = st[:, 3:7]; v[s, :k] = st[:, 7:10]; w[s, :k] = st[:, 10:13]
+            mass[s, :k] = self.mass[g]; geom[s, :k, 0] = self.radius[g]
+            inertia = 0.4 * self.mass[g] * self.radius[g] ** 2    # Sphere::computeInertia, Geometry.h:41
+            for d in (0, 4, 8):
+                ib[s, :k, d] = inertia; ibi[s, :k, d] = 1.0 / inertia
+            for f, fb in enumerate(self.fixed):                     # container boxes behind the dynamic bodies
+                j = k + f
+                xs[s, j] = fb["x"]; q[s, j] = fb["q"]; fixed[s, j] = 1; gtype[s, j] = 1; geom[s, j, :3] = fb["dim"]
+                dim = np.asarray(fb["dim"], np.float32)
+                diag = np.array([dim[1] ** 2 + dim[2] ** 2, dim[0] ** 2 + dim[2] ** 2, dim[0] ** 2 + dim[1] ** 2], np.float32) / 12.0
+                ib[s, j, [0, 4, 8]] = diag; ibi[s, j, [0, 4, 8]] = 1.0 / diag
+            counts[s] = k + nf
+            self.scene_ids.append(g); self.scene_owned.append(sc["owned"])
+        gtype[:] = np.where(fixed == 1, 1, SPHERE)
+        self.ctx.upload_bodies(xs, q, v, w, mass, ib, ibi, fixed, gtype, geom, counts=counts)
+        maps = halo_maps(part, self.rank, NBc)
+        self.ctx.halo_set_local(maps["local_src"], maps["local_dst"])
+        peers = [p for p in range(self.world) if p != self.rank]
+        send = np.concatenate([maps["send"][p] for p in peers]) if peers else np.zeros(0, np.int32)
+        recv = np.concatenate([maps["recv"][p] for p in peers]) if peers else np.zeros(0, np.int32)
+        self.ctx.halo_set_remote(send, recv)
+        self.send_splits = [int(maps["send"][p].size) if p != self.rank else 0 for p in range(self.world)]
+        self.recv_splits = [int(maps["recv"][p].size) if p != self.rank else 0 for p in range(self.world)]
+        if self.comm is not None:
+            self.comm.prepare(sum(self.send_splits), sum(self.recv_splits))
+        self.steps_since_rebuild = 0
+        owned = sum(int(o.sum()) for o in self.scene_owned)
+        total = sum(len(g) for g in self.scene_ids)
+        self.stats.update(rebuilds=self.stats["rebuilds"] + 1, halo_bodies=total - owned, owned_bodies=owned,
+                          scenes=len(scenes), remote_halos=sum(self.recv_splits), max_bodies=NBc)
+
+    # ---- stepping ----------------------------------------------------------------------------------------------
+    def step(self, n=1):
+        for _ in range(n):
+            if self.steps_since_rebuild >= self.K:
+                self.gather_state()
+                self.rebuild()
+            self.ctx.step(self.dt, 1)
+            self.ctx.halo_sync_local()
+            if self.comm is not None and self.world > 1:
+                self.ctx.halo_pack(self.comm.send_ptr())
+                self.ctx.sync()                                    # the pack kernel runs on the context's stream
+                self.comm.exchange(self.send_splits, self.recv_splits)   # NCCL all_to_all over NVLink
+                self.ctx.halo_unpack(self.comm.recv_ptr())
+            self.steps_since_rebuild += 1
+
+    def gather_state(self):
+        """Owners' state of ALL bodies on every rank (all-reduce of disjoint contributions)."""
+        self.ctx.sync()
+        st = self.ctx.download_state()
+        full = np.zeros((self.n, STATE_W), np.float32)
+        for s, (g, own) in enumerate(zip(self.scene_ids, self.scene_owned)):
+            k = len(g)
+            rows = np.concatenate([st["x"][s, :k], st["q"][s, :k], st["v"][s, :k], st["w"][s, :k]], axis=1)
+            full[g[own]] = rows[own]
+        if self.comm is not None and self.world > 1:
+            full = self.comm.all_reduce_sum(full)
+        self.state = full
+        return full
+
+    def max_penetration(self):
+        """Deepest contact over this rank's scenes (contacts between two halo copies are someone else's)."""
+        self.ctx.sync()
+        worst = 0.0
+        for s in range(len(self.scene_ids)):
+            c = self.ctx.contacts(s)
+            if c["phi"].size:
+                worst = max(worst, float(-c["phi"].min()))
+        return worst
+
+    def close(self):
+        if self.ctx is not None:
+            self.ctx.close(); self.ctx = None
+
+
+class TorchComm:
+    """NCCL plumbing through torch.distributed: device buffers for the packed halo state, all_to_all_single."""
+
+    def __init__(self, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.device = torch, dist, torch.device("cuda", device)
+        self.sbuf = self.rbuf = None
+
+    def prepare(self, n_send, n_recv):
+        self.sbuf = self.torch.zeros(max(n_send, 1) * STATE_W, dtype=self.torch.float32, device=self.device)
+        self.rbuf = self.torch.zeros(max(n_recv, 1) * STATE_W, dtype=self.torch.float32, device=self.device)
+        self.n_send, self.n_recv = n_send, n_recv
+
+    def send_ptr(self): return self.sbuf.data_ptr()
+    def recv_ptr(self): return self.rbuf.data_ptr()
+
+    def exchange(self, send_splits, recv_splits):
+        inp = self.sbuf[: self.n_send * STATE_W]
+        out = self.rbuf[: self.n_recv * STATE_W]
+        self.dist.all_to_all_single(out, inp, [r * STATE_W for r in recv_splits], [s * STATE_W for s in send_splits])
+        self.torch.cuda.synchronize(self.device)
+
+    def all_reduce_sum(self, arr):
+        t = self.torch.from_numpy(arr).to(self.device)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+
+def sphere_pile(nx, ny, nz, radius=0.5, jitter=0.01, seed=1234):
+    """nx x ny x nz lattice of touching spheres (spacing 2r) resting in an open box of five fixed boxes, the
+    marble-box construction (Scenarios.h:18-80) scaled up; returns (x, radius, mass, fixed_bodies)."""
+    rng = np.random.default_rng(seed)
+    d = 2.0 * radius
+    ii, kk, jj = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    x = np.stack([(ii - 0.5 * (nx - 1)) * d, 2.0 + kk * d, (jj - 0.5 * (nz - 1)) * d], axis=-1).reshape(-1, 3).astype(np.float32)
+    x[:, [0, 2]] += rng.uniform(-jitter, jitter, (x.shape[0], 2)).astype(np.float32)
+    ex, ez, hy = nx * d + d, nz * d + d, ny * d + 2.0
+    s, c = np.sin(0.5 * 1.57), np.cos(0.5 * 1.57)
+    qi, qy = [0, 0, 0, 1], [0, s, 0, c]
+    fixed = [dict(x=[0.5 * ex - 0.25, 0.5 * hy, 0], q=qi, dim=[0.4, hy, ez]), dict(x=[-0.5 * ex + 0.25, 0.5 * hy, 0], q=qi, dim=[0.4, hy, ez]),
+             dict(x=[0, 0.5 * hy, 0.5 * ez - 0.25], q=qy, dim=[0.4, hy, ex]), dict(x=[0, 0.5 * hy, -0.5 * ez + 0.25], q=qy, dim=[0.4, hy, ex]),
+             dict(x=[0, 0, 0], q=qi, dim=[ex, 0.4, ez])]
+    n = x.shape[0]
+    return x, np.full(n, radius, np.float32), np.ones(n, np.float32), fixed
