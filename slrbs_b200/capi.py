@@ -16,7 +16,7 @@ SPHERICAL, HINGE = 1, 2
 
 # every symbol include/slrbs_b200.h declares
 SYMBOLS = [
-    "slrbs_last_error", "slrbs_version", "slrbs_create", "slrbs_destroy", "slrbs_set_params",
+    "slrbs_last_error", "slrbs_version", "slrbs_describe", "slrbs_create", "slrbs_destroy", "slrbs_set_params",
     "slrbs_upload_bodies", "slrbs_upload_joints", "slrbs_upload_state", "slrbs_download_state",
     "slrbs_set_external_forces", "slrbs_step", "slrbs_sync", "slrbs_stage_prepare", "slrbs_stage_detect",
     "slrbs_stage_jacobians", "slrbs_stage_solve", "slrbs_stage_integrate", "slrbs_download_contact_counts",
@@ -50,6 +50,7 @@ def load_library():
     fp, ip, vp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_void_p
     L.slrbs_last_error.restype = C.c_char_p
     L.slrbs_version.restype = C.c_char_p
+    L.slrbs_describe.argtypes = [vp, C.c_char_p, C.c_int]
     L.slrbs_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.slrbs_destroy.argtypes = [vp]
     L.slrbs_destroy.restype = None
@@ -121,6 +122,11 @@ class Context:
         if rc < 0:
             raise SlrbsError(f"slrbs error {rc}: {self.L.slrbs_last_error().decode()}")
         return rc
+
+    def describe(self):
+        buf = C.create_string_buffer(256)
+        self._ck(self.L.slrbs_describe(self.h, buf, 256))
+        return buf.value.decode()
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:

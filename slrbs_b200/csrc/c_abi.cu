@@ -158,6 +158,20 @@ extern "C" {
 const char* slrbs_last_error(void) { return g_err.c_str(); }
 const char* slrbs_version(void) { return "slrbs_b200 0.1 (sm_100a)"; }
 
+int slrbs_describe(slrbs_ctx* c, char* buf, int buf_len)
+{
+    if (!c || !buf || buf_len <= 0) return fail(SLRBS_E_ARG, "slrbs_describe: bad argument");
+    char tmp[256];
+    if (c->v.level_mode)
+        std::snprintf(tmp, sizeof tmp, "solver=k_pgs_lv<G=%d> (level-scheduled, %d lanes/scene) detect=%s graph=%d", c->level_group,
+                      c->level_group, detect_variant(c->v, c->broadphase), c->use_graph);
+    else
+        std::snprintf(tmp, sizeof tmp, "solver=k_pgs (thread/scene, cp.async row ring) detect=%s graph=%d",
+                      detect_variant(c->v, c->broadphase), c->use_graph);
+    std::snprintf(buf, (size_t)buf_len, "%s", tmp);
+    return (int)std::strlen(buf);
+}
+
 int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int max_joints, int max_contacts)
 {
     if (!out || n_scenes <= 0 || max_bodies <= 0 || max_bodies > MAX_BODIES_PER_SCENE || max_joints < 0 || max_contacts < 0)

@@ -487,6 +487,22 @@ void init_detect_kernels()
     cudaFuncSetAttribute(k_detect_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
+// name of the kernel launch_detect() picks (same decision tree), for slrbs_describe
+const char* detect_variant(const View& v, int broadphase)
+{
+    const bool grid = broadphase > 0 || (broadphase < 0 && v.NB >= 512);
+    int H = 64;
+    while (H < v.NB && H < 4096) H <<= 1;
+    const size_t cta_smem = (size_t)v.NB * 16 + detect_cta_smem_ints(v.NB, grid, H, DETECT_CTA_THREADS / 32) * 4;
+    if (((v.NB >= 512 && v.B <= 4096) || (v.NB >= 128 && v.B <= 512)) && cta_smem <= 200 * 1024)
+        return grid ? "k_detect_cta<grid>" : "k_detect_cta<all-pairs>";
+    const size_t per_warp = (size_t)v.NB * 16 + detect_smem_ints(v.NB, grid, H) * 4;
+    int warps = 8;
+    while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+    if ((v.NB < 24 && !v.level_mode) || per_warp * warps > 200 * 1024) return "k_detect_serial";
+    return grid ? "k_detect_warp<grid>" : "k_detect_warp<all-pairs>";
+}
+
 void launch_detect(const View& v, int broadphase, cudaStream_t s)
 {
     // broadphase: 0 = off (all pairs), 1 = hashed grid, -1 = auto (grid for scenes of >= 512 bodies)

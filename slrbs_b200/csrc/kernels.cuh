@@ -19,6 +19,7 @@ void launch_prepare(const View& v, cudaStream_t s);
 void launch_detect(const View& v, int broadphase, cudaStream_t s);
 bool detect_warp_fits(int NB);
 void init_detect_kernels();
+const char* detect_variant(const View& v, int broadphase);
 void init_level_kernels();
 void launch_contact_rows(const View& v, float h, cudaStream_t s);
 void launch_joint_rows(const View& v, float h, cudaStream_t s);

@@ -48,8 +48,13 @@ def build_partition(x, block, halo_w, world):
         m = block_rank == r
         scene_of_block[m] = np.arange(m.sum())
     bidx = np.searchsorted(ukeys, key)                             # block index of every body
-    # halo candidates: (body, neighbour block) pairs within halo_w of the neighbour's box
+    # halo candidates: (body, neighbour block) pairs. A body is copied into the neighbour at offset d when, on every
+    # axis where d is non-zero, it lies within halo_w of that face (a box-shaped, slightly generous neighbourhood:
+    # cheaper than the exact distance to the neighbouring cube and still a superset of what can touch)
     rel = x - origin - cell * block                                # position inside the own cell, in [0, block)
+    near_lo, near_hi = rel <= halo_w, (block - rel) <= halo_w      # [n, 3]
+    border = np.nonzero((near_lo | near_hi).any(axis=1))[0]        # interior bodies are nobody's halo
+    nlo, nhi, bcell = near_lo[border], near_hi[border], cell[border]
     pairs_body, pairs_block = [np.arange(n)], [bidx]
     owned_flag = [np.ones(n, bool)]
     for dx in (-1, 0, 1):
@@ -57,19 +62,21 @@ def build_partition(x, block, halo_w, world):
             for dz in (-1, 0, 1):
                 if dx == dy == dz == 0:
                     continue
-                d = np.array([dx, dy, dz])
-                gap = np.where(d < 0, rel, np.where(d > 0, block - rel, 0.0))
-                near = np.sqrt((gap * gap).sum(axis=1)) <= halo_w
-                nc = cell[near] + d
+                m = np.ones(len(border), bool)
+                for ax, dd in enumerate((dx, dy, dz)):
+                    if dd < 0: m &= nlo[:, ax]
+                    elif dd > 0: m &= nhi[:, ax]
+                if not m.any():
+                    continue
+                nc = bcell[m] + np.array([dx, dy, dz])
                 ok = ((nc >= 0) & (nc < ncell)).all(axis=1)
-                ids = np.nonzero(near)[0][ok]
+                ids = border[m][ok]
                 nk = (nc[ok, 0] * ncell[1] + nc[ok, 1]) * ncell[2] + nc[ok, 2]
-                pos = np.searchsorted(ukeys, nk)
-                pos = np.minimum(pos, len(ukeys) - 1)
+                pos = np.minimum(np.searchsorted(ukeys, nk), len(ukeys) - 1)
                 exists = ukeys[pos] == nk
-                pairs_body.append(ids[exists]); pairs_block.append(pos[exists]); owned_flag.append(np.zeros(exists.sum(), bool))
+                pairs_body.append(ids[exists]); pairs_block.append(pos[exists]); owned_flag.append(np.zeros(int(exists.sum()), bool))
     pb, pk, po = np.concatenate(pairs_body), np.concatenate(pairs_block), np.concatenate(owned_flag)
-    order = np.lexsort((pb, pk))                                   # by block, then global body id
+    order = np.argsort(pk.astype(np.int64) * n + pb, kind="stable")      # by block, then global body id
     pb, pk, po = pb[order], pk[order], po[order]
     starts = np.searchsorted(pk, np.arange(len(ukeys)))
     ends = np.searchsorted(pk, np.arange(len(ukeys)), side="right")
@@ -120,15 +127,23 @@ class PartitionedPile:
     """Driver of one rank. `comm` is None (single process, world 1) or a torch.distributed-like object used through
     all_reduce_sum(tensor) and all_to_all(out, inp, out_splits, in_splits) (see TorchComm)."""
 
-    def __init__(self, x, radius, mass, fixed_bodies, block=8.0, rebuild_every=10, vmax=6.0, dt=0.01, rank=0, world=1,
-                 device=0, comm=None, contact_factor=4, mu=0.8, iters=10):
+    def __init__(self, x, radius, mass, fixed_bodies, block=8.0, rebuild_every=0, vmax=6.0, dt=0.01, rank=0, world=1,
+                 device=0, comm=None, contact_factor=4, mu=0.8, iters=10, slack=0.5):
+        """rebuild_every = K > 0 fixes the re-partition interval and sizes the halo for speeds up to `vmax`;
+        K = 0 (default) adapts it: the halo gets `slack` metres of room and the next re-partition is scheduled for
+        when the fastest body (current speed plus free-fall acceleration) could have used half of it."""
         self.n = x.shape[0]
         self.radius = np.asarray(radius, np.float32); self.mass = np.asarray(mass, np.float32)
         self.fixed = fixed_bodies                                 # list of dict(x, q, dim)
         self.block, self.K, self.vmax, self.dt = float(block), int(rebuild_every), float(vmax), float(dt)
         self.rank, self.world, self.device, self.comm = rank, world, device, comm
         self.contact_factor, self.mu, self.iters = contact_factor, mu, iters
-        self.halo_w = 2.0 * float(self.radius.max()) + 2e-3 + 2.0 * self.vmax * self.K * self.dt
+        self.adaptive, self.slack = self.K <= 0, float(slack)
+        if self.adaptive:
+            self.halo_w = 2.0 * float(self.radius.max()) + 2e-3 + self.slack
+            self.K = 1
+        else:
+            self.halo_w = 2.0 * float(self.radius.max()) + 2e-3 + 2.0 * self.vmax * self.K * self.dt
         self.state = np.zeros((self.n, STATE_W), np.float32)
         self.state[:, :3] = x
         self.state[:, 6] = 1.0
@@ -139,6 +154,8 @@ class PartitionedPile:
 
     # ---- partition + upload ------------------------------------------------------------------------------------
     def rebuild(self):
+        import time
+        t0 = time.perf_counter()
         part = build_partition(self.state[:, :3], self.block, min(self.halo_w, self.block), self.world)
         if part["n_blocks"] > 1 and self.halo_w > self.block:
             raise ValueError(f"halo width {self.halo_w:.2f} exceeds the block size {self.block}: rebuild more often or use larger blocks")
@@ -190,8 +207,18 @@ class PartitionedPile:
         if self.comm is not None:
             self.comm.prepare(sum(self.send_splits), sum(self.recv_splits))
         self.steps_since_rebuild = 0
+        if self.adaptive:
+            # two bodies may approach each other: each may use slack / 2 before the next re-partition.
+            # displacement after k steps <= v0 k dt + g (k dt)^2 / 2  (v0 = fastest body now)
+            v0 = float(np.sqrt((self.state[:, 7:10] ** 2).sum(axis=1).max())) if self.n else 0.0
+            k = 1
+            while k < 200 and v0 * (k + 1) * self.dt + 4.905 * ((k + 1) * self.dt) ** 2 <= 0.5 * self.slack:
+                k += 1
+            self.K = k
         owned = sum(int(o.sum()) for o in self.scene_owned)
         total = sum(len(g) for g in self.scene_ids)
+        self.stats["rebuild_s"] = self.stats.get("rebuild_s", 0.0) + time.perf_counter() - t0
+        self.stats["K"] = self.K
         self.stats.update(rebuilds=self.stats["rebuilds"] + 1, halo_bodies=total - owned, owned_bodies=owned,
                           scenes=len(scenes), remote_halos=sum(self.recv_splits), max_bodies=NBc)
 
@@ -212,6 +239,8 @@ class PartitionedPile:
 
     def gather_state(self):
         """Owners' state of ALL bodies on every rank (all-reduce of disjoint contributions)."""
+        import time
+        t0 = time.perf_counter()
         self.ctx.sync()
         st = self.ctx.download_state()
         full = np.zeros((self.n, STATE_W), np.float32)
@@ -222,6 +251,7 @@ class PartitionedPile:
         if self.comm is not None and self.world > 1:
             full = self.comm.all_reduce_sum(full)
         self.state = full
+        self.stats["gather_s"] = self.stats.get("gather_s", 0.0) + time.perf_counter() - t0
         return full
 
     def max_penetration(self):

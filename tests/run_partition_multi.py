@@ -9,7 +9,7 @@ from slrbs_b200 import Context
 from slrbs_b200.partition import PartitionedPile, TorchComm, sphere_pile
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, nargs=3, default=[24, 8, 12]); ap.add_argument("--block", type=float, default=6.0)
+ap.add_argument("--dims", type=int, nargs=3, default=[24, 8, 12]); ap.add_argument("--block", type=float, default=6.0)
 ap.add_argument("--steps", type=int, default=60); ap.add_argument("--rebuild", type=int, default=10)
 ap.add_argument("--check", type=int, default=1)
 a = ap.parse_args()
@@ -17,7 +17,7 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-x, r, m, fixed = sphere_pile(*a.n)
+x, r, m, fixed = sphere_pile(*a.dims)
 comm = TorchComm(local) if world > 1 else None
 pile = PartitionedPile(x, r, m, fixed, block=a.block, rebuild_every=a.rebuild, rank=rank, world=world, device=local, comm=comm)
 pile.step(5)
@@ -33,7 +33,7 @@ state = pile.gather_state()
 out = dict(world=world, bodies=int(x.shape[0]), steps=a.steps, ms_per_step=1e3 * dt / a.steps, body_steps_per_s=x.shape[0] * a.steps / dt,
            max_penetration=pen, stats=pile.stats, finite=bool(np.isfinite(state).all()))
 if rank == 0 and a.check and x.shape[0] <= 5000:
-    one = PartitionedPile(x, r, m, fixed, block=max(a.n) * 2.0 + 8.0, rebuild_every=10 ** 9, rank=0, world=1, device=local)
+    one = PartitionedPile(x, r, m, fixed, block=max(a.dims) * 2.0 + 8.0, rebuild_every=10 ** 9, rank=0, world=1, device=local)
     one.step(5 + a.steps)
     ref = one.gather_state()
     d = np.linalg.norm(state[:, :3] - ref[:, :3], axis=1)
