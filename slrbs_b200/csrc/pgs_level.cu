@@ -127,6 +127,8 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
 enum { LV_THREADS = 32 };       // one warp per CTA: 32 / G scenes; small CTAs pack shared memory tightly (a
                                 // 1000-body scene needs 32 KB of accumulators: 7 scenes per SM instead of 4)
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
 struct BodyW { float4* w; };     // shared-memory accumulators of one scene: [body][2] (linear, angular)
 __device__ __forceinline__ void ld_w(const float4* w, int body, V3& l, V3& a) { l = mk3(w[2 * body]); a = mk3(w[2 * body + 1]); }
 __device__ __forceinline__ void st_w(float4* w, int body, const V3& l, const V3& a) { w[2 * body] = mk4(l, 0.f); w[2 * body + 1] = mk4(a, 0.f); }
@@ -197,6 +199,18 @@ __global__ void __launch_bounds__(LV_THREADS, MINB) k_pgs_lv(View v, float dt, i
         }
         for (int lev = 1, p0 = 0; lev <= ncl; ++lev) {
             const int p1 = v.clev_end[at(v, lev, scene)];
+            if (G == 32 && v.B >= 256) {   // (measured: pays only for wide scenes in batches whose rows stream from HBM)
+                // pull the rows this lane will solve in the NEXT level (or the first level of the next sweep) towards L2
+                // while the current level is solved: the row stream is far larger than L2 and would otherwise pay an
+                // HBM round trip at the start of every level
+                int q0 = p1, q1 = p1;
+                if (lev < ncl) q1 = v.clev_end[at(v, lev + 1, scene)];
+                else if (it + 1 < iters) { q0 = 0; q1 = v.clev_end[at(v, 1, scene)]; }
+                for (int q = q0 + gl; q < q1; q += G) {
+#pragma unroll
+                    for (int f = 0; f < CROW_FIELDS; ++f) prefetch_l2(&v.crow[at_crow(v, f, q, scene)]);
+                }
+            }
             for (int p = p0 + gl; p < p1; p += G) {
                 float4 F[CROW_FIELDS];
 #pragma unroll
