@@ -124,8 +124,10 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
 // ------------------------------------------------------------------------------------
 // solve
 // ------------------------------------------------------------------------------------
-enum { LV_THREADS = 32 };       // one warp per CTA: 32 / G scenes; small CTAs pack shared memory tightly (a
-                                // 1000-body scene needs 32 KB of accumulators: 7 scenes per SM instead of 4)
+// CTA size: one warp holding 32 / G scenes (small CTAs pack shared memory tightly: a 1000-body scene needs 32 KB of
+// accumulators, so 7 scenes fit an SM), or G = 64 / 128 lanes = 2 / 4 warps on ONE scene whose levels are wider
+// than a warp (block barrier between levels instead of a warp barrier).
+template <int G> struct LvCfg { enum { THREADS = G < 32 ? 32 : G, SPC = THREADS / G }; };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
@@ -136,20 +138,22 @@ __device__ __forceinline__ void st_w(float4* w, int body, const V3& l, const V3&
 template <int G>
 __device__ __forceinline__ void group_sync(unsigned mask)
 {
-    if (G >= 32) __syncwarp(); else __syncwarp(mask);
+    if (G > 32) __syncthreads();
+    else if (G == 32) __syncwarp();
+    else __syncwarp(mask);
 }
 
 // MINB = warps per SM the register allocation must allow: 16 (128 registers, a few spills) wins when the batch
 // can fill 16 warps per SM, 12 (162 registers, no spills) when it cannot and single-warp latency is what matters.
 template <int G, int MINB>
-__global__ void __launch_bounds__(LV_THREADS, MINB) k_pgs_lv(View v, float dt, int iters, float mu)
+__global__ void __launch_bounds__(LvCfg<G>::THREADS, MINB) k_pgs_lv(View v, float dt, int iters, float mu)
 {
     extern __shared__ float4 smem_w[];
-    constexpr int SPC = LV_THREADS / G;                          // scenes per CTA
+    constexpr int SPC = LvCfg<G>::SPC;                           // scenes per CTA
     const int grp = threadIdx.x / G, gl = threadIdx.x % G;
     const int scene = blockIdx.x * SPC + grp;
     const unsigned mask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
-    if (scene >= v.B) return;                                    // whole groups leave together
+    if (scene >= v.B) return;                                    // whole groups (for G > 32: whole CTAs) leave together
     float4* w = smem_w + (size_t)grp * v.NB * 2;
     const int nb = v.nbodies[scene], nj = v.njoints[scene], nc = v.ncontacts[scene];
     const int njl = v.njlev[scene], ncl = v.nclev[scene];
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(LV_THREADS, MINB) k_pgs_lv(View v, float dt, i
         }
         for (int lev = 1, p0 = 0; lev <= ncl; ++lev) {
             const int p1 = v.clev_end[at(v, lev, scene)];
-            if (G == 32 && v.B >= 256) {   // (measured: pays only for wide scenes in batches whose rows stream from HBM)
+            if (G >= 32 && v.B >= 256) {   // (measured: pays only for wide scenes in batches whose rows stream from HBM)
                 // pull the rows this lane will solve in the NEXT level (or the first level of the next sweep) towards L2
                 // while the current level is solved: the row stream is far larger than L2 and would otherwise pay an
                 // HBM round trip at the start of every level
@@ -314,36 +318,38 @@ void launch_joint_levels(const View& v, cudaStream_t s)
 template <int G>
 static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t s)
 {
-    const int spc = LV_THREADS / G;
+    constexpr int threads = LvCfg<G>::THREADS, spc = LvCfg<G>::SPC;
     const size_t smem = (size_t)spc * v.NB * 2 * sizeof(float4);
     const unsigned blocks = (unsigned)((v.B + spc - 1) / spc);
-    if (blocks >= 148u * 8u) k_pgs_lv<G, 16><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
-    else k_pgs_lv<G, 12><<<blocks, LV_THREADS, smem, s>>>(v, dt, iters, mu);
+    constexpr int lo = 12 * 32 / threads, hi = 16 * 32 / threads;       // 12 / 16 warps per SM
+    if ((size_t)blocks * threads >= 148u * 8u * 32u) k_pgs_lv<G, hi><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
+    else k_pgs_lv<G, lo><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
 }
 
 template <int G>
 static void init_lv()
 {
-    cudaFuncSetAttribute(k_pgs_lv<G, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_pgs_lv<G, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    constexpr int threads = LvCfg<G>::THREADS;
+    cudaFuncSetAttribute(k_pgs_lv<G, 12 * 32 / threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_lv<G, 16 * 32 / threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 // per-device kernel attributes (called from slrbs_create with the device current)
 void init_level_kernels()
 {
-    init_lv<4>(); init_lv<8>(); init_lv<16>(); init_lv<32>();
+    init_lv<4>(); init_lv<8>(); init_lv<16>(); init_lv<32>(); init_lv<64>(); init_lv<128>();
     cudaFuncSetAttribute(k_contact_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 int level_group_size(const View& v, int requested)
 {
     int g = requested;
-    if (g != 4 && g != 8 && g != 16 && g != 32) g = v.NB < 24 ? 4 : (v.NB <= 96 ? 8 : (v.NB <= 512 ? 16 : 32));
-    // the accumulators of LV_THREADS / g scenes must fit in shared memory
-    while (g < 32 && (size_t)(LV_THREADS / g) * v.NB * 32 > 200 * 1024) g <<= 1;
+    if (g != 4 && g != 8 && g != 16 && g != 32 && g != 64 && g != 128) g = v.NB < 24 ? 4 : (v.NB <= 96 ? 8 : (v.NB <= 512 ? 16 : (v.B <= 296 ? 64 : 32)));   // few wide scenes: 2 warps each
+    // the accumulators of the 32 / g scenes of a warp must fit in shared memory
+    while (g < 32 && (size_t)(32 / g) * v.NB * 32 > 200 * 1024) g <<= 1;
     return g;
 }
 
-bool level_mode_fits(int max_bodies) { return (size_t)(LV_THREADS / 32) * max_bodies * 32 <= 200 * 1024; }
+bool level_mode_fits(int max_bodies) { return (size_t)max_bodies * 32 <= 200 * 1024; }
 
 void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, cudaStream_t s)
 {
@@ -351,6 +357,8 @@ void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, c
     case 4:  launch_lv<4>(v, dt, iters, mu, s); break;
     case 8:  launch_lv<8>(v, dt, iters, mu, s); break;
     case 16: launch_lv<16>(v, dt, iters, mu, s); break;
+    case 64: launch_lv<64>(v, dt, iters, mu, s); break;
+    case 128: launch_lv<128>(v, dt, iters, mu, s); break;
     default: launch_lv<32>(v, dt, iters, mu, s); break;
     }
 }
