@@ -25,6 +25,7 @@ struct DetectSmem {               // per-warp shared-memory arrays
     int* cell_start;              // [H+1] grid: bucket offsets (after the fill: bucket ends)
     int* cell_items;              // [NB] grid: sphere indices grouped by bucket
     int* special;                 // [NB] grid: non-sphere body indices, ascending
+    int* counter;                 // [2] grid: number of candidates gathered for the current row
     int* cand;                    // [CAND_CAP] grid: candidate partners of the current row (unordered)
     int* order;                   // [HIT_CAP] grid: hit slots in ascending-j order
     int* hits;                    // [HIT_CAP][HIT_WORDS] grid: j, b0, b1, cnt, n, p[4], phi[4] of the pairs that touch
@@ -33,7 +34,7 @@ struct DetectSmem {               // per-warp shared-memory arrays
 __host__ __device__ inline size_t detect_smem_ints(int NB, bool grid, int H)
 {
     size_t n = (size_t)NB;                                     // sf
-    if (grid) n += (size_t)H + 1 + NB + NB + CAND_CAP + HIT_CAP + HIT_CAP * HIT_WORDS;
+    if (grid) n += (size_t)H + 1 + NB + NB + 2 + CAND_CAP + HIT_CAP + HIT_CAP * HIT_WORDS;
     return n;
 }
 
@@ -72,51 +73,42 @@ __device__ __forceinline__ void emit_chunk(const View& v, const DetectSmem& sm, 
     count += total;
 }
 
-// Partners of sphere i from the grid: the spheres of the 27 neighbouring cells (each distinct bucket once) plus
-// every non-sphere body, unordered in sm.cand; entries with j <= i are marked dead (-1). Returns their number,
-// or -1 when the row has more than CAND_CAP candidates (the caller then walks all j > i). Warp-collective.
+// Partners j > i of sphere i from the grid: the spheres of the 27 neighbouring cells plus the non-sphere bodies,
+// unordered in sm.cand. Two neighbouring cells may hash to the same bucket, so a partner can appear twice; the
+// duplicates are dropped once the touching pairs are known (grid_collect). Returns the number of candidates, or
+// -1 when there are more than CAND_CAP (the caller then walks all j > i). Warp-collective.
 __device__ __forceinline__ int gather_candidates(const DetectSmem& sm, int lane, int i, const float4& ci, float inv_h, int H,
                                                  int nsph, int nspecial)
 {
     const int Hmask = H - 1;
-    const int ix = (int)floorf(ci.x * inv_h), iy = (int)floorf(ci.y * inv_h), iz = (int)floorf(ci.z * inv_h);
-    int h = -1, beg = 0, cnt = 0;
-    if (lane < 27) h = cell_hash(ix + lane % 3 - 1, iy + (lane / 3) % 3 - 1, iz + lane / 9 - 1, Hmask);
-    const unsigned same = __match_any_sync(0xffffffffu, h);
-    if (lane < 27 && (__ffs(same) - 1) == lane) {                // first lane of every distinct bucket
-        beg = sm.cell_start[h + 1];
+    if (lane == 0) *sm.counter = 0;
+    __syncwarp();
+    if (lane < 27) {
+        const int ix = (int)floorf(ci.x * inv_h), iy = (int)floorf(ci.y * inv_h), iz = (int)floorf(ci.z * inv_h);
+        const int h = cell_hash(ix + lane % 3 - 1, iy + (lane / 3) % 3 - 1, iz + lane / 9 - 1, Hmask);
+        const int beg = sm.cell_start[h + 1];
         const int end = (h + 2 <= H) ? sm.cell_start[h + 2] : nsph;
-        cnt = end - beg;
-    }
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total + nspecial > CAND_CAP) return -1;
-    const int off = incl - cnt;
-    for (int k = 0; k < cnt; ++k) {
-        const int j = sm.cell_items[beg + k];
-        sm.cand[off + k] = j > i ? j : -1;
+        for (int k = beg; k < end; ++k) {
+            const int j = sm.cell_items[k];
+            if (j > i) { const int slot = atomicAdd(sm.counter, 1); if (slot < CAND_CAP) sm.cand[slot] = j; }
+        }
     }
     for (int k = lane; k < nspecial; k += 32) {
         const int j = sm.special[k];
-        sm.cand[total + k] = j > i ? j : -1;
+        if (j > i) { const int slot = atomicAdd(sm.counter, 1); if (slot < CAND_CAP) sm.cand[slot] = j; }
     }
     __syncwarp();
-    return total + nspecial;
+    const int total = *sm.counter;
+    return total > CAND_CAP ? -1 : total;
 }
 
-// One grid row, step 1: tests the unordered candidates and buffers the pairs that touch in sm.hits. Returns the
-// row's contact count (nh = number of buffered pairs), or -1 if more than HIT_CAP pairs touch (the caller then
-// redoes the row with the ordered all-pairs walk). Warp-collective.
+// One grid row, step 1: tests the unordered candidates and buffers the pairs that touch in sm.hits (duplicates of a
+// partner dropped). Returns the row's contact count (nh = number of buffered pairs), or -1 if more than HIT_CAP
+// pairs touch (the caller then redoes the row with the ordered all-pairs walk). Warp-collective.
 __device__ __forceinline__ int grid_collect(const View& v, const DetectSmem& sm, int scene, int lane, int i, const float4& ci, int fi,
                                             int ncand, int& nh)
 {
     const unsigned lt = (1u << lane) - 1u;
-    int ncontacts = 0;
     nh = 0;
     for (int k0 = 0; k0 < ncand; k0 += 32) {
         const int k = k0 + lane;
@@ -137,14 +129,25 @@ __device__ __forceinline__ int grid_collect(const View& v, const DetectSmem& sm,
                 if (q < o.cnt) { f[7 + 3 * q] = o.p[q].x; f[8 + 3 * q] = o.p[q].y; f[9 + 3 * q] = o.p[q].z; f[19 + q] = o.phi[q]; }
             }
         }
-        int c = o.cnt;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-        ncontacts += c;
         nh += __popc(any);
     }
     __syncwarp();
-    return nh > HIT_CAP ? -1 : ncontacts;
+    if (nh > HIT_CAP) return -1;
+    if (nh == 0) return 0;
+    // drop repeated partners (keep the first), count the contacts
+    int c = 0;
+    if (lane < nh) {
+        const int myj = sm.hits[lane * HIT_WORDS];
+        bool dup = false;
+        for (int m = 0; m < lane; ++m) dup |= sm.hits[m * HIT_WORDS] == myj;
+        c = dup ? 0 : sm.hits[lane * HIT_WORDS + 3];
+    }
+    __syncwarp();
+    if (lane < nh) sm.hits[lane * HIT_WORDS + 3] = c;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    __syncwarp();
+    return c;
 }
 
 // One grid row, step 2: orders the buffered pairs by partner index (distinct) and appends their contacts at `base`.
@@ -154,7 +157,7 @@ __device__ __forceinline__ void grid_flush(const View& v, const DetectSmem& sm, 
     if (lane < nh) {
         const int myj = sm.hits[lane * HIT_WORDS];
         int rank = 0;
-        for (int m = 0; m < nh; ++m) rank += sm.hits[m * HIT_WORDS] < myj;
+        for (int m = 0; m < nh; ++m) { const int oj = sm.hits[m * HIT_WORDS]; rank += (oj < myj) || (oj == myj && m < lane); }
         sm.order[rank] = lane;
     }
     __syncwarp();
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(256) k_detect_warp(View v, int warps_per_cta, 
     int* ip = reinterpret_cast<int*>(smem4 + (size_t)warps_per_cta * v.NB) + (size_t)warp * detect_smem_ints(v.NB, GRID, H);
     sm.sf = ip; ip += v.NB;
     sm.cell_start = ip; sm.cell_items = ip + H + 1; sm.special = sm.cell_items + v.NB;
-    sm.cand = sm.special + v.NB; sm.order = sm.cand + CAND_CAP; sm.hits = sm.order + HIT_CAP;
+    sm.counter = sm.special + v.NB; sm.cand = sm.counter + 2; sm.order = sm.cand + CAND_CAP; sm.hits = sm.order + HIT_CAP;
 
     const int n = v.nbodies[scene];
     float rmax = 0.f;
@@ -295,7 +298,7 @@ enum { DETECT_CTA_THREADS = 512 };
 __host__ __device__ inline size_t detect_cta_smem_ints(int NB, bool grid, int H, int warps)
 {
     size_t n = (size_t)NB + NB + 2;                            // sf, rowcnt
-    if (grid) n += (size_t)H + 1 + NB + NB + (size_t)(CAND_CAP + HIT_CAP + HIT_CAP * HIT_WORDS) * warps;
+    if (grid) n += (size_t)H + 1 + NB + NB + (size_t)(2 + CAND_CAP + HIT_CAP + HIT_CAP * HIT_WORDS) * warps;
     return n;
 }
 
@@ -338,8 +341,8 @@ __global__ void __launch_bounds__(DETECT_CTA_THREADS, 2) k_detect_cta(View v, in
     sm.sf = ip; ip += v.NB;
     int* rowcnt = ip; ip += v.NB + 2;
     sm.cell_start = ip; sm.cell_items = ip + H + 1; sm.special = sm.cell_items + v.NB;
-    sm.cand = sm.special + v.NB + (size_t)warp * (CAND_CAP + HIT_CAP + HIT_CAP * HIT_WORDS);
-    sm.order = sm.cand + CAND_CAP; sm.hits = sm.order + HIT_CAP;
+    sm.counter = sm.special + v.NB + (size_t)warp * (2 + CAND_CAP + HIT_CAP + HIT_CAP * HIT_WORDS);
+    sm.cand = sm.counter + 2; sm.order = sm.cand + CAND_CAP; sm.hits = sm.order + HIT_CAP;
 
     const int n = v.nbodies[scene];
     if (tid == 0) { s_rmax = 0; s_nspecial = 0; s_total = 0; }
