@@ -606,7 +606,7 @@ static void joint_jacobian(orc_system* s, con_t* j)
     /* Rows are rewritten in place each step; entries never written stay 0 from construction. */
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
         j->J0[r][c] = (r == c) ? 1.f : 0.f;
-        j->J1[r][c] = (r == c) ? -1.f : 0.f;
+        j->J1[r][c] = (r == c) ? -1.f : -0.f;     /* J1.block(0,0,3,3) = -sEye: off-diagonals are -0 */
     }
     set_hat(j->J0, v3_neg(rr0));
     set_hat(j->J1, rr1);

@@ -232,7 +232,11 @@ __global__ void __launch_bounds__(128) k_joint_rows(View v, float h)
 #pragma unroll
         for (int k = 0; k < 6; ++k) { J0[r][k] = 0.f; J1[r][k] = 0.f; }
     J0[0][0] = J0[1][1] = J0[2][2] = 1.f;
-    J1[0][0] = J1[1][1] = J1[2][2] = -1.f;
+    // J1.block(0,0,3,3) = -sEye (Hinge.cpp:54): the off-diagonals are -0, kept so exported rows match to the bit
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) J1[r][k] = (r == k) ? -1.f : -0.f;
     set_hat(J0, -rr0);
     set_hat(J1, rr1);
     V3 nxu = mk3(0.f, 0.f, 0.f), nxv = mk3(0.f, 0.f, 0.f);
@@ -1077,7 +1081,8 @@ __global__ void k_export_joints(View v, int scene, int n, float* J0, float* J1, 
     const int dim = __float_as_int(G[16].z);
     float A0[5][6], A1[5][6];
     for (int r = 0; r < 5; ++r) for (int k = 0; k < 6; ++k) { A0[r][k] = 0.f; A1[r][k] = 0.f; }
-    A0[0][0] = A0[1][1] = A0[2][2] = 1.f; A1[0][0] = A1[1][1] = A1[2][2] = -1.f;
+    A0[0][0] = A0[1][1] = A0[2][2] = 1.f;
+    for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) A1[r][k] = (r == k) ? -1.f : -0.f;   // -sEye
     set_hat(A0, -rr0); set_hat(A1, rr1);
     if (dim == 5) {
         set_row(A0[3], mk3(0.f, 0.f, 0.f), nxu); set_row(A0[4], mk3(0.f, 0.f, 0.f), nxv);

@@ -1,4 +1,7 @@
-"""ctypes binding for the CPU oracle (oracle/libslrbs_oracle.so).
+"""ctypes binding for the CPU oracle (oracle/libslrbs_oracle.so) and, when it has been built, for
+oracle/_ref/libslrbs_ref.so = the reference's own sources compiled against the Eigen API shim
+(oracle/ref_shim).  Both export the same orc_* entry points; `Oracle(scene)` is the C restatement,
+`Reference(scene)` the reference's code.
 
 TEST INFRASTRUCTURE ONLY.  The product (slrbs_b200/) never imports this module.
 """
@@ -11,19 +14,53 @@ import numpy as np
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _ORACLE_DIR = os.path.join(_ROOT, "oracle")
 _LIB_PATH = os.path.join(_ORACLE_DIR, "libslrbs_oracle.so")
+_REF_PATH = os.path.join(_ORACLE_DIR, "_ref", "libslrbs_ref.so")
 
 SPHERE, BOX, PLANE, CYLINDER = 0, 1, 2, 3
 CONTACT, SPHERICAL, HINGE = 0, 1, 2
 
 _lib = None
+_ref = None
 
 
 def build_oracle():
     subprocess.check_call(["make", "-s", "-C", _ORACLE_DIR])
 
 
-def lib():
-    global _lib
+def ref_available():
+    """oracle/_ref is built here (where /root/reference exists) and travels prebuilt to the GPU box."""
+    return os.path.exists(_REF_PATH)
+
+
+class _Optional:
+    """Symbols the reference driver does not export (per-stage entry points) resolve to a stub."""
+
+    def __init__(self, L):
+        self._L = L
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._L, name)
+        except AttributeError:
+            class _Missing:
+                argtypes = None
+                restype = None
+
+                def __call__(self, *a):
+                    raise NotImplementedError(f"{name} is not exported by oracle/_ref")
+            m = _Missing()
+            setattr(self, name, m)
+            return m
+
+
+def lib(impl="oracle"):
+    global _lib, _ref
+    if impl == "ref":
+        if _ref is None:
+            if not ref_available():
+                raise FileNotFoundError(_REF_PATH + " (make -C oracle ref)")
+            _ref = _bind(_Optional(C.CDLL(_REF_PATH)))
+        return _ref
     if _lib is not None:
         return _lib
     src = os.path.join(_ORACLE_DIR, "slrbs_oracle.c")
@@ -31,7 +68,11 @@ def lib():
         os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_LIB_PATH)
     ):
         build_oracle()
-    L = C.CDLL(_LIB_PATH)
+    _lib = _bind(C.CDLL(_LIB_PATH))
+    return _lib
+
+
+def _bind(L):
     fp = C.POINTER(C.c_float)
     ip = C.POINTER(C.c_int)
     vp = C.c_void_p
@@ -75,7 +116,6 @@ def lib():
     L.orc_scene_marble_box_n.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.orc_time_steps.argtypes = [vp, C.c_float, C.c_int]
     L.orc_time_steps.restype = C.c_double
-    _lib = L
     return L
 
 
@@ -106,8 +146,10 @@ SCENES = {
 class Oracle:
     """One RigidBodySystem of the restated reference."""
 
+    impl = "oracle"
+
     def __init__(self, scene=None, **kw):
-        self.L = lib()
+        self.L = lib(self.impl)
         self.h = self.L.orc_create()
         if scene is not None:
             self.load_scene(scene, **kw)
@@ -258,3 +300,8 @@ class Oracle:
     def set_joint_lambda(self, lam):
         a = np.ascontiguousarray(np.asarray(lam, np.float32).reshape(self.n_joints, 5))
         self.L.orc_set_joint_lambda(self.h, _f(a))
+
+
+class Reference(Oracle):
+    """Same interface, backed by the reference's own sources (oracle/_ref)."""
+    impl = "ref"

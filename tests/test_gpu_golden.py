@@ -1,0 +1,61 @@
+"""GPU parity against the committed golden vectors of the reference's own code (tests/golden/ref_*.npz).
+
+From each checkpoint state of the reference the device takes one step through the C ABI: the contact list
+(count, order, pairs, p, n, pene) must match BIT FOR BIT; impulses within 1e-4 * max|lambda| + 1e-6; the
+state after the step within 2e-6 (x, q) / 2e-4 (velocities) relative to max(1, |.|max).  A free-running
+device trajectory from the initial state is compared at `total` steps with the per-scene tolerance below
+(contact-dense scenes amplify last-bit differences of the sweep; the joint-only / single-contact scenes stay tight).
+"""
+import numpy as np
+import pytest
+
+from golden_lib import SCENE_KW, contacts, load, state
+from gpu_helpers import assert_bit_equal, context_from_oracles
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+# |x_gpu - x_ref|max after `total` free-running steps
+TRAJ_TOL = {"marble_box": 2e-2, "marble_box_n": 2e-2, "sphere_on_box": 1e-4, "cylinder_on_plane": 2e-3,
+            "car": 5e-3, "swinging_boxes": 5e-2, "sphere_stack": 1e-3}
+
+
+@pytest.mark.parametrize("scene", sorted(SCENE_KW))
+def test_one_step_from_reference_checkpoints(scene):
+    g = load(scene)
+    dt = float(g["dt"])
+    cps = [int(k) for k in g["checkpoints"]]
+    builders = [Oracle(scene, **SCENE_KW[scene]) for _ in cps]          # scene tables only (masses, shapes, joints)
+    ctx = context_from_oracles(builders, max_contacts=1024)
+    pre = [state(g, f"pre_{k}") for k in cps]
+    ctx.upload_state(*[np.stack([p[key] for p in pre]) for key in ("x", "q", "v", "w")])
+    if builders[0].n_joints:
+        ctx.set_joint_lambda(np.stack([g[f"pre_{k}_jlam"] for k in cps]))
+    ctx.step(dt, 1); ctx.sync()
+    counts, gs = ctx.contact_counts(), ctx.download_state()
+    for s, k in enumerate(cps):
+        ref = contacts(g, k)
+        assert counts[s] == ref["body0"].size, (scene, k, counts[s], ref["body0"].size)
+        if counts[s]:
+            c = ctx.contacts(s)
+            np.testing.assert_array_equal(c["body0"], ref["body0"]); np.testing.assert_array_equal(c["body1"], ref["body1"])
+            for key in ("p", "n", "phi"):
+                assert_bit_equal(c[key], ref[key], f"{scene} step {k + 1} contact {key}")
+            scale = max(float(np.abs(ref["lam"]).max()), 1e-3)
+            np.testing.assert_allclose(c["lam"], ref["lam"], rtol=0, atol=1e-4 * scale + 1e-6)
+        post = state(g, f"post_{k}")
+        for key, tol in (("x", 2e-6), ("q", 2e-6), ("v", 2e-4), ("w", 2e-4)):
+            np.testing.assert_allclose(gs[key][s], post[key], rtol=0, atol=tol * max(1.0, float(np.abs(post[key]).max())),
+                                       err_msg=f"{scene} post {k} {key}")
+    ctx.close()
+
+
+@pytest.mark.parametrize("scene", sorted(SCENE_KW))
+def test_free_running_trajectory(scene):
+    g = load(scene)
+    o = Oracle(scene, **SCENE_KW[scene])
+    ctx = context_from_oracles([o], max_contacts=1024)
+    ctx.step(float(g["dt"]), int(g["total"])); ctx.sync()
+    gs, fin = ctx.download_state(), state(g, "final")
+    assert np.abs(gs["x"][0] - fin["x"]).max() < TRAJ_TOL[scene], (scene, np.abs(gs["x"][0] - fin["x"]).max())
+    ctx.close()
