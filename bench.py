@@ -11,11 +11,13 @@ shard the batch by scene index with no data-path collective (weak scaling: fixed
 Prints ONE JSON line (rank 0). Keys beyond the base contract:
   roofline      the PGS sweep kernel (dominant): algorithmic bytes (464 B / contact visit, 744 B / hinge
                 visit) / its CUDA-event duration, against the measured HBM copy peak
-  cpu_baseline  the restated reference (oracle/) timed single-threaded on this box's host CPU
+  cpu_baseline  the reference's own sources (oracle/_ref: compiled unmodified against the Eigen API shim,
+                kind "reference"; the C restatement, kind "port", only if that build is absent) timed
+                single-threaded on this box's host CPU
   e2e           the same metric through the C ABI with HOST buffers: every step uploads x,q,v,omega
                 of every body from pinned host memory and downloads them again
-The --impl reference arm times the restated reference (the upstream binary cannot be built here:
-it needs Eigen + Polyscope from the network) on all host cores, one independent scene per process.
+The --impl reference arm times the same CPU implementation on all host cores, one independent scene per
+process (the reference is single-threaded and keeps process-wide solver state).
 """
 import argparse
 import json
@@ -233,8 +235,12 @@ def run_ours(args):
 
 # ---- CPU legs: the only place bench.py touches oracle/ -------------------------------------------
 def _oracle_system(workload, seed, settle):
+    """One CPU scene of the workload, settled.  Returns (system, kind): the reference's own sources
+    (oracle/_ref, kind "reference") when that library is present, else the C restatement (kind "port").
+    The settle always runs on the restatement (it is bit-identical to oracle/_ref, tests/test_ref_vs_oracle.py,
+    and ~2x faster); the settled state is then handed to the system that gets timed."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_lib import Oracle
+    from oracle_lib import Oracle, Reference, ref_available
     scene, abc, _, _, _, jitter = WORKLOADS[workload]
     kw = {"k": abc[0]} if scene == "sphere_stack" else ({"nx": abc[0], "nz": abc[1], "ny": abc[2]} if scene == "marble_box_n" else {})
     o = Oracle(scene, **kw)
@@ -246,27 +252,37 @@ def _oracle_system(workload, seed, settle):
         o.set_state(**st)
     o.set_params(MU, 0, SOLVER_ITERS, True)
     o.step(DT, settle)
-    return o
+    if not ref_available():
+        return o, "port"
+    r = Reference(scene, **kw)
+    r.set_params(MU, 0, SOLVER_ITERS, True)
+    r.set_state(**o.state())
+    if o.n_joints:
+        r.set_joint_lambda(o.joint_rows()["lam"])
+    r.step(DT, 1)                                           # builds its contact list
+    return r, "reference"
 
 
 def cpu_baseline_single(workload, settle, budget_s=12.0):
-    """Restated reference, one thread, one scene of the same workload; bounded to ~budget_s."""
-    o = _oracle_system(workload, 1234, settle)
+    """The reference's CPU implementation, one thread, one scene of the same workload; bounded to ~budget_s."""
+    o, kind = _oracle_system(workload, 1234, settle)
     n, t = 0, 0.0
-    chunk = 50
+    chunk = 10
     while t < budget_s:
         t += o.time_steps(DT, chunk); n += chunk
     cores = os.cpu_count()
-    return {"value": o.n_bodies * n / t, "unit": "body-steps/s", "cores": 1, "kind": "port",
+    what = ("reference sources compiled against the Eigen API shim (oracle/_ref)" if kind == "reference"
+            else "C restatement of the reference (oracle/_ref not built)")
+    return {"value": o.n_bodies * n / t, "unit": "body-steps/s", "cores": 1, "kind": kind,
             "sample": f"1 scene of {workload} ({o.n_bodies} bodies, {o.n_contacts} contacts), {n} steps after a {settle}-step settle, "
-                      f"single thread like the reference; host has {cores} logical cores"}
+                      f"single thread like the reference; {what}; host has {cores} logical cores"}
 
 
 def _ref_worker(job):
     workload, seed, settle, steps = job
-    o = _oracle_system(workload, seed, settle)
-    o.time_steps(DT, 5)
-    return o.time_steps(DT, steps), o.n_bodies
+    o, kind = _oracle_system(workload, seed, settle)
+    o.time_steps(DT, 2)
+    return o.time_steps(DT, steps), o.n_bodies, kind
 
 
 def run_reference(args):
@@ -277,7 +293,7 @@ def run_reference(args):
     workload = args.workload
     settle = WORKLOADS[workload][4]
     cores = os.cpu_count() or 1
-    sub = {"marble_box": 40, "marble_box_1k": 5}.get(workload, 2000)    # oracle steps per worker per bench step
+    sub = {"marble_box": 20, "marble_box_1k": 2}.get(workload, 1000)    # CPU steps per worker per bench step
     total = sub * (args.steps + args.warmup)
     with ProcessPoolExecutor(max_workers=cores) as ex:
         t0 = time.perf_counter()
@@ -293,8 +309,10 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{workload} x {B} scenes/GPU", "scenes_per_gpu": B, "bodies_per_scene": nb, "dt": DT,
                    "solver": "Box-PGS", "solver_iters": SOLVER_ITERS, "mu": MU},
-        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores} independent scenes of {workload}, one process per logical core, {sub} reference steps per "
+        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": res[0][2],
+                         "sample": f"{cores} independent scenes of {workload}, one process per logical core ("
+                                   + ("reference sources + Eigen API shim, oracle/_ref" if res[0][2] == "reference" else "C restatement")
+                                   + f"), {sub} reference steps per "
                                    f"bench step ({total} per scene) after a {settle}-step settle; wall {wall:.1f} s incl. settle"},
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

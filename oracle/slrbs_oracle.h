@@ -9,13 +9,21 @@
  * --impl reference legs may load this library.  The product path
  * (slrbs_b200/csrc, slrbs_b200/host) never links or calls it.
  *
- * PARITY STATUS: "parity unpinned by reference tests".  The reference ships no
- * tests, golden vectors or fixtures and cannot be built
- * here (needs Eigen 3.4 + Polyscope via network FetchContent, CMakeLists.txt:15-33),
- * so there is no oracle/_ref.  What pins this restatement instead:
- *   (1) line-by-line fidelity to the cited reference lines,
- *   (2) the known answers of SURVEY.md Appendix B (tests/test_oracle_known_answers.py),
- *   (3) analytic invariants (free fall, momentum, hinge phi -> 0).
+ * PARITY STATUS: pinned against the reference's own code, with one stated gap.
+ * The reference ships no tests, golden vectors or fixtures and its
+ * build system cannot run here (Eigen 3.4 + Polyscope come from network FetchContent,
+ * CMakeLists.txt:15-33).  Instead, oracle/Makefile (target `ref`) compiles the reference's
+ * UNMODIFIED step-path sources, where they lie under /root/reference, against an Eigen *API
+ * shim* (oracle/ref_shim/Eigen/Dense) into oracle/_ref/libslrbs_ref.so, and
+ * tests/test_ref_vs_oracle.py shows this restatement equal to that build BIT FOR BIT: states,
+ * contact lists (pairs, order, p, n, t, b, pene, lambda), Jacobian rows and joint impulses, on
+ * all five Scenarios.h scenes, two synthetic scenes, random piles, Box-PGS / CG / CR,
+ * save/restore and the pre-step force hook.  tests/golden/ref_*.npz are outputs of that build
+ * (tests/golden/make_golden.py) and travel to the GPU box.
+ * THE GAP: Eigen itself is absent, so the summation orders INSIDE Eigen calls (listed below)
+ * are shared assumptions of the shim and of this file, not observations of Eigen 3.4.  They
+ * decide last-bit rounding only.  The known answers of SURVEY.md Appendix B
+ * (tests/test_oracle_known_answers.py) and analytic invariants remain as independent checks.
  *
  * Third-party arithmetic restated: Eigen, tag 3.4 (CMakeLists.txt:24-33, not
  * vendored).  Operation orders chosen (documented in slrbs_oracle.c "eig_*"):

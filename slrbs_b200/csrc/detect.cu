@@ -12,6 +12,7 @@
 //     can touch (hash collisions only add candidates): the emitted contact list is identical.
 // k_detect_serial      one thread per scene, for scenes of a few bodies (a car has 15 pairs).
 #include "kernels.cuh"
+#include <cstdlib>
 #include "narrowphase.cuh"
 
 namespace slrbs {
@@ -451,6 +452,211 @@ __global__ void __launch_bounds__(DETECT_CTA_THREADS, 2) k_detect_cta(View v, in
     if (tid == 0) v.ncontacts[scene] = s_total < v.NC ? s_total : v.NC;
 }
 
+// ------------------------------------------------------------------------------------
+// k_detect_rows  one CTA per scene, one THREAD per sphere row. After the grid is built in shared memory, thread i
+// walks the 27 neighbouring cells of sphere i and the non-sphere bodies itself, keeps the partners j > i that touch
+// in a short ascending list in shared memory (16-bit indices, repeated partners from colliding buckets dropped),
+// and the row's contact count. Rows of non-sphere bodies, and sphere rows with more than ROW_HITS partners, are
+// walked by a warp each in the reference's all-pairs order (dense_row). A block scan turns the counts into output
+// offsets, then every thread re-evaluates its few touching pairs and writes them: the list is in the reference's
+// lexicographic (i, j) order with no sorting of candidates, no per-row barriers and all 32 lanes testing pairs.
+// Every sphere-row partner yields exactly one contact (sphere-sphere, sphere-box; CollisionDetect.cpp:102-150).
+// ------------------------------------------------------------------------------------
+enum { ROW_HITS = 16, ROW_DENSE = 0xFF };
+
+__host__ __device__ inline size_t detect_rows_smem_bytes(int NB, int H)
+{
+    // sp | sf, rowoff[NB+1], cell_start[H+2], cell_items, special, dense_list | hits u16[NB][ROW_HITS] | nh u8[NB]
+    return (size_t)NB * 16 + ((size_t)NB * 5 + H + 8) * 4 + (size_t)NB * ROW_HITS * 2 + (((size_t)NB + 15) & ~(size_t)15);
+}
+
+__global__ void __launch_bounds__(512) k_detect_rows(View v, int H)
+{
+    extern __shared__ float4 smem4[];
+    __shared__ int s_rmax, s_nspecial, s_ndense, s_warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x, W = T >> 5;
+    const int scene = blockIdx.x;
+    DetectSmem sm;
+    sm.sp = smem4;
+    int* ip = reinterpret_cast<int*>(smem4 + v.NB);
+    sm.sf = ip; ip += v.NB;
+    int* rowoff = ip; ip += v.NB + 1;
+    sm.cell_start = ip; ip += H + 2;
+    sm.cell_items = ip; ip += v.NB;
+    sm.special = ip; ip += v.NB;
+    int* dense_list = ip; ip += v.NB;
+    unsigned short* hits = reinterpret_cast<unsigned short*>(ip);
+    unsigned char* nhits = reinterpret_cast<unsigned char*>(hits + (size_t)v.NB * ROW_HITS);
+
+    const int n = v.nbodies[scene];
+    if (tid == 0) { s_rmax = 0; s_nspecial = 0; s_ndense = 0; }
+    for (int c = tid; c <= H + 1; c += T) sm.cell_start[c] = 0;
+    __syncthreads();
+    float rmax = 0.f;
+    for (int b = tid; b < n; b += T) {
+        const size_t i = at(v, b, scene);
+        const float4 c = v.cproxy[i];
+        const int f = v.flags[i];
+        sm.sp[b] = c; sm.sf[b] = f;
+        if ((f & FLAG_TYPE_MASK) == GEOM_SPHERE) rmax = fmaxf(rmax, c.w);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, d));
+    if (lane == 0) atomicMax(&s_rmax, __float_as_int(rmax));    // radii are >= 0: integer order = float order
+    __syncthreads();
+    const float inv_h = 1.0f / (2.0f * __int_as_float(s_rmax) + 2e-3f);
+    const int Hmask = H - 1;
+    // bucket counts; non-sphere bodies listed in ascending order by warp 0
+    for (int b = tid; b < n; b += T) {
+        if ((sm.sf[b] & FLAG_TYPE_MASK) == GEOM_SPHERE) {
+            const float4 c = sm.sp[b];
+            atomicAdd(&sm.cell_start[cell_hash((int)floorf(c.x * inv_h), (int)floorf(c.y * inv_h), (int)floorf(c.z * inv_h), Hmask) + 1], 1);
+        }
+    }
+    if (warp == 0) {
+        int ns = 0;
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            const int b = b0 + lane;
+            const bool spec = b < n && (sm.sf[b] & FLAG_TYPE_MASK) != GEOM_SPHERE;
+            const unsigned m = __ballot_sync(0xffffffffu, spec);
+            if (spec) { const int k = ns + __popc(m & ((1u << lane) - 1u)); sm.special[k] = b; dense_list[k] = b; }
+            ns += __popc(m);
+        }
+        if (lane == 0) { s_nspecial = ns; s_ndense = ns; }
+    }
+    __syncthreads();
+    if (warp == 0) {                                             // inclusive scan: cell_start[c] = end of bucket c-1
+        int carry = 0;
+        for (int c0 = 1; c0 <= H; c0 += 32) {
+            const int c = c0 + lane;
+            int incl = c <= H ? sm.cell_start[c] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (c <= H) sm.cell_start[c] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) sm.cell_start[H + 1] = carry;
+    }
+    __syncthreads();
+    // fill backwards: afterwards cell_start[h+1] = begin of bucket h, cell_start[h+2] = its end (bucket H-1 ends at nsph)
+    for (int b = tid; b < n; b += T) {
+        if ((sm.sf[b] & FLAG_TYPE_MASK) == GEOM_SPHERE) {
+            const float4 c = sm.sp[b];
+            const int h = cell_hash((int)floorf(c.x * inv_h), (int)floorf(c.y * inv_h), (int)floorf(c.z * inv_h), Hmask);
+            sm.cell_items[atomicSub(&sm.cell_start[h + 1], 1) - 1] = b;
+        }
+    }
+    __syncthreads();
+    const int nspecial = s_nspecial;
+
+    // ---- pass 1: one thread per sphere row -------------------------------------------------------------------------
+    for (int i = tid; i < n; i += T) {
+        const int fi = sm.sf[i];
+        if ((fi & FLAG_TYPE_MASK) != GEOM_SPHERE) { nhits[i] = ROW_DENSE; continue; }
+        const float4 ci = sm.sp[i];
+        unsigned short* my = hits + (size_t)i * ROW_HITS;
+        int nh = 0;
+        bool over = false;
+        const int ix = (int)floorf(ci.x * inv_h), iy = (int)floorf(ci.y * inv_h), iz = (int)floorf(ci.z * inv_h);
+        // cell_hash(ix+dx, iy+dy, iz+dz) from per-axis partial products
+        const unsigned hx0 = (unsigned)(ix - 1) * 73856093u, hx1 = (unsigned)ix * 73856093u, hx2 = (unsigned)(ix + 1) * 73856093u;
+#pragma unroll 1
+        for (int cc = 0; cc < 27; ++cc) {
+            const int dy = (cc / 3) % 3, dz = cc / 9, dx = cc - 3 * (cc / 3);
+            const unsigned hyz = ((unsigned)(iy + dy - 1) * 19349663u) ^ ((unsigned)(iz + dz - 1) * 83492791u);
+            const int h = (int)(((dx == 0 ? hx0 : (dx == 1 ? hx1 : hx2)) ^ hyz) & (unsigned)Hmask);
+            const int beg = sm.cell_start[h + 1], end = sm.cell_start[h + 2];
+            for (int k = beg; k < end; ++k) {
+                const int j = sm.cell_items[k];
+                if (j <= i) continue;
+                // the grid holds spheres only: the touch test of collisionDetectSphereSphere (CollisionDetect.cpp:111-115,
+                // same expressions as sphere_sphere(), so the same decision to the bit) without building the contact
+                const float4 cj = sm.sp[j];
+                if ((fi & sm.sf[j]) & FLAG_FIXED) continue;
+                const V3 vec = mk3(ci) - mk3(cj);
+                const float sq = sqnorm(vec), lim = (ci.w + cj.w) + 1e-3f;
+                if (sq > 1.0001f * (lim * lim)) continue;        // cannot pass the exact test below
+                if (!(sqrtf(sq) < lim)) continue;
+                int pos = nh;                                    // sorted insert, repeated partner dropped
+                while (pos > 0 && my[pos - 1] > j) --pos;
+                if (pos > 0 && my[pos - 1] == j) continue;
+                if (nh == ROW_HITS) { over = true; break; }
+                for (int m = nh; m > pos; --m) my[m] = my[m - 1];
+                my[pos] = (unsigned short)j;
+                ++nh;
+            }
+            if (over) break;
+        }
+        for (int k = 0; k < nspecial && !over; ++k) {
+            const int j = sm.special[k];
+            if (j <= i) continue;
+            PairOut o;
+            test_pair(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
+            if (o.cnt == 0) continue;
+            if (nh == ROW_HITS) { over = true; break; }
+            int pos = nh;
+            while (pos > 0 && my[pos - 1] > j) --pos;
+            for (int m = nh; m > pos; --m) my[m] = my[m - 1];
+            my[pos] = (unsigned short)j;
+            ++nh;
+        }
+        if (over) { nhits[i] = ROW_DENSE; dense_list[atomicAdd(&s_ndense, 1)] = i; }
+        else { nhits[i] = (unsigned char)nh; rowoff[i] = nh; }
+    }
+    __syncthreads();
+    // ---- dense rows (non-sphere bodies, overfull sphere rows): one warp per row, all j > i ---------------------------
+    const int ndense = s_ndense;
+    for (int k = warp; k < ndense; k += W) {
+        const int i = dense_list[k];
+        const int c = dense_row<false>(v, sm, scene, lane, i, n, 0);
+        if (lane == 0) rowoff[i] = c;
+    }
+    __syncthreads();
+    // ---- exclusive block scan of the row counts ----------------------------------------------------------------------
+    {
+        const int per = (n + T - 1) / T;
+        const int r0 = min(tid * per, n), r1 = min(r0 + per, n);
+        int sum = 0;
+        for (int r = r0; r < r1; ++r) sum += rowoff[r];
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int w2 = 0; w2 < warp; ++w2) base += s_warp_tot[w2];
+        int run = base + incl - sum;
+        for (int r = r0; r < r1; ++r) { const int c = rowoff[r]; rowoff[r] = run; run += c; }
+        if (tid == T - 1) rowoff[n] = run;
+        __syncthreads();
+    }
+    // ---- pass 2: write ---------------------------------------------------------------------------------------------------
+    for (int i = tid; i < n; i += T) {
+        const int nh = nhits[i];
+        if (nh == ROW_DENSE) continue;
+        const float4 ci = sm.sp[i];
+        const int fi = sm.sf[i];
+        const int base = rowoff[i];
+        for (int k = 0; k < nh; ++k) {
+            const int j = hits[(size_t)i * ROW_HITS + k];
+            PairOut o;
+            test_pair(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
+            write_contacts(v, scene, base + k, o);
+        }
+    }
+    for (int k = warp; k < ndense; k += W) {
+        const int i = dense_list[k];
+        dense_row<true>(v, sm, scene, lane, i, n, rowoff[i]);
+    }
+    if (tid == 0) { const int tot = rowoff[n]; v.ncontacts[scene] = tot < v.NC ? tot : v.NC; }
+}
+
 // scenes of a few bodies: one thread per scene walks the pairs
 __global__ void __launch_bounds__(128) k_detect_serial(View v)
 {
@@ -488,14 +694,24 @@ void init_detect_kernels()
     cudaFuncSetAttribute(k_detect_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_detect_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_detect_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_detect_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+// SLRBS_DETECT_ROWS=0 disables the thread-per-row kernel (A/B against the warp-per-row kernels)
+static bool use_rows_kernel(const View& v, bool grid, int H)
+{
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("SLRBS_DETECT_ROWS"); enabled = e ? atoi(e) : 1; }
+    return enabled && grid && v.NB >= 128 && v.NB <= 65535 && detect_rows_smem_bytes(v.NB, H) <= 200 * 1024;
 }
 
 // name of the kernel launch_detect() picks (same decision tree), for slrbs_describe
 const char* detect_variant(const View& v, int broadphase)
 {
-    const bool grid = broadphase > 0 || (broadphase < 0 && v.NB >= 512);
+    const bool grid = broadphase > 0 || (broadphase < 0 && v.NB >= 128);
     int H = 64;
     while (H < v.NB && H < 4096) H <<= 1;
+    if (use_rows_kernel(v, grid, H)) return "k_detect_rows";
     const size_t cta_smem = (size_t)v.NB * 16 + detect_cta_smem_ints(v.NB, grid, H, DETECT_CTA_THREADS / 32) * 4;
     if (((v.NB >= 512 && v.B <= 4096) || (v.NB >= 128 && v.B <= 512)) && cta_smem <= 200 * 1024)
         return grid ? "k_detect_cta<grid>" : "k_detect_cta<all-pairs>";
@@ -509,9 +725,17 @@ const char* detect_variant(const View& v, int broadphase)
 void launch_detect(const View& v, int broadphase, cudaStream_t s)
 {
     // broadphase: 0 = off (all pairs), 1 = hashed grid, -1 = auto (grid for scenes of >= 512 bodies)
-    const bool grid = broadphase > 0 || (broadphase < 0 && v.NB >= 512);
+    const bool grid = broadphase > 0 || (broadphase < 0 && v.NB >= 128);
     int H = 64;
     while (H < v.NB && H < 4096) H <<= 1;
+    // scenes of >= 128 bodies: one CTA per scene, one thread per sphere row
+    if (use_rows_kernel(v, grid, H)) {
+        static int forced = -1;
+        if (forced < 0) { const char* e = getenv("SLRBS_DETECT_THREADS"); forced = e ? atoi(e) : 0; }
+        const int threads = forced ? forced : (v.NB >= 512 ? 512 : (v.NB >= 256 ? 256 : 128));
+        k_detect_rows<<<(unsigned)v.B, threads, detect_rows_smem_bytes(v.NB, H), s>>>(v, H);
+        return;
+    }
     // big scenes in a batch too small to fill the GPU with one warp per scene: one CTA (16 warps) per scene
     const size_t cta_smem = (size_t)v.NB * 16 + detect_cta_smem_ints(v.NB, grid, H, DETECT_CTA_THREADS / 32) * 4;
     if (((v.NB >= 512 && v.B <= 4096) || (v.NB >= 128 && v.B <= 512)) && cta_smem <= 200 * 1024) {
