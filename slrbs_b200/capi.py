@@ -24,7 +24,8 @@ SYMBOLS = [
     "slrbs_download_joint_lambda", "slrbs_upload_joint_lambda", "slrbs_download_body_dyn",
     "slrbs_save_state", "slrbs_restore_state", "slrbs_profile_enable", "slrbs_profile_read",
     "slrbs_timer_start", "slrbs_timer_stop", "slrbs_halo_set_local", "slrbs_halo_set_remote", "slrbs_halo_sync_local",
-    "slrbs_halo_pack", "slrbs_halo_unpack",
+    "slrbs_halo_pack", "slrbs_halo_unpack", "slrbs_pile_init", "slrbs_pile_export", "slrbs_pile_rebuild",
+    "slrbs_pile_requests", "slrbs_pile_set_send", "slrbs_pile_scene_keys",
 ]
 
 
@@ -82,6 +83,12 @@ def load_library():
     L.slrbs_halo_sync_local.argtypes = [vp]
     L.slrbs_halo_pack.argtypes = [vp, C.c_void_p]
     L.slrbs_halo_unpack.argtypes = [vp, C.c_void_p]
+    L.slrbs_pile_init.argtypes = [vp, C.c_int, fp, fp, fp, C.c_float, C.c_float, ip, C.c_int, C.c_int, C.c_int, fp]
+    L.slrbs_pile_export.argtypes = [vp, C.c_void_p, C.c_void_p]
+    L.slrbs_pile_rebuild.argtypes = [vp, C.c_void_p, ip]
+    L.slrbs_pile_requests.argtypes = [vp, C.c_void_p]
+    L.slrbs_pile_set_send.argtypes = [vp, C.c_void_p, C.c_int]
+    L.slrbs_pile_scene_keys.argtypes = [vp, C.c_int, C.c_int, ip]
     L.slrbs_timer_start.argtypes = [vp]
     L.slrbs_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.slrbs_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double),
@@ -302,6 +309,34 @@ class Context:
     def halo_sync_local(self): self._ck(self.L.slrbs_halo_sync_local(self.h))
     def halo_pack(self, device_ptr): self._ck(self.L.slrbs_halo_pack(self.h, C.c_void_p(device_ptr)))
     def halo_unpack(self, device_ptr): self._ck(self.L.slrbs_halo_unpack(self.h, C.c_void_p(device_ptr)))
+
+    # -- one large pile re-partitioned on the device --------------------------------
+    def pile_init(self, radius, mass, origin, block, halo_w, ncell, cx0, cx1, fixed10):
+        r = np.ascontiguousarray(np.asarray(radius, np.float32)); m = np.ascontiguousarray(np.asarray(mass, np.float32))
+        o = np.ascontiguousarray(np.asarray(origin, np.float32)); nc = np.ascontiguousarray(np.asarray(ncell, np.int32))
+        f = np.ascontiguousarray(np.asarray(fixed10, np.float32).reshape(-1, 10))
+        self._ck(self.L.slrbs_pile_init(self.h, r.size, _f(r), _f(m), _f(o), float(block), float(halo_w), _i(nc), int(cx0), int(cx1),
+                                        f.shape[0], _f(f) if f.shape[0] else None))
+
+    def pile_export(self, table_ptr, vmax2_ptr):
+        self._ck(self.L.slrbs_pile_export(self.h, C.c_void_p(table_ptr), C.c_void_p(vmax2_ptr)))
+
+    def pile_rebuild(self, table_ptr):
+        """Returns info8; raises SlrbsError on capacity overflow (info8 is then in self.pile_info)."""
+        info = np.zeros(8, np.int32)
+        self.pile_info = info
+        self._ck(self.L.slrbs_pile_rebuild(self.h, C.c_void_p(table_ptr), _i(info)))
+        return info
+
+    def pile_requests(self, gids_ptr): self._ck(self.L.slrbs_pile_requests(self.h, C.c_void_p(gids_ptr)))
+    def pile_set_send(self, gids_ptr, n): self._ck(self.L.slrbs_pile_set_send(self.h, C.c_void_p(gids_ptr), int(n)))
+
+    def pile_scene_keys(self, scene):
+        out = np.zeros(self.max_bodies, np.int32)
+        n = self.L.slrbs_pile_scene_keys(self.h, int(scene), out.size, _i(out))
+        if n < 0:
+            self._ck(n)
+        return out[:n]
 
     # -- measurement ---------------------------------------------------------------
     def profile_enable(self, on=True):

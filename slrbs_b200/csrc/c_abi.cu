@@ -51,6 +51,17 @@ struct slrbs_ctx {
     // halo maps (device copies of the index lists)
     int *halo_src = nullptr, *halo_dst = nullptr, *halo_send = nullptr, *halo_recv = nullptr;
     int n_halo_local = 0, n_halo_send = 0, n_halo_recv = 0;
+    bool halo_borrowed = false;                 // the four lists above point into the pile's buffers (not freed singly)
+    // one large pile re-partitioned on the device (pile.cu)
+    struct {
+        bool on = false;
+        PileGrid g{};
+        float *radius = nullptr, *mass = nullptr, *fixed10 = nullptr;
+        int *count = nullptr, *keys = nullptr, *loc = nullptr, *info = nullptr;
+        int *hsrc = nullptr, *hdst = nullptr, *ldst = nullptr, *lgid = nullptr, *rdst = nullptr, *rgid = nullptr, *recv = nullptr;
+        int *send = nullptr; int send_cap = 0;
+        int n_left = 0, n_right = 0;
+    } pile;
 };
 
 namespace {
@@ -187,6 +198,7 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     CU(cudaSetDevice(device));
     init_detect_kernels();
     init_level_kernels();
+    init_pile_kernels();
     slrbs_ctx* c = new slrbs_ctx();
     { const char* g = std::getenv("SLRBS_GRAPH"); if (g) c->use_graph = std::atoi(g); }
     c->device = device;
@@ -242,7 +254,8 @@ void slrbs_destroy(slrbs_ctx* c)
     if (c->stage) cudaFree(c->stage);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->graph) cudaGraphExecDestroy(c->graph);
-    cudaFree(c->halo_src); cudaFree(c->halo_dst); cudaFree(c->halo_send); cudaFree(c->halo_recv);
+    if (!c->halo_borrowed) { cudaFree(c->halo_src); cudaFree(c->halo_dst); cudaFree(c->halo_send); cudaFree(c->halo_recv); }
+    if (c->pile.send) cudaFree(c->pile.send);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
@@ -610,6 +623,7 @@ static int set_index_list(slrbs_ctx* c, int** dev, int* count, int n, const int3
     for (int i = 0; i < n; ++i)
         if (host[i] < 0 || host[i] >= limit) return fail(SLRBS_E_ARG, std::string(what) + ": flat body index out of range");
     CU(cudaStreamSynchronize(c->stream));
+    if (c->halo_borrowed) { c->halo_src = c->halo_dst = c->halo_send = c->halo_recv = nullptr; c->halo_borrowed = false; }
     if (*dev) { CU(cudaFree(*dev)); *dev = nullptr; }
     *count = 0;
     if (n > 0) {
@@ -663,6 +677,124 @@ int slrbs_halo_unpack(slrbs_ctx* c, const void* device_buffer)
     CU(cudaSetDevice(c->device));
     launch_halo_unpack(c->v, c->n_halo_recv, c->halo_recv, (const float*)device_buffer, c->stream);
     return check_launch(c);
+}
+
+// ---- one large pile, re-partitioned on the device (pile.cu) ----------------------------------------------------------
+int slrbs_pile_init(slrbs_ctx* c, int n_global, const float* radius, const float* mass, const float* origin3, float block,
+                    float halo_w, const int32_t* ncell3, int cx0, int cx1, int n_fixed, const float* fixed10)
+{
+    if (!c || n_global <= 0 || !radius || !mass || !origin3 || !ncell3 || block <= 0.f || halo_w < 0.f || halo_w > block ||
+        n_fixed < 0 || (n_fixed > 0 && !fixed10) || cx0 < 0 || cx1 <= cx0 || cx1 > ncell3[0] || n_global > (1 << 29))
+        return fail(SLRBS_E_ARG, "slrbs_pile_init: bad argument");
+    if ((int64_t)(cx1 - cx0) * ncell3[1] * ncell3[2] != c->v.B)
+        return fail(SLRBS_E_ARG, "slrbs_pile_init: the context must hold one scene per owned block ((cx1-cx0)*ncy*ncz)");
+    if (c->v.NB <= n_fixed) return fail(SLRBS_E_ARG, "slrbs_pile_init: max_bodies must exceed the number of fixed bodies");
+    if (c->pile.on) return fail(SLRBS_E_ARG, "slrbs_pile_init: already initialised for this context");
+    CU(cudaSetDevice(c->device));
+    auto& P = c->pile;
+    P.g.ox = origin3[0]; P.g.oy = origin3[1]; P.g.oz = origin3[2]; P.g.block = block; P.g.halo_w = halo_w;
+    P.g.ncx = ncell3[0]; P.g.ncy = ncell3[1]; P.g.ncz = ncell3[2]; P.g.cx0 = cx0; P.g.cx1 = cx1;
+    P.g.nfixed = n_fixed; P.g.nbdyn = c->v.NB - n_fixed; P.g.n_global = n_global;
+    if (pile_sort_smem(P.g.nbdyn) > 128 * 1024) return fail(SLRBS_E_ARG, "slrbs_pile_init: more than 32768 dynamic bodies per block");
+    const size_t slots = (size_t)c->v.B * P.g.nbdyn;
+    int r;
+    if ((r = dalloc(c, &P.radius, (size_t)n_global)) || (r = dalloc(c, &P.mass, (size_t)n_global)) ||
+        (r = dalloc(c, &P.fixed10, (size_t)10 * (n_fixed ? n_fixed : 1))) || (r = dalloc(c, &P.count, (size_t)c->v.B)) ||
+        (r = dalloc(c, &P.keys, slots)) || (r = dalloc(c, &P.loc, (size_t)n_global)) || (r = dalloc(c, &P.info, 8)) ||
+        (r = dalloc(c, &P.hsrc, slots)) || (r = dalloc(c, &P.hdst, slots)) || (r = dalloc(c, &P.ldst, slots)) ||
+        (r = dalloc(c, &P.lgid, slots)) || (r = dalloc(c, &P.rdst, slots)) || (r = dalloc(c, &P.rgid, slots)) ||
+        (r = dalloc(c, &P.recv, slots)))
+        return r;
+    CU(cudaMemcpyAsync(P.radius, radius, sizeof(float) * (size_t)n_global, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(P.mass, mass, sizeof(float) * (size_t)n_global, cudaMemcpyHostToDevice, c->stream));
+    if (n_fixed) CU(cudaMemcpyAsync(P.fixed10, fixed10, sizeof(float) * 10 * (size_t)n_fixed, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    P.on = true;
+    return 0;
+}
+
+int slrbs_pile_export(slrbs_ctx* c, void* d_table, void* d_vmax2)
+{
+    if (!c || !c->pile.on || !d_table || !d_vmax2) return fail(SLRBS_E_ARG, "slrbs_pile_export: bad argument");
+    CU(cudaSetDevice(c->device));
+    launch_pile_export(c->v, c->pile.g, c->pile.count, c->pile.keys, (float*)d_table, (unsigned*)d_vmax2, c->stream);
+    return check_launch(c);
+}
+
+int slrbs_pile_rebuild(slrbs_ctx* c, const void* d_table, int32_t* info8)
+{
+    if (!c || !c->pile.on || !d_table || !info8) return fail(SLRBS_E_ARG, "slrbs_pile_rebuild: bad argument");
+    CU(cudaSetDevice(c->device));
+    auto& P = c->pile;
+    launch_pile_rebuild(c->v, P.g, (const float*)d_table, P.radius, P.mass, P.fixed10, P.count, P.keys, P.loc, P.info,
+                        P.hsrc, P.hdst, P.ldst, P.lgid, P.rdst, P.rgid, c->stream);
+    int r;
+    if ((r = check_launch(c, 4))) return r;
+    CU(cudaMemcpyAsync(info8, P.info, sizeof(int) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (!c->halo_borrowed) {
+        cudaFree(c->halo_src); cudaFree(c->halo_dst); cudaFree(c->halo_send); cudaFree(c->halo_recv);
+        c->halo_send = nullptr; c->n_halo_send = 0;
+    }
+    c->halo_borrowed = true;
+    c->halo_src = P.hsrc; c->halo_dst = P.hdst; c->n_halo_local = info8[0] ? 0 : info8[2];
+    P.n_left = info8[3]; P.n_right = info8[4];
+    if (P.n_left) CU(cudaMemcpyAsync(P.recv, P.ldst, sizeof(int) * (size_t)P.n_left, cudaMemcpyDeviceToDevice, c->stream));
+    if (P.n_right) CU(cudaMemcpyAsync(P.recv + P.n_left, P.rdst, sizeof(int) * (size_t)P.n_right, cudaMemcpyDeviceToDevice, c->stream));
+    c->halo_recv = P.recv; c->n_halo_recv = info8[0] ? 0 : P.n_left + P.n_right;
+    c->halo_send = P.send; c->n_halo_send = 0;                  // until slrbs_pile_set_send
+    c->joints_dirty = true;
+    return info8[0] ? fail(SLRBS_E_CAPACITY, "slrbs_pile_rebuild: a block holds more bodies than max_bodies") : 0;
+}
+
+int slrbs_pile_requests(slrbs_ctx* c, void* d_gids_out)
+{
+    if (!c || !c->pile.on || (!d_gids_out && c->pile.n_left + c->pile.n_right > 0)) return fail(SLRBS_E_ARG, "slrbs_pile_requests: bad argument");
+    CU(cudaSetDevice(c->device));
+    auto& P = c->pile;
+    int* o = (int*)d_gids_out;
+    if (P.n_left) CU(cudaMemcpyAsync(o, P.lgid, sizeof(int) * (size_t)P.n_left, cudaMemcpyDeviceToDevice, c->stream));
+    if (P.n_right) CU(cudaMemcpyAsync(o + P.n_left, P.rgid, sizeof(int) * (size_t)P.n_right, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slrbs_pile_set_send(slrbs_ctx* c, const void* d_gids, int n)
+{
+    if (!c || !c->pile.on || n < 0 || (n > 0 && !d_gids)) return fail(SLRBS_E_ARG, "slrbs_pile_set_send: bad argument");
+    CU(cudaSetDevice(c->device));
+    auto& P = c->pile;
+    if (n > P.send_cap) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (P.send) CU(cudaFree(P.send));
+        P.send = nullptr; P.send_cap = 0;
+        const int cap = n + n / 4 + 256;
+        CU(cudaMalloc((void**)&P.send, sizeof(int) * (size_t)cap));
+        P.send_cap = cap;
+    }
+    launch_pile_lookup((const int*)d_gids, n, P.loc, P.send, P.info, c->stream);
+    int r;
+    if ((r = check_launch(c))) return r;
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, P.info + 7, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (flag) return fail(SLRBS_E_ARG, "slrbs_pile_set_send: a requested body is not owned by this rank");
+    c->halo_send = P.send; c->n_halo_send = n;
+    return 0;
+}
+
+int slrbs_pile_scene_keys(slrbs_ctx* c, int scene, int max_out, int32_t* keys_out)
+{
+    if (!c || !c->pile.on || scene < 0 || scene >= c->v.B || max_out < 0 || (max_out > 0 && !keys_out))
+        return fail(SLRBS_E_ARG, "slrbs_pile_scene_keys: bad argument");
+    CU(cudaSetDevice(c->device));
+    int n = 0;
+    CU(cudaMemcpyAsync(&n, c->pile.count + scene, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    n = n < c->pile.g.nbdyn ? n : c->pile.g.nbdyn;
+    const int m = n < max_out ? n : max_out;
+    if (m > 0) CU(cudaMemcpy(keys_out, c->pile.keys + (size_t)scene * c->pile.g.nbdyn, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost));
+    return n;
 }
 
 int slrbs_profile_enable(slrbs_ctx* c, int on)

@@ -14,6 +14,15 @@ struct JointStage {
     const float *r0, *q0, *r1, *q1;
 };
 
+// fixed grid of cubic blocks of one large pile (pile.cu): this rank owns the blocks with block-x in [cx0, cx1)
+struct PileGrid {
+    float ox, oy, oz, block, halo_w;
+    int ncx, ncy, ncz, cx0, cx1;
+    int nbdyn;        // dynamic-body capacity of a scene (max_bodies - nfixed)
+    int nfixed;       // container boxes appended to every scene
+    int n_global;     // bodies of the whole pile
+};
+
 void launch_prepare(const View& v, cudaStream_t s);
 // detect.cu; broadphase: 0 all pairs, 1 hashed grid, -1 auto (grid for scenes of >= 512 bodies)
 void launch_detect(const View& v, int broadphase, cudaStream_t s);
@@ -43,6 +52,13 @@ void launch_snapshot(const View& v, int scene0, int ns, int restore, cudaStream_
 void launch_halo_copy(const View& v, int n, const int* src, const int* dst, cudaStream_t s);
 void launch_halo_pack(const View& v, int n, const int* idx, float* buf, cudaStream_t s);
 void launch_halo_unpack(const View& v, int n, const int* idx, const float* buf, cudaStream_t s);
+void init_pile_kernels();
+size_t pile_sort_smem(int nbdyn);
+void launch_pile_export(const View& v, const PileGrid& g, const int* count, const int* keys, float* table, unsigned* vmax2, cudaStream_t s);
+void launch_pile_rebuild(const View& v, const PileGrid& g, const float* table, const float* radius, const float* mass, const float* fixed10,
+                         int* count, int* keys, int* loc, int* info, int* hsrc, int* hdst, int* ldst, int* lgid, int* rdst, int* rgid,
+                         cudaStream_t s);
+void launch_pile_lookup(const int* gids, int n, const int* loc, int* out, int* info, cudaStream_t s);
 void launch_export_contacts(const View& v, int scene, int n, int* body0, int* body1, float* p3, float* n3, float* t3,
                             float* b3, float* phi, float* lam3, float* J0, float* J1, float* M0, float* M1,
                             float* A9, float* rhs3, cudaStream_t s);

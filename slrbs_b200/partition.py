@@ -20,7 +20,7 @@ exchange index lists: each derives its own send / receive lists from the same gl
 """
 import numpy as np
 
-from .capi import Context, SPHERE
+from .capi import Context, SlrbsError, SPHERE
 
 STATE_W = 13      # x3 q4 v3 w3
 
@@ -262,6 +262,225 @@ class PartitionedPile:
             c = self.ctx.contacts(s)
             if c["phi"].size:
                 worst = max(worst, float(-c["phi"].min()))
+        return worst
+
+    def close(self):
+        if self.ctx is not None:
+            self.ctx.close(); self.ctx = None
+
+
+# ---- device-side re-partition (fixed grid of blocks; slrbs_pile_* in the C ABI, csrc/pile.cu) ---------------------------
+def fixed_grid(x, block, margin):
+    """Origin and cell counts of the fixed block grid that covers the initial pile plus `margin` on every side
+    (bodies that leave it are clamped into the boundary blocks)."""
+    x = np.asarray(x, np.float32)
+    lo = (x.min(axis=0) - np.float32(margin)).astype(np.float32)
+    hi = (x.max(axis=0) + np.float32(margin)).astype(np.float32)
+    ncell = np.maximum(np.ceil((hi - lo) / np.float32(block)).astype(np.int64), 1)
+    return lo, ncell.astype(np.int32)
+
+
+def slab_bounds(x, origin, block, ncx, world):
+    """Contiguous slabs of block-x indices, balanced by body count, at least one block column per rank."""
+    assert ncx >= world, f"{world} ranks need at least {world} block columns along x (have {ncx}): use smaller blocks"
+    cx = np.clip(np.floor((np.asarray(x, np.float32)[:, 0] - origin[0]) / np.float32(block)).astype(np.int64), 0, ncx - 1)
+    per_x = np.bincount(cx, minlength=ncx)
+    cum = np.concatenate([[0], np.cumsum(per_x)])
+    bounds = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        b = int(np.searchsorted(cum, target, side="left"))
+        b = max(b, bounds[-1] + 1)                       # at least one column for the previous rank
+        b = min(b, ncx - (world - r))                    # and one for each rank still to come
+        bounds.append(b)
+    bounds.append(ncx)
+    return bounds
+
+
+def grid_partition_numpy(x, origin, block, halo_w, ncell, cx0, cx1):
+    """Host mirror (float32, same expressions) of k_pile_classify + k_pile_sort: for every scene of the slab
+    [cx0, cx1) the sorted keys global id * 2 + halo flag. Used by the tests to check the device partition."""
+    x = np.asarray(x, np.float32)
+    origin = np.asarray(origin, np.float32); block = np.float32(block); halo_w = np.float32(halo_w)
+    ncell = np.asarray(ncell, np.int64)
+    rel = x - origin
+    cell = np.clip(np.floor(rel / block).astype(np.int64), 0, ncell - 1)
+    inside = rel - cell.astype(np.float32) * block
+    lo, hi = inside <= halo_w, (block - inside) <= halo_w
+    nscenes = (cx1 - cx0) * int(ncell[1]) * int(ncell[2])
+    scene_l, key_l = [], []
+    gid = np.arange(x.shape[0], dtype=np.int64)
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                m = np.ones(x.shape[0], bool)
+                for ax, dd in enumerate((dx, dy, dz)):
+                    if dd < 0: m &= lo[:, ax]
+                    elif dd > 0: m &= hi[:, ax]
+                nc = cell + np.array([dx, dy, dz])
+                m &= (nc[:, 0] >= cx0) & (nc[:, 0] < cx1) & (nc[:, 1] >= 0) & (nc[:, 1] < ncell[1]) & (nc[:, 2] >= 0) & (nc[:, 2] < ncell[2])
+                sc = ((nc[m, 0] - cx0) * ncell[1] + nc[m, 1]) * ncell[2] + nc[m, 2]
+                scene_l.append(sc); key_l.append(gid[m] * 2 + (1 if (dx or dy or dz) else 0))
+    sc, key = np.concatenate(scene_l), np.concatenate(key_l)
+    order = np.lexsort((key, sc))
+    sc, key = sc[order], key[order]
+    starts = np.searchsorted(sc, np.arange(nscenes)); ends = np.searchsorted(sc, np.arange(nscenes), side="right")
+    return [key[a:b].astype(np.int32) for a, b in zip(starts, ends)]
+
+
+class DevicePile:
+    """One rank of a pile whose re-partition runs on the device (no host round trip of the body states).
+
+    Space is a fixed grid of blocks; the rank owns a slab of block columns, one scene per block. Every K steps the
+    owners' states are scattered into a dense device table (slrbs_pile_export), summed over the ranks with an NCCL
+    all-reduce, and every rank rebuilds its scenes from the table on its GPU (slrbs_pile_rebuild). Halo copies owned
+    by a neighbour rank are requested from it once per rebuild (an all-to-all of global ids) and refreshed after every
+    step by slrbs_halo_pack -> NCCL all_to_all_single -> slrbs_halo_unpack; halo copies owned locally by an indexed
+    device copy. K follows the fastest body so that nothing can cross the halo between two rebuilds."""
+
+    def __init__(self, x, radius, mass, fixed_bodies, block=8.0, dt=0.01, rank=0, world=1, device=0, slack=0.5,
+                 contact_factor=4, mu=0.8, iters=10, rebuild_every=0, max_bodies=0):
+        import torch
+        self.torch = torch
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+        self.n = int(x.shape[0])
+        self.radius = np.ascontiguousarray(radius, np.float32); self.mass = np.ascontiguousarray(mass, np.float32)
+        self.block, self.dt, self.slack = float(block), float(dt), float(slack)
+        self.rank, self.world, self.device = rank, world, device
+        self.contact_factor, self.mu, self.iters = contact_factor, mu, iters
+        self.fixed_K = int(rebuild_every)
+        self.halo_w = min(2.0 * float(self.radius.max()) + 2e-3 + self.slack, self.block)
+        self.fixed10 = np.array([list(f["x"]) + list(f["q"]) + list(f["dim"]) for f in fixed_bodies], np.float32).reshape(-1, 10)
+        self.origin, self.ncell = fixed_grid(x, self.block, 2.0 * self.halo_w)
+        self.bounds = slab_bounds(x, self.origin, self.block, int(self.ncell[0]), world)
+        self.cx0, self.cx1 = self.bounds[rank], self.bounds[rank + 1]
+        self.B = (self.cx1 - self.cx0) * int(self.ncell[1]) * int(self.ncell[2])
+        dev = torch.device("cuda", device)
+        state = np.zeros((self.n, STATE_W), np.float32)
+        state[:, :3] = x; state[:, 6] = 1.0
+        self.table = torch.from_numpy(state).to(dev).reshape(-1)
+        self.vmax2 = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ctx = None
+        nf = self.fixed10.shape[0]
+        if max_bodies <= 0:                                        # uniform-density guess; grown on overflow
+            cells = float(np.prod(self.ncell.astype(np.float64)))
+            grow = ((self.block + 2.0 * self.halo_w) / self.block) ** 3
+            max_bodies = int(1.5 * self.n / cells * grow) + nf + 64
+        self.NB = max_bodies
+        self.stats = dict(rebuilds=0, rebuild_s=0.0, grows=0)
+        self.steps_since_rebuild, self.K = 0, 1
+        self.sbuf = self.rbuf = None
+        self._rebuild(first=True)
+
+    # ---- context + rebuild --------------------------------------------------------------------------------------
+    def _make_ctx(self):
+        if self.ctx is not None:
+            self.ctx.close()
+        self.ctx = Context(self.B, self.NB, 0, self.contact_factor * self.NB, device=self.device)
+        self.ctx.set_params(self.mu, 0, self.iters, True)
+        self.ctx.pile_init(self.radius, self.mass, self.origin, self.block, self.halo_w, self.ncell, self.cx0, self.cx1, self.fixed10)
+
+    def _rebuild(self, first=False):
+        import time
+        torch = self.torch
+        t0 = time.perf_counter()
+        if self.ctx is None:
+            self._make_ctx()
+        if not first:
+            self.table.zero_(); self.vmax2.zero_()
+            torch.cuda.synchronize(self.device)
+            self.ctx.pile_export(self.table.data_ptr(), self.vmax2.data_ptr())
+            self.ctx.sync()
+            if self.world > 1:
+                self.dist.all_reduce(self.table)                                   # disjoint owners: sum = gather
+                self.dist.all_reduce(self.vmax2, op=self.dist.ReduceOp.MAX)        # float bits of v^2 >= 0 order like ints
+                torch.cuda.synchronize(self.device)
+        while True:
+            try:
+                info = self.ctx.pile_rebuild(self.table.data_ptr())
+                break
+            except SlrbsError:
+                info = self.ctx.pile_info
+                if not info[0]:
+                    raise
+                self.NB = int(info[1] * 1.25) + self.fixed10.shape[0] + 64         # a block outgrew the scenes: larger context
+                self.stats["grows"] += 1
+                self._make_ctx()
+        self.info = info
+        nl, nr = int(info[3]), int(info[4])
+        if self.world > 1:
+            dev = self.table.device
+            req = torch.empty(max(nl + nr, 1), dtype=torch.int32, device=dev)
+            self.ctx.pile_requests(req.data_ptr())
+            ask = [0] * self.world                                                 # how many bodies I ask of each peer
+            if self.rank > 0: ask[self.rank - 1] = nl
+            if self.rank < self.world - 1: ask[self.rank + 1] = nr
+            assert (nl == 0 or self.rank > 0) and (nr == 0 or self.rank < self.world - 1)
+            ask_t = torch.tensor(ask, dtype=torch.int32, device=dev); give_t = torch.empty_like(ask_t)
+            self.dist.all_to_all_single(give_t, ask_t)
+            give = [int(v) for v in give_t.cpu()]                                  # how many each peer asks of me
+            gids = torch.empty(max(sum(give), 1), dtype=torch.int32, device=dev)
+            self.dist.all_to_all_single(gids[: sum(give)], req[: nl + nr], give, ask)
+            torch.cuda.synchronize(self.device)
+            self.ctx.pile_set_send(gids.data_ptr(), sum(give))
+            self.ask13, self.give13 = [a * STATE_W for a in ask], [g * STATE_W for g in give]
+            self.sbuf = torch.empty(max(sum(give), 1) * STATE_W, dtype=torch.float32, device=dev)
+            self.rbuf = torch.empty(max(nl + nr, 1) * STATE_W, dtype=torch.float32, device=dev)
+            self.n_give, self.n_ask = sum(give), nl + nr
+        if self.fixed_K > 0:
+            self.K = self.fixed_K
+        else:
+            # two bodies may approach each other: each may use slack / 2 before the next rebuild;
+            # displacement after k steps <= v0 k dt + g (k dt)^2 / 2  (v0 = fastest body now)
+            v2 = float(np.array([int(self.vmax2.cpu()[0])], np.int32).view(np.float32)[0]) if not first else 0.0
+            v0 = float(np.sqrt(max(v2, 0.0)))
+            k = 1
+            while k < 200 and v0 * (k + 1) * self.dt + 4.905 * ((k + 1) * self.dt) ** 2 <= 0.5 * self.slack:
+                k += 1
+            self.K = k
+        self.steps_since_rebuild = 0
+        self.stats["rebuilds"] += 1
+        self.stats["rebuild_s"] += time.perf_counter() - t0
+        self.stats.update(K=self.K, scenes=self.B, max_bodies=self.NB, largest_scene=int(info[1]), local_halos=int(info[2]),
+                          remote_halos=nl + nr, slots=int(info[5]), owned=int(info[6]))
+
+    # ---- stepping ------------------------------------------------------------------------------------------------
+    def step(self, n=1):
+        for _ in range(n):
+            if self.steps_since_rebuild >= self.K:
+                self._rebuild()
+            self.ctx.step(self.dt, 1)
+            self.ctx.halo_sync_local()
+            if self.world > 1:
+                self.ctx.halo_pack(self.sbuf.data_ptr())
+                self.ctx.sync()
+                self.dist.all_to_all_single(self.rbuf[: self.n_ask * STATE_W], self.sbuf[: self.n_give * STATE_W], self.ask13, self.give13)
+                self.torch.cuda.synchronize(self.device)
+                self.ctx.halo_unpack(self.rbuf.data_ptr())
+            self.steps_since_rebuild += 1
+
+    def gather_state(self):
+        """[n, 13] states of ALL bodies (owners' values) on every rank."""
+        torch = self.torch
+        self.table.zero_(); self.vmax2.zero_()
+        torch.cuda.synchronize(self.device)
+        self.ctx.pile_export(self.table.data_ptr(), self.vmax2.data_ptr())
+        self.ctx.sync()
+        if self.world > 1:
+            self.dist.all_reduce(self.table)
+            torch.cuda.synchronize(self.device)
+        return self.table.cpu().numpy().reshape(self.n, STATE_W).copy()
+
+    def max_penetration(self):
+        self.ctx.sync()
+        cnt = self.ctx.contact_counts()
+        worst = 0.0
+        for s in np.nonzero(cnt > 0)[0]:
+            c = self.ctx.contacts(int(s))
+            worst = max(worst, float(-c["phi"].min()))
         return worst
 
     def close(self):

@@ -6,12 +6,12 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from slrbs_b200 import Context
-from slrbs_b200.partition import PartitionedPile, TorchComm, sphere_pile
+from slrbs_b200.partition import DevicePile, PartitionedPile, TorchComm, sphere_pile
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--dims", type=int, nargs=3, default=[24, 8, 12]); ap.add_argument("--block", type=float, default=6.0)
 ap.add_argument("--steps", type=int, default=60); ap.add_argument("--rebuild", type=int, default=10)
-ap.add_argument("--check", type=int, default=1)
+ap.add_argument("--check", type=int, default=1); ap.add_argument("--device-rebuild", type=int, default=0)
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -19,7 +19,10 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 x, r, m, fixed = sphere_pile(*a.dims)
 comm = TorchComm(local) if world > 1 else None
-pile = PartitionedPile(x, r, m, fixed, block=a.block, rebuild_every=a.rebuild, rank=rank, world=world, device=local, comm=comm)
+if a.device_rebuild:
+    pile = DevicePile(x, r, m, fixed, block=a.block, rank=rank, world=world, device=local)
+else:
+    pile = PartitionedPile(x, r, m, fixed, block=a.block, rebuild_every=a.rebuild, rank=rank, world=world, device=local, comm=comm)
 pile.step(5)
 torch.cuda.synchronize()
 if world > 1: dist.barrier()

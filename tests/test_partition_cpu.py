@@ -95,3 +95,29 @@ def test_two_ranks_exchange_matching_halo_lists_over_gloo():
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+# ---- fixed-grid partition (host mirror of the device re-partition, csrc/pile.cu) -------------------------------
+def test_fixed_grid_mirror_owns_every_body_once_and_keeps_neighbours():
+    from slrbs_b200.partition import fixed_grid, grid_partition_numpy, slab_bounds
+    x = pile()
+    n = x.shape[0]
+    block, halo_w = 4.0, 1.3
+    origin, ncell = fixed_grid(x, block, 2 * halo_w)
+    bounds = slab_bounds(x, origin, block, int(ncell[0]), 3)
+    assert bounds[0] == 0 and bounds[-1] == ncell[0] and all(b > a for a, b in zip(bounds, bounds[1:]))
+    owned = np.zeros(n, int)
+    scene_of = {}
+    members = []
+    for r in range(3):
+        for s, keys in enumerate(grid_partition_numpy(x, origin, block, halo_w, ncell, bounds[r], bounds[r + 1])):
+            assert (np.diff(keys >> 1) > 0).all()                        # sorted by global id, unique
+            owned[keys[(keys & 1) == 0] >> 1] += 1
+            for g in keys[(keys & 1) == 0] >> 1:
+                scene_of[int(g)] = len(members)
+            members.append(set((keys >> 1).tolist()))
+    assert (owned == 1).all()
+    d = np.linalg.norm(x[:, None, :] - x[None, :, :], axis=-1)
+    ii, jj = np.nonzero((d < halo_w - 1e-5) & (d > 0))
+    for i, j in zip(ii[::5], jj[::5]):
+        assert int(j) in members[scene_of[int(i)]]                       # whoever can touch an owned body is in its scene
