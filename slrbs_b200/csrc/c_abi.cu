@@ -228,13 +228,13 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     A(v.nbodies, v.B) A(v.njoints, v.B) A(v.ncontacts, v.B) A(v.overflow, 1) A(v.visit_counters, 2)
     A(v.pos, nb) A(v.quat, nb) A(v.vel, nb) A(v.omg, nb) A(v.flags, nb) A(v.geomA, nb) A(v.geomB, nb)
     A(v.ibody, 9 * nb) A(v.ibodyinv, 9 * nb) A(v.cproxy, nb) A(v.bext, nb) A(v.force, nb) A(v.torque, nb)
-    A(v.extf, nb) A(v.extt, nb) A(v.Iw, 9 * nb) A(v.Iinvw, 9 * nb) A(v.wl, nb) A(v.wa, nb)
+    A(v.extf, nb) A(v.extt, nb) A(v.Iw, 9 * nb) A(v.Iinvw, 9 * nb) A(v.wl, nb) A(v.wa, nb) A(v.brec, 8 * nb)
     A(v.s_pos, nb) A(v.s_quat, nb) A(v.s_vel, nb) A(v.s_omg, nb)
     A(v.jdef, nj) A(v.jr0, nj) A(v.jq0, nj) A(v.jr1, nj) A(v.jq1, nj) A(v.jlam, nj) A(v.jlam4, nj)
     A(v.jrow, (size_t)JROW_FIELDS * v.NJ * bpad)
     A(v.cids, nc) A(v.cp, nc) A(v.cn, nc) A(v.crow, (size_t)CROW_FIELDS * v.NC * bpad)
     if (v.level_mode) {
-        A(v.cpos, nc) A(v.clev_end, nc + v.B) A(v.nclev, v.B) A(v.lv_last, nb)
+        A(v.cpos, nc) A(v.cslot, nc) A(v.clev_end, nc + v.B) A(v.nclev, v.B) A(v.lv_last, nb)
         A(v.jpos, nj) A(v.jlev_end, nj + v.B) A(v.njlev, v.B)
     }
 #undef A

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
                                 fabsf(R.m[2][0]) * hd.x + fabsf(R.m[2][1]) * hd.y + fabsf(R.m[2][2]) * hd.z, 0.f);
     }
     // RigidBody::updateInertiaMatrix (RigidBody.cpp:78-89)
+    M3 Iinv;
     if (!(fl & FLAG_FIXED)) {
         const Q4 q = mkq(v.quat[i]);
         const M3 R = rotation_matrix(q);
@@ -79,30 +80,45 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
         const M3 Ib = load_m3(v.ibody, v, slot, scene);
         const M3 Ibi = load_m3(v.ibodyinv, v, slot, scene);
         store_m3(v.Iw, v, slot, scene, matmul(matmul(R, Ib), Rinv));
-        store_m3(v.Iinvw, v, slot, scene, matmul(matmul(R, Ibi), Rinv));
+        Iinv = matmul(matmul(R, Ibi), Rinv);
     } else {
-        M3 Z;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) Z.m[k / 3][k % 3] = 0.f;
-        store_m3(v.Iinvw, v, slot, scene, Z);
+        for (int k = 0; k < 9; ++k) Iinv.m[k / 3][k % 3] = 0.f;
     }
+    store_m3(v.Iinvw, v, slot, scene, Iinv);
+    // everything the row builders gather per body, as one 128 B line
+    float4* rec = v.brec + at_brec(v, slot, scene);
+    const float4 vl = v.vel[i], om = v.omg[i];
+    rec[0] = px;
+    rec[1] = make_float4(vl.x, vl.y, vl.z, (fl & FLAG_FIXED) ? 1.f : 0.f);
+    rec[2] = make_float4(om.x, om.y, om.z, 0.f);
+    rec[3] = mk4(f, 0.f);
+    rec[4] = mk4(tau, 0.f);
+    rec[5] = make_float4(Iinv.m[0][0], Iinv.m[0][1], Iinv.m[0][2], 0.f);
+    rec[6] = make_float4(Iinv.m[1][0], Iinv.m[1][1], Iinv.m[1][2], 0.f);
+    rec[7] = make_float4(Iinv.m[2][0], Iinv.m[2][1], Iinv.m[2][2], 0.f);
 }
 
 // ------------------------------------------------------------------------------------
 // K4  contact frame, Jacobian blocks, J M^-1, 3x3 diagonal block, RHS
 // ------------------------------------------------------------------------------------
+#ifndef CONTACT_ROWS_MIN_BLOCKS
+#define CONTACT_ROWS_MIN_BLOCKS 4
+#endif
 struct BodyDyn { V3 x, xdot, omega, f, tau; float mass; M3 Iinv; bool fixed; };
 
 __device__ __forceinline__ BodyDyn load_body_dyn(const View& v, int slot, int scene)
 {
     BodyDyn b;
-    const size_t i = at(v, slot, scene);
-    const float4 px = v.pos[i];
-    b.x = mk3(px); b.mass = px.w;
-    b.xdot = mk3(v.vel[i]); b.omega = mk3(v.omg[i]);
-    b.f = mk3(v.force[i]); b.tau = mk3(v.torque[i]);
-    b.Iinv = load_m3(v.Iinvw, v, slot, scene);
-    b.fixed = (v.flags[i] & FLAG_FIXED) != 0;
+    const float4* __restrict__ rec = v.brec + at_brec(v, slot, scene);
+    const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4], r5 = rec[5], r6 = rec[6], r7 = rec[7];
+    b.x = mk3(r0); b.mass = r0.w;
+    b.xdot = mk3(r1); b.fixed = r1.w != 0.f;
+    b.omega = mk3(r2);
+    b.f = mk3(r3); b.tau = mk3(r4);
+    b.Iinv.m[0][0] = r5.x; b.Iinv.m[0][1] = r5.y; b.Iinv.m[0][2] = r5.z;
+    b.Iinv.m[1][0] = r6.x; b.Iinv.m[1][1] = r6.y; b.Iinv.m[1][2] = r6.z;
+    b.Iinv.m[2][0] = r7.x; b.Iinv.m[2][1] = r7.y; b.Iinv.m[2][2] = r7.z;
     return b;
 }
 
@@ -131,12 +147,9 @@ __device__ __forceinline__ float dot6_seq(const float* a, const float* b)
     return acc;
 }
 
-__global__ void __launch_bounds__(128) k_contact_rows(View v, float h)
+// one contact: frame, Jacobian blocks, J M^-1, diagonal block, RHS -> its row record at `pos` of the scene's stream
+__device__ __forceinline__ void contact_row(const View& v, float h, int scene, int slot, int pos)
 {
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (size_t)v.NC * v.B) return;
-    const int scene = (int)(tid % v.B), slot = (int)(tid / v.B);
-    if (slot >= v.ncontacts[scene]) return;
     const size_t c = at(v, slot, scene);
     const int2 ids = v.cids[c];
     const float4 pp = v.cp[c];
@@ -182,7 +195,6 @@ __global__ void __launch_bounds__(128) k_contact_rows(View v, float h)
     }
     const int packed = (ids.x | (b0.fixed ? 0x8000 : 0)) | ((ids.y | (b1.fixed ? 0x8000 : 0)) << 16);
     float4* R = v.crow;
-    const int pos = contact_pos(v, slot, scene);                 // slot, or its place in the level-ordered stream
 #define CROW(f) R[at_crow(v, f, pos, scene)]
     CROW(0)  = mk4(n, 1.0f / b0.mass);
     CROW(1)  = mk4(t, 1.0f / b1.mass);
@@ -201,6 +213,26 @@ __global__ void __launch_bounds__(128) k_contact_rows(View v, float h)
     CROW(14) = make_float4(M1[2][3], M1[2][4], M1[2][5], A[2][1]);
     CROW(CROW_LAMBDA) = make_float4(0.f, 0.f, 0.f, 0.f);       // lambda = 0 (Contact.cpp:66, SolverBoxPGS.cpp:210)
 #undef CROW
+}
+
+// thread / (contact slot, scene), scenes fastest: the warp-blocked tiles of mode 0 are written as full 512 B segments
+__global__ void __launch_bounds__(128, CONTACT_ROWS_MIN_BLOCKS) k_contact_rows(View v, float h)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)v.NC * v.B) return;
+    const int scene = (int)(tid % v.B), slot = (int)(tid / v.B);
+    if (slot >= v.ncontacts[scene]) return;
+    contact_row(v, h, scene, slot, contact_pos(v, slot, scene));
+}
+
+// level mode: thread / (position in the scene's level-ordered stream), positions fastest, so that the lanes of a warp
+// write 32 consecutive records of one scene (the [scene][field][pos] layout makes that one 512 B segment per field;
+// with scenes fastest every 16 B field of every row was a store of its own, 1 MB apart from its neighbours')
+__global__ void __launch_bounds__(128, CONTACT_ROWS_MIN_BLOCKS) k_contact_rows_lv(View v, float h)
+{
+    const int scene = blockIdx.y, pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= v.ncontacts[scene]) return;
+    contact_row(v, h, scene, v.cslot[(size_t)scene * v.NC + pos], pos);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1123,7 +1155,11 @@ __global__ void k_export_body_dyn(View v, int scene, int n, float* f3, float* ta
 static inline unsigned blocks_for(size_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 void launch_prepare(const View& v, cudaStream_t s) { k_prepare<<<blocks_for((size_t)v.NB * v.B, 256), 256, 0, s>>>(v); }
-void launch_contact_rows(const View& v, float h, cudaStream_t s) { k_contact_rows<<<blocks_for((size_t)v.NC * v.B, 128), 128, 0, s>>>(v, h); }
+void launch_contact_rows(const View& v, float h, cudaStream_t s)
+{
+    if (v.level_mode && v.B <= 65535) k_contact_rows_lv<<<dim3(blocks_for((size_t)v.NC, 128), (unsigned)v.B), 128, 0, s>>>(v, h);
+    else k_contact_rows<<<blocks_for((size_t)v.NC * v.B, 128), 128, 0, s>>>(v, h);
+}
 void launch_joint_rows(const View& v, float h, cudaStream_t s) { if (v.NJ > 0) k_joint_rows<<<blocks_for((size_t)v.NJ * v.B, 128), 128, 0, s>>>(v, h); }
 void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s)
 {

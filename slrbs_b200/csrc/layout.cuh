@@ -65,6 +65,8 @@ struct View {
     float  *Iw;         // [9][NB][B] world inertia
     float  *Iinvw;      // [9][NB][B]
     float4 *wl, *wa;    // PGS body accumulators sum(J^T lambda); after solve: fc, tauc
+    float4 *brec;       // [B][NB][8] per-body record for the row builders (one 128 B line per body, written by k_prepare):
+                        // x|mass, xdot|fixed, omega|-, f|-, tau|-, Iinv rows 0..2
     float4 *s_pos, *s_quat, *s_vel, *s_omg;   // RigidBodySystemState snapshot
     // joints, [NJ][B]
     int4   *jdef;       // type, body0, body1, dim
@@ -82,12 +84,14 @@ struct View {
     float4 *cn;         // n | -
     float4 *crow;       // mode 0: [B/32][NC][CROW_FIELDS][32]; mode 1: [B][CROW_FIELDS][NC]
     int    *cpos;       // [NC][B] position of contact slot in the level-ordered row stream (level mode)
+    int    *cslot;      // [B][NC] inverse of cpos: contact slot at a position of the level-ordered stream (level mode)
     int    *clev_end;   // [NC+1][B] end offset of contact level l (1-based; entry 0 is 0)
     int    *nclev;      // [B] number of contact levels
     int    *lv_last;    // [NB][B] scratch: last level that touched a body
 };
 
 __host__ __device__ __forceinline__ size_t at(const View& v, int slot, int scene) { return (size_t)slot * v.B + scene; }
+__host__ __device__ __forceinline__ size_t at_brec(const View& v, int slot, int scene) { return ((size_t)scene * v.NB + slot) * 8; }
 __host__ __device__ __forceinline__ size_t at_kry(const View& v, int vec, int k, int slot, int scene) { return (((size_t)vec * 5 + k) * v.NJ + slot) * v.B + scene; }
 __host__ __device__ __forceinline__ size_t at_b9(const View& v, int k, int slot, int scene) { return ((size_t)k * v.NB + slot) * v.B + scene; }
 // row record addressing: `pos` is the contact / joint slot in mode 0 and the position in the

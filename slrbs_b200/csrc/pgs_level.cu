@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
     for (int c = lane; c < nc; c += 32) {
         const size_t ci = at(v, c, scene);
         const int packed = v.cpos[ci];
-        v.cpos[ci] = hist[packed >> 16] + (packed & 0xffff);
+        const int pos = hist[packed >> 16] + (packed & 0xffff);
+        v.cpos[ci] = pos;
+        v.cslot[(size_t)scene * v.NC + pos] = c;
     }
     if (lane == 0) v.nclev[scene] = nlev;
 }

@@ -444,6 +444,8 @@ class DevicePile:
         self.steps_since_rebuild = 0
         self.stats["rebuilds"] += 1
         self.stats["rebuild_s"] += time.perf_counter() - t0
+        if not first:
+            self.stats["steady_rebuild_s"] = self.stats.get("steady_rebuild_s", 0.0) + time.perf_counter() - t0
         self.stats.update(K=self.K, scenes=self.B, max_bodies=self.NB, largest_scene=int(info[1]), local_halos=int(info[2]),
                           remote_halos=nl + nr, slots=int(info[5]), owned=int(info[6]))
 

@@ -12,6 +12,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--dims", type=int, nargs=3, default=[24, 8, 12]); ap.add_argument("--block", type=float, default=6.0)
 ap.add_argument("--steps", type=int, default=60); ap.add_argument("--rebuild", type=int, default=10)
 ap.add_argument("--check", type=int, default=1); ap.add_argument("--device-rebuild", type=int, default=0)
+ap.add_argument("--slack", type=float, default=0.5)
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -20,7 +21,7 @@ if world > 1:
 x, r, m, fixed = sphere_pile(*a.dims)
 comm = TorchComm(local) if world > 1 else None
 if a.device_rebuild:
-    pile = DevicePile(x, r, m, fixed, block=a.block, rank=rank, world=world, device=local)
+    pile = DevicePile(x, r, m, fixed, block=a.block, rank=rank, world=world, device=local, slack=a.slack)
 else:
     pile = PartitionedPile(x, r, m, fixed, block=a.block, rebuild_every=a.rebuild, rank=rank, world=world, device=local, comm=comm)
 pile.step(5)
