@@ -72,29 +72,57 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
     for (int b = lane; b < nb; b += 32) last[b] = (v.flags[at(v, b, scene)] & FLAG_FIXED) ? -1 : 0;
     for (int l = lane; l <= nc + 1; l += 32) hist[l] = 0;
     __syncwarp();
+    // The level of a contact depends on the levels of all earlier contacts of its two bodies: a sequential chain, walked
+    // by lane 0 out of shared memory (ids staged by the warp in chunks of 32; two dependent shared-memory accesses per
+    // contact). The stable rank inside a level (counting sort) is off that chain: per chunk all lanes match the lanes
+    // of equal level and count the lower ones.
     int nlev = 0;
+    int2 nxt = make_int2(0, 0);
+    if (lane < nc) nxt = v.cids[at(v, lane, scene)];
     for (int c0 = 0; c0 < nc; c0 += 32) {
-        if (c0 + lane < nc) idbuf[lane] = v.cids[at(v, c0 + lane, scene)];
+        const int m = min(32, nc - c0);
+        idbuf[lane] = nxt;
+        if (c0 + 32 + lane < nc) nxt = v.cids[at(v, c0 + 32 + lane, scene)];   // next chunk's ids, in flight during the chain
         __syncwarp();
         if (lane == 0) {
-            const int m = min(32, nc - c0);
-            for (int k = 0; k < m; ++k) {
-                const int2 ids = idbuf[k];
-                const int l0 = last[ids.x], l1 = last[ids.y];
-                const int L = max(max(l0, l1), 0) + 1;          // fixed bodies (-1) do not order anything
-                if (l0 >= 0) last[ids.x] = L;
-                if (l1 >= 0) last[ids.y] = L;
-                const int rank = hist[L];
-                hist[L] = rank + 1;
-                outbuf[k] = (L << 16) | rank;
-                nlev = max(nlev, L);
+            if (m == 32) {                                       // full chunk: ids in registers, only `last` is on the chain
+                int2 r[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) r[k] = idbuf[k];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const int l0 = last[r[k].x], l1 = last[r[k].y];
+                    const int L = max(max(l0, l1), 0) + 1;      // fixed bodies (-1) do not order anything
+                    if (l0 >= 0) last[r[k].x] = L;
+                    if (l1 >= 0) last[r[k].y] = L;
+                    outbuf[k] = L;
+                }
+            } else {
+                for (int k = 0; k < m; ++k) {
+                    const int2 ids = idbuf[k];
+                    const int l0 = last[ids.x], l1 = last[ids.y];
+                    const int L = max(max(l0, l1), 0) + 1;
+                    if (l0 >= 0) last[ids.x] = L;
+                    if (l1 >= 0) last[ids.y] = L;
+                    outbuf[k] = L;
+                }
             }
         }
         __syncwarp();
-        if (c0 + lane < nc) v.cpos[at(v, c0 + lane, scene)] = outbuf[lane];
+        const unsigned act = __ballot_sync(0xffffffffu, lane < m);
+        if (lane < m) {
+            const int myL = outbuf[lane];
+            const unsigned same = __match_any_sync(act, myL);
+            const int base = hist[myL];
+            __syncwarp(act);
+            if (lane == __ffs(same) - 1) hist[myL] = base + __popc(same);
+            v.cpos[at(v, c0 + lane, scene)] = (myL << 16) | (base + __popc(same & ((1u << lane) - 1u)));
+            nlev = max(nlev, myL);
+        }
         __syncwarp();
     }
-    nlev = __shfl_sync(0xffffffffu, nlev, 0);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nlev = max(nlev, __shfl_xor_sync(0xffffffffu, nlev, d));
     // exclusive prefix of the per-level counts -> level starts (in place), level ends to global
     int carry = 0;
     for (int l0 = 1; l0 <= nlev; l0 += 32) {
