@@ -6,7 +6,7 @@ detection, Jacobian assembly, 10 Box-PGS sweeps, integration. Scenes are indepen
 shard the batch by scene index with no data-path collective (weak scaling: fixed scenes per GPU).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload marble_box|car|swinging_boxes|sphere_stack|marble_box_1k] [--scenes B]
+                    [--workload marble_box|car|swinging_boxes|sphere_stack|marble_box_1k|box_stack] [--scenes B]
 
 Prints ONE JSON line (rank 0). Keys beyond the base contract:
   roofline      the PGS sweep kernel (dominant): algorithmic bytes (464 B / contact visit, 744 B / hinge
@@ -46,6 +46,9 @@ WORKLOADS = {
     "swinging_boxes": ("swinging_boxes", (0, 0, 0), 0, 65536, 50, 0.0),
     "sphere_stack":   ("sphere_stack", (8, 0, 0), 32, 262144, 50, 0.0),
     "marble_box_1k":  ("marble_box_n", (10, 10, 10), 4096, 1024, 200, 0.01),   # BASELINE configs[1]: ~1k spheres in a box
+    # BASELINE configs[0] "box-stack on plane": NOT a reference scene and needs box-box / box-plane contacts, which the
+    # reference does not have -> the extension pairs (slrbs_set_extensions), no reference parity for this workload
+    "box_stack":      ("box_stack", (5, 0, 0), 32, 262144, 50, 0.0),
 }
 
 
@@ -137,6 +140,8 @@ def run_ours(args):
 
     ctx = Context(B, nb, nj, nc, device=local)
     ctx.set_params(MU, 0, SOLVER_ITERS, True)
+    if args.workload == "box_stack":
+        ctx.set_extensions(1)
     variants = ctx.describe()
     ctx.upload_bodies(x, s["q"], s["v"], s["w"], s["mass"], s["ibody"], s["ibodyinv"], s["fixed"], s["geom_type"], s["geom"])
     if nj:
@@ -242,7 +247,7 @@ def _oracle_system(workload, seed, settle):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle, Reference, ref_available
     scene, abc, _, _, _, jitter = WORKLOADS[workload]
-    kw = {"k": abc[0]} if scene == "sphere_stack" else ({"nx": abc[0], "nz": abc[1], "ny": abc[2]} if scene == "marble_box_n" else {})
+    kw = {"k": abc[0]} if scene in ("sphere_stack", "box_stack") else ({"nx": abc[0], "nz": abc[1], "ny": abc[2]} if scene == "marble_box_n" else {})
     o = Oracle(scene, **kw)
     if jitter > 0:
         st = o.state(); fixed = o.body_params()["fixed"] == 1
@@ -252,7 +257,7 @@ def _oracle_system(workload, seed, settle):
         o.set_state(**st)
     o.set_params(MU, 0, SOLVER_ITERS, True)
     o.step(DT, settle)
-    if not ref_available():
+    if not ref_available() or scene == "box_stack":          # the extension pairs exist only in the restatement
         return o, "port"
     r = Reference(scene, **kw)
     r.set_params(MU, 0, SOLVER_ITERS, True)

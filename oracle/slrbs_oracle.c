@@ -184,6 +184,7 @@ struct orc_system {
     int   solverIter;       /* RigidBodySystem.cpp:22 */
     int   collisions;       /* m_collisionsEnabled, :26 */
     long long pairs_tested;
+    int   ext_pairs;        /* extension: sphere-plane, box-plane, box-box contacts (no reference counterpart) */
 };
 
 static void push_int(int **arr, int *n, int *cap, int v)
@@ -514,6 +515,160 @@ static void detect_cylinder_plane(orc_system* s, int i0, int i1)
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* EXTENSION pairs: sphere-plane, box-plane, box-box. */
+/* The reference silently ignores these pairs (CollisionDetect.cpp:45-73): */
+/* there is NO reference behaviour to match ("parity unpinned - no         */
+/* reference path"). Off by default; orc_set_extensions(s, 1) appends them */
+/* AFTER the reference's five cases, so existing results do not change.    */
+/* This file only restates the device routines so that the contact lists   */
+/* can be compared bit for bit; physics is validated on penetration.       */
+/* ------------------------------------------------------------------ */
+void orc_set_extensions(orc_system* s, int flags) { s->ext_pairs = flags & 1; }
+
+/* sphere (body0) against the half space of a plane (body1) */
+static void ext_sphere_plane(orc_system* s, int i0, int i1)
+{
+    const body_t* sp = &s->bodies[i0];
+    const body_t* pl = &s->bodies[i1];
+    const v3 planen = q_rot(pl->q, pl->plane_n);
+    const v3 planep = v3_add(q_rot(pl->q, pl->plane_p), pl->x);
+    const float dist = distance_point_plane(sp->x, planep, planen) - sp->radius;
+    if (dist < 1e-3f)
+        new_contact(s, i0, i1, v3_sub(sp->x, v3_scale(sp->radius, planen)), planen, fminf(0.0f, dist));
+}
+
+/* box (body0) against a plane (body1): its corners below the plane, at most 4, in corner order
+ * (bit 0 of the corner index = +x, bit 1 = +y, bit 2 = +z) */
+static void ext_box_plane(orc_system* s, int i0, int i1)
+{
+    const body_t* bx = &s->bodies[i0];
+    const body_t* pl = &s->bodies[i1];
+    const v3 planen = q_rot(pl->q, pl->plane_n);
+    const v3 planep = v3_add(q_rot(pl->q, pl->plane_p), pl->x);
+    const v3 h = V3(0.5f * bx->dim.x, 0.5f * bx->dim.y, 0.5f * bx->dim.z);
+    int cnt = 0;
+    for (int k = 0; k < 8 && cnt < 4; ++k) {
+        const v3 local = V3((k & 1) ? h.x : -h.x, (k & 2) ? h.y : -h.y, (k & 4) ? h.z : -h.z);
+        const v3 c = v3_add(q_rot(bx->q, local), bx->x);
+        const float d = distance_point_plane(c, planep, planen);
+        if (d < 1e-3f) { new_contact(s, i0, i1, c, planen, fminf(0.0f, d)); ++cnt; }
+    }
+}
+
+static inline v3 m3_col(const m3* R, int k) { return V3(R->m[0][k], R->m[1][k], R->m[2][k]); }
+static inline float proj_radius(const v3 ax[3], const float h[3], v3 L)
+{
+    return sum3(h[0] * fabsf(v3_dot(ax[0], L)), h[1] * fabsf(v3_dot(ax[1], L)), h[2] * fabsf(v3_dot(ax[2], L)));
+}
+
+/* box (body0 = i) against box (body1 = j): separating-axis test over the 15 axes (3 + 3 face normals, 9 edge
+ * cross products); the axis of least overlap gives the normal (faces preferred). Face contact: the incident face
+ * is clipped against the side planes of the reference face and the clipped corners at or below the reference face
+ * become contacts (at most 4: the extremes along the face diagonals). Edge contact: the midpoint of the closest
+ * points of the two edges. The normal points from body1 to body0 like every other contact. */
+static void ext_box_box(orc_system* s, int i0, int i1)
+{
+    const body_t* A = &s->bodies[i0];
+    const body_t* B = &s->bodies[i1];
+    const m3 Ra = q_to_matrix(A->q), Rb = q_to_matrix(B->q);
+    const v3 ax[2][3] = { { m3_col(&Ra, 0), m3_col(&Ra, 1), m3_col(&Ra, 2) }, { m3_col(&Rb, 0), m3_col(&Rb, 1), m3_col(&Rb, 2) } };
+    const float hh[2][3] = { { 0.5f * A->dim.x, 0.5f * A->dim.y, 0.5f * A->dim.z }, { 0.5f * B->dim.x, 0.5f * B->dim.y, 0.5f * B->dim.z } };
+    const v3 xc[2] = { A->x, B->x };
+    const v3 t = v3_sub(B->x, A->x);
+    float best = 3.0e38f; int best_idx = -1; v3 bestL = V3(0, 0, 0);
+    for (int idx = 0; idx < 15; ++idx) {
+        v3 L;
+        if (idx < 3) L = ax[0][idx];
+        else if (idx < 6) L = ax[1][idx - 3];
+        else {
+            const v3 c = v3_cross(ax[0][(idx - 6) / 3], ax[1][(idx - 6) % 3]);
+            const float l2 = v3_sqnorm(c);
+            if (l2 < 1e-6f) continue;                         /* (nearly) parallel edges: covered by the face axes */
+            L = v3_div(c, sqrtf(l2));
+        }
+        const float overlap = (proj_radius(ax[0], hh[0], L) + proj_radius(ax[1], hh[1], L)) - fabsf(v3_dot(t, L));
+        if (overlap < -1e-3f) return;                         /* separated by more than the contact margin */
+        if (idx < 6) { if (overlap < best) { best = overlap; best_idx = idx; bestL = L; } }
+        else if (overlap < best - 0.05f * fabsf(best) - 1e-4f) { best = overlap; best_idx = idx; bestL = L; }
+    }
+    if (best_idx < 0) return;
+    if (best_idx >= 6) {
+        /* edge - edge */
+        const int ea = (best_idx - 6) / 3, eb = (best_idx - 6) % 3;
+        const v3 nab = (v3_dot(t, bestL) > 0.0f) ? bestL : v3_neg(bestL);        /* from A towards B */
+        v3 pa = A->x, pb = B->x;
+        for (int k = 0; k < 3; ++k) {
+            if (k != ea) pa = v3_add(pa, v3_scale((v3_dot(ax[0][k], nab) > 0.0f) ? hh[0][k] : -hh[0][k], ax[0][k]));
+            if (k != eb) pb = v3_add(pb, v3_scale((v3_dot(ax[1][k], nab) < 0.0f) ? hh[1][k] : -hh[1][k], ax[1][k]));
+        }
+        const v3 ua = ax[0][ea], ub = ax[1][eb];
+        const v3 d = v3_sub(pb, pa);
+        const float a = v3_dot(ua, ub), da = v3_dot(d, ua), db = v3_dot(d, ub);
+        const float den = 1.0f - a * a;
+        const float sa = (da - a * db) / den, sb = (a * da - db) / den;
+        const v3 ca = v3_add(pa, v3_scale(sa, ua)), cb = v3_add(pb, v3_scale(sb, ub));
+        new_contact(s, i0, i1, v3_scale(0.5f, v3_add(ca, cb)), v3_neg(nab), fminf(0.0f, -best));
+        return;
+    }
+    /* face contact: reference box r (0 = A, 1 = B), incident box c */
+    const int r = best_idx < 3 ? 0 : 1, c = 1 - r, k = best_idx < 3 ? best_idx : best_idx - 3;
+    const v3 rc = v3_sub(xc[c], xc[r]);
+    const v3 nr = (v3_dot(rc, ax[r][k]) > 0.0f) ? ax[r][k] : v3_neg(ax[r][k]);   /* outward normal of the reference face */
+    int m = 0; float dmax = -1.0f;
+    for (int q = 0; q < 3; ++q) { const float dq = fabsf(v3_dot(ax[c][q], nr)); if (dq > dmax) { dmax = dq; m = q; } }
+    const float sgn = (v3_dot(ax[c][m], nr) > 0.0f) ? -1.0f : 1.0f;               /* incident face looks against nr */
+    const int u = (m + 1) % 3, w = (m + 2) % 3;
+    const v3 fc = v3_add(xc[c], v3_scale(sgn * hh[c][m], ax[c][m]));
+    const v3 eu = v3_scale(hh[c][u], ax[c][u]), ew = v3_scale(hh[c][w], ax[c][w]);
+    v3 poly[16], tmp[16];
+    int np = 4;
+    poly[0] = v3_add(v3_add(fc, eu), ew); poly[1] = v3_add(v3_sub(fc, eu), ew);
+    poly[2] = v3_sub(v3_sub(fc, eu), ew); poly[3] = v3_sub(v3_add(fc, eu), ew);
+    const int ru = (k + 1) % 3, rw = (k + 2) % 3;
+    for (int side = 0; side < 4 && np > 0; ++side) {         /* Sutherland-Hodgman against the 4 side planes */
+        const int axn = side < 2 ? ru : rw;
+        const float sg = (side & 1) ? -1.0f : 1.0f;
+        const v3 pn = v3_scale(sg, ax[r][axn]);
+        const float lim = hh[r][axn];
+        int nn = 0;
+        for (int e = 0; e < np; ++e) {
+            const v3 p0 = poly[e], p1 = poly[(e + 1) % np];
+            const float d0 = v3_dot(v3_sub(p0, xc[r]), pn) - lim, d1 = v3_dot(v3_sub(p1, xc[r]), pn) - lim;
+            if (d0 <= 0.0f) tmp[nn++] = p0;
+            if ((d0 <= 0.0f) != (d1 <= 0.0f)) {
+                const float tt = d0 / (d0 - d1);
+                tmp[nn++] = v3_add(p0, v3_scale(tt, v3_sub(p1, p0)));
+            }
+        }
+        np = nn;
+        for (int e = 0; e < np; ++e) poly[e] = tmp[e];
+    }
+    /* keep the corners at or below the reference face (+ margin) */
+    v3 pts[16]; float dep[16], ca_[16], cb_[16];
+    int nk = 0;
+    for (int e = 0; e < np; ++e) {
+        const v3 rel = v3_sub(poly[e], xc[r]);
+        const float d = v3_dot(rel, nr) - hh[r][k];
+        if (d < 1e-3f) { pts[nk] = poly[e]; dep[nk] = d; ca_[nk] = v3_dot(rel, ax[r][ru]); cb_[nk] = v3_dot(rel, ax[r][rw]); ++nk; }
+    }
+    const v3 n = (r == 0) ? v3_neg(nr) : nr;                  /* from body1 (B) towards body0 (A) */
+    if (nk <= 4) {
+        for (int e = 0; e < nk; ++e) new_contact(s, i0, i1, pts[e], n, fminf(0.0f, dep[e]));
+        return;
+    }
+    int pick[4]; int npick = 0;
+    for (int dgn = 0; dgn < 4; ++dgn) {                       /* extremes along (+a+b), (-a+b), (-a-b), (+a-b) */
+        const float sa = (dgn == 0 || dgn == 3) ? 1.0f : -1.0f, sb = (dgn < 2) ? 1.0f : -1.0f;
+        int arg = 0; float bestv = -3.0e38f;
+        for (int e = 0; e < nk; ++e) { const float val = sa * ca_[e] + sb * cb_[e]; if (val > bestv) { bestv = val; arg = e; } }
+        int dup = 0;
+        for (int q = 0; q < npick; ++q) dup |= (pick[q] == arg);
+        if (!dup) pick[npick++] = arg;
+    }
+    for (int q = 0; q < npick; ++q) new_contact(s, i0, i1, pts[pick[q]], n, fminf(0.0f, dep[pick[q]]));
+}
+
 /* CollisionDetect::detectCollisions, CollisionDetect.cpp:27-76 */
 void orc_stage_detect(orc_system* s)
 {
@@ -532,6 +687,13 @@ void orc_stage_detect(orc_system* s)
             else if (t1 == ORC_SPHERE && t0 == ORC_BOX)      detect_sphere_box(s, j, i);
             else if (t0 == ORC_CYLINDER && t1 == ORC_PLANE)  detect_cylinder_plane(s, i, j);
             else if (t1 == ORC_CYLINDER && t0 == ORC_PLANE)  detect_cylinder_plane(s, j, i);
+            else if (s->ext_pairs) {                          /* extension pairs, after the reference's chain */
+                if (t0 == ORC_SPHERE && t1 == ORC_PLANE)      ext_sphere_plane(s, i, j);
+                else if (t1 == ORC_SPHERE && t0 == ORC_PLANE) ext_sphere_plane(s, j, i);
+                else if (t0 == ORC_BOX && t1 == ORC_PLANE)    ext_box_plane(s, i, j);
+                else if (t1 == ORC_BOX && t0 == ORC_PLANE)    ext_box_plane(s, j, i);
+                else if (t0 == ORC_BOX && t1 == ORC_BOX)      ext_box_box(s, i, j);
+            }
         }
     }
 }
@@ -1402,4 +1564,20 @@ void orc_scene_marble_box_n(orc_system* s, int nx, int nz, int ny)
     B[s3].x = V3(0.0f, 0.5f * hy, -wallz);
     B[s3].q = q_from_angle_axis(1.57f, V3(0, 1, 0));
     B[s4].x = V3(0.0f, 0.0f, 0.0f);
+}
+
+/* EXTENSION scene (BASELINE.json config 0 "box-stack on plane"; no such scene in Scenarios.h): k unit boxes
+ * (mass 1) stacked on a fixed Plane at y = 0, centres at y = 0.5 + i * 1.0, alternately turned by 0.3 rad about y
+ * so that the face-face clipping is exercised. Needs orc_set_extensions(s, 1). Bodies: boxes bottom-up, then the plane. */
+void orc_scene_box_stack(orc_system* s, int k)
+{
+    orc_clear(s);
+    for (int i = 0; i < k; ++i) {
+        const int b = add_simple(s, 1.0f, ORC_BOX, 1.0f, 1.0f, 1.0f, 0, 0, 0);
+        s->bodies[b].x = V3(0.0f, 0.5f + (float)i * 1.0f, 0.0f);
+        if (i & 1) s->bodies[b].q = q_from_angle_axis(0.3f, V3(0, 1, 0));
+    }
+    const int pl = add_simple(s, 1.0f, ORC_PLANE, 0, 0, 0, 0, 1.0f, 0);
+    s->bodies[pl].fixed = 1;
+    s->ext_pairs = 1;
 }

@@ -117,6 +117,11 @@ void orc_scene_car(orc_system* s);               /* :178-247 */
 void orc_scene_sphere_stack(orc_system* s, int k);                 /* C1p */
 void orc_scene_marble_box_n(orc_system* s, int nx, int nz, int ny);/* MB1k family */
 
+/* EXTENSIONS without a reference counterpart: flags bit 0 = sphere-plane, box-plane and box-box
+ * contacts, appended after the reference's dispatch chain (off by default) */
+void orc_set_extensions(orc_system* s, int flags);
+void orc_scene_box_stack(orc_system* s, int k);  /* k unit boxes on a Plane (BASELINE config 0); enables the extension */
+
 /* timing helper for the CPU baseline: runs n steps, returns seconds (CLOCK_MONOTONIC) */
 double orc_time_steps(orc_system* s, float dt, int n);
 

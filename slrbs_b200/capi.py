@@ -25,7 +25,7 @@ SYMBOLS = [
     "slrbs_save_state", "slrbs_restore_state", "slrbs_profile_enable", "slrbs_profile_read",
     "slrbs_timer_start", "slrbs_timer_stop", "slrbs_halo_set_local", "slrbs_halo_set_remote", "slrbs_halo_sync_local",
     "slrbs_halo_pack", "slrbs_halo_unpack", "slrbs_pile_init", "slrbs_pile_export", "slrbs_pile_rebuild",
-    "slrbs_pile_requests", "slrbs_pile_set_send", "slrbs_pile_scene_keys",
+    "slrbs_pile_requests", "slrbs_pile_set_send", "slrbs_pile_scene_keys", "slrbs_set_extensions",
 ]
 
 
@@ -56,6 +56,7 @@ def load_library():
     L.slrbs_destroy.argtypes = [vp]
     L.slrbs_destroy.restype = None
     L.slrbs_set_params.argtypes = [vp, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.slrbs_set_extensions.argtypes = [vp, C.c_int]
     L.slrbs_upload_bodies.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, fp, fp, fp, fp, fp, fp, fp, ip, ip, fp]
     L.slrbs_upload_joints.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, fp, fp, fp, fp]
     L.slrbs_upload_state.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]
@@ -129,6 +130,10 @@ class Context:
         if rc < 0:
             raise SlrbsError(f"slrbs error {rc}: {self.L.slrbs_last_error().decode()}")
         return rc
+
+    def set_extensions(self, flags=1):
+        """Extension contact pairs without a reference counterpart (sphere-plane, box-plane, box-box)."""
+        self._ck(self.L.slrbs_set_extensions(self.h, int(flags)))
 
     def describe(self):
         buf = C.create_string_buffer(256)

@@ -270,6 +270,14 @@ int slrbs_set_params(slrbs_ctx* c, float mu, int solver_id, int solver_iters, in
     return 0;
 }
 
+int slrbs_set_extensions(slrbs_ctx* c, int flags)
+{
+    if (!c || flags < 0 || flags > 1) return fail(SLRBS_E_ARG, "slrbs_set_extensions: bad argument");
+    if (c->v.ext_pairs != (flags & 1) && c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }   // the View is baked into the graph
+    c->v.ext_pairs = flags & 1;
+    return 0;
+}
+
 int slrbs_upload_bodies(slrbs_ctx* c, int scene0, int ns, int n, const int32_t* counts,
                         const float* x3, const float* q4, const float* v3, const float* w3,
                         const float* mass, const float* ibody9, const float* ibodyinv9,

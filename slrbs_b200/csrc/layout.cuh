@@ -46,6 +46,7 @@ struct View {
     int *overflow;                        // [1] set when a scene exceeded NC
     unsigned long long *visit_counters;   // [2] contact visits, joint visits (profiling)
     int profiling;
+    int ext_pairs;                        // extension: sphere-plane, box-plane, box-box contacts (no reference counterpart)
     // bodies, [NB][B]
     float4 *pos;        // x y z | mass
     float4 *quat;       // x y z w

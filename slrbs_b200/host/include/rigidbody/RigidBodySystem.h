@@ -39,6 +39,9 @@ public:
     void setPreStepFunc(PreStepFunc _func) { m_preStepFunc = _func; }
     void setResetFunc(ResetFunc _func) { m_resetFunc = _func; }
     void setEnableCollisionDetection(bool _enableCollisions) { m_collisionsEnabled = _enableCollisions; }
+    // EXTENSION (not in the reference): also generate sphere-plane, box-plane and box-box contacts, which the
+    // reference's dispatch ignores (src/collision/CollisionDetect.cpp:45-73). Off by default.
+    void setExtendedContacts(bool _on) { m_extContacts = _on; }
 
     int solverIter;
     int solverId;   // PGS = 0, Conj. Gradient = 1, Conj. Residual = 2
@@ -61,6 +64,7 @@ private:
     std::vector<Joint*> m_joints;
     std::unique_ptr<CollisionDetect> m_collisionDetect;
     bool m_collisionsEnabled;
+    bool m_extContacts = false;
     PreStepFunc m_preStepFunc;
     ResetFunc m_resetFunc;
     // per-system solver objects (the reference keeps them in a file-static array shared by every

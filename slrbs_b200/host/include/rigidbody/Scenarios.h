@@ -138,6 +138,20 @@ public:
         sys.addBody(box(1.0f, V3(10.0f, 0.4f, 10.0f), V3(0.0f, 0.0f, 0.0f), true));
     }
 
+    // EXTENSION scene (BASELINE config 0 "box-stack on plane"; the reference has neither the scene nor box-box / box-plane
+    // contacts): k unit boxes stacked on the ground plane, every other one turned 0.3 rad about y. Boxes bottom-up, then the plane.
+    static void createBoxStack(RigidBodySystem& sys, int k)
+    {
+        begin(sys);
+        for (int i = 0; i < k; ++i) {
+            RigidBody* b = box(1.0f, V3(1.0f, 1.0f, 1.0f), V3(0.0f, 0.5f + (float)i * 1.0f, 0.0f), false);
+            if (i & 1) b->q = Eigen::AngleAxisf(0.3f, V3(0, 1, 0));
+            sys.addBody(b);
+        }
+        sys.addBody(groundPlane());
+        sys.setExtendedContacts(true);
+    }
+
     // createMarbleBox's construction scaled to nx x nz columns of ny marbles, container sized to fit.
     static void createMarbleBoxN(RigidBodySystem& sys, int nx, int nz, int ny)
     {

@@ -310,6 +310,7 @@ void RigidBodySystem::step(float dt)
         }
 
         check(slrbs_set_params(m_ctx, Contact::mu, solverId, solverIter, m_collisionsEnabled ? 1 : 0), "slrbs_set_params");
+        check(slrbs_set_extensions(m_ctx, m_extContacts ? 1 : 0), "slrbs_set_extensions");
         check(slrbs_stage_prepare(m_ctx), "slrbs_stage_prepare");
         if (m_collisionsEnabled) {
             m_collisionDetect->detectCollisions();

@@ -42,6 +42,7 @@ slrbs_host_system* slrbs_host_scene_create(const char* scene, int a, int b, int 
     else if (name == "car") Scenarios::createCarScene(h->sys);
     else if (name == "sphere_stack") Scenarios::createSphereStack(h->sys, a);
     else if (name == "marble_box_n") Scenarios::createMarbleBoxN(h->sys, a, b, c);
+    else if (name == "box_stack") Scenarios::createBoxStack(h->sys, a);
     else if (name == "empty") {}
     else { g_err = "unknown scene: " + name; return nullptr; }
     return h.release();

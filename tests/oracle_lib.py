@@ -112,6 +112,8 @@ def _bind(L):
     for name in ("orc_scene_marble_box", "orc_scene_sphere_on_box", "orc_scene_swinging_boxes",
                  "orc_scene_cylinder_on_plane", "orc_scene_car"):
         getattr(L, name).argtypes = [vp]
+    L.orc_set_extensions.argtypes = [vp, C.c_int]
+    L.orc_scene_box_stack.argtypes = [vp, C.c_int]
     L.orc_scene_sphere_stack.argtypes = [vp, C.c_int]
     L.orc_scene_marble_box_n.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.orc_time_steps.argtypes = [vp, C.c_float, C.c_int]
@@ -166,6 +168,8 @@ class Oracle:
     def load_scene(self, scene, **kw):
         if scene in SCENES:
             getattr(self.L, SCENES[scene])(self.h)
+        elif scene == "box_stack":
+            self.L.orc_scene_box_stack(self.h, int(kw.get("k", 5)))
         elif scene == "sphere_stack":
             self.L.orc_scene_sphere_stack(self.h, int(kw.get("k", 8)))
         elif scene == "marble_box_n":
@@ -192,6 +196,10 @@ class Oracle:
 
     def set_params(self, mu=0.8, solver_id=0, solver_iter=10, collisions=True):
         self.L.orc_set_params(self.h, float(mu), int(solver_id), int(solver_iter), int(bool(collisions)))
+
+    def set_extensions(self, flags=1):
+        """Extension pairs without a reference counterpart (sphere-plane, box-plane, box-box)."""
+        self.L.orc_set_extensions(self.h, int(flags))
 
     # -- stepping ----------------------------------------------------
     def step(self, dt=0.01, n=1):
