@@ -160,6 +160,13 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
 template <int G> struct LvCfg { enum { THREADS = G < 32 ? 32 : G, SPC = THREADS / G }; };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
+}
+#ifndef LV_BULK_PREFETCH
+#define LV_BULK_PREFETCH 1
+#endif
 
 struct BodyW { float4* w; };     // shared-memory accumulators of one scene: [body][2] (linear, angular)
 __device__ __forceinline__ void ld_w(const float4* w, int body, V3& l, V3& a) { l = mk3(w[2 * body]); a = mk3(w[2 * body + 1]); }
@@ -240,9 +247,14 @@ __global__ void __launch_bounds__(LvCfg<G>::THREADS, MINB) k_pgs_lv(View v, floa
                 int q0 = p1, q1 = p1;
                 if (lev < ncl) q1 = v.clev_end[at(v, lev + 1, scene)];
                 else if (it + 1 < iters) { q0 = 0; q1 = v.clev_end[at(v, 1, scene)]; }
-                for (int q = q0 + gl; q < q1; q += G) {
+                if (LV_BULK_PREFETCH) {
+                    // the rows of a level are contiguous per field ([scene][field][pos]): one bulk L2 prefetch per field
+                    if (gl < CROW_FIELDS && q1 > q0) prefetch_l2_bulk(&v.crow[at_crow(v, gl, q0, scene)], (unsigned)(q1 - q0) * 16u);
+                } else {
+                    for (int q = q0 + gl; q < q1; q += G) {
 #pragma unroll
-                    for (int f = 0; f < CROW_FIELDS; ++f) prefetch_l2(&v.crow[at_crow(v, f, q, scene)]);
+                        for (int f = 0; f < CROW_FIELDS; ++f) prefetch_l2(&v.crow[at_crow(v, f, q, scene)]);
+                    }
                 }
             }
             for (int p = p0 + gl; p < p1; p += G) {
