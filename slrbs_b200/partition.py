@@ -328,6 +328,27 @@ def grid_partition_numpy(x, origin, block, halo_w, ncell, cx0, cx1):
     return [key[a:b].astype(np.int32) for a, b in zip(starts, ends)]
 
 
+def exchange_requests(dist, rank, world, req, n_left, n_right):
+    """Request protocol of the device-side re-partition, for slabs along x (a rank's only neighbours are rank - 1 and
+    rank + 1). `req` holds the global ids of the halo copies this rank needs refreshed, the left neighbour's first
+    (n_left) and then the right neighbour's (n_right), in the order the rank will unpack them. Every rank tells its
+    neighbours how many it asks for, then the id lists travel (all_to_all_single). Returns (gids, ask, give): the ids
+    the neighbours asked of this rank, ordered by asking rank (so the left neighbour's first), and the per-rank
+    counts asked / given, which are also the split sizes of the per-step state exchange. Works on CUDA tensors over
+    NCCL and on CPU tensors over gloo (tests/test_partition_cpu.py)."""
+    import torch
+    assert (n_left == 0 or rank > 0) and (n_right == 0 or rank < world - 1), "a halo copy's owner must be an adjacent slab"
+    ask = [0] * world
+    if rank > 0: ask[rank - 1] = int(n_left)
+    if rank < world - 1: ask[rank + 1] = int(n_right)
+    ask_t = torch.tensor(ask, dtype=torch.int32, device=req.device); give_t = torch.empty_like(ask_t)
+    dist.all_to_all_single(give_t, ask_t)
+    give = [int(v) for v in give_t.cpu()]
+    gids = torch.empty(max(sum(give), 1), dtype=torch.int32, device=req.device)
+    dist.all_to_all_single(gids[: sum(give)], req[: n_left + n_right], give, ask)
+    return gids, ask, give
+
+
 class DevicePile:
     """One rank of a pile whose re-partition runs on the device (no host round trip of the body states).
 
@@ -415,15 +436,7 @@ class DevicePile:
             dev = self.table.device
             req = torch.empty(max(nl + nr, 1), dtype=torch.int32, device=dev)
             self.ctx.pile_requests(req.data_ptr())
-            ask = [0] * self.world                                                 # how many bodies I ask of each peer
-            if self.rank > 0: ask[self.rank - 1] = nl
-            if self.rank < self.world - 1: ask[self.rank + 1] = nr
-            assert (nl == 0 or self.rank > 0) and (nr == 0 or self.rank < self.world - 1)
-            ask_t = torch.tensor(ask, dtype=torch.int32, device=dev); give_t = torch.empty_like(ask_t)
-            self.dist.all_to_all_single(give_t, ask_t)
-            give = [int(v) for v in give_t.cpu()]                                  # how many each peer asks of me
-            gids = torch.empty(max(sum(give), 1), dtype=torch.int32, device=dev)
-            self.dist.all_to_all_single(gids[: sum(give)], req[: nl + nr], give, ask)
+            gids, ask, give = exchange_requests(self.dist, self.rank, self.world, req, nl, nr)
             torch.cuda.synchronize(self.device)
             self.ctx.pile_set_send(gids.data_ptr(), sum(give))
             self.ask13, self.give13 = [a * STATE_W for a in ask], [g * STATE_W for g in give]

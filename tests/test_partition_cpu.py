@@ -121,3 +121,55 @@ def test_fixed_grid_mirror_owns_every_body_once_and_keeps_neighbours():
     ii, jj = np.nonzero((d < halo_w - 1e-5) & (d > 0))
     for i, j in zip(ii[::5], jj[::5]):
         assert int(j) in members[scene_of[int(i)]]                       # whoever can touch an owned body is in its scene
+
+
+def _device_protocol_worker(rank, world, port, ret):
+    """One rank of the device-side re-partition's exchange protocol, with the device kernels replaced by their host
+    mirror: requests for remote halo copies -> ids the neighbours ask of me -> the per-step state exchange in those
+    orders. Every halo copy must end up with its owner's state."""
+    from slrbs_b200.partition import exchange_requests, fixed_grid, grid_partition_numpy, slab_bounds, STATE_W
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = pile((16, 5, 6))
+    n = x.shape[0]
+    block, halo_w = 3.0, 1.3
+    origin, ncell = fixed_grid(x, block, 2 * halo_w)
+    bounds = slab_bounds(x, origin, block, int(ncell[0]), world)
+    cx0, cx1 = bounds[rank], bounds[rank + 1]
+    scenes = grid_partition_numpy(x, origin, block, halo_w, ncell, cx0, cx1)
+    cx_of = np.clip(np.floor((x[:, 0] - origin[0]) / np.float32(block)).astype(np.int64), 0, ncell[0] - 1)
+    # what k_pile_halo_map produces: (scene, slot, gid) of the halo copies owned by the left / right neighbour
+    left, right, owned_at = [], [], {}
+    for s, keys in enumerate(scenes):
+        for slot, key in enumerate(keys):
+            g = int(key) >> 1
+            if not (key & 1):
+                owned_at[g] = (s, slot)
+            elif cx_of[g] < cx0:
+                left.append((s, slot, g))
+            elif cx_of[g] >= cx1:
+                right.append((s, slot, g))
+    req = torch.tensor([g for _, _, g in left + right] or [0], dtype=torch.int32)
+    gids, ask, give = exchange_requests(dist, rank, world, req, len(left), len(right))
+    gids = gids[: sum(give)].numpy()
+    assert all(int(g) in owned_at for g in gids)                         # k_pile_lookup would flag anything else
+    # per-step refresh: pack my owners' states in the asked order, exchange, unpack in my request order
+    state = np.arange(n * STATE_W, dtype=np.float32).reshape(n, STATE_W) + 0.5 * rank      # "owner's state" = f(gid, owner rank)
+    sbuf = torch.from_numpy(np.ascontiguousarray(state[gids]).reshape(-1) if gids.size else np.zeros(0, np.float32))
+    rbuf = torch.zeros((len(left) + len(right)) * STATE_W, dtype=torch.float32)
+    dist.all_to_all_single(rbuf, sbuf, [a * STATE_W for a in ask], [g * STATE_W for g in give])
+    got = rbuf.numpy().reshape(-1, STATE_W)
+    ok = True
+    for k, (_, _, g) in enumerate(left + right):
+        owner = rank - 1 if k < len(left) else rank + 1
+        ok &= bool(np.array_equal(got[k], np.arange(g * STATE_W, (g + 1) * STATE_W, dtype=np.float32) + 0.5 * owner))
+    ret[rank] = (ok, len(left), len(right))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_device_repartition_protocol_over_gloo_three_ranks():
+    ret = mp.Manager().dict()
+    mp.spawn(_device_protocol_worker, args=(3, _free_port(), ret), nprocs=3, join=True)
+    assert all(ret[r][0] for r in range(3))
+    assert ret[0][1] == 0 and ret[2][2] == 0 and ret[1][1] > 0 and ret[1][2] > 0      # the middle rank has both neighbours
