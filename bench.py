@@ -38,6 +38,7 @@ SOLVER_ITERS = 10   # RigidBodySystem.cpp:22
 MU = 0.8            # Contact.cpp:4
 BYTES_PER_CONTACT_VISIT = 464
 BYTES_PER_HINGE_VISIT = 744
+E2E_CHUNKS = int(os.environ.get("SLRBS_E2E_CHUNKS", "8"))                  # contexts the batch is split into for the end-to-end arm (transfer / compute overlap)
 
 # workload -> (Scenarios builder, (a,b,c), contact capacity / scene, scenes / GPU, settle steps, jitter)
 WORKLOADS = {
@@ -170,22 +171,55 @@ def run_ours(args):
     contacts_mean = float(ctx.contact_counts().mean())
 
     # ---- end-to-end through the C ABI with host buffers ------------------------------------------
+    # The scenes are split over E2E_CHUNKS contexts (one stream each) so that one chunk's PCIe transfers overlap with
+    # another chunk's step: every step still uploads x,q,v,omega of EVERY body from pinned host memory, advances every
+    # scene once and downloads every body's state again before the step counts as done.
     hx = torch.empty((B, nb, 3), dtype=torch.float32).pin_memory(); hq = torch.empty((B, nb, 4), dtype=torch.float32).pin_memory()
     hv = torch.empty((B, nb, 3), dtype=torch.float32).pin_memory(); hw = torch.empty((B, nb, 3), dtype=torch.float32).pin_memory()
     ptr = [t.data_ptr() for t in (hx, hq, hv, hw)]
     ctx.download_state_raw(B, nb, *ptr)
+    nch = E2E_CHUNKS if B % E2E_CHUNKS == 0 and B // E2E_CHUNKS >= 64 else 1
+    if nch == 1:
+        chunks = [(ctx, 0, B)]
+    else:
+        ctx.close(); ctx = None                             # free the big context's memory for the chunk contexts
+        Bc = B // nch
+        chunks = []
+        for k in range(nch):
+            c = Context(Bc, nb, nj, nc, device=local)
+            c.set_params(MU, 0, SOLVER_ITERS, True)
+            if args.workload == "box_stack":
+                c.set_extensions(1)
+            sl = slice(k * Bc, (k + 1) * Bc)
+            c.upload_bodies(hx[sl].numpy(), hq[sl].numpy(), hv[sl].numpy(), hw[sl].numpy(), s["mass"], s["ibody"], s["ibodyinv"], s["fixed"],
+                            s["geom_type"], s["geom"])
+            if nj:
+                c.upload_joints(s["jtype"], s["jb0"], s["jb1"], s["r0"], s["q0"], s["r1"], s["q1"])
+            chunks.append((c, k * Bc, Bc))
+    sizes = (3, 4, 3, 3)
+    cptr = [[p + 4 * sz * nb * s0 for p, sz in zip(ptr, sizes)] for _, s0, _ in chunks]
+
+    def e2e_step():
+        for (c, _, n_sc), pp in zip(chunks, cptr):
+            c.upload_state_raw_async(n_sc, nb, *pp)         # H2D: 13 floats / body
+            c.step(DT, 1)
+            c.download_state_raw_async(n_sc, nb, *pp)       # D2H: 13 floats / body
+        for c, _, _ in chunks:
+            c.sync()                                        # every body's new state is in host memory
+
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):                                      # warm the staging buffers
-        ctx.upload_state_raw(B, nb, *ptr); ctx.step(DT, 1); ctx.download_state_raw(B, nb, *ptr)
+    for _ in range(3):                                      # warm the staging buffers (and capture the step graphs)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.upload_state_raw(B, nb, *ptr)                   # H2D: 13 floats / body
-        ctx.step(DT, 1)
-        ctx.download_state_raw(B, nb, *ptr)                 # D2H: 13 floats / body (synchronises)
+        e2e_step()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
+    for c, _, _ in chunks:
+        if c is not ctx:
+            c.close()
 
     from slrbs_b200 import sharding
     ms, e2e_ms = sharding.reduce_over_ranks([ms, e2e_ms], "max")           # device time: max over ranks
@@ -226,14 +260,15 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": alg_bytes / launches, "ms_per_launch": solve_ms / launches,
                      "share_of_step": solve_ms / ms if ms else None},
         "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": int(B * nb * 13 * 4),
-                "d2h_bytes_per_step": int(B * nb * 13 * 4), "steps": e2e_steps},
+                "d2h_bytes_per_step": int(B * nb * 13 * 4), "steps": e2e_steps, "contexts": len(chunks)},
         "gpu_launches": int(float(agg[4])),
         "clocks": clocks,
     }
     if world == 1:
         out["cpu_baseline"] = cpu_baseline_single(args.workload, settle)
     print(json.dumps(out), flush=True)
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

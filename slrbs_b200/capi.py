@@ -17,7 +17,7 @@ SPHERICAL, HINGE = 1, 2
 # every symbol include/slrbs_b200.h declares
 SYMBOLS = [
     "slrbs_last_error", "slrbs_version", "slrbs_describe", "slrbs_create", "slrbs_destroy", "slrbs_set_params",
-    "slrbs_upload_bodies", "slrbs_upload_joints", "slrbs_upload_state", "slrbs_download_state",
+    "slrbs_upload_bodies", "slrbs_upload_joints", "slrbs_upload_state", "slrbs_download_state", "slrbs_download_state_async", "slrbs_upload_state_async",
     "slrbs_set_external_forces", "slrbs_step", "slrbs_sync", "slrbs_stage_prepare", "slrbs_stage_detect",
     "slrbs_stage_jacobians", "slrbs_stage_solve", "slrbs_stage_integrate", "slrbs_download_contact_counts",
     "slrbs_download_contacts", "slrbs_download_contact_rows", "slrbs_download_joint_rows",
@@ -60,6 +60,8 @@ def load_library():
     L.slrbs_upload_bodies.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, fp, fp, fp, fp, fp, fp, fp, ip, ip, fp]
     L.slrbs_upload_joints.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, fp, fp, fp, fp]
     L.slrbs_upload_state.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]
+    L.slrbs_download_state_async.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]
+    L.slrbs_upload_state_async.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]
     L.slrbs_download_state.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]
     L.slrbs_set_external_forces.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, C.c_int]
     L.slrbs_step.argtypes = [vp, C.c_float, C.c_int]
@@ -212,6 +214,16 @@ class Context:
     def download_state_raw(self, ns, n, px, pq, pv, pw, scene0=0):
         cast = lambda p: None if not p else C.cast(p, C.POINTER(C.c_float))
         self._ck(self.L.slrbs_download_state(self.h, scene0, ns, n, cast(px), cast(pq), cast(pv), cast(pw)))
+
+    def upload_state_raw_async(self, ns, n, px, pq, pv, pw, scene0=0):
+        """No wait: the (pinned) host buffers must not change before the next sync()."""
+        cast = lambda p: None if not p else C.cast(p, C.POINTER(C.c_float))
+        self._ck(self.L.slrbs_upload_state_async(self.h, scene0, ns, n, cast(px), cast(pq), cast(pv), cast(pw)))
+
+    def download_state_raw_async(self, ns, n, px, pq, pv, pw, scene0=0):
+        """No wait: the (pinned) host buffers are valid after the next sync()."""
+        cast = lambda p: None if not p else C.cast(p, C.POINTER(C.c_float))
+        self._ck(self.L.slrbs_download_state_async(self.h, scene0, ns, n, cast(px), cast(pq), cast(pv), cast(pw)))
 
     def download_state(self, scene0=0, n_scenes=None, n_bodies=None):
         ns = n_scenes or (self.n_scenes - scene0)

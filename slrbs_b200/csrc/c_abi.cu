@@ -337,7 +337,19 @@ int slrbs_upload_joints(slrbs_ctx* c, int scene0, int ns, int n, const int32_t* 
     return 0;
 }
 
+static int upload_state_impl(slrbs_ctx* c, int scene0, int ns, int n, const float* x3, const float* q4, const float* v3, const float* w3, bool wait);
+
 int slrbs_upload_state(slrbs_ctx* c, int scene0, int ns, int n, const float* x3, const float* q4, const float* v3, const float* w3)
+{
+    return upload_state_impl(c, scene0, ns, n, x3, q4, v3, w3, true);
+}
+
+int slrbs_upload_state_async(slrbs_ctx* c, int scene0, int ns, int n, const float* x3, const float* q4, const float* v3, const float* w3)
+{
+    return upload_state_impl(c, scene0, ns, n, x3, q4, v3, w3, false);
+}
+
+static int upload_state_impl(slrbs_ctx* c, int scene0, int ns, int n, const float* x3, const float* q4, const float* v3, const float* w3, bool wait)
 {
     if (!range_ok(c, scene0, ns) || n <= 0 || n > c->v.NB) return fail(SLRBS_E_ARG, "slrbs_upload_state: bad range");
     CU(cudaSetDevice(c->device));
@@ -351,11 +363,23 @@ int slrbs_upload_state(slrbs_ctx* c, int scene0, int ns, int n, const float* x3,
     // counts unchanged: pass the live counts back to themselves
     launch_upload_bodies(c->v, scene0, ns, n, c->v.nbodies + scene0, st, c->stream);
     if ((r = check_launch(c))) return r;
-    CU(cudaStreamSynchronize(c->stream));      // the caller may reuse its (possibly pinned) buffers on return
+    if (wait) CU(cudaStreamSynchronize(c->stream));      // the caller may reuse its (possibly pinned) buffers on return
     return 0;
 }
 
+static int download_state_impl(slrbs_ctx* c, int scene0, int ns, int n, float* x3, float* q4, float* v3, float* w3, bool wait);
+
 int slrbs_download_state(slrbs_ctx* c, int scene0, int ns, int n, float* x3, float* q4, float* v3, float* w3)
+{
+    return download_state_impl(c, scene0, ns, n, x3, q4, v3, w3, true);
+}
+
+int slrbs_download_state_async(slrbs_ctx* c, int scene0, int ns, int n, float* x3, float* q4, float* v3, float* w3)
+{
+    return download_state_impl(c, scene0, ns, n, x3, q4, v3, w3, false);
+}
+
+static int download_state_impl(slrbs_ctx* c, int scene0, int ns, int n, float* x3, float* q4, float* v3, float* w3, bool wait)
 {
     if (!range_ok(c, scene0, ns) || n <= 0 || n > c->v.NB) return fail(SLRBS_E_ARG, "slrbs_download_state: bad range");
     CU(cudaSetDevice(c->device));
@@ -372,7 +396,7 @@ int slrbs_download_state(slrbs_ctx* c, int scene0, int ns, int n, float* x3, flo
     if (q4) CU(cudaMemcpyAsync(q4, dq, 4 * m * 4, cudaMemcpyDeviceToHost, c->stream));
     if (v3) CU(cudaMemcpyAsync(v3, dv, 3 * m * 4, cudaMemcpyDeviceToHost, c->stream));
     if (w3) CU(cudaMemcpyAsync(w3, dw, 3 * m * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    if (wait) CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
