@@ -12,13 +12,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--dims", type=int, nargs=3, default=[24, 8, 12]); ap.add_argument("--block", type=float, default=6.0)
 ap.add_argument("--steps", type=int, default=60); ap.add_argument("--rebuild", type=int, default=10)
 ap.add_argument("--check", type=int, default=1); ap.add_argument("--device-rebuild", type=int, default=0)
-ap.add_argument("--slack", type=float, default=0.5)
+ap.add_argument("--slack", type=float, default=0.5); ap.add_argument("--mixed-radii", type=int, default=0)
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 x, r, m, fixed = sphere_pile(*a.dims)
+if a.mixed_radii:                                  # BASELINE config 4 substitute: mixed spheres r in {0.25, 0.5}, mass ~ r^3
+    rng = np.random.default_rng(7)
+    small = rng.random(x.shape[0]) < 0.5
+    r = np.where(small, 0.25, 0.5).astype(np.float32); m = np.where(small, 0.125, 1.0).astype(np.float32)
 comm = TorchComm(local) if world > 1 else None
 if a.device_rebuild:
     pile = DevicePile(x, r, m, fixed, block=a.block, rank=rank, world=world, device=local, slack=a.slack)

@@ -358,3 +358,35 @@ def test_ragged_batch_with_per_scene_counts():
         assert cnt[s] == o.n_contacts, specs[s]
         np.testing.assert_allclose(g["x"][s, : o.n_bodies], o.state()["x"], rtol=0, atol=3e-3, err_msg=str(specs[s]))
     ctx.close()
+
+
+def test_degenerate_scenes_empty_single_body_and_no_contact_capacity():
+    """Ragged extremes in one batch: a scene with no live bodies, a scene with one body, and a full scene; then a
+    context created with max_contacts = 0 (collision stage skipped like setEnableCollisionDetection(false))."""
+    full = Oracle("sphere_on_box")
+    one = Oracle(); one.add_body(2.0, SPHERE, [0.3], x=[0, 5, 0], v=[1, 0, 0], w=[0, 2, 0])
+    from slrbs_b200 import Context
+    from gpu_helpers import scene_arrays
+    a, b = scene_arrays(full), scene_arrays(one)
+    nb = 2
+    def pad(arr, k):
+        out = np.zeros((nb,) + arr.shape[1:], arr.dtype); out[:arr.shape[0]] = arr; return out
+    keys = ("x", "q", "v", "w", "mass", "ibody", "ibodyinv", "fixed", "geom_type", "geom")
+    stacked = {k: np.stack([pad(a[k], 2), pad(b[k], 1), pad(b[k], 1)]) for k in keys}
+    stacked["mass"][stacked["mass"] == 0] = 1.0
+    ctx = Context(3, nb, 0, 8)
+    ctx.upload_bodies(*[stacked[k] for k in keys], counts=np.array([2, 1, 0], np.int32))
+    for _ in range(100):
+        ctx.step(DT); full.step(DT); one.step(DT)
+    ctx.sync()
+    g = ctx.download_state()
+    for k in "xqvw":
+        assert_bit_equal(g[k][1, :1], one.state()[k], k)                 # free flight: bit-exact
+    np.testing.assert_allclose(g["x"][0], full.state()["x"], rtol=0, atol=1e-4)
+    assert list(ctx.contact_counts()) == [full.n_contacts, 0, 0]
+    ctx.close()
+    nocap = Context(1, 2, 0, 0)
+    nocap.upload_bodies(*[stacked[k][0] for k in keys])
+    nocap.step(DT, 5); nocap.sync()
+    assert np.isfinite(nocap.download_state()["x"]).all()
+    nocap.close()
