@@ -29,7 +29,61 @@ SCENES = {
 }
 
 
+# solverId 1 / 2 (CG / CR, joint-only: SolverConjGradient.cpp, SolverConjResidual.cpp) and a spherical-joint chain
+# (Spherical.cpp; no reference scene uses it): one-step checkpoints only, because the reference's Krylov iterations
+# amplify last-bit differences by orders of magnitude per step (tests/test_gpu_parity.py)
+VARIANTS = {
+    "car_cg": ("car", 1, 20, [0, 3, 30]), "car_cr": ("car", 2, 20, [0, 3, 30]),
+    "swinging_boxes_cg": ("swinging_boxes", 1, 20, [0, 5, 40]), "swinging_boxes_cr": ("swinging_boxes", 2, 20, [0, 5, 40]),
+}
+
+
+def spherical_chain(cls):
+    o = cls()
+    o.add_body(1.0, 1, [1, 1, 1], fixed=True, x=[0, 10, 0])
+    prev = 0
+    for k in range(6):
+        b = o.add_body(1.0 + 0.5 * k, 0, [0.3], x=[0.8 * (k + 1), 10, 0], v=[0, 0, 0.5 * k])
+        o.add_spherical(prev, b, [0.4, 0, 0], [-0.4, 0, 0])
+        prev = b
+    o.set_params(0.8, 0, 10, False)
+    return o
+
+
+def variants():
+    for name, (scene, solver_id, iters, checkpoints) in VARIANTS.items():
+        r = Reference(scene)
+        r.set_params(0.8, solver_id, iters, True)
+        out = {"checkpoints": np.asarray(checkpoints, np.int32), "solver_id": np.int32(solver_id), "solver_iter": np.int32(iters),
+               "dt": np.float32(DT)}
+        done = 0
+        for k in checkpoints:
+            r.step(DT, k - done); done = k
+            st = r.state()
+            for key in st:
+                out[f"pre_{k}_{key}"] = st[key]
+            out[f"pre_{k}_jlam"] = r.joint_rows()["lam"]
+            r.step(DT); done += 1
+            st = r.state()
+            for key in st:
+                out[f"post_{k}_{key}"] = st[key]
+            out[f"post_{k}_jlam"] = r.joint_rows()["lam"]
+        np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), **out)
+        print(name, "ok")
+    r = spherical_chain(Reference)
+    out = {"dt": np.float32(DT), "total": np.int32(150)}
+    for k in (1, 50, 150):
+        r.step(DT, k - (0 if k == 1 else (1 if k == 50 else 50)))
+        st = r.state()
+        for key in st:
+            out[f"at_{k}_{key}"] = st[key]
+        out[f"at_{k}_jlam"] = r.joint_rows()["lam"]
+    np.savez_compressed(os.path.join(HERE, "ref_spherical_chain.npz"), **out)
+    print("spherical_chain ok")
+
+
 def main():
+    variants()
     for scene, (kw, checkpoints, total) in SCENES.items():
         r = Reference(scene, **kw)
         out = {"checkpoints": np.asarray(checkpoints, np.int32), "total": np.int32(total), "dt": np.float32(DT)}

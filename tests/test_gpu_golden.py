@@ -59,3 +59,40 @@ def test_free_running_trajectory(scene):
     gs, fin = ctx.download_state(), state(g, "final")
     assert np.abs(gs["x"][0] - fin["x"]).max() < TRAJ_TOL[scene], (scene, np.abs(gs["x"][0] - fin["x"]).max())
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["car_cg", "car_cr", "swinging_boxes_cg", "swinging_boxes_cr"])
+def test_krylov_one_step_from_reference_checkpoints(name):
+    """solverId 1 / 2 on the device against the reference's own CG / CR: one step from each checkpoint state; joint
+    impulses within 2e-3 of the largest impulse, positions within 1e-4 (the reference's Krylov iterations amplify
+    last-bit differences, so longer horizons are compared in tests/test_gpu_parity.py against the oracle's own
+    1-ulp sensitivity)."""
+    g = load(name)
+    scene = name.rsplit("_", 1)[0]
+    cps = [int(k) for k in g["checkpoints"]]
+    builders = [Oracle(scene) for _ in cps]
+    ctx = context_from_oracles(builders, max_contacts=32)
+    ctx.set_params(0.8, int(g["solver_id"]), int(g["solver_iter"]), True)
+    ctx.upload_state(*[np.stack([g[f"pre_{k}_{key}"] for k in cps]) for key in "xqvw"])
+    ctx.set_joint_lambda(np.stack([g[f"pre_{k}_jlam"] for k in cps]))
+    ctx.step(float(g["dt"]), 1); ctx.sync()
+    lam, st = ctx.joint_lambda(), ctx.download_state()
+    for s, k in enumerate(cps):
+        ref = g[f"post_{k}_jlam"]
+        np.testing.assert_allclose(lam[s], ref, rtol=0, atol=2e-3 * max(float(np.abs(ref).max()), 1e-3), err_msg=f"{name}@{k}")
+        np.testing.assert_allclose(st["x"][s], g[f"post_{k}_x"], rtol=0, atol=1e-4)
+    ctx.close()
+
+
+def test_spherical_chain_trajectory_against_reference():
+    from test_golden_cpu import spherical_chain
+    g = load("spherical_chain")
+    o = spherical_chain()
+    ctx = context_from_oracles([o], max_contacts=8); ctx.set_params(0.8, 0, 10, False)
+    done = 0
+    for k in (1, 50, 150):
+        ctx.step(float(g["dt"]), k - done); done = k
+        ctx.sync()
+        st = ctx.download_state()
+        np.testing.assert_allclose(st["x"][0], g[f"at_{k}_x"], rtol=0, atol=2e-3, err_msg=f"step {k}")
+    ctx.close()
