@@ -46,7 +46,9 @@ WORKLOADS = {
     "car":            ("car", (0, 0, 0), 16, 262144, 50, 0.0),
     "swinging_boxes": ("swinging_boxes", (0, 0, 0), 0, 65536, 50, 0.0),
     "sphere_stack":   ("sphere_stack", (8, 0, 0), 32, 262144, 50, 0.0),
-    "marble_box_1k":  ("marble_box_n", (10, 10, 10), 4096, 1024, 200, 0.01),   # BASELINE configs[1]: ~1k spheres in a box
+    # BASELINE configs[1]: ~1k spheres in a box. 2664 scenes = 2 x (9 scenes per SM x 148 SMs): with the packed 24 B
+    # accumulators 9 warp-scenes fit an SM, so this batch is exactly two full waves of the level-scheduled solver
+    "marble_box_1k":  ("marble_box_n", (10, 10, 10), 4096, 2664, 200, 0.01),
     # BASELINE configs[0] "box-stack on plane": NOT a reference scene and needs box-box / box-plane contacts, which the
     # reference does not have -> the extension pairs (slrbs_set_extensions), no reference parity for this workload
     "box_stack":      ("box_stack", (5, 0, 0), 32, 262144, 50, 0.0),

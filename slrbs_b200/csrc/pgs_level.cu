@@ -182,9 +182,39 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes)
 #define LV_BULK_PREFETCH 1
 #endif
 
-struct BodyW { float4* w; };     // shared-memory accumulators of one scene: [body][2] (linear, angular)
-__device__ __forceinline__ void ld_w(const float4* w, int body, V3& l, V3& a) { l = mk3(w[2 * body]); a = mk3(w[2 * body + 1]); }
-__device__ __forceinline__ void st_w(float4* w, int body, const V3& l, const V3& a) { w[2 * body] = mk4(l, 0.f); w[2 * body + 1] = mk4(a, 0.f); }
+// shared-memory accumulators of one scene, per body (linear xyz, angular xyz): either two padded float4 (32 B, two
+// 16 B accesses: best when shared memory is plentiful) or three float2 (24 B: a 1000-body scene then needs 24 KB and 9
+// scenes fit an SM instead of 7; chosen when the padded layout would cap the warps per SM)
+template <bool W24> struct Acc;
+template <> struct Acc<false> {
+    enum { FLOATS = 8 };
+    static __device__ __forceinline__ void ld(const float* w, int body, V3& l, V3& a)
+    {
+        const float4* p = reinterpret_cast<const float4*>(w) + 2 * body;
+        l = mk3(p[0]); a = mk3(p[1]);
+    }
+    static __device__ __forceinline__ void st(float* w, int body, const V3& l, const V3& a)
+    {
+        float4* p = reinterpret_cast<float4*>(w) + 2 * body;
+        p[0] = mk4(l, 0.f); p[1] = mk4(a, 0.f);
+    }
+};
+template <> struct Acc<true> {
+    enum { FLOATS = 6 };
+    static __device__ __forceinline__ void ld(const float* w, int body, V3& l, V3& a)
+    {
+        const float2* p = reinterpret_cast<const float2*>(w) + 3 * body;
+        const float2 p0 = p[0], p1 = p[1], p2 = p[2];
+        l = mk3(p0.x, p0.y, p1.x); a = mk3(p1.y, p2.x, p2.y);
+    }
+    static __device__ __forceinline__ void st(float* w, int body, const V3& l, const V3& a)
+    {
+        float2* p = reinterpret_cast<float2*>(w) + 3 * body;
+        p[0] = make_float2(l.x, l.y); p[1] = make_float2(l.z, a.x); p[2] = make_float2(a.y, a.z);
+    }
+};
+#define ld_w Acc<W24>::ld
+#define st_w Acc<W24>::st
 
 template <int G>
 __device__ __forceinline__ void group_sync(unsigned mask)
@@ -196,21 +226,21 @@ __device__ __forceinline__ void group_sync(unsigned mask)
 
 // MINB = warps per SM the register allocation must allow: 16 (128 registers, a few spills) wins when the batch
 // can fill 16 warps per SM, 12 (162 registers, no spills) when it cannot and single-warp latency is what matters.
-template <int G, int MINB>
+template <int G, int MINB, bool W24>
 __global__ void __launch_bounds__(LvCfg<G>::THREADS, MINB) k_pgs_lv(View v, float dt, int iters, float mu)
 {
-    extern __shared__ float4 smem_w[];
+    extern __shared__ float4 smem_w4[];
+    float* smem_w = reinterpret_cast<float*>(smem_w4);
     constexpr int SPC = LvCfg<G>::SPC;                           // scenes per CTA
     const int grp = threadIdx.x / G, gl = threadIdx.x % G;
     const int scene = blockIdx.x * SPC + grp;
     const unsigned mask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
     if (scene >= v.B) return;                                    // whole groups (for G > 32: whole CTAs) leave together
-    float4* w = smem_w + (size_t)grp * v.NB * 2;
+    float* w = smem_w + (size_t)grp * v.NB * Acc<W24>::FLOATS;
     const int nb = v.nbodies[scene], nj = v.njoints[scene], nc = v.ncontacts[scene];
     const int njl = v.njlev[scene], ncl = v.nclev[scene];
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int i = gl; i < 2 * nb; i += G) w[i] = z4;
+    for (int i = gl; i < Acc<W24>::FLOATS * nb; i += G) w[i] = 0.f;
     group_sync<G>(mask);
     // joints keep last step's lambda (Hinge.cpp:33-63 never zeroes it): seed w with it, level by level
     for (int lev = 1, p0 = 0; lev <= njl; ++lev) {
@@ -292,7 +322,7 @@ __global__ void __launch_bounds__(LvCfg<G>::THREADS, MINB) k_pgs_lv(View v, floa
     }
 
     // constraint forces (RigidBodySystem.cpp:185-220) in the same per-body order: w becomes fc / tauc
-    for (int i = gl; i < 2 * nb; i += G) w[i] = z4;
+    for (int i = gl; i < Acc<W24>::FLOATS * nb; i += G) w[i] = 0.f;
     group_sync<G>(mask);
     for (int lev = 1, p0 = 0; lev <= njl; ++lev) {
         const int p1 = v.jlev_end[at(v, lev, scene)];
@@ -347,8 +377,10 @@ __global__ void __launch_bounds__(LvCfg<G>::THREADS, MINB) k_pgs_lv(View v, floa
         group_sync<G>(mask);
     }
     for (int i = gl; i < nb; i += G) {
-        v.wl[at(v, i, scene)] = w[2 * i];
-        v.wa[at(v, i, scene)] = w[2 * i + 1];
+        V3 fl, fa;
+        ld_w(w, i, fl, fa);
+        v.wl[at(v, i, scene)] = mk4(fl, 0.f);
+        v.wa[at(v, i, scene)] = mk4(fa, 0.f);
     }
     if (v.profiling && gl == 0) {
         atomicAdd(&v.visit_counters[0], (unsigned long long)nc * iters);
@@ -371,23 +403,39 @@ void launch_joint_levels(const View& v, cudaStream_t s)
     k_joint_levels<<<(unsigned)((v.B + 127) / 128), 128, 0, s>>>(v);
 }
 
+// padded accumulators unless they would keep the SM below 12 warps
+static bool lv_pack24(int threads, int spc, int NB)
+{
+    return ((size_t)spc * NB * 32 + 1024) * (size_t)(12 * 32 / threads) > 227u * 1024u;
+}
+size_t level_smem_bytes(int threads, int spc, int NB) { return (size_t)spc * NB * (lv_pack24(threads, spc, NB) ? 24 : 32); }
+
 template <int G>
 static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t s)
 {
     constexpr int threads = LvCfg<G>::THREADS, spc = LvCfg<G>::SPC;
-    const size_t smem = (size_t)spc * v.NB * 2 * sizeof(float4);
+    const bool w24 = lv_pack24(threads, spc, v.NB);
+    const size_t smem = level_smem_bytes(threads, spc, v.NB);
     const unsigned blocks = (unsigned)((v.B + spc - 1) / spc);
     constexpr int lo = 12 * 32 / threads, hi = 16 * 32 / threads;       // 12 / 16 warps per SM
-    if ((size_t)blocks * threads >= 148u * 8u * 32u) k_pgs_lv<G, hi><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
-    else k_pgs_lv<G, lo><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
+    const bool many = (size_t)blocks * threads >= 148u * 8u * 32u;
+    if (w24) {
+        if (many) k_pgs_lv<G, hi, true><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
+        else k_pgs_lv<G, lo, true><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
+    } else {
+        if (many) k_pgs_lv<G, hi, false><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
+        else k_pgs_lv<G, lo, false><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
+    }
 }
 
 template <int G>
 static void init_lv()
 {
     constexpr int threads = LvCfg<G>::THREADS;
-    cudaFuncSetAttribute(k_pgs_lv<G, 12 * 32 / threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_pgs_lv<G, 16 * 32 / threads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_lv<G, 12 * 32 / threads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_lv<G, 16 * 32 / threads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_lv<G, 12 * 32 / threads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_lv<G, 16 * 32 / threads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 // per-device kernel attributes (called from slrbs_create with the device current)
 void init_level_kernels()
@@ -401,11 +449,11 @@ int level_group_size(const View& v, int requested)
     int g = requested;
     if (g != 4 && g != 8 && g != 16 && g != 32 && g != 64 && g != 128) g = v.NB < 24 ? 4 : (v.NB <= 96 ? 8 : (v.NB <= 512 ? 16 : (v.B <= 296 ? 64 : 32)));   // few wide scenes: 2 warps each
     // the accumulators of the 32 / g scenes of a warp must fit in shared memory
-    while (g < 32 && (size_t)(32 / g) * v.NB * 32 > 200 * 1024) g <<= 1;
+    while (g < 32 && (size_t)(32 / g) * v.NB * 24 > 200 * 1024) g <<= 1;
     return g;
 }
 
-bool level_mode_fits(int max_bodies) { return (size_t)max_bodies * 32 <= 200 * 1024; }
+bool level_mode_fits(int max_bodies) { return (size_t)max_bodies * 24 <= 200 * 1024; }
 
 void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, cudaStream_t s)
 {
