@@ -804,7 +804,7 @@ int slrbs_pile_set_send(slrbs_ctx* c, const void* d_gids, int n)
         CU(cudaMalloc((void**)&P.send, sizeof(int) * (size_t)cap));
         P.send_cap = cap;
     }
-    launch_pile_lookup((const int*)d_gids, n, P.loc, P.send, P.info, c->stream);
+    launch_pile_lookup((const int*)d_gids, n, P.g.n_global, P.loc, P.send, P.info, c->stream);
     int r;
     if ((r = check_launch(c))) return r;
     int flag = 0;

@@ -58,7 +58,7 @@ void launch_pile_export(const View& v, const PileGrid& g, const int* count, cons
 void launch_pile_rebuild(const View& v, const PileGrid& g, const float* table, const float* radius, const float* mass, const float* fixed10,
                          int* count, int* keys, int* loc, int* info, int* hsrc, int* hdst, int* ldst, int* lgid, int* rdst, int* rgid,
                          cudaStream_t s);
-void launch_pile_lookup(const int* gids, int n, const int* loc, int* out, int* info, cudaStream_t s);
+void launch_pile_lookup(const int* gids, int n, int n_global, const int* loc, int* out, int* info, cudaStream_t s);
 void launch_export_contacts(const View& v, int scene, int n, int* body0, int* body1, float* p3, float* n3, float* t3,
                             float* b3, float* phi, float* lam3, float* J0, float* J1, float* M0, float* M1,
                             float* A9, float* rhs3, cudaStream_t s);

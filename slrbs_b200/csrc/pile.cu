@@ -207,11 +207,13 @@ __global__ void __launch_bounds__(256) k_pile_halo_map(View v, PileGrid g, const
 }
 
 // a neighbour rank asked for the bodies `gids` (in its own order): where do their owned copies live here?
-__global__ void k_pile_lookup(const int* __restrict__ gids, int n, const int* __restrict__ loc, int* __restrict__ out, int* __restrict__ info)
+__global__ void k_pile_lookup(const int* __restrict__ gids, int n, int n_global, const int* __restrict__ loc, int* __restrict__ out,
+                              int* __restrict__ info)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int a = loc[gids[i]];
+    const int g = gids[i];
+    const int a = (g >= 0 && g < n_global) ? loc[g] : -1;
     out[i] = a < 0 ? 0 : a;
     if (a < 0) info[7] = 1;                                      // asked for a body this rank does not own
 }
@@ -239,7 +241,7 @@ void launch_pile_rebuild(const View& v, const PileGrid& g, const float* table, c
     k_pile_halo_map<<<blocks_for((size_t)g.nbdyn * v.B, 256), 256, 0, s>>>(v, g, count, keys, table, loc, info, hsrc, hdst, ldst, lgid, rdst, rgid);
 }
 
-void launch_pile_lookup(const int* gids, int n, const int* loc, int* out, int* info, cudaStream_t s)
-{ if (n > 0) k_pile_lookup<<<blocks_for((size_t)n, 256), 256, 0, s>>>(gids, n, loc, out, info); }
+void launch_pile_lookup(const int* gids, int n, int n_global, const int* loc, int* out, int* info, cudaStream_t s)
+{ if (n > 0) k_pile_lookup<<<blocks_for((size_t)n, 256), 256, 0, s>>>(gids, n, n_global, loc, out, info); }
 
 }  // namespace slrbs
