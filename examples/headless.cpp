@@ -1,0 +1,43 @@
+// headless.cpp -- the reference's main loop without the viewer (main.cpp:8-16 starts SimViewer, whose draw callback
+// builds a scene with Scenarios and calls RigidBodySystem::step(dt / subSteps) every frame, SimViewer.cpp:235-266).
+// This program is written against the reference's OWN headers and class names; compiled against
+// slrbs_b200/host/include it runs on the B200 through libslrbs_host.so / libslrbs_b200.so:
+//
+//     g++ -std=c++17 -Islrbs_b200/host/include -Iinclude examples/headless.cpp -Lslrbs_b200 -lslrbs_host -lslrbs_b200
+//
+// usage: slrbs_headless <marble_box|sphere_on_box|swinging_boxes|cylinder_on_plane|car> [steps] [solverId]
+// prints "i x y z qx qy qz qw" for every body after the last step, then "contacts N".
+#include "rigidbody/RigidBodySystem.h"
+#include "rigidbody/RigidBody.h"
+#include "rigidbody/Scenarios.h"
+#include "contact/Contact.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+int main(int argc, char* argv[])
+{
+    const std::string scene = argc > 1 ? argv[1] : "marble_box";
+    const int steps = argc > 2 ? std::atoi(argv[2]) : 100;
+    RigidBodySystem sys;
+    if (scene == "marble_box") Scenarios::createMarbleBox(sys);
+    else if (scene == "sphere_on_box") Scenarios::createSphereOnBox(sys);
+    else if (scene == "swinging_boxes") Scenarios::createSwingingBoxes(sys);
+    else if (scene == "cylinder_on_plane") Scenarios::createCylinderOnPlane(sys);
+    else if (scene == "car") Scenarios::createCarScene(sys);
+    else { std::fprintf(stderr, "unknown scene %s\n", scene.c_str()); return 2; }
+    sys.solverId = argc > 3 ? std::atoi(argv[3]) : 0;            // PGS = 0, CG = 1, CR = 2 (RigidBodySystem.h:56)
+    sys.solverIter = 10;
+    const float dt = 0.01f;                                      // SimViewer.cpp:113
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < steps; ++i) sys.step(dt);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    int i = 0;
+    for (RigidBody* b : sys.getBodies())
+        std::printf("%d %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", i++, b->x[0], b->x[1], b->x[2], b->q.x(), b->q.y(), b->q.z(), b->q.w());
+    std::printf("contacts %zu\n", sys.getContacts().size());
+    std::fprintf(stderr, "%s: %d steps in %.1f ms\n", scene.c_str(), steps, ms);
+    return 0;
+}

@@ -7,6 +7,7 @@
 #include "joint/Spherical.h"
 #include "rigidbody/RigidBody.h"
 #include "rigidbody/RigidBodySystem.h"
+#include "polyscope/polyscope.h"
 #include "util/MeshAssets.h"
 #include "util/Types.h"
 

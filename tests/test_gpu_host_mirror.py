@@ -72,3 +72,17 @@ def test_solver_iterations_and_friction_knobs():
     np.testing.assert_allclose(h.state()["w"], o.state()["w"], rtol=0, atol=2e-2)
     h.set_solver(0, 10, 0.8, True)
     h.close()
+
+
+def test_headless_program_written_against_the_reference_headers():
+    """examples/headless.cpp uses only the reference's class surface (RigidBodySystem, Scenarios, public fields);
+    built against the mirror headers it must reproduce the oracle's car after 120 steps."""
+    import os, subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "slrbs_b200", "slrbs_headless")
+    out = subprocess.run([exe, "car", "120"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l.split() for l in out.stdout.splitlines() if l and l[0].isdigit()]
+    x = np.array([[float(v) for v in l[1:4]] for l in lines], np.float32)
+    o = Oracle("car"); o.step(DT, 120)
+    np.testing.assert_allclose(x, o.state()["x"], rtol=0, atol=2e-3)
+    assert f"contacts {o.n_contacts}" in out.stdout
