@@ -328,6 +328,32 @@ def grid_partition_numpy(x, origin, block, halo_w, ncell, cx0, cx1):
     return [key[a:b].astype(np.int32) for a, b in zip(starts, ends)]
 
 
+def contact_velocity_residual(ctx, n_scenes, owned=None):
+    """Velocity-level constraint residual of the contacts a context currently holds: the largest approach speed
+    max(0, -(v0 + w0 x r0 - v1 - w1 x r1) . n) over the contacts (0 for a converged non-penetration solve), and the
+    number of contacts counted. `owned(scene)` -> boolean array over the scene's body slots: only contacts that touch
+    an owned body count (contacts between two halo copies belong to other blocks, where they are counted)."""
+    st = ctx.download_state()
+    cnt = ctx.contact_counts()
+    worst, total = 0.0, 0
+    for s in np.nonzero(cnt[:n_scenes] > 0)[0]:
+        c = ctx.contacts(int(s))
+        b0, b1 = c["body0"], c["body1"]
+        x, v, w = st["x"][s], st["v"][s], st["w"][s]
+        r0, r1 = c["p"] - x[b0], c["p"] - x[b1]
+        rel = (v[b0] + np.cross(w[b0], r0)) - (v[b1] + np.cross(w[b1], r1))
+        vn = np.einsum("ij,ij->i", rel, c["n"])
+        if owned is not None:
+            own = owned(int(s))
+            keep = own[b0] | own[b1]
+            if not keep.any():
+                continue
+            vn = vn[keep]
+        worst = max(worst, float(np.maximum(0.0, -vn).max()))
+        total += int(vn.size)
+    return worst, total
+
+
 def exchange_requests(dist, rank, world, req, n_left, n_right):
     """Request protocol of the device-side re-partition, for slabs along x (a rank's only neighbours are rank - 1 and
     rank + 1). `req` holds the global ids of the halo copies this rank needs refreshed, the left neighbour's first
@@ -497,6 +523,18 @@ class DevicePile:
             c = self.ctx.contacts(int(s))
             worst = max(worst, float(-c["phi"].min()))
         return worst
+
+    def velocity_residual(self):
+        """Residual over the contacts that touch a body this rank owns (halo-halo contacts are other blocks' business;
+        the halo copies carry their owners' post-step velocities, so owned-halo contacts measure the coupling error)."""
+        self.ctx.sync()
+
+        def owned(s):
+            keys = self.ctx.pile_scene_keys(s)
+            m = np.zeros(self.ctx.max_bodies, bool)
+            m[: keys.size] = (keys & 1) == 0
+            return m
+        return contact_velocity_residual(self.ctx, self.B, owned)
 
     def close(self):
         if self.ctx is not None:

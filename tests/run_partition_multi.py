@@ -6,7 +6,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from slrbs_b200 import Context
-from slrbs_b200.partition import DevicePile, PartitionedPile, TorchComm, sphere_pile
+from slrbs_b200.partition import DevicePile, PartitionedPile, TorchComm, contact_velocity_residual, sphere_pile
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--dims", type=int, nargs=3, default=[24, 8, 12]); ap.add_argument("--block", type=float, default=6.0)
@@ -37,15 +37,17 @@ pile.ctx.sync(); torch.cuda.synchronize()
 if world > 1: dist.barrier()
 dt = time.perf_counter() - t0
 pen = pile.max_penetration()
+res = pile.velocity_residual() if a.device_rebuild else contact_velocity_residual(pile.ctx, pile.ctx.n_scenes)
 state = pile.gather_state()
 out = dict(world=world, bodies=int(x.shape[0]), steps=a.steps, ms_per_step=1e3 * dt / a.steps, body_steps_per_s=x.shape[0] * a.steps / dt,
-           max_penetration=pen, stats=pile.stats, finite=bool(np.isfinite(state).all()))
+           max_penetration=pen, approach_speed_residual=res[0], contacts=res[1], stats=pile.stats, finite=bool(np.isfinite(state).all()))
 if rank == 0 and a.check and x.shape[0] <= 5000:
     one = PartitionedPile(x, r, m, fixed, block=max(a.dims) * 2.0 + 8.0, rebuild_every=10 ** 9, rank=0, world=1, device=local)
     one.step(5 + a.steps)
     ref = one.gather_state()
     d = np.linalg.norm(state[:, :3] - ref[:, :3], axis=1)
-    out.update(mono_max_penetration=one.max_penetration(), mean_drift=float(d.mean()), max_drift=float(d.max()),
+    mres = contact_velocity_residual(one.ctx, one.ctx.n_scenes)
+    out.update(mono_max_penetration=one.max_penetration(), mono_approach_speed_residual=mres[0], mono_contacts=mres[1], mean_drift=float(d.mean()), max_drift=float(d.max()),
                mean_height=float(state[:, 1].mean()), mono_mean_height=float(ref[:, 1].mean()),
                kinetic=float((state[:, 7:10] ** 2).sum()), mono_kinetic=float((ref[:, 7:10] ** 2).sum()))
     one.close()

@@ -74,6 +74,11 @@ def test_cut_pile_matches_single_scene_and_is_deterministic():
     assert np.isfinite(a).all() and cut.stats["rebuilds"] >= 6
     drift = np.linalg.norm(a[:, :3] - b[:, :3], axis=1)
     assert cut.max_penetration() < 0.05 and one.max_penetration() < 0.05
+    # velocity-level constraint residual (largest approach speed at a contact, m/s): the cut pile must be in the same
+    # range as the single scene, whose 10 unconverged PGS sweeps leave a residual of their own
+    from slrbs_b200.partition import contact_velocity_residual
+    r_cut, r_one = cut.velocity_residual()[0], contact_velocity_residual(one.ctx, 1)[0]
+    assert r_cut < max(3.0 * r_one, 0.5), (r_cut, r_one)
     assert drift.mean() < 0.15, drift.mean()
     assert abs(a[:, 1].mean() - b[:, 1].mean()) < 0.02
     assert a[:, 1].min() > 0.2 + 0.5 - 0.06
