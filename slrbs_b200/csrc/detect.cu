@@ -10,7 +10,11 @@
 //     non-sphere body, restricted to j > i and sorted ascending. A contact needs a centre distance
 //     below r_i + r_j + 1e-3 <= cell size - 1e-3, so the candidate set is a superset of the pairs that
 //     can touch (hash collisions only add candidates): the emitted contact list is identical.
+// k_detect_rows       one CTA per scene, one THREAD per sphere row (scenes of >= 128 bodies; the default for them).
+// k_detect_cta<GRID>  one CTA per scene, one warp per row (kept for scenes too large for k_detect_rows' shared memory).
 // k_detect_serial      one thread per scene, for scenes of a few bodies (a car has 15 pairs).
+// The kernels themselves are in detect_kernels.inl, compiled twice: namespace dref (the reference's pair dispatch) and
+// namespace dext (plus the extension pairs, slrbs_set_extensions); this file holds the shared definitions and launchers.
 #include "kernels.cuh"
 #include <cstdlib>
 #include "narrowphase.cuh"
@@ -123,7 +127,7 @@ const char* detect_variant(const View& v, int broadphase)
 
 void launch_detect(const View& v, int broadphase, cudaStream_t s)
 {
-    // broadphase: 0 = off (all pairs), 1 = hashed grid, -1 = auto (grid for scenes of >= 512 bodies)
+    // broadphase: 0 = off (all pairs), 1 = hashed grid, -1 = auto (grid for scenes of >= 128 bodies)
     const bool grid = broadphase > 0 || (broadphase < 0 && v.NB >= 128);
     int H = 64;
     while (H < v.NB && H < 4096) H <<= 1;

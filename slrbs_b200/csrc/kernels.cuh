@@ -24,7 +24,7 @@ struct PileGrid {
 };
 
 void launch_prepare(const View& v, cudaStream_t s);
-// detect.cu; broadphase: 0 all pairs, 1 hashed grid, -1 auto (grid for scenes of >= 512 bodies)
+// detect.cu; broadphase: 0 all pairs, 1 hashed grid, -1 auto (grid for scenes of >= 128 bodies)
 void launch_detect(const View& v, int broadphase, cudaStream_t s);
 bool detect_warp_fits(int NB);
 void init_detect_kernels();
