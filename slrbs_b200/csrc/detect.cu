@@ -57,7 +57,10 @@ __host__ __device__ inline size_t detect_cta_smem_ints(int NB, bool grid, int H,
     return n;
 }
 
-enum { ROW_HITS = 16, ROW_DENSE = 0xFF };
+#ifndef SLRBS_ROW_HITS
+#define SLRBS_ROW_HITS 12     // touching partners j > i kept per sphere row (fuller rows take the warp-per-row walk)
+#endif
+enum { ROW_HITS = SLRBS_ROW_HITS, ROW_DENSE = 0xFF };
 
 __host__ __device__ inline size_t detect_rows_smem_bytes(int NB, int H)
 {
@@ -109,7 +112,9 @@ static int grid_buckets(int NB)
     if (forced < 0) { const char* e = getenv("SLRBS_DETECT_HASH"); forced = e ? atoi(e) : 0; }
     auto buckets = [NB](int f) { int H = 64; while (H < NB * f && H < 8192) H <<= 1; return H; };
     if (forced > 0) return buckets(forced);
-    auto ctas = [NB](int H) { return (227 * 1024) / (detect_rows_smem_bytes(NB, H) + 1024); };
+    // resident CTAs per SM: by shared memory, and by the 64 registers x threads of the kernel
+    const int threads = NB >= 512 ? 512 : (NB >= 256 ? 256 : 128);
+    auto ctas = [NB, threads](int H) { return min((int)((227 * 1024) / (detect_rows_smem_bytes(NB, H) + 1024)), 65536 / (64 * threads)); };
     int f = 4;
     while (f > 1 && ctas(buckets(f)) < ctas(buckets(1))) f >>= 1;
     return buckets(f);
