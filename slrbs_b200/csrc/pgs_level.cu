@@ -17,6 +17,7 @@
 //                             from HBM in level order (scene-major [field][pos] so the lanes of a level
 //                             read consecutive records), group barrier between levels
 #include "kernels.cuh"
+#include <cstdlib>
 #include "pgs_math.cuh"
 
 namespace slrbs {
@@ -431,7 +432,10 @@ static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t
     constexpr int lo = 12 * 32 / threads, hi = 16 * 32 / threads;       // 12 / 16 warps per SM
     const bool many = (size_t)blocks * threads >= 148u * 8u * 32u;
     if (w24) {
-        if (many) k_pgs_lv<G, hi, true><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
+        // shared memory already keeps the SM below 12 warps here: the variant with the larger register budget (no spills)
+        static int force_hi = -1;
+        if (force_hi < 0) { const char* e = getenv("SLRBS_PGS_W24_HI"); force_hi = e ? atoi(e) : 0; }
+        if (many && force_hi) k_pgs_lv<G, hi, true><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
         else k_pgs_lv<G, lo, true><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
     } else {
         if (many) k_pgs_lv<G, hi, false><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
