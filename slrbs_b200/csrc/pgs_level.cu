@@ -438,7 +438,13 @@ static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t
         if (many && force_hi) k_pgs_lv<G, hi, true><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
         else k_pgs_lv<G, lo, true><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
     } else {
-        if (many) k_pgs_lv<G, hi, false><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
+        static int minb = -1;                                   // SLRBS_PGS_MINB: 1 = always the 170-register variant, 2 = always the 128-register one
+        if (minb < 0) { const char* e = getenv("SLRBS_PGS_MINB"); minb = e ? atoi(e) : 0; }
+        // measured (profiles/README.md): scenes of ~100-500 bodies (G = 16) run faster under the 128-register cap at every
+        // batch size (16 instead of 12 warps per SM), tiny scenes (G = 4, 8) and single wide scenes faster without it
+        const bool auto_hi = G == 16 ? true : (G == 32 ? many : false);
+        const bool use_hi = minb == 1 ? false : (minb == 2 ? true : auto_hi);
+        if (use_hi) k_pgs_lv<G, hi, false><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
         else k_pgs_lv<G, lo, false><<<blocks, threads, smem, s>>>(v, dt, iters, mu);
     }
 }
