@@ -42,7 +42,9 @@ E2E_CHUNKS = int(os.environ.get("SLRBS_E2E_CHUNKS", "8"))                  # con
 
 # workload -> (Scenarios builder, (a,b,c), contact capacity / scene, scenes / GPU, settle steps, jitter)
 WORKLOADS = {
-    "marble_box":     ("marble_box", (0, 0, 0), 768, 32768, 150, 0.01),      # the reference scene itself, 167 bodies
+    # the reference scene itself, 167 bodies; 49152 scenes = 1536 warps of the thread-per-scene solver, 10.4 per SM (12 fit;
+    # 32768 scenes leave it at 6.9 warps per SM: 3.79e8 vs 4.06e8 body-steps/s; beyond 53248 a second, ragged wave starts)
+    "marble_box":     ("marble_box", (0, 0, 0), 768, 49152, 150, 0.01),
     "car":            ("car", (0, 0, 0), 16, 262144, 50, 0.0),
     "swinging_boxes": ("swinging_boxes", (0, 0, 0), 0, 65536, 50, 0.0),
     "sphere_stack":   ("sphere_stack", (8, 0, 0), 32, 262144, 50, 0.0),
