@@ -470,7 +470,10 @@ __device__ __forceinline__ void add_force(const View& v, int body, int scene, co
     v.wa[i] = mk4(mk3(v.wa[i]) + fa, 0.f);
 }
 
-enum { PGS_THREADS = 32, PGS_STAGES = 2, PGS_MIN_CTAS = 12 };
+#ifndef SLRBS_PGS_MIN_CTAS
+#define SLRBS_PGS_MIN_CTAS 12
+#endif
+enum { PGS_THREADS = 32, PGS_STAGES = 2, PGS_MIN_CTAS = SLRBS_PGS_MIN_CTAS };
 
 __global__ void __launch_bounds__(PGS_THREADS, PGS_MIN_CTAS) k_pgs(View v, float dt, int iters, float mu)
 {
