@@ -17,6 +17,9 @@
 //                             from HBM in level order (scene-major [field][pos] so the lanes of a level
 //                             read consecutive records), group barrier between levels
 #include "kernels.cuh"
+#ifndef SLRBS_LV_LO
+#define SLRBS_LV_LO 12      // warps per SM the register allocation of the "lo" variants must allow
+#endif
 #include <cstdlib>
 #include "pgs_math.cuh"
 
@@ -429,7 +432,7 @@ static void launch_lv(const View& v, float dt, int iters, float mu, cudaStream_t
     const bool w24 = lv_pack24(threads, spc, v.NB);
     const size_t smem = level_smem_bytes(threads, spc, v.NB);
     const unsigned blocks = (unsigned)((v.B + spc - 1) / spc);
-    constexpr int lo = 12 * 32 / threads, hi = 16 * 32 / threads;       // 12 / 16 warps per SM
+    constexpr int lo = SLRBS_LV_LO * 32 / threads, hi = 16 * 32 / threads;       // 12 / 16 warps per SM
     const bool many = (size_t)blocks * threads >= 148u * 8u * 32u;
     if (w24) {
         // shared memory already keeps the SM below 12 warps here: the variant with the larger register budget (no spills)
@@ -453,9 +456,9 @@ template <int G>
 static void init_lv()
 {
     constexpr int threads = LvCfg<G>::THREADS;
-    cudaFuncSetAttribute(k_pgs_lv<G, 12 * 32 / threads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_lv<G, SLRBS_LV_LO * 32 / threads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(k_pgs_lv<G, 16 * 32 / threads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_pgs_lv<G, 12 * 32 / threads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_lv<G, SLRBS_LV_LO * 32 / threads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(k_pgs_lv<G, 16 * 32 / threads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 // per-device kernel attributes (called from slrbs_create with the device current)
