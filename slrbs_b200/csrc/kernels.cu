@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
 // K4  contact frame, Jacobian blocks, J M^-1, 3x3 diagonal block, RHS
 // ------------------------------------------------------------------------------------
 #ifndef CONTACT_ROWS_MIN_BLOCKS
-#define CONTACT_ROWS_MIN_BLOCKS 4
+#define CONTACT_ROWS_MIN_BLOCKS 5
 #endif
 struct BodyDyn { V3 x, xdot, omega, f, tau; float mass; M3 Iinv; bool fixed; };
 
