@@ -1161,12 +1161,240 @@ void orc_get_solver_blocks(orc_system* s, float h, float* Acontact9, float* rhs_
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* EXTENSION: block principal pivoting, solverId 3.    */
+/* No reference counterpart: parity unpinned. The CUDA kernel k_bpp    */
+/* follows this function operation for operation.                      */
+/*                                                                     */
+/* Unknowns: the scalar rows of all joints (insertion order, bilateral)*/
+/* then of all contacts (detection order; normal, two friction rows).  */
+/* A = J Minv J^T over non-fixed bodies + eps I (1e-5 on joint rows as */
+/* in SolverBoxPGS.cpp:143, 1e-3 on contact rows), b = buildRHS.       */
+/* Solve the box LCP  w = A lambda - b,  lo <= lambda <= hi,           */
+/*   lambda = lo => w >= 0, lambda = hi => w <= 0, else w = 0          */
+/* with lo/hi = 0/inf (normal), -/+ inf (joints), -/+ mu lambda_n      */
+/* (friction) by Judice-Pires block pivoting: each step solves the     */
+/* free rows exactly (dense Cholesky), then every infeasible row       */
+/* changes set; after 3 steps without a new minimum of infeasible rows */
+/* only the highest infeasible row is swapped. The friction bounds are */
+/* held constant while the sets settle (first pass: 0, frictionless),  */
+/* then refreshed from the pass's normal impulses, until they move by  */
+/* less than 1e-6. At most 5 * solverIter pivot steps over all passes; */
+/* the result is projected onto the bounds.                            */
+/* ------------------------------------------------------------------ */
+enum { BPP_FREE = 0, BPP_LOWER = 1, BPP_UPPER = 2 };
+enum { BPP_BILATERAL = 0, BPP_NORMAL = 1, BPP_FRICTION = 2 };
+#define BPP_TOL 1e-6f
+
+typedef struct {
+    float J0[6], J1[6], M0[6], M1[6];
+    int   b0, b1;                /* body index, -1 when fixed */
+    int   kind, parent;          /* parent: the contact's normal row */
+    float rhs, eps;
+} bpp_row;
+
+static int bpp_rows(orc_system* s, float h, bpp_row** out)
+{
+    int n = 3 * s->n_contacts;
+    for (int i = 0; i < s->n_joints; ++i) n += s->joints[i].dim;
+    bpp_row* R = (bpp_row*)calloc((size_t)(n ? n : 1), sizeof(bpp_row));
+    int k = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int cnt = pass == 0 ? s->n_joints : s->n_contacts;
+        for (int i = 0; i < cnt; ++i) {
+            con_t* c = pass == 0 ? &s->joints[i] : &s->contacts[i];
+            float b[5] = { 0, 0, 0, 0, 0 };
+            build_rhs(s, c, h, b);
+            const int first = k;
+            for (int r = 0; r < c->dim; ++r, ++k) {
+                memcpy(R[k].J0, c->J0[r], sizeof R[k].J0); memcpy(R[k].J1, c->J1[r], sizeof R[k].J1);
+                memcpy(R[k].M0, c->J0Minv[r], sizeof R[k].M0); memcpy(R[k].M1, c->J1Minv[r], sizeof R[k].M1);
+                R[k].b0 = s->bodies[c->body0].fixed ? -1 : c->body0;
+                R[k].b1 = s->bodies[c->body1].fixed ? -1 : c->body1;
+                R[k].kind = pass == 0 ? BPP_BILATERAL : (r == 0 ? BPP_NORMAL : BPP_FRICTION);
+                R[k].parent = first;
+                R[k].rhs = b[r];
+                R[k].eps = pass == 0 ? 1e-5f : 1e-3f;
+            }
+        }
+    }
+    *out = R;
+    return n;
+}
+
+static inline float dot6(const float* a, const float* b)
+{
+    float acc = 0.f;
+    for (int k = 0; k < 6; ++k) acc += a[k] * b[k];
+    return acc;
+}
+
+static float bpp_entry(const bpp_row* R, int i, int j)
+{
+    const bpp_row* a = &R[i]; const bpp_row* c = &R[j];
+    float acc = 0.f;
+    if (a->b0 >= 0) {
+        if (a->b0 == c->b0) acc += dot6(a->M0, c->J0);
+        if (a->b0 == c->b1) acc += dot6(a->M0, c->J1);
+    }
+    if (a->b1 >= 0) {
+        if (a->b1 == c->b0) acc += dot6(a->M1, c->J0);
+        if (a->b1 == c->b1) acc += dot6(a->M1, c->J1);
+    }
+    if (i == j) acc += a->eps;
+    return acc;
+}
+
+static inline float bpp_hi(const bpp_row* R, const float* lam, int i, float mu)
+{
+    const float ln = lam[R[i].parent];
+    return mu * (ln > 0.f ? ln : 0.f);
+}
+
+static void bpp_store(orc_system* s, const float* lam)
+{
+    int k = 0;
+    for (int i = 0; i < s->n_joints; ++i) for (int r = 0; r < s->joints[i].dim; ++r) s->joints[i].lambda[r] = lam[k++];
+    for (int i = 0; i < s->n_contacts; ++i) for (int r = 0; r < 3; ++r) s->contacts[i].lambda[r] = lam[k++];
+}
+
+static void solve_bpp(orc_system* s, float h)
+{
+    bpp_row* R;
+    const int n = bpp_rows(s, h, &R);
+    for (int i = 0; i < s->n_contacts; ++i) s->contacts[i].lambda[0] = s->contacts[i].lambda[1] = s->contacts[i].lambda[2] = 0.f;
+    const int maxit = 5 * s->solverIter;
+    if (n == 0 || maxit <= 0) { free(R); return; }
+    float* lam = (float*)calloc((size_t)n * 4, sizeof(float));
+    float *w = lam + n, *y = lam + 2 * n, *hi = lam + 3 * n;
+    int* state = (int*)calloc((size_t)n * 3, sizeof(int));
+    int *F = state + n, *move = state + 2 * n;
+    float* M = (float*)calloc((size_t)n * (n + 1) / 2, sizeof(float));
+#define TRI(i, j) ((size_t)(i) * ((i) + 1) / 2 + (j))
+    for (int i = 0; i < n; ++i) state[i] = R[i].kind == BPP_BILATERAL ? BPP_FREE : BPP_LOWER;
+    int best = n + 1, budget = 3, refresh = 1;
+    for (int it = 0; it < maxit; ++it) {
+        if (refresh) {
+            /* friction bounds from the normal impulses of the last converged pass (0 on the first): the pass
+             * below is a box LCP with constant bounds; a friction row of an open contact is pinned at 0 */
+            for (int i = 0; i < n; ++i) {
+                hi[i] = R[i].kind == BPP_FRICTION ? bpp_hi(R, lam, i, s->mu) : 0.f;
+                if (R[i].kind == BPP_FRICTION && hi[i] <= 0.f) state[i] = BPP_LOWER;
+            }
+            refresh = 0; best = n + 1; budget = 3;
+        }
+        int nf = 0;
+        for (int i = 0; i < n; ++i) {
+            if (state[i] == BPP_FREE) F[nf++] = i;
+            else lam[i] = R[i].kind == BPP_FRICTION ? (state[i] == BPP_LOWER ? -hi[i] : hi[i]) : 0.f;
+        }
+        /* free rows: A_FF lam_F = b_F - A_FB lam_B */
+        for (int a = 0; a < nf; ++a) {
+            for (int c = 0; c <= a; ++c) M[TRI(a, c)] = bpp_entry(R, F[a], F[c]);
+            float acc = R[F[a]].rhs;
+            for (int j = 0; j < n; ++j) if (state[j] != BPP_FREE && lam[j] != 0.f) acc -= bpp_entry(R, F[a], j) * lam[j];
+            y[a] = acc;
+        }
+        for (int k = 0; k < nf; ++k) {
+            float d = M[TRI(k, k)];
+            d = sqrtf(d > 1e-12f ? d : 1e-12f);
+            M[TRI(k, k)] = d;
+            for (int i = k + 1; i < nf; ++i) M[TRI(i, k)] /= d;
+            for (int i = k + 1; i < nf; ++i)
+                for (int j = k + 1; j <= i; ++j) M[TRI(i, j)] -= M[TRI(i, k)] * M[TRI(j, k)];
+        }
+        for (int k = 0; k < nf; ++k) {
+            y[k] /= M[TRI(k, k)];
+            for (int i = k + 1; i < nf; ++i) y[i] -= M[TRI(i, k)] * y[k];
+        }
+        for (int k = nf - 1; k >= 0; --k) {
+            y[k] /= M[TRI(k, k)];
+            for (int i = 0; i < k; ++i) y[i] -= M[TRI(k, i)] * y[k];
+        }
+        for (int a = 0; a < nf; ++a) lam[F[a]] = y[a];
+        /* residual velocities of the bound rows and the rows that must change set */
+        int ninf = 0, last = -1;
+        for (int i = 0; i < n; ++i) {
+            move[i] = -1;
+            if (R[i].kind == BPP_BILATERAL) continue;
+            if (R[i].kind == BPP_FRICTION && hi[i] <= 0.f) continue;
+            if (state[i] == BPP_FREE) {
+                if (R[i].kind == BPP_NORMAL) { if (lam[i] < -BPP_TOL) move[i] = BPP_LOWER; }
+                else if (lam[i] < -hi[i] - BPP_TOL) move[i] = BPP_LOWER;
+                else if (lam[i] > hi[i] + BPP_TOL) move[i] = BPP_UPPER;
+            } else {
+                float acc = -R[i].rhs;
+                for (int j = 0; j < n; ++j) if (lam[j] != 0.f) acc += bpp_entry(R, i, j) * lam[j];
+                w[i] = acc;
+                if (state[i] == BPP_LOWER && acc < -BPP_TOL) move[i] = BPP_FREE;
+                if (state[i] == BPP_UPPER && acc > BPP_TOL) move[i] = BPP_FREE;
+            }
+            if (move[i] >= 0) { ++ninf; last = i; }
+        }
+        if (ninf == 0) {
+            float shift = 0.f;
+            for (int i = 0; i < n; ++i) if (R[i].kind == BPP_FRICTION) {
+                const float ds = fabsf(bpp_hi(R, lam, i, s->mu) - hi[i]);
+                if (ds > shift) shift = ds;
+            }
+            if (shift <= BPP_TOL) break;       /* sets and friction bounds are both stationary */
+            refresh = 1;
+            continue;
+        }
+        int block = 1;
+        if (ninf < best) { best = ninf; budget = 3; }
+        else if (budget > 0) --budget;
+        else block = 0;
+        if (block) { for (int i = 0; i < n; ++i) if (move[i] >= 0) state[i] = move[i]; }
+        else state[last] = move[last];
+    }
+    /* admissible impulses whatever happened: project onto the bounds */
+    for (int i = 0; i < n; ++i) if (R[i].kind == BPP_NORMAL && lam[i] < 0.f) lam[i] = 0.f;
+    for (int i = 0; i < n; ++i) if (R[i].kind == BPP_FRICTION) {
+        const float nh = bpp_hi(R, lam, i, s->mu);
+        if (lam[i] < -nh) lam[i] = -nh; else if (lam[i] > nh) lam[i] = nh;
+    }
+#undef TRI
+    bpp_store(s, lam);
+    free(M); free(state); free(lam); free(R);
+}
+
+/* natural-map residual of the box LCP solve_bpp poses, for the impulses currently stored:
+ * max_i | lambda_i - clamp(lambda_i - w_i, lo_i, hi_i) |  (0 at a solution) */
+float orc_blcp_residual(orc_system* s, float h)
+{
+    bpp_row* R;
+    const int n = bpp_rows(s, h, &R);
+    float* lam = (float*)calloc((size_t)(n ? n : 1), sizeof(float));
+    int k = 0;
+    for (int i = 0; i < s->n_joints; ++i) for (int r = 0; r < s->joints[i].dim; ++r) lam[k++] = s->joints[i].lambda[r];
+    for (int i = 0; i < s->n_contacts; ++i) for (int r = 0; r < 3; ++r) lam[k++] = s->contacts[i].lambda[r];
+    float worst = 0.f;
+    for (int i = 0; i < n; ++i) {
+        float acc = -R[i].rhs;
+        for (int j = 0; j < n; ++j) acc += bpp_entry(R, i, j) * lam[j];
+        float res;
+        if (R[i].kind == BPP_BILATERAL) res = fabsf(acc);
+        else {
+            const float hi = R[i].kind == BPP_NORMAL ? INFINITY : bpp_hi(R, lam, i, s->mu);
+            const float lo = R[i].kind == BPP_NORMAL ? 0.f : -hi;
+            float z = lam[i] - acc;
+            if (z < lo) z = lo; else if (z > hi) z = hi;
+            res = fabsf(lam[i] - z);
+        }
+        if (res > worst) worst = res;
+    }
+    free(lam); free(R);
+    return worst;
+}
+
 /* calcConstraintForces head, RigidBodySystem.cpp:181-182 */
 void orc_stage_solve(orc_system* s, float dt)
 {
     switch (s->solverId) {
     case 1:  solve_conj_gradient(s, dt); break;
     case 2:  solve_conj_residual(s, dt); break;
+    case 3:  solve_bpp(s, dt); break;                 /* extension, no reference counterpart */
     default: solve_box_pgs(s, dt); break;
     }
 }

@@ -100,6 +100,9 @@ void orc_get_joints(const orc_system* s, int* type, int* body0, int* body1, floa
 void orc_get_joint_rows(const orc_system* s, float* J0_30, float* J1_30, float* J0Minv_30, float* J1Minv_30,
                         float* phi5, float* lambda5);
 void orc_set_joint_lambda(orc_system* s, const float* lambda5);
+/* EXTENSION (no reference counterpart): solver_id 3 = block principal pivoting over joints and contacts;
+ * residual of the box LCP it poses for the impulses currently stored (after orc_stage_solve) */
+float orc_blcp_residual(orc_system* s, float h);
 /* solver diagonal blocks and RHS as built before the PGS loop (SolverBoxPGS.cpp:134-211); needs jacobians */
 void orc_get_solver_blocks(orc_system* s, float h, float* Acontact9, float* rhs_contact3, float* Ajoint25, float* rhs_joint5);
 

@@ -113,6 +113,8 @@ def _bind(L):
                  "orc_scene_cylinder_on_plane", "orc_scene_car"):
         getattr(L, name).argtypes = [vp]
     L.orc_set_extensions.argtypes = [vp, C.c_int]
+    L.orc_blcp_residual.argtypes = [vp, C.c_float]
+    L.orc_blcp_residual.restype = C.c_float
     L.orc_scene_box_stack.argtypes = [vp, C.c_int]
     L.orc_scene_sphere_stack.argtypes = [vp, C.c_int]
     L.orc_scene_marble_box_n.argtypes = [vp, C.c_int, C.c_int, C.c_int]
@@ -213,6 +215,7 @@ class Oracle:
     def stage_detect(self): self.L.orc_stage_detect(self.h)
     def stage_jacobians(self): self.L.orc_stage_jacobians(self.h)
     def stage_solve(self, dt): self.L.orc_stage_solve(self.h, float(dt))
+    def blcp_residual(self, dt): return float(self.L.orc_blcp_residual(self.h, float(dt)))
     def stage_scatter(self, dt): self.L.orc_stage_scatter(self.h, float(dt))
     def stage_integrate(self, dt): self.L.orc_stage_integrate(self.h, float(dt))
     def save_state(self): self.L.orc_save_state(self.h)
