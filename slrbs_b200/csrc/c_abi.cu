@@ -138,6 +138,13 @@ int fold_events(slrbs_ctx* c)
 
 int solve_launch(slrbs_ctx* c, float dt)
 {
+    if (c->solver_id == 3) {
+        // block principal pivoting over joints and contacts (extension), then the PGS kernel with zero sweeps for the force scatter
+        launch_bpp(c->v, c->solver_iters, c->mu, c->stream);
+        if (c->v.level_mode) launch_pgs_level(c->v, dt, 0, c->mu, c->level_group, c->stream);
+        else launch_pgs(c->v, dt, 0, c->mu, c->stream);
+        return check_launch(c, 2);
+    }
     if (c->solver_id != 0) {
         // joint-only Krylov solve, then the PGS kernel with zero sweeps for the force scatter
         if (c->v.NJ > 0 && !c->v.kry) {
@@ -198,6 +205,7 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     CU(cudaSetDevice(device));
     init_detect_kernels();
     init_level_kernels();
+    init_bpp_kernel();
     init_pile_kernels();
     slrbs_ctx* c = new slrbs_ctx();
     { const char* g = std::getenv("SLRBS_GRAPH"); if (g) c->use_graph = std::atoi(g); }
@@ -265,7 +273,7 @@ void slrbs_destroy(slrbs_ctx* c)
 
 int slrbs_set_params(slrbs_ctx* c, float mu, int solver_id, int solver_iters, int collisions_enabled)
 {
-    if (!c || solver_id < 0 || solver_id > 2 || solver_iters < 0) return fail(SLRBS_E_ARG, "slrbs_set_params: bad argument");
+    if (!c || solver_id < 0 || solver_id > 3 || solver_iters < 0) return fail(SLRBS_E_ARG, "slrbs_set_params: bad argument");
     c->mu = mu; c->solver_id = solver_id; c->solver_iters = solver_iters; c->collisions = collisions_enabled ? 1 : 0;
     return 0;
 }
@@ -479,7 +487,7 @@ int slrbs_step(slrbs_ctx* c, float dt, int n_steps)
     // Replay one captured step n times: a small batch is launch-bound (5-7 kernels of a few microseconds each).
     // Anything that is not a plain launch on the stream happens before the capture.
     if (c->v.level_mode && c->joints_dirty) { launch_joint_levels(c->v, c->stream); c->joints_dirty = false; if ((r = check_launch(c))) return r; }
-    if (c->solver_id != 0 && c->v.NJ > 0 && !c->v.kry) { if ((r = dalloc(c, &c->v.kry, (size_t)7 * 5 * c->v.NJ * c->v.B))) return r; }
+    if ((c->solver_id == 1 || c->solver_id == 2) && c->v.NJ > 0 && !c->v.kry) { if ((r = dalloc(c, &c->v.kry, (size_t)7 * 5 * c->v.NJ * c->v.B))) return r; }
     const bool same = c->graph && c->gsig.dt == dt && c->gsig.mu == c->mu && c->gsig.iters == c->solver_iters &&
                       c->gsig.solver == c->solver_id && c->gsig.collisions == c->collisions && c->gsig.has_ext == c->v.has_ext;
     if (!same) {
@@ -509,7 +517,8 @@ int slrbs_sync(slrbs_ctx* c)
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(c->h_flag, c->v.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (*c->h_flag) return fail(SLRBS_E_CAPACITY, "a scene produced more contacts than max_contacts; extra contacts were dropped");
+    if (*c->h_flag & 1) return fail(SLRBS_E_CAPACITY, "a scene produced more contacts than max_contacts; extra contacts were dropped");
+    if (*c->h_flag & 2) return fail(SLRBS_E_CAPACITY, "a scene has more constraint rows than the pivoting solver holds (solver_id 3: 288 scalar rows); its impulses were left at zero");
     return 0;
 }
 

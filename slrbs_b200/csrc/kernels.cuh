@@ -34,6 +34,11 @@ void launch_contact_rows(const View& v, float h, cudaStream_t s);
 void launch_joint_rows(const View& v, float h, cudaStream_t s);
 void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s);
 void launch_krylov(const View& v, int solver_id, int iters, cudaStream_t s);
+// bpp.cu: block principal pivoting (solverId 3, extension); one CTA per scene, at most BPP_MAX_ROWS scalar rows per scene
+enum { BPP_MAX_ROWS = 288 };
+void init_bpp_kernel();
+int  bpp_row_capacity(const View& v);
+void launch_bpp(const View& v, int iters, float mu, cudaStream_t s);
 // level-scheduled solver (pgs_level.cu)
 void launch_joint_levels(const View& v, cudaStream_t s);
 void launch_contact_levels(const View& v, cudaStream_t s);

@@ -314,7 +314,7 @@ __device__ __forceinline__ void write_contacts(const View& v, int scene, int bas
                 v.cp[c] = mk4(o.p[k], o.phi[k]);
                 v.cn[c] = mk4(o.n, 0.f);
             } else {
-                *v.overflow = 1;
+                atomicOr(v.overflow, 1);
             }
         }
     }

@@ -44,7 +44,7 @@ public:
     void setExtendedContacts(bool _on) { m_extContacts = _on; }
 
     int solverIter;
-    int solverId;   // PGS = 0, Conj. Gradient = 1, Conj. Residual = 2
+    int solverId;   // PGS = 0, Conj. Gradient = 1, Conj. Residual = 2; extension: block principal pivoting = 3
 
     // ---- device controls (additions; the reference is CPU-only) ----------------------------
     void setDevice(int cudaDevice) { m_device = cudaDevice; }
@@ -69,7 +69,7 @@ private:
     ResetFunc m_resetFunc;
     // per-system solver objects (the reference keeps them in a file-static array shared by every
     // system, RigidBodySystem.cpp:17,29-31; kept per system here so batches do not alias)
-    std::unique_ptr<Solver> m_solvers[3];
+    std::unique_ptr<Solver> m_solvers[4];
 
     // device mirror
     slrbs_ctx* m_ctx = nullptr;

@@ -11,6 +11,7 @@
 #include "solvers/SolverBoxPGS.h"
 #include "solvers/SolverConjGradient.h"
 #include "solvers/SolverConjResidual.h"
+#include "solvers/SolverBPP.h"
 
 #include "slrbs_b200.h"
 
@@ -34,6 +35,7 @@ RigidBodySystem::RigidBodySystem() : solverIter(10), solverId(0), m_collisionsEn
     m_solvers[0] = std::make_unique<SolverBoxPGS>(this);
     m_solvers[1] = std::make_unique<SolverConjGradient>(this);
     m_solvers[2] = std::make_unique<SolverConjResidual>(this);
+    m_solvers[3] = std::make_unique<SolverBPP>(this);          // extension
 }
 
 RigidBodySystem::~RigidBodySystem()
@@ -319,7 +321,7 @@ void RigidBodySystem::step(float dt)
             deviceContactJacobians(dt);
         }
         // calcConstraintForces (RigidBodySystem.cpp:177-183): the selected Solver object runs the solve
-        Solver* solver = m_solvers[std::min(std::max(solverId, 0), 2)].get();
+        Solver* solver = m_solvers[std::min(std::max(solverId, 0), 3)].get();
         solver->setMaxIter(solverIter);
         solver->solve(dt);
         check(slrbs_stage_integrate(m_ctx, dt), "slrbs_stage_integrate");
@@ -336,7 +338,7 @@ void RigidBodySystem::step(float dt)
         readBack(m_contactReadback);
         return;
     }
-    throw std::runtime_error("RigidBodySystem::step: contact capacity kept overflowing");
+    throw std::runtime_error(std::string("RigidBodySystem::step: capacity kept overflowing: ") + slrbs_last_error());
 }
 
 // ---- CollisionDetect / Solver seams ---------------------------------------------------------------
@@ -352,3 +354,4 @@ void CollisionDetect::clear()
 void SolverBoxPGS::solve(float h) { m_rigidBodySystem->deviceSolve(0, m_maxIter, h); }
 void SolverConjGradient::solve(float h) { m_rigidBodySystem->deviceSolve(1, m_maxIter, h); }
 void SolverConjResidual::solve(float h) { m_rigidBodySystem->deviceSolve(2, m_maxIter, h); }
+void SolverBPP::solve(float h) { m_rigidBodySystem->deviceSolve(3, m_maxIter, h); }
