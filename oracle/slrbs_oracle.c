@@ -1179,7 +1179,7 @@ void orc_get_solver_blocks(orc_system* s, float h, float* Acontact9, float* rhs_
 /* only the highest infeasible row is swapped. The friction bounds are */
 /* held constant while the sets settle (first pass: 0, frictionless),  */
 /* then refreshed from the pass's normal impulses, until they move by  */
-/* less than 1e-6. At most 5 * solverIter pivot steps over all passes; */
+/* less than 1e-5 (1 + bound). At most 5 * solverIter pivot steps over all passes; */
 /* the result is projected onto the bounds.                            */
 /* ------------------------------------------------------------------ */
 enum { BPP_FREE = 0, BPP_LOWER = 1, BPP_UPPER = 2 };
@@ -1334,10 +1334,11 @@ static void solve_bpp(orc_system* s, float h)
         if (ninf == 0) {
             float shift = 0.f;
             for (int i = 0; i < n; ++i) if (R[i].kind == BPP_FRICTION) {
-                const float ds = fabsf(bpp_hi(R, lam, i, s->mu) - hi[i]);
+                const float nh = bpp_hi(R, lam, i, s->mu);
+                const float ds = fabsf(nh - hi[i]) / (1.0f + nh);
                 if (ds > shift) shift = ds;
             }
-            if (shift <= BPP_TOL) break;       /* sets and friction bounds are both stationary */
+            if (shift <= 1e-5f) break;         /* sets and friction bounds are both stationary */
             refresh = 1;
             continue;
         }

@@ -10,9 +10,11 @@
 // ([field][row], 24 floats + two body ids + rhs per row); entries of A = J Minv J^T + eps I are formed on
 // demand from them (two rows couple only through a shared non-fixed body, so most entries are four integer
 // compares). Each pivot step: ordered compaction of the free set (one warp, ballots), gather of A_FF into a
-// packed lower triangle in shared memory, right-looking Cholesky (pivot column cached in a vector, one warp
-// per trailing row), two triangular solves, residual velocities of the bound rows (one thread per row,
-// sequential over columns), set changes by the Judice-Pires rule. Shared memory bounds the scene at
+// packed lower triangle in shared memory, left-looking Cholesky with the forward substitution riding along as an
+// extra row (one thread per row, one barrier per column), back substitution, residual velocities of the bound
+// rows (one thread per row, sequential over columns), set changes by the Judice-Pires rule. Scenes of at most 64
+// rows run on a single warp (32-thread CTA, warp barriers) with the dense A kept in shared memory; a batch is
+// served by one launch per size class, each skipping the other classes' scenes. Shared memory bounds the scene at
 // BPP_MAX_ROWS scalar rows; a larger scene raises the context's capacity flag (bit 1) and keeps zero impulses.
 #include "kernels.cuh"
 #include "pgs_math.cuh"
@@ -21,10 +23,22 @@ namespace slrbs {
 
 enum { BPP_FREE = 0, BPP_LOWER = 1, BPP_UPPER = 2 };
 enum { BPP_BILATERAL = 0, BPP_NORMAL = 1, BPP_FRICTION = 2 };
-enum { BPP_ROW_FLOATS = 24, BPP_ROW_WORDS = 36 };     // J0 J1 M0 M1 | b0 b1 kind parent rhs lam y hi col state F move
+enum { BPP_ROW_FLOATS = 24, BPP_ROW_WORDS = 36, BPP_WARP_ROWS = 64 };     // J0 J1 M0 M1 | b0 b1 kind parent rhs lam y hi col state F move
 #define BPP_TOL 1e-6f
 
-__host__ __device__ inline size_t bpp_smem_words(int n) { return (size_t)BPP_ROW_WORDS * n + (size_t)n * (n + 1) / 2 + 8; }
+// shared-memory words of a scene of at most n rows. One-warp variant: the dense A ([n][n | 1]) is kept, and the
+// Cholesky triangle (n + 1 rows: the right-hand side is its last row) reuses the row records' space once A is formed.
+__host__ __device__ inline size_t bpp_tri_words(int n) { return (size_t)n * (n + 1) / 2; }
+__host__ __device__ inline size_t bpp_rec_words(int n, bool one_warp)
+{
+    const size_t rec = (size_t)BPP_ROW_FLOATS * n;
+    return one_warp && bpp_tri_words(n + 1) > rec ? bpp_tri_words(n + 1) : rec;
+}
+__host__ __device__ inline size_t bpp_smem_words(int n, bool one_warp)
+{
+    const size_t vec = (size_t)(BPP_ROW_WORDS - BPP_ROW_FLOATS) * n + 8;
+    return bpp_rec_words(n, one_warp) + vec + (one_warp ? (size_t)n * (n | 1) : bpp_tri_words(n + 1));
+}
 
 struct BppRows {
     int n;                     // row capacity = stride of the [field][row] arrays
@@ -69,7 +83,12 @@ __device__ __forceinline__ void bpp_put_row(const BppRows& R, int k, const float
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-__global__ void k_bpp(View v, int maxit, float mu, int cap)
+// ONE_WARP: a scene of at most 64 rows is solved by a single warp (32-thread CTA), every barrier a __syncwarp
+template <bool ONE_WARP>
+__device__ __forceinline__ void bpp_sync() { if (ONE_WARP) __syncwarp(); else __syncthreads(); }
+
+template <bool ONE_WARP>
+__global__ void k_bpp(View v, int maxit, float mu, int cap, int min_rows, int flag_overflow)
 {
     extern __shared__ float sm[];
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
@@ -78,34 +97,39 @@ __global__ void k_bpp(View v, int maxit, float mu, int cap)
     BppRows R;
     R.n = cap;
     R.Rf = sm;
-    R.b0 = (int*)(sm + BPP_ROW_FLOATS * cap); R.b1 = R.b0 + cap; R.kind = R.b1 + cap; R.parent = R.kind + cap;
+    R.b0 = (int*)(sm + bpp_rec_words(cap, ONE_WARP)); R.b1 = R.b0 + cap; R.kind = R.b1 + cap; R.parent = R.kind + cap;
     R.rhs = (float*)(R.parent + cap);
     float* lam = R.rhs + cap; float* y = lam + cap; float* hi = y + cap; float* col = hi + cap;
     int* state = (int*)(col + cap); int* F = state + cap; int* move = F + cap;
     int* ctl = move + cap;                        // [0] ninf [1] last [2] shift bits [3] nf
-    float* M = (float*)(ctl + 8);
+    float* M = ONE_WARP ? sm : (float*)(ctl + 8);
+    const float* Ad = (const float*)(ctl + 8);    // one-warp variant: dense A, row stride ld
+    const int ld = cap | 1;
+    auto entry = [&](int i, int j) { return ONE_WARP ? Ad[i * ld + j] : bpp_entry(R, i, j); };
 
-    if (3 * nj + 3 * nc > cap) {                   // every joint has at least three rows; uniform per CTA
-        if (tid == 0) atomicOr(v.overflow, 2);
+    // a batch is served by one launch per size class (launch_bpp); this CTA skips a scene that belongs to another
+    // class. All exits below are uniform per CTA.
+    if (3 * nj + 3 * nc > cap) {                   // every joint has at least three rows
+        if (flag_overflow && tid == 0) atomicOr(v.overflow, 2);
         return;
     }
     // joint row offsets: dims into move[], serial prefix by one thread (a scene has a handful of joints)
     for (int s = tid; s < nj; s += T) move[s] = __float_as_int(__ldg(&v.jrow[at_jrow(v, 16, joint_pos(v, s, scene), scene)]).z);
-    __syncthreads();
+    bpp_sync<ONE_WARP>();
     if (tid == 0) {
         int acc = 0;
         for (int s = 0; s < nj; ++s) { const int d = move[s]; F[s] = acc; acc += d; }
         ctl[3] = acc;
     }
-    __syncthreads();
+    bpp_sync<ONE_WARP>();
     const int njr = ctl[3];
     const int n = njr + 3 * nc;
-    if (n > cap) {                                 // uniform per CTA
-        if (tid == 0) atomicOr(v.overflow, 2);
+    if (n > cap) {
+        if (flag_overflow && tid == 0) atomicOr(v.overflow, 2);
         return;
     }
-    if (n == 0 || maxit <= 0) return;
-    __syncthreads();
+    if (n == 0 || n < min_rows || maxit <= 0) return;
+    bpp_sync<ONE_WARP>();
 
     for (int s = tid; s < nj; s += T) {
         JointRec r;
@@ -158,12 +182,17 @@ __global__ void k_bpp(View v, int maxit, float mu, int cap)
             R.rhs[k] = Fr[3 + a].w;
         }
     }
-    __syncthreads();
+    bpp_sync<ONE_WARP>();
     for (int i = tid; i < n; i += T) { lam[i] = 0.f; state[i] = R.kind[i] == BPP_BILATERAL ? BPP_FREE : BPP_LOWER; }
-    __syncthreads();
+    if (ONE_WARP) {
+        float* A = (float*)(ctl + 8);
+        for (int e = tid; e < n * n; e += T) { const int i = e / n, j = e - i * n; A[i * ld + j] = bpp_entry(R, i, j); }
+    }
+    bpp_sync<ONE_WARP>();
 
-    int best = n + 1, budget = 3, refresh = 1;
+    int best = n + 1, budget = 3, refresh = 1, steps = 0;
     for (int it = 0; it < maxit; ++it) {
+        ++steps;
         if (refresh) {
             for (int i = tid; i < n; i += T) {
                 float h = 0.f;
@@ -175,7 +204,7 @@ __global__ void k_bpp(View v, int maxit, float mu, int cap)
                 hi[i] = h;
             }
             refresh = 0; best = n + 1; budget = 3;
-            __syncthreads();
+            bpp_sync<ONE_WARP>();
         }
         // free list in ascending order (warp 0), bound values
         if (warp == 0) {
@@ -191,56 +220,54 @@ __global__ void k_bpp(View v, int maxit, float mu, int cap)
         }
         for (int i = tid; i < n; i += T)
             if (state[i] != BPP_FREE) lam[i] = R.kind[i] == BPP_FRICTION ? (state[i] == BPP_LOWER ? -hi[i] : hi[i]) : 0.f;
-        __syncthreads();
+        bpp_sync<ONE_WARP>();
         const int nf = ctl[3];
         // A_FF (packed lower triangle) and the right-hand side b_F - A_FB lam_B
         for (int a = warp; a < nf; a += nw) {
             const int ia = F[a];
-            for (int c = lane; c <= a; c += 32) M[tri(a, c)] = bpp_entry(R, ia, F[c]);
+            for (int c = lane; c <= a; c += 32) M[tri(a, c)] = entry(ia, F[c]);
         }
         for (int a = tid; a < nf; a += T) {
             const int ia = F[a];
             float acc = R.rhs[ia];
-            for (int j = 0; j < n; ++j) if (state[j] != BPP_FREE && lam[j] != 0.f) acc -= bpp_entry(R, ia, j) * lam[j];
-            y[a] = acc;
+            for (int j = 0; j < n; ++j) if (state[j] != BPP_FREE && lam[j] != 0.f) acc -= entry(ia, j) * lam[j];
+            M[tri(nf, a)] = acc;                   // the right-hand side rides along as row nf of the triangle
         }
-        // right-looking Cholesky
-        for (int k = 0; k < nf; ++k) {
-            __syncthreads();
-            float d = M[tri(k, k)];
-            d = sqrtf(d > 1e-12f ? d : 1e-12f);
-            for (int i = k + 1 + tid; i < nf; i += T) { const float c = M[tri(i, k)] / d; M[tri(i, k)] = c; col[i] = c; }
-            __syncthreads();
-            if (tid == 0) M[tri(k, k)] = d;
-            for (int i = k + 1 + warp; i < nf; i += nw) {
-                const float ci = col[i];
-                const int ro = tri(i, 0);
-                for (int j = k + 1 + lane; j <= i; j += 32) M[ro + j] -= ci * col[j];
+        // Cholesky and L z = y in one left-looking pass, one thread per row: element (i, c) takes its updates in
+        // the order k = 0 .. c-1 exactly as the right-looking loop of the restatement applies them, and every
+        // thread recomputes the pivot of its column from the same numbers (no second barrier per column).
+        // Row c's diagonal slot keeps A(c, c); the pivots live in col[].
+        for (int c = 0; c < nf; ++c) {
+            bpp_sync<ONE_WARP>();
+            const int rc = tri(c, 0);
+            for (int i = c + tid; i <= nf; i += T) {
+                const int ri = tri(i, 0);
+                float acc = M[ri + c], dc = M[rc + c];
+                for (int j = 0; j < c; ++j) { const float lc = M[rc + j]; acc -= M[ri + j] * lc; dc -= lc * lc; }
+                dc = sqrtf(dc > 1e-12f ? dc : 1e-12f);
+                if (i == c) col[c] = dc; else M[ri + c] = acc / dc;
             }
         }
-        // L z = y (z in col), then L^T x = z (x in y)
-        for (int k = 0; k < nf; ++k) {
-            __syncthreads();
-            const float yk = y[k] / M[tri(k, k)];
-            for (int i = k + 1 + tid; i < nf; i += T) y[i] -= M[tri(i, k)] * yk;
-            if (tid == 0) col[k] = yk;
-        }
+        bpp_sync<ONE_WARP>();
+        // L^T x = z: z from row nf into y, x back into row nf
+        for (int a = tid; a < nf; a += T) y[a] = M[tri(nf, a)];
         for (int k = nf - 1; k >= 0; --k) {
-            __syncthreads();
-            const float xk = col[k] / M[tri(k, k)];
-            for (int i = tid; i < k; i += T) col[i] -= M[tri(k, i)] * xk;
-            if (tid == 0) y[k] = xk;
+            bpp_sync<ONE_WARP>();
+            const float xk = y[k] / col[k];
+            for (int i = tid; i < k; i += T) y[i] -= M[tri(k, i)] * xk;
+            if (tid == 0) M[tri(nf, k)] = xk;
         }
-        __syncthreads();
-        for (int a = tid; a < nf; a += T) lam[F[a]] = y[a];
-        __syncthreads();
+        bpp_sync<ONE_WARP>();
+        for (int a = tid; a < nf; a += T) lam[F[a]] = M[tri(nf, a)];
+        bpp_sync<ONE_WARP>();
         // residual velocities of the bound rows, rows that must change set, drift of the friction bounds
         for (int i = tid; i < n; i += T) {
             int mv = -1;
             const int kind = R.kind[i];
             if (kind == BPP_FRICTION) {
                 const float ln = lam[R.parent[i]];
-                const float ds = fabsf(mu * (ln > 0.f ? ln : 0.f) - hi[i]);
+                const float nh = mu * (ln > 0.f ? ln : 0.f);
+                const float ds = fabsf(nh - hi[i]) / (1.0f + nh);
                 atomicMax(&ctl[2], __float_as_int(ds));
             }
             if (kind != BPP_BILATERAL && !(kind == BPP_FRICTION && hi[i] <= 0.f)) {
@@ -251,7 +278,7 @@ __global__ void k_bpp(View v, int maxit, float mu, int cap)
                     else if (lam[i] > hi[i] + BPP_TOL) mv = BPP_UPPER;
                 } else {
                     float acc = -R.rhs[i];
-                    for (int j = 0; j < n; ++j) if (lam[j] != 0.f) acc += bpp_entry(R, i, j) * lam[j];
+                    for (int j = 0; j < n; ++j) if (lam[j] != 0.f) acc += entry(i, j) * lam[j];
                     if (st == BPP_LOWER && acc < -BPP_TOL) mv = BPP_FREE;
                     if (st == BPP_UPPER && acc > BPP_TOL) mv = BPP_FREE;
                 }
@@ -259,13 +286,13 @@ __global__ void k_bpp(View v, int maxit, float mu, int cap)
             move[i] = mv;
             if (mv >= 0) { atomicAdd(&ctl[0], 1); atomicMax(&ctl[1], i); }
         }
-        __syncthreads();
+        bpp_sync<ONE_WARP>();
         const int ninf = ctl[0], last = ctl[1];
         const float shift = __int_as_float(ctl[2]);
         if (ninf == 0) {
-            if (shift <= BPP_TOL) break;
+            if (shift <= 1e-5f) break;
             refresh = 1;
-            __syncthreads();                      // ctl is reset by warp 0 at the top of the next step
+            bpp_sync<ONE_WARP>();                      // ctl is reset by warp 0 at the top of the next step
             continue;
         }
         bool block = true;
@@ -274,18 +301,19 @@ __global__ void k_bpp(View v, int maxit, float mu, int cap)
         else block = false;
         if (block) { for (int i = tid; i < n; i += T) if (move[i] >= 0) state[i] = move[i]; }
         else if (tid == 0) state[last] = move[last];
-        __syncthreads();
+        bpp_sync<ONE_WARP>();
     }
-    __syncthreads();
+    bpp_sync<ONE_WARP>();
+    if (v.profiling && tid == 0) atomicAdd(&v.visit_counters[0], (unsigned long long)steps);     // pivot steps
     // project onto the bounds (normal rows first: the friction bounds use the projected normals), store
     for (int i = tid; i < n; i += T) if (R.kind[i] == BPP_NORMAL && lam[i] < 0.f) lam[i] = 0.f;
-    __syncthreads();
+    bpp_sync<ONE_WARP>();
     for (int i = tid; i < n; i += T) if (R.kind[i] == BPP_FRICTION) {
         const float ln = lam[R.parent[i]];
         const float h = mu * (ln > 0.f ? ln : 0.f);
         if (lam[i] < -h) lam[i] = -h; else if (lam[i] > h) lam[i] = h;
     }
-    __syncthreads();
+    bpp_sync<ONE_WARP>();
     for (int s = tid; s < nc; s += T) {
         const int k = njr + 3 * s;
         v.crow[at_crow(v, CROW_LAMBDA, contact_pos(v, s, scene), scene)] = make_float4(lam[k], lam[k + 1], lam[k + 2], 0.f);
@@ -310,14 +338,32 @@ int bpp_row_capacity(const View& v)
 
 void init_bpp_kernel()
 {
-    cudaFuncSetAttribute(k_bpp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bpp_smem_words(BPP_MAX_ROWS) * sizeof(float)));
+    cudaFuncSetAttribute(k_bpp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bpp_smem_words(BPP_MAX_ROWS, false) * sizeof(float)));
+    cudaFuncSetAttribute(k_bpp<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_bpp<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-void launch_bpp(const View& v, int iters, float mu, cudaStream_t s)
+// One launch per size class; every launch covers all scenes and a scene is solved by the smallest class that holds
+// its rows (a CTA of another class exits at once), so shared memory per CTA -- and with it the number of scenes
+// resident on an SM -- follows the scene's size rather than the context's capacity.
+int launch_bpp(const View& v, int iters, float mu, cudaStream_t s)
 {
+    static const int classes[] = { 32, 48, BPP_WARP_ROWS, 96, 144, 208, BPP_MAX_ROWS };
     const int cap = bpp_row_capacity(v);
-    const int threads = cap <= 64 ? 64 : 256;
-    k_bpp<<<(unsigned)v.B, threads, bpp_smem_words(cap) * sizeof(float), s>>>(v, 5 * iters, mu, cap);
+    int prev = 0, launches = 0;
+    for (int cls : classes) {
+        const int c = cls < cap ? cls : cap;
+        const int min_rows = prev ? prev + 1 : 0, last = c == cap;
+        if (c <= BPP_WARP_ROWS)
+            k_bpp<true><<<(unsigned)v.B, 32, bpp_smem_words(c, true) * sizeof(float), s>>>(v, 5 * iters, mu, c, min_rows, last);
+        else
+            k_bpp<false><<<(unsigned)v.B, c <= 96 ? 64 : (c <= 144 ? 128 : 256), bpp_smem_words(c, false) * sizeof(float), s>>>(
+                v, 5 * iters, mu, c, min_rows, last);
+        ++launches;
+        prev = c;
+        if (last) break;
+    }
+    return launches;
 }
 
 }  // namespace slrbs

@@ -138,23 +138,9 @@ int fold_events(slrbs_ctx* c)
 
 int solve_launch(slrbs_ctx* c, float dt)
 {
-    if (c->solver_id == 3) {
-        // block principal pivoting over joints and contacts (extension), then the PGS kernel with zero sweeps for the force scatter
-        launch_bpp(c->v, c->solver_iters, c->mu, c->stream);
-        if (c->v.level_mode) launch_pgs_level(c->v, dt, 0, c->mu, c->level_group, c->stream);
-        else launch_pgs(c->v, dt, 0, c->mu, c->stream);
-        return check_launch(c, 2);
-    }
-    if (c->solver_id != 0) {
-        // joint-only Krylov solve, then the PGS kernel with zero sweeps for the force scatter
-        if (c->v.NJ > 0 && !c->v.kry) {
-            int r = dalloc(c, &c->v.kry, (size_t)7 * 5 * c->v.NJ * c->v.B);
-            if (r) return r;
-        }
-        launch_krylov(c->v, c->solver_id, c->solver_iters, c->stream);
-        if (c->v.level_mode) launch_pgs_level(c->v, dt, 0, c->mu, c->level_group, c->stream);
-        else launch_pgs(c->v, dt, 0, c->mu, c->stream);
-        return check_launch(c, 2);
+    if ((c->solver_id == 1 || c->solver_id == 2) && c->v.NJ > 0 && !c->v.kry) {
+        int r = dalloc(c, &c->v.kry, (size_t)7 * 5 * c->v.NJ * c->v.B);
+        if (r) return r;
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->profiling) {
@@ -163,10 +149,16 @@ int solve_launch(slrbs_ctx* c, float dt)
         e0 = c->ev[c->ev_used]; e1 = c->ev[c->ev_used + 1]; c->ev_used += 2;
         CU(cudaEventRecord(e0, c->stream));
     }
-    if (c->v.level_mode) launch_pgs_level(c->v, dt, c->solver_iters, c->mu, c->level_group, c->stream);
-    else launch_pgs(c->v, dt, c->solver_iters, c->mu, c->stream);
+    // solvers 1-3 write their impulses, then the PGS kernel runs with zero sweeps for the force scatter:
+    // 1, 2 joint-only Krylov solves; 3 block principal pivoting over joints and contacts (extension)
+    int launches = 1;
+    int sweeps = c->solver_iters;
+    if (c->solver_id == 3) { launches = 1 + launch_bpp(c->v, c->solver_iters, c->mu, c->stream); sweeps = 0; }
+    else if (c->solver_id != 0) { launch_krylov(c->v, c->solver_id, c->solver_iters, c->stream); sweeps = 0; launches = 2; }
+    if (c->v.level_mode) launch_pgs_level(c->v, dt, sweeps, c->mu, c->level_group, c->stream);
+    else launch_pgs(c->v, dt, sweeps, c->mu, c->stream);
     if (c->profiling) { CU(cudaEventRecord(e1, c->stream)); c->solve_launches++; }
-    return check_launch(c);
+    return check_launch(c, launches);
 }
 
 }  // namespace

@@ -38,7 +38,7 @@ void launch_krylov(const View& v, int solver_id, int iters, cudaStream_t s);
 enum { BPP_MAX_ROWS = 288 };
 void init_bpp_kernel();
 int  bpp_row_capacity(const View& v);
-void launch_bpp(const View& v, int iters, float mu, cudaStream_t s);
+int  launch_bpp(const View& v, int iters, float mu, cudaStream_t s);   // returns the number of launches
 // level-scheduled solver (pgs_level.cu)
 void launch_joint_levels(const View& v, cudaStream_t s);
 void launch_contact_levels(const View& v, cudaStream_t s);

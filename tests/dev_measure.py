@@ -12,13 +12,16 @@ ap.add_argument("--scene", default="marble_box"); ap.add_argument("--B", type=in
 ap.add_argument("--nc", type=int, default=1024); ap.add_argument("--settle", type=int, default=200)
 ap.add_argument("--steps", type=int, default=20); ap.add_argument("--k", type=int, default=8)
 ap.add_argument("--mode", default=""); ap.add_argument("--group", default="")
+ap.add_argument("--solver", type=int, default=0); ap.add_argument("--ext", type=int, default=0)
 a = ap.parse_args()
 if a.mode: os.environ["SLRBS_PGS_MODE"] = a.mode
 if a.group: os.environ["SLRBS_LEVEL_GROUP"] = a.group
-o = Oracle(a.scene, k=a.k) if a.scene == "sphere_stack" else (Oracle("marble_box_n", nx=10, nz=10, ny=10) if a.scene == "mb1k" else Oracle(a.scene))
+o = Oracle(a.scene, k=a.k) if a.scene in ("sphere_stack", "box_stack") else (Oracle("marble_box_n", nx=10, nz=10, ny=10) if a.scene == "mb1k" else Oracle(a.scene))
 s = scene_arrays(o)
 B, nb, nj = a.B, o.n_bodies, o.n_joints
 ctx = Context(B, nb, nj, a.nc)
+ctx.set_params(solver_id=a.solver)
+if a.ext: ctx.set_extensions(1)
 rng = np.random.default_rng(1234)
 x = np.broadcast_to(s["x"], (B, nb, 3)).copy()
 dyn = s["fixed"] == 0
@@ -28,6 +31,15 @@ ctx.upload_bodies(x, s["q"], s["v"], s["w"], s["mass"], s["ibody"], s["ibodyinv"
 if nj: ctx.upload_joints(s["jtype"], s["jb0"], s["jb1"], s["r0"], s["q0"], s["r1"], s["q1"])
 t0 = time.time(); ctx.step(0.01, a.settle); ctx.sync(); t1 = time.time()
 print(f"settle {a.settle} steps: {t1-t0:.3f}s  contacts/scene mean {ctx.contact_counts().mean():.1f} max {ctx.contact_counts().max()}")
+if a.solver:
+    t0 = time.time(); ctx.step(0.01, a.steps); ctx.sync(); t1 = time.time()
+    dt = (t1 - t0) / a.steps
+    print(f"{a.scene} B={B} solver {a.solver}: {dt*1e3:.3f} ms/step  {B*nb/dt/1e6:.1f} M body-steps/s")
+    if a.solver == 3:
+        ctx.profile_enable(True); ctx.profile_read(True); ctx.step(0.01, 5); ctx.sync()
+        p = ctx.profile_read(True)
+        print(f"  pivot steps per scene-solve: {p['contact_visits'] / (5 * B):.2f}  solve {p['solve_ms'] / 5:.3f} ms/step")
+    sys.exit(0)
 ctx.profile_enable(True); ctx.profile_read(True)
 t0 = time.time(); ctx.step(0.01, a.steps); ctx.sync(); t1 = time.time()
 p = ctx.profile_read(True)
