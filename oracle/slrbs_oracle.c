@@ -1179,8 +1179,8 @@ void orc_get_solver_blocks(orc_system* s, float h, float* Acontact9, float* rhs_
 /* only the highest infeasible row is swapped. The friction bounds are */
 /* held constant while the sets settle (first pass: 0, frictionless),  */
 /* then refreshed from the pass's normal impulses, until they move by  */
-/* less than 1e-5 (1 + bound). At most 5 * solverIter pivot steps over all passes; */
-/* the result is projected onto the bounds.                            */
+/* less than 1e-5 (1 + bound). At most 5 * solverIter pivot steps over */
+/* all passes; the result is projected onto the bounds.                */
 /* ------------------------------------------------------------------ */
 enum { BPP_FREE = 0, BPP_LOWER = 1, BPP_UPPER = 2 };
 enum { BPP_BILATERAL = 0, BPP_NORMAL = 1, BPP_FRICTION = 2 };

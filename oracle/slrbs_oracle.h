@@ -25,6 +25,10 @@
  * decide last-bit rounding only.  The known answers of SURVEY.md Appendix B
  * (tests/test_oracle_known_answers.py) and analytic invariants remain as independent checks.
  *
+ * EXTENSIONS without a reference counterpart -- PARITY UNPINNED for these, by construction: the contact pairs behind
+ * orc_set_extensions (sphere-plane, box-plane, box-box) and solver_id 3 (block principal pivoting, solve_bpp).  The
+ * restatement DEFINES them; the device is compared with it, and physics is checked on residuals and resting scenes.
+ *
  * Third-party arithmetic restated: Eigen, tag 3.4 (CMakeLists.txt:24-33, not
  * vendored).  Operation orders chosen (documented in slrbs_oracle.c "eig_*"):
  *   - fixed-size 3-term reductions (dot, squaredNorm, 3x3 products) use Eigen's
