@@ -10,6 +10,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #include <time.h>
 
@@ -158,6 +159,7 @@ typedef struct {
     v3    dim;             /* box */
     float height;          /* cylinder */
     v3    plane_p, plane_n;
+    int   shape;           /* ORC_SDF: index into sys->shapes (extension) */
     int  *contacts; int n_contacts, cap_contacts;   /* indices into sys->contacts, detection order */
     int  *joints;   int n_joints,   cap_joints;     /* indices into sys->joints, insertion order   */
     /* RigidBodyState snapshot */
@@ -175,7 +177,17 @@ typedef struct {
     v3    p, n, t, b; float pene;    /* contact only */
 } con_t;
 
+/* EXTENSION: a triangle mesh as a signed-distance grid (negative inside) plus its vertices as sample points, both in
+ * the body frame; node (i, j, k) sits at origin + cell * (i, j, k), value grid[(k * ny + j) * nx + i] */
+typedef struct {
+    int   nx, ny, nz, nv;
+    v3    origin; float cell, radius;     /* radius: largest vertex norm (bounding sphere about the body origin) */
+    v3    bbmin, bbmax;
+    float *grid, *verts;
+} sdf_shape;
+
 struct orc_system {
+    sdf_shape *shapes; int n_shapes, cap_shapes;
     body_t *bodies;   int n_bodies,   cap_bodies;
     con_t  *joints;   int n_joints,   cap_joints;
     con_t  *contacts; int n_contacts, cap_contacts;
@@ -211,6 +223,8 @@ void orc_destroy(orc_system* s)
 {
     if (!s) return;
     orc_clear(s);
+    for (int i = 0; i < s->n_shapes; ++i) { free(s->shapes[i].grid); free(s->shapes[i].verts); }
+    free(s->shapes);
     free(s->bodies); free(s->joints); free(s->contacts);
     free(s);
 }
@@ -229,6 +243,7 @@ static m3 compute_inertia(const body_t* b, float mass)
         I.m[0][0] = I.m[1][1] = I.m[2][2] = (2.0f / 5.0f) * mass * b->radius * b->radius;
         break;
     case ORC_BOX:
+    case ORC_SDF:
         I.m[0][0] = (1.0f / 12.0f) * mass * (b->dim.y * b->dim.y + b->dim.z * b->dim.z);
         I.m[1][1] = (1.0f / 12.0f) * mass * (b->dim.x * b->dim.x + b->dim.z * b->dim.z);
         I.m[2][2] = (1.0f / 12.0f) * mass * (b->dim.x * b->dim.x + b->dim.y * b->dim.y);
@@ -265,6 +280,10 @@ int orc_add_body(orc_system* s, float mass, int geom_type, const float* g, int f
     case ORC_BOX:      b->dim = V3(g[0], g[1], g[2]); break;
     case ORC_PLANE:    b->plane_p = V3(g[0], g[1], g[2]); b->plane_n = V3(g[3], g[4], g[5]); break;
     case ORC_CYLINDER: b->height = g[0]; b->radius = g[1]; break;
+    case ORC_SDF:      /* extension: inertia of the solid box around the mesh vertices */
+        b->shape = (int)g[0];
+        b->dim = v3_sub(s->shapes[b->shape].bbmax, s->shapes[b->shape].bbmin);
+        break;
     }
     b->x = x3 ? V3(x3[0], x3[1], x3[2]) : V3(0, 0, 0);
     if (q) { b->q.x = q[0]; b->q.y = q[1]; b->q.z = q[2]; b->q.w = q[3]; } else b->q = q_identity();
@@ -670,6 +689,232 @@ static void ext_box_box(orc_system* s, int i0, int i1)
 }
 
 /* CollisionDetect::detectCollisions, CollisionDetect.cpp:27-76 */
+/* ------------------------------------------------------------------ */
+/* EXTENSION: triangle meshes as signed-distance grids. */
+/* No reference counterpart (the reference has no SDF code): parity    */
+/* unpinned; csrc/sdf.cuh follows these routines operation for         */
+/* operation so contact lists can be compared bit for bit.             */
+/* ------------------------------------------------------------------ */
+int orc_add_sdf_shape(orc_system* s, int nx, int ny, int nz, const float* origin3, float cell, const float* grid,
+                      int nv, const float* verts)
+{
+    if (s->n_shapes == s->cap_shapes) {
+        s->cap_shapes = s->cap_shapes ? s->cap_shapes * 2 : 4;
+        s->shapes = (sdf_shape*)realloc(s->shapes, (size_t)s->cap_shapes * sizeof(sdf_shape));
+    }
+    sdf_shape* S = &s->shapes[s->n_shapes];
+    S->nx = nx; S->ny = ny; S->nz = nz; S->nv = nv;
+    S->origin = V3(origin3[0], origin3[1], origin3[2]); S->cell = cell;
+    S->grid = (float*)malloc((size_t)nx * ny * nz * sizeof(float));
+    memcpy(S->grid, grid, (size_t)nx * ny * nz * sizeof(float));
+    S->verts = (float*)malloc((size_t)nv * 3 * sizeof(float));
+    memcpy(S->verts, verts, (size_t)nv * 3 * sizeof(float));
+    S->radius = 0.f;
+    S->bbmin = V3(1e30f, 1e30f, 1e30f); S->bbmax = V3(-1e30f, -1e30f, -1e30f);
+    for (int i = 0; i < nv; ++i) {
+        const v3 p = V3(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]);
+        const float r = v3_norm(p);
+        if (r > S->radius) S->radius = r;
+        S->bbmin = V3(fminf(S->bbmin.x, p.x), fminf(S->bbmin.y, p.y), fminf(S->bbmin.z, p.z));
+        S->bbmax = V3(fmaxf(S->bbmax.x, p.x), fmaxf(S->bbmax.y, p.y), fmaxf(S->bbmax.z, p.z));
+    }
+    return s->n_shapes++;
+}
+
+/* closest point of triangle abc to p (Voronoi-region walk) */
+static v3 closest_on_triangle(v3 p, v3 a, v3 b, v3 c)
+{
+    const v3 ab = v3_sub(b, a), ac = v3_sub(c, a), ap = v3_sub(p, a);
+    const float d1 = v3_dot(ab, ap), d2 = v3_dot(ac, ap);
+    if (d1 <= 0.f && d2 <= 0.f) return a;
+    const v3 bp = v3_sub(p, b);
+    const float d3 = v3_dot(ab, bp), d4 = v3_dot(ac, bp);
+    if (d3 >= 0.f && d4 <= d3) return b;
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) return v3_add(a, v3_scale(d1 / (d1 - d3), ab));
+    const v3 cp = v3_sub(p, c);
+    const float d5 = v3_dot(ab, cp), d6 = v3_dot(ac, cp);
+    if (d6 >= 0.f && d5 <= d6) return c;
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) return v3_add(a, v3_scale(d2 / (d2 - d6), ac));
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f)
+        return v3_add(b, v3_scale((d4 - d3) / ((d4 - d3) + (d5 - d6)), v3_sub(c, b)));
+    const float denom = 1.0f / (va + vb + vc);
+    return v3_add(a, v3_add(v3_scale(vb * denom, ab), v3_scale(vc * denom, ac)));
+}
+
+/* does the ray p + t d, t > 0, cross triangle abc (Moller-Trumbore) */
+static int ray_hits_triangle(v3 p, v3 d, v3 a, v3 b, v3 c)
+{
+    const v3 e1 = v3_sub(b, a), e2 = v3_sub(c, a);
+    const v3 h = v3_cross(d, e2);
+    const float det = v3_dot(e1, h);
+    if (fabsf(det) < 1e-12f) return 0;
+    const float f = 1.0f / det;
+    const v3 sv = v3_sub(p, a);
+    const float u = f * v3_dot(sv, h);
+    if (u < 0.f || u > 1.f) return 0;
+    const v3 q = v3_cross(sv, e1);
+    const float w = f * v3_dot(d, q);
+    if (w < 0.f || u + w > 1.f) return 0;
+    return f * v3_dot(e2, q) > 0.f;
+}
+
+/* signed distance of every grid node to a closed triangle mesh: distance to the closest triangle, negative when a ray in
+ * a fixed skew direction crosses the surface an odd number of times */
+void orc_build_sdf(int nv, const float* verts, int nt, const int* tris, int nx, int ny, int nz, const float* origin3,
+                   float cell, float* out)
+{
+    (void)nv;
+    const v3 dir = V3(0.9f, 0.3137f, 0.2918f);
+    for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+        const v3 p = V3(origin3[0] + cell * (float)i, origin3[1] + cell * (float)j, origin3[2] + cell * (float)k);
+        float best = 1e30f;
+        int crossings = 0;
+        for (int t = 0; t < nt; ++t) {
+            const float* pa = verts + 3 * tris[3 * t]; const float* pb = verts + 3 * tris[3 * t + 1]; const float* pc = verts + 3 * tris[3 * t + 2];
+            const v3 a = V3(pa[0], pa[1], pa[2]), b = V3(pb[0], pb[1], pb[2]), c = V3(pc[0], pc[1], pc[2]);
+            const float d2 = v3_sqnorm(v3_sub(p, closest_on_triangle(p, a, b, c)));
+            if (d2 < best) best = d2;
+            crossings += ray_hits_triangle(p, dir, a, b, c);
+        }
+        const float d = sqrtf(best);
+        out[((size_t)k * ny + j) * nx + i] = (crossings & 1) ? -d : d;
+    }
+}
+
+/* 'v x y z' and 'f a/b/c ...' lines as OBJLoader::load reads them (src/util/OBJLoader.cpp:34-122): first index of each
+ * face token, 1-based, faces are triangles. Returns 0 on success. */
+int orc_load_obj(const char* path, float* verts, int max_v, int* tris, int max_t, int* nv_out, int* nt_out)
+{
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    char line[512];
+    int nv = 0, nt = 0;
+    while (fgets(line, sizeof line, f)) {
+        if (line[0] == 'v' && line[1] == ' ') {
+            float x, y, z;
+            if (sscanf(line + 2, "%f %f %f", &x, &y, &z) == 3 && nv < max_v) { verts[3 * nv] = x; verts[3 * nv + 1] = y; verts[3 * nv + 2] = z; ++nv; }
+        } else if (line[0] == 'f' && line[1] == ' ') {
+            int idx[3], k = 0;
+            for (char* tok = strtok(line + 2, " \t\r\n"); tok && k < 3; tok = strtok(NULL, " \t\r\n")) idx[k++] = atoi(tok);
+            if (k == 3 && nt < max_t) { tris[3 * nt] = idx[0] - 1; tris[3 * nt + 1] = idx[1] - 1; tris[3 * nt + 2] = idx[2] - 1; ++nt; }
+        }
+    }
+    fclose(f);
+    *nv_out = nv; *nt_out = nt;
+    return 0;
+}
+
+static inline float lerpf(float a, float b, float t) { return a + t * (b - a); }
+
+/* trilinear value and unit gradient of the grid at the body-frame point pl. Outside the grid the point is clamped onto
+ * the grid's box and its distance to the box is added (the surface is at least a margin inside the box) */
+static void sdf_sample(const sdf_shape* S, v3 pl, float* phi, v3* grad)
+{
+    float fx = (pl.x - S->origin.x) / S->cell, fy = (pl.y - S->origin.y) / S->cell, fz = (pl.z - S->origin.z) / S->cell;
+    const float cx = fminf(fmaxf(fx, 0.f), (float)(S->nx - 1)), cy = fminf(fmaxf(fy, 0.f), (float)(S->ny - 1)),
+                cz = fminf(fmaxf(fz, 0.f), (float)(S->nz - 1));
+    const float outside = S->cell * v3_norm(V3(fx - cx, fy - cy, fz - cz));
+    fx = cx; fy = cy; fz = cz;
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    if (i > S->nx - 2) i = S->nx - 2;
+    if (j > S->ny - 2) j = S->ny - 2;
+    if (k > S->nz - 2) k = S->nz - 2;
+    const float tx = fx - (float)i, ty = fy - (float)j, tz = fz - (float)k;
+    const float* g = S->grid + ((size_t)k * S->ny + j) * S->nx + i;
+    const size_t sy = (size_t)S->nx, sz = (size_t)S->nx * S->ny;
+    const float c000 = g[0], c100 = g[1], c010 = g[sy], c110 = g[sy + 1];
+    const float c001 = g[sz], c101 = g[sz + 1], c011 = g[sz + sy], c111 = g[sz + sy + 1];
+    *phi = lerpf(lerpf(lerpf(c000, c100, tx), lerpf(c010, c110, tx), ty), lerpf(lerpf(c001, c101, tx), lerpf(c011, c111, tx), ty), tz) + outside;
+    v3 gr;
+    gr.x = lerpf(lerpf(c100 - c000, c110 - c010, ty), lerpf(c101 - c001, c111 - c011, ty), tz);
+    gr.y = lerpf(lerpf(c010 - c000, c110 - c100, tx), lerpf(c011 - c001, c111 - c101, tx), tz);
+    gr.z = lerpf(lerpf(c001 - c000, c101 - c100, tx), lerpf(c011 - c010, c111 - c110, tx), ty);
+    const float n2 = v3_sqnorm(gr);
+    *grad = n2 > 0.f ? v3_div(gr, sqrtf(n2)) : V3(0.f, 1.f, 0.f);
+}
+
+/* the (at most) four deepest sample points of a pair, deepest first, ties in sampling order */
+typedef struct { int cnt; float phi[4]; v3 p[4], n[4]; } sdf_hits;
+static void sdf_hit(sdf_hits* H, float phi, v3 p, v3 n)
+{
+    int at = H->cnt;
+    while (at > 0 && phi < H->phi[at - 1]) --at;
+    if (at >= 4) return;
+    const int last = H->cnt < 4 ? H->cnt : 3;
+    for (int k = last; k > at; --k) { H->phi[k] = H->phi[k - 1]; H->p[k] = H->p[k - 1]; H->n[k] = H->n[k - 1]; }
+    H->phi[at] = phi; H->p[at] = p; H->n[at] = n;
+    if (H->cnt < 4) ++H->cnt;
+}
+static void sdf_emit(orc_system* s, int b0, int b1, const sdf_hits* H)
+{
+    /* one normal per pair, that of the deepest point (the device's pair record carries a single normal) */
+    for (int k = 0; k < H->cnt; ++k) new_contact(s, b0, b1, H->p[k], H->n[0], fminf(0.0f, H->phi[k]));
+}
+
+/* mesh (body0): vertices under the plane (body1) */
+static void ext_sdf_plane(orc_system* s, int i0, int i1)
+{
+    const body_t* m = &s->bodies[i0];
+    const body_t* pl = &s->bodies[i1];
+    const sdf_shape* S = &s->shapes[m->shape];
+    const v3 planen = q_rot(pl->q, pl->plane_n);
+    const v3 planep = v3_add(q_rot(pl->q, pl->plane_p), pl->x);
+    if (distance_point_plane(m->x, planep, planen) > S->radius + 1e-3f) return;
+    sdf_hits H; H.cnt = 0;
+    for (int k = 0; k < S->nv; ++k) {
+        const v3 pw = v3_add(q_rot(m->q, V3(S->verts[3 * k], S->verts[3 * k + 1], S->verts[3 * k + 2])), m->x);
+        const float d = distance_point_plane(pw, planep, planen);
+        if (d < 1e-3f) sdf_hit(&H, d, pw, planen);
+    }
+    sdf_emit(s, i0, i1, &H);
+}
+
+/* sphere (body0): its centre in the grid of the mesh (body1) */
+static void ext_sphere_sdf(orc_system* s, int i0, int i1)
+{
+    const body_t* sp = &s->bodies[i0];
+    const body_t* m = &s->bodies[i1];
+    const sdf_shape* S = &s->shapes[m->shape];
+    const v3 rel = v3_sub(sp->x, m->x);
+    if (v3_norm(rel) > S->radius + sp->radius + 1e-3f) return;
+    float val; v3 g;
+    sdf_sample(S, q_rot(q_inverse(m->q), rel), &val, &g);
+    const float d = val - sp->radius;
+    if (d < 1e-3f) {
+        const v3 n = q_rot(m->q, g);
+        new_contact(s, i0, i1, v3_sub(sp->x, v3_scale(sp->radius, n)), n, fminf(0.0f, d));
+    }
+}
+
+/* vertices of mesh `from` sampled in the grid of mesh `in`; flip = -1 when the normal must point the other way */
+static void sdf_verts_in(const orc_system* s, const body_t* from, const body_t* in, float flip, sdf_hits* H)
+{
+    const sdf_shape* Sf = &s->shapes[from->shape];
+    const sdf_shape* Si = &s->shapes[in->shape];
+    const quat qinv = q_inverse(in->q);
+    for (int k = 0; k < Sf->nv; ++k) {
+        const v3 pw = v3_add(q_rot(from->q, V3(Sf->verts[3 * k], Sf->verts[3 * k + 1], Sf->verts[3 * k + 2])), from->x);
+        float val; v3 g;
+        sdf_sample(Si, q_rot(qinv, v3_sub(pw, in->x)), &val, &g);
+        if (val < 1e-3f) sdf_hit(H, val, pw, v3_scale(flip, q_rot(in->q, g)));
+    }
+}
+
+/* mesh i0 (body0) against mesh i1 (body1): body0's vertices in body1's grid, then body1's in body0's */
+static void ext_sdf_sdf(orc_system* s, int i0, int i1)
+{
+    const body_t* a = &s->bodies[i0];
+    const body_t* b = &s->bodies[i1];
+    if (v3_norm(v3_sub(a->x, b->x)) > s->shapes[a->shape].radius + s->shapes[b->shape].radius + 1e-3f) return;
+    sdf_hits H; H.cnt = 0;
+    sdf_verts_in(s, a, b, 1.0f, &H);       /* gradient of b's grid points out of b, towards body0 */
+    sdf_verts_in(s, b, a, -1.0f, &H);      /* gradient of a's grid points out of a: flip */
+    sdf_emit(s, i0, i1, &H);
+}
+
 void orc_stage_detect(orc_system* s)
 {
     s->pairs_tested = 0;
@@ -693,6 +938,11 @@ void orc_stage_detect(orc_system* s)
                 else if (t0 == ORC_BOX && t1 == ORC_PLANE)    ext_box_plane(s, i, j);
                 else if (t1 == ORC_BOX && t0 == ORC_PLANE)    ext_box_plane(s, j, i);
                 else if (t0 == ORC_BOX && t1 == ORC_BOX)      ext_box_box(s, i, j);
+                else if (t0 == ORC_SDF && t1 == ORC_PLANE)    ext_sdf_plane(s, i, j);
+                else if (t1 == ORC_SDF && t0 == ORC_PLANE)    ext_sdf_plane(s, j, i);
+                else if (t0 == ORC_SPHERE && t1 == ORC_SDF)   ext_sphere_sdf(s, i, j);
+                else if (t1 == ORC_SPHERE && t0 == ORC_SDF)   ext_sphere_sdf(s, j, i);
+                else if (t0 == ORC_SDF && t1 == ORC_SDF)      ext_sdf_sdf(s, i, j);
             }
         }
     }
@@ -1534,6 +1784,7 @@ void orc_get_body_params(const orc_system* s, float* mass, float* ibody9, float*
             case ORC_PLANE:    o[0] = b->plane_p.x; o[1] = b->plane_p.y; o[2] = b->plane_p.z;
                                o[3] = b->plane_n.x; o[4] = b->plane_n.y; o[5] = b->plane_n.z; break;
             case ORC_CYLINDER: o[0] = b->height; o[1] = b->radius; break;
+            case ORC_SDF:      o[0] = (float)b->shape; break;
             }
         }
     }

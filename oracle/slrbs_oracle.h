@@ -54,7 +54,8 @@ extern "C" {
 
 typedef struct orc_system orc_system;
 
-enum { ORC_SPHERE = 0, ORC_BOX = 1, ORC_PLANE = 2, ORC_CYLINDER = 3 };
+enum { ORC_SPHERE = 0, ORC_BOX = 1, ORC_PLANE = 2, ORC_CYLINDER = 3,
+       ORC_SDF = 4 /* EXTENSION: mesh as signed-distance grid, geom6 = {shape id} */ };
 enum { ORC_CONTACT = 0, ORC_SPHERICAL = 1, ORC_HINGE = 2 };
 
 orc_system* orc_create(void);
@@ -109,6 +110,17 @@ void orc_set_joint_lambda(orc_system* s, const float* lambda5);
 float orc_blcp_residual(orc_system* s, float h);
 /* solver diagonal blocks and RHS as built before the PGS loop (SolverBoxPGS.cpp:134-211); needs jacobians */
 void orc_get_solver_blocks(orc_system* s, float h, float* Acontact9, float* rhs_contact3, float* Ajoint25, float* rhs_joint5);
+
+/* EXTENSION (no reference counterpart): triangle meshes as signed-distance grids. A shape = grid
+ * (node (i,j,k) at origin + cell*(i,j,k), value grid[(k*ny+j)*nx+i], negative inside) + its vertices as sample points,
+ * body frame. Contacts (with orc_set_extensions): mesh-plane, sphere-mesh, mesh-mesh; at most the 4 deepest points of a
+ * pair, one normal per pair. orc_build_sdf: grid of a closed triangle mesh. orc_load_obj: 'v' / 'f' lines as
+ * src/util/OBJLoader.cpp:34-122 reads them. */
+int  orc_add_sdf_shape(orc_system* s, int nx, int ny, int nz, const float* origin3, float cell, const float* grid,
+                       int nv, const float* verts);
+void orc_build_sdf(int nv, const float* verts, int nt, const int* tris, int nx, int ny, int nz, const float* origin3,
+                   float cell, float* out);
+int  orc_load_obj(const char* path, float* verts, int max_v, int* tris, int max_t, int* nv_out, int* nt_out);
 
 /* RigidBodySystemState save/restore (src/rigidbody/RigidBodyState.cpp:18-72) */
 void orc_save_state(orc_system* s);

@@ -17,6 +17,7 @@ _LIB_PATH = os.path.join(_ORACLE_DIR, "libslrbs_oracle.so")
 _REF_PATH = os.path.join(_ORACLE_DIR, "_ref", "libslrbs_ref.so")
 
 SPHERE, BOX, PLANE, CYLINDER = 0, 1, 2, 3
+SDF = 4  # extension: mesh as signed-distance grid
 CONTACT, SPHERICAL, HINGE = 0, 1, 2
 
 _lib = None
@@ -114,6 +115,11 @@ def _bind(L):
         getattr(L, name).argtypes = [vp]
     L.orc_set_extensions.argtypes = [vp, C.c_int]
     L.orc_blcp_residual.argtypes = [vp, C.c_float]
+    L.orc_add_sdf_shape.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, C.c_float, fp, C.c_int, fp]
+    L.orc_add_sdf_shape.restype = C.c_int
+    L.orc_build_sdf.argtypes = [C.c_int, fp, C.c_int, ip, C.c_int, C.c_int, C.c_int, fp, C.c_float, fp]
+    L.orc_load_obj.argtypes = [C.c_char_p, fp, C.c_int, ip, C.c_int, ip, ip]
+    L.orc_load_obj.restype = C.c_int
     L.orc_blcp_residual.restype = C.c_float
     L.orc_scene_box_stack.argtypes = [vp, C.c_int]
     L.orc_scene_sphere_stack.argtypes = [vp, C.c_int]
@@ -198,6 +204,13 @@ class Oracle:
 
     def set_params(self, mu=0.8, solver_id=0, solver_iter=10, collisions=True):
         self.L.orc_set_params(self.h, float(mu), int(solver_id), int(solver_iter), int(bool(collisions)))
+
+    def add_sdf_shape(self, shape):
+        """shape: dict(dims=(nx,ny,nz), origin, cell, grid, verts) as mesh_lib.make_shape returns."""
+        nx, ny, nz = shape["dims"]
+        g = np.ascontiguousarray(shape["grid"], np.float32); v = np.ascontiguousarray(shape["verts"], np.float32)
+        o = np.asarray(shape["origin"], np.float32)
+        return self.L.orc_add_sdf_shape(self.h, nx, ny, nz, _f(o), float(shape["cell"]), _f(g), len(v), _f(v))
 
     def set_extensions(self, flags=1):
         """Extension pairs without a reference counterpart (sphere-plane, box-plane, box-box)."""

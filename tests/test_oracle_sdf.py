@@ -1,0 +1,92 @@
+"""SDF-mesh contacts in the oracle. EXTENSION: the reference has no SDF code, so nothing is pinned to
+reference output; checks are geometric (the grid of a sphere mesh is |p| - r) and physical (meshes come to rest on a
+plane, on each other and under a sphere without sinking in)."""
+import os
+
+import numpy as np
+import pytest
+
+import mesh_lib
+from oracle_lib import Oracle, PLANE, SDF, SPHERE
+
+DT = 0.01
+BUNNY = "/root/reference/resources/bunny.obj"
+
+
+@pytest.fixture(scope="module")
+def blob_shape():
+    v, f = mesh_lib.blob()
+    return mesh_lib.build_sdf(v, f)
+
+
+def test_grid_of_a_sphere_mesh_is_distance_to_the_sphere():
+    v, f = mesh_lib.icosphere(2)
+    sh = mesh_lib.build_sdf(v * 0.5, f, cell=0.08)
+    nx, ny, nz = sh["dims"]
+    g = sh["grid"].reshape(nz, ny, nx)
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    p = sh["origin"] + sh["cell"] * np.stack([i, j, k], -1)
+    exact = np.linalg.norm(p, axis=-1) - 0.5
+    assert np.abs(g - exact).max() < 0.02            # faceting error of a 162-vertex sphere
+    far = np.abs(exact) > 0.03
+    assert np.array_equal(np.sign(g[far]), np.sign(exact[far]))
+
+
+def test_obj_reader(tmp_path):
+    path = tmp_path / "tet.obj"
+    path.write_text("# comment\no tet\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nvn 0 0 1\nf 1//1 3//1 2//1\nf 1/5/1 2/5/1 4/5/1\nf 2 3 4\nf 1 4 3\n")
+    v, t = mesh_lib.load_obj(str(path))
+    assert v.shape == (4, 3) and t.tolist() == [[0, 2, 1], [0, 1, 3], [1, 2, 3], [0, 3, 2]]
+
+
+@pytest.mark.skipif(not os.path.exists(BUNNY), reason="reference resources not present")
+def test_reference_bunny_loads_and_builds():
+    v, t = mesh_lib.load_obj(BUNNY)
+    assert v.shape == (350, 3) and t.shape == (686, 3)
+    sh = mesh_lib.build_sdf(v, t, cell=0.08)
+    g = sh["grid"]
+    assert np.isfinite(g).all() and (g < 0).sum() > 50 and g[0] > 0      # an inside exists, the corner is outside
+
+
+def resting_height(o, body):
+    return float(o.state()["x"][body, 1])
+
+
+def test_mesh_rests_on_a_plane(blob_shape):
+    o = Oracle(); o.set_extensions(1)
+    sid = o.add_sdf_shape(blob_shape)
+    o.add_body(1.0, SDF, [sid], x=[0, 1.0, 0])
+    o.add_body(1.0, PLANE, [0, 0, 0, 0, 1, 0], fixed=True)
+    o.step(DT, 300)
+    st = o.state()
+    assert np.isfinite(st["x"]).all()
+    assert abs(st["v"][0][1]) < 0.2 and o.n_contacts >= 1     # a bumpy blob keeps rocking; it must not fall or bounce
+    # lowest vertex within a few mm of the plane
+    q = st["q"][0]; R = quat_matrix(q)
+    low = (blob_shape["verts"] @ R.T + st["x"][0])[:, 1].min()
+    assert -5e-3 < low < 5e-3, low
+
+
+def quat_matrix(q):
+    x, y, z, w = [float(c) for c in q]
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def test_mesh_on_mesh_and_sphere_on_mesh_do_not_sink(blob_shape):
+    o = Oracle(); o.set_extensions(1)
+    sid = o.add_sdf_shape(blob_shape)
+    o.add_body(1.0, SDF, [sid], x=[0, 0.6, 0])
+    o.add_body(1.0, SDF, [sid], x=[0.05, 1.75, 0.02])
+    o.add_body(1.0, SPHERE, [0.3], x=[0.0, 2.8, 0.0])
+    o.add_body(1.0, PLANE, [0, 0, 0, 0, 1, 0], fixed=True)
+    seen_mm = seen_sm = 0
+    for _ in range(150):
+        o.step(DT)
+        c = o.contacts()
+        pairs = set(zip(c["body0"].tolist(), c["body1"].tolist()))
+        seen_mm += (0, 1) in pairs; seen_sm += (2, 1) in pairs
+        assert c["phi"].min(initial=0.0) > -0.05           # penetration stays shallow
+    assert seen_mm > 20 and seen_sm > 5
+    assert np.isfinite(o.state()["x"]).all()
