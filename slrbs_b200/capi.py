@@ -26,6 +26,7 @@ SYMBOLS = [
     "slrbs_timer_start", "slrbs_timer_stop", "slrbs_halo_set_local", "slrbs_halo_set_remote", "slrbs_halo_sync_local",
     "slrbs_halo_pack", "slrbs_halo_unpack", "slrbs_pile_init", "slrbs_pile_export", "slrbs_pile_rebuild",
     "slrbs_pile_requests", "slrbs_pile_set_send", "slrbs_pile_scene_keys", "slrbs_set_extensions",
+    "slrbs_sdf_build", "slrbs_sdf_add_shape",
 ]
 
 
@@ -57,6 +58,8 @@ def load_library():
     L.slrbs_destroy.restype = None
     L.slrbs_set_params.argtypes = [vp, C.c_float, C.c_int, C.c_int, C.c_int]
     L.slrbs_set_extensions.argtypes = [vp, C.c_int]
+    L.slrbs_sdf_build.argtypes = [C.c_int, C.c_int, fp, C.c_int, ip, C.c_int, C.c_int, C.c_int, fp, C.c_float, fp]
+    L.slrbs_sdf_add_shape.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, C.c_float, fp, C.c_int, fp]
     L.slrbs_upload_bodies.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, fp, fp, fp, fp, fp, fp, fp, ip, ip, fp]
     L.slrbs_upload_joints.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, ip, ip, fp, fp, fp, fp]
     L.slrbs_upload_state.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp, fp, fp, fp]
@@ -136,6 +139,13 @@ class Context:
     def set_extensions(self, flags=1):
         """Extension contact pairs without a reference counterpart (sphere-plane, box-plane, box-box)."""
         self._ck(self.L.slrbs_set_extensions(self.h, int(flags)))
+
+    def add_sdf_shape(self, dims, origin, cell, grid, verts):
+        """Extension: a mesh as signed-distance grid + sample vertices; returns the shape id for geom_type 4 bodies."""
+        g = np.ascontiguousarray(grid, np.float32).reshape(-1); v = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+        o = np.ascontiguousarray(origin, np.float32)
+        assert g.size == dims[0] * dims[1] * dims[2]
+        return self._ck(self.L.slrbs_sdf_add_shape(self.h, int(dims[0]), int(dims[1]), int(dims[2]), _f(o), float(cell), _f(g), len(v), _f(v)))
 
     def describe(self):
         buf = C.create_string_buffer(256)
@@ -373,3 +383,15 @@ class Context:
         self._ck(self.L.slrbs_profile_read(self.h, int(bool(reset)), C.byref(a), C.byref(ms), C.byref(b), C.byref(c), C.byref(d)))
         return dict(solve_launches=a.value, solve_ms=ms.value, contact_visits=b.value, joint_visits=c.value,
                     total_launches=d.value)
+
+
+def sdf_build(verts, tris, dims, origin, cell, device=0):
+    """Extension: signed-distance grid of a closed triangle mesh, computed on the device (slrbs_sdf_build)."""
+    L = load_library()
+    v = np.ascontiguousarray(verts, np.float32).reshape(-1, 3); t = np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
+    o = np.ascontiguousarray(origin, np.float32)
+    out = np.zeros(int(dims[0]) * int(dims[1]) * int(dims[2]), np.float32)
+    rc = L.slrbs_sdf_build(int(device), len(v), _f(v), len(t), _i(t), int(dims[0]), int(dims[1]), int(dims[2]), _f(o), float(cell), _f(out))
+    if rc < 0:
+        raise SlrbsError(L.slrbs_last_error().decode())
+    return out

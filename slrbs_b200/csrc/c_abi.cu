@@ -48,6 +48,9 @@ struct slrbs_ctx {
     cudaGraphExec_t graph = nullptr;
     struct { float dt, mu; int iters, solver, collisions, has_ext, launches; } gsig = { 0.f, 0.f, 0, 0, 0, 0, 0 };
     int use_graph = 1;
+    // extension: mesh shapes as signed-distance grids (host mirror of the device table v.sdf_shapes)
+    SdfShape shapes[MAX_SDF_SHAPES] = {};
+    int n_shapes = 0;
     // halo maps (device copies of the index lists)
     int *halo_src = nullptr, *halo_dst = nullptr, *halo_send = nullptr, *halo_recv = nullptr;
     int n_halo_local = 0, n_halo_send = 0, n_halo_recv = 0;
@@ -233,6 +236,7 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     A(v.jdef, nj) A(v.jr0, nj) A(v.jq0, nj) A(v.jr1, nj) A(v.jq1, nj) A(v.jlam, nj) A(v.jlam4, nj)
     A(v.jrow, (size_t)JROW_FIELDS * v.NJ * bpad)
     A(v.cids, nc) A(v.cp, nc) A(v.cn, nc) A(v.crow, (size_t)CROW_FIELDS * v.NC * bpad)
+    { SdfShape* tab = nullptr; A(tab, MAX_SDF_SHAPES) v.sdf_shapes = tab; }
     if (v.level_mode) {
         A(v.cpos, nc) A(v.cslot, nc) A(v.clev_end, nc + v.B) A(v.nclev, v.B) A(v.lv_last, nb)
         A(v.jpos, nj) A(v.jlev_end, nj + v.B) A(v.njlev, v.B)
@@ -268,6 +272,55 @@ int slrbs_set_params(slrbs_ctx* c, float mu, int solver_id, int solver_iters, in
     if (!c || solver_id < 0 || solver_id > 3 || solver_iters < 0) return fail(SLRBS_E_ARG, "slrbs_set_params: bad argument");
     c->mu = mu; c->solver_id = solver_id; c->solver_iters = solver_iters; c->collisions = collisions_enabled ? 1 : 0;
     return 0;
+}
+
+// EXTENSION (no reference counterpart): meshes as signed-distance grids
+int slrbs_sdf_build(int device, int nv, const float* verts, int nt, const int32_t* tris, int nx, int ny, int nz,
+                    const float* origin3, float cell, float* grid_out)
+{
+    if (nv <= 0 || nt <= 0 || !verts || !tris || nx < 2 || ny < 2 || nz < 2 || !origin3 || !(cell > 0.f) || !grid_out)
+        return fail(SLRBS_E_ARG, "slrbs_sdf_build: bad argument");
+    for (int k = 0; k < 3 * nt; ++k) if (tris[k] < 0 || tris[k] >= nv) return fail(SLRBS_E_ARG, "slrbs_sdf_build: triangle index out of range");
+    CU(cudaSetDevice(device));
+    const size_t n = (size_t)nx * ny * nz;
+    float *dv = nullptr, *dg = nullptr; int* dt = nullptr;
+    CU(cudaMalloc((void**)&dv, sizeof(float) * 3 * nv));
+    CU(cudaMalloc((void**)&dt, sizeof(int) * 3 * nt));
+    CU(cudaMalloc((void**)&dg, sizeof(float) * n));
+    int rc = 0;
+    cudaError_t e = cudaMemcpy(dv, verts, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dt, tris, sizeof(int) * 3 * nt, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { launch_build_sdf(dv, nt, dt, nx, ny, nz, origin3[0], origin3[1], origin3[2], cell, dg, 0); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(grid_out, dg, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(SLRBS_E_CUDA, std::string("slrbs_sdf_build: ") + cudaGetErrorString(e));
+    cudaFree(dv); cudaFree(dt); cudaFree(dg);
+    return rc;
+}
+
+int slrbs_sdf_add_shape(slrbs_ctx* c, int nx, int ny, int nz, const float* origin3, float cell, const float* grid, int nv, const float* verts)
+{
+    if (!c || nx < 2 || ny < 2 || nz < 2 || !origin3 || !(cell > 0.f) || !grid || nv <= 0 || !verts)
+        return fail(SLRBS_E_ARG, "slrbs_sdf_add_shape: bad argument");
+    if (c->n_shapes >= MAX_SDF_SHAPES) return fail(SLRBS_E_CAPACITY, "slrbs_sdf_add_shape: shape table is full");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)nx * ny * nz;
+    float *dg = nullptr, *dv = nullptr;
+    int r;
+    if ((r = dalloc(c, &dg, n)) || (r = dalloc(c, &dv, (size_t)3 * nv))) return r;
+    CU(cudaMemcpyAsync(dg, grid, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dv, verts, sizeof(float) * 3 * nv, cudaMemcpyHostToDevice, c->stream));
+    SdfShape& S = c->shapes[c->n_shapes];
+    S.grid = dg; S.verts = dv; S.nx = nx; S.ny = ny; S.nz = nz; S.nv = nv;
+    S.ox = origin3[0]; S.oy = origin3[1]; S.oz = origin3[2]; S.cell = cell;
+    S.radius = 0.f;
+    for (int k = 0; k < nv; ++k) {                     // largest vertex norm, the restatement's association a0 + (a1 + a2)
+        const float x = verts[3 * k], y = verts[3 * k + 1], z = verts[3 * k + 2];
+        const float rr = std::sqrt(x * x + (y * y + z * z));
+        if (rr > S.radius) S.radius = rr;
+    }
+    CU(cudaMemcpyAsync(const_cast<SdfShape*>(c->v.sdf_shapes) + c->n_shapes, &S, sizeof(SdfShape), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));             // the host buffers may go away after the call
+    return c->n_shapes++;
 }
 
 int slrbs_set_extensions(slrbs_ctx* c, int flags)

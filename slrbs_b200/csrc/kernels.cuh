@@ -39,6 +39,9 @@ enum { BPP_MAX_ROWS = 288 };
 void init_bpp_kernel();
 int  bpp_row_capacity(const View& v);
 int  launch_bpp(const View& v, int iters, float mu, cudaStream_t s);   // returns the number of launches
+// sdf.cu (extension): signed-distance grid of a closed triangle mesh, all pointers on the device
+void launch_build_sdf(const float* verts, int nt, const int* tris, int nx, int ny, int nz, float ox, float oy, float oz, float cell,
+                      float* out, cudaStream_t s);
 // level-scheduled solver (pgs_level.cu)
 void launch_joint_levels(const View& v, cudaStream_t s);
 void launch_contact_levels(const View& v, cudaStream_t s);

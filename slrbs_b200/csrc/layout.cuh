@@ -17,7 +17,7 @@
 
 namespace slrbs {
 
-enum { GEOM_SPHERE = 0, GEOM_BOX = 1, GEOM_PLANE = 2, GEOM_CYLINDER = 3 };
+enum { GEOM_SPHERE = 0, GEOM_BOX = 1, GEOM_PLANE = 2, GEOM_CYLINDER = 3, GEOM_SDF = 4 /* extension: mesh as signed-distance grid */ };
 enum { FLAG_TYPE_MASK = 0xF, FLAG_FIXED = 0x10 };
 enum { CROW_FIELDS = 16, JROW_FIELDS = 17, CROW_LAMBDA = 15 };
 enum { MAX_BODIES_PER_SCENE = 32767 };   // body ids are packed 2 x 16 bit in the contact row record
@@ -38,6 +38,14 @@ enum { BODY_FIXED_BIT = (int)0x80000000 };
 //  14 (L10 L20 L21 L30)  15 (L31 L32 L40 L41)  16 (L42 L43 dim slot)
 // J0 = [I hat(-rr0); 0 nxu; 0 nxv], J1 = [-I hat(rr1); 0 -nxu; 0 -nxv] (Hinge.cpp:50-57).
 
+// extension (sdf.cuh): a mesh as signed-distance grid + sample vertices, body frame; device pointers
+struct SdfShape {
+    const float* grid; const float* verts;
+    int nx, ny, nz, nv;
+    float ox, oy, oz, cell, radius;
+};
+enum { MAX_SDF_SHAPES = 16 };
+
 struct View {
     int B, NB, NJ, NC;
     int level_mode;                       // 0: rows as warp-blocked tiles in slot order (k_pgs)
@@ -47,6 +55,7 @@ struct View {
     unsigned long long *visit_counters;   // [2] contact visits, joint visits (profiling)
     int profiling;
     int ext_pairs;                        // extension: sphere-plane, box-plane, box-box contacts (no reference counterpart)
+    const SdfShape* sdf_shapes;           // extension: [MAX_SDF_SHAPES] shape table for GEOM_SDF bodies (geomA.x = shape id)
     // bodies, [NB][B]
     float4 *pos;        // x y z | mass
     float4 *quat;       // x y z w

@@ -4,6 +4,7 @@
 #pragma once
 #include "layout.cuh"
 #include "vecmath.cuh"
+#include "sdf.cuh"
 
 namespace slrbs {
 
@@ -272,7 +273,7 @@ __device__ __forceinline__ void ext_box_box(PairOut& o, const float4* __restrict
 
 // extension dispatch, reached only when the reference's chain matched nothing and the extension is enabled; one
 // out-of-line function taking plain pointers, so that the detection kernels' own register budget is untouched
-__device__ __noinline__ void ext_pair(PairOut& o, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+__device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                                       const float4* __restrict__ geomB, size_t ii, size_t jj, int i, int j, float4 ci, int ti, float4 cj, int tj)
 {
     if (ti == GEOM_SPHERE && tj == GEOM_PLANE)      ext_sphere_plane(o, quat, geomA, geomB, jj, i, j, ci, cj);
@@ -280,6 +281,11 @@ __device__ __noinline__ void ext_pair(PairOut& o, const float4* __restrict__ qua
     else if (ti == GEOM_BOX && tj == GEOM_PLANE)    ext_box_plane(o, quat, geomA, geomB, ii, jj, i, j, ci, cj);
     else if (tj == GEOM_BOX && ti == GEOM_PLANE)    ext_box_plane(o, quat, geomA, geomB, jj, ii, j, i, cj, ci);
     else if (ti == GEOM_BOX && tj == GEOM_BOX)      ext_box_box(o, quat, geomA, ii, jj, i, j, ci, cj);
+    else if (ti == GEOM_SDF && tj == GEOM_PLANE)    ext_sdf_plane(o, shapes, quat, geomA, geomB, ii, jj, i, j, ci, cj);
+    else if (tj == GEOM_SDF && ti == GEOM_PLANE)    ext_sdf_plane(o, shapes, quat, geomA, geomB, jj, ii, j, i, cj, ci);
+    else if (ti == GEOM_SPHERE && tj == GEOM_SDF)   ext_sphere_sdf(o, shapes, quat, geomA, jj, i, j, ci, cj);
+    else if (tj == GEOM_SPHERE && ti == GEOM_SDF)   ext_sphere_sdf(o, shapes, quat, geomA, ii, j, i, cj, ci);
+    else if (ti == GEOM_SDF && tj == GEOM_SDF)      ext_sdf_sdf(o, shapes, quat, geomA, ii, jj, i, j, ci, cj);
 }
 
 // the reference's dispatch chain for the ordered pair (i < j), CollisionDetect.cpp:41-73
@@ -300,7 +306,7 @@ __device__ __forceinline__ void test_pair(PairOut& o, const View& v, int scene, 
     }
     else if (ti == GEOM_CYLINDER && tj == GEOM_PLANE)    cylinder_plane(o, v.quat, v.geomA, v.geomB, at(v, i, scene), at(v, j, scene), i, j, ci, cj);
     else if (tj == GEOM_CYLINDER && ti == GEOM_PLANE)    cylinder_plane(o, v.quat, v.geomA, v.geomB, at(v, j, scene), at(v, i, scene), j, i, cj, ci);
-    else if (EXT)                                        ext_pair(o, v.quat, v.geomA, v.geomB, at(v, i, scene), at(v, j, scene), i, j, ci, ti, cj, tj);
+    else if (EXT)                                        ext_pair(o, v.sdf_shapes, v.quat, v.geomA, v.geomB, at(v, i, scene), at(v, j, scene), i, j, ci, ti, cj, tj);
 }
 
 __device__ __forceinline__ void write_contacts(const View& v, int scene, int base, const PairOut& o)

@@ -1,0 +1,127 @@
+// sdf.cuh -- EXTENSION: triangle meshes as signed-distance grids. The reference has no SDF code;
+// these routines follow oracle/slrbs_oracle.c (sdf_sample, ext_sdf_plane, ext_sphere_sdf, ext_sdf_sdf) operation for
+// operation (-fmad=false), so contact lists agree with the restatement bit for bit on the same grid.
+// A shape = grid (node (i,j,k) at origin + cell*(i,j,k), value grid[(k*ny+j)*nx+i], negative inside) + the mesh vertices
+// as sample points, both in the body frame. A pair yields at most its four deepest sample points, deepest first, with
+// the normal of the deepest one (the pair record carries a single normal).
+#pragma once
+#include "layout.cuh"
+#include "vecmath.cuh"
+
+namespace slrbs {
+
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return a + t * (b - a); }
+
+__device__ __forceinline__ void sdf_sample(const SdfShape& S, const V3& pl, float& phi, V3& grad)
+{
+    float fx = (pl.x - S.ox) / S.cell, fy = (pl.y - S.oy) / S.cell, fz = (pl.z - S.oz) / S.cell;
+    const float cx = fminf(fmaxf(fx, 0.f), (float)(S.nx - 1)), cy = fminf(fmaxf(fy, 0.f), (float)(S.ny - 1)),
+                cz = fminf(fmaxf(fz, 0.f), (float)(S.nz - 1));
+    const float outside = S.cell * norm(mk3(fx - cx, fy - cy, fz - cz));
+    fx = cx; fy = cy; fz = cz;
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    if (i > S.nx - 2) i = S.nx - 2;
+    if (j > S.ny - 2) j = S.ny - 2;
+    if (k > S.nz - 2) k = S.nz - 2;
+    const float tx = fx - (float)i, ty = fy - (float)j, tz = fz - (float)k;
+    const float* g = S.grid + ((size_t)k * S.ny + j) * S.nx + i;
+    const size_t sy = (size_t)S.nx, sz = (size_t)S.nx * S.ny;
+    const float c000 = __ldg(g), c100 = __ldg(g + 1), c010 = __ldg(g + sy), c110 = __ldg(g + sy + 1);
+    const float c001 = __ldg(g + sz), c101 = __ldg(g + sz + 1), c011 = __ldg(g + sz + sy), c111 = __ldg(g + sz + sy + 1);
+    phi = lerpf(lerpf(lerpf(c000, c100, tx), lerpf(c010, c110, tx), ty), lerpf(lerpf(c001, c101, tx), lerpf(c011, c111, tx), ty), tz) + outside;
+    V3 gr;
+    gr.x = lerpf(lerpf(c100 - c000, c110 - c010, ty), lerpf(c101 - c001, c111 - c011, ty), tz);
+    gr.y = lerpf(lerpf(c010 - c000, c110 - c100, tx), lerpf(c011 - c001, c111 - c101, tx), tz);
+    gr.z = lerpf(lerpf(c001 - c000, c101 - c100, tx), lerpf(c011 - c010, c111 - c110, tx), ty);
+    const float n2 = sqnorm(gr);
+    grad = n2 > 0.f ? gr / sqrtf(n2) : mk3(0.f, 1.f, 0.f);
+}
+
+struct SdfHits { int cnt; float phi[4]; V3 p[4], n[4]; };
+__device__ __forceinline__ void sdf_hit(SdfHits& H, float phi, const V3& p, const V3& n)
+{
+    int at = H.cnt;
+    while (at > 0 && phi < H.phi[at - 1]) --at;
+    if (at >= 4) return;
+    const int last = H.cnt < 4 ? H.cnt : 3;
+    for (int k = last; k > at; --k) { H.phi[k] = H.phi[k - 1]; H.p[k] = H.p[k - 1]; H.n[k] = H.n[k - 1]; }
+    H.phi[at] = phi; H.p[at] = p; H.n[at] = n;
+    if (H.cnt < 4) ++H.cnt;
+}
+template <class Out>
+__device__ __forceinline__ void sdf_emit(Out& o, int b0, int b1, const SdfHits& H)
+{
+    if (H.cnt == 0) return;
+    o.b0 = b0; o.b1 = b1; o.n = H.n[0];
+    for (int k = 0; k < H.cnt; ++k) o.add(H.p[k], fminf(0.0f, H.phi[k]));
+}
+__device__ __forceinline__ V3 sdf_vertex(const SdfShape& S, int k) { return mk3(__ldg(S.verts + 3 * k), __ldg(S.verts + 3 * k + 1), __ldg(S.verts + 3 * k + 2)); }
+
+// mesh (body0): vertices under the plane (body1)
+template <class Out>
+__device__ void ext_sdf_plane(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+                              const float4* __restrict__ geomB, size_t mi, size_t pi, int im, int ip, const float4& cm, const float4& cpl)
+{
+    const SdfShape S = shapes[(int)__ldg(&geomA[mi]).x];
+    const Q4 qp = mkq(__ldg(&quat[pi]));
+    const V3 planen = rotate(qp, mk3(__ldg(&geomB[pi])));
+    const V3 planep = rotate(qp, mk3(__ldg(&geomA[pi]))) + mk3(cpl);
+    const V3 xm = mk3(cm);
+    if (dot(xm - planep, planen) > S.radius + 1e-3f) return;
+    const Q4 qm = mkq(__ldg(&quat[mi]));
+    SdfHits H; H.cnt = 0;
+    for (int k = 0; k < S.nv; ++k) {
+        const V3 pw = rotate(qm, sdf_vertex(S, k)) + xm;
+        const float d = dot(pw - planep, planen);
+        if (d < 1e-3f) sdf_hit(H, d, pw, planen);
+    }
+    sdf_emit(o, im, ip, H);
+}
+
+// sphere (body0): its centre in the grid of the mesh (body1)
+template <class Out>
+__device__ void ext_sphere_sdf(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+                               size_t mi, int is, int im, const float4& cs, const float4& cm)
+{
+    const SdfShape S = shapes[(int)__ldg(&geomA[mi]).x];
+    const V3 xs = mk3(cs), rel = xs - mk3(cm);
+    if (norm(rel) > S.radius + cs.w + 1e-3f) return;
+    const Q4 qm = mkq(__ldg(&quat[mi]));
+    float val; V3 g;
+    sdf_sample(S, rotate(qinverse(qm), rel), val, g);
+    const float d = val - cs.w;
+    if (d < 1e-3f) {
+        const V3 n = rotate(qm, g);
+        o.b0 = is; o.b1 = im; o.n = n;
+        o.add(xs - cs.w * n, fminf(0.0f, d));
+    }
+}
+
+__device__ __forceinline__ void sdf_verts_in(const SdfShape& Sf, const Q4& qf, const V3& xf, const SdfShape& Si, const Q4& qi, const V3& xi,
+                                             float flip, SdfHits& H)
+{
+    const Q4 qinv = qinverse(qi);
+    for (int k = 0; k < Sf.nv; ++k) {
+        const V3 pw = rotate(qf, sdf_vertex(Sf, k)) + xf;
+        float val; V3 g;
+        sdf_sample(Si, rotate(qinv, pw - xi), val, g);
+        if (val < 1e-3f) sdf_hit(H, val, pw, flip * rotate(qi, g));
+    }
+}
+
+// mesh i (body0) against mesh j (body1): body0's vertices in body1's grid, then body1's in body0's
+template <class Out>
+__device__ void ext_sdf_sdf(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+                            size_t ai, size_t bi, int ia, int ib, const float4& ca, const float4& cb)
+{
+    const SdfShape Sa = shapes[(int)__ldg(&geomA[ai]).x], Sb = shapes[(int)__ldg(&geomA[bi]).x];
+    const V3 xa = mk3(ca), xb = mk3(cb);
+    if (norm(xa - xb) > Sa.radius + Sb.radius + 1e-3f) return;
+    const Q4 qa = mkq(__ldg(&quat[ai])), qb = mkq(__ldg(&quat[bi]));
+    SdfHits H; H.cnt = 0;
+    sdf_verts_in(Sa, qa, xa, Sb, qb, xb, 1.0f, H);
+    sdf_verts_in(Sb, qb, xb, Sa, qa, xa, -1.0f, H);
+    sdf_emit(o, ia, ib, H);
+}
+
+}  // namespace slrbs

@@ -1,0 +1,93 @@
+"""GPU: SDF-mesh contacts (geom_type 4, csrc/sdf.cuh / sdf.cu) against the restatement. EXTENSION -- the reference has
+no SDF code; the device and the C restatement implement the same routines, so the grid built on the
+device and the contact lists (pairs, order, p, n, pene) must agree bit for bit, trajectories within fp32 tolerance."""
+import numpy as np
+import pytest
+
+import mesh_lib
+from oracle_lib import Oracle, PLANE, SDF, SPHERE
+from gpu_helpers import assert_bit_equal, context_from_oracles, push_state
+from slrbs_b200 import capi
+
+pytestmark = pytest.mark.gpu
+DT = 0.01
+
+
+@pytest.fixture(scope="module")
+def shape():
+    v, f = mesh_lib.blob()
+    return mesh_lib.build_sdf(v, f)
+
+
+def test_device_grid_equals_the_restatements(shape):
+    g = capi.sdf_build(shape["verts"], shape["tris"], shape["dims"], shape["origin"], shape["cell"])
+    assert_bit_equal(g, shape["grid"], "sdf grid")
+    assert (g < 0).sum() > 100
+
+
+def pile(shape, rng, n_mesh=6, n_sphere=3):
+    o = Oracle(); o.set_extensions(1)
+    sid = o.add_sdf_shape(shape)
+    for i in range(n_mesh):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        o.add_body(1.0, SDF, [sid], x=[rng.uniform(-0.4, 0.4), 0.6 + 0.95 * i, rng.uniform(-0.4, 0.4)], q=q)
+    for i in range(n_sphere):
+        o.add_body(1.0, SPHERE, [0.3], x=[rng.uniform(-0.3, 0.3), 0.8 + 0.95 * n_mesh + 0.7 * i, rng.uniform(-0.3, 0.3)])
+    o.add_body(1.0, PLANE, [0, 0, 0, 0, 1, 0], fixed=True)
+    return o
+
+
+def frozen(shape, src):
+    c = Oracle(); c.set_extensions(1)
+    sid = c.add_sdf_shape(shape)
+    bp = src.body_params(); st = src.state()
+    for i in range(src.n_bodies):
+        c.add_body(float(bp["mass"][i]), int(bp["geom_type"][i]), [sid] if bp["geom_type"][i] == SDF else bp["geom"][i].tolist(),
+                   fixed=bool(bp["fixed"][i]))
+    c.set_state(**st)
+    return c
+
+
+def make_ctx(oracles, shape, nc=256):
+    ctx = context_from_oracles(oracles, max_contacts=nc)
+    ctx.set_extensions(1)
+    assert ctx.add_sdf_shape(shape["dims"], shape["origin"], shape["cell"], shape["grid"], shape["verts"]) == 0
+    return ctx
+
+
+def test_contact_lists_bit_exact_along_a_pile_trajectory(shape):
+    rng = np.random.default_rng(3)
+    o = pile(shape, rng)
+    oracles, done = [], 0
+    for st in [0, 40, 80, 120, 200, 300]:
+        o.step(DT, st - done); done = st
+        oracles.append(frozen(shape, o))
+    ctx = make_ctx(oracles, shape)
+    push_state(ctx, oracles)
+    ctx.stage_prepare(); ctx.stage_detect(); ctx.sync()
+    cnt = ctx.contact_counts()
+    kinds = set()
+    for s, c in enumerate(oracles):
+        c.stage_prepare(); c.stage_detect()
+        assert cnt[s] == c.n_contacts, (s, cnt[s], c.n_contacts)
+        if c.n_contacts:
+            g, r = ctx.contacts(s), c.contacts()
+            np.testing.assert_array_equal(g["body0"], r["body0"]); np.testing.assert_array_equal(g["body1"], r["body1"])
+            for k in ("p", "n", "phi"):
+                assert_bit_equal(g[k], r[k], f"scene {s} {k}")
+            gt = c.body_params()["geom_type"]
+            kinds |= {(int(gt[a]), int(gt[b])) for a, b in zip(r["body0"], r["body1"])}
+    assert {(SDF, PLANE), (SDF, SDF), (SPHERE, SDF)} <= kinds, kinds
+    ctx.close()
+
+
+def test_pile_trajectory_follows_the_restatement(shape):
+    rng = np.random.default_rng(11)
+    o = pile(shape, rng, n_mesh=3, n_sphere=1)
+    ctx = make_ctx([o, o], shape)
+    ctx.step(DT, 60); ctx.sync()
+    o.step(DT, 60)
+    g, c = ctx.download_state(), o.state()
+    for s in range(2):
+        np.testing.assert_allclose(g["x"][s], c["x"], atol=5e-3)
+    ctx.close()
