@@ -6,6 +6,7 @@
 //     g++ -std=c++17 -Islrbs_b200/host/include -Iinclude examples/headless.cpp -Lslrbs_b200 -lslrbs_host -lslrbs_b200
 //
 // usage: slrbs_headless <marble_box|sphere_on_box|swinging_boxes|cylinder_on_plane|car> [steps] [solverId]
+//        slrbs_headless mesh_pile <steps> <solverId> <file.obj> [n] [scale]      (extension: SDF-mesh bodies)
 // prints "i x y z qx qy qz qw" for every body after the last step, then "contacts N".
 #include "rigidbody/RigidBodySystem.h"
 #include "rigidbody/RigidBody.h"
@@ -27,6 +28,10 @@ int main(int argc, char* argv[])
     else if (scene == "swinging_boxes") Scenarios::createSwingingBoxes(sys);
     else if (scene == "cylinder_on_plane") Scenarios::createCylinderOnPlane(sys);
     else if (scene == "car") Scenarios::createCarScene(sys);
+    else if (scene == "mesh_pile") {                            // extension: slrbs_headless mesh_pile <steps> <solverId> <file.obj> [n] [scale]
+        if (argc < 5) { std::fprintf(stderr, "mesh_pile needs an OBJ file\n"); return 2; }
+        Scenarios::createMeshPile(sys, argv[4], argc > 5 ? std::atoi(argv[5]) : 5, argc > 6 ? (float)std::atof(argv[6]) : 1.0f);
+    }
     else { std::fprintf(stderr, "unknown scene %s\n", scene.c_str()); return 2; }
     sys.solverId = argc > 3 ? std::atoi(argv[3]) : 0;            // PGS = 0, CG = 1, CR = 2 (RigidBodySystem.h:56)
     sys.solverIter = 10;

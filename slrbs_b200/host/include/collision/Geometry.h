@@ -3,7 +3,7 @@
 #pragma once
 #include "util/Types.h"
 
-enum eGeometryType { kSphere, kBox, kPlane, kCylinder };
+enum eGeometryType { kSphere, kBox, kPlane, kCylinder, kSDFMesh /* extension, collision/SDFMesh.h */ };
 
 class Geometry {
 public:

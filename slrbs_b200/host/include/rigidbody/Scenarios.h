@@ -3,6 +3,7 @@
 // table-driven helpers, headless (no viewer styling). createSphereStack / createMarbleBoxN are
 // additions used by the benchmarks: same primitives, more bodies.
 #pragma once
+#include "collision/SDFMesh.h"
 #include "joint/Hinge.h"
 #include "joint/Spherical.h"
 #include "rigidbody/RigidBody.h"
@@ -147,6 +148,24 @@ public:
         for (int i = 0; i < k; ++i) {
             RigidBody* b = box(1.0f, V3(1.0f, 1.0f, 1.0f), V3(0.0f, 0.5f + (float)i * 1.0f, 0.0f), false);
             if (i & 1) b->q = Eigen::AngleAxisf(0.3f, V3(0, 1, 0));
+            sys.addBody(b);
+        }
+        sys.addBody(groundPlane());
+        sys.setExtendedContacts(true);
+    }
+
+    // EXTENSION scene (BASELINE config 3 "bunny pile"; the reference has no mesh collision): n copies of one closed mesh
+    // (an OBJ file such as the reference's resources/bunny.obj, scaled so its bounding box is about one unit across), each
+    // turned by a different angle, dropped in a column onto the ground plane. Meshes bottom-up, then the plane.
+    static void createMeshPile(RigidBodySystem& sys, const std::string& objPath, int n, float scale = 1.0f, float cell = 0.06f)
+    {
+        begin(sys);
+        std::shared_ptr<SDFShape> shape = SDFShape::fromOBJ(objPath, scale, cell);
+        const float h = shape->bbmax[1] - shape->bbmin[1];
+        for (int i = 0; i < n; ++i) {
+            RigidBody* b = new RigidBody(1.0f, new SDFMesh(shape), "");
+            b->x = V3(0.05f * (float)(i % 3 - 1), 0.6f * h + 1.1f * h * (float)i, 0.05f * (float)(i % 2));
+            b->q = Quat(Eigen::AngleAxisf(0.7f * (float)i, V3(0, 1, 0)));
             sys.addBody(b);
         }
         sys.addBody(groundPlane());

@@ -12,6 +12,7 @@
 #include "solvers/SolverConjGradient.h"
 #include "solvers/SolverConjResidual.h"
 #include "solvers/SolverBPP.h"
+#include "collision/SDFMesh.h"
 
 #include "slrbs_b200.h"
 
@@ -120,9 +121,28 @@ static bool sameBits(const std::vector<float>& a, const std::vector<float>& b)
     return a.size() == b.size() && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * sizeof(float)) == 0);
 }
 
+// extension: distinct SDF shapes of the bodies, in order of first appearance = their slots in the device shape table
+static std::vector<const SDFShape*> collectShapes(const std::vector<RigidBody*>& bodies)
+{
+    std::vector<const SDFShape*> shapes;
+    for (const RigidBody* b : bodies) {
+        if (b->geometry->getType() != kSDFMesh) continue;
+        const SDFShape* sh = static_cast<const SDFMesh*>(b->geometry.get())->shape.get();
+        auto it = std::find(shapes.begin(), shapes.end(), sh);
+        sh->shapeId = (int)(it - shapes.begin());
+        if (it == shapes.end()) shapes.push_back(sh);
+    }
+    return shapes;
+}
+
 void RigidBodySystem::uploadAll()
 {
     const int n = (int)m_bodies.size(), nj = (int)m_joints.size();
+    for (const SDFShape* sh : collectShapes(m_bodies)) {
+        const int id = slrbs_sdf_add_shape(m_ctx, sh->nx, sh->ny, sh->nz, sh->origin, sh->cell, sh->grid.data(), (int)sh->verts.size() / 3, sh->verts.data());
+        check(id, "slrbs_sdf_add_shape");
+        if (id != sh->shapeId) throw std::runtime_error("RigidBodySystem: SDF shape table out of step");
+    }
     std::vector<float> st; packState(st);
     std::vector<float> mass(n), ib(9 * n), ibi(9 * n), geom(6 * n, 0.f);
     std::vector<int32_t> fixed(n), type(n);
@@ -160,6 +180,7 @@ void RigidBodySystem::ensureContext()
 {
     const int n = (int)m_bodies.size(), nj = (int)m_joints.size();
     if (n == 0) return;
+    collectShapes(m_bodies);
     std::vector<float> params; packParams(params);
     if (!m_topologyDirty && m_ctx && sameBits(params, m_paramSnapshot)) return;
     if (m_contactCapacity == 0) m_contactCapacity = std::max(64, 8 * n);

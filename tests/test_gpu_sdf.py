@@ -91,3 +91,42 @@ def test_pile_trajectory_follows_the_restatement(shape):
     for s in range(2):
         np.testing.assert_allclose(g["x"][s], c["x"], atol=5e-3)
     ctx.close()
+
+
+def write_obj(path, v, f):
+    with open(path, "w") as fh:
+        fh.write("# procedural blob\no blob\n")
+        for p in v:
+            fh.write(f"v {p[0]:.6f} {p[1]:.6f} {p[2]:.6f}\n")
+        for t in f:
+            fh.write(f"f {t[0] + 1}//1 {t[1] + 1}//1 {t[2] + 1}//1\n")
+
+
+def test_mesh_pile_through_the_headless_program(tmp_path):
+    """examples/headless.cpp, written against the reference's class names + the SDFMesh extension: OBJ file -> SDFShape
+    (grid built on the device) -> Scenarios::createMeshPile -> RigidBodySystem::step."""
+    import os, subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "slrbs_b200", "slrbs_headless")
+    assert os.path.exists(exe), "build the host mirror first (make -C slrbs_b200/host)"
+    v, f = mesh_lib.blob()
+    obj = str(tmp_path / "blob.obj")
+    write_obj(obj, v, f)
+    n, steps = 3, 120
+    out = subprocess.run([exe, "mesh_pile", str(steps), "0", obj, str(n)], capture_output=True, text=True, check=True).stdout.split("\n")
+    rows = np.array([[float(t) for t in ln.split()[1:]] for ln in out if ln and ln[0].isdigit()])
+    assert rows.shape == (n + 1, 7) and np.isfinite(rows).all()
+    # the same scene in the restatement: vertices as the OBJ text holds them, re-centred on their bounding box
+    vr, fr = mesh_lib.load_obj(obj)
+    vr = (vr - 0.5 * (vr.min(0) + vr.max(0))).astype(np.float32)
+    sh = mesh_lib.build_sdf(vr, fr, cell=0.06, margin=3)
+    o = Oracle(); o.set_extensions(1)
+    sid = o.add_sdf_shape(sh)
+    h = float(vr[:, 1].max() - vr[:, 1].min())
+    for i in range(n):
+        a = 0.7 * i
+        o.add_body(1.0, SDF, [sid], x=[0.05 * (i % 3 - 1), 0.6 * h + 1.1 * h * i, 0.05 * (i % 2)],
+                   q=[0.0, np.sin(0.5 * a), 0.0, np.cos(0.5 * a)])
+    o.add_body(1.0, PLANE, [0, 0, 0, 0, 1, 0], fixed=True)
+    o.step(DT, steps)
+    np.testing.assert_allclose(rows[:, :3], o.state()["x"], atol=2e-2)
+    assert int([ln for ln in out if ln.startswith("contacts")][0].split()[1]) > 0
