@@ -16,12 +16,25 @@ ap.add_argument("--solver", type=int, default=0); ap.add_argument("--ext", type=
 a = ap.parse_args()
 if a.mode: os.environ["SLRBS_PGS_MODE"] = a.mode
 if a.group: os.environ["SLRBS_LEVEL_GROUP"] = a.group
-o = Oracle(a.scene, k=a.k) if a.scene in ("sphere_stack", "box_stack") else (Oracle("marble_box_n", nx=10, nz=10, ny=10) if a.scene == "mb1k" else Oracle(a.scene))
+shape = None
+if a.scene == "mesh_pile":
+    import mesh_lib
+    from oracle_lib import SDF, PLANE
+    mv, mf = mesh_lib.blob(); shape = mesh_lib.build_sdf(mv, mf)
+    o = Oracle(); o.set_extensions(1); sid = o.add_sdf_shape(shape)
+    for i in range(a.k):
+        ang = 0.7 * i
+        o.add_body(1.0, SDF, [sid], x=[0.05 * (i % 3 - 1), 0.6 + 1.1 * i, 0.05 * (i % 2)], q=[0.0, np.sin(0.5 * ang), 0.0, np.cos(0.5 * ang)])
+    o.add_body(1.0, PLANE, [0, 0, 0, 0, 1, 0], fixed=True)
+    a.ext = 1
+else:
+  o = Oracle(a.scene, k=a.k) if a.scene in ("sphere_stack", "box_stack") else (Oracle("marble_box_n", nx=10, nz=10, ny=10) if a.scene == "mb1k" else Oracle(a.scene))
 s = scene_arrays(o)
 B, nb, nj = a.B, o.n_bodies, o.n_joints
 ctx = Context(B, nb, nj, a.nc)
 ctx.set_params(solver_id=a.solver)
 if a.ext: ctx.set_extensions(1)
+if shape is not None: ctx.add_sdf_shape(shape["dims"], shape["origin"], shape["cell"], shape["grid"], shape["verts"])
 rng = np.random.default_rng(1234)
 x = np.broadcast_to(s["x"], (B, nb, 3)).copy()
 dyn = s["fixed"] == 0
