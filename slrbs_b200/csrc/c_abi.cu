@@ -320,6 +320,8 @@ int slrbs_sdf_add_shape(slrbs_ctx* c, int nx, int ny, int nz, const float* origi
     }
     CU(cudaMemcpyAsync(const_cast<SdfShape*>(c->v.sdf_shapes) + c->n_shapes, &S, sizeof(SdfShape), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));             // the host buffers may go away after the call
+    c->v.n_sdf = c->n_shapes + 1;
+    if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }     // the captured launches carry the old View
     return c->n_shapes++;
 }
 

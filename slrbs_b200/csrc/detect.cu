@@ -140,7 +140,7 @@ const char* detect_variant(const View& v, int broadphase)
     const size_t per_warp = (size_t)v.NB * 16 + detect_smem_ints(v.NB, grid, H) * 4;
     int warps = 8;
     while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
-    if ((v.NB < 24 && !v.level_mode) || per_warp * warps > 200 * 1024) return "k_detect_serial";
+    if ((v.NB < 24 && !v.level_mode && !v.n_sdf) || per_warp * warps > 200 * 1024) return "k_detect_serial";
     return grid ? "k_detect_warp<grid>" : "k_detect_warp<all-pairs>";
 }
 
@@ -168,8 +168,9 @@ void launch_detect(const View& v, int broadphase, cudaStream_t s)
     int warps = 8;
     while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
     const size_t smem = per_warp * warps;
-    // tiny scenes (car: 15 pairs) leave a warp idle: one thread per scene is faster there; huge ones do not fit
-    if ((v.NB < 24 && !v.level_mode) || smem > 200 * 1024) { DETECT_KERNEL(v, k_detect_serial)<<<(unsigned)((v.B + 127) / 128), 128, 0, s>>>(v); return; }
+    // tiny scenes (car: 15 pairs) leave a warp idle: one thread per scene is faster there (not with mesh bodies, whose
+    // pairs the warp walks together); huge ones do not fit
+    if ((v.NB < 24 && !v.level_mode && !v.n_sdf) || smem > 200 * 1024) { DETECT_KERNEL(v, k_detect_serial)<<<(unsigned)((v.B + 127) / 128), 128, 0, s>>>(v); return; }
     const unsigned blocks = (unsigned)((v.B + warps - 1) / warps);
     if (grid) DETECT_KERNEL(v, k_detect_warp<true>)<<<blocks, warps * 32, smem, s>>>(v, warps, H);
     else DETECT_KERNEL(v, k_detect_warp<false>)<<<blocks, warps * 32, smem, s>>>(v, warps, H);

@@ -8,8 +8,7 @@ __device__ __forceinline__ void emit_chunk(const View& v, const DetectSmem& sm, 
                                            int fi, int j, int& count)
 {
     PairOut o;
-    o.cnt = 0;
-    if (j >= 0) test_pair<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
+    test_pair_warp<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j >= 0 ? j : i], sm.sf[j >= 0 ? j : i], lane);
     const unsigned any = __ballot_sync(0xffffffffu, o.cnt > 0);
     if (any == 0) return;
     const unsigned multi = __ballot_sync(0xffffffffu, o.cnt > 1);
@@ -262,8 +261,7 @@ __device__ __forceinline__ int dense_row(const View& v, const DetectSmem& sm, in
     for (int j0 = i + 1; j0 < n; j0 += 32) {
         const int j = j0 + lane;
         PairOut o;
-        o.cnt = 0;
-        if (j < n) test_pair<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
+        test_pair_warp<DETECT_EXT>(o, v, scene, i, j < n ? j : -1, ci, fi, sm.sp[j < n ? j : i], sm.sf[j < n ? j : i], lane);
         const unsigned any = __ballot_sync(0xffffffffu, o.cnt > 0);
         if (any == 0) continue;
         int incl = o.cnt;

@@ -56,6 +56,7 @@ struct View {
     int profiling;
     int ext_pairs;                        // extension: sphere-plane, box-plane, box-box contacts (no reference counterpart)
     const SdfShape* sdf_shapes;           // extension: [MAX_SDF_SHAPES] shape table for GEOM_SDF bodies (geomA.x = shape id)
+    int n_sdf;                            // shapes in the table (mesh pairs want the warp-per-scene detection kernels)
     // bodies, [NB][B]
     float4 *pos;        // x y z | mass
     float4 *quat;       // x y z w

@@ -273,9 +273,12 @@ __device__ __forceinline__ void ext_box_box(PairOut& o, const float4* __restrict
 
 // extension dispatch, reached only when the reference's chain matched nothing and the extension is enabled; one
 // out-of-line function taking plain pointers, so that the detection kernels' own register budget is untouched
+// defer: a mesh pair whose samples a whole warp will walk (test_pair_warp) is only marked, cnt = -1
 __device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
-                                      const float4* __restrict__ geomB, size_t ii, size_t jj, int i, int j, float4 ci, int ti, float4 cj, int tj)
+                                      const float4* __restrict__ geomB, size_t ii, size_t jj, int i, int j, float4 ci, int ti, float4 cj, int tj,
+                                      bool defer)
 {
+    if (defer && ((ti == GEOM_SDF && (tj == GEOM_SDF || tj == GEOM_PLANE)) || (tj == GEOM_SDF && ti == GEOM_PLANE))) { o.cnt = -1; return; }
     if (ti == GEOM_SPHERE && tj == GEOM_PLANE)      ext_sphere_plane(o, quat, geomA, geomB, jj, i, j, ci, cj);
     else if (tj == GEOM_SPHERE && ti == GEOM_PLANE) ext_sphere_plane(o, quat, geomA, geomB, ii, j, i, cj, ci);
     else if (ti == GEOM_BOX && tj == GEOM_PLANE)    ext_box_plane(o, quat, geomA, geomB, ii, jj, i, j, ci, cj);
@@ -289,7 +292,7 @@ __device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes, const 
 }
 
 // the reference's dispatch chain for the ordered pair (i < j), CollisionDetect.cpp:41-73
-template <bool EXT>
+template <bool EXT, bool DEFER = false>
 __device__ __forceinline__ void test_pair(PairOut& o, const View& v, int scene, int i, int j,
                                           const float4& ci, int fi, const float4& cj, int fj)
 {
@@ -306,7 +309,42 @@ __device__ __forceinline__ void test_pair(PairOut& o, const View& v, int scene, 
     }
     else if (ti == GEOM_CYLINDER && tj == GEOM_PLANE)    cylinder_plane(o, v.quat, v.geomA, v.geomB, at(v, i, scene), at(v, j, scene), i, j, ci, cj);
     else if (tj == GEOM_CYLINDER && ti == GEOM_PLANE)    cylinder_plane(o, v.quat, v.geomA, v.geomB, at(v, j, scene), at(v, i, scene), j, i, cj, ci);
-    else if (EXT)                                        ext_pair(o, v.sdf_shapes, v.quat, v.geomA, v.geomB, at(v, i, scene), at(v, j, scene), i, j, ci, ti, cj, tj);
+    else if (EXT)                                        ext_pair(o, v.sdf_shapes, v.quat, v.geomA, v.geomB, at(v, i, scene), at(v, j, scene), i, j, ci, ti, cj, tj, DEFER);
+}
+
+// a mesh pair (i, j) walked by the whole warp; every lane gets the result
+__device__ __noinline__ void coop_pair(PairOut& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+                                       const float4* __restrict__ geomB, const float4* __restrict__ cproxy, const int* __restrict__ flags,
+                                       size_t ii, size_t jj, int i, int j, int lane)
+{
+    const int ti = __ldg(&flags[ii]) & FLAG_TYPE_MASK, tj = __ldg(&flags[jj]) & FLAG_TYPE_MASK;
+    const float4 ci = __ldg(&cproxy[ii]), cj = __ldg(&cproxy[jj]);
+    if (ti == GEOM_SDF && tj == GEOM_PLANE)      coop_sdf_plane(o, shapes, quat, geomA, geomB, ii, jj, i, j, ci, cj, lane);
+    else if (tj == GEOM_SDF && ti == GEOM_PLANE) coop_sdf_plane(o, shapes, quat, geomA, geomB, jj, ii, j, i, cj, ci, lane);
+    else                                         coop_sdf_sdf(o, shapes, quat, geomA, ii, jj, i, j, ci, cj, lane);
+}
+
+// Warp-collective form of test_pair: every lane passes its own partner j (or -1 for none) of the same body i. Pairs are
+// tested lane-parallel as usual, except mesh pairs (extension), which are deferred and then walked one after the other by
+// all 32 lanes together.
+template <bool EXT>
+__device__ __forceinline__ void test_pair_warp(PairOut& o, const View& v, int scene, int i, int j, const float4& ci, int fi,
+                                               const float4& cj, int fj, int lane)
+{
+    o.cnt = 0;
+    if (j >= 0) test_pair<EXT, true>(o, v, scene, i, j, ci, fi, cj, fj);
+    if (EXT) {
+        unsigned def = __ballot_sync(0xffffffffu, o.cnt < 0);
+        while (def) {
+            const int src = __ffs(def) - 1;
+            def &= def - 1;
+            const int pj = __shfl_sync(0xffffffffu, j, src);
+            PairOut r;
+            r.cnt = 0;
+            coop_pair(r, v.sdf_shapes, v.quat, v.geomA, v.geomB, v.cproxy, v.flags, at(v, i, scene), at(v, pj, scene), i, pj, lane);
+            if (lane == src) o = r;
+        }
+    }
 }
 
 __device__ __forceinline__ void write_contacts(const View& v, int scene, int base, const PairOut& o)

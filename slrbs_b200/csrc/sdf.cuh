@@ -124,4 +124,91 @@ __device__ void ext_sdf_sdf(Out& o, const SdfShape* shapes, const float4* __rest
     sdf_emit(o, ia, ib, H);
 }
 
+// ---- warp-cooperative versions: all 32 lanes call with the same arguments, the samples are dealt to the lanes, and the
+// four deepest of the pair are merged in the order (phi, sample index) -- the order in which the one-thread routines
+// above keep them (stable insertion), so the result is the same bit for bit. Every lane returns the full result.
+struct SdfHitsIdx { int cnt; float phi[4]; int idx[4]; V3 p[4], n[4]; };
+__device__ __forceinline__ void sdf_hit_idx(SdfHitsIdx& H, float phi, int idx, const V3& p, const V3& n)
+{
+    int at = H.cnt;
+    while (at > 0 && phi < H.phi[at - 1]) --at;
+    if (at >= 4) return;
+    const int last = H.cnt < 4 ? H.cnt : 3;
+    for (int k = last; k > at; --k) { H.phi[k] = H.phi[k - 1]; H.idx[k] = H.idx[k - 1]; H.p[k] = H.p[k - 1]; H.n[k] = H.n[k - 1]; }
+    H.phi[at] = phi; H.idx[at] = idx; H.p[at] = p; H.n[at] = n;
+    if (H.cnt < 4) ++H.cnt;
+}
+template <class Out>
+__device__ __forceinline__ void sdf_merge_emit(Out& o, int b0, int b1, const SdfHitsIdx& H, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    int head = 0;
+    for (int r = 0; r < 4; ++r) {
+        const bool have = head < H.cnt;
+        const float ph = have ? H.phi[head] : 3.0e38f;
+        const int id = have ? H.idx[head] : 0x7fffffff;
+        float mn = ph;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mn = fminf(mn, __shfl_xor_sync(full, mn, d));
+        if (mn >= 3.0e38f) break;                                   // warp-uniform
+        int mi = (ph == mn) ? id : 0x7fffffff;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mi = min(mi, __shfl_xor_sync(full, mi, d));
+        const int win = __ffs(__ballot_sync(full, have && ph == mn && id == mi)) - 1;
+        V3 p = mk3(0.f, 0.f, 0.f), n = p;
+        if (have) { p = H.p[head]; n = H.n[head]; }
+        p = mk3(__shfl_sync(full, p.x, win), __shfl_sync(full, p.y, win), __shfl_sync(full, p.z, win));
+        n = mk3(__shfl_sync(full, n.x, win), __shfl_sync(full, n.y, win), __shfl_sync(full, n.z, win));
+        if (r == 0) { o.b0 = b0; o.b1 = b1; o.n = n; }
+        o.add(p, fminf(0.0f, mn));
+        if (lane == win) ++head;
+    }
+}
+
+template <class Out>
+__device__ void coop_sdf_plane(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+                               const float4* __restrict__ geomB, size_t mi, size_t pi, int im, int ip, const float4& cm, const float4& cpl, int lane)
+{
+    const SdfShape S = shapes[(int)__ldg(&geomA[mi]).x];
+    const Q4 qp = mkq(__ldg(&quat[pi]));
+    const V3 planen = rotate(qp, mk3(__ldg(&geomB[pi])));
+    const V3 planep = rotate(qp, mk3(__ldg(&geomA[pi]))) + mk3(cpl);
+    const V3 xm = mk3(cm);
+    if (dot(xm - planep, planen) > S.radius + 1e-3f) return;
+    const Q4 qm = mkq(__ldg(&quat[mi]));
+    SdfHitsIdx H; H.cnt = 0;
+    for (int k = lane; k < S.nv; k += 32) {
+        const V3 pw = rotate(qm, sdf_vertex(S, k)) + xm;
+        const float d = dot(pw - planep, planen);
+        if (d < 1e-3f) sdf_hit_idx(H, d, k, pw, planen);
+    }
+    sdf_merge_emit(o, im, ip, H, lane);
+}
+
+__device__ __forceinline__ void coop_verts_in(const SdfShape& Sf, const Q4& qf, const V3& xf, const SdfShape& Si, const Q4& qi, const V3& xi,
+                                              float flip, int idx0, SdfHitsIdx& H, int lane)
+{
+    const Q4 qinv = qinverse(qi);
+    for (int k = lane; k < Sf.nv; k += 32) {
+        const V3 pw = rotate(qf, sdf_vertex(Sf, k)) + xf;
+        float val; V3 g;
+        sdf_sample(Si, rotate(qinv, pw - xi), val, g);
+        if (val < 1e-3f) sdf_hit_idx(H, val, idx0 + k, pw, flip * rotate(qi, g));
+    }
+}
+
+template <class Out>
+__device__ void coop_sdf_sdf(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+                             size_t ai, size_t bi, int ia, int ib, const float4& ca, const float4& cb, int lane)
+{
+    const SdfShape Sa = shapes[(int)__ldg(&geomA[ai]).x], Sb = shapes[(int)__ldg(&geomA[bi]).x];
+    const V3 xa = mk3(ca), xb = mk3(cb);
+    if (norm(xa - xb) > Sa.radius + Sb.radius + 1e-3f) return;
+    const Q4 qa = mkq(__ldg(&quat[ai])), qb = mkq(__ldg(&quat[bi]));
+    SdfHitsIdx H; H.cnt = 0;
+    coop_verts_in(Sa, qa, xa, Sb, qb, xb, 1.0f, 0, H, lane);
+    coop_verts_in(Sb, qb, xb, Sa, qa, xa, -1.0f, Sa.nv, H, lane);
+    sdf_merge_emit(o, ia, ib, H, lane);
+}
+
 }  // namespace slrbs

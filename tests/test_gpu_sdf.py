@@ -130,3 +130,23 @@ def test_mesh_pile_through_the_headless_program(tmp_path):
     o.step(DT, steps)
     np.testing.assert_allclose(rows[:, :3], o.state()["x"], atol=2e-2)
     assert int([ln for ln in out if ln.startswith("contacts")][0].split()[1]) > 0
+
+
+def test_mesh_pile_with_the_pivoting_solver(shape):
+    """BASELINE config 3 asks for the mesh pile under the BPP solver: both extensions together, device vs restatement."""
+    rng = np.random.default_rng(11)
+    o = pile(shape, rng, n_mesh=3, n_sphere=1)
+    o.set_params(solver_id=3, solver_iter=10)
+    ctx = make_ctx([o, o], shape)
+    ctx.set_params(solver_id=3, solver_iters=10)
+    ctx.step(DT, 60); ctx.sync()
+    worst = 0.0
+    for _ in range(60):
+        o.stage_prepare(); o.stage_detect(); o.stage_jacobians(); o.stage_solve(DT)
+        worst = max(worst, o.blcp_residual(DT))
+        o.stage_scatter(DT); o.stage_integrate(DT)
+    assert worst < 1e-4
+    g, c = ctx.download_state(), o.state()
+    for s in range(2):
+        np.testing.assert_allclose(g["x"][s], c["x"], atol=5e-3)
+    ctx.close()
