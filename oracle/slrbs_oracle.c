@@ -903,6 +903,45 @@ static void sdf_verts_in(const orc_system* s, const body_t* from, const body_t* 
     }
 }
 
+/* signed distance and outward unit normal of a box of half extents h at the box-frame point c */
+static float box_sdf(v3 c, v3 h, v3* n)
+{
+    const v3 q = V3(fminf(fmaxf(c.x, -h.x), h.x), fminf(fmaxf(c.y, -h.y), h.y), fminf(fmaxf(c.z, -h.z), h.z));
+    const v3 dx = v3_sub(c, q);
+    const float dist = v3_norm(dx);
+    if (dist > 0.f) { *n = v3_div(dx, dist); return dist; }
+    const float ex = h.x - fabsf(c.x), ey = h.y - fabsf(c.y), ez = h.z - fabsf(c.z);      /* inside: nearest face */
+    if (ex <= ey && ex <= ez) { *n = V3(c.x < 0.f ? -1.f : 1.f, 0.f, 0.f); return -ex; }
+    if (ey <= ez)             { *n = V3(0.f, c.y < 0.f ? -1.f : 1.f, 0.f); return -ey; }
+    *n = V3(0.f, 0.f, c.z < 0.f ? -1.f : 1.f); return -ez;
+}
+
+/* mesh (body0) against box (body1): the mesh vertices against the box, then the box corners (bit 0 = +x, bit 1 = +y,
+ * bit 2 = +z) in the mesh's grid */
+static void ext_sdf_box(orc_system* s, int i0, int i1)
+{
+    const body_t* m = &s->bodies[i0];
+    const body_t* bx = &s->bodies[i1];
+    const sdf_shape* S = &s->shapes[m->shape];
+    const v3 h = V3(0.5f * bx->dim.x, 0.5f * bx->dim.y, 0.5f * bx->dim.z);
+    if (v3_norm(v3_sub(m->x, bx->x)) > S->radius + v3_norm(h) + 1e-3f) return;
+    const quat qbinv = q_inverse(bx->q), qminv = q_inverse(m->q);
+    sdf_hits H; H.cnt = 0;
+    for (int k = 0; k < S->nv; ++k) {
+        const v3 pw = v3_add(q_rot(m->q, V3(S->verts[3 * k], S->verts[3 * k + 1], S->verts[3 * k + 2])), m->x);
+        v3 nl;
+        const float d = box_sdf(q_rot(qbinv, v3_sub(pw, bx->x)), h, &nl);
+        if (d < 1e-3f) sdf_hit(&H, d, pw, q_rot(bx->q, nl));
+    }
+    for (int k = 0; k < 8; ++k) {
+        const v3 pw = v3_add(q_rot(bx->q, V3((k & 1) ? h.x : -h.x, (k & 2) ? h.y : -h.y, (k & 4) ? h.z : -h.z)), bx->x);
+        float val; v3 g;
+        sdf_sample(S, q_rot(qminv, v3_sub(pw, m->x)), &val, &g);
+        if (val < 1e-3f) sdf_hit(&H, val, pw, v3_neg(q_rot(m->q, g)));
+    }
+    sdf_emit(s, i0, i1, &H);
+}
+
 /* mesh i0 (body0) against mesh i1 (body1): body0's vertices in body1's grid, then body1's in body0's */
 static void ext_sdf_sdf(orc_system* s, int i0, int i1)
 {
@@ -943,6 +982,8 @@ void orc_stage_detect(orc_system* s)
                 else if (t0 == ORC_SPHERE && t1 == ORC_SDF)   ext_sphere_sdf(s, i, j);
                 else if (t1 == ORC_SPHERE && t0 == ORC_SDF)   ext_sphere_sdf(s, j, i);
                 else if (t0 == ORC_SDF && t1 == ORC_SDF)      ext_sdf_sdf(s, i, j);
+                else if (t0 == ORC_SDF && t1 == ORC_BOX)      ext_sdf_box(s, i, j);
+                else if (t1 == ORC_SDF && t0 == ORC_BOX)      ext_sdf_box(s, j, i);
             }
         }
     }

@@ -113,7 +113,7 @@ void orc_get_solver_blocks(orc_system* s, float h, float* Acontact9, float* rhs_
 
 /* EXTENSION (no reference counterpart): triangle meshes as signed-distance grids. A shape = grid
  * (node (i,j,k) at origin + cell*(i,j,k), value grid[(k*ny+j)*nx+i], negative inside) + its vertices as sample points,
- * body frame. Contacts (with orc_set_extensions): mesh-plane, sphere-mesh, mesh-mesh; at most the 4 deepest points of a
+ * body frame. Contacts (with orc_set_extensions): mesh-plane, sphere-mesh, mesh-mesh, mesh-box; at most the 4 deepest points of a
  * pair, one normal per pair. orc_build_sdf: grid of a closed triangle mesh. orc_load_obj: 'v' / 'f' lines as
  * src/util/OBJLoader.cpp:34-122 reads them. */
 int  orc_add_sdf_shape(orc_system* s, int nx, int ny, int nz, const float* origin3, float cell, const float* grid,

@@ -278,7 +278,7 @@ __device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes, const 
                                       const float4* __restrict__ geomB, size_t ii, size_t jj, int i, int j, float4 ci, int ti, float4 cj, int tj,
                                       bool defer)
 {
-    if (defer && ((ti == GEOM_SDF && (tj == GEOM_SDF || tj == GEOM_PLANE)) || (tj == GEOM_SDF && ti == GEOM_PLANE))) { o.cnt = -1; return; }
+    if (defer && ((ti == GEOM_SDF && (tj == GEOM_SDF || tj == GEOM_PLANE || tj == GEOM_BOX)) || (tj == GEOM_SDF && (ti == GEOM_PLANE || ti == GEOM_BOX)))) { o.cnt = -1; return; }
     if (ti == GEOM_SPHERE && tj == GEOM_PLANE)      ext_sphere_plane(o, quat, geomA, geomB, jj, i, j, ci, cj);
     else if (tj == GEOM_SPHERE && ti == GEOM_PLANE) ext_sphere_plane(o, quat, geomA, geomB, ii, j, i, cj, ci);
     else if (ti == GEOM_BOX && tj == GEOM_PLANE)    ext_box_plane(o, quat, geomA, geomB, ii, jj, i, j, ci, cj);
@@ -289,6 +289,8 @@ __device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes, const 
     else if (ti == GEOM_SPHERE && tj == GEOM_SDF)   ext_sphere_sdf(o, shapes, quat, geomA, jj, i, j, ci, cj);
     else if (tj == GEOM_SPHERE && ti == GEOM_SDF)   ext_sphere_sdf(o, shapes, quat, geomA, ii, j, i, cj, ci);
     else if (ti == GEOM_SDF && tj == GEOM_SDF)      ext_sdf_sdf(o, shapes, quat, geomA, ii, jj, i, j, ci, cj);
+    else if (ti == GEOM_SDF && tj == GEOM_BOX)      ext_sdf_box(o, shapes, quat, geomA, ii, jj, i, j, ci, cj);
+    else if (tj == GEOM_SDF && ti == GEOM_BOX)      ext_sdf_box(o, shapes, quat, geomA, jj, ii, j, i, cj, ci);
 }
 
 // the reference's dispatch chain for the ordered pair (i < j), CollisionDetect.cpp:41-73
@@ -321,6 +323,8 @@ __device__ __noinline__ void coop_pair(PairOut& o, const SdfShape* shapes, const
     const float4 ci = __ldg(&cproxy[ii]), cj = __ldg(&cproxy[jj]);
     if (ti == GEOM_SDF && tj == GEOM_PLANE)      coop_sdf_plane(o, shapes, quat, geomA, geomB, ii, jj, i, j, ci, cj, lane);
     else if (tj == GEOM_SDF && ti == GEOM_PLANE) coop_sdf_plane(o, shapes, quat, geomA, geomB, jj, ii, j, i, cj, ci, lane);
+    else if (ti == GEOM_SDF && tj == GEOM_BOX)   coop_sdf_box(o, shapes, quat, geomA, ii, jj, i, j, ci, cj, lane);
+    else if (tj == GEOM_SDF && ti == GEOM_BOX)   coop_sdf_box(o, shapes, quat, geomA, jj, ii, j, i, cj, ci, lane);
     else                                         coop_sdf_sdf(o, shapes, quat, geomA, ii, jj, i, j, ci, cj, lane);
 }
 

@@ -124,6 +124,48 @@ __device__ void ext_sdf_sdf(Out& o, const SdfShape* shapes, const float4* __rest
     sdf_emit(o, ia, ib, H);
 }
 
+// signed distance and outward unit normal of a box of half extents h at the box-frame point c
+__device__ __forceinline__ float box_sdf(const V3& c, const V3& h, V3& n)
+{
+    const V3 q = mk3(fminf(fmaxf(c.x, -h.x), h.x), fminf(fmaxf(c.y, -h.y), h.y), fminf(fmaxf(c.z, -h.z), h.z));
+    const V3 dx = c - q;
+    const float dist = norm(dx);
+    if (dist > 0.f) { n = dx / dist; return dist; }
+    const float ex = h.x - fabsf(c.x), ey = h.y - fabsf(c.y), ez = h.z - fabsf(c.z);
+    if (ex <= ey && ex <= ez) { n = mk3(c.x < 0.f ? -1.f : 1.f, 0.f, 0.f); return -ex; }
+    if (ey <= ez)             { n = mk3(0.f, c.y < 0.f ? -1.f : 1.f, 0.f); return -ey; }
+    n = mk3(0.f, 0.f, c.z < 0.f ? -1.f : 1.f); return -ez;
+}
+__device__ __forceinline__ V3 box_corner(const V3& h, int k) { return mk3((k & 1) ? h.x : -h.x, (k & 2) ? h.y : -h.y, (k & 4) ? h.z : -h.z); }
+
+// mesh (body0) against box (body1): the mesh vertices against the box, then the box corners in the mesh's grid
+template <class Out>
+__device__ void ext_sdf_box(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+                            size_t mi, size_t bi, int im, int ib, const float4& cm, const float4& cb)
+{
+    const SdfShape S = shapes[(int)__ldg(&geomA[mi]).x];
+    const float4 dim = __ldg(&geomA[bi]);
+    const V3 h = mk3(0.5f * dim.x, 0.5f * dim.y, 0.5f * dim.z);
+    const V3 xm = mk3(cm), xb = mk3(cb);
+    if (norm(xm - xb) > S.radius + norm(h) + 1e-3f) return;
+    const Q4 qm = mkq(__ldg(&quat[mi])), qb = mkq(__ldg(&quat[bi]));
+    const Q4 qbinv = qinverse(qb), qminv = qinverse(qm);
+    SdfHits H; H.cnt = 0;
+    for (int k = 0; k < S.nv; ++k) {
+        const V3 pw = rotate(qm, sdf_vertex(S, k)) + xm;
+        V3 nl;
+        const float d = box_sdf(rotate(qbinv, pw - xb), h, nl);
+        if (d < 1e-3f) sdf_hit(H, d, pw, rotate(qb, nl));
+    }
+    for (int k = 0; k < 8; ++k) {
+        const V3 pw = rotate(qb, box_corner(h, k)) + xb;
+        float val; V3 g;
+        sdf_sample(S, rotate(qminv, pw - xm), val, g);
+        if (val < 1e-3f) sdf_hit(H, val, pw, -rotate(qm, g));
+    }
+    sdf_emit(o, im, ib, H);
+}
+
 // ---- warp-cooperative versions: all 32 lanes call with the same arguments, the samples are dealt to the lanes, and the
 // four deepest of the pair are merged in the order (phi, sample index) -- the order in which the one-thread routines
 // above keep them (stable insertion), so the result is the same bit for bit. Every lane returns the full result.
@@ -209,6 +251,33 @@ __device__ void coop_sdf_sdf(Out& o, const SdfShape* shapes, const float4* __res
     coop_verts_in(Sa, qa, xa, Sb, qb, xb, 1.0f, 0, H, lane);
     coop_verts_in(Sb, qb, xb, Sa, qa, xa, -1.0f, Sa.nv, H, lane);
     sdf_merge_emit(o, ia, ib, H, lane);
+}
+
+template <class Out>
+__device__ void coop_sdf_box(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+                             size_t mi, size_t bi, int im, int ib, const float4& cm, const float4& cb, int lane)
+{
+    const SdfShape S = shapes[(int)__ldg(&geomA[mi]).x];
+    const float4 dim = __ldg(&geomA[bi]);
+    const V3 h = mk3(0.5f * dim.x, 0.5f * dim.y, 0.5f * dim.z);
+    const V3 xm = mk3(cm), xb = mk3(cb);
+    if (norm(xm - xb) > S.radius + norm(h) + 1e-3f) return;
+    const Q4 qm = mkq(__ldg(&quat[mi])), qb = mkq(__ldg(&quat[bi]));
+    const Q4 qbinv = qinverse(qb), qminv = qinverse(qm);
+    SdfHitsIdx H; H.cnt = 0;
+    for (int k = lane; k < S.nv; k += 32) {
+        const V3 pw = rotate(qm, sdf_vertex(S, k)) + xm;
+        V3 nl;
+        const float d = box_sdf(rotate(qbinv, pw - xb), h, nl);
+        if (d < 1e-3f) sdf_hit_idx(H, d, k, pw, rotate(qb, nl));
+    }
+    if (lane < 8) {
+        const V3 pw = rotate(qb, box_corner(h, lane)) + xb;
+        float val; V3 g;
+        sdf_sample(S, rotate(qminv, pw - xm), val, g);
+        if (val < 1e-3f) sdf_hit_idx(H, val, S.nv + lane, pw, -rotate(qm, g));
+    }
+    sdf_merge_emit(o, im, ib, H, lane);
 }
 
 }  // namespace slrbs

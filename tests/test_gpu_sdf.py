@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import mesh_lib
-from oracle_lib import Oracle, PLANE, SDF, SPHERE
+from oracle_lib import Oracle, BOX, PLANE, SDF, SPHERE
 from gpu_helpers import assert_bit_equal, context_from_oracles, push_state
 from slrbs_b200 import capi
 
@@ -30,9 +30,11 @@ def pile(shape, rng, n_mesh=6, n_sphere=3):
     sid = o.add_sdf_shape(shape)
     for i in range(n_mesh):
         q = rng.normal(size=4); q /= np.linalg.norm(q)
-        o.add_body(1.0, SDF, [sid], x=[rng.uniform(-0.4, 0.4), 0.6 + 0.95 * i, rng.uniform(-0.4, 0.4)], q=q)
+        o.add_body(1.0, SDF, [sid], x=[rng.uniform(-0.4, 0.4), 0.9 + 0.95 * i, rng.uniform(-0.4, 0.4)], q=q)
     for i in range(n_sphere):
-        o.add_body(1.0, SPHERE, [0.3], x=[rng.uniform(-0.3, 0.3), 0.8 + 0.95 * n_mesh + 0.7 * i, rng.uniform(-0.3, 0.3)])
+        o.add_body(1.0, SPHERE, [0.3], x=[rng.uniform(-0.3, 0.3), 1.5 + 0.95 * n_mesh + 0.7 * i, rng.uniform(-0.3, 0.3)])
+    o.add_body(1.0, BOX, [0.5, 0.4, 0.6], x=[0.2, 0.9 + 0.95 * n_mesh, -0.1])          # a loose box on top of the meshes
+    o.add_body(1.0, BOX, [1.2, 0.3, 1.2], x=[0.0, 0.15, 0.0], fixed=True)                   # a fixed slab on the plane
     o.add_body(1.0, PLANE, [0, 0, 0, 0, 1, 0], fixed=True)
     return o
 
@@ -59,7 +61,7 @@ def test_contact_lists_bit_exact_along_a_pile_trajectory(shape):
     rng = np.random.default_rng(3)
     o = pile(shape, rng)
     oracles, done = [], 0
-    for st in [0, 40, 80, 120, 200, 300]:
+    for st in [0, 40, 80, 126, 200, 300]:
         o.step(DT, st - done); done = st
         oracles.append(frozen(shape, o))
     ctx = make_ctx(oracles, shape)
@@ -77,7 +79,7 @@ def test_contact_lists_bit_exact_along_a_pile_trajectory(shape):
                 assert_bit_equal(g[k], r[k], f"scene {s} {k}")
             gt = c.body_params()["geom_type"]
             kinds |= {(int(gt[a]), int(gt[b])) for a, b in zip(r["body0"], r["body1"])}
-    assert {(SDF, PLANE), (SDF, SDF), (SPHERE, SDF)} <= kinds, kinds
+    assert {(SDF, PLANE), (SDF, SDF), (SPHERE, SDF), (SDF, BOX)} <= kinds, kinds
     ctx.close()
 
 

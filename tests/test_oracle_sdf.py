@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import mesh_lib
-from oracle_lib import Oracle, PLANE, SDF, SPHERE
+from oracle_lib import Oracle, BOX, PLANE, SDF, SPHERE
 
 DT = 0.01
 BUNNY = "/root/reference/resources/bunny.obj"
@@ -90,3 +90,22 @@ def test_mesh_on_mesh_and_sphere_on_mesh_do_not_sink(blob_shape):
         assert c["phi"].min(initial=0.0) > -0.05           # penetration stays shallow
     assert seen_mm > 20 and seen_sm > 5
     assert np.isfinite(o.state()["x"]).all()
+
+
+def test_mesh_rests_on_a_box_and_a_box_on_a_mesh(blob_shape):
+    o = Oracle(); o.set_extensions(1)
+    sid = o.add_sdf_shape(blob_shape)
+    o.add_body(1.0, SDF, [sid], x=[0.1, 0.9, 0.0])
+    o.add_body(0.5, BOX, [0.4, 0.4, 0.4], x=[0.1, 1.9, 0.0])
+    o.add_body(1.0, BOX, [6.0, 0.4, 6.0], x=[0, 0, 0], fixed=True)          # slab, top at y = 0.2
+    seen_mesh_slab = seen_mesh_box = 0
+    for _ in range(200):
+        o.step(DT)
+        c = o.contacts()
+        pairs = set(zip(c["body0"].tolist(), c["body1"].tolist()))
+        seen_mesh_slab += (0, 2) in pairs; seen_mesh_box += (0, 1) in pairs
+        assert c["phi"].min(initial=0.0) > -0.06
+    assert seen_mesh_slab > 50 and seen_mesh_box > 5
+    st = o.state()
+    low = (blob_shape["verts"] @ quat_matrix(st["q"][0]).T + st["x"][0])[:, 1].min()
+    assert 0.2 - 5e-3 < low < 0.2 + 5e-3, low
