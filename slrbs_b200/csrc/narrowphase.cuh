@@ -278,6 +278,21 @@ __device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes, const 
                                       const float4* __restrict__ geomB, size_t ii, size_t jj, int i, int j, float4 ci, int ti, float4 cj, int tj,
                                       bool defer)
 {
+    // bounding spheres first: none of the routines below can produce a contact for bodies further apart than this
+    // (their own tolerances are 1e-3), and it keeps far pairs out of the box-box SAT and the deferred mesh walks
+    {
+        float bi = -1.f, bj = -1.f;
+        if (ti == GEOM_SPHERE) bi = ci.w;
+        else if (ti == GEOM_BOX) { const float4 d = __ldg(&geomA[ii]); bi = norm(mk3(0.5f * d.x, 0.5f * d.y, 0.5f * d.z)); }
+        else if (ti == GEOM_SDF) bi = shapes[(int)__ldg(&geomA[ii]).x].radius;
+        if (tj == GEOM_SPHERE) bj = cj.w;
+        else if (tj == GEOM_BOX) { const float4 d = __ldg(&geomA[jj]); bj = norm(mk3(0.5f * d.x, 0.5f * d.y, 0.5f * d.z)); }
+        else if (tj == GEOM_SDF) bj = shapes[(int)__ldg(&geomA[jj]).x].radius;
+        if (bi >= 0.f && bj >= 0.f) {
+            const float lim = bi + bj + 0.01f;
+            if (sqnorm(mk3(ci) - mk3(cj)) > lim * lim) return;
+        }
+    }
     if (defer && ((ti == GEOM_SDF && (tj == GEOM_SDF || tj == GEOM_PLANE || tj == GEOM_BOX)) || (tj == GEOM_SDF && (ti == GEOM_PLANE || ti == GEOM_BOX)))) { o.cnt = -1; return; }
     if (ti == GEOM_SPHERE && tj == GEOM_PLANE)      ext_sphere_plane(o, quat, geomA, geomB, jj, i, j, ci, cj);
     else if (tj == GEOM_SPHERE && ti == GEOM_PLANE) ext_sphere_plane(o, quat, geomA, geomB, ii, j, i, cj, ci);

@@ -27,6 +27,28 @@ if a.scene == "mesh_pile":
         o.add_body(1.0, SDF, [sid], x=[0.05 * (i % 3 - 1), 0.6 + 1.1 * i, 0.05 * (i % 2)], q=[0.0, np.sin(0.5 * ang), 0.0, np.cos(0.5 * ang)])
     o.add_body(1.0, PLANE, [0, 0, 0, 0, 1, 0], fixed=True)
     a.ext = 1
+elif a.scene == "mixed_pile":
+    # BASELINE config 3: mixed spheres / boxes / meshes poured into a box container, a.k bodies per scene
+    import mesh_lib
+    from oracle_lib import SDF, BOX, SPHERE
+    mv, mf = mesh_lib.blob(radius=0.35); shape = mesh_lib.build_sdf(mv, mf, cell=0.05)
+    o = Oracle(); o.set_extensions(1); sid = o.add_sdf_shape(shape)
+    side = max(2, int(round((a.k / 6.0) ** (1.0 / 3.0))))
+    nlay = (a.k + side * side - 1) // (side * side)
+    rr = np.random.default_rng(7)
+    for i in range(a.k):
+        ix, iz, iy = i % side, (i // side) % side, i // (side * side)
+        pos = [(ix - 0.5 * (side - 1)) * 1.0, 0.9 + 1.0 * iy, (iz - 0.5 * (side - 1)) * 1.0]
+        q = rr.normal(size=4); q /= np.linalg.norm(q)
+        kind = i % 3
+        if kind == 0: o.add_body(1.0, SPHERE, [0.35], x=pos)
+        elif kind == 1: o.add_body(1.0, BOX, [0.55, 0.55, 0.55], x=pos, q=q)
+        else: o.add_body(1.0, SDF, [sid], x=pos, q=q)
+    ext = side * 1.0 + 1.0
+    o.add_body(1.0, BOX, [ext + 1.0, 0.4, ext + 1.0], x=[0, 0, 0], fixed=True)
+    for sx, sz in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+        o.add_body(1.0, BOX, [0.4 if sx else ext + 1.0, nlay + 3.0, 0.4 if sz else ext + 1.0], x=[sx * 0.5 * (ext + 0.4), 0.5 * (nlay + 3.0), sz * 0.5 * (ext + 0.4)], fixed=True)
+    a.ext = 1
 else:
   o = Oracle(a.scene, k=a.k) if a.scene in ("sphere_stack", "box_stack") else (Oracle("marble_box_n", nx=10, nz=10, ny=10) if a.scene == "mb1k" else Oracle(a.scene))
 s = scene_arrays(o)
