@@ -284,10 +284,10 @@ __device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes, const 
         float bi = -1.f, bj = -1.f;
         if (ti == GEOM_SPHERE) bi = ci.w;
         else if (ti == GEOM_BOX) { const float4 d = __ldg(&geomA[ii]); bi = norm(mk3(0.5f * d.x, 0.5f * d.y, 0.5f * d.z)); }
-        else if (ti == GEOM_SDF) bi = shapes[(int)__ldg(&geomA[ii]).x].radius;
+        else if (ti == GEOM_SDF) bi = sdf_shape_of(shapes, geomA, ii).radius;
         if (tj == GEOM_SPHERE) bj = cj.w;
         else if (tj == GEOM_BOX) { const float4 d = __ldg(&geomA[jj]); bj = norm(mk3(0.5f * d.x, 0.5f * d.y, 0.5f * d.z)); }
-        else if (tj == GEOM_SDF) bj = shapes[(int)__ldg(&geomA[jj]).x].radius;
+        else if (tj == GEOM_SDF) bj = sdf_shape_of(shapes, geomA, jj).radius;
         if (bi >= 0.f && bj >= 0.f) {
             const float lim = bi + bj + 0.01f;
             if (sqnorm(mk3(ci) - mk3(cj)) > lim * lim) return;

@@ -12,6 +12,14 @@ namespace slrbs {
 
 __device__ __forceinline__ float lerpf(float a, float b, float t) { return a + t * (b - a); }
 
+// shape of a GEOM_SDF body (geomA.x = shape id); an id outside the table or a slot never filled gives an empty shape
+__device__ __forceinline__ SdfShape sdf_shape_of(const SdfShape* shapes, const float4* __restrict__ geomA, size_t bi)
+{
+    const int id = (int)__ldg(&geomA[bi]).x;
+    if (id < 0 || id >= MAX_SDF_SHAPES) { SdfShape e; e.grid = nullptr; e.verts = nullptr; e.nx = e.ny = e.nz = 2; e.nv = 0; e.ox = e.oy = e.oz = 0.f; e.cell = 1.f; e.radius = 0.f; return e; }
+    return shapes[id];
+}
+
 __device__ __forceinline__ void sdf_sample(const SdfShape& S, const V3& pl, float& phi, V3& grad)
 {
     float fx = (pl.x - S.ox) / S.cell, fy = (pl.y - S.oy) / S.cell, fz = (pl.z - S.oz) / S.cell;
@@ -62,7 +70,8 @@ template <class Out>
 __device__ void ext_sdf_plane(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                               const float4* __restrict__ geomB, size_t mi, size_t pi, int im, int ip, const float4& cm, const float4& cpl)
 {
-    const SdfShape S = shapes[(int)__ldg(&geomA[mi]).x];
+    const SdfShape S = sdf_shape_of(shapes, geomA, mi);
+    if (!S.grid) return;
     const Q4 qp = mkq(__ldg(&quat[pi]));
     const V3 planen = rotate(qp, mk3(__ldg(&geomB[pi])));
     const V3 planep = rotate(qp, mk3(__ldg(&geomA[pi]))) + mk3(cpl);
@@ -83,7 +92,8 @@ template <class Out>
 __device__ void ext_sphere_sdf(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                                size_t mi, int is, int im, const float4& cs, const float4& cm)
 {
-    const SdfShape S = shapes[(int)__ldg(&geomA[mi]).x];
+    const SdfShape S = sdf_shape_of(shapes, geomA, mi);
+    if (!S.grid) return;
     const V3 xs = mk3(cs), rel = xs - mk3(cm);
     if (norm(rel) > S.radius + cs.w + 1e-3f) return;
     const Q4 qm = mkq(__ldg(&quat[mi]));
@@ -114,7 +124,8 @@ template <class Out>
 __device__ void ext_sdf_sdf(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                             size_t ai, size_t bi, int ia, int ib, const float4& ca, const float4& cb)
 {
-    const SdfShape Sa = shapes[(int)__ldg(&geomA[ai]).x], Sb = shapes[(int)__ldg(&geomA[bi]).x];
+    const SdfShape Sa = sdf_shape_of(shapes, geomA, ai), Sb = sdf_shape_of(shapes, geomA, bi);
+    if (!Sa.grid || !Sb.grid) return;
     const V3 xa = mk3(ca), xb = mk3(cb);
     if (norm(xa - xb) > Sa.radius + Sb.radius + 1e-3f) return;
     const Q4 qa = mkq(__ldg(&quat[ai])), qb = mkq(__ldg(&quat[bi]));
@@ -143,7 +154,8 @@ template <class Out>
 __device__ void ext_sdf_box(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                             size_t mi, size_t bi, int im, int ib, const float4& cm, const float4& cb)
 {
-    const SdfShape S = shapes[(int)__ldg(&geomA[mi]).x];
+    const SdfShape S = sdf_shape_of(shapes, geomA, mi);
+    if (!S.grid) return;
     const float4 dim = __ldg(&geomA[bi]);
     const V3 h = mk3(0.5f * dim.x, 0.5f * dim.y, 0.5f * dim.z);
     const V3 xm = mk3(cm), xb = mk3(cb);
@@ -211,7 +223,8 @@ template <class Out>
 __device__ void coop_sdf_plane(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                                const float4* __restrict__ geomB, size_t mi, size_t pi, int im, int ip, const float4& cm, const float4& cpl, int lane)
 {
-    const SdfShape S = shapes[(int)__ldg(&geomA[mi]).x];
+    const SdfShape S = sdf_shape_of(shapes, geomA, mi);
+    if (!S.grid) return;
     const Q4 qp = mkq(__ldg(&quat[pi]));
     const V3 planen = rotate(qp, mk3(__ldg(&geomB[pi])));
     const V3 planep = rotate(qp, mk3(__ldg(&geomA[pi]))) + mk3(cpl);
@@ -243,7 +256,8 @@ template <class Out>
 __device__ void coop_sdf_sdf(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                              size_t ai, size_t bi, int ia, int ib, const float4& ca, const float4& cb, int lane)
 {
-    const SdfShape Sa = shapes[(int)__ldg(&geomA[ai]).x], Sb = shapes[(int)__ldg(&geomA[bi]).x];
+    const SdfShape Sa = sdf_shape_of(shapes, geomA, ai), Sb = sdf_shape_of(shapes, geomA, bi);
+    if (!Sa.grid || !Sb.grid) return;
     const V3 xa = mk3(ca), xb = mk3(cb);
     if (norm(xa - xb) > Sa.radius + Sb.radius + 1e-3f) return;
     const Q4 qa = mkq(__ldg(&quat[ai])), qb = mkq(__ldg(&quat[bi]));
@@ -257,7 +271,8 @@ template <class Out>
 __device__ void coop_sdf_box(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                              size_t mi, size_t bi, int im, int ib, const float4& cm, const float4& cb, int lane)
 {
-    const SdfShape S = shapes[(int)__ldg(&geomA[mi]).x];
+    const SdfShape S = sdf_shape_of(shapes, geomA, mi);
+    if (!S.grid) return;
     const float4 dim = __ldg(&geomA[bi]);
     const V3 h = mk3(0.5f * dim.x, 0.5f * dim.y, 0.5f * dim.z);
     const V3 xm = mk3(cm), xb = mk3(cb);

@@ -152,3 +152,16 @@ def test_mesh_pile_with_the_pivoting_solver(shape):
     for s in range(2):
         np.testing.assert_allclose(g["x"][s], c["x"], atol=5e-3)
     ctx.close()
+
+
+def test_mesh_body_without_an_uploaded_shape_makes_no_contacts(shape):
+    o = Oracle(); o.set_extensions(1)
+    sid = o.add_sdf_shape(shape)
+    o.add_body(1.0, SDF, [sid], x=[0, 0.3, 0])
+    o.add_body(1.0, SPHERE, [0.3], x=[0.0, 0.9, 0.0])
+    o.add_body(1.0, PLANE, [0, 0, 0, 0, 1, 0], fixed=True)
+    ctx = context_from_oracles([o], max_contacts=32)          # the shape is never given to the context
+    ctx.set_extensions(1)
+    ctx.step(DT, 3); ctx.sync()
+    assert ctx.contact_counts()[0] == 0
+    ctx.close()
