@@ -565,7 +565,13 @@ int slrbs_sync(slrbs_ctx* c)
     CU(cudaMemcpyAsync(c->h_flag, c->v.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (*c->h_flag & 1) return fail(SLRBS_E_CAPACITY, "a scene produced more contacts than max_contacts; extra contacts were dropped");
-    if (*c->h_flag & 2) return fail(SLRBS_E_CAPACITY, "a scene has more constraint rows than the pivoting solver holds (solver_id 3: 288 scalar rows); its impulses were left at zero");
+    if (*c->h_flag & 2) {
+        // reported once (the contact-capacity bit stays set: the contact lists of that context are truncated for good)
+        static const int zero = 0;
+        CU(cudaMemcpyAsync(c->v.overflow, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return fail(SLRBS_E_CAPACITY, "a scene has more constraint rows than the pivoting solver holds (solver_id 3: 288 scalar rows); its impulses were left at zero");
+    }
     return 0;
 }
 

@@ -95,6 +95,8 @@ def test_bpp_refuses_a_scene_with_more_rows_than_it_holds():
     ctx.step(DT, 80)
     with pytest.raises(SlrbsError):
         ctx.sync()
+    ctx.set_params(solver_id=0, solver_iters=10)       # reported once: the context is usable again with Box-PGS
+    ctx.step(DT, 2); ctx.sync()
     ctx.close()
 
 
