@@ -4,6 +4,7 @@
 #include "../../include/slrbs_b200.h"
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -199,6 +200,7 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
         return fail(SLRBS_E_CUDA, std::string("slrbs_create: device is ") + prop.name + ", kernels are built for sm_100a only");
     CU(cudaSetDevice(device));
     init_detect_kernels();
+    init_pair_kernels();
     init_level_kernels();
     init_bpp_kernel();
     init_pile_kernels();
@@ -330,6 +332,18 @@ int slrbs_set_extensions(slrbs_ctx* c, int flags)
     if (!c || flags < 0 || flags > 1) return fail(SLRBS_E_ARG, "slrbs_set_extensions: bad argument");
     if (c->v.ext_pairs != (flags & 1) && c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }   // the View is baked into the graph
     c->v.ext_pairs = flags & 1;
+    // scenes of >= 128 bodies with the extension pairs use the pair-parallel detection (detect_pairs.cu): candidate
+    // candidate lists of 64 pairs per body and scene, one result record per contact slot; SLRBS_DETECT_PAIRS=0 keeps the row-parallel kernels
+    const char* e = std::getenv("SLRBS_DETECT_PAIRS");
+    if (c->v.ext_pairs && c->v.NB >= 128 && !c->v.pc_pairs && !(e && std::atoi(e) == 0)) {
+        CU(cudaSetDevice(c->device));
+        const int cap = 64 * c->v.NB;
+        int r;
+        if ((r = dalloc(c, &c->v.pc_pairs, (size_t)cap * c->v.B)) || (r = dalloc(c, &c->v.pc_count, (size_t)c->v.B)) ||
+            (r = dalloc(c, &c->v.pc_hits, (size_t)c->v.B)) || (r = dalloc(c, &c->v.pc_out, (size_t)c->v.NC * c->v.B * 6)))
+            return r;
+        c->v.pc_cap = cap;
+    }
     return 0;
 }
 
@@ -565,6 +579,16 @@ int slrbs_sync(slrbs_ctx* c)
     CU(cudaMemcpyAsync(c->h_flag, c->v.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (*c->h_flag & 1) return fail(SLRBS_E_CAPACITY, "a scene produced more contacts than max_contacts; extra contacts were dropped");
+    if (*c->h_flag & 4) {
+        std::vector<int> cand(c->v.B), hits(c->v.B);
+        CU(cudaMemcpy(cand.data(), c->v.pc_count, sizeof(int) * c->v.B, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hits.data(), c->v.pc_hits, sizeof(int) * c->v.B, cudaMemcpyDeviceToHost));
+        int mc = 0, mh = 0;
+        for (int k = 0; k < c->v.B; ++k) { mc = std::max(mc, cand[k]); mh = std::max(mh, hits[k]); }
+        return fail(SLRBS_E_CAPACITY, "a scene produced more candidate or touching pairs than the pair-parallel detection holds (last step: " +
+                    std::to_string(mc) + " candidates of " + std::to_string(c->v.pc_cap) + ", " + std::to_string(mh) + " touching pairs of " +
+                    std::to_string(std::min(c->v.NC, 16384)) + "); contacts were dropped");
+    }
     if (*c->h_flag & 2) {
         // reported once (the contact-capacity bit stays set: the contact lists of that context are truncated for good)
         static const int zero = 0;

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)v.NB * v.B) return;
     const int scene = (int)(tid % v.B), slot = (int)(tid / v.B);
-    if (slot == 0) v.ncontacts[scene] = 0;                       // CollisionDetect::clear, RigidBodySystem.cpp:75
+    if (slot == 0) { v.ncontacts[scene] = 0; if (v.pc_count) { v.pc_count[scene] = 0; v.pc_hits[scene] = 0; } }   // CollisionDetect::clear, RigidBodySystem.cpp:75
     if (slot >= v.nbodies[scene]) return;
     const size_t i = at(v, slot, scene);
     const float4 px = v.pos[i];

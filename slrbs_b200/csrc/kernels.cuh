@@ -28,6 +28,9 @@ void launch_prepare(const View& v, cudaStream_t s);
 void launch_detect(const View& v, int broadphase, cudaStream_t s);
 bool detect_warp_fits(int NB);
 void init_detect_kernels();
+// detect_pairs.cu: pair-parallel detection for extension scenes of >= 128 bodies (used when v.pc_pairs is set)
+void init_pair_kernels();
+void launch_detect_pairs(const View& v, cudaStream_t s);
 const char* detect_variant(const View& v, int broadphase);
 void init_level_kernels();
 void launch_contact_rows(const View& v, float h, cudaStream_t s);

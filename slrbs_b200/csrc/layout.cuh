@@ -57,6 +57,12 @@ struct View {
     int ext_pairs;                        // extension: sphere-plane, box-plane, box-box contacts (no reference counterpart)
     const SdfShape* sdf_shapes;           // extension: [MAX_SDF_SHAPES] shape table for GEOM_SDF bodies (geomA.x = shape id)
     int n_sdf;                            // shapes in the table (mesh pairs want the warp-per-scene detection kernels)
+    // pair-parallel detection of extension scenes with >= 128 bodies (detect_pairs.cu); null otherwise
+    int2*   pc_pairs;                     // [B][pc_cap] candidate pairs (i, j), unordered
+    int*    pc_count;                     // [B] candidates appended this step (zeroed by k_prepare)
+    int*    pc_hits;                      // [B] pairs that touch (zeroed by k_prepare)
+    float4* pc_out;                       // [B][NC][6] narrow-phase result of each touching pair, unordered
+    int     pc_cap;
     // bodies, [NB][B]
     float4 *pos;        // x y z | mass
     float4 *quat;       // x y z w

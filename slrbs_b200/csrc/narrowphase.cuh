@@ -36,7 +36,7 @@ __device__ __forceinline__ void sphere_sphere(PairOut& o, int i0, int i1, const 
 }
 
 // CollisionDetect.cpp:125-150 (body0 = sphere, body1 = box)
-__device__ __noinline__ void sphere_box(PairOut& o, const float4* __restrict__ quat, const float4* __restrict__ geomA, size_t bi,
+static __device__ __noinline__ void sphere_box(PairOut& o, const float4* __restrict__ quat, const float4* __restrict__ geomA, size_t bi,
                                        int is, int ib, const float4& cs, const float4& cb)
 {
     const V3 xs = mk3(cs), xb = mk3(cb);
@@ -58,7 +58,7 @@ __device__ __noinline__ void sphere_box(PairOut& o, const float4* __restrict__ q
 }
 
 // CollisionDetect.cpp:152-274 (body0 = cylinder, body1 = plane)
-__device__ __noinline__ void cylinder_plane(PairOut& o, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+static __device__ __noinline__ void cylinder_plane(PairOut& o, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                                            const float4* __restrict__ geomB, size_t ci, size_t pi, int ic, int ip,
                                            const float4& cc, const float4& cpl)
 {
@@ -274,7 +274,7 @@ __device__ __forceinline__ void ext_box_box(PairOut& o, const float4* __restrict
 // extension dispatch, reached only when the reference's chain matched nothing and the extension is enabled; one
 // out-of-line function taking plain pointers, so that the detection kernels' own register budget is untouched
 // defer: a mesh pair whose samples a whole warp will walk (test_pair_warp) is only marked, cnt = -1
-__device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+static __device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                                       const float4* __restrict__ geomB, size_t ii, size_t jj, int i, int j, float4 ci, int ti, float4 cj, int tj,
                                       bool defer)
 {
@@ -330,7 +330,7 @@ __device__ __forceinline__ void test_pair(PairOut& o, const View& v, int scene, 
 }
 
 // a mesh pair (i, j) walked by the whole warp; every lane gets the result
-__device__ __noinline__ void coop_pair(PairOut& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+static __device__ __noinline__ void coop_pair(PairOut& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
                                        const float4* __restrict__ geomB, const float4* __restrict__ cproxy, const int* __restrict__ flags,
                                        size_t ii, size_t jj, int i, int j, int lane)
 {
@@ -343,7 +343,7 @@ __device__ __noinline__ void coop_pair(PairOut& o, const SdfShape* shapes, const
     else                                         coop_sdf_sdf(o, shapes, quat, geomA, ii, jj, i, j, ci, cj, lane);
 }
 
-// Warp-collective form of test_pair: every lane passes its own partner j (or -1 for none) of the same body i. Pairs are
+// Warp-collective form of test_pair: every lane passes its own pair (i, j), j = -1 for none. Pairs are
 // tested lane-parallel as usual, except mesh pairs (extension), which are deferred and then walked one after the other by
 // all 32 lanes together.
 template <bool EXT>
@@ -357,10 +357,10 @@ __device__ __forceinline__ void test_pair_warp(PairOut& o, const View& v, int sc
         while (def) {
             const int src = __ffs(def) - 1;
             def &= def - 1;
-            const int pj = __shfl_sync(0xffffffffu, j, src);
+            const int pi = __shfl_sync(0xffffffffu, i, src), pj = __shfl_sync(0xffffffffu, j, src);
             PairOut r;
             r.cnt = 0;
-            coop_pair(r, v.sdf_shapes, v.quat, v.geomA, v.geomB, v.cproxy, v.flags, at(v, i, scene), at(v, pj, scene), i, pj, lane);
+            coop_pair(r, v.sdf_shapes, v.quat, v.geomA, v.geomB, v.cproxy, v.flags, at(v, pi, scene), at(v, pj, scene), pi, pj, lane);
             if (lane == src) o = r;
         }
     }

@@ -82,3 +82,5 @@ dt = (t1 - t0) / a.steps
 alg = 464 * p["contact_visits"] + 744 * p["joint_visits"]
 print(f"{a.scene} B={B}: {dt*1e3:.3f} ms/step  {B*nb/dt/1e6:.1f} M body-steps/s | pgs {p['solve_ms']/p['solve_launches']:.3f} ms/launch "
       f"share {p['solve_ms']/1e3/(t1-t0):.2f}  alg {alg/ (p['solve_ms']/1e3)/1e9:.1f} GB/s  visits/launch c={p['contact_visits']/p['solve_launches']:.0f} j={p['joint_visits']/p['solve_launches']:.0f}")
+st = ctx.download_state(); bad = (~np.isfinite(st['x']).all(axis=(1, 2))).sum()
+if bad: print(f"  scenes with non-finite positions: {bad} of {B}")

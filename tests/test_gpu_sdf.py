@@ -165,3 +165,62 @@ def test_mesh_body_without_an_uploaded_shape_makes_no_contacts(shape):
     ctx.step(DT, 3); ctx.sync()
     assert ctx.contact_counts()[0] == 0
     ctx.close()
+
+
+def mixed_scene(shape, n=150, seed=7):
+    """Spheres, boxes and meshes in equal parts on a lattice inside four walls on a slab (dev_measure's mixed_pile)."""
+    o = Oracle(); o.set_extensions(1)
+    sid = o.add_sdf_shape(shape)
+    side = max(2, int(round((n / 6.0) ** (1.0 / 3.0))))
+    nlay = (n + side * side - 1) // (side * side)
+    rr = np.random.default_rng(seed)
+    for i in range(n):
+        ix, iz, iy = i % side, (i // side) % side, i // (side * side)
+        pos = [(ix - 0.5 * (side - 1)) * 1.1, 1.0 + 1.15 * iy, (iz - 0.5 * (side - 1)) * 1.1]
+        q = rr.normal(size=4); q /= np.linalg.norm(q)
+        if i % 3 == 0:
+            o.add_body(1.0, SPHERE, [0.35], x=pos)
+        elif i % 3 == 1:
+            o.add_body(1.0, BOX, [0.55, 0.55, 0.55], x=pos, q=q)
+        else:
+            o.add_body(1.0, SDF, [sid], x=pos, q=q)
+    ext = side * 1.1 + 1.0
+    o.add_body(1.0, BOX, [ext + 1.0, 0.4, ext + 1.0], x=[0, 0, 0], fixed=True)
+    for sx, sz in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+        o.add_body(1.0, BOX, [0.4 if sx else ext + 1.0, nlay + 3.0, 0.4 if sz else ext + 1.0],
+                   x=[sx * 0.5 * (ext + 0.4), 0.5 * (nlay + 3.0), sz * 0.5 * (ext + 0.4)], fixed=True)
+    o.add_body(1.0, PLANE, [0, -0.2, 0, 0, 1, 0], fixed=True)
+    return o
+
+
+@pytest.mark.parametrize("pairs", ["1", "0"], ids=["pair-parallel", "row-parallel"])
+def test_mixed_scene_of_160_bodies_bit_exact(shape, pairs, monkeypatch):
+    """>= 128 bodies with the extension pairs: detect_pairs.cu (candidates -> warp narrow phase -> per-scene sort) and,
+    with SLRBS_DETECT_PAIRS=0, the row-parallel kernels; both must give the restatement's contact list bit for bit."""
+    monkeypatch.setenv("SLRBS_DETECT_PAIRS", pairs)
+    o = mixed_scene(shape)
+    oracles, done = [], 0
+    for st in [0, 50, 90, 140, 220]:
+        o.step(DT, st - done); done = st
+        oracles.append(frozen(shape, o))
+    ctx = make_ctx(oracles, shape, nc=4096)
+    assert ("k_pair" in ctx.describe()) == (pairs == "1"), ctx.describe()
+    push_state(ctx, oracles)
+    ctx.stage_prepare(); ctx.stage_detect(); ctx.sync()
+    cnt = ctx.contact_counts()
+    for s, c in enumerate(oracles):
+        c.stage_prepare(); c.stage_detect()
+        assert cnt[s] == c.n_contacts, (s, cnt[s], c.n_contacts)
+        g, r = ctx.contacts(s), c.contacts()
+        np.testing.assert_array_equal(g["body0"], r["body0"]); np.testing.assert_array_equal(g["body1"], r["body1"])
+        for k in ("p", "n", "phi"):
+            assert_bit_equal(g[k], r[k], f"scene {s} {k}")
+    assert cnt.max() > 300
+    # and a few whole steps stay together
+    ctx.step(DT, 20); ctx.sync()
+    for c in oracles:
+        c.step(DT, 20)
+    g = ctx.download_state()
+    for s, c in enumerate(oracles):
+        np.testing.assert_allclose(g["x"][s], c.state()["x"], atol=2e-2)      # 20 steps of a tumbling pile, fp32 solver
+    ctx.close()
