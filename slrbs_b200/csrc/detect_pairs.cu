@@ -25,7 +25,7 @@ __device__ __forceinline__ float4 body_bound(const View& v, size_t bi, int type,
     return make_float4(-1.f, -1.f, -1.f, 0.f);
 }
 
-__global__ void __launch_bounds__(128) k_pair_candidates(View v)
+__global__ void __launch_bounds__(128) k_pair_candidates(View v, int jchunk)
 {
     const int scene = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = v.nbodies[scene];
@@ -39,8 +39,10 @@ __global__ void __launch_bounds__(128) k_pair_candidates(View v)
     }
     // every lane visits the same j (broadcast loads); a pair is taken by the lane with i < j. The bounds are conservative
     // (1 cm of slack against the routines' own 1e-3 tolerances), so no pair that can touch is lost.
-    const int j0 = blockIdx.x * blockDim.x + 1;                   // no lane of this CTA has a partner below this
-    for (int j = j0; j < n; ++j) {
+    // blockIdx.z deals the partner range to several CTAs when the batch alone would not fill the GPU
+    const int j0 = max((int)(blockIdx.x * blockDim.x + 1), (int)blockIdx.z * jchunk);     // no lane of this CTA has a partner below this
+    const int j1 = min(n, ((int)blockIdx.z + 1) * jchunk);
+    for (int j = j0; j < j1; ++j) {
         const size_t jj = at(v, j, scene);
         const float4 cj = __ldg(&v.cproxy[jj]);
         const int fj = __ldg(&v.flags[jj]);
@@ -165,7 +167,12 @@ void init_pair_kernels()
 void launch_detect_pairs(const View& v, cudaStream_t s)
 {
     const dim3 gb((unsigned)((v.NB + 127) / 128), (unsigned)v.B), gc((unsigned)((v.pc_cap + 127) / 128), (unsigned)v.B);
-    k_pair_candidates<<<gb, 128, 0, s>>>(v);
+    // about eight CTAs per SM in total
+    const int rows = (v.NB + 127) / 128;
+    int split = (int)((148 * 8 + (long)rows * v.B - 1) / ((long)rows * v.B));
+    split = split < 1 ? 1 : (split > 32 ? 32 : split);
+    const int jchunk = (v.NB + split - 1) / split;
+    k_pair_candidates<<<dim3(gb.x, gb.y, (unsigned)((v.NB + jchunk - 1) / jchunk)), 128, 0, s>>>(v, jchunk);
     k_pair_narrow<<<gc, 128, 0, s>>>(v);
     const int sc = pair_sort_capacity(v);
     k_pair_order<<<(unsigned)v.B, ORDER_THREADS, (size_t)sc * 8, s>>>(v, sc);
