@@ -7,7 +7,8 @@
 //
 // usage: slrbs_headless <marble_box|sphere_on_box|swinging_boxes|cylinder_on_plane|car> [steps] [solverId]
 //        slrbs_headless mesh_pile <steps> <solverId> <file.obj> [n] [scale]      (extension: SDF-mesh bodies)
-// prints "i x y z qx qy qz qw" for every body after the last step, then "contacts N".
+// prints "i x y z qx qy qz qw" for every body after the last step, then "contacts N"; with SLRBS_DUMP=<file> also writes
+// every body's pose after every step (for offline rendering).
 #include "rigidbody/RigidBodySystem.h"
 #include "rigidbody/RigidBody.h"
 #include "rigidbody/Scenarios.h"
@@ -37,7 +38,17 @@ int main(int argc, char* argv[])
     sys.solverIter = 10;
     const float dt = 0.01f;                                      // SimViewer.cpp:113
     const auto t0 = std::chrono::steady_clock::now();
-    for (int i = 0; i < steps; ++i) sys.step(dt);
+    // state dump for offline rendering: SLRBS_DUMP=<file> writes "step body x y z qx qy qz qw" after every step
+    std::FILE* dump = std::getenv("SLRBS_DUMP") ? std::fopen(std::getenv("SLRBS_DUMP"), "w") : nullptr;
+    for (int i = 0; i < steps; ++i) {
+        sys.step(dt);
+        if (dump) {
+            int k = 0;
+            for (RigidBody* b : sys.getBodies())
+                std::fprintf(dump, "%d %d %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", i, k++, b->x[0], b->x[1], b->x[2], b->q.x(), b->q.y(), b->q.z(), b->q.w());
+        }
+    }
+    if (dump) std::fclose(dump);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     int i = 0;
     for (RigidBody* b : sys.getBodies())

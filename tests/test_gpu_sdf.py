@@ -114,7 +114,11 @@ def test_mesh_pile_through_the_headless_program(tmp_path):
     obj = str(tmp_path / "blob.obj")
     write_obj(obj, v, f)
     n, steps = 3, 120
-    out = subprocess.run([exe, "mesh_pile", str(steps), "0", obj, str(n)], capture_output=True, text=True, check=True).stdout.split("\n")
+    dump = str(tmp_path / "frames.txt")
+    out = subprocess.run([exe, "mesh_pile", str(steps), "0", obj, str(n)], capture_output=True, text=True, check=True,
+                         env=dict(os.environ, SLRBS_DUMP=dump)).stdout.split("\n")
+    frames = np.loadtxt(dump)
+    assert frames.shape == (steps * (n + 1), 9) and frames[-1, 0] == steps - 1
     rows = np.array([[float(t) for t in ln.split()[1:]] for ln in out if ln and ln[0].isdigit()])
     assert rows.shape == (n + 1, 7) and np.isfinite(rows).all()
     # the same scene in the restatement: vertices as the OBJ text holds them, re-centred on their bounding box
@@ -131,6 +135,7 @@ def test_mesh_pile_through_the_headless_program(tmp_path):
     o.add_body(1.0, PLANE, [0, 0, 0, 0, 1, 0], fixed=True)
     o.step(DT, steps)
     np.testing.assert_allclose(rows[:, :3], o.state()["x"], atol=2e-2)
+    np.testing.assert_array_equal(frames[-(n + 1):, 2:5].astype(np.float32), rows[:, :3].astype(np.float32))      # last frame = final state
     assert int([ln for ln in out if ln.startswith("contacts")][0].split()[1]) > 0
 
 
