@@ -57,6 +57,43 @@ WORKLOADS = {
 }
 
 
+SOLVER_SOURCES = ("pgs_split.cu", "pgs_level.cu", "pgs_level.cuh", "pgs_math.cuh", "layout.cuh", "kernels.cu")
+
+
+def solver_source_hash():
+    """Hash of the sources that decide the solver kernels' memory traffic: a measured-DRAM record in
+    profiles/pgs_traffic.json only counts while it was taken on the same kernels."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in SOLVER_SOURCES:
+        with open(os.path.join(ROOT, "slrbs_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def common_config(workload, B, nb, nj):
+    """The workload description BOTH arms print (identical keys and values)."""
+    scene, abc, nc, _, settle, jitter = WORKLOADS[workload]
+    return {"workload": f"{workload} x {B} scenes/GPU", "scene": scene, "scene_args": list(abc), "scenes_per_gpu": B,
+            "bodies_per_scene": nb, "joints_per_scene": nj, "dt": DT, "solver": "Box-PGS", "solver_iters": SOLVER_ITERS, "mu": MU,
+            "settle_steps": settle, "jitter": jitter,
+            "l2": "no flush: the per-step working set (constraint rows of all scenes) is larger than the 126 MB L2"
+                  if workload in ("marble_box", "marble_box_1k") else "no flush: every step re-detects and rebuilds all rows; inputs of a step are the previous step's outputs"}
+
+
+def bind_rank_to_cores(local, world):
+    """One contiguous share of the host's cores per rank (its own threads, its pinned buffers' first touch): 8 ranks of
+    one box otherwise float over the same cores. Uses the GPU's local CPU list when the platform exposes one."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        share = max(1, len(cpus) // max(world, 1))
+        mine = cpus[local * share:(local + 1) * share] or cpus
+        os.sched_setaffinity(0, mine)
+        return f"cores {mine[0]}-{mine[-1]}"
+    except Exception as e:       # not fatal: binding is an optimisation
+        return f"unbound ({e})"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -137,6 +174,7 @@ def run_ours(args):
 
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    binding = bind_rank_to_cores(local, world)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -160,8 +198,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timed region ------------------------------------------------------------
-    ctx.profile_enable(True); ctx.profile_read(True)
+    # ---- device-resident timed region (CUDA-graph replay, the path slrbs_step takes for a caller) ------
+    ctx.profile_read(True)                                 # zero the launch counter
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     ctx.timer_start()
@@ -169,6 +207,15 @@ def run_ours(args):
     ms = ctx.timer_stop()
     barrier()
     clocks = sampler.stop() if sampler else None
+    ctx.sync()
+    launches_timed = int(ctx.profile_read(True)["total_launches"])       # kernels launched (graph nodes replayed) in the timed region
+    # ---- separate profiled pass: CUDA events around every solver launch + visit counters (profiling replaces the graph by
+    # plain launches, so it is kept out of the headline region) -------------------------------------
+    psteps = max(3, min(args.steps, 10))
+    ctx.profile_enable(True); ctx.profile_read(True)
+    ctx.timer_start()
+    ctx.step(DT, psteps)
+    prof_ms = ctx.timer_stop()
     prof = ctx.profile_read(True)
     ctx.profile_enable(False)
     ctx.sync()
@@ -178,10 +225,23 @@ def run_ours(args):
     # The scenes are split over E2E_CHUNKS contexts (one stream each) so that one chunk's PCIe transfers overlap with
     # another chunk's step: every step still uploads x,q,v,omega of EVERY body from pinned host memory, advances every
     # scene once and downloads every body's state again before the step counts as done.
-    hx = torch.empty((B, nb, 3), dtype=torch.float32).pin_memory(); hq = torch.empty((B, nb, 4), dtype=torch.float32).pin_memory()
-    hv = torch.empty((B, nb, 3), dtype=torch.float32).pin_memory(); hw = torch.empty((B, nb, 3), dtype=torch.float32).pin_memory()
+    # pinned buffers: cudaHostAlloc by this rank after its core binding, first touched here (fill_) by the bound thread
+    hx, hq, hv, hw = [torch.empty((B, nb, k), dtype=torch.float32, pin_memory=True).fill_(0) for k in (3, 4, 3, 3)]
     ptr = [t.data_ptr() for t in (hx, hq, hv, hw)]
     ctx.download_state_raw(B, nb, *ptr)
+    # what the host link gives this rank while ALL ranks copy at once (explains the end-to-end number at N > 1)
+    pcie = {}
+    dbuf = torch.empty_like(hx, device="cuda")
+    for name, (dst, src) in (("h2d", (dbuf, hx)), ("d2h", (hx, dbuf))):
+        dst.copy_(src, non_blocking=True); barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dst.copy_(src, non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        pcie[name] = 5 * hx.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    ctx.download_state_raw(B, nb, *ptr)
+    del dbuf
     nch = E2E_CHUNKS if B % E2E_CHUNKS == 0 and B // E2E_CHUNKS >= 64 else 1
     if nch == 1:
         chunks = [(ctx, 0, B)]
@@ -226,7 +286,7 @@ def run_ours(args):
             c.close()
 
     from slrbs_b200 import sharding
-    ms, e2e_ms = sharding.reduce_over_ranks([ms, e2e_ms], "max")           # device time: max over ranks
+    ms, e2e_ms, h2d_inv, d2h_inv = sharding.reduce_over_ranks([ms, e2e_ms, 1.0 / pcie["h2d"], 1.0 / pcie["d2h"]], "max")   # device time: max over ranks
     agg = [prof["solve_ms"], float(prof["solve_launches"]), float(prof["contact_visits"]), float(prof["joint_visits"]),
            float(prof["total_launches"])]                                    # roofline / launches: rank 0's GPU
     if rank != 0:
@@ -239,37 +299,48 @@ def run_ours(args):
     solve_ms, launches = float(agg[0]), max(float(agg[1]), 1.0)
     alg_bytes = BYTES_PER_CONTACT_VISIT * float(agg[2]) + BYTES_PER_HINGE_VISIT * float(agg[3])
     achieved = alg_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
-    traffic = None
+    # measured DRAM bytes of the solver kernel (one `ncu --set full` capture, profiles/pgs_traffic.json): used only while the
+    # record was taken on these very kernel sources, workload and batch
+    traffic, traffic_note = None, "no ncu capture recorded for this workload / batch"
     tp = os.path.join(ROOT, "profiles", "pgs_traffic.json")
     if os.path.exists(tp):
         try:
-            tj = json.load(open(tp))
-            for rec in (tj if isinstance(tj, list) else [tj]):
+            for rec in json.load(open(tp)):
                 if rec.get("workload") == args.workload and rec.get("scenes") == B:
-                    traffic = rec.get("dram_bytes_per_launch")
+                    if rec.get("source_hash") == solver_source_hash():
+                        traffic, traffic_note = rec.get("dram_bytes_per_launch"), rec.get("source")
+                    else:
+                        traffic_note = "stale: the recorded capture was taken on different solver sources"
         except Exception:
             pass
+    kernel = "k_pgs_sp" if "k_pgs_sp" in variants else ("k_pgs_lv" if "k_pgs_lv" in variants else "k_pgs")
+    cfg = common_config(args.workload, B, nb, nj)
     out = {
         "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload} x {B} scenes/GPU (Scenarios.h scene, {nb} bodies, {nj} joints, "
-                               f"{contacts_mean:.0f} contacts/scene after a {settle}-step settle)",
-                   "scenes_per_gpu": B, "bodies_per_scene": nb, "dt": DT, "solver": "Box-PGS", "solver_iters": SOLVER_ITERS,
-                   "kernels": variants,
-                   "mu": MU, "sharding": f"scene index, {world} ranks, no data-path collective",
-                   "l2": "per-step working set (constraint rows) is larger than the 126 MB L2, no flush needed"},
-        "roofline": {"kernel": "k_pgs_lv" if "k_pgs_lv" in variants else "k_pgs", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+        "config": cfg,
+        "details": {"kernels": variants, "contacts_per_scene": round(contacts_mean, 1),
+                    "sharding": f"scene index, {world} ranks, no data-path collective", "host_binding": binding,
+                    "timed_region": "CUDA-graph replay of slrbs_step; roofline from a separate profiled pass of "
+                                    f"{psteps} steps ({prof_ms / psteps:.3f} ms/step with per-launch events)"},
+        "roofline": {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_note,
+                     # measured DRAM bytes / event time / peak: what the memory system actually moved (the contract figure
+                     # `frac` counts 464 B per contact visit, more than a row record holds)
+                     "frac_dram": (traffic / (solve_ms / launches * 1e-3) / 1e9 / peak) if traffic else None,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes / launches, "ms_per_launch": solve_ms / launches,
                      # SURVEY 8(d), informational: the same visits at 244 B per contact visit (rows recomputed from compact
                      # data instead of streamed); the fraction above uses the 464 B contract figure
                      "achieved_at_244B_per_contact_visit": ((244.0 * float(agg[2]) + BYTES_PER_HINGE_VISIT * float(agg[3])) / (solve_ms * 1e-3) / 1e9
                                                            if solve_ms > 0 else 0.0),
-                     "share_of_step": solve_ms / ms if ms else None},
+                     "share_of_step": solve_ms / prof_ms if prof_ms else None},
         "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": int(B * nb * 13 * 4),
-                "d2h_bytes_per_step": int(B * nb * 13 * 4), "steps": e2e_steps, "contexts": len(chunks)},
-        "gpu_launches": int(float(agg[4])),
+                "d2h_bytes_per_step": int(B * nb * 13 * 4), "steps": e2e_steps, "contexts": len(chunks),
+                "payload": "x,q,v,omega of every body up and down every step (13 floats each way)",
+                "host_link_gbs_per_rank_all_ranks_copying": {"h2d": 1.0 / h2d_inv, "d2h": 1.0 / d2h_inv}},
+        "gpu_launches": launches_timed,
         "clocks": clocks,
     }
     if world == 1:
@@ -364,6 +435,12 @@ def run_reference(args):
         res = list(ex.map(_ref_worker, [(workload, 1234 + i, settle, total) for i in range(cores)]))
         wall = time.perf_counter() - t0
     nb = res[0][1]
+    # the library the workers timed, loaded once in this process too (the driver's loaded-library record looks at the parent)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import lib, ref_available
+    loaded = lib("ref" if res[0][2] == "reference" and ref_available() else "oracle")
+    nj = _oracle_system(workload, 1234, 0)[0].n_joints
+    del loaded
     tmax = max(r[0] for r in res)
     value = cores * nb * total / tmax
     B = args.scenes or WORKLOADS[workload][3]
@@ -371,8 +448,7 @@ def run_reference(args):
         "impl": "reference", "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tmax * 1e3 / (args.steps + args.warmup),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{workload} x {B} scenes/GPU", "scenes_per_gpu": B, "bodies_per_scene": nb, "dt": DT,
-                   "solver": "Box-PGS", "solver_iters": SOLVER_ITERS, "mu": MU},
+        "config": common_config(workload, B, nb, nj),
         "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": res[0][2],
                          "sample": f"{cores} independent scenes of {workload}, one process per logical core ("
                                    + ("reference sources + Eigen API shim, oracle/_ref" if res[0][2] == "reference" else "C restatement")

@@ -35,8 +35,10 @@ struct slrbs_ctx {
     float mu = 0.8f;
     int solver_id = 0, solver_iters = 10, collisions = 1;
     int level_group = 8;                        // lanes per scene of the level-scheduled solver
+    bool level_split = false;                   // two lanes per contact row (pgs_split.cu) for the wide-scene groups
     int broadphase = -1;                        // -1 auto, 0 all pairs, 1 hashed grid (SLRBS_BROADPHASE)
     bool joints_dirty = true;                   // joint levels must be recomputed (bodies / joints uploaded)
+    std::vector<int> h_nbodies;                 // host mirror of the body counts set through slrbs_upload_bodies (0 = unknown)
     std::vector<void*> allocs;
     char* stage = nullptr; size_t stage_cap = 0, stage_off = 0;
     int* h_flag = nullptr;                      // pinned copy of the overflow flag
@@ -159,7 +161,7 @@ int solve_launch(slrbs_ctx* c, float dt)
     int sweeps = c->solver_iters;
     if (c->solver_id == 3) { launches = 1 + launch_bpp(c->v, c->solver_iters, c->mu, c->stream); sweeps = 0; }
     else if (c->solver_id != 0) { launch_krylov(c->v, c->solver_id, c->solver_iters, c->stream); sweeps = 0; launches = 2; }
-    if (c->v.level_mode) launch_pgs_level(c->v, dt, sweeps, c->mu, c->level_group, c->stream);
+    if (c->v.level_mode) launch_pgs_level(c->v, dt, sweeps, c->mu, c->level_group, c->level_split, c->stream);
     else launch_pgs(c->v, dt, sweeps, c->mu, c->stream);
     if (c->profiling) { CU(cudaEventRecord(e1, c->stream)); c->solve_launches++; }
     return check_launch(c, launches);
@@ -176,7 +178,10 @@ int slrbs_describe(slrbs_ctx* c, char* buf, int buf_len)
 {
     if (!c || !buf || buf_len <= 0) return fail(SLRBS_E_ARG, "slrbs_describe: bad argument");
     char tmp[256];
-    if (c->v.level_mode)
+    if (c->v.level_mode && c->level_split)
+        std::snprintf(tmp, sizeof tmp, "solver=k_pgs_sp<ROWS=%d> (level-scheduled, 2 lanes/contact row, %d threads/scene) detect=%s graph=%d",
+                      c->level_group, 2 * c->level_group, detect_variant(c->v, c->broadphase), c->use_graph);
+    else if (c->v.level_mode)
         std::snprintf(tmp, sizeof tmp, "solver=k_pgs_lv<G=%d> (level-scheduled, %d lanes/scene) detect=%s graph=%d", c->level_group,
                       c->level_group, detect_variant(c->v, c->broadphase), c->use_graph);
     else
@@ -223,6 +228,7 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
         else v.level_mode = (n_scenes <= 8192 && fits) ? 1 : 0;
         const char* g = std::getenv("SLRBS_LEVEL_GROUP");
         c->level_group = level_group_size(v, g ? std::atoi(g) : 0);
+        c->level_split = v.level_mode && level_split_wanted(v, c->level_group);
         const char* bp = std::getenv("SLRBS_BROADPHASE");
         if (bp) c->broadphase = std::atoi(bp) ? 1 : 0;
     }
@@ -230,7 +236,7 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     const size_t bpad = ((size_t)v.B + 31) / 32 * 32;      // row records are blocked 32 scenes at a time
     int r = 0;
 #define A(p, n) if ((r = dalloc(c, &p, n))) { slrbs_destroy(c); return r; }
-    A(v.nbodies, v.B) A(v.njoints, v.B) A(v.ncontacts, v.B) A(v.overflow, 1) A(v.visit_counters, 2)
+    A(v.nbodies, v.B) A(v.njoints, v.B) A(v.ncontacts, v.B) A(v.overflow, 1) A(v.visit_counters, 2) A(v.ext_mode, v.B)
     A(v.pos, nb) A(v.quat, nb) A(v.vel, nb) A(v.omg, nb) A(v.flags, nb) A(v.geomA, nb) A(v.geomB, nb)
     A(v.ibody, 9 * nb) A(v.ibodyinv, 9 * nb) A(v.cproxy, nb) A(v.bext, nb) A(v.force, nb) A(v.torque, nb)
     A(v.extf, nb) A(v.extt, nb) A(v.Iw, 9 * nb) A(v.Iinvw, 9 * nb) A(v.wl, nb) A(v.wa, nb) A(v.brec, 8 * nb)
@@ -355,8 +361,12 @@ int slrbs_upload_bodies(slrbs_ctx* c, int scene0, int ns, int n, const int32_t* 
     if (!range_ok(c, scene0, ns) || n <= 0 || n > c->v.NB) return fail(SLRBS_E_ARG, "slrbs_upload_bodies: bad range");
     if (!x3 || !q4 || !v3 || !w3 || !mass || !ibody9 || !ibodyinv9 || !fixed || !geom_type || !geom6)
         return fail(SLRBS_E_ARG, "slrbs_upload_bodies: all body arrays are required");
-    CU(cudaSetDevice(c->device));
     const size_t m = (size_t)ns * n;
+    if (counts) for (int k = 0; k < ns; ++k)
+        if (counts[k] < 0 || counts[k] > n) return fail(SLRBS_E_ARG, "slrbs_upload_bodies: counts[] must lie in 0..n_bodies");
+    for (size_t k = 0; k < m; ++k)
+        if (geom_type[k] < GEOM_SPHERE || geom_type[k] > GEOM_SDF) return fail(SLRBS_E_ARG, "slrbs_upload_bodies: geom_type must be 0..4");
+    CU(cudaSetDevice(c->device));
     int r = stage_reserve(c, pad256(m * 4) * (3 + 4 + 3 + 3 + 1 + 9 + 9 + 1 + 1 + 6) + pad256((size_t)ns * 4) + 4096);
     if (r) return r;
     BodyStage st{};
@@ -369,6 +379,8 @@ int slrbs_upload_bodies(slrbs_ctx* c, int scene0, int ns, int n, const int32_t* 
         return r;
     launch_upload_bodies(c->v, scene0, ns, n, dcounts, st, c->stream);
     if ((r = check_launch(c))) return r;
+    if (c->h_nbodies.empty()) c->h_nbodies.assign((size_t)c->v.B, 0);
+    for (int k = 0; k < ns; ++k) c->h_nbodies[scene0 + k] = counts ? counts[k] : n;
     c->joints_dirty = true;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -381,15 +393,25 @@ int slrbs_upload_joints(slrbs_ctx* c, int scene0, int ns, int n, const int32_t* 
     if (!range_ok(c, scene0, ns) || n < 0 || n > c->v.NJ) return fail(SLRBS_E_ARG, "slrbs_upload_joints: bad range");
     CU(cudaSetDevice(c->device));
     if (n == 0) {
+        // removing the joints of a scene range: the level tables (njlev, jlev_end, jpos) are what k_pgs_lv walks, so they
+        // must be rebuilt, and the removed joints' impulses must not survive into a later upload
         CU(cudaMemsetAsync(c->v.njoints + scene0, 0, sizeof(int) * ns, c->stream));
+        if (c->v.NJ > 0) { launch_clear_joint_lambda(c->v, scene0, ns, c->stream); int r0 = check_launch(c); if (r0) return r0; }
+        c->joints_dirty = true;
+        CU(cudaStreamSynchronize(c->stream));
         return 0;
     }
     if (!type || !body0 || !body1 || !r0 || !r1) return fail(SLRBS_E_ARG, "slrbs_upload_joints: type/body/r arrays are required");
     const size_t m = (size_t)ns * n;
+    if (counts) for (int k = 0; k < ns; ++k)
+        if (counts[k] < 0 || counts[k] > n) return fail(SLRBS_E_ARG, "slrbs_upload_joints: counts[] must lie in 0..n_joints");
     for (size_t i = 0; i < m; ++i) {
+        const int sc = scene0 + (int)(i / (size_t)n);
+        if (counts && (int)(i % (size_t)n) >= counts[sc - scene0]) continue;                             // padding entries are never read
         if (type[i] != 1 && type[i] != 2) return fail(SLRBS_E_ARG, "slrbs_upload_joints: type must be 1 (spherical) or 2 (hinge)");
-        if (body0[i] < 0 || body0[i] >= c->v.NB || body1[i] < 0 || body1[i] >= c->v.NB)
-            return fail(SLRBS_E_ARG, "slrbs_upload_joints: body index out of range");
+        const int lim = (!c->h_nbodies.empty() && c->h_nbodies[sc] > 0) ? c->h_nbodies[sc] : c->v.NB;   // the scene's own body count when known
+        if (body0[i] < 0 || body0[i] >= lim || body1[i] < 0 || body1[i] >= lim)
+            return fail(SLRBS_E_ARG, "slrbs_upload_joints: body index out of range for its scene");
     }
     int r = stage_reserve(c, pad256(m * 4) * (3 + 3 + 4 + 3 + 4) + pad256((size_t)ns * 4) + 4096);
     if (r) return r;
@@ -479,9 +501,10 @@ int slrbs_set_external_forces(slrbs_ctx* c, int scene0, int ns, int n, const flo
     if (r) return r;
     const float *df = nullptr, *dt = nullptr;
     if ((r = stage_in(c, f3, 3 * m, &df)) || (r = stage_in(c, tau3, 3 * m, &dt))) return r;
-    launch_set_ext(c->v, scene0, ns, n, df, dt, c->stream);
+    // the mode is kept per scene (View::ext_mode): a call on a sub-range leaves the other scenes as they were
+    launch_set_ext(c->v, scene0, ns, n, df, dt, (f3 || tau3) ? 1 + mode : 0, c->stream);
     if ((r = check_launch(c))) return r;
-    if (f3 || tau3) c->v.has_ext = 1 + mode;
+    if (f3 || tau3) c->v.has_ext = 1;
     else if (scene0 == 0 && ns == c->v.B) c->v.has_ext = 0;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -578,24 +601,26 @@ int slrbs_sync(slrbs_ctx* c)
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(c->h_flag, c->v.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (*c->h_flag & 1) return fail(SLRBS_E_CAPACITY, "a scene produced more contacts than max_contacts; extra contacts were dropped");
-    if (*c->h_flag & 4) {
+    const int flags = *c->h_flag;
+    if (!flags) return 0;
+    // every cause is reported once per occurrence: contacts are re-detected each step, so a transient overflow must not
+    // poison the context, and the caller can tell the causes apart (only the first is cured by a larger max_contacts)
+    std::string pairs_msg;
+    if (flags & 4) {
         std::vector<int> cand(c->v.B), hits(c->v.B);
         CU(cudaMemcpy(cand.data(), c->v.pc_count, sizeof(int) * c->v.B, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(hits.data(), c->v.pc_hits, sizeof(int) * c->v.B, cudaMemcpyDeviceToHost));
         int mc = 0, mh = 0;
         for (int k = 0; k < c->v.B; ++k) { mc = std::max(mc, cand[k]); mh = std::max(mh, hits[k]); }
-        return fail(SLRBS_E_CAPACITY, "a scene produced more candidate or touching pairs than the pair-parallel detection holds (last step: " +
+        pairs_msg = "a scene produced more candidate or touching pairs than the pair-parallel detection holds (last step: " +
                     std::to_string(mc) + " candidates of " + std::to_string(c->v.pc_cap) + ", " + std::to_string(mh) + " touching pairs of " +
-                    std::to_string(std::min(c->v.NC, 16384)) + "); contacts were dropped");
+                    std::to_string(std::min(c->v.NC, 16384)) + "); contacts were dropped";
     }
-    if (*c->h_flag & 2) {
-        // reported once (the contact-capacity bit stays set: the contact lists of that context are truncated for good)
-        static const int zero = 0;
-        CU(cudaMemcpyAsync(c->v.overflow, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        return fail(SLRBS_E_CAPACITY, "a scene has more constraint rows than the pivoting solver holds (solver_id 3: 288 scalar rows); its impulses were left at zero");
-    }
+    CU(cudaMemsetAsync(c->v.overflow, 0, sizeof(int), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (flags & 1) return fail(SLRBS_E_CAPACITY, "a scene produced more contacts than max_contacts; extra contacts were dropped");
+    if (flags & 4) return fail(SLRBS_E_CAPACITY_PAIRS, pairs_msg);
+    if (flags & 2) return fail(SLRBS_E_CAPACITY_ROWS, "a scene has more constraint rows than the pivoting solver holds (solver_id 3); its impulses were left at zero");
     return 0;
 }
 

@@ -43,7 +43,11 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)v.NB * v.B) return;
     const int scene = (int)(tid % v.B), slot = (int)(tid / v.B);
-    if (slot == 0) { v.ncontacts[scene] = 0; if (v.pc_count) { v.pc_count[scene] = 0; v.pc_hits[scene] = 0; } }   // CollisionDetect::clear, RigidBodySystem.cpp:75
+    if (slot == 0) {                                             // CollisionDetect::clear, RigidBodySystem.cpp:75
+        v.ncontacts[scene] = 0;
+        if (v.nclev) v.nclev[scene] = 0;                         // the level kernel walks levels, not counts: no stale rows when detection is skipped
+        if (v.pc_count) { v.pc_count[scene] = 0; v.pc_hits[scene] = 0; }
+    }
     if (slot >= v.nbodies[scene]) return;
     const size_t i = at(v, slot, scene);
     const float4 px = v.pos[i];
@@ -51,10 +55,11 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
     // b->f = b->mass * Vector3f(0, -9.81, 0); tau = 0  (RigidBodySystem.cpp:60-61)
     V3 f = mass * mk3(0.f, -9.81f, 0.f);
     V3 tau = mk3(0.f, 0.f, 0.f);
-    if (v.has_ext == 1) {                                        // pre-step callback contribution (:70-73)
+    const int ext = v.has_ext ? v.ext_mode[scene] : 0;           // per scene: a sub-range call must not change the other scenes
+    if (ext == 1) {                                              // pre-step callback contribution (:70-73)
         f = f + mk3(v.extf[i]);
         tau = tau + mk3(v.extt[i]);
-    } else if (v.has_ext == 2) {                                 // callback result given absolutely
+    } else if (ext == 2) {                                       // callback result given absolutely
         f = mk3(v.extf[i]);
         tau = mk3(v.extt[i]);
     }
@@ -982,6 +987,15 @@ __global__ void k_upload_joints(View v, int scene0, int ns, int n, const int* co
     v.jlam4[j] = 0.f;
 }
 
+__global__ void k_clear_joint_lambda(View v, int scene0, int ns)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)ns * v.NJ) return;
+    const size_t j = at(v, (int)(tid / ns), scene0 + (int)(tid % ns));
+    v.jlam[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.jlam4[j] = 0.f;
+}
+
 __global__ void k_joint_lambda(View v, int scene0, int ns, int n, float* lam5, int upload)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -998,11 +1012,12 @@ __global__ void k_joint_lambda(View v, int scene0, int ns, int n, float* lam5, i
     }
 }
 
-__global__ void k_set_ext(View v, int scene0, int ns, int n, const float* f3, const float* t3)
+__global__ void k_set_ext(View v, int scene0, int ns, int n, const float* f3, const float* t3, int mode)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)ns * n) return;
     const int ls = (int)(tid % ns), slot = (int)(tid / ns);
+    if (slot == 0) v.ext_mode[scene0 + ls] = mode;
     const size_t h = (size_t)ls * n + slot;
     const size_t i = at(v, slot, scene0 + ls);
     v.extf[i] = f3 ? make_float4(f3[3 * h], f3[3 * h + 1], f3[3 * h + 2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1015,7 +1030,7 @@ __global__ void k_snapshot(View v, int scene0, int ns, int restore)
     if (tid >= (size_t)ns * v.NB) return;
     const int ls = (int)(tid % ns), slot = (int)(tid / ns);
     const int scene = scene0 + ls;
-    if (restore && slot == 0) v.ncontacts[scene] = 0;            // RigidBodyState.cpp:71
+    if (restore && slot == 0) { v.ncontacts[scene] = 0; if (v.nclev) v.nclev[scene] = 0; }   // RigidBodyState.cpp:71
     if (slot >= v.nbodies[scene]) return;
     const size_t i = at(v, slot, scene);
     if (restore) {
@@ -1185,10 +1200,12 @@ void launch_download_state(const View& v, int scene0, int ns, int n, const BodyS
 { k_download_state<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, st); }
 void launch_upload_joints(const View& v, int scene0, int ns, int n, const int* counts, const JointStage& st, cudaStream_t s)
 { k_upload_joints<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, counts, st); }
+void launch_clear_joint_lambda(const View& v, int scene0, int ns, cudaStream_t s)
+{ k_clear_joint_lambda<<<blocks_for((size_t)ns * v.NJ, 256), 256, 0, s>>>(v, scene0, ns); }
 void launch_joint_lambda(const View& v, int scene0, int ns, int n, float* lam5, int upload, cudaStream_t s)
 { k_joint_lambda<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, lam5, upload); }
-void launch_set_ext(const View& v, int scene0, int ns, int n, const float* f3, const float* t3, cudaStream_t s)
-{ k_set_ext<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, f3, t3); }
+void launch_set_ext(const View& v, int scene0, int ns, int n, const float* f3, const float* t3, int mode, cudaStream_t s)
+{ k_set_ext<<<blocks_for((size_t)ns * n, 256), 256, 0, s>>>(v, scene0, ns, n, f3, t3, mode); }
 void launch_snapshot(const View& v, int scene0, int ns, int restore, cudaStream_t s)
 { k_snapshot<<<blocks_for((size_t)ns * v.NB, 256), 256, 0, s>>>(v, scene0, ns, restore); }
 void launch_halo_copy(const View& v, int n, const int* src, const int* dst, cudaStream_t s)

@@ -49,16 +49,21 @@ void launch_build_sdf(const float* verts, int nt, const int* tris, int nx, int n
 void launch_joint_levels(const View& v, cudaStream_t s);
 void launch_contact_levels(const View& v, cudaStream_t s);
 size_t contact_levels_smem(int NB, int NC);
-void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, cudaStream_t s);
+void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, bool split, cudaStream_t s);
 int  level_group_size(const View& v, int requested);
+// pgs_split.cu: the level schedule with two lanes per contact row (one per body side); rows = 32 or 64 rows per level step
+void init_split_kernels();
+void launch_pgs_split(const View& v, float dt, int iters, float mu, int rows, cudaStream_t s);
+bool level_split_wanted(const View& v, int group);
 bool level_mode_fits(int max_bodies);
 void launch_integrate(const View& v, float dt, cudaStream_t s);
 
 void launch_upload_bodies(const View& v, int scene0, int ns, int n, const int* counts, const BodyStage& st, cudaStream_t s);
 void launch_download_state(const View& v, int scene0, int ns, int n, const BodyStage& st, cudaStream_t s);
 void launch_upload_joints(const View& v, int scene0, int ns, int n, const int* counts, const JointStage& st, cudaStream_t s);
+void launch_clear_joint_lambda(const View& v, int scene0, int ns, cudaStream_t s);
 void launch_joint_lambda(const View& v, int scene0, int ns, int n, float* lam5, int upload, cudaStream_t s);
-void launch_set_ext(const View& v, int scene0, int ns, int n, const float* f3, const float* t3, cudaStream_t s);
+void launch_set_ext(const View& v, int scene0, int ns, int n, const float* f3, const float* t3, int mode, cudaStream_t s);
 void launch_snapshot(const View& v, int scene0, int ns, int restore, cudaStream_t s);
 void launch_halo_copy(const View& v, int n, const int* src, const int* dst, cudaStream_t s);
 void launch_halo_pack(const View& v, int n, const int* idx, float* buf, cudaStream_t s);

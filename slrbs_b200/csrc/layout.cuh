@@ -78,7 +78,8 @@ struct View {
     float4 *force;      // f | -
     float4 *torque;     // tau | -
     float4 *extf, *extt;
-    int     has_ext;
+    int     has_ext;    // 0 until slrbs_set_external_forces is first called (k_prepare then skips ext_mode)
+    int    *ext_mode;   // [B] 0 none, 1 additive (pre-step callback contribution), 2 absolute
     float  *Iw;         // [9][NB][B] world inertia
     float  *Iinvw;      // [9][NB][B]
     float4 *wl, *wa;    // PGS body accumulators sum(J^T lambda); after solve: fc, tauc

@@ -22,6 +22,7 @@
 #endif
 #include <cstdlib>
 #include "pgs_math.cuh"
+#include "pgs_level.cuh"
 
 namespace slrbs {
 
@@ -183,46 +184,6 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
 // than a warp (block barrier between levels instead of a warp barrier).
 template <int G> struct LvCfg { enum { THREADS = G < 32 ? 32 : G, SPC = THREADS / G }; };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
-}
-#ifndef LV_BULK_PREFETCH
-#define LV_BULK_PREFETCH 1
-#endif
-
-// shared-memory accumulators of one scene, per body (linear xyz, angular xyz): either two padded float4 (32 B, two
-// 16 B accesses: best when shared memory is plentiful) or three float2 (24 B: a 1000-body scene then needs 24 KB and 9
-// scenes fit an SM instead of 7; chosen when the padded layout would cap the warps per SM)
-template <bool W24> struct Acc;
-template <> struct Acc<false> {
-    enum { FLOATS = 8 };
-    static __device__ __forceinline__ void ld(const float* w, int body, V3& l, V3& a)
-    {
-        const float4* p = reinterpret_cast<const float4*>(w) + 2 * body;
-        l = mk3(p[0]); a = mk3(p[1]);
-    }
-    static __device__ __forceinline__ void st(float* w, int body, const V3& l, const V3& a)
-    {
-        float4* p = reinterpret_cast<float4*>(w) + 2 * body;
-        p[0] = mk4(l, 0.f); p[1] = mk4(a, 0.f);
-    }
-};
-template <> struct Acc<true> {
-    enum { FLOATS = 6 };
-    static __device__ __forceinline__ void ld(const float* w, int body, V3& l, V3& a)
-    {
-        const float2* p = reinterpret_cast<const float2*>(w) + 3 * body;
-        const float2 p0 = p[0], p1 = p[1], p2 = p[2];
-        l = mk3(p0.x, p0.y, p1.x); a = mk3(p1.y, p2.x, p2.y);
-    }
-    static __device__ __forceinline__ void st(float* w, int body, const V3& l, const V3& a)
-    {
-        float2* p = reinterpret_cast<float2*>(w) + 3 * body;
-        p[0] = make_float2(l.x, l.y); p[1] = make_float2(l.z, a.x); p[2] = make_float2(a.y, a.z);
-    }
-};
 #define ld_w Acc<W24>::ld
 #define st_w Acc<W24>::st
 
@@ -248,7 +209,7 @@ __global__ void __launch_bounds__(LvCfg<G>::THREADS, MINB) k_pgs_lv(View v, floa
     if (scene >= v.B) return;                                    // whole groups (for G > 32: whole CTAs) leave together
     float* w = smem_w + (size_t)grp * v.NB * Acc<W24>::FLOATS;
     const int nb = v.nbodies[scene], nj = v.njoints[scene], nc = v.ncontacts[scene];
-    const int njl = v.njlev[scene], ncl = v.nclev[scene];
+    const int njl = nj > 0 ? v.njlev[scene] : 0, ncl = nc > 0 ? v.nclev[scene] : 0;   // no rows, no levels (stale tables are never walked)
 
     for (int i = gl; i < Acc<W24>::FLOATS * nb; i += G) w[i] = 0.f;
     group_sync<G>(mask);
@@ -465,6 +426,7 @@ static void init_lv()
 void init_level_kernels()
 {
     init_lv<4>(); init_lv<8>(); init_lv<16>(); init_lv<32>(); init_lv<64>(); init_lv<128>();
+    init_split_kernels();
     cudaFuncSetAttribute(k_contact_levels<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_contact_levels<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
@@ -480,8 +442,18 @@ int level_group_size(const View& v, int requested)
 
 bool level_mode_fits(int max_bodies) { return (size_t)max_bodies * 24 <= 200 * 1024; }
 
-void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, cudaStream_t s)
+// The side-split kernel (pgs_split.cu) serves the wide scenes that used to get one or two warps of one lane per row
+// (G = 32 / 64): twice the warps on the same shared memory. SLRBS_PGS_SPLIT=0 keeps the one-lane-per-row kernels (A/B).
+bool level_split_wanted(const View& v, int group)
 {
+    const char* e = getenv("SLRBS_PGS_SPLIT");                   // read when a context is created
+    const int on = e ? atoi(e) : 1;
+    return on && (group == 32 || group == 64) && (size_t)v.NB * 24 <= 200 * 1024;
+}
+
+void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, bool split, cudaStream_t s)
+{
+    if (split) { launch_pgs_split(v, dt, iters, mu, group, s); return; }
     switch (group) {
     case 4:  launch_lv<4>(v, dt, iters, mu, s); break;
     case 8:  launch_lv<8>(v, dt, iters, mu, s); break;

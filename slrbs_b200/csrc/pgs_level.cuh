@@ -1,0 +1,52 @@
+// pgs_level.cuh -- pieces shared by the level-scheduled solver kernels (pgs_level.cu: one lane per row; pgs_split.cu:
+// two lanes per contact row, one per body side).
+#pragma once
+#include "pgs_math.cuh"
+
+namespace slrbs {
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
+}
+#ifndef LV_BULK_PREFETCH
+#define LV_BULK_PREFETCH 1
+#endif
+
+// shared-memory accumulators of one scene, per body (linear xyz, angular xyz): either two padded float4 (32 B, two
+// 16 B accesses: best when shared memory is plentiful) or three float2 (24 B: a 1000-body scene then needs 24 KB and 9
+// scenes fit an SM instead of 7; chosen when the padded layout would cap the warps per SM)
+template <bool W24> struct Acc;
+template <> struct Acc<false> {
+    enum { FLOATS = 8 };
+    static __device__ __forceinline__ void ld(const float* w, int body, V3& l, V3& a)
+    {
+        const float4* p = reinterpret_cast<const float4*>(w) + 2 * body;
+        l = mk3(p[0]); a = mk3(p[1]);
+    }
+    static __device__ __forceinline__ void st(float* w, int body, const V3& l, const V3& a)
+    {
+        float4* p = reinterpret_cast<float4*>(w) + 2 * body;
+        p[0] = mk4(l, 0.f); p[1] = mk4(a, 0.f);
+    }
+};
+template <> struct Acc<true> {
+    enum { FLOATS = 6 };
+    static __device__ __forceinline__ void ld(const float* w, int body, V3& l, V3& a)
+    {
+        const float2* p = reinterpret_cast<const float2*>(w) + 3 * body;
+        const float2 p0 = p[0], p1 = p[1], p2 = p[2];
+        l = mk3(p0.x, p0.y, p1.x); a = mk3(p1.y, p2.x, p2.y);
+    }
+    static __device__ __forceinline__ void st(float* w, int body, const V3& l, const V3& a)
+    {
+        float2* p = reinterpret_cast<float2*>(w) + 3 * body;
+        p[0] = make_float2(l.x, l.y); p[1] = make_float2(l.z, a.x); p[2] = make_float2(a.y, a.z);
+    }
+};
+
+// level-ordered row streams ([scene][field][pos], layout.cuh mode 1) addressed without the layout-mode test of at_crow
+__device__ __forceinline__ const float4* crow_scene(const View& v, int scene) { return v.crow + (size_t)scene * CROW_FIELDS * v.NC; }
+
+}  // namespace slrbs

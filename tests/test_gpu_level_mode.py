@@ -13,15 +13,20 @@ pytestmark = pytest.mark.gpu
 DT = 0.01
 
 
-def make(mode, oracles, group=None, **kw):
+def make(mode, oracles, group=None, split=None, **kw):
+    """split: None = the library's choice, 0 / 1 = one lane per row (k_pgs_lv) / two lanes per contact row (k_pgs_sp)
+    for the wide-scene groups 32 and 64."""
     os.environ["SLRBS_PGS_MODE"] = mode
     if group:
         os.environ["SLRBS_LEVEL_GROUP"] = str(group)
+    if split is not None:
+        os.environ["SLRBS_PGS_SPLIT"] = str(int(split))
     try:
         return context_from_oracles(oracles, **kw)
     finally:
         os.environ.pop("SLRBS_PGS_MODE", None)
         os.environ.pop("SLRBS_LEVEL_GROUP", None)
+        os.environ.pop("SLRBS_PGS_SPLIT", None)
 
 
 def jittered(scene, n, **kw):
@@ -37,14 +42,19 @@ def jittered(scene, n, **kw):
     return out
 
 
-@pytest.mark.parametrize("scene,kw,n_scenes,steps,group", [
-    ("marble_box", {}, 5, 60, 8), ("marble_box", {}, 3, 25, 4), ("marble_box", {}, 3, 25, 16), ("marble_box", {}, 2, 25, 32),
-    ("car", {}, 7, 80, 8), ("swinging_boxes", {}, 3, 60, 8), ("cylinder_on_plane", {}, 2, 80, 8),
-    ("marble_box_n", dict(nx=5, nz=4, ny=6), 3, 40, 16)])
-def test_level_mode_is_bit_identical_to_sequential(scene, kw, n_scenes, steps, group):
+@pytest.mark.parametrize("scene,kw,n_scenes,steps,group,split", [
+    ("marble_box", {}, 5, 60, 8, None), ("marble_box", {}, 3, 25, 4, None), ("marble_box", {}, 3, 25, 16, None),
+    ("marble_box", {}, 2, 25, 32, 0), ("marble_box", {}, 2, 25, 32, 1), ("marble_box", {}, 2, 25, 64, 1),
+    ("car", {}, 7, 80, 8, None), ("swinging_boxes", {}, 3, 60, 8, None), ("cylinder_on_plane", {}, 2, 80, 8, None),
+    # joints and cylinder-plane contacts through the side-split kernel (its joint rows run on the even lanes)
+    ("car", {}, 3, 80, 32, 1), ("swinging_boxes", {}, 2, 60, 32, 1), ("cylinder_on_plane", {}, 2, 80, 64, 1),
+    ("marble_box_n", dict(nx=5, nz=4, ny=6), 3, 40, 16, None)])
+def test_level_mode_is_bit_identical_to_sequential(scene, kw, n_scenes, steps, group, split):
     oracles = jittered(scene, n_scenes, **kw)
     a = make("thread", oracles, max_contacts=1024)
-    b = make("level", oracles, group=group, max_contacts=1024)
+    b = make("level", oracles, group=group, split=split, max_contacts=1024)
+    if split is not None and group in (32, 64):
+        assert ("k_pgs_sp" in b.describe()) == bool(split), b.describe()
     for k in range(steps):
         a.step(DT); b.step(DT)
         if k in (0, 1, steps // 2, steps - 1):
@@ -97,15 +107,17 @@ def test_krylov_in_level_mode():
     a.close(); b.close()
 
 
-def test_big_scene_variant_with_packed_accumulators():
-    """Thousand-body scenes take the kernel variant with 24 B packed accumulators (9 instead of 7 scenes per SM). It must
-    still give the bits of the sequential kernel."""
+@pytest.mark.parametrize("split", [0, 1])
+def test_big_scene_variant_with_packed_accumulators(split):
+    """Thousand-body scenes take the kernel variants with 24 B packed accumulators (9 instead of 7 scenes per SM): one
+    lane per row (k_pgs_lv<32>) or two lanes per contact row (k_pgs_sp<32>, the default). Both must still give the bits
+    of the sequential kernel."""
     oracles = jittered("marble_box_n", 2, nx=10, nz=10, ny=10)
     for o in oracles:
         o.step(DT, 60)                                   # let contacts with the walls and floor form
     a = make("thread", oracles, max_contacts=4096)
-    b = make("level", oracles, group=32, max_contacts=4096)
-    assert "G=32" in b.describe()
+    b = make("level", oracles, group=32, split=split, max_contacts=4096)
+    assert ("ROWS=32" if split else "G=32") in b.describe()
     for k in range(12):
         a.step(DT); b.step(DT)
     a.sync(); b.sync()
