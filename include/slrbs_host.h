@@ -45,6 +45,26 @@ void slrbs_host_get_joint_lambda(const slrbs_host_system* s, float* lambda5);
 void slrbs_host_save(slrbs_host_system* s);
 void slrbs_host_restore(slrbs_host_system* s);
 
+/* EXTENSION: install a host-side Gauss-Seidel solver written against the reference's Solver.h (only solve(h) overridden) as
+ * solver `solver_id`; step() then runs the host-solver path (rows mirrored to the host objects, lambdas sent back) */
+void slrbs_host_use_host_solver(slrbs_host_system* s, int solver_id);
+
+/* RigidBodySystemBatch (slrbs_b200/host/include/rigidbody/RigidBodySystemBatch.h): n_scenes copies of a system's bodies, joints
+ * and current state in one device context; step is asynchronous and reads nothing back. 0 / -1 + slrbs_host_last_error(). */
+typedef struct slrbs_host_batch slrbs_host_batch;
+slrbs_host_batch* slrbs_host_batch_create(const slrbs_host_system* prototype, int n_scenes, int device, int contacts_per_scene);
+void slrbs_host_batch_destroy(slrbs_host_batch* b);
+int  slrbs_host_batch_set_solver(slrbs_host_batch* b, int solver_id, int solver_iter, float mu, int collisions);
+int  slrbs_host_batch_step(slrbs_host_batch* b, float dt, int n);
+int  slrbs_host_batch_sync(slrbs_host_batch* b);
+int  slrbs_host_batch_set_state(slrbs_host_batch* b, int scene0, int n_scenes, const float* x3, const float* q4, const float* v3, const float* w3);
+int  slrbs_host_batch_get_state(slrbs_host_batch* b, int scene0, int n_scenes, float* x3, float* q4, float* v3, float* w3);
+int  slrbs_host_batch_set_forces(slrbs_host_batch* b, int scene0, int n_scenes, const float* f3, const float* tau3, int absolute);
+int  slrbs_host_batch_save(slrbs_host_batch* b);
+int  slrbs_host_batch_reset(slrbs_host_batch* b, int scene0, int n_scenes);
+int  slrbs_host_batch_contact_counts(slrbs_host_batch* b, int scene0, int n_scenes, int32_t* counts);
+int  slrbs_host_batch_read_scene(slrbs_host_batch* b, int scene, slrbs_host_system* into);
+
 #ifdef __cplusplus
 }
 #endif

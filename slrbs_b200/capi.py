@@ -21,7 +21,7 @@ SYMBOLS = [
     "slrbs_set_external_forces", "slrbs_step", "slrbs_sync", "slrbs_stage_prepare", "slrbs_stage_detect",
     "slrbs_stage_jacobians", "slrbs_stage_solve", "slrbs_stage_integrate", "slrbs_download_contact_counts",
     "slrbs_download_contacts", "slrbs_download_contact_rows", "slrbs_download_joint_rows",
-    "slrbs_download_joint_lambda", "slrbs_upload_joint_lambda", "slrbs_download_body_dyn",
+    "slrbs_download_joint_lambda", "slrbs_upload_joint_lambda", "slrbs_upload_contact_lambda", "slrbs_download_body_dyn",
     "slrbs_save_state", "slrbs_restore_state", "slrbs_profile_enable", "slrbs_profile_read",
     "slrbs_timer_start", "slrbs_timer_stop", "slrbs_halo_set_local", "slrbs_halo_set_remote", "slrbs_halo_sync_local",
     "slrbs_halo_pack", "slrbs_halo_unpack", "slrbs_pile_init", "slrbs_pile_export", "slrbs_pile_rebuild",
@@ -80,6 +80,7 @@ def load_library():
     L.slrbs_download_joint_rows.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, fp, fp]
     L.slrbs_download_joint_lambda.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
     L.slrbs_upload_joint_lambda.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
+    L.slrbs_upload_contact_lambda.argtypes = [vp, C.c_int, C.c_int, fp]
     L.slrbs_download_body_dyn.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp]
     L.slrbs_save_state.argtypes = [vp]
     L.slrbs_restore_state.argtypes = [vp, C.c_int, C.c_int]
@@ -315,6 +316,11 @@ class Context:
     def set_joint_lambda(self, lam, scene0=0):
         lam = np.ascontiguousarray(np.asarray(lam, np.float32).reshape(-1, self.n_joints, 5))
         self._ck(self.L.slrbs_upload_joint_lambda(self.h, scene0, lam.shape[0], self.n_joints, _f(lam)))
+
+    def set_contact_lambda(self, lam, scene=0):
+        """Contact::lambda of one scene in detection order (what a host-side Solver subclass leaves behind)."""
+        lam = np.ascontiguousarray(np.asarray(lam, np.float32).reshape(-1, 3))
+        self._ck(self.L.slrbs_upload_contact_lambda(self.h, scene, lam.shape[0], _f(lam)))
 
     def body_dyn(self, scene=0):
         n = self.n_bodies

@@ -35,7 +35,7 @@ struct slrbs_ctx {
     float mu = 0.8f;
     int solver_id = 0, solver_iters = 10, collisions = 1;
     int level_group = 8;                        // lanes per scene of the level-scheduled solver
-    bool level_split = false;                   // two lanes per contact row (pgs_split.cu) for the wide-scene groups
+    int level_variant = 0;                      // 0 k_pgs_lv, 1 k_pgs_sp (two lanes per contact row, opt-in), 2 k_pgs_pipe (contact-only scenes, pipelined)
     int broadphase = -1;                        // -1 auto, 0 all pairs, 1 hashed grid (SLRBS_BROADPHASE)
     bool joints_dirty = true;                   // joint levels must be recomputed (bodies / joints uploaded)
     std::vector<int> h_nbodies;                 // host mirror of the body counts set through slrbs_upload_bodies (0 = unknown)
@@ -161,7 +161,7 @@ int solve_launch(slrbs_ctx* c, float dt)
     int sweeps = c->solver_iters;
     if (c->solver_id == 3) { launches = 1 + launch_bpp(c->v, c->solver_iters, c->mu, c->stream); sweeps = 0; }
     else if (c->solver_id != 0) { launch_krylov(c->v, c->solver_id, c->solver_iters, c->stream); sweeps = 0; launches = 2; }
-    if (c->v.level_mode) launch_pgs_level(c->v, dt, sweeps, c->mu, c->level_group, c->level_split, c->stream);
+    if (c->v.level_mode) launch_pgs_level(c->v, dt, sweeps, c->mu, c->level_group, c->level_variant, c->stream);
     else launch_pgs(c->v, dt, sweeps, c->mu, c->stream);
     if (c->profiling) { CU(cudaEventRecord(e1, c->stream)); c->solve_launches++; }
     return check_launch(c, launches);
@@ -178,7 +178,10 @@ int slrbs_describe(slrbs_ctx* c, char* buf, int buf_len)
 {
     if (!c || !buf || buf_len <= 0) return fail(SLRBS_E_ARG, "slrbs_describe: bad argument");
     char tmp[256];
-    if (c->v.level_mode && c->level_split)
+    if (c->v.level_mode && c->level_variant == 2)
+        std::snprintf(tmp, sizeof tmp, "solver=k_pgs_pipe (level-scheduled, 1 warp/scene, next chunk's rows prefetched into registers) detect=%s graph=%d",
+                      detect_variant(c->v, c->broadphase), c->use_graph);
+    else if (c->v.level_mode && c->level_variant == 1)
         std::snprintf(tmp, sizeof tmp, "solver=k_pgs_sp<ROWS=%d> (level-scheduled, 2 lanes/contact row, %d threads/scene) detect=%s graph=%d",
                       c->level_group, 2 * c->level_group, detect_variant(c->v, c->broadphase), c->use_graph);
     else if (c->v.level_mode)
@@ -222,13 +225,13 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     {
         const char* m = std::getenv("SLRBS_PGS_MODE");
         const bool fits = level_mode_fits(max_bodies) && detect_warp_fits(max_bodies) &&
-                          contact_levels_smem(max_bodies, max_contacts) <= 200 * 1024;
+                          contact_levels_smem(max_bodies, max_contacts) <= 200 * 1024 && max_contacts < 65535;   // (level, rank) are packed 16 : 16
         if (m && std::strcmp(m, "thread") == 0) v.level_mode = 0;
         else if (m && std::strcmp(m, "level") == 0) v.level_mode = fits ? 1 : 0;
         else v.level_mode = (n_scenes <= 8192 && fits) ? 1 : 0;
         const char* g = std::getenv("SLRBS_LEVEL_GROUP");
         c->level_group = level_group_size(v, g ? std::atoi(g) : 0);
-        c->level_split = v.level_mode && level_split_wanted(v, c->level_group);
+        c->level_variant = !v.level_mode ? 0 : (level_split_wanted(v, c->level_group) ? 1 : (level_pipe_wanted(v, c->level_group) ? 2 : 0));
         const char* bp = std::getenv("SLRBS_BROADPHASE");
         if (bp) c->broadphase = std::atoi(bp) ? 1 : 0;
     }
@@ -723,6 +726,23 @@ int slrbs_upload_joint_lambda(slrbs_ctx* c, int scene0, int ns, int n, const flo
     const float* d = nullptr;
     if ((r = stage_in(c, lambda5, 5 * m, &d))) return r;
     launch_joint_lambda(c->v, scene0, ns, n, (float*)d, 1, c->stream);
+    if ((r = check_launch(c))) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slrbs_upload_contact_lambda(slrbs_ctx* c, int scene, int n, const float* lambda3)
+{
+    if (!range_ok(c, scene, 1) || n < 0 || (n > 0 && !lambda3)) return fail(SLRBS_E_ARG, "slrbs_upload_contact_lambda: bad argument");
+    CU(cudaSetDevice(c->device));
+    int total = 0, r;
+    if ((r = scene_count(c, c->v.ncontacts, scene, &total))) return r;
+    if (n > total) return fail(SLRBS_E_ARG, "slrbs_upload_contact_lambda: more impulses than the scene has contacts");
+    if (n == 0) return 0;
+    if ((r = stage_reserve(c, pad256((size_t)n * 12) + 4096))) return r;
+    const float* d = nullptr;
+    if ((r = stage_in(c, lambda3, (size_t)3 * n, &d))) return r;
+    launch_import_contact_lambda(c->v, scene, n, d, c->stream);
     if ((r = check_launch(c))) return r;
     CU(cudaStreamSynchronize(c->stream));
     return 0;

@@ -1119,6 +1119,14 @@ __global__ void k_export_contacts(View v, int scene, int n, int* body0, int* bod
     if (rhs3) { rhs3[3 * c] = F[3].w; rhs3[3 * c + 1] = F[4].w; rhs3[3 * c + 2] = F[5].w; }
 }
 
+// Contact::lambda written by a host-side Solver subclass (the Solver seam, include/solvers/Solver.h:9-43)
+__global__ void k_import_contact_lambda(View v, int scene, int n, const float* lam3)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    v.crow[at_crow(v, CROW_LAMBDA, contact_pos(v, c, scene), scene)] = make_float4(lam3[3 * c], lam3[3 * c + 1], lam3[3 * c + 2], 0.f);
+}
+
 __global__ void k_export_joints(View v, int scene, int n, float* J0, float* J1, float* M0, float* M1, float* rhs5)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1218,6 +1226,8 @@ void launch_export_contacts(const View& v, int scene, int n, int* body0, int* bo
                             float* b3, float* phi, float* lam3, float* J0, float* J1, float* M0, float* M1,
                             float* A9, float* rhs3, cudaStream_t s)
 { if (n > 0) k_export_contacts<<<blocks_for(n, 128), 128, 0, s>>>(v, scene, n, body0, body1, p3, n3, t3, b3, phi, lam3, J0, J1, M0, M1, A9, rhs3); }
+void launch_import_contact_lambda(const View& v, int scene, int n, const float* lam3, cudaStream_t s)
+{ if (n > 0) k_import_contact_lambda<<<blocks_for(n, 128), 128, 0, s>>>(v, scene, n, lam3); }
 void launch_export_joints(const View& v, int scene, int n, float* J0, float* J1, float* M0, float* M1, float* rhs5, cudaStream_t s)
 { if (n > 0) k_export_joints<<<blocks_for(n, 128), 128, 0, s>>>(v, scene, n, J0, J1, M0, M1, rhs5); }
 void launch_export_body_dyn(const View& v, int scene, int n, float* f3, float* tau3, float* fc3, float* tauc3, float* I9, float* Iinv9, cudaStream_t s)

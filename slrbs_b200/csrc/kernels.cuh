@@ -49,12 +49,16 @@ void launch_build_sdf(const float* verts, int nt, const int* tris, int nx, int n
 void launch_joint_levels(const View& v, cudaStream_t s);
 void launch_contact_levels(const View& v, cudaStream_t s);
 size_t contact_levels_smem(int NB, int NC);
-void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, bool split, cudaStream_t s);
+void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, int variant, cudaStream_t s);   // variant: 0 k_pgs_lv, 1 k_pgs_sp, 2 k_pgs_pipe
 int  level_group_size(const View& v, int requested);
 // pgs_split.cu: the level schedule with two lanes per contact row (one per body side); rows = 32 or 64 rows per level step
 void init_split_kernels();
 void launch_pgs_split(const View& v, float dt, int iters, float mu, int rows, cudaStream_t s);
 bool level_split_wanted(const View& v, int group);
+// pgs_pipe.cu: one warp per contact-only scene, next chunk's rows prefetched into a second register buffer
+void init_pipe_kernels();
+void launch_pgs_pipe(const View& v, float dt, int iters, float mu, cudaStream_t s);
+bool level_pipe_wanted(const View& v, int group);
 bool level_mode_fits(int max_bodies);
 void launch_integrate(const View& v, float dt, cudaStream_t s);
 
@@ -78,6 +82,7 @@ void launch_pile_lookup(const int* gids, int n, int n_global, const int* loc, in
 void launch_export_contacts(const View& v, int scene, int n, int* body0, int* body1, float* p3, float* n3, float* t3,
                             float* b3, float* phi, float* lam3, float* J0, float* J1, float* M0, float* M1,
                             float* A9, float* rhs3, cudaStream_t s);
+void launch_import_contact_lambda(const View& v, int scene, int n, const float* lam3, cudaStream_t s);
 void launch_export_joints(const View& v, int scene, int n, float* J0, float* J1, float* M0, float* M1, float* rhs5, cudaStream_t s);
 void launch_export_body_dyn(const View& v, int scene, int n, float* f3, float* tau3, float* fc3, float* tauc3,
                             float* I9, float* Iinv9, cudaStream_t s);

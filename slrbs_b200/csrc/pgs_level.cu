@@ -65,29 +65,39 @@ __global__ void __launch_bounds__(128) k_joint_levels(View v)
 // depends on the levels of all earlier contacts of its bodies, a strictly sequential chain kept short by
 // doing it out of shared-memory tables); the lanes stage the ids in chunks of 32 and do the counting sort.
 // ------------------------------------------------------------------------------------
-// H = the type of the per-level counters / starts: 16 bit when the contact capacity allows, which takes the kernel's
-// shared memory from 21 KB to 13 KB for (NB, NC) = (1005, 4096), i.e. 18 instead of 11 scenes per SM (one wave for 2664)
-__host__ __device__ inline size_t levels_hist_bytes(int NC, size_t hsize) { return (((size_t)NC + 2) * hsize + 7) & ~(size_t)7; }
+// Shared memory per scene decides how many scenes an SM walks at once, and the walk is a latency chain: `last` is 16 bit
+// (a level number < 65535; 0xFFFF = fixed body; level mode needs max_contacts < 65535, slrbs_create), and the per-level counters live in shared memory only for the first LEVEL_HIST_CAP
+// levels -- a thousand-sphere pile has ~130 -- with the scene's clev_end column in global memory as the overflow area for
+// deeper chains. (NB, NC) = (1005, 4096): 4.5 KB per scene instead of 12.6 KB, so the 18 scenes per SM of a 2664-scene batch
+// are resident together (before: 16 per SM, i.e. a second, nearly empty wave).
+enum { LEVEL_HIST_CAP = 1024, LV_FIXED = 0xFFFF };
 
-template <typename H>
+struct LevelHist {
+    unsigned short* s; int* g; size_t B;                          // g[l * B]: the scene's clev_end column, used as scratch for l >= CAP
+    __device__ __forceinline__ int get(int l) const { return l < LEVEL_HIST_CAP ? (int)s[l] : g[(size_t)l * B]; }
+    __device__ __forceinline__ void set(int l, int x) const { if (l < LEVEL_HIST_CAP) s[l] = (unsigned short)x; else g[(size_t)l * B] = x; }
+};
+
 __global__ void __launch_bounds__(32) k_contact_levels(View v)
 {
     extern __shared__ int lsm[];
     const int lane = threadIdx.x, scene = blockIdx.x;
-    int* last = lsm;                       // [NB] last level that touched a body; -1 marks a fixed body
-    unsigned char* after_last = reinterpret_cast<unsigned char*>(lsm + (((size_t)v.NB + 1) & ~(size_t)1));
-    H* hist = reinterpret_cast<H*>(after_last);               // [NC + 2]
-    int2* idbuf = reinterpret_cast<int2*>(after_last + levels_hist_bytes(v.NC, sizeof(H)));   // [32], 8-byte aligned
-    int* outbuf = reinterpret_cast<int*>(idbuf + 32);         // [32]
+    unsigned short* last = reinterpret_cast<unsigned short*>(lsm);   // [NB] last level that touched a body; LV_FIXED marks a fixed body
+    unsigned short* hist_s = reinterpret_cast<unsigned short*>(last + (((size_t)v.NB + 3) & ~(size_t)3));   // [LEVEL_HIST_CAP]
+    int2* idbuf = reinterpret_cast<int2*>(hist_s + LEVEL_HIST_CAP);   // [32], 8-byte aligned
+    int* outbuf = reinterpret_cast<int*>(idbuf + 32);             // [32]
+    const LevelHist hist{ hist_s, v.clev_end + scene, (size_t)v.B };
     const int nb = v.nbodies[scene], nc = v.ncontacts[scene];
     for (int b0 = 0; b0 < nb; b0 += 256) {                      // 8 independent flag loads in flight per lane
         int fl[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) { const int b = b0 + u * 32 + lane; fl[u] = b < nb ? v.flags[at(v, b, scene)] : 0; }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int b = b0 + u * 32 + lane; if (b < nb) last[b] = (fl[u] & FLAG_FIXED) ? -1 : 0; }
+        for (int u = 0; u < 8; ++u) { const int b = b0 + u * 32 + lane; if (b < nb) last[b] = (fl[u] & FLAG_FIXED) ? (unsigned short)LV_FIXED : (unsigned short)0; }
     }
-    for (int l = lane; l <= nc + 1; l += 32) hist[l] = 0;
+    // a chain can be at most nc levels deep; counters of levels the walk never reaches are never read
+    for (int l = lane; l <= min(nc, LEVEL_HIST_CAP - 1); l += 32) hist_s[l] = 0;
+    for (int l = LEVEL_HIST_CAP + lane; l <= nc; l += 32) hist.g[(size_t)l * hist.B] = 0;
     __syncwarp();
     // The level of a contact depends on the levels of all earlier contacts of its two bodies: a sequential chain, walked
     // by lane 0 out of shared memory (ids staged by the warp in chunks of 32; two dependent shared-memory accesses per
@@ -109,18 +119,18 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
                     const int l0 = last[r[k].x], l1 = last[r[k].y];
-                    const int L = max(max(l0, l1), 0) + 1;      // fixed bodies (-1) do not order anything
-                    if (l0 >= 0) last[r[k].x] = L;
-                    if (l1 >= 0) last[r[k].y] = L;
+                    const int L = max(l0 == LV_FIXED ? 0 : l0, l1 == LV_FIXED ? 0 : l1) + 1;   // fixed bodies do not order anything
+                    if (l0 != LV_FIXED) last[r[k].x] = (unsigned short)L;
+                    if (l1 != LV_FIXED) last[r[k].y] = (unsigned short)L;
                     outbuf[k] = L;
                 }
             } else {
                 for (int k = 0; k < m; ++k) {
                     const int2 ids = idbuf[k];
                     const int l0 = last[ids.x], l1 = last[ids.y];
-                    const int L = max(max(l0, l1), 0) + 1;
-                    if (l0 >= 0) last[ids.x] = L;
-                    if (l1 >= 0) last[ids.y] = L;
+                    const int L = max(l0 == LV_FIXED ? 0 : l0, l1 == LV_FIXED ? 0 : l1) + 1;
+                    if (l0 != LV_FIXED) last[ids.x] = (unsigned short)L;
+                    if (l1 != LV_FIXED) last[ids.y] = (unsigned short)L;
                     outbuf[k] = L;
                 }
             }
@@ -130,21 +140,23 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
         if (lane < m) {
             const int myL = outbuf[lane];
             const unsigned same = __match_any_sync(act, myL);
-            const int base = hist[myL];
+            const int base = hist.get(myL);
             __syncwarp(act);
-            if (lane == __ffs(same) - 1) hist[myL] = (H)(base + __popc(same));
-            v.cpos[at(v, c0 + lane, scene)] = (myL << 16) | (base + __popc(same & ((1u << lane) - 1u)));
+            if (lane == __ffs(same) - 1) hist.set(myL, base + __popc(same));
+            v.cpos[at(v, c0 + lane, scene)] = (int)(((unsigned)myL << 16) | (unsigned)(base + __popc(same & ((1u << lane) - 1u))));
             nlev = max(nlev, myL);
         }
         __syncwarp();
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) nlev = max(nlev, __shfl_xor_sync(0xffffffffu, nlev, d));
-    // exclusive prefix of the per-level counts -> level starts (in place), level ends to global
+    // exclusive prefix of the per-level counts -> level starts (shared counters, in place) and level ends (global). A level
+    // past the shared counters had its count in clev_end itself, which now receives its end; its start is read back below
+    // as the end of the level before it.
     int carry = 0;
     for (int l0 = 1; l0 <= nlev; l0 += 32) {
         const int l = l0 + lane;
-        const int c = l <= nlev ? hist[l] : 0;
+        const int c = l <= nlev ? hist.get(l) : 0;
         int incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -152,8 +164,8 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
             if (lane >= d) incl += t;
         }
         if (l <= nlev) {
-            hist[l] = (H)(carry + incl - c);
-            v.clev_end[at(v, l, scene)] = carry + incl;
+            if (l < LEVEL_HIST_CAP) hist_s[l] = (unsigned short)(carry + incl - c);   // level start
+            v.clev_end[at(v, l, scene)] = carry + incl;                               // level end (for l >= CAP the start is the previous level's end)
         }
         carry += __shfl_sync(0xffffffffu, incl, 31);
     }
@@ -167,7 +179,9 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
         for (int u = 0; u < 8; ++u) {
             const int c = c0 + u * 32 + lane;
             if (c < nc) {
-                const int pos = hist[pk[u] >> 16] + (pk[u] & 0xffff);
+                const int L = (int)((unsigned)pk[u] >> 16);
+                const int start = L < LEVEL_HIST_CAP ? (int)hist_s[L] : v.clev_end[at(v, L - 1, scene)];
+                const int pos = start + (pk[u] & 0xffff);
                 v.cpos[at(v, c, scene)] = pos;
                 v.cslot[(size_t)scene * v.NC + pos] = c;
             }
@@ -362,16 +376,14 @@ __global__ void __launch_bounds__(LvCfg<G>::THREADS, MINB) k_pgs_lv(View v, floa
 // ------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------
-static bool levels_hist16(int NC) { return NC + 2 < 65535; }
-size_t contact_levels_smem(int NB, int NC)
+size_t contact_levels_smem(int NB, int)
 {
-    return (((size_t)NB + 1) & ~(size_t)1) * 4 + levels_hist_bytes(NC, levels_hist16(NC) ? 2 : 4) + 32 * 8 + 32 * 4;
+    return (((size_t)NB + 3) & ~(size_t)3) * 2 + (size_t)LEVEL_HIST_CAP * 2 + 32 * 8 + 32 * 4;
 }
 
 void launch_contact_levels(const View& v, cudaStream_t s)
 {
-    if (levels_hist16(v.NC)) k_contact_levels<unsigned short><<<(unsigned)v.B, 32, contact_levels_smem(v.NB, v.NC), s>>>(v);
-    else k_contact_levels<int><<<(unsigned)v.B, 32, contact_levels_smem(v.NB, v.NC), s>>>(v);
+    k_contact_levels<<<(unsigned)v.B, 32, contact_levels_smem(v.NB, v.NC), s>>>(v);
 }
 
 void launch_joint_levels(const View& v, cudaStream_t s)
@@ -427,8 +439,8 @@ void init_level_kernels()
 {
     init_lv<4>(); init_lv<8>(); init_lv<16>(); init_lv<32>(); init_lv<64>(); init_lv<128>();
     init_split_kernels();
-    cudaFuncSetAttribute(k_contact_levels<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_contact_levels<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    init_pipe_kernels();
+    cudaFuncSetAttribute(k_contact_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 int level_group_size(const View& v, int requested)
@@ -442,18 +454,21 @@ int level_group_size(const View& v, int requested)
 
 bool level_mode_fits(int max_bodies) { return (size_t)max_bodies * 24 <= 200 * 1024; }
 
-// The side-split kernel (pgs_split.cu) serves the wide scenes that used to get one or two warps of one lane per row
-// (G = 32 / 64): twice the warps on the same shared memory. SLRBS_PGS_SPLIT=0 keeps the one-lane-per-row kernels (A/B).
+// The side-split kernel (pgs_split.cu: two lanes per contact row) is opt-in (SLRBS_PGS_SPLIT=1) for the wide-scene groups
+// G = 32 / 64. Measured on marble_box_1k x 2664 it is slower than one lane per row (6.3 vs 5.1 ms): the level step is bound
+// by the latency of its critical path, not by issue slots, and a second warp per scene shortens the chain by less than
+// its barrier adds (profiles/README.md).
 bool level_split_wanted(const View& v, int group)
 {
     const char* e = getenv("SLRBS_PGS_SPLIT");                   // read when a context is created
-    const int on = e ? atoi(e) : 1;
+    const int on = e ? atoi(e) : 0;
     return on && (group == 32 || group == 64) && (size_t)v.NB * 24 <= 200 * 1024;
 }
 
-void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, bool split, cudaStream_t s)
+void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, int variant, cudaStream_t s)
 {
-    if (split) { launch_pgs_split(v, dt, iters, mu, group, s); return; }
+    if (variant == 1) { launch_pgs_split(v, dt, iters, mu, group, s); return; }
+    if (variant == 2) { launch_pgs_pipe(v, dt, iters, mu, s); return; }
     switch (group) {
     case 4:  launch_lv<4>(v, dt, iters, mu, s); break;
     case 8:  launch_lv<8>(v, dt, iters, mu, s); break;

@@ -7,6 +7,7 @@
 
 #include <functional>
 #include <memory>
+#include <unordered_map>
 #include <vector>
 
 class Contact;
@@ -42,6 +43,9 @@ public:
     // EXTENSION (not in the reference): also generate sphere-plane, box-plane and box-box contacts, which the
     // reference's dispatch ignores (src/collision/CollisionDetect.cpp:45-73). Off by default.
     void setExtendedContacts(bool _on) { m_extContacts = _on; }
+    // EXTENSION: replace the solver object behind solverId = id (0..3); the system takes ownership. The reference keeps
+    // its solvers in a file-static array (RigidBodySystem.cpp:17,29-31), so there a user edits that file instead.
+    void setSolver(int id, Solver* solver);
 
     int solverIter;
     int solverId;   // PGS = 0, Conj. Gradient = 1, Conj. Residual = 2; extension: block principal pivoting = 3
@@ -81,6 +85,10 @@ private:
     bool m_extActive = false;
     float m_lastDt = 0.01f;
     std::vector<float> m_paramSnapshot, m_stateSnapshot, m_lambdaSnapshot;
+    mutable std::unordered_map<const RigidBody*, int> m_bodyIndex;   // body -> index, rebuilt when bodies were added / cleared
+    mutable bool m_bodyIndexDirty = true;
+    int bodyIndexOf(const RigidBody* b) const;
+    bool hostSolve(Solver* solver, float dt);
 
     void ensureContext();
     void uploadAll();

@@ -22,12 +22,22 @@
 #include <string>
 #include <unordered_map>
 
-namespace {
-int indexOf(const std::vector<RigidBody*>& bodies, const RigidBody* b)
+// body pointer -> index without the O(bodies) scan per joint (packParams runs every step)
+int RigidBodySystem::bodyIndexOf(const RigidBody* b) const
 {
-    for (size_t i = 0; i < bodies.size(); ++i) if (bodies[i] == b) return (int)i;
-    return -1;
+    if (m_bodyIndexDirty) {
+        m_bodyIndex.clear();
+        for (size_t i = 0; i < m_bodies.size(); ++i) m_bodyIndex[m_bodies[i]] = (int)i;
+        m_bodyIndexDirty = false;
+    }
+    const auto it = m_bodyIndex.find(b);
+    return it == m_bodyIndex.end() ? -1 : it->second;
 }
+
+void RigidBodySystem::setSolver(int id, Solver* solver)
+{
+    if (id < 0 || id > 3) { delete solver; throw std::runtime_error("RigidBodySystem::setSolver: id must be 0..3"); }
+    m_solvers[id].reset(solver);
 }
 
 RigidBodySystem::RigidBodySystem() : solverIter(10), solverId(0), m_collisionsEnabled(true), m_preStepFunc(nullptr), m_resetFunc(nullptr)
@@ -50,7 +60,7 @@ void RigidBodySystem::check(int rc, const char* what) const
     if (rc < 0) throw std::runtime_error(std::string(what) + ": " + slrbs_last_error());
 }
 
-void RigidBodySystem::addBody(RigidBody* _b) { m_bodies.push_back(_b); m_topologyDirty = true; }
+void RigidBodySystem::addBody(RigidBody* _b) { m_bodies.push_back(_b); m_topologyDirty = true; m_bodyIndexDirty = true; }
 
 void RigidBodySystem::addJoint(Joint* _j)
 {
@@ -69,6 +79,7 @@ void RigidBodySystem::clear()
     for (RigidBody* b : m_bodies) delete b;
     m_bodies.clear();
     m_topologyDirty = true;
+    m_bodyIndexDirty = true;
 }
 
 const std::vector<Contact*>& RigidBodySystem::getContacts() const { return m_collisionDetect->getContacts(); }
@@ -89,7 +100,7 @@ void RigidBodySystem::packParams(std::vector<float>& out) const
         out.insert(out.end(), b->IbodyInv.data(), b->IbodyInv.data() + 9);
     }
     for (const Joint* j : m_joints) {
-        out.push_back((float)j->getType()); out.push_back((float)indexOf(m_bodies, j->body0)); out.push_back((float)indexOf(m_bodies, j->body1));
+        out.push_back((float)j->getType()); out.push_back((float)bodyIndexOf(j->body0)); out.push_back((float)bodyIndexOf(j->body1));
         for (int k = 0; k < 3; ++k) out.push_back(j->r0[k]);
         for (int k = 0; k < 3; ++k) out.push_back(j->r1[k]);
         out.push_back(j->q0.x()); out.push_back(j->q0.y()); out.push_back(j->q0.z()); out.push_back(j->q0.w());
@@ -161,7 +172,7 @@ void RigidBodySystem::uploadAll()
         std::vector<float> r0(3 * nj), r1(3 * nj), q0(4 * nj), q1(4 * nj);
         for (int i = 0; i < nj; ++i) {
             const Joint* j = m_joints[i];
-            jt[i] = (int)j->getType(); b0[i] = indexOf(m_bodies, j->body0); b1[i] = indexOf(m_bodies, j->body1);
+            jt[i] = (int)j->getType(); b0[i] = bodyIndexOf(j->body0); b1[i] = bodyIndexOf(j->body1);
             for (int k = 0; k < 3; ++k) { r0[3 * i + k] = j->r0[k]; r1[3 * i + k] = j->r1[k]; }
             q0[4 * i] = j->q0.x(); q0[4 * i + 1] = j->q0.y(); q0[4 * i + 2] = j->q0.z(); q0[4 * i + 3] = j->q0.w();
             q1[4 * i] = j->q1.x(); q1[4 * i + 1] = j->q1.y(); q1[4 * i + 2] = j->q1.z(); q1[4 * i + 3] = j->q1.w();
@@ -344,7 +355,8 @@ void RigidBodySystem::step(float dt)
         // calcConstraintForces (RigidBodySystem.cpp:177-183): the selected Solver object runs the solve
         Solver* solver = m_solvers[std::min(std::max(solverId, 0), 3)].get();
         solver->setMaxIter(solverIter);
-        solver->solve(dt);
+        if (solver->deviceSolverId() >= 0) solver->solve(dt);
+        else if (!hostSolve(solver, dt)) { m_contactCapacity *= 2; m_topologyDirty = true; continue; }
         check(slrbs_stage_integrate(m_ctx, dt), "slrbs_stage_integrate");
 
         const int rc = slrbs_sync(m_ctx);
@@ -360,6 +372,58 @@ void RigidBodySystem::step(float dt)
         return;
     }
     throw std::runtime_error(std::string("RigidBodySystem::step: capacity kept overflowing: ") + slrbs_last_error());
+}
+
+// A Solver subclass without a device kernel (deviceSolverId() < 0, i.e. one written against the reference's
+// include/solvers/Solver.h): give it what SolverBoxPGS::solve reads in the reference -- every body's f, tau, xdot, omega,
+// Iinv and contact / joint lists, every constraint's J0, J1, J0Minv, J1Minv, phi, lambda (SolverBoxPGS.cpp:27-82) -- run
+// solve(h) on the host, then hand the lambdas back: zero device sweeps leave them as uploaded and scatter the constraint
+// forces (RigidBodySystem.cpp:185-220) ahead of the integration.
+bool RigidBodySystem::hostSolve(Solver* solver, float dt)
+{
+    const int n = (int)m_bodies.size(), nj = (int)m_joints.size();
+    const int rc0 = slrbs_sync(m_ctx);
+    if (rc0 == SLRBS_E_CAPACITY) return false;                   // more contacts than the context holds: the caller grows it and redoes the step
+    check(rc0, "slrbs_sync");
+    std::vector<float> f(3 * n), tau(3 * n), I(9 * n), Ii(9 * n);
+    check(slrbs_download_body_dyn(m_ctx, 0, n, f.data(), tau.data(), nullptr, nullptr, I.data(), Ii.data()), "slrbs_download_body_dyn");
+    for (int i = 0; i < n; ++i) {
+        RigidBody* b = m_bodies[i];
+        b->f = Eigen::Vector3f(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+        b->tau = Eigen::Vector3f(tau[3 * i], tau[3 * i + 1], tau[3 * i + 2]);
+        b->fc.setZero(); b->tauc.setZero();
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { b->Iinv(r, c) = Ii[9 * i + 3 * r + c]; if (!b->fixed) b->I(r, c) = I[9 * i + 3 * r + c]; }
+    }
+    const bool rows = m_rowReadback;
+    m_rowReadback = true;                                        // J blocks exactly as the device assembled them
+    mirrorContacts();
+    m_rowReadback = rows;
+    if (nj > 0) {
+        std::vector<float> J0(30 * nj), J1(30 * nj), M0(30 * nj), M1(30 * nj);
+        check(slrbs_download_joint_rows(m_ctx, 0, nj, J0.data(), J1.data(), M0.data(), M1.data(), nullptr), "slrbs_download_joint_rows");
+        for (int i = 0; i < nj; ++i) {
+            Joint* j = m_joints[i];
+            j->computeJacobian();                                // phi (and the blocks) from the host fields ...
+            for (unsigned r = 0; r < j->dim; ++r) for (int k = 0; k < 6; ++k) {   // ... the blocks then taken from the device
+                j->J0(r, k) = J0[30 * i + 6 * r + k]; j->J1(r, k) = J1[30 * i + 6 * r + k];
+                j->J0Minv(r, k) = M0[30 * i + 6 * r + k]; j->J1Minv(r, k) = M1[30 * i + 6 * r + k];
+            }
+        }
+    }
+    solver->solve(dt);
+    auto& contacts = m_collisionDetect->getContacts();
+    if (!contacts.empty()) {
+        std::vector<float> lam(3 * contacts.size());
+        for (size_t i = 0; i < contacts.size(); ++i) for (int k = 0; k < 3; ++k) lam[3 * i + k] = contacts[i]->lambda(k);
+        check(slrbs_upload_contact_lambda(m_ctx, 0, (int)contacts.size(), lam.data()), "slrbs_upload_contact_lambda");
+    }
+    if (nj > 0) {
+        std::vector<float> lam; packLambda(lam);
+        check(slrbs_upload_joint_lambda(m_ctx, 0, 1, nj, lam.data()), "slrbs_upload_joint_lambda");
+        m_lambdaSnapshot = lam;
+    }
+    deviceSolve(0, 0, dt);                                       // zero sweeps: force scatter of the uploaded impulses
+    return true;
 }
 
 // ---- CollisionDetect / Solver seams ---------------------------------------------------------------

@@ -4,11 +4,17 @@
 #include "contact/Contact.h"
 #include "polyscope/polyscope.h"
 #include "rigidbody/RigidBodyState.h"
+#include "rigidbody/RigidBodySystemBatch.h"
+#include "solvers/Solver.h"
 #include "rigidbody/Scenarios.h"
 
+#include <algorithm>
 #include <cstring>
+#include <vector>
 #include <memory>
 #include <string>
+
+struct slrbs_host_batch { std::unique_ptr<RigidBodySystemBatch> batch; };
 
 struct slrbs_host_system {
     RigidBodySystem sys;
@@ -176,5 +182,133 @@ void slrbs_host_restore(slrbs_host_system* s)
 {
     if (s->saved) s->saved->restore(s->sys);
 }
+
+// ---- a Solver subclass written against the reference's header: only solve(h) is overridden, so it runs on the host -----------
+// Projected Gauss-Seidel over the mirrored constraint objects, in the reference's row order (joints, then contacts) with one
+// velocity-impulse accumulator per body -- the same maths as SolverBoxPGS.cpp:126-250 written from the public fields a user
+// solver sees (J0, J1, J0Minv, J1Minv, phi, lambda, body->f / tau / xdot / omega / fixed). Used by the tests to exercise the
+// host-solver path of RigidBodySystem::step.
+namespace {
+class HostGaussSeidel : public Solver {
+public:
+    explicit HostGaussSeidel(RigidBodySystem* sys) : Solver(sys) {}
+    void solve(float h) override
+    {
+        auto& bodies = m_rigidBodySystem->getBodies();
+        std::vector<Joint*> rows(m_rigidBodySystem->getJoints().begin(), m_rigidBodySystem->getJoints().end());
+        const size_t nJoints = rows.size();
+        for (Contact* c : m_rigidBodySystem->getContacts()) { c->lambda.setZero(); rows.push_back(c); }
+        std::vector<int> index(bodies.size());
+        std::vector<std::vector<float>> w(bodies.size(), std::vector<float>(6, 0.f));      // sum of J^T lambda per body
+        auto slot = [&](const RigidBody* b) { for (size_t i = 0; i < bodies.size(); ++i) if (bodies[i] == b) return (int)i; return -1; };
+        struct Row { int b0, b1; std::vector<float> A, rhs; };
+        std::vector<Row> R(rows.size());
+        for (size_t i = 0; i < rows.size(); ++i) {
+            Joint* j = rows[i];
+            const int d = (int)j->dim;
+            Row& r = R[i];
+            r.b0 = j->body0->fixed ? -1 : slot(j->body0); r.b1 = j->body1->fixed ? -1 : slot(j->body1);
+            r.A.assign((size_t)d * d, 0.f); r.rhs.assign(d, 0.f);
+            for (int a = 0; a < d; ++a) {
+                float b = -(0.3f / h) * j->phi(a);
+                const RigidBody* bs[2] = { j->body0, j->body1 };
+                const JBlock* Js[2] = { &j->J0, &j->J1 };
+                const JBlock* Ms[2] = { &j->J0Minv, &j->J1Minv };
+                for (int s = 0; s < 2; ++s) {
+                    if (bs[s]->fixed) continue;
+                    for (int k = 0; k < 3; ++k) {
+                        b -= h * (*Ms[s])(a, k) * bs[s]->f[k] + h * (*Ms[s])(a, 3 + k) * bs[s]->tau[k];
+                        b -= (*Js[s])(a, k) * bs[s]->xdot[k] + (*Js[s])(a, 3 + k) * bs[s]->omega[k];
+                    }
+                    for (int c = 0; c < d; ++c) for (int k = 0; k < 6; ++k) r.A[(size_t)a * d + c] += (*Ms[s])(a, k) * (*Js[s])(c, k);
+                }
+                r.rhs[a] = b;
+                if (i < nJoints) r.A[(size_t)a * d + a] += 1e-5f;
+            }
+            for (int a = 0; a < d; ++a) {                        // warm start: joints keep last step's impulses
+                if (r.b0 >= 0) for (int k = 0; k < 6; ++k) w[r.b0][k] += j->J0(a, k) * j->lambda(a);
+                if (r.b1 >= 0) for (int k = 0; k < 6; ++k) w[r.b1][k] += j->J1(a, k) * j->lambda(a);
+            }
+        }
+        for (int it = 0; it < m_maxIter; ++it)
+            for (size_t i = 0; i < rows.size(); ++i) {
+                Joint* j = rows[i];
+                const int d = (int)j->dim;
+                const Row& r = R[i];
+                std::vector<float> x(r.rhs);
+                for (int a = 0; a < d; ++a) {                    // x = b - sum over the OTHER constraints of the two bodies
+                    for (int k = 0; k < 6; ++k) {
+                        if (r.b0 >= 0) { float own = 0.f; for (int c = 0; c < d; ++c) own += j->J0(c, k) * j->lambda(c); x[a] -= j->J0Minv(a, k) * (w[r.b0][k] - own); }
+                        if (r.b1 >= 0) { float own = 0.f; for (int c = 0; c < d; ++c) own += j->J1(c, k) * j->lambda(c); x[a] -= j->J1Minv(a, k) * (w[r.b1][k] - own); }
+                    }
+                }
+                std::vector<float> lam(d);
+                if (i >= nJoints) {                              // contact: normal >= 0, tangents inside the friction box
+                    const float* A = r.A.data();
+                    lam[0] = std::max(0.f, (x[0] - A[1] * j->lambda(1) - A[2] * j->lambda(2)) / (A[0] + 1e-3f));
+                    const float lim = Contact::mu * lam[0];
+                    lam[1] = std::min(lim, std::max(-lim, (x[1] - A[3] * lam[0] - A[5] * j->lambda(2)) / A[4]));
+                    lam[2] = std::min(lim, std::max(-lim, (x[2] - A[6] * lam[0] - A[7] * lam[1]) / A[8]));
+                } else {                                         // joint: dense solve of the d x d block (Gaussian elimination)
+                    std::vector<float> M(r.A), y(x);
+                    for (int c = 0; c < d; ++c) for (int a = c + 1; a < d; ++a) {
+                        const float m = M[(size_t)a * d + c] / M[(size_t)c * d + c];
+                        for (int k = c; k < d; ++k) M[(size_t)a * d + k] -= m * M[(size_t)c * d + k];
+                        y[a] -= m * y[c];
+                    }
+                    for (int a = d - 1; a >= 0; --a) {
+                        float sum = y[a];
+                        for (int k = a + 1; k < d; ++k) sum -= M[(size_t)a * d + k] * lam[k];
+                        lam[a] = sum / M[(size_t)a * d + a];
+                    }
+                }
+                for (int a = 0; a < d; ++a) {
+                    const float dl = lam[a] - j->lambda(a);
+                    if (r.b0 >= 0) for (int k = 0; k < 6; ++k) w[r.b0][k] += j->J0(a, k) * dl;
+                    if (r.b1 >= 0) for (int k = 0; k < 6; ++k) w[r.b1][k] += j->J1(a, k) * dl;
+                    j->lambda(a) = lam[a];
+                }
+            }
+    }
+};
+}  // namespace
+
+/* replaces the solver behind solver_id (0..3) by a host-side Gauss-Seidel written against the reference's Solver.h
+ * (deviceSolverId() not overridden): RigidBodySystem::step then runs the host-solver path */
+void slrbs_host_use_host_solver(slrbs_host_system* s, int solver_id)
+{
+    s->sys.setSolver(solver_id, new HostGaussSeidel(&s->sys));
+}
+
+/* ---- RigidBodySystemBatch ------------------------------------------------------------------------------------------- */
+slrbs_host_batch* slrbs_host_batch_create(const slrbs_host_system* proto, int n_scenes, int device, int contacts_per_scene)
+{
+    try {
+        std::unique_ptr<slrbs_host_batch> h(new slrbs_host_batch());
+        h->batch.reset(new RigidBodySystemBatch(proto->sys, n_scenes, device, contacts_per_scene));
+        return h.release();
+    } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+void slrbs_host_batch_destroy(slrbs_host_batch* b) { delete b; }
+#define BATCH_TRY(stmt) try { stmt; return 0; } catch (const std::exception& e) { g_err = e.what(); return -1; }
+int slrbs_host_batch_set_solver(slrbs_host_batch* b, int solver_id, int solver_iter, float mu, int collisions)
+{
+    b->batch->solverId = solver_id; b->batch->solverIter = solver_iter; b->batch->mu = mu;
+    b->batch->setEnableCollisionDetection(collisions != 0);
+    return 0;
+}
+int slrbs_host_batch_step(slrbs_host_batch* b, float dt, int n) { BATCH_TRY(b->batch->step(dt, n)) }
+int slrbs_host_batch_sync(slrbs_host_batch* b) { BATCH_TRY(b->batch->sync()) }
+int slrbs_host_batch_set_state(slrbs_host_batch* b, int scene0, int ns, const float* x3, const float* q4, const float* v3, const float* w3)
+{ BATCH_TRY(b->batch->setState(scene0, ns, x3, q4, v3, w3)) }
+int slrbs_host_batch_get_state(slrbs_host_batch* b, int scene0, int ns, float* x3, float* q4, float* v3, float* w3)
+{ BATCH_TRY(b->batch->getState(scene0, ns, x3, q4, v3, w3)) }
+int slrbs_host_batch_set_forces(slrbs_host_batch* b, int scene0, int ns, const float* f3, const float* tau3, int absolute)
+{ BATCH_TRY(if (f3 || tau3) b->batch->setExternalForces(scene0, ns, f3, tau3, absolute != 0); else b->batch->clearExternalForces(scene0, ns)) }
+int slrbs_host_batch_save(slrbs_host_batch* b) { BATCH_TRY(b->batch->saveState()) }
+int slrbs_host_batch_reset(slrbs_host_batch* b, int scene0, int ns) { BATCH_TRY(b->batch->resetScenes(scene0, ns)) }
+int slrbs_host_batch_contact_counts(slrbs_host_batch* b, int scene0, int ns, int32_t* counts) { BATCH_TRY(b->batch->getContactCounts(scene0, ns, counts)) }
+int slrbs_host_batch_read_scene(slrbs_host_batch* b, int scene, slrbs_host_system* into) { BATCH_TRY(b->batch->readScene(scene, into->sys)) }
+#undef BATCH_TRY
 
 }  // extern "C"

@@ -15,7 +15,10 @@ SYMBOLS = [
     "slrbs_host_num_joints", "slrbs_host_num_contacts", "slrbs_host_export_bodies", "slrbs_host_export_joints",
     "slrbs_host_set_solver", "slrbs_host_set_prestep_force", "slrbs_host_set_state", "slrbs_host_step",
     "slrbs_host_get_state", "slrbs_host_get_contacts", "slrbs_host_get_joint_lambda", "slrbs_host_save",
-    "slrbs_host_restore",
+    "slrbs_host_restore", "slrbs_host_use_host_solver", "slrbs_host_batch_create", "slrbs_host_batch_destroy",
+    "slrbs_host_batch_set_solver", "slrbs_host_batch_step", "slrbs_host_batch_sync", "slrbs_host_batch_set_state",
+    "slrbs_host_batch_get_state", "slrbs_host_batch_set_forces", "slrbs_host_batch_save", "slrbs_host_batch_reset",
+    "slrbs_host_batch_contact_counts", "slrbs_host_batch_read_scene",
 ]
 
 
@@ -55,6 +58,22 @@ def load_host_library():
               "slrbs_host_set_state", "slrbs_host_get_state", "slrbs_host_get_contacts", "slrbs_host_get_joint_lambda",
               "slrbs_host_save", "slrbs_host_restore"):
         getattr(L, n).restype = None
+    L.slrbs_host_use_host_solver.argtypes = [vp, C.c_int]
+    L.slrbs_host_use_host_solver.restype = None
+    L.slrbs_host_batch_create.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.slrbs_host_batch_create.restype = vp
+    L.slrbs_host_batch_destroy.argtypes = [vp]
+    L.slrbs_host_batch_destroy.restype = None
+    L.slrbs_host_batch_set_solver.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_int]
+    L.slrbs_host_batch_step.argtypes = [vp, C.c_float, C.c_int]
+    L.slrbs_host_batch_sync.argtypes = [vp]
+    L.slrbs_host_batch_set_state.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, fp]
+    L.slrbs_host_batch_get_state.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, fp]
+    L.slrbs_host_batch_set_forces.argtypes = [vp, C.c_int, C.c_int, fp, fp, C.c_int]
+    L.slrbs_host_batch_save.argtypes = [vp]
+    L.slrbs_host_batch_reset.argtypes = [vp, C.c_int, C.c_int]
+    L.slrbs_host_batch_contact_counts.argtypes = [vp, C.c_int, C.c_int, ip]
+    L.slrbs_host_batch_read_scene.argtypes = [vp, C.c_int, vp]
     _LIB = L
     return L
 
@@ -148,6 +167,67 @@ class HostSystem:
 
     def save(self): self.L.slrbs_host_save(self.h)
     def restore(self): self.L.slrbs_host_restore(self.h)
+
+    def use_host_solver(self, solver_id=0):
+        """Replace solver `solver_id` by a host-side Gauss-Seidel subclass of Solver that only overrides solve(h)."""
+        self.L.slrbs_host_use_host_solver(self.h, int(solver_id))
+
+
+class HostBatch:
+    """RigidBodySystemBatch: n_scenes copies of a HostSystem's bodies, joints and current state in one device context."""
+
+    def __init__(self, prototype, n_scenes, device=0, contacts_per_scene=0):
+        self.L = load_host_library()
+        self.n_scenes, self.n_bodies, self.n_joints = int(n_scenes), prototype.n_bodies, prototype.n_joints
+        self.h = self.L.slrbs_host_batch_create(prototype.h, int(n_scenes), int(device), int(contacts_per_scene))
+        if not self.h:
+            raise SlrbsError(self.L.slrbs_host_last_error().decode())
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SlrbsError(self.L.slrbs_host_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.slrbs_host_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_solver(self, solver_id=0, solver_iter=10, mu=0.8, collisions=True):
+        self._ck(self.L.slrbs_host_batch_set_solver(self.h, int(solver_id), int(solver_iter), float(mu), int(bool(collisions))))
+
+    def step(self, dt=0.01, n=1): self._ck(self.L.slrbs_host_batch_step(self.h, float(dt), int(n)))
+    def sync(self): self._ck(self.L.slrbs_host_batch_sync(self.h))
+    def save(self): self._ck(self.L.slrbs_host_batch_save(self.h))
+    def reset(self, scene0=0, n_scenes=None): self._ck(self.L.slrbs_host_batch_reset(self.h, int(scene0), int(n_scenes or self.n_scenes - scene0)))
+
+    def state(self, scene0=0, n_scenes=None):
+        ns, n = int(n_scenes or self.n_scenes - scene0), self.n_bodies
+        o = dict(x=np.zeros((ns, n, 3), np.float32), q=np.zeros((ns, n, 4), np.float32), v=np.zeros((ns, n, 3), np.float32),
+                 w=np.zeros((ns, n, 3), np.float32))
+        self._ck(self.L.slrbs_host_batch_get_state(self.h, int(scene0), ns, _f(o["x"]), _f(o["q"]), _f(o["v"]), _f(o["w"])))
+        return o
+
+    def set_state(self, x, q, v, w, scene0=0):
+        a = [np.ascontiguousarray(np.asarray(t, np.float32)) for t in (x, q, v, w)]
+        self._ck(self.L.slrbs_host_batch_set_state(self.h, int(scene0), a[0].shape[0], *[_f(t) for t in a]))
+
+    def set_forces(self, f=None, tau=None, scene0=0, n_scenes=1, absolute=False):
+        a = [None if t is None else np.ascontiguousarray(np.asarray(t, np.float32)) for t in (f, tau)]
+        self._ck(self.L.slrbs_host_batch_set_forces(self.h, int(scene0), int(n_scenes), _f(a[0]), _f(a[1]), int(bool(absolute))))
+
+    def contact_counts(self):
+        c = np.zeros(self.n_scenes, np.int32)
+        self._ck(self.L.slrbs_host_batch_contact_counts(self.h, 0, self.n_scenes, _i(c)))
+        return c
+
+    def read_scene(self, scene, into):
+        self._ck(self.L.slrbs_host_batch_read_scene(self.h, int(scene), into.h))
 
 
 def scene_arrays(scene, a=0, b=0, c=0):

@@ -86,3 +86,57 @@ def test_headless_program_written_against_the_reference_headers():
     o = Oracle("car"); o.step(DT, 120)
     np.testing.assert_allclose(x, o.state()["x"], rtol=0, atol=2e-3)
     assert f"contacts {o.n_contacts}" in out.stdout
+
+
+def test_batch_matches_single_systems():
+    """RigidBodySystemBatch: every scene of a batch evolves exactly as a RigidBodySystem built the same way (bit for bit:
+    same kernels, same order); reset by scene index, per-scene forces, readScene."""
+    proto = host_api.HostSystem("car")
+    batch = host_api.HostBatch(proto, 5)
+    single = host_api.HostSystem("car")
+    batch.save()
+    batch.step(DT, 40); batch.sync()
+    single.step(DT, 40)
+    st = batch.state()
+    for s in range(5):
+        for k in "xqvw":
+            assert_bit_equal(st[k][s], single.state()[k], f"scene {s} {k}")
+    assert (batch.contact_counts() == single.n_contacts).all()
+    # reset scenes 1..2 to the saved state: they restart (joint lambda kept, RigidBodyState.cpp:26-40), the others go on
+    batch.reset(1, 2)
+    batch.step(DT, 10); batch.sync()
+    single.step(DT, 10)
+    st = batch.state()
+    for s in (0, 3, 4):
+        assert_bit_equal(st["x"][s], single.state()["x"], f"scene {s} after the partial reset")
+    o = Oracle("car"); o.step(DT, 10)
+    np.testing.assert_allclose(st["x"][1], o.state()["x"], rtol=0, atol=5e-3)       # warm-started joints: close to a fresh run
+    assert_bit_equal(st["x"][1], st["x"][2], "the two reset scenes agree")
+    # a force on scene 4 only
+    f = np.zeros((1, batch.n_bodies, 3), np.float32); f[0, 0] = [0.0, 30.0, 0.0]
+    batch.set_forces(f=f, scene0=4, n_scenes=1)
+    batch.step(DT, 5); batch.sync()
+    single.step(DT, 5)
+    st = batch.state()
+    assert_bit_equal(st["x"][0], single.state()["x"], "scene 0 unaffected by scene 4's force")
+    assert st["x"][4][0, 1] > st["x"][0][0, 1]
+    target = host_api.HostSystem("car")
+    batch.read_scene(0, target)
+    assert_bit_equal(target.state()["x"], single.state()["x"], "readScene")
+    for h in (proto, single, target):
+        h.close()
+    batch.close()
+
+
+@pytest.mark.parametrize("scene,steps,tol", [("sphere_on_box", 120, 2e-3), ("car", 80, 5e-3), ("marble_box", 15, 5e-3)])
+def test_solver_subclass_without_device_kernel_runs_on_the_host(scene, steps, tol):
+    """A Solver subclass that only overrides solve(h) (as one written against the reference's Solver.h would) is run on the
+    host: rows mirrored into the public fields, lambdas sent back, force scatter and integration on the device."""
+    h, o = host_api.HostSystem(scene), Oracle(scene)
+    h.use_host_solver(0)
+    for k in range(steps):
+        h.step(DT); o.step(DT)
+    assert h.n_contacts == o.n_contacts
+    np.testing.assert_allclose(h.state()["x"], o.state()["x"], rtol=0, atol=tol)
+    np.testing.assert_allclose(h.state()["v"], o.state()["v"], rtol=0, atol=20 * tol)
+    h.close()

@@ -13,20 +13,23 @@ pytestmark = pytest.mark.gpu
 DT = 0.01
 
 
-def make(mode, oracles, group=None, split=None, **kw):
-    """split: None = the library's choice, 0 / 1 = one lane per row (k_pgs_lv) / two lanes per contact row (k_pgs_sp)
-    for the wide-scene groups 32 and 64."""
+VARIANTS = {"lv": ("0", "0", "k_pgs_lv"), "split": ("1", "0", "k_pgs_sp"), "pipe": ("0", "1", "k_pgs_pipe")}
+
+
+def make(mode, oracles, group=None, variant=None, **kw):
+    """variant: None = the library's choice; for the wide-scene groups "lv" = one lane per row (k_pgs_lv), "split" = two
+    lanes per contact row (k_pgs_sp, groups 32 / 64), "pipe" = one warp per contact-only scene with register prefetch
+    (k_pgs_pipe, group 32)."""
     os.environ["SLRBS_PGS_MODE"] = mode
     if group:
         os.environ["SLRBS_LEVEL_GROUP"] = str(group)
-    if split is not None:
-        os.environ["SLRBS_PGS_SPLIT"] = str(int(split))
+    if variant is not None:
+        os.environ["SLRBS_PGS_SPLIT"], os.environ["SLRBS_PGS_PIPE"] = VARIANTS[variant][:2]
     try:
         return context_from_oracles(oracles, **kw)
     finally:
-        os.environ.pop("SLRBS_PGS_MODE", None)
-        os.environ.pop("SLRBS_LEVEL_GROUP", None)
-        os.environ.pop("SLRBS_PGS_SPLIT", None)
+        for k in ("SLRBS_PGS_MODE", "SLRBS_LEVEL_GROUP", "SLRBS_PGS_SPLIT", "SLRBS_PGS_PIPE"):
+            os.environ.pop(k, None)
 
 
 def jittered(scene, n, **kw):
@@ -42,19 +45,20 @@ def jittered(scene, n, **kw):
     return out
 
 
-@pytest.mark.parametrize("scene,kw,n_scenes,steps,group,split", [
+@pytest.mark.parametrize("scene,kw,n_scenes,steps,group,variant", [
     ("marble_box", {}, 5, 60, 8, None), ("marble_box", {}, 3, 25, 4, None), ("marble_box", {}, 3, 25, 16, None),
-    ("marble_box", {}, 2, 25, 32, 0), ("marble_box", {}, 2, 25, 32, 1), ("marble_box", {}, 2, 25, 64, 1),
+    ("marble_box", {}, 2, 25, 32, "lv"), ("marble_box", {}, 2, 25, 32, "split"), ("marble_box", {}, 2, 25, 64, "split"),
+    ("marble_box", {}, 2, 25, 32, "pipe"), ("sphere_on_box", {}, 2, 120, 32, "pipe"), ("cylinder_on_plane", {}, 2, 80, 32, "pipe"),
     ("car", {}, 7, 80, 8, None), ("swinging_boxes", {}, 3, 60, 8, None), ("cylinder_on_plane", {}, 2, 80, 8, None),
     # joints and cylinder-plane contacts through the side-split kernel (its joint rows run on the even lanes)
-    ("car", {}, 3, 80, 32, 1), ("swinging_boxes", {}, 2, 60, 32, 1), ("cylinder_on_plane", {}, 2, 80, 64, 1),
+    ("car", {}, 3, 80, 32, "split"), ("swinging_boxes", {}, 2, 60, 32, "split"), ("cylinder_on_plane", {}, 2, 80, 64, "split"),
     ("marble_box_n", dict(nx=5, nz=4, ny=6), 3, 40, 16, None)])
-def test_level_mode_is_bit_identical_to_sequential(scene, kw, n_scenes, steps, group, split):
+def test_level_mode_is_bit_identical_to_sequential(scene, kw, n_scenes, steps, group, variant):
     oracles = jittered(scene, n_scenes, **kw)
     a = make("thread", oracles, max_contacts=1024)
-    b = make("level", oracles, group=group, split=split, max_contacts=1024)
-    if split is not None and group in (32, 64):
-        assert ("k_pgs_sp" in b.describe()) == bool(split), b.describe()
+    b = make("level", oracles, group=group, variant=variant, max_contacts=1024)
+    if variant is not None:
+        assert VARIANTS[variant][2] in b.describe(), b.describe()
     for k in range(steps):
         a.step(DT); b.step(DT)
         if k in (0, 1, steps // 2, steps - 1):
@@ -107,17 +111,17 @@ def test_krylov_in_level_mode():
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("split", [0, 1])
-def test_big_scene_variant_with_packed_accumulators(split):
+@pytest.mark.parametrize("variant", ["lv", "split", "pipe"])
+def test_big_scene_variant_with_packed_accumulators(variant):
     """Thousand-body scenes take the kernel variants with 24 B packed accumulators (9 instead of 7 scenes per SM): one
-    lane per row (k_pgs_lv<32>) or two lanes per contact row (k_pgs_sp<32>, the default). Both must still give the bits
-    of the sequential kernel."""
+    lane per row (k_pgs_lv<32>), two lanes per contact row (k_pgs_sp<32>) or the register-pipelined warp (k_pgs_pipe, the
+    default for contact-only scenes). All must still give the bits of the sequential kernel."""
     oracles = jittered("marble_box_n", 2, nx=10, nz=10, ny=10)
     for o in oracles:
         o.step(DT, 60)                                   # let contacts with the walls and floor form
     a = make("thread", oracles, max_contacts=4096)
-    b = make("level", oracles, group=32, split=split, max_contacts=4096)
-    assert ("ROWS=32" if split else "G=32") in b.describe()
+    b = make("level", oracles, group=32, variant=variant, max_contacts=4096)
+    assert VARIANTS[variant][2] in b.describe(), b.describe()
     for k in range(12):
         a.step(DT); b.step(DT)
     a.sync(); b.sync()
