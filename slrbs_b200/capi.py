@@ -21,7 +21,7 @@ SYMBOLS = [
     "slrbs_set_external_forces", "slrbs_step", "slrbs_sync", "slrbs_stage_prepare", "slrbs_stage_detect",
     "slrbs_stage_jacobians", "slrbs_stage_solve", "slrbs_stage_integrate", "slrbs_download_contact_counts",
     "slrbs_download_contacts", "slrbs_download_contact_rows", "slrbs_download_joint_rows",
-    "slrbs_download_joint_lambda", "slrbs_upload_joint_lambda", "slrbs_upload_contact_lambda", "slrbs_download_body_dyn",
+    "slrbs_download_joint_lambda", "slrbs_upload_joint_lambda", "slrbs_upload_contact_lambda", "slrbs_download_contact_schedule", "slrbs_download_body_dyn",
     "slrbs_save_state", "slrbs_restore_state", "slrbs_profile_enable", "slrbs_profile_read",
     "slrbs_timer_start", "slrbs_timer_stop", "slrbs_halo_set_local", "slrbs_halo_set_remote", "slrbs_halo_sync_local",
     "slrbs_halo_pack", "slrbs_halo_unpack", "slrbs_pile_init", "slrbs_pile_export", "slrbs_pile_rebuild",
@@ -81,6 +81,7 @@ def load_library():
     L.slrbs_download_joint_lambda.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
     L.slrbs_upload_joint_lambda.argtypes = [vp, C.c_int, C.c_int, C.c_int, fp]
     L.slrbs_upload_contact_lambda.argtypes = [vp, C.c_int, C.c_int, fp]
+    L.slrbs_download_contact_schedule.argtypes = [vp, C.c_int, C.c_int, ip, C.c_int, ip, ip]
     L.slrbs_download_body_dyn.argtypes = [vp, C.c_int, C.c_int, fp, fp, fp, fp, fp, fp]
     L.slrbs_save_state.argtypes = [vp]
     L.slrbs_restore_state.argtypes = [vp, C.c_int, C.c_int]
@@ -316,6 +317,13 @@ class Context:
     def set_joint_lambda(self, lam, scene0=0):
         lam = np.ascontiguousarray(np.asarray(lam, np.float32).reshape(-1, self.n_joints, 5))
         self._ck(self.L.slrbs_upload_joint_lambda(self.h, scene0, lam.shape[0], self.n_joints, _f(lam)))
+
+    def contact_schedule(self, scene=0):
+        """(position of every contact in the solver's row stream, end of every dependency level / colour in it)."""
+        n = int(self.contact_counts(scene, 1)[0])
+        pos = np.zeros(max(n, 1), np.int32); ends = np.zeros(max(n, 64), np.int32); nl = np.zeros(1, np.int32)
+        self._ck(self.L.slrbs_download_contact_schedule(self.h, scene, n, _i(pos), len(ends), _i(ends), _i(nl)))
+        return pos[:n], ends[:int(nl[0])]
 
     def set_contact_lambda(self, lam, scene=0):
         """Contact::lambda of one scene in detection order (what a host-side Solver subclass leaves behind)."""

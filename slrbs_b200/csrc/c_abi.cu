@@ -161,7 +161,11 @@ int solve_launch(slrbs_ctx* c, float dt)
     int sweeps = c->solver_iters;
     if (c->solver_id == 3) { launches = 1 + launch_bpp(c->v, c->solver_iters, c->mu, c->stream); sweeps = 0; }
     else if (c->solver_id != 0) { launch_krylov(c->v, c->solver_id, c->solver_iters, c->stream); sweeps = 0; launches = 2; }
-    if (c->v.level_mode) launch_pgs_level(c->v, dt, sweeps, c->mu, c->level_group, c->level_variant, c->stream);
+    if (c->v.color_mode) {
+        const cudaError_t e = (cudaError_t)launch_pgs_color(c->v, dt, sweeps, c->mu, c->stream);
+        if (e != cudaSuccess) return fail(SLRBS_E_CUDA, std::string("k_pgs_color (cooperative launch): ") + cudaGetErrorString(e));
+    }
+    else if (c->v.level_mode) launch_pgs_level(c->v, dt, sweeps, c->mu, c->level_group, c->level_variant, c->stream);
     else launch_pgs(c->v, dt, sweeps, c->mu, c->stream);
     if (c->profiling) { CU(cudaEventRecord(e1, c->stream)); c->solve_launches++; }
     return check_launch(c, launches);
@@ -178,7 +182,10 @@ int slrbs_describe(slrbs_ctx* c, char* buf, int buf_len)
 {
     if (!c || !buf || buf_len <= 0) return fail(SLRBS_E_ARG, "slrbs_describe: bad argument");
     char tmp[256];
-    if (c->v.level_mode && c->level_variant == 2)
+    if (c->v.color_mode)
+        std::snprintf(tmp, sizeof tmp, "solver=k_pgs_color (graph-coloured, all SMs, accumulators in HBM) detect=%s graph=%d",
+                      detect_variant(c->v, c->broadphase), c->use_graph);
+    else if (c->v.level_mode && c->level_variant == 2)
         std::snprintf(tmp, sizeof tmp, "solver=k_pgs_pipe (level-scheduled, 1 warp/scene, next chunk's rows prefetched into registers) detect=%s graph=%d",
                       detect_variant(c->v, c->broadphase), c->use_graph);
     else if (c->v.level_mode && c->level_variant == 1)
@@ -226,12 +233,18 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
         const char* m = std::getenv("SLRBS_PGS_MODE");
         const bool fits = level_mode_fits(max_bodies) && detect_warp_fits(max_bodies) &&
                           contact_levels_smem(max_bodies, max_contacts) <= 200 * 1024 && max_contacts < 65535;   // (level, rank) are packed 16 : 16
+        // scenes too large for one SM's shared memory, a few at a time: graph-coloured solver (pgs_color.cu; order differs from
+        // the reference, validated on the constraint residual). SLRBS_PGS_MODE=color forces it for smaller scenes.
+        const bool colorable = max_contacts < 65535 && max_contacts > 0;
         if (m && std::strcmp(m, "thread") == 0) v.level_mode = 0;
         else if (m && std::strcmp(m, "level") == 0) v.level_mode = fits ? 1 : 0;
+        else if (m && std::strcmp(m, "color") == 0) { v.level_mode = colorable ? 1 : 0; v.color_mode = v.level_mode; }
+        else if (!level_mode_fits(max_bodies) && n_scenes <= 64 && colorable) { v.level_mode = 1; v.color_mode = 1; }
         else v.level_mode = (n_scenes <= 8192 && fits) ? 1 : 0;
         const char* g = std::getenv("SLRBS_LEVEL_GROUP");
         c->level_group = level_group_size(v, g ? std::atoi(g) : 0);
-        c->level_variant = !v.level_mode ? 0 : (level_split_wanted(v, c->level_group) ? 1 : (level_pipe_wanted(v, c->level_group) ? 2 : 0));
+        c->level_variant = !v.level_mode ? 0 : (v.color_mode ? 3 : (level_split_wanted(v, c->level_group) ? 1 : (level_pipe_wanted(v, c->level_group) ? 2 : 0)));
+        if (v.color_mode) c->use_graph = 0;                     // the solver is one cooperative launch; such scenes are not launch bound
         const char* bp = std::getenv("SLRBS_BROADPHASE");
         if (bp) c->broadphase = std::atoi(bp) ? 1 : 0;
     }
@@ -248,8 +261,17 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     A(v.jrow, (size_t)JROW_FIELDS * v.NJ * bpad)
     A(v.cids, nc) A(v.cp, nc) A(v.cn, nc) A(v.crow, (size_t)CROW_FIELDS * v.NC * bpad)
     { SdfShape* tab = nullptr; A(tab, MAX_SDF_SHAPES) v.sdf_shapes = tab; }
+    if (v.color_mode) {
+        A(v.cmask, nb) A(v.cwin, nb) A(v.nclev_max, 1)
+        // scenes no single CTA can hold are detected pair-parallel over the whole GPU (detect_pairs.cu), extension pairs or not
+        if (!detect_warp_fits(max_bodies) || max_bodies > 3000) {
+            const int cap = 64 * v.NB;
+            A(v.pc_pairs, (size_t)cap * v.B) A(v.pc_count, v.B) A(v.pc_hits, v.B) A(v.pc_out, (size_t)v.NC * v.B * 6)
+            v.pc_cap = cap;
+        }
+    }
     if (v.level_mode) {
-        A(v.cpos, nc) A(v.cslot, nc) A(v.clev_end, nc + v.B) A(v.nclev, v.B) A(v.lv_last, nb)
+        A(v.cpos, nc) A(v.cslot, nc) A(v.clev_end, nc + v.B + 65 * (size_t)v.B) A(v.nclev, v.B) A(v.lv_last, nb)
         A(v.jpos, nj) A(v.jlev_end, nj + v.B) A(v.njlev, v.B)
     }
 #undef A
@@ -526,6 +548,7 @@ int slrbs_stage_detect(slrbs_ctx* c)
     CU(cudaSetDevice(c->device));
     if (!c->collisions || c->v.NC == 0) return 0;               // RigidBodySystem.cpp:77
     launch_detect(c->v, c->broadphase, c->stream);
+    if (c->v.color_mode) { launch_contact_colors(c->v, c->stream); return check_launch(c, 2 + (c->v.pc_pairs ? 2 : 0)); }
     if (c->v.level_mode) { launch_contact_levels(c->v, c->stream); return check_launch(c, 2); }
     return check_launch(c);
 }
@@ -623,6 +646,7 @@ int slrbs_sync(slrbs_ctx* c)
     CU(cudaStreamSynchronize(c->stream));
     if (flags & 1) return fail(SLRBS_E_CAPACITY, "a scene produced more contacts than max_contacts; extra contacts were dropped");
     if (flags & 4) return fail(SLRBS_E_CAPACITY_PAIRS, pairs_msg);
+    if (flags & 8) return fail(SLRBS_E_CAPACITY_ROWS, "graph colouring: a body has contacts of more than 64 colours; those contacts share the last colour (solved with a race)");
     if (flags & 2) return fail(SLRBS_E_CAPACITY_ROWS, "a scene has more constraint rows than the pivoting solver holds (solver_id 3); its impulses were left at zero");
     return 0;
 }
@@ -729,6 +753,26 @@ int slrbs_upload_joint_lambda(slrbs_ctx* c, int scene0, int ns, int n, const flo
     if ((r = check_launch(c))) return r;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+int slrbs_download_contact_schedule(slrbs_ctx* c, int scene, int max_out, int32_t* position, int max_levels, int32_t* level_end, int32_t* n_levels)
+{
+    if (!range_ok(c, scene, 1) || max_out < 0 || max_levels < 0) return fail(SLRBS_E_ARG, "slrbs_download_contact_schedule: bad argument");
+    if (!c->v.level_mode) return fail(SLRBS_E_UNSUPPORTED, "slrbs_download_contact_schedule: the thread-per-scene solver keeps the contacts in slot order");
+    CU(cudaSetDevice(c->device));
+    int total = 0, r, nl = 0;
+    if ((r = scene_count(c, c->v.ncontacts, scene, &total))) return r;
+    if (total > 0 && (r = scene_count(c, c->v.nclev, scene, &nl))) return r;
+    if (n_levels) *n_levels = nl;
+    const int n = total < max_out ? total : max_out;
+    // cpos is [NC][B], clev_end [level][B]: strided columns of one scene
+    if (n > 0 && position)
+        CU(cudaMemcpy2DAsync(position, sizeof(int), c->v.cpos + scene, sizeof(int) * (size_t)c->v.B, sizeof(int), (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    const int m = nl < max_levels ? nl : max_levels;
+    if (m > 0 && level_end)
+        CU(cudaMemcpy2DAsync(level_end, sizeof(int), c->v.clev_end + (size_t)c->v.B + scene, sizeof(int) * (size_t)c->v.B, sizeof(int), (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return total;
 }
 
 int slrbs_upload_contact_lambda(slrbs_ctx* c, int scene, int n, const float* lambda3)

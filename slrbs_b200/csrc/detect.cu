@@ -131,7 +131,7 @@ static bool use_rows_kernel(const View& v, bool grid, int H)
 // name of the kernel launch_detect() picks (same decision tree), for slrbs_describe
 const char* detect_variant(const View& v, int broadphase)
 {
-    if (v.ext_pairs && v.pc_pairs) return "k_pair_candidates + k_pair_narrow + k_pair_order";
+    if (v.pc_pairs) return "k_pair_candidates + k_pair_narrow + k_pair_order";
     const bool grid = broadphase > 0 || (broadphase < 0 && v.NB >= 128);
     const int H = grid_buckets(v.NB);
     if (use_rows_kernel(v, grid, H)) return "k_detect_rows";
@@ -148,7 +148,7 @@ const char* detect_variant(const View& v, int broadphase)
 void launch_detect(const View& v, int broadphase, cudaStream_t s)
 {
     // broadphase: 0 = off (all pairs), 1 = hashed grid, -1 = auto (grid for scenes of >= 128 bodies)
-    if (v.ext_pairs && v.pc_pairs) { launch_detect_pairs(v, s); return; }       // mixed scenes of >= 128 bodies (detect_pairs.cu)
+    if (v.pc_pairs) { launch_detect_pairs(v, s); return; }       // mixed scenes of >= 128 bodies, scenes too large for one CTA (detect_pairs.cu)
     const bool grid = broadphase > 0 || (broadphase < 0 && v.NB >= 128);
     const int H = grid_buckets(v.NB);
     // scenes of >= 128 bodies: one CTA per scene, one thread per sphere row

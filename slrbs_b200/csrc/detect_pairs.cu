@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(128) k_pair_candidates(View v, int jchunk)
     }
 }
 
+template <bool EXT>
 __global__ void __launch_bounds__(128) k_pair_narrow(View v)
 {
     const int scene = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(128) k_pair_narrow(View v)
         cj = __ldg(&v.cproxy[jj]); fj = __ldg(&v.flags[jj]);
     }
     PairOut o;
-    test_pair_warp<true>(o, v, scene, i, j, ci, fi, cj, fj, lane);
+    test_pair_warp<EXT>(o, v, scene, i, j, ci, fi, cj, fj, lane);
     if (!live || o.cnt <= 0) return;
     // pairs that touch claim a slot of the scene's hit list (any order; k_pair_order sorts them by (i, j))
     const int slot = atomicAdd(&v.pc_hits[scene], 1);
@@ -94,11 +95,16 @@ __global__ void __launch_bounds__(128) k_pair_narrow(View v)
 
 enum { ORDER_THREADS = 512 };
 
+// WIDE = false: keys and record indices sorted together in shared memory (8 B per touching pair, <= 16384 pairs).
+// WIDE = true : scenes with up to 32768 touching pairs (one large scene of ~10^4 bodies): only the keys fit (4 B each); after
+//               the sort every record finds its rank by binary search (keys are unique) and the sorted order of the
+//               record indices goes to a global scratch list (the scene's cslot row, free until the rows are ordered).
+template <bool WIDE>
 __global__ void __launch_bounds__(ORDER_THREADS) k_pair_order(View v, int sort_cap)
 {
     extern __shared__ unsigned sm_u[];
     unsigned* key = sm_u;                      // [sort_cap] (i << 16) | j
-    unsigned* val = sm_u + sort_cap;           // [sort_cap] candidate index, later the pair's output offset
+    unsigned* val = WIDE ? reinterpret_cast<unsigned*>(v.cslot + (size_t)blockIdx.x * v.NC) : sm_u + sort_cap;   // [sort_cap] record index
     __shared__ int s_warp[ORDER_THREADS / 32];
     const int scene = blockIdx.x, tid = threadIdx.x, T = ORDER_THREADS, lane = tid & 31, warp = tid >> 5;
     if (tid == 0 && v.pc_count[scene] > v.pc_cap) atomicOr(v.overflow, 4);
@@ -106,10 +112,10 @@ __global__ void __launch_bounds__(ORDER_THREADS) k_pair_order(View v, int sort_c
     int m = v.pc_hits[scene];
     const int lim = sort_cap < v.NC ? sort_cap : v.NC;
     if (m > lim) { if (tid == 0) atomicOr(v.overflow, 4); m = lim; }
-    for (int k = tid; k < m; k += T) { key[k] = (unsigned)__float_as_int(out[(size_t)k * PAIR_REC].w); val[k] = (unsigned)k; }
+    for (int k = tid; k < m; k += T) { key[k] = (unsigned)__float_as_int(out[(size_t)k * PAIR_REC].w); if (!WIDE) val[k] = (unsigned)k; }
     int P = 1;
     while (P < m) P <<= 1;
-    for (int k = m + tid; k < P; k += T) { key[k] = 0xffffffffu; val[k] = 0u; }
+    for (int k = m + tid; k < P; k += T) { key[k] = 0xffffffffu; if (!WIDE) val[k] = 0u; }
     __syncthreads();
     for (int size = 2; size <= P; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -117,10 +123,22 @@ __global__ void __launch_bounds__(ORDER_THREADS) k_pair_order(View v, int sort_c
                 const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
                 const bool up = ((lo & size) == 0);
                 const unsigned a = key[lo], b = key[hi];
-                if ((a > b) == up) { key[lo] = b; key[hi] = a; const unsigned x = val[lo]; val[lo] = val[hi]; val[hi] = x; }
+                if ((a > b) == up) {
+                    key[lo] = b; key[hi] = a;
+                    if (!WIDE) { const unsigned x = val[lo]; val[lo] = val[hi]; val[hi] = x; }
+                }
             }
             __syncthreads();
         }
+    }
+    if (WIDE) {
+        for (int k = tid; k < m; k += T) {
+            const unsigned mine = (unsigned)__float_as_int(out[(size_t)k * PAIR_REC].w);
+            int lo = 0, hi = m - 1;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] < mine) lo = mid + 1; else hi = mid; }
+            val[lo] = (unsigned)k;
+        }
+        __syncthreads();
     }
     // exclusive scan of the contact counts in sorted order
     const int per = (m + T - 1) / T;
@@ -152,16 +170,21 @@ __global__ void __launch_bounds__(ORDER_THREADS) k_pair_order(View v, int sort_c
     if (tid == T - 1) v.ncontacts[scene] = run < v.NC ? run : v.NC;
 }
 
+// touching pairs <= contacts; 16384 x 8 B = 128 KB of keys + indices, or (contexts with cslot, i.e. level / colour mode)
+// 32768 x 4 B of keys with the indices in global memory
+static bool pair_sort_wide(const View& v) { return v.NC > 16384 && v.cslot != nullptr; }
 int pair_sort_capacity(const View& v)
 {
+    const int top = pair_sort_wide(v) ? 32768 : 16384;
     int cap = 1024;
-    while (cap < v.NC && cap < 16384) cap <<= 1;               // touching pairs <= contacts; 16384 x 8 B = 128 KB
+    while (cap < v.NC && cap < top) cap <<= 1;
     return cap;
 }
 
 void init_pair_kernels()
 {
-    cudaFuncSetAttribute(k_pair_order, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    cudaFuncSetAttribute(k_pair_order<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    cudaFuncSetAttribute(k_pair_order<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
 }
 
 void launch_detect_pairs(const View& v, cudaStream_t s)
@@ -173,9 +196,11 @@ void launch_detect_pairs(const View& v, cudaStream_t s)
     split = split < 1 ? 1 : (split > 32 ? 32 : split);
     const int jchunk = (v.NB + split - 1) / split;
     k_pair_candidates<<<dim3(gb.x, gb.y, (unsigned)((v.NB + jchunk - 1) / jchunk)), 128, 0, s>>>(v, jchunk);
-    k_pair_narrow<<<gc, 128, 0, s>>>(v);
+    if (v.ext_pairs) k_pair_narrow<true><<<gc, 128, 0, s>>>(v);
+    else k_pair_narrow<false><<<gc, 128, 0, s>>>(v);
     const int sc = pair_sort_capacity(v);
-    k_pair_order<<<(unsigned)v.B, ORDER_THREADS, (size_t)sc * 8, s>>>(v, sc);
+    if (pair_sort_wide(v)) k_pair_order<true><<<(unsigned)v.B, ORDER_THREADS, (size_t)sc * 4, s>>>(v, sc);
+    else k_pair_order<false><<<(unsigned)v.B, ORDER_THREADS, (size_t)sc * 8, s>>>(v, sc);
 }
 
 }  // namespace slrbs

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) k_prepare(View v)
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)v.NB * v.B) return;
     const int scene = (int)(tid % v.B), slot = (int)(tid / v.B);
+    if (tid == 0 && v.nclev_max) *v.nclev_max = 0;
     if (slot == 0) {                                             // CollisionDetect::clear, RigidBodySystem.cpp:75
         v.ncontacts[scene] = 0;
         if (v.nclev) v.nclev[scene] = 0;                         // the level kernel walks levels, not counts: no stale rows when detection is skipped

@@ -60,6 +60,9 @@ void init_pipe_kernels();
 void launch_pgs_pipe(const View& v, float dt, int iters, float mu, cudaStream_t s);
 bool level_pipe_wanted(const View& v, int group);
 bool level_mode_fits(int max_bodies);
+// pgs_color.cu: graph-coloured solver for large scenes (accumulators in HBM, one grid barrier per colour)
+void launch_contact_colors(const View& v, cudaStream_t s);
+int  launch_pgs_color(const View& v, float dt, int iters, float mu, cudaStream_t s);   // cudaError_t of the cooperative launch
 void launch_integrate(const View& v, float dt, cudaStream_t s);
 
 void launch_upload_bodies(const View& v, int scene0, int ns, int n, const int* counts, const BodyStage& st, cudaStream_t s);

@@ -106,6 +106,10 @@ struct View {
     int    *clev_end;   // [NC+1][B] end offset of contact level l (1-based; entry 0 is 0)
     int    *nclev;      // [B] number of contact levels
     int    *lv_last;    // [NB][B] scratch: last level that touched a body
+    // graph-coloured solver for scenes too large for one SM (pgs_color.cu): colours take the place of the contact levels
+    int     color_mode;
+    unsigned long long *cmask, *cwin;   // [B][NB] colours used by a body's contacts | lowest bid among its uncoloured contacts
+    int    *nclev_max;  // [1] largest colour count over the scenes (reset by k_prepare)
 };
 
 __host__ __device__ __forceinline__ size_t at(const View& v, int slot, int scene) { return (size_t)slot * v.B + scene; }
