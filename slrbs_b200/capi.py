@@ -24,7 +24,7 @@ SYMBOLS = [
     "slrbs_download_joint_lambda", "slrbs_upload_joint_lambda", "slrbs_upload_contact_lambda", "slrbs_download_contact_schedule", "slrbs_download_body_dyn",
     "slrbs_save_state", "slrbs_restore_state", "slrbs_profile_enable", "slrbs_profile_read",
     "slrbs_timer_start", "slrbs_timer_stop", "slrbs_halo_set_local", "slrbs_halo_set_remote", "slrbs_halo_sync_local",
-    "slrbs_halo_pack", "slrbs_halo_unpack", "slrbs_pile_init", "slrbs_pile_export", "slrbs_pile_rebuild",
+    "slrbs_halo_pack", "slrbs_halo_unpack", "slrbs_stream", "slrbs_device", "slrbs_pile_init", "slrbs_pile_export", "slrbs_pile_rebuild",
     "slrbs_pile_requests", "slrbs_pile_set_send", "slrbs_pile_scene_keys", "slrbs_set_extensions",
     "slrbs_sdf_build", "slrbs_sdf_add_shape",
 ]
@@ -90,6 +90,9 @@ def load_library():
     L.slrbs_halo_set_remote.argtypes = [vp, C.c_int, ip, C.c_int, ip]
     L.slrbs_halo_sync_local.argtypes = [vp]
     L.slrbs_halo_pack.argtypes = [vp, C.c_void_p]
+    L.slrbs_stream.argtypes = [vp]
+    L.slrbs_stream.restype = C.c_void_p
+    L.slrbs_device.argtypes = [vp]
     L.slrbs_halo_unpack.argtypes = [vp, C.c_void_p]
     L.slrbs_pile_init.argtypes = [vp, C.c_int, fp, fp, fp, C.c_float, C.c_float, ip, C.c_int, C.c_int, C.c_int, fp]
     L.slrbs_pile_export.argtypes = [vp, C.c_void_p, C.c_void_p]

@@ -870,6 +870,9 @@ int slrbs_halo_sync_local(slrbs_ctx* c)
     return check_launch(c);
 }
 
+void* slrbs_stream(slrbs_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int slrbs_device(slrbs_ctx* c) { return c ? c->device : -1; }
+
 int slrbs_halo_pack(slrbs_ctx* c, void* device_buffer)
 {
     if (!c || (c->n_halo_send > 0 && !device_buffer)) return fail(SLRBS_E_ARG, "slrbs_halo_pack: bad argument");

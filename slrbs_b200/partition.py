@@ -18,6 +18,8 @@ on penetration / residual against a single-scene run, not on trajectories (north
 The partition itself (build_partition) is pure numpy and identical on every rank, so ranks need not
 exchange index lists: each derives its own send / receive lists from the same global picture.
 """
+import os
+
 import numpy as np
 
 from .capi import Context, SlrbsError, SPHERE
@@ -386,13 +388,17 @@ class DevicePile:
     device copy. K follows the fastest body so that nothing can cross the halo between two rebuilds."""
 
     def __init__(self, x, radius, mass, fixed_bodies, block=8.0, dt=0.01, rank=0, world=1, device=0, slack=0.5,
-                 contact_factor=4, mu=0.8, iters=10, rebuild_every=0, max_bodies=0):
+                 contact_factor=4, mu=0.8, iters=10, rebuild_every=0, max_bodies=0, dist=None, native=None):
+        """dist: the collectives (default torch.distributed; tests pass an EmulatedGroup handle to run several ranks on one
+        GPU). native: a NativeHaloComm (libslrbs_pile.so) -- the per-step halo refresh then runs pack -> ncclSend/ncclRecv ->
+        unpack on the context's own stream with no host synchronisation."""
         import torch
         self.torch = torch
-        self.dist = None
-        if world > 1:
-            import torch.distributed as dist
-            self.dist = dist
+        self.dist = dist
+        self.native = native
+        if world > 1 and dist is None:
+            import torch.distributed as tdist
+            self.dist = tdist
         self.n = int(x.shape[0])
         self.radius = np.ascontiguousarray(radius, np.float32); self.mass = np.ascontiguousarray(mass, np.float32)
         self.block, self.dt, self.slack = float(block), float(dt), float(slack)
@@ -469,6 +475,9 @@ class DevicePile:
             self.sbuf = torch.empty(max(sum(give), 1) * STATE_W, dtype=torch.float32, device=dev)
             self.rbuf = torch.empty(max(nl + nr, 1) * STATE_W, dtype=torch.float32, device=dev)
             self.n_give, self.n_ask = sum(give), nl + nr
+            # what goes to / comes from the left and the right neighbour (slabs along x), for the native exchange
+            self.give_lr = (give[self.rank - 1] if self.rank > 0 else 0, give[self.rank + 1] if self.rank < self.world - 1 else 0)
+            self.ask_lr = (nl, nr)
         if self.fixed_K > 0:
             self.K = self.fixed_K
         else:
@@ -495,7 +504,10 @@ class DevicePile:
                 self._rebuild()
             self.ctx.step(self.dt, 1)
             self.ctx.halo_sync_local()
-            if self.world > 1:
+            if self.world > 1 and self.native is not None:
+                # stream-ordered: pack -> grouped ncclSend / ncclRecv with the two neighbours -> unpack, all on the context's stream
+                self.native.halo_exchange(self.ctx, self.sbuf.data_ptr(), self.rbuf.data_ptr(), self.give_lr, self.ask_lr)
+            elif self.world > 1:
                 self.ctx.halo_pack(self.sbuf.data_ptr())
                 self.ctx.sync()
                 self.dist.all_to_all_single(self.rbuf[: self.n_ask * STATE_W], self.sbuf[: self.n_give * STATE_W], self.ask13, self.give13)
@@ -539,6 +551,114 @@ class DevicePile:
     def close(self):
         if self.ctx is not None:
             self.ctx.close(); self.ctx = None
+
+
+class EmulatedGroup:
+    """Several ranks of a DevicePile on ONE GPU in ONE process, one Python thread per rank: the subset of
+    torch.distributed the pile uses (all_reduce, all_to_all_single), done with device copies between the ranks' tensors
+    at thread barriers. Lets the whole multi-rank path -- exported state table, requested-id protocol, packed halo
+    refresh, rebuild -- run and be checked on a one-GPU box; NCCL itself refuses two ranks on one device."""
+
+    class ReduceOp:
+        SUM, MAX = 0, 1
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+        self.result = None
+
+    def handle(self, rank):
+        return _EmulatedDist(self, rank)
+
+
+class _EmulatedDist:
+    def __init__(self, group, rank):
+        self.g, self.rank, self.ReduceOp = group, rank, EmulatedGroup.ReduceOp
+
+    def all_reduce(self, t, op=EmulatedGroup.ReduceOp.SUM):
+        import torch
+        g = self.g
+        torch.cuda.synchronize()
+        g.slots[self.rank] = t
+        g.barrier.wait()
+        if self.rank == 0:
+            acc = g.slots[0].clone()
+            for other in g.slots[1:]:
+                acc = torch.maximum(acc, other) if op == EmulatedGroup.ReduceOp.MAX else acc + other
+            g.result = acc
+            torch.cuda.synchronize()
+        g.barrier.wait()
+        t.copy_(g.result)
+        torch.cuda.synchronize()
+        g.barrier.wait()
+
+    def all_to_all_single(self, out, inp, out_splits=None, in_splits=None):
+        import torch
+        g, w = self.g, self.g.world
+        if in_splits is None:
+            in_splits = [inp.numel() // w] * w
+        if out_splits is None:
+            out_splits = [out.numel() // w] * w
+        torch.cuda.synchronize()
+        g.slots[self.rank] = (inp, list(in_splits))
+        g.barrier.wait()
+        o = 0
+        for src in range(w):
+            sin, ssp = g.slots[src]
+            a = sum(ssp[: self.rank]); n = ssp[self.rank]
+            assert n == out_splits[src], (self.rank, src, n, out_splits[src])
+            if n:
+                out[o:o + n].copy_(sin[a:a + n])
+            o += n
+        torch.cuda.synchronize()
+        g.barrier.wait()
+
+
+class NativeHaloComm:
+    """libslrbs_pile.so: NCCL point-to-point between slab neighbours, issued on the simulation context's own stream.
+    The 128-byte NCCL unique id is made on rank 0 and handed to the other ranks by the caller (any side channel;
+    run_partition_multi.py broadcasts it with torch.distributed)."""
+
+    def __init__(self, rank, world, device, unique_id):
+        import ctypes as C
+        from .capi import load_library
+        load_library()
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libslrbs_pile.so")
+        if not os.path.exists(path):
+            raise SlrbsError(f"{path} is missing: build it with `make -C slrbs_b200/csrc pile`")
+        self.L = C.CDLL(path)
+        self.L.slrbs_pile_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_char_p]
+        self.L.slrbs_pile_comm_halo_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        self.L.slrbs_pile_comm_destroy.argtypes = [C.c_void_p]
+        self.L.slrbs_pile_comm_last_error.restype = C.c_char_p
+        self.h = C.c_void_p()
+        if self.L.slrbs_pile_comm_create(C.byref(self.h), rank, world, device, bytes(unique_id)) != 0:
+            raise SlrbsError(self.L.slrbs_pile_comm_last_error().decode())
+
+    @staticmethod
+    def unique_id():
+        import ctypes as C
+        from .capi import load_library
+        load_library()
+        L = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libslrbs_pile.so"))
+        buf = C.create_string_buffer(128)
+        if L.slrbs_pile_comm_unique_id(buf) != 0:
+            raise SlrbsError("ncclGetUniqueId failed")
+        return buf.raw
+
+    def halo_exchange(self, ctx, send_ptr, recv_ptr, give_lr, ask_lr):
+        import ctypes as C
+        rc = self.L.slrbs_pile_comm_halo_exchange(self.h, ctx.h, C.c_void_p(send_ptr), C.c_void_p(recv_ptr),
+                                                  int(give_lr[0]), int(give_lr[1]), int(ask_lr[0]), int(ask_lr[1]))
+        if rc != 0:
+            raise SlrbsError(self.L.slrbs_pile_comm_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.slrbs_pile_comm_destroy(self.h)
+            self.h = None
 
 
 class TorchComm:

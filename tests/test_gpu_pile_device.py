@@ -16,7 +16,7 @@ import sys
 import numpy as np
 import pytest
 
-from slrbs_b200.partition import DevicePile, PartitionedPile, grid_partition_numpy, sphere_pile
+from slrbs_b200.partition import DevicePile, EmulatedGroup, PartitionedPile, grid_partition_numpy, sphere_pile
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -88,6 +88,56 @@ def test_cut_pile_matches_single_scene_and_is_deterministic():
     again.step(120)
     np.testing.assert_array_equal(again.gather_state(), a)
     again.close()
+
+
+def _run_ranks(world, fn):
+    """fn(rank) in one thread per rank; re-raises the first failure."""
+    import threading
+    out, err = [None] * world, []
+
+    def body(r):
+        try:
+            out[r] = fn(r)
+        except BaseException as e:          # noqa: BLE001 - reported by the main thread
+            err.append(e)
+    th = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    if err:
+        raise err[0]
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_rank_path_emulated_on_one_gpu(world):
+    """The whole multi-rank path on ONE GPU: `world` ranks of the same pile, one thread and one device context each, the
+    collectives replaced by device copies at thread barriers (EmulatedGroup). Exercises what the 2-GPU test exercises --
+    slab ownership, exported state table summed over the ranks, requested-id protocol with the slab neighbours,
+    slrbs_halo_pack -> exchange -> slrbs_halo_unpack every step, re-partition with bodies migrating between ranks -- and,
+    because the blocks and their halo copies are the same whoever owns them, must reproduce the one-rank run bit for bit."""
+    x, r, m, fixed = sphere_pile(18, 6, 8, jitter=0.05, seed=11)
+    one = DevicePile(x, r, m, fixed, block=4.0)
+    one.step(45)
+    ref = one.gather_state()
+    assert one.stats["rebuilds"] >= 3
+    one.close()
+    group = EmulatedGroup(world)
+
+    def run(rank):
+        p = DevicePile(x, r, m, fixed, block=4.0, rank=rank, world=world, dist=group.handle(rank))
+        assert p.B > 0
+        p.step(45)
+        st = p.gather_state()
+        stats = dict(p.stats)
+        p.close()
+        return st, stats
+    res = _run_ranks(world, run)
+    assert sum(s["owned"] for _, s in res) == x.shape[0]
+    assert all(s["remote_halos"] > 0 for _, s in res), [s["remote_halos"] for _, s in res]
+    for st, _ in res:
+        np.testing.assert_array_equal(st, ref)
 
 
 def test_two_gpus_device_rebuild_and_nccl_halos():
