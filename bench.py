@@ -54,7 +54,12 @@ WORKLOADS = {
     # BASELINE configs[0] "box-stack on plane": NOT a reference scene and needs box-box / box-plane contacts, which the
     # reference does not have -> the extension pairs (slrbs_set_extensions), no reference parity for this workload
     "box_stack":      ("box_stack", (5, 0, 0), 32, 262144, 50, 0.0),
+    # ONE scene no SM can hold (9605 bodies, ~28 000 touching pairs): pair-parallel detection over the whole GPU and the
+    # graph-coloured solver (pgs_color.cu); order differs from the reference, validated on the residual (tests/test_gpu_color.py)
+    "big_scene":      ("marble_box_n", (20, 20, 24), 40000, 1, 100, 0.01),
 }
+# --workload pile_1m / pile: one pile cut into blocks over the ranks (slrbs_b200/partition.py), handled by run_pile()
+PILE_DIMS = {"pile_1m": (100, 100, 100), "pile": (48, 24, 48)}
 
 
 SOLVER_SOURCES = ("pgs_split.cu", "pgs_level.cu", "pgs_level.cuh", "pgs_math.cuh", "layout.cuh", "kernels.cu")
@@ -313,7 +318,7 @@ def run_ours(args):
                         traffic_note = "stale: the recorded capture was taken on different solver sources"
         except Exception:
             pass
-    kernel = "k_pgs_sp" if "k_pgs_sp" in variants else ("k_pgs_lv" if "k_pgs_lv" in variants else "k_pgs")
+    kernel = next((k for k in ("k_pgs_pipe", "k_pgs_color", "k_pgs_sp", "k_pgs_lv") if k in variants), "k_pgs")
     cfg = common_config(args.workload, B, nb, nj)
     out = {
         "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": args.steps,
@@ -348,6 +353,109 @@ def run_ours(args):
     print(json.dumps(out), flush=True)
     if ctx is not None:
         ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_pile(args):
+    """One pile of touching spheres in a five-box container, cut into blocks; ranks own slabs of block columns. Per step:
+    slrbs_step on every block scene, local halo copy, packed halo exchange with the slab neighbours (NCCL point-to-point on
+    the context's stream, libslrbs_pile.so); every K steps a device-side re-partition (all-reduced state table)."""
+    import torch
+    import torch.distributed as dist
+    from slrbs_b200.partition import DevicePile, NativeHaloComm, sphere_pile
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    binding = bind_rank_to_cores(local, world)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dims = PILE_DIMS[args.workload]
+    x, r, m, fixed = sphere_pile(*dims)
+    native = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(NativeHaloComm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        native = NativeHaloComm(rank, world, local, bytes(idt.cpu().numpy().tobytes()))
+    pile = DevicePile(x, r, m, fixed, block=8.0, rank=rank, world=world, device=local, native=native)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pile.step(max(args.warmup, 3))
+    pile.ctx.sync()
+    r0, s0 = pile.stats["rebuilds"], pile.stats.get("steady_rebuild_s", 0.0)
+    sampler = ClockSampler(local) if rank == 0 else None
+    pile.ctx.profile_read(True)
+    barrier()
+    t0 = time.perf_counter()
+    pile.ctx.timer_start()
+    pile.step(args.steps)
+    ms = pile.ctx.timer_stop()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = int(pile.ctx.profile_read(True)["total_launches"])
+    rebuilds, rebuild_ms = pile.stats["rebuilds"] - r0, (pile.stats.get("steady_rebuild_s", 0.0) - s0) * 1e3
+    # profiled pass for the solver share (per-launch events)
+    psteps = 5
+    pile.ctx.profile_enable(True); pile.ctx.profile_read(True)
+    pile.step(psteps); pile.ctx.sync()
+    prof = pile.ctx.profile_read(True)
+    pile.ctx.profile_enable(False)
+    # end to end: every step also brings the owners' states to pinned host memory (13 floats per body)
+    host = torch.empty((x.shape[0], 13), dtype=torch.float32, pin_memory=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pile.step(1)
+        pile.table.zero_(); pile.vmax2.zero_(); torch.cuda.synchronize(local)
+        pile.ctx.pile_export(pile.table.data_ptr(), pile.vmax2.data_ptr()); pile.ctx.sync()
+        host.copy_(pile.table.view(-1, 13), non_blocking=True); torch.cuda.synchronize(local)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    from slrbs_b200 import sharding
+    ms, wall_ms, e2e_ms = sharding.reduce_over_ranks([ms, wall_ms, e2e_ms], "max")
+    variants = pile.ctx.describe()
+    stats = dict(pile.stats)
+    pen = pile.max_penetration()
+    if rank == 0:
+        n = int(x.shape[0])
+        peak, peak_src = load_peaks()
+        solve_ms, nl = float(prof["solve_ms"]), max(float(prof["solve_launches"]), 1.0)
+        alg = BYTES_PER_CONTACT_VISIT * float(prof["contact_visits"])
+        achieved = alg / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+        out = {
+            "metric": "body_steps_per_sec", "value": n * args.steps / (ms * 1e-3), "unit": "body-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: one pile of {dims[0]}x{dims[1]}x{dims[2]} = {n} spheres in a five-box container",
+                       "bodies": n, "dt": DT, "solver": "Box-PGS inside a block (reference row order), block-Jacobi across block faces",
+                       "solver_iters": SOLVER_ITERS, "mu": MU, "block_edge": 8.0,
+                       "l2": "no flush: the row records of all block scenes exceed the 126 MB L2"},
+            "details": {"kernels": variants, "host_binding": binding, "stats": stats, "wall_ms_per_step": wall_ms / args.steps,
+                        "rebuilds_in_timed_region": rebuilds, "rebuild_ms_total": rebuild_ms,
+                        "halo_exchange": "ncclSend/ncclRecv with the slab neighbours on the context stream (libslrbs_pile.so)" if native else "local indexed copy only (one rank)",
+                        "max_penetration": pen,
+                        "phases_ms_per_step": {"solver": solve_ms / psteps, "rebuild": rebuild_ms / args.steps,
+                                               "other_kernels_and_exchange": max(ms / args.steps - solve_ms / psteps - rebuild_ms / args.steps, 0.0)}},
+            "roofline": {"kernel": next((k for k in ("k_pgs_pipe", "k_pgs_color", "k_pgs_sp", "k_pgs_lv") if k in variants), "k_pgs"),
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "frac_dram": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg / nl,
+                         "ms_per_launch": solve_ms / nl},
+            "e2e": {"value": n * e2e_steps / (e2e_ms * 1e-3), "unit": "body-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": int(n * 13 * 4), "steps": e2e_steps,
+                    "payload": "every step downloads x,q,v,omega of every body from its owner rank; nothing is uploaded (the pile has no per-step host input)"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    pile.close()
+    if native is not None:
+        native.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -465,11 +573,17 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="marble_box_1k", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="marble_box_1k", choices=sorted(WORKLOADS) + sorted(PILE_DIMS))
     ap.add_argument("--scenes", type=int, default=0, help="scenes per GPU (default: per workload)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload in PILE_DIMS:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference's all-pairs loop cannot run a pile of this size "
+                              "(5e11 pair tests per step for 1e6 spheres); see cpu_baseline.extrapolated in the other arm"}), flush=True)
+        else:
+            run_pile(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -81,14 +81,17 @@ __device__ __forceinline__ void bpp_put_row(const BppRows& R, int k, const float
     }
 }
 
-__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+__device__ __forceinline__ size_t tri(int i, int j) { return (size_t)i * (i + 1) / 2 + j; }
 
 // ONE_WARP: a scene of at most 64 rows is solved by a single warp (32-thread CTA), every barrier a __syncwarp
 template <bool ONE_WARP>
 __device__ __forceinline__ void bpp_sync() { if (ONE_WARP) __syncwarp(); else __syncthreads(); }
 
-template <bool ONE_WARP>
-__global__ void k_bpp(View v, int maxit, float mu, int cap, int min_rows, int flag_overflow)
+// BIG: scenes beyond BPP_MAX_ROWS rows (the reference's own marble box has 1107): the row records and the packed Cholesky
+// triangle of the free set live in a per-scene global scratch area (L2 resident: 2.5 MB for 1107 rows) instead of shared
+// memory, which then only holds the per-row vectors; same code, same operation order, one 1024-thread CTA per scene.
+template <bool ONE_WARP, bool BIG = false>
+__global__ void k_bpp(View v, int maxit, float mu, int cap, int min_rows, int flag_overflow, float* scratch = nullptr, size_t scratch_stride = 0)
 {
     extern __shared__ float sm[];
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
@@ -96,13 +99,14 @@ __global__ void k_bpp(View v, int maxit, float mu, int cap, int min_rows, int fl
     const int nj = v.njoints[scene], nc = v.ncontacts[scene];
     BppRows R;
     R.n = cap;
-    R.Rf = sm;
-    R.b0 = (int*)(sm + bpp_rec_words(cap, ONE_WARP)); R.b1 = R.b0 + cap; R.kind = R.b1 + cap; R.parent = R.kind + cap;
+    float* const gs = BIG ? scratch + (size_t)blockIdx.x * scratch_stride : nullptr;
+    R.Rf = BIG ? gs : sm;
+    R.b0 = (int*)(sm + (BIG ? 0 : bpp_rec_words(cap, ONE_WARP))); R.b1 = R.b0 + cap; R.kind = R.b1 + cap; R.parent = R.kind + cap;
     R.rhs = (float*)(R.parent + cap);
     float* lam = R.rhs + cap; float* y = lam + cap; float* hi = y + cap; float* col = hi + cap;
     int* state = (int*)(col + cap); int* F = state + cap; int* move = F + cap;
     int* ctl = move + cap;                        // [0] ninf [1] last [2] shift bits [3] nf
-    float* M = ONE_WARP ? sm : (float*)(ctl + 8);
+    float* M = BIG ? gs + (size_t)BPP_ROW_FLOATS * cap : (ONE_WARP ? sm : (float*)(ctl + 8));
     const float* Ad = (const float*)(ctl + 8);    // one-warp variant: dense A, row stride ld
     const int ld = cap | 1;
     auto entry = [&](int i, int j) { return ONE_WARP ? Ad[i * ld + j] : bpp_entry(R, i, j); };
@@ -239,9 +243,9 @@ __global__ void k_bpp(View v, int maxit, float mu, int cap, int min_rows, int fl
         // Row c's diagonal slot keeps A(c, c); the pivots live in col[].
         for (int c = 0; c < nf; ++c) {
             bpp_sync<ONE_WARP>();
-            const int rc = tri(c, 0);
+            const size_t rc = tri(c, 0);
             for (int i = c + tid; i <= nf; i += T) {
-                const int ri = tri(i, 0);
+                const size_t ri = tri(i, 0);
                 float acc = M[ri + c], dc = M[rc + c];
                 for (int j = 0; j < c; ++j) { const float lc = M[rc + j]; acc -= M[ri + j] * lc; dc -= lc * lc; }
                 dc = sqrtf(dc > 1e-12f ? dc : 1e-12f);
@@ -336,24 +340,37 @@ int bpp_row_capacity(const View& v)
     return (int)(want < BPP_MAX_ROWS ? (want > 0 ? want : 1) : BPP_MAX_ROWS);
 }
 
+// rows the global-scratch variant holds for this context (0: not needed or too much scratch), floats of scratch per scene
+int bpp_big_capacity(const View& v)
+{
+    const long want = 3L * v.NC + 5L * v.NJ;
+    if (want <= BPP_MAX_ROWS) return 0;
+    const long cap = want < BPP_BIG_MAX_ROWS ? want : BPP_BIG_MAX_ROWS;
+    return (double)bpp_big_scratch_floats((int)cap) * 4.0 * v.B <= 8e9 ? (int)cap : 0;
+}
+size_t bpp_big_scratch_floats(int cap) { return (size_t)BPP_ROW_FLOATS * cap + bpp_tri_words(cap + 1); }
+static size_t bpp_big_smem_words(int cap) { return (size_t)(BPP_ROW_WORDS - BPP_ROW_FLOATS) * cap + 8; }
+
 void init_bpp_kernel()
 {
     cudaFuncSetAttribute(k_bpp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bpp_smem_words(BPP_MAX_ROWS, false) * sizeof(float)));
     cudaFuncSetAttribute(k_bpp<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_bpp<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_bpp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bpp_big_smem_words(BPP_BIG_MAX_ROWS) * sizeof(float)));
 }
 
 // One launch per size class; every launch covers all scenes and a scene is solved by the smallest class that holds
 // its rows (a CTA of another class exits at once), so shared memory per CTA -- and with it the number of scenes
 // resident on an SM -- follows the scene's size rather than the context's capacity.
-int launch_bpp(const View& v, int iters, float mu, cudaStream_t s)
+int launch_bpp(const View& v, int iters, float mu, float* big_scratch, cudaStream_t s)
 {
     static const int classes[] = { 32, 48, BPP_WARP_ROWS, 96, 144, 208, BPP_MAX_ROWS };
     const int cap = bpp_row_capacity(v);
+    const int big = big_scratch ? bpp_big_capacity(v) : 0;
     int prev = 0, launches = 0;
     for (int cls : classes) {
         const int c = cls < cap ? cls : cap;
-        const int min_rows = prev ? prev + 1 : 0, last = c == cap;
+        const int min_rows = prev ? prev + 1 : 0, last = c == cap && !big;        // the last class flags scenes nobody holds
         if (c <= BPP_WARP_ROWS)
             k_bpp<true><<<(unsigned)v.B, 32, bpp_smem_words(c, true) * sizeof(float), s>>>(v, 5 * iters, mu, c, min_rows, last);
         else
@@ -361,7 +378,12 @@ int launch_bpp(const View& v, int iters, float mu, cudaStream_t s)
                 v, 5 * iters, mu, c, min_rows, last);
         ++launches;
         prev = c;
-        if (last) break;
+        if (c == cap) break;
+    }
+    if (big) {
+        k_bpp<false, true><<<(unsigned)v.B, 1024, bpp_big_smem_words(big) * sizeof(float), s>>>(v, 5 * iters, mu, big, BPP_MAX_ROWS + 1, 1, big_scratch,
+                                                                                           bpp_big_scratch_floats(big));
+        ++launches;
     }
     return launches;
 }

@@ -35,6 +35,7 @@ struct slrbs_ctx {
     float mu = 0.8f;
     int solver_id = 0, solver_iters = 10, collisions = 1;
     int level_group = 8;                        // lanes per scene of the level-scheduled solver
+    float* bpp_scratch = nullptr;               // global scratch of the pivoting solver for scenes beyond 288 rows (allocated on first use)
     int level_variant = 0;                      // 0 k_pgs_lv, 1 k_pgs_sp (two lanes per contact row, opt-in), 2 k_pgs_pipe (contact-only scenes, pipelined)
     int broadphase = -1;                        // -1 auto, 0 all pairs, 1 hashed grid (SLRBS_BROADPHASE)
     bool joints_dirty = true;                   // joint levels must be recomputed (bodies / joints uploaded)
@@ -159,7 +160,11 @@ int solve_launch(slrbs_ctx* c, float dt)
     // 1, 2 joint-only Krylov solves; 3 block principal pivoting over joints and contacts (extension)
     int launches = 1;
     int sweeps = c->solver_iters;
-    if (c->solver_id == 3) { launches = 1 + launch_bpp(c->v, c->solver_iters, c->mu, c->stream); sweeps = 0; }
+    if (c->solver_id == 3) {
+        const int big = bpp_big_capacity(c->v);
+        if (big && !c->bpp_scratch) { int r = dalloc(c, &c->bpp_scratch, bpp_big_scratch_floats(big) * (size_t)c->v.B); if (r) return r; }
+        launches = 1 + launch_bpp(c->v, c->solver_iters, c->mu, c->bpp_scratch, c->stream); sweeps = 0;
+    }
     else if (c->solver_id != 0) { launch_krylov(c->v, c->solver_id, c->solver_iters, c->stream); sweeps = 0; launches = 2; }
     if (c->v.color_mode) {
         const cudaError_t e = (cudaError_t)launch_pgs_color(c->v, dt, sweeps, c->mu, c->stream);
@@ -598,6 +603,7 @@ int slrbs_step(slrbs_ctx* c, float dt, int n_steps)
     // Anything that is not a plain launch on the stream happens before the capture.
     if (c->v.level_mode && c->joints_dirty) { launch_joint_levels(c->v, c->stream); c->joints_dirty = false; if ((r = check_launch(c))) return r; }
     if ((c->solver_id == 1 || c->solver_id == 2) && c->v.NJ > 0 && !c->v.kry) { if ((r = dalloc(c, &c->v.kry, (size_t)7 * 5 * c->v.NJ * c->v.B))) return r; }
+    if (c->solver_id == 3 && !c->bpp_scratch) { const int big = bpp_big_capacity(c->v); if (big && (r = dalloc(c, &c->bpp_scratch, bpp_big_scratch_floats(big) * (size_t)c->v.B))) return r; }
     const bool same = c->graph && c->gsig.dt == dt && c->gsig.mu == c->mu && c->gsig.iters == c->solver_iters &&
                       c->gsig.solver == c->solver_id && c->gsig.collisions == c->collisions && c->gsig.has_ext == c->v.has_ext;
     if (!same) {

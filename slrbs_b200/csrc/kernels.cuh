@@ -38,10 +38,13 @@ void launch_joint_rows(const View& v, float h, cudaStream_t s);
 void launch_pgs(const View& v, float dt, int iters, float mu, cudaStream_t s);
 void launch_krylov(const View& v, int solver_id, int iters, cudaStream_t s);
 // bpp.cu: block principal pivoting (solverId 3, extension); one CTA per scene, at most BPP_MAX_ROWS scalar rows per scene
-enum { BPP_MAX_ROWS = 288 };
+// (shared memory); scenes beyond that run from a global scratch area, up to BPP_BIG_MAX_ROWS
+enum { BPP_MAX_ROWS = 288, BPP_BIG_MAX_ROWS = 4096 };
 void init_bpp_kernel();
 int  bpp_row_capacity(const View& v);
-int  launch_bpp(const View& v, int iters, float mu, cudaStream_t s);   // returns the number of launches
+int  bpp_big_capacity(const View& v);
+size_t bpp_big_scratch_floats(int cap);
+int  launch_bpp(const View& v, int iters, float mu, float* big_scratch, cudaStream_t s);   // returns the number of launches
 // sdf.cu (extension): signed-distance grid of a closed triangle mesh, all pointers on the device
 void launch_build_sdf(const float* verts, int nt, const int* tris, int nx, int ny, int nz, float ox, float oy, float oz, float cell,
                       float* out, cudaStream_t s);

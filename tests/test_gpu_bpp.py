@@ -88,11 +88,32 @@ def test_bpp_trajectories_follow_the_restatement(name, kw, ext, nc):
     ctx.close()
 
 
-def test_bpp_refuses_a_scene_with_more_rows_than_it_holds():
-    o = Oracle("marble_box")                       # 369+ contacts = 1100+ rows > 288
-    ctx = context_from_oracles([o], max_contacts=1024)
+def test_bpp_solves_the_reference_marble_box_from_global_scratch():
+    """The reference's own marble box has 369+ contacts = 1100+ scalar rows, beyond what shared memory holds (288): such scenes
+    run the same algorithm with the row records and the Cholesky triangle in a global scratch area (k_bpp<BIG>)."""
+    o = Oracle("marble_box"); o.set_params(solver_id=3, solver_iter=10)
+    o.step(DT, 3)
+    snap = Oracle("marble_box"); snap.set_params(solver_id=3, solver_iter=10); snap.set_state(**o.state())
+    ctx = context_from_oracles([snap], max_contacts=1024)
     ctx.set_params(solver_id=3, solver_iters=10)
-    ctx.step(DT, 80)
+    ctx.stage_prepare(); ctx.stage_detect(); ctx.stage_jacobians(DT); ctx.stage_solve(DT); ctx.sync()
+    snap.stage_prepare(); snap.stage_detect(); snap.stage_jacobians(); snap.stage_solve(DT)
+    assert snap.n_contacts == ctx.contact_counts()[0] and 3 * snap.n_contacts > 288
+    assert snap.blcp_residual(DT) < 1e-4
+    ref = snap.contacts()["lam"]
+    np.testing.assert_allclose(ctx.contacts(0)["lam"], ref, atol=5e-4 * max(1.0, float(np.abs(ref).max())), rtol=0)
+    # and a short trajectory stays with the restatement's
+    ctx.stage_integrate(DT); snap.stage_scatter(DT); snap.stage_integrate(DT)
+    ctx.step(DT, 10); ctx.sync(); snap.step(DT, 10)
+    np.testing.assert_allclose(ctx.download_state()["x"][0], snap.state()["x"], atol=5e-3)
+    ctx.close()
+
+
+def test_bpp_refuses_a_scene_with_more_rows_than_it_holds():
+    o = Oracle("marble_box_n", nx=12, nz=12, ny=16)      # ~7000 contacts = 21 000 rows > 4096
+    ctx = context_from_oracles([o], max_contacts=8192)
+    ctx.set_params(solver_id=3, solver_iters=10)
+    ctx.step(DT, 2)
     with pytest.raises(SlrbsError):
         ctx.sync()
     ctx.set_params(solver_id=0, solver_iters=10)       # reported once: the context is usable again with Box-PGS
