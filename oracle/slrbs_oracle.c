@@ -954,6 +954,129 @@ static void ext_sdf_sdf(orc_system* s, int i0, int i1)
     sdf_emit(s, i0, i1, &H);
 }
 
+/* ---- EXTENSION: cylinder pairs the reference ignores (sphere-cylinder, cylinder-box, cylinder-cylinder, mesh-cylinder;
+ * CollisionDetect.cpp:45-73 only knows cylinder-plane). No reference behaviour exists: a finite cylinder (axis = local y,
+ * Geometry.h:79-106) is an analytic signed-distance function plus CYL_SAMPLES surface points -- three rings of 16 (both
+ * rims and mid height) and the two cap centres -- and the pairs reuse the mesh machinery: sample points of one shape in
+ * the distance field of the other, at most the four deepest per pair, the normal of the deepest. */
+enum { CYL_RING = 16, CYL_SAMPLES = 50 };
+static const float CYL_COS[CYL_RING] = { 1.0f, 0.9238795f, 0.70710677f, 0.38268343f, 0.0f, -0.38268343f, -0.70710677f, -0.9238795f,
+                                         -1.0f, -0.9238795f, -0.70710677f, -0.38268343f, 0.0f, 0.38268343f, 0.70710677f, 0.9238795f };
+static const float CYL_SIN[CYL_RING] = { 0.0f, 0.38268343f, 0.70710677f, 0.9238795f, 1.0f, 0.9238795f, 0.70710677f, 0.38268343f,
+                                         0.0f, -0.38268343f, -0.70710677f, -0.9238795f, -1.0f, -0.9238795f, -0.70710677f, -0.38268343f };
+static v3 cyl_sample(int k, float h2, float r)
+{
+    if (k >= 3 * CYL_RING) return V3(0.f, k == 3 * CYL_RING ? -h2 : h2, 0.f);
+    const int ring = k / CYL_RING, a = k - ring * CYL_RING;
+    return V3(r * CYL_COS[a], ring == 0 ? -h2 : (ring == 1 ? 0.f : h2), r * CYL_SIN[a]);
+}
+/* signed distance and outward unit normal of the cylinder (half height h2, radius r) at the cylinder-frame point c */
+static float cyl_sdf(v3 c, float h2, float r, v3* n)
+{
+    const float rho = sqrtf(c.x * c.x + c.z * c.z);
+    const v3 radial = rho > 0.f ? V3(c.x / rho, 0.f, c.z / rho) : V3(1.f, 0.f, 0.f);
+    const float dr = rho - r, dy = fabsf(c.y) - h2, sy = c.y < 0.f ? -1.f : 1.f;
+    if (dr <= 0.f && dy <= 0.f) {                         /* inside: nearest of the side and the caps */
+        if (dr > dy) { *n = radial; return dr; }
+        *n = V3(0.f, sy, 0.f); return dy;
+    }
+    if (dr > 0.f && dy > 0.f) {                           /* nearest point on a rim */
+        const float d = sqrtf(dr * dr + dy * dy);
+        *n = V3((dr * radial.x) / d, (dy * sy) / d, (dr * radial.z) / d);
+        return d;
+    }
+    if (dr > 0.f) { *n = radial; return dr; }
+    *n = V3(0.f, sy, 0.f); return dy;
+}
+static inline float cyl_bound(const body_t* c) { const float h2 = 0.5f * c->height; return sqrtf(h2 * h2 + c->radius * c->radius); }
+
+/* sphere (body0) against cylinder (body1) */
+static void ext_sphere_cyl(orc_system* s, int i0, int i1)
+{
+    const body_t* sp = &s->bodies[i0];
+    const body_t* cy = &s->bodies[i1];
+    const v3 rel = v3_sub(sp->x, cy->x);
+    if (v3_norm(rel) > sp->radius + cyl_bound(cy) + 1e-3f) return;
+    v3 nl;
+    const float d = cyl_sdf(q_rot(q_inverse(cy->q), rel), 0.5f * cy->height, cy->radius, &nl) - sp->radius;
+    if (d < 1e-3f) {
+        const v3 n = q_rot(cy->q, nl);
+        new_contact(s, i0, i1, v3_sub(sp->x, v3_scale(sp->radius, n)), n, fminf(0.0f, d));
+    }
+}
+
+/* surface points of cylinder `from` in the distance field of cylinder `in`; flip as in sdf_verts_in */
+static void cyl_samples_in_cyl(const body_t* from, const body_t* in, float flip, sdf_hits* H)
+{
+    const quat qinv = q_inverse(in->q);
+    for (int k = 0; k < CYL_SAMPLES; ++k) {
+        const v3 pw = v3_add(q_rot(from->q, cyl_sample(k, 0.5f * from->height, from->radius)), from->x);
+        v3 nl;
+        const float d = cyl_sdf(q_rot(qinv, v3_sub(pw, in->x)), 0.5f * in->height, in->radius, &nl);
+        if (d < 1e-3f) sdf_hit(H, d, pw, v3_scale(flip, q_rot(in->q, nl)));
+    }
+}
+
+/* cylinder (body0) against cylinder (body1) */
+static void ext_cyl_cyl(orc_system* s, int i0, int i1)
+{
+    const body_t* a = &s->bodies[i0];
+    const body_t* b = &s->bodies[i1];
+    if (v3_norm(v3_sub(a->x, b->x)) > cyl_bound(a) + cyl_bound(b) + 1e-3f) return;
+    sdf_hits H; H.cnt = 0;
+    cyl_samples_in_cyl(a, b, 1.0f, &H);
+    cyl_samples_in_cyl(b, a, -1.0f, &H);
+    sdf_emit(s, i0, i1, &H);
+}
+
+/* cylinder (body0) against box (body1): the cylinder's surface points against the box, then the box corners in the cylinder */
+static void ext_cyl_box(orc_system* s, int i0, int i1)
+{
+    const body_t* cy = &s->bodies[i0];
+    const body_t* bx = &s->bodies[i1];
+    const v3 h = V3(0.5f * bx->dim.x, 0.5f * bx->dim.y, 0.5f * bx->dim.z);
+    if (v3_norm(v3_sub(cy->x, bx->x)) > cyl_bound(cy) + v3_norm(h) + 1e-3f) return;
+    const quat qbinv = q_inverse(bx->q), qcinv = q_inverse(cy->q);
+    sdf_hits H; H.cnt = 0;
+    for (int k = 0; k < CYL_SAMPLES; ++k) {
+        const v3 pw = v3_add(q_rot(cy->q, cyl_sample(k, 0.5f * cy->height, cy->radius)), cy->x);
+        v3 nl;
+        const float d = box_sdf(q_rot(qbinv, v3_sub(pw, bx->x)), h, &nl);
+        if (d < 1e-3f) sdf_hit(&H, d, pw, q_rot(bx->q, nl));
+    }
+    for (int k = 0; k < 8; ++k) {
+        const v3 pw = v3_add(q_rot(bx->q, V3((k & 1) ? h.x : -h.x, (k & 2) ? h.y : -h.y, (k & 4) ? h.z : -h.z)), bx->x);
+        v3 nl;
+        const float d = cyl_sdf(q_rot(qcinv, v3_sub(pw, cy->x)), 0.5f * cy->height, cy->radius, &nl);
+        if (d < 1e-3f) sdf_hit(&H, d, pw, v3_neg(q_rot(cy->q, nl)));
+    }
+    sdf_emit(s, i0, i1, &H);
+}
+
+/* mesh (body0) against cylinder (body1): the mesh vertices against the cylinder, then the cylinder's surface points in the grid */
+static void ext_sdf_cyl(orc_system* s, int i0, int i1)
+{
+    const body_t* m = &s->bodies[i0];
+    const body_t* cy = &s->bodies[i1];
+    const sdf_shape* S = &s->shapes[m->shape];
+    if (v3_norm(v3_sub(m->x, cy->x)) > S->radius + cyl_bound(cy) + 1e-3f) return;
+    const quat qcinv = q_inverse(cy->q), qminv = q_inverse(m->q);
+    sdf_hits H; H.cnt = 0;
+    for (int k = 0; k < S->nv; ++k) {
+        const v3 pw = v3_add(q_rot(m->q, V3(S->verts[3 * k], S->verts[3 * k + 1], S->verts[3 * k + 2])), m->x);
+        v3 nl;
+        const float d = cyl_sdf(q_rot(qcinv, v3_sub(pw, cy->x)), 0.5f * cy->height, cy->radius, &nl);
+        if (d < 1e-3f) sdf_hit(&H, d, pw, q_rot(cy->q, nl));
+    }
+    for (int k = 0; k < CYL_SAMPLES; ++k) {
+        const v3 pw = v3_add(q_rot(cy->q, cyl_sample(k, 0.5f * cy->height, cy->radius)), cy->x);
+        float val; v3 g;
+        sdf_sample(S, q_rot(qminv, v3_sub(pw, m->x)), &val, &g);
+        if (val < 1e-3f) sdf_hit(&H, val, pw, v3_neg(q_rot(m->q, g)));
+    }
+    sdf_emit(s, i0, i1, &H);
+}
+
 void orc_stage_detect(orc_system* s)
 {
     s->pairs_tested = 0;
@@ -984,6 +1107,13 @@ void orc_stage_detect(orc_system* s)
                 else if (t0 == ORC_SDF && t1 == ORC_SDF)      ext_sdf_sdf(s, i, j);
                 else if (t0 == ORC_SDF && t1 == ORC_BOX)      ext_sdf_box(s, i, j);
                 else if (t1 == ORC_SDF && t0 == ORC_BOX)      ext_sdf_box(s, j, i);
+                else if (t0 == ORC_SPHERE && t1 == ORC_CYLINDER)   ext_sphere_cyl(s, i, j);
+                else if (t1 == ORC_SPHERE && t0 == ORC_CYLINDER)   ext_sphere_cyl(s, j, i);
+                else if (t0 == ORC_CYLINDER && t1 == ORC_BOX)      ext_cyl_box(s, i, j);
+                else if (t1 == ORC_CYLINDER && t0 == ORC_BOX)      ext_cyl_box(s, j, i);
+                else if (t0 == ORC_CYLINDER && t1 == ORC_CYLINDER) ext_cyl_cyl(s, i, j);
+                else if (t0 == ORC_SDF && t1 == ORC_CYLINDER)      ext_sdf_cyl(s, i, j);
+                else if (t1 == ORC_SDF && t0 == ORC_CYLINDER)      ext_sdf_cyl(s, j, i);
             }
         }
     }

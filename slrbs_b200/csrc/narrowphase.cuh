@@ -285,9 +285,11 @@ static __device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes,
         if (ti == GEOM_SPHERE) bi = ci.w;
         else if (ti == GEOM_BOX) { const float4 d = __ldg(&geomA[ii]); bi = norm(mk3(0.5f * d.x, 0.5f * d.y, 0.5f * d.z)); }
         else if (ti == GEOM_SDF) bi = sdf_shape_of(shapes, geomA, ii).radius;
+        else if (ti == GEOM_CYLINDER) bi = cyl_bound(__ldg(&geomA[ii]));
         if (tj == GEOM_SPHERE) bj = cj.w;
         else if (tj == GEOM_BOX) { const float4 d = __ldg(&geomA[jj]); bj = norm(mk3(0.5f * d.x, 0.5f * d.y, 0.5f * d.z)); }
         else if (tj == GEOM_SDF) bj = sdf_shape_of(shapes, geomA, jj).radius;
+        else if (tj == GEOM_CYLINDER) bj = cyl_bound(__ldg(&geomA[jj]));
         if (bi >= 0.f && bj >= 0.f) {
             const float lim = bi + bj + 0.01f;
             if (sqnorm(mk3(ci) - mk3(cj)) > lim * lim) return;
@@ -306,6 +308,13 @@ static __device__ __noinline__ void ext_pair(PairOut& o, const SdfShape* shapes,
     else if (ti == GEOM_SDF && tj == GEOM_SDF)      ext_sdf_sdf(o, shapes, quat, geomA, ii, jj, i, j, ci, cj);
     else if (ti == GEOM_SDF && tj == GEOM_BOX)      ext_sdf_box(o, shapes, quat, geomA, ii, jj, i, j, ci, cj);
     else if (tj == GEOM_SDF && ti == GEOM_BOX)      ext_sdf_box(o, shapes, quat, geomA, jj, ii, j, i, cj, ci);
+    else if (ti == GEOM_SPHERE && tj == GEOM_CYLINDER)   ext_sphere_cyl(o, quat, geomA, jj, i, j, ci, cj);
+    else if (tj == GEOM_SPHERE && ti == GEOM_CYLINDER)   ext_sphere_cyl(o, quat, geomA, ii, j, i, cj, ci);
+    else if (ti == GEOM_CYLINDER && tj == GEOM_BOX)      ext_cyl_box(o, quat, geomA, ii, jj, i, j, ci, cj);
+    else if (tj == GEOM_CYLINDER && ti == GEOM_BOX)      ext_cyl_box(o, quat, geomA, jj, ii, j, i, cj, ci);
+    else if (ti == GEOM_CYLINDER && tj == GEOM_CYLINDER) ext_cyl_cyl(o, quat, geomA, ii, jj, i, j, ci, cj);
+    else if (ti == GEOM_SDF && tj == GEOM_CYLINDER)      ext_sdf_cyl(o, shapes, quat, geomA, ii, jj, i, j, ci, cj);
+    else if (tj == GEOM_SDF && ti == GEOM_CYLINDER)      ext_sdf_cyl(o, shapes, quat, geomA, jj, ii, j, i, cj, ci);
 }
 
 // the reference's dispatch chain for the ordered pair (i < j), CollisionDetect.cpp:41-73

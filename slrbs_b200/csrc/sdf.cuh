@@ -178,6 +178,141 @@ __device__ void ext_sdf_box(Out& o, const SdfShape* shapes, const float4* __rest
     sdf_emit(o, im, ib, H);
 }
 
+// ---- EXTENSION: cylinder pairs the reference ignores (sphere-cylinder, cylinder-box, cylinder-cylinder, mesh-cylinder;
+// CollisionDetect.cpp:45-73 only knows cylinder-plane). Follows oracle/slrbs_oracle.c (cyl_sdf, cyl_sample, ext_sphere_cyl,
+// ext_cyl_cyl, ext_cyl_box, ext_sdf_cyl) operation for operation: a finite cylinder (axis = local y) is an analytic signed
+// distance plus CYL_SAMPLES surface points (three rings of 16 and the cap centres); sample points of one shape are tested
+// in the distance field of the other, the four deepest kept.
+enum { CYL_RING = 16, CYL_SAMPLES = 50 };
+__device__ __forceinline__ V3 cyl_sample(int k, float h2, float r)
+{
+    // cos / sin of 2 pi a / 16 as the same literals the restatement uses (libm and CUDA need not round alike)
+    const float C[CYL_RING] = { 1.0f, 0.9238795f, 0.70710677f, 0.38268343f, 0.0f, -0.38268343f, -0.70710677f, -0.9238795f,
+                                -1.0f, -0.9238795f, -0.70710677f, -0.38268343f, 0.0f, 0.38268343f, 0.70710677f, 0.9238795f };
+    if (k >= 3 * CYL_RING) return mk3(0.f, k == 3 * CYL_RING ? -h2 : h2, 0.f);
+    const int ring = k / CYL_RING, a = k - ring * CYL_RING;
+    return mk3(r * C[a], ring == 0 ? -h2 : (ring == 1 ? 0.f : h2), r * C[(a + 12) & 15]);       // sin a = cos (a - 4) = C[a + 12]
+}
+__device__ __forceinline__ float cyl_sdf(const V3& c, float h2, float r, V3& n)
+{
+    const float rho = sqrtf(c.x * c.x + c.z * c.z);
+    const V3 radial = rho > 0.f ? mk3(c.x / rho, 0.f, c.z / rho) : mk3(1.f, 0.f, 0.f);
+    const float dr = rho - r, dy = fabsf(c.y) - h2, sy = c.y < 0.f ? -1.f : 1.f;
+    if (dr <= 0.f && dy <= 0.f) {
+        if (dr > dy) { n = radial; return dr; }
+        n = mk3(0.f, sy, 0.f); return dy;
+    }
+    if (dr > 0.f && dy > 0.f) {
+        const float d = sqrtf(dr * dr + dy * dy);
+        n = mk3((dr * radial.x) / d, (dy * sy) / d, (dr * radial.z) / d);
+        return d;
+    }
+    if (dr > 0.f) { n = radial; return dr; }
+    n = mk3(0.f, sy, 0.f); return dy;
+}
+__device__ __forceinline__ float cyl_bound(const float4& hr) { const float h2 = 0.5f * hr.x; return sqrtf(h2 * h2 + hr.y * hr.y); }
+
+// sphere (body0) against cylinder (body1)
+template <class Out>
+__device__ void ext_sphere_cyl(Out& o, const float4* __restrict__ quat, const float4* __restrict__ geomA, size_t ci_, int is, int ic,
+                               const float4& cs, const float4& cc)
+{
+    const float4 hr = __ldg(&geomA[ci_]);
+    const V3 xs = mk3(cs), rel = xs - mk3(cc);
+    if (norm(rel) > cs.w + cyl_bound(hr) + 1e-3f) return;
+    const Q4 qc = mkq(__ldg(&quat[ci_]));
+    V3 nl;
+    const float d = cyl_sdf(rotate(qinverse(qc), rel), 0.5f * hr.x, hr.y, nl) - cs.w;
+    if (d < 1e-3f) {
+        const V3 n = rotate(qc, nl);
+        o.b0 = is; o.b1 = ic; o.n = n;
+        o.add(xs - cs.w * n, fminf(0.0f, d));
+    }
+}
+
+__device__ __forceinline__ void cyl_samples_in_cyl(const float4& hf, const Q4& qf, const V3& xf, const float4& hi, const Q4& qi, const V3& xi,
+                                                   float flip, SdfHits& H)
+{
+    const Q4 qinv = qinverse(qi);
+    for (int k = 0; k < CYL_SAMPLES; ++k) {
+        const V3 pw = rotate(qf, cyl_sample(k, 0.5f * hf.x, hf.y)) + xf;
+        V3 nl;
+        const float d = cyl_sdf(rotate(qinv, pw - xi), 0.5f * hi.x, hi.y, nl);
+        if (d < 1e-3f) sdf_hit(H, d, pw, flip * rotate(qi, nl));
+    }
+}
+
+// cylinder (body0) against cylinder (body1)
+template <class Out>
+__device__ void ext_cyl_cyl(Out& o, const float4* __restrict__ quat, const float4* __restrict__ geomA, size_t ai, size_t bi, int ia, int ib,
+                            const float4& ca, const float4& cb)
+{
+    const float4 ha = __ldg(&geomA[ai]), hb = __ldg(&geomA[bi]);
+    const V3 xa = mk3(ca), xb = mk3(cb);
+    if (norm(xa - xb) > cyl_bound(ha) + cyl_bound(hb) + 1e-3f) return;
+    const Q4 qa = mkq(__ldg(&quat[ai])), qb = mkq(__ldg(&quat[bi]));
+    SdfHits H; H.cnt = 0;
+    cyl_samples_in_cyl(ha, qa, xa, hb, qb, xb, 1.0f, H);
+    cyl_samples_in_cyl(hb, qb, xb, ha, qa, xa, -1.0f, H);
+    sdf_emit(o, ia, ib, H);
+}
+
+// cylinder (body0) against box (body1)
+template <class Out>
+__device__ void ext_cyl_box(Out& o, const float4* __restrict__ quat, const float4* __restrict__ geomA, size_t ci_, size_t bi, int ic, int ib,
+                            const float4& cc, const float4& cb)
+{
+    const float4 hr = __ldg(&geomA[ci_]), dim = __ldg(&geomA[bi]);
+    const V3 h = mk3(0.5f * dim.x, 0.5f * dim.y, 0.5f * dim.z);
+    const V3 xc = mk3(cc), xb = mk3(cb);
+    if (norm(xc - xb) > cyl_bound(hr) + norm(h) + 1e-3f) return;
+    const Q4 qc = mkq(__ldg(&quat[ci_])), qb = mkq(__ldg(&quat[bi]));
+    const Q4 qbinv = qinverse(qb), qcinv = qinverse(qc);
+    SdfHits H; H.cnt = 0;
+    for (int k = 0; k < CYL_SAMPLES; ++k) {
+        const V3 pw = rotate(qc, cyl_sample(k, 0.5f * hr.x, hr.y)) + xc;
+        V3 nl;
+        const float d = box_sdf(rotate(qbinv, pw - xb), h, nl);
+        if (d < 1e-3f) sdf_hit(H, d, pw, rotate(qb, nl));
+    }
+    for (int k = 0; k < 8; ++k) {
+        const V3 pw = rotate(qb, box_corner(h, k)) + xb;
+        V3 nl;
+        const float d = cyl_sdf(rotate(qcinv, pw - xc), 0.5f * hr.x, hr.y, nl);
+        if (d < 1e-3f) sdf_hit(H, d, pw, -rotate(qc, nl));
+    }
+    sdf_emit(o, ic, ib, H);
+}
+
+// mesh (body0) against cylinder (body1), one thread (the warp-cooperative walk is kept for the mesh pairs with many samples on
+// BOTH sides; a cylinder adds 50)
+template <class Out>
+__device__ void ext_sdf_cyl(Out& o, const SdfShape* shapes, const float4* __restrict__ quat, const float4* __restrict__ geomA,
+                            size_t mi, size_t ci_, int im, int ic, const float4& cm, const float4& cc)
+{
+    const SdfShape S = sdf_shape_of(shapes, geomA, mi);
+    if (!S.grid) return;
+    const float4 hr = __ldg(&geomA[ci_]);
+    const V3 xm = mk3(cm), xc = mk3(cc);
+    if (norm(xm - xc) > S.radius + cyl_bound(hr) + 1e-3f) return;
+    const Q4 qm = mkq(__ldg(&quat[mi])), qc = mkq(__ldg(&quat[ci_]));
+    const Q4 qcinv = qinverse(qc), qminv = qinverse(qm);
+    SdfHits H; H.cnt = 0;
+    for (int k = 0; k < S.nv; ++k) {
+        const V3 pw = rotate(qm, sdf_vertex(S, k)) + xm;
+        V3 nl;
+        const float d = cyl_sdf(rotate(qcinv, pw - xc), 0.5f * hr.x, hr.y, nl);
+        if (d < 1e-3f) sdf_hit(H, d, pw, rotate(qc, nl));
+    }
+    for (int k = 0; k < CYL_SAMPLES; ++k) {
+        const V3 pw = rotate(qc, cyl_sample(k, 0.5f * hr.x, hr.y)) + xc;
+        float val; V3 g;
+        sdf_sample(S, rotate(qminv, pw - xm), val, g);
+        if (val < 1e-3f) sdf_hit(H, val, pw, -rotate(qm, g));
+    }
+    sdf_emit(o, im, ic, H);
+}
+
 // ---- warp-cooperative versions: all 32 lanes call with the same arguments, the samples are dealt to the lanes, and the
 // four deepest of the pair are merged in the order (phi, sample index) -- the order in which the one-thread routines
 // above keep them (stable insertion), so the result is the same bit for bit. Every lane returns the full result.

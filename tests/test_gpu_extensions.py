@@ -106,3 +106,50 @@ def test_box_stack_trajectory_and_batch():
         np.testing.assert_allclose(g["x"][e], s["x"], rtol=0, atol=2e-3)
     np.testing.assert_allclose(g["x"][0, :5, 1], 0.5 + np.arange(5), atol=0.01)  # the unpushed stack stays up
     ctx.close()
+
+
+def test_many_cylinder_poses_against_box_sphere_and_cylinder():
+    """The cylinder pairs the reference ignores (sphere-cylinder, cylinder-box, cylinder-cylinder): device and restatement
+    implement the same sampled-surface-against-distance-field routines; lists must agree bit for bit."""
+    rng = np.random.default_rng(23)
+    oracles = []
+    for trial in range(96):
+        o = Oracle(); o.set_extensions(1)
+        q0 = rng.normal(size=4); q0 /= np.linalg.norm(q0)
+        if trial % 3 == 0:
+            o.add_body(1.0, BOX, [2.0, 1.0, 1.5], q=q0, fixed=True)
+        elif trial % 3 == 1:
+            o.add_body(1.0, CYLINDER, [1.5, 0.8], q=q0, fixed=True)
+        else:
+            o.add_body(1.0, SPHERE, [0.7], fixed=True)
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        if trial % 5 == 0:
+            q = np.array([0, 0, 0, 1.0])
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        o.add_body(1.0, CYLINDER, [0.4 + rng.random(), 0.2 + 0.4 * rng.random()], x=d * rng.uniform(0.5, 1.7), q=q)
+        oracles.append(o)
+    ctx = context_from_oracles(oracles, max_contacts=16)
+    ctx.set_extensions(1)
+    check_contacts(ctx, oracles)
+    cnt = ctx.contact_counts()
+    assert (cnt > 0).sum() > 30 and cnt.max() == 4
+    ctx.close()
+
+
+def test_cylinders_resting_on_a_box_trajectory():
+    def scene():
+        o = Oracle(); o.set_extensions(1)
+        o.add_body(1.0, BOX, [8, 0.4, 8], fixed=True)
+        o.add_body(1.0, CYLINDER, [1.0, 0.5], x=[-2, 1.0, 0])
+        o.add_body(1.0, CYLINDER, [1.0, 0.5], x=[2, 1.0, 0], q=[np.sin(np.pi / 4), 0, 0, np.cos(np.pi / 4)])
+        o.add_body(1.0, SPHERE, [0.3], x=[-2, 2.2, 0])
+        return o
+    o = scene()
+    ctx = context_from_oracles([scene(), scene()], max_contacts=32)
+    ctx.set_extensions(1)
+    ctx.step(DT, 300); ctx.sync()
+    o.step(DT, 300)
+    assert ctx.contact_counts()[0] == o.n_contacts
+    np.testing.assert_allclose(ctx.download_state()["x"][0], o.state()["x"], rtol=0, atol=3e-3)
+    assert abs(ctx.download_state()["x"][1][1, 1] - 0.7) < 5e-3
+    ctx.close()
