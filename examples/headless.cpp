@@ -7,9 +7,11 @@
 //
 // usage: slrbs_headless <marble_box|sphere_on_box|swinging_boxes|cylinder_on_plane|car> [steps] [solverId]
 //        slrbs_headless mesh_pile <steps> <solverId> <file.obj> [n] [scale]      (extension: SDF-mesh bodies)
+//        slrbs_headless batch <scene> <nScenes> <steps>                          (extension: RigidBodySystemBatch, N copies of a scene)
 // prints "i x y z qx qy qz qw" for every body after the last step, then "contacts N"; with SLRBS_DUMP=<file> also writes
 // every body's pose after every step (for offline rendering).
 #include "rigidbody/RigidBodySystem.h"
+#include "rigidbody/RigidBodySystemBatch.h"
 #include "rigidbody/RigidBody.h"
 #include "rigidbody/Scenarios.h"
 #include "contact/Contact.h"
@@ -21,8 +23,12 @@
 
 int main(int argc, char* argv[])
 {
-    const std::string scene = argc > 1 ? argv[1] : "marble_box";
-    const int steps = argc > 2 ? std::atoi(argv[2]) : 100;
+    std::string scene = argc > 1 ? argv[1] : "marble_box";
+    int steps = argc > 2 ? std::atoi(argv[2]) : 100;
+    // batch <scene> <nScenes> <steps>: the same scene builders, N copies stepped together without readback
+    const bool batched = scene == "batch";
+    const int nScenes = batched && argc > 3 ? std::atoi(argv[3]) : 1;
+    if (batched) { scene = argc > 2 ? argv[2] : "car"; steps = argc > 4 ? std::atoi(argv[4]) : 100; }
     RigidBodySystem sys;
     if (scene == "marble_box") Scenarios::createMarbleBox(sys);
     else if (scene == "sphere_on_box") Scenarios::createSphereOnBox(sys);
@@ -34,6 +40,21 @@ int main(int argc, char* argv[])
         Scenarios::createMeshPile(sys, argv[4], argc > 5 ? std::atoi(argv[5]) : 5, argc > 6 ? (float)std::atof(argv[6]) : 1.0f);
     }
     else { std::fprintf(stderr, "unknown scene %s\n", scene.c_str()); return 2; }
+    if (batched) {
+        RigidBodySystemBatch envs(sys, nScenes);
+        envs.saveState();
+        const auto b0 = std::chrono::steady_clock::now();
+        envs.step(0.01f, steps);
+        envs.sync();
+        const double bms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b0).count();
+        envs.readScene(nScenes - 1, sys);                        // the last scene's state into the prototype's public fields
+        int k = 0;
+        for (RigidBody* b : sys.getBodies())
+            std::printf("%d %.9g %.9g %.9g %.9g %.9g %.9g %.9g\n", k++, b->x[0], b->x[1], b->x[2], b->q.x(), b->q.y(), b->q.z(), b->q.w());
+        std::fprintf(stderr, "%s x %d scenes: %d steps in %.1f ms (%.3g body-steps/s)\n", scene.c_str(), nScenes, steps, bms,
+                     1e3 * (double)envs.numBodies() * nScenes * steps / bms);
+        return 0;
+    }
     sys.solverId = argc > 3 ? std::atoi(argv[3]) : 0;            // PGS = 0, CG = 1, CR = 2 (RigidBodySystem.h:56)
     sys.solverIter = 10;
     const float dt = 0.01f;                                      // SimViewer.cpp:113

@@ -140,3 +140,15 @@ def test_solver_subclass_without_device_kernel_runs_on_the_host(scene, steps, to
     np.testing.assert_allclose(h.state()["x"], o.state()["x"], rtol=0, atol=tol)
     np.testing.assert_allclose(h.state()["v"], o.state()["v"], rtol=0, atol=20 * tol)
     h.close()
+
+
+def test_headless_batch_program():
+    """`slrbs_headless batch car 64 120`: RigidBodySystemBatch from C++; the last scene equals the single-system run."""
+    import os, subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "slrbs_b200", "slrbs_headless")
+    out = subprocess.run([exe, "batch", "car", "64", "120"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l.split() for l in out.stdout.splitlines() if l and l[0].isdigit()]
+    x = np.array([[float(v) for v in l[1:4]] for l in lines], np.float32)
+    o = Oracle("car"); o.step(DT, 120)
+    np.testing.assert_allclose(x, o.state()["x"], rtol=0, atol=2e-3)
