@@ -40,6 +40,9 @@ BYTES_PER_CONTACT_VISIT = 464
 BYTES_PER_HINGE_VISIT = 744
 E2E_CHUNKS = int(os.environ.get("SLRBS_E2E_CHUNKS", "8"))                  # contexts the batch is split into for the end-to-end arm (transfer / compute overlap)
 
+# --workload mixed_pile: BASELINE configs[3], 10 002 mixed spheres / boxes / closed meshes in ONE scene (slrbs_b200/scenes.py):
+# extension contact pairs, SDF meshes, pair-parallel detection, graph-coloured solver; handled by build_batch()
+MIXED_PILE_BODIES = 10002
 # workload -> (Scenarios builder, (a,b,c), contact capacity / scene, scenes / GPU, settle steps, jitter)
 WORKLOADS = {
     # the reference scene itself, 167 bodies; 49152 scenes = 1536 warps of the thread-per-scene solver, 10.4 per SM (12 fit;
@@ -57,9 +60,11 @@ WORKLOADS = {
     # ONE scene no SM can hold (9605 bodies, ~28 000 touching pairs): pair-parallel detection over the whole GPU and the
     # graph-coloured solver (pgs_color.cu); order differs from the reference, validated on the residual (tests/test_gpu_color.py)
     "big_scene":      ("marble_box_n", (20, 20, 24), 40000, 1, 100, 0.01),
+    "mixed_pile":     ("mixed_pile", (MIXED_PILE_BODIES, 0, 0), 60000, 1, 150, 0.0),
 }
 # --workload pile_1m / pile: one pile cut into blocks over the ranks (slrbs_b200/partition.py), handled by run_pile()
 PILE_DIMS = {"pile_1m": (100, 100, 100), "pile": (48, 24, 48)}
+
 
 
 SOLVER_SOURCES = ("pgs_split.cu", "pgs_level.cu", "pgs_level.cuh", "pgs_math.cuh", "layout.cuh", "kernels.cu")
@@ -161,7 +166,13 @@ def build_batch(workload, B, rank):
     index (the data does not depend on the number of ranks)."""
     from slrbs_b200 import host_api, sharding
     scene, abc, nc, _, settle, jitter = WORKLOADS[workload]
-    s = host_api.scene_arrays(scene, *abc)
+    if scene == "mixed_pile":
+        from slrbs_b200 import scenes
+        mv, mf = scenes.blob()
+        s = scenes.mixed_pile(abc[0], mv)
+        s["mesh"] = (mv, mf)
+    else:
+        s = host_api.scene_arrays(scene, *abc)
     nb = s["x"].shape[0]
     x = np.broadcast_to(s["x"], (B, nb, 3)).copy()
     if jitter > 0:
@@ -188,8 +199,12 @@ def run_ours(args):
 
     ctx = Context(B, nb, nj, nc, device=local)
     ctx.set_params(MU, 0, SOLVER_ITERS, True)
-    if args.workload == "box_stack":
+    if args.workload in ("box_stack", "mixed_pile"):
         ctx.set_extensions(1)
+    if "mesh" in s:
+        from slrbs_b200 import scenes
+        sh = scenes.sdf_shape(*s["mesh"], device=local)
+        ctx.add_sdf_shape(sh["dims"], sh["origin"], sh["cell"], sh["grid"], sh["verts"])
     variants = ctx.describe()
     ctx.upload_bodies(x, s["q"], s["v"], s["w"], s["mass"], s["ibody"], s["ibodyinv"], s["fixed"], s["geom_type"], s["geom"])
     if nj:
@@ -257,7 +272,7 @@ def run_ours(args):
         for k in range(nch):
             c = Context(Bc, nb, nj, nc, device=local)
             c.set_params(MU, 0, SOLVER_ITERS, True)
-            if args.workload == "box_stack":
+            if args.workload in ("box_stack", "mixed_pile"):
                 c.set_extensions(1)
             sl = slice(k * Bc, (k + 1) * Bc)
             c.upload_bodies(hx[sl].numpy(), hq[sl].numpy(), hv[sl].numpy(), hw[sl].numpy(), s["mass"], s["ibody"], s["ibodyinv"], s["fixed"],
@@ -469,6 +484,21 @@ def _oracle_system(workload, seed, settle):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle, Reference, ref_available
     scene, abc, _, _, _, jitter = WORKLOADS[workload]
+    if scene == "mixed_pile":
+        # extension pairs + mesh bodies exist only in the restatement; same body tables as the GPU arm (slrbs_b200/scenes.py),
+        # the distance grid built by the restatement's own orc_build_sdf (bit-identical to the device's, tests/test_gpu_sdf.py)
+        import mesh_lib
+        from slrbs_b200 import scenes
+        mv, mf = scenes.blob()
+        t = scenes.mixed_pile(abc[0], mv)
+        o = Oracle(); o.set_extensions(1)
+        sid = o.add_sdf_shape(mesh_lib.build_sdf(mv, mf, cell=0.05))
+        for i in range(t["x"].shape[0]):
+            g = [sid] if t["geom_type"][i] == 4 else t["geom"][i]
+            o.add_body(float(t["mass"][i]), int(t["geom_type"][i]), g, fixed=bool(t["fixed"][i]), x=t["x"][i], q=t["q"][i])
+        o.set_params(MU, 0, SOLVER_ITERS, True)
+        o.step(DT, min(settle, 2))
+        return o, "port"
     kw = {"k": abc[0]} if scene in ("sphere_stack", "box_stack") else ({"nx": abc[0], "nz": abc[1], "ny": abc[2]} if scene == "marble_box_n" else {})
     o = Oracle(scene, **kw)
     if jitter > 0:
@@ -494,7 +524,7 @@ def cpu_baseline_single(workload, settle, budget_s=12.0):
     """The reference's CPU implementation, one thread, one scene of the same workload; bounded to ~budget_s."""
     o, kind = _oracle_system(workload, 1234, settle)
     n, t = 0, 0.0
-    chunk = 10
+    chunk = 10 if o.n_bodies < 5000 else 1
     while t < budget_s:
         t += o.time_steps(DT, chunk); n += chunk
     cores = os.cpu_count()
@@ -516,6 +546,8 @@ def cpu_baseline_single(workload, settle, budget_s=12.0):
         out["port_value"] = p.n_bodies * pn / pt
         what = (f"reference sources compiled against the Eigen API shim (oracle/_ref); port_value = the C restatement on the same "
                 f"scene ({pn} steps)")
+    if workload == "mixed_pile":
+        settle = min(settle, 2)         # the all-pairs CPU loop over 10^4 mixed bodies takes seconds per step: the sample starts from the lattice
     out["sample"] = (f"1 scene of {workload} ({o.n_bodies} bodies, {o.n_contacts} contacts), {n} steps after a {settle}-step settle, "
                      f"single thread like the reference; {what}; host has {cores} logical cores")
     return out
