@@ -283,21 +283,23 @@ def run_ours(args):
     sizes = (3, 4, 3, 3)
     cptr = [[p + 4 * sz * nb * s0 for p, sz in zip(ptr, sizes)] for _, s0, _ in chunks]
 
-    def e2e_step():
-        for (c, _, n_sc), pp in zip(chunks, cptr):
-            c.upload_state_raw_async(n_sc, nb, *pp)         # H2D: 13 floats / body
-            c.step(DT, 1)
-            c.download_state_raw_async(n_sc, nb, *pp)       # D2H: 13 floats / body
+    def e2e_run(nsteps):
+        # per chunk and step: wait until the chunk's previous result is in host memory, upload its state again, step, download.
+        # The wait is per chunk (not a barrier over all chunks), so chunk 0 starts step k + 1 while chunk 7 still finishes step k.
+        for _ in range(nsteps):
+            for (c, _, n_sc), pp in zip(chunks, cptr):
+                c.sync()
+                c.upload_state_raw_async(n_sc, nb, *pp)     # H2D: 13 floats / body
+                c.step(DT, 1)
+                c.download_state_raw_async(n_sc, nb, *pp)   # D2H: 13 floats / body
         for c, _, _ in chunks:
             c.sync()                                        # every body's new state is in host memory
 
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(3):                                      # warm the staging buffers (and capture the step graphs)
-        e2e_step()
+    e2e_run(3)                                              # warm the staging buffers (and capture the step graphs)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_run(e2e_steps)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
