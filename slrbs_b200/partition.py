@@ -446,11 +446,26 @@ class DevicePile:
             self.table.zero_(); self.vmax2.zero_()
             torch.cuda.synchronize(self.device)
             self.ctx.pile_export(self.table.data_ptr(), self.vmax2.data_ptr())
-            self.ctx.sync()
+            grow = 0
+            try:
+                self.ctx.sync()
+            except SlrbsError as e:
+                # a block produced more contacts than its scene holds since the last re-partition (they were dropped for
+                # those steps): the exported states are complete all the same; rebuild into a context with more contact slots
+                if "more contacts" not in str(e):
+                    raise
+                grow = 1
             if self.world > 1:
                 self.dist.all_reduce(self.table)                                   # disjoint owners: sum = gather
                 self.dist.all_reduce(self.vmax2, op=self.dist.ReduceOp.MAX)        # float bits of v^2 >= 0 order like ints
+                g = torch.tensor([grow], dtype=torch.int32, device=self.table.device)
+                self.dist.all_reduce(g, op=self.dist.ReduceOp.MAX)                 # every rank keeps the same capacity
+                grow = int(g.cpu()[0])
                 torch.cuda.synchronize(self.device)
+            if grow:
+                self.contact_factor = int(self.contact_factor * 1.5) + 1
+                self.stats["contact_grows"] = self.stats.get("contact_grows", 0) + 1
+                self._make_ctx()
         while True:
             try:
                 info = self.ctx.pile_rebuild(self.table.data_ptr())
