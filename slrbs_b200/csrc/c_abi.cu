@@ -771,9 +771,9 @@ int slrbs_download_contact_schedule(slrbs_ctx* c, int scene, int max_out, int32_
     if (total > 0 && (r = scene_count(c, c->v.nclev, scene, &nl))) return r;
     if (n_levels) *n_levels = nl;
     const int n = total < max_out ? total : max_out;
-    // cpos is [NC][B], clev_end [level][B]: strided columns of one scene
+    // cpos is [B][NC] in level / colour mode (atc), clev_end [level][B]: a strided column of one scene
     if (n > 0 && position)
-        CU(cudaMemcpy2DAsync(position, sizeof(int), c->v.cpos + scene, sizeof(int) * (size_t)c->v.B, sizeof(int), (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(position, c->v.cpos + (size_t)scene * c->v.NC, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     const int m = nl < max_levels ? nl : max_levels;
     if (m > 0 && level_end)
         CU(cudaMemcpy2DAsync(level_end, sizeof(int), c->v.clev_end + (size_t)c->v.B + scene, sizeof(int) * (size_t)c->v.B, sizeof(int), (size_t)m, cudaMemcpyDeviceToHost, c->stream));

@@ -156,7 +156,7 @@ __device__ __forceinline__ float dot6_seq(const float* a, const float* b)
 // one contact: frame, Jacobian blocks, J M^-1, diagonal block, RHS -> its row record at `pos` of the scene's stream
 __device__ __forceinline__ void contact_row(const View& v, float h, int scene, int slot, int pos)
 {
-    const size_t c = at(v, slot, scene);
+    const size_t c = atc(v, slot, scene);
     const int2 ids = v.cids[c];
     const float4 pp = v.cp[c];
     const V3 p = mk3(pp), n = mk3(v.cn[c]);
@@ -1089,7 +1089,7 @@ __global__ void k_export_contacts(View v, int scene, int n, int* body0, int* bod
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
-    const size_t ci = at(v, c, scene);
+    const size_t ci = atc(v, c, scene);
     const int2 ids = v.cids[ci];
     if (body0) body0[c] = ids.x;
     if (body1) body1[c] = ids.y;

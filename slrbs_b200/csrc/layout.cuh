@@ -97,6 +97,7 @@ struct View {
     int    *njlev;      // [B] number of joint levels
     float  *kry;        // [7][5][NJ][B] Krylov work vectors x, r, p, b, Ap, Ar, Ax (allocated on first CG/CR solve)
     // contacts, [NC][B]
+    // contacts: cids, cp, cn, cpos are indexed with atc() ([NC][B], or [B][NC] in level / colour mode)
     int2   *cids;       // body0, body1 (role ordered: sphere/box, cylinder/plane)
     float4 *cp;         // p | pene
     float4 *cn;         // n | -
@@ -113,6 +114,9 @@ struct View {
 };
 
 __host__ __device__ __forceinline__ size_t at(const View& v, int slot, int scene) { return (size_t)slot * v.B + scene; }
+// contact-slot arrays (cids, cp, cn, cpos): scene-minor like everything else for the thread-per-scene kernels, but SCENE-MAJOR
+// ([scene][slot]) in level / colour mode, where a warp or a CTA works on ONE scene and walks consecutive slots
+__host__ __device__ __forceinline__ size_t atc(const View& v, int slot, int scene) { return v.level_mode ? (size_t)scene * v.NC + slot : (size_t)slot * v.B + scene; }
 __host__ __device__ __forceinline__ size_t at_brec(const View& v, int slot, int scene) { return ((size_t)scene * v.NB + slot) * 8; }
 __host__ __device__ __forceinline__ size_t at_kry(const View& v, int vec, int k, int slot, int scene) { return (((size_t)vec * 5 + k) * v.NJ + slot) * v.B + scene; }
 __host__ __device__ __forceinline__ size_t at_b9(const View& v, int k, int slot, int scene) { return ((size_t)k * v.NB + slot) * v.B + scene; }
@@ -128,7 +132,7 @@ __host__ __device__ __forceinline__ size_t at_jrow(const View& v, int f, int pos
     if (v.level_mode) return ((size_t)scene * JROW_FIELDS + f) * v.NJ + pos;
     return ((((size_t)(scene >> 5) * v.NJ + pos) * JROW_FIELDS + f) << 5) + (scene & 31);
 }
-__host__ __device__ __forceinline__ int contact_pos(const View& v, int slot, int scene) { return v.level_mode ? v.cpos[at(v, slot, scene)] : slot; }
+__host__ __device__ __forceinline__ int contact_pos(const View& v, int slot, int scene) { return v.level_mode ? v.cpos[(size_t)scene * v.NC + slot] : slot; }
 __host__ __device__ __forceinline__ int joint_pos(const View& v, int slot, int scene) { return v.level_mode ? v.jpos[at(v, slot, scene)] : slot; }
 
 }  // namespace slrbs

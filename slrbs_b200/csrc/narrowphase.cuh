@@ -381,7 +381,7 @@ __device__ __forceinline__ void write_contacts(const View& v, int scene, int bas
     for (int k = 0; k < 4; ++k) {
         if (k < o.cnt) {
             if (base + k < v.NC) {
-                const size_t c = at(v, base + k, scene);
+                const size_t c = atc(v, base + k, scene);
                 v.cids[c] = make_int2(o.b0, o.b1);
                 v.cp[c] = mk4(o.p[k], o.phi[k]);
                 v.cn[c] = mk4(o.n, 0.f);

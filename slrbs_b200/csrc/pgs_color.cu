@@ -46,17 +46,17 @@ __global__ void __launch_bounds__(COLOR_THREADS) k_contact_colors(View v)
     const int nb = v.nbodies[scene], nc = v.ncontacts[scene];
     unsigned long long* mask = v.cmask + (size_t)scene * v.NB;    // colours taken by the coloured contacts of a body
     unsigned long long* win = v.cwin + (size_t)scene * v.NB;      // lowest bid of the uncoloured contacts of a body
-    int* color = v.cpos;                                          // [NC][B]: the colour while colouring, then the position
+    int* color = v.cpos;                                          // (atc) the colour while colouring, then the position
     for (int b = tid; b < nb; b += T) { mask[b] = 0ull; win[b] = ~0ull; }
-    for (int c = tid; c < nc; c += T) color[at(v, c, scene)] = -1;
+    for (int c = tid; c < nc; c += T) color[atc(v, c, scene)] = -1;
     if (tid == 0) { s_remaining = nc; s_ncol = 0; }
     if (tid < MAX_COLORS) { s_hist[tid] = 0; s_run[tid] = 0; }
     __syncthreads();
     while (s_remaining > 0) {
         // bids
         for (int c = tid; c < nc; c += T) {
-            if (color[at(v, c, scene)] >= 0) continue;
-            const int2 ids = v.cids[at(v, c, scene)];
+            if (color[atc(v, c, scene)] >= 0) continue;
+            const int2 ids = v.cids[atc(v, c, scene)];
             const unsigned long long bid = ((unsigned long long)mix32((unsigned)c) << 32) | (unsigned)c;
             if (!(v.flags[at(v, ids.x, scene)] & FLAG_FIXED)) atomicMin(&win[ids.x], bid);
             if (!(v.flags[at(v, ids.y, scene)] & FLAG_FIXED)) atomicMin(&win[ids.y], bid);
@@ -65,15 +65,15 @@ __global__ void __launch_bounds__(COLOR_THREADS) k_contact_colors(View v)
         // contacts that hold both bodies take a colour; they share no body with each other, so the masks they read are final
         int done = 0;
         for (int c = tid; c < nc; c += T) {
-            if (color[at(v, c, scene)] >= 0) continue;
-            const int2 ids = v.cids[at(v, c, scene)];
+            if (color[atc(v, c, scene)] >= 0) continue;
+            const int2 ids = v.cids[atc(v, c, scene)];
             const unsigned long long bid = ((unsigned long long)mix32((unsigned)c) << 32) | (unsigned)c;
             const bool dyn0 = !(v.flags[at(v, ids.x, scene)] & FLAG_FIXED), dyn1 = !(v.flags[at(v, ids.y, scene)] & FLAG_FIXED);
             if ((dyn0 && __ldcg(&win[ids.x]) != bid) || (dyn1 && __ldcg(&win[ids.y]) != bid)) continue;
             const unsigned long long used = (dyn0 ? __ldcg(&mask[ids.x]) : 0ull) | (dyn1 ? __ldcg(&mask[ids.y]) : 0ull);
             int k = __ffsll((long long)~used) - 1;
             if (k < 0) { k = MAX_COLORS - 1; atomicOr(v.overflow, 8); }      // a body with 64 contacts of distinct colours
-            color[at(v, c, scene)] = k;
+            color[atc(v, c, scene)] = k;
             if (dyn0) { atomicOr(&mask[ids.x], 1ull << k); atomicExch(&win[ids.x], ~0ull); }
             if (dyn1) { atomicOr(&mask[ids.y], 1ull << k); atomicExch(&win[ids.y], ~0ull); }
             atomicAdd(&s_hist[k], 1);
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(COLOR_THREADS) k_contact_colors(View v)
     // stable counting sort: position = start of the colour + number of earlier contacts of that colour
     for (int c0 = 0; c0 < nc; c0 += T) {
         const int c = c0 + tid;
-        const int k = c < nc ? color[at(v, c, scene)] : -1;
+        const int k = c < nc ? color[atc(v, c, scene)] : -1;
         for (int q = lane; q < MAX_COLORS; q += 32) s_wcnt[warp][q] = 0;
         __syncwarp();
         const unsigned act = __ballot_sync(0xffffffffu, k >= 0);
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(COLOR_THREADS) k_contact_colors(View v)
             int before = 0;
             for (int w = 0; w < warp; ++w) before += s_wcnt[w][k];
             const int pos = s_hist[k] + s_run[k] + before + rank;
-            color[at(v, c, scene)] = pos;
+            color[atc(v, c, scene)] = pos;
             v.cslot[(size_t)scene * v.NC + pos] = c;
         }
         __syncthreads();

@@ -105,11 +105,11 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
     // of equal level and count the lower ones.
     int nlev = 0;
     int2 nxt = make_int2(0, 0);
-    if (lane < nc) nxt = v.cids[at(v, lane, scene)];
+    if (lane < nc) nxt = v.cids[atc(v, lane, scene)];
     for (int c0 = 0; c0 < nc; c0 += 32) {
         const int m = min(32, nc - c0);
         idbuf[lane] = nxt;
-        if (c0 + 32 + lane < nc) nxt = v.cids[at(v, c0 + 32 + lane, scene)];   // next chunk's ids, in flight during the chain
+        if (c0 + 32 + lane < nc) nxt = v.cids[atc(v, c0 + 32 + lane, scene)];   // next chunk's ids, in flight during the chain
         __syncwarp();
         if (lane == 0) {
             if (m == 32) {                                       // full chunk: ids in registers, only `last` is on the chain
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
             const int base = hist.get(myL);
             __syncwarp(act);
             if (lane == __ffs(same) - 1) hist.set(myL, base + __popc(same));
-            v.cpos[at(v, c0 + lane, scene)] = (int)(((unsigned)myL << 16) | (unsigned)(base + __popc(same & ((1u << lane) - 1u))));
+            v.cpos[atc(v, c0 + lane, scene)] = (int)(((unsigned)myL << 16) | (unsigned)(base + __popc(same & ((1u << lane) - 1u))));
             nlev = max(nlev, myL);
         }
         __syncwarp();
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
     for (int c0 = 0; c0 < nc; c0 += 256) {
         int pk[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int c = c0 + u * 32 + lane; pk[u] = c < nc ? v.cpos[at(v, c, scene)] : 0; }
+        for (int u = 0; u < 8; ++u) { const int c = c0 + u * 32 + lane; pk[u] = c < nc ? v.cpos[atc(v, c, scene)] : 0; }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int c = c0 + u * 32 + lane;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(32) k_contact_levels(View v)
                 const int L = (int)((unsigned)pk[u] >> 16);
                 const int start = L < LEVEL_HIST_CAP ? (int)hist_s[L] : v.clev_end[at(v, L - 1, scene)];
                 const int pos = start + (pk[u] & 0xffff);
-                v.cpos[at(v, c, scene)] = pos;
+                v.cpos[atc(v, c, scene)] = pos;
                 v.cslot[(size_t)scene * v.NC + pos] = c;
             }
         }
