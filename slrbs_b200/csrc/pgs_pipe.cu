@@ -52,9 +52,22 @@ struct LevelEnds {
 
 }  // namespace
 
-template <bool W24>
+// STREAM: the row records are read once per sweep and the whole stream is far larger than L2 -- demand loads then carry an
+// L2 evict-first policy (and do not allocate in L1), so that a line leaves L2 as soon as it has been consumed and the lines the
+// bulk prefetch brought in for the next level are not the ones pushed out.
+__device__ __forceinline__ float4 ldg_stream(const float4* p, unsigned long long policy)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;\n"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(policy));
+    return r;
+}
+
+template <bool W24, bool STREAM>
 __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters, float mu)
 {
+    unsigned long long policy = 0;
+    if (STREAM) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
     extern __shared__ float4 smem_pp4[];
     float* w = reinterpret_cast<float*>(smem_pp4);
     const int scene = blockIdx.x, lane = threadIdx.x;
@@ -91,7 +104,8 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
 #define PIPE_ISSUE(F, LAM, c)                                                                                          \
     if ((c).ok && (c).base + lane < (c).p1) {                                                                          \
         const unsigned q_ = (unsigned)((c).base + lane);                                                               \
-        _Pragma("unroll") for (int f = 0; f < CROW_LAMBDA; ++f) F[f] = __ldg(rows + (q_ + (unsigned)f * uNC));         \
+        _Pragma("unroll") for (int f = 0; f < CROW_LAMBDA; ++f)                                                         \
+            F[f] = STREAM ? ldg_stream(rows + (q_ + (unsigned)f * uNC), policy) : __ldg(rows + (q_ + (unsigned)f * uNC)); \
         LAM = rows[q_ + (unsigned)CROW_LAMBDA * uNC];                                                                  \
     }
 #define PIPE_SOLVE(F, LAM, c)                                                                                          \
@@ -175,8 +189,10 @@ static bool pp_pack24(int NB) { return ((size_t)NB * 32 + 1024) * 9 > 227u * 102
 
 void init_pipe_kernels()
 {
-    cudaFuncSetAttribute(k_pgs_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_pgs_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_pipe<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_pipe<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_pgs_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 
 // contexts without joint capacity whose scenes get one warp each (group 32)
@@ -189,8 +205,16 @@ bool level_pipe_wanted(const View& v, int group)
 
 void launch_pgs_pipe(const View& v, float dt, int iters, float mu, cudaStream_t s)
 {
-    if (pp_pack24(v.NB)) k_pgs_pipe<true><<<(unsigned)v.B, 32, (size_t)v.NB * 24, s>>>(v, dt, iters, mu);
-    else k_pgs_pipe<false><<<(unsigned)v.B, 32, (size_t)v.NB * 32, s>>>(v, dt, iters, mu);
+    static int stream = -1;                                      // SLRBS_PIPE_STREAM=1: evict-first row loads (A/B switch)
+    if (stream < 0) { const char* e = getenv("SLRBS_PIPE_STREAM"); stream = e ? atoi(e) : 0; }
+    const bool st = stream && v.B >= 256;
+    if (pp_pack24(v.NB)) {
+        if (st) k_pgs_pipe<true, true><<<(unsigned)v.B, 32, (size_t)v.NB * 24, s>>>(v, dt, iters, mu);
+        else k_pgs_pipe<true, false><<<(unsigned)v.B, 32, (size_t)v.NB * 24, s>>>(v, dt, iters, mu);
+    } else {
+        if (st) k_pgs_pipe<false, true><<<(unsigned)v.B, 32, (size_t)v.NB * 32, s>>>(v, dt, iters, mu);
+        else k_pgs_pipe<false, false><<<(unsigned)v.B, 32, (size_t)v.NB * 32, s>>>(v, dt, iters, mu);
+    }
 }
 
 }  // namespace slrbs
