@@ -89,9 +89,9 @@ __device__ __forceinline__ void bpp_sync() { if (ONE_WARP) __syncwarp(); else __
 
 // BIG: scenes beyond BPP_MAX_ROWS rows (the reference's own marble box has 1107): the row records and the packed Cholesky
 // triangle of the free set live in a per-scene global scratch area (L2 resident: 2.5 MB for 1107 rows) instead of shared
-// memory, which then only holds the per-row vectors; same code, same operation order, one 1024-thread CTA per scene.
+// memory, which then only holds the per-row vectors; same code, same operation order, one 512-thread CTA per scene.
 template <bool ONE_WARP, bool BIG = false>
-__global__ void k_bpp(View v, int maxit, float mu, int cap, int min_rows, int flag_overflow, float* scratch = nullptr, size_t scratch_stride = 0)
+__global__ void __launch_bounds__(BIG ? 512 : 256) k_bpp(View v, int maxit, float mu, int cap, int min_rows, int flag_overflow, float* scratch = nullptr, size_t scratch_stride = 0)
 {
     extern __shared__ float sm[];
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
@@ -168,7 +168,7 @@ __global__ void k_bpp(View v, int maxit, float mu, int cap, int min_rows, int fl
         float4 Fr[CROW_FIELDS];
         const int p = contact_pos(v, s, scene);
 #pragma unroll
-        for (int f = 0; f < CROW_FIELDS - 1; ++f) Fr[f] = __ldg(&v.crow[at_crow(v, f, p, scene)]);
+        load_crow_fields(v, p, scene, Fr);
         const ContactIds c = contact_ids(Fr);
         const float im0 = Fr[0].w, im1 = Fr[1].w;
 #pragma unroll
@@ -381,7 +381,7 @@ int launch_bpp(const View& v, int iters, float mu, float* big_scratch, cudaStrea
         if (c == cap) break;
     }
     if (big) {
-        k_bpp<false, true><<<(unsigned)v.B, 1024, bpp_big_smem_words(big) * sizeof(float), s>>>(v, 5 * iters, mu, big, BPP_MAX_ROWS + 1, 1, big_scratch,
+        k_bpp<false, true><<<(unsigned)v.B, 512, bpp_big_smem_words(big) * sizeof(float), s>>>(v, 5 * iters, mu, big, BPP_MAX_ROWS + 1, 1, big_scratch,
                                                                                            bpp_big_scratch_floats(big));
         ++launches;
     }

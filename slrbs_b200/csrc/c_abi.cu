@@ -187,12 +187,15 @@ int slrbs_describe(slrbs_ctx* c, char* buf, int buf_len)
 {
     if (!c || !buf || buf_len <= 0) return fail(SLRBS_E_ARG, "slrbs_describe: bad argument");
     char tmp[256];
-    if (c->v.color_mode)
+    if (c->v.level_mode && c->level_variant == 4)
+        std::snprintf(tmp, sizeof tmp, "solver=k_pgs_gacc (level-scheduled, 1 warp/scene, accumulators in L1/L2, 18 warps/SM, %s B rows) detect=%s graph=%d",
+                      c->v.crow_compact ? "208" : "256", detect_variant(c->v, c->broadphase), c->use_graph);
+    else if (c->v.color_mode)
         std::snprintf(tmp, sizeof tmp, "solver=k_pgs_color (graph-coloured, all SMs, accumulators in HBM) detect=%s graph=%d",
                       detect_variant(c->v, c->broadphase), c->use_graph);
     else if (c->v.level_mode && c->level_variant == 2)
-        std::snprintf(tmp, sizeof tmp, "solver=k_pgs_pipe (level-scheduled, 1 warp/scene, next chunk's rows prefetched into registers) detect=%s graph=%d",
-                      detect_variant(c->v, c->broadphase), c->use_graph);
+        std::snprintf(tmp, sizeof tmp, "solver=k_pgs_pipe (level-scheduled, 1 warp/scene, next chunk's rows prefetched into registers, %s B rows) detect=%s graph=%d",
+                      c->v.crow_compact ? "208" : "256", detect_variant(c->v, c->broadphase), c->use_graph);
     else if (c->v.level_mode && c->level_variant == 1)
         std::snprintf(tmp, sizeof tmp, "solver=k_pgs_sp<ROWS=%d> (level-scheduled, 2 lanes/contact row, %d threads/scene) detect=%s graph=%d",
                       c->level_group, 2 * c->level_group, detect_variant(c->v, c->broadphase), c->use_graph);
@@ -248,7 +251,8 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
         else v.level_mode = (n_scenes <= 8192 && fits) ? 1 : 0;
         const char* g = std::getenv("SLRBS_LEVEL_GROUP");
         c->level_group = level_group_size(v, g ? std::atoi(g) : 0);
-        c->level_variant = !v.level_mode ? 0 : (v.color_mode ? 3 : (level_split_wanted(v, c->level_group) ? 1 : (level_pipe_wanted(v, c->level_group) ? 2 : 0)));
+        c->level_variant = !v.level_mode ? 0 : (v.color_mode ? 3 : (level_split_wanted(v, c->level_group) ? 1 : (level_gacc_wanted(v, c->level_group) ? 4 : (level_pipe_wanted(v, c->level_group) ? 2 : 0))));
+        v.crow_compact = ((c->level_variant == 2 || c->level_variant == 4) && pipe_rows_compact()) ? 1 : 0;
         if (v.color_mode) c->use_graph = 0;                     // the solver is one cooperative launch; such scenes are not launch bound
         const char* bp = std::getenv("SLRBS_BROADPHASE");
         if (bp) c->broadphase = std::atoi(bp) ? 1 : 0;
@@ -266,6 +270,7 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     A(v.jrow, (size_t)JROW_FIELDS * v.NJ * bpad)
     A(v.cids, nc) A(v.cp, nc) A(v.cn, nc) A(v.crow, (size_t)CROW_FIELDS * v.NC * bpad)
     { SdfShape* tab = nullptr; A(tab, MAX_SDF_SHAPES) v.sdf_shapes = tab; }
+    if (c->level_variant == 4) { A(v.wacc, 2 * nb) }
     if (v.color_mode) {
         A(v.cmask, nb) A(v.cwin, nb) A(v.nclev_max, 1)
         // scenes no single CTA can hold are detected pair-parallel over the whole GPU (detect_pairs.cu), extension pairs or not

@@ -202,6 +202,22 @@ __device__ __forceinline__ void contact_row(const View& v, float h, int scene, i
     const int packed = (ids.x | (b0.fixed ? 0x8000 : 0)) | ((ids.y | (b1.fixed ? 0x8000 : 0)) << 16);
     float4* R = v.crow;
 #define CROW(f) R[at_crow(v, f, pos, scene)]
+    if (v.crow_compact) {                                       // 13 fields (pgs_math.cuh: crow_expand)
+        CROW(0)  = mk4(n, 1.0f / b0.mass);
+        CROW(1)  = mk4(t, 1.0f / b1.mass);
+        CROW(2)  = mk4(bb, __int_as_float(packed));
+        CROW(3)  = mk4(rr0, rhs[0]);
+        CROW(4)  = mk4(rr1, rhs[1]);
+        CROW(5)  = make_float4(M0[0][3], M0[0][4], M0[0][5], rhs[2]);
+        CROW(6)  = make_float4(M0[1][3], M0[1][4], M0[1][5], A[0][0]);
+        CROW(7)  = make_float4(M0[2][3], M0[2][4], M0[2][5], A[1][1]);
+        CROW(8)  = make_float4(M1[0][3], M1[0][4], M1[0][5], A[2][2]);
+        CROW(9)  = make_float4(M1[1][3], M1[1][4], M1[1][5], A[0][1]);
+        CROW(10) = make_float4(M1[2][3], M1[2][4], M1[2][5], A[0][2]);
+        CROW(11) = make_float4(A[1][0], A[1][2], A[2][0], A[2][1]);
+        CROW(CROW_LAMBDA) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     CROW(0)  = mk4(n, 1.0f / b0.mass);
     CROW(1)  = mk4(t, 1.0f / b1.mass);
     CROW(2)  = mk4(bb, __int_as_float(packed));
@@ -1099,7 +1115,8 @@ __global__ void k_export_contacts(View v, int scene, int n, int* body0, int* bod
     if (phi) phi[c] = pp.w;
     float4 F[CROW_FIELDS];
     const int cp_ = contact_pos(v, c, scene);
-    for (int f = 0; f < CROW_FIELDS; ++f) F[f] = v.crow[at_crow(v, f, cp_, scene)];
+    load_crow_fields(v, cp_, scene, F);
+    F[CROW_LAMBDA] = v.crow[at_crow(v, CROW_LAMBDA, cp_, scene)];
     if (t3) { t3[3 * c] = F[1].x; t3[3 * c + 1] = F[1].y; t3[3 * c + 2] = F[1].z; }
     if (b3) { b3[3 * c] = F[2].x; b3[3 * c + 1] = F[2].y; b3[3 * c + 2] = F[2].z; }
     if (lam3) { const float4 l = F[CROW_LAMBDA]; lam3[3 * c] = l.x; lam3[3 * c + 1] = l.y; lam3[3 * c + 2] = l.z; }

@@ -52,7 +52,7 @@ void launch_build_sdf(const float* verts, int nt, const int* tris, int nx, int n
 void launch_joint_levels(const View& v, cudaStream_t s);
 void launch_contact_levels(const View& v, cudaStream_t s);
 size_t contact_levels_smem(int NB, int NC);
-void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, int variant, cudaStream_t s);   // variant: 0 k_pgs_lv, 1 k_pgs_sp, 2 k_pgs_pipe
+void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, int variant, cudaStream_t s);   // variant: 0 k_pgs_lv, 1 k_pgs_sp, 2 k_pgs_pipe, 4 k_pgs_gacc
 int  level_group_size(const View& v, int requested);
 // pgs_split.cu: the level schedule with two lanes per contact row (one per body side); rows = 32 or 64 rows per level step
 void init_split_kernels();
@@ -62,6 +62,11 @@ bool level_split_wanted(const View& v, int group);
 void init_pipe_kernels();
 void launch_pgs_pipe(const View& v, float dt, int iters, float mu, cudaStream_t s);
 bool level_pipe_wanted(const View& v, int group);
+bool pipe_rows_compact();
+// pgs_gacc.cu: one warp per contact-only scene, accumulators in global memory (L1 / L2), 18 warps per SM
+void init_gacc_kernels();
+void launch_pgs_gacc(const View& v, float dt, int iters, float mu, cudaStream_t s);
+bool level_gacc_wanted(const View& v, int group);
 bool level_mode_fits(int max_bodies);
 // pgs_color.cu: graph-coloured solver for large scenes (accumulators in HBM, one grid barrier per colour)
 void launch_contact_colors(const View& v, cudaStream_t s);

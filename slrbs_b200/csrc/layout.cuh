@@ -83,6 +83,7 @@ struct View {
     float  *Iw;         // [9][NB][B] world inertia
     float  *Iinvw;      // [9][NB][B]
     float4 *wl, *wa;    // PGS body accumulators sum(J^T lambda); after solve: fc, tauc
+    float4 *wacc;       // [B][NB][2] scene-major accumulators of k_pgs_gacc (allocated for contexts that use it)
     float4 *brec;       // [B][NB][8] per-body record for the row builders (one 128 B line per body, written by k_prepare):
                         // x|mass, xdot|fixed, omega|-, f|-, tau|-, Iinv rows 0..2
     float4 *s_pos, *s_quat, *s_vel, *s_omg;   // RigidBodySystemState snapshot
@@ -109,6 +110,9 @@ struct View {
     int    *lv_last;    // [NB][B] scratch: last level that touched a body
     // graph-coloured solver for scenes too large for one SM (pgs_color.cu): colours take the place of the contact levels
     int     color_mode;
+    // contact row records in the 13-field compact form (208 B instead of 256 B: rr0, rr1 stored, a0d = rr0 x d and
+    // a1d = -(rr1 x d) recomputed by the consumer, bit-identically); contexts served by k_pgs_pipe, SLRBS_ROWS_COMPACT
+    int     crow_compact;
     unsigned long long *cmask, *cwin;   // [B][NB] colours used by a body's contacts | lowest bid among its uncoloured contacts
     int    *nclev_max;  // [1] largest colour count over the scenes (reset by k_prepare)
 };

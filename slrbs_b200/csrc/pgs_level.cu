@@ -440,6 +440,7 @@ void init_level_kernels()
     init_lv<4>(); init_lv<8>(); init_lv<16>(); init_lv<32>(); init_lv<64>(); init_lv<128>();
     init_split_kernels();
     init_pipe_kernels();
+    init_gacc_kernels();
     cudaFuncSetAttribute(k_contact_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
@@ -469,6 +470,7 @@ void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, i
 {
     if (variant == 1) { launch_pgs_split(v, dt, iters, mu, group, s); return; }
     if (variant == 2) { launch_pgs_pipe(v, dt, iters, mu, s); return; }
+    if (variant == 4) { launch_pgs_gacc(v, dt, iters, mu, s); return; }
     switch (group) {
     case 4:  launch_lv<4>(v, dt, iters, mu, s); break;
     case 8:  launch_lv<8>(v, dt, iters, mu, s); break;

@@ -63,9 +63,10 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p, unsigned long long
     return r;
 }
 
-template <bool W24, bool STREAM>
+template <bool W24, bool STREAM, bool COMPACT>
 __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters, float mu)
 {
+    constexpr int NF = COMPACT ? CROW_COMPACT_FIELDS : CROW_LAMBDA;      // read-only fields of a stored record
     unsigned long long policy = 0;
     if (STREAM) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
     extern __shared__ float4 smem_pp4[];
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
                 int q0 = c.p1, q1 = c.p1;
                 if (c.lev < ncl) q1 = le.end_of(c.lev + 1, lane);
                 else if (c.it + 1 < iters) { q0 = 0; q1 = le.end_of(1, lane); }
-                if (lane < CROW_FIELDS && q1 > q0) prefetch_l2_bulk(rows + (size_t)lane * uNC + q0, (unsigned)(q1 - q0) * 16u);
+                if (lane < CROW_FIELDS && (!COMPACT || lane < CROW_COMPACT_FIELDS || lane == CROW_LAMBDA) && q1 > q0)
+                    prefetch_l2_bulk(rows + (size_t)lane * uNC + q0, (unsigned)(q1 - q0) * 16u);
             }
         }
         return c;
@@ -104,17 +106,20 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
 #define PIPE_ISSUE(F, LAM, c)                                                                                          \
     if ((c).ok && (c).base + lane < (c).p1) {                                                                          \
         const unsigned q_ = (unsigned)((c).base + lane);                                                               \
-        _Pragma("unroll") for (int f = 0; f < CROW_LAMBDA; ++f)                                                         \
+        _Pragma("unroll") for (int f = 0; f < NF; ++f)                                                                  \
             F[f] = STREAM ? ldg_stream(rows + (q_ + (unsigned)f * uNC), policy) : __ldg(rows + (q_ + (unsigned)f * uNC)); \
         LAM = rows[q_ + (unsigned)CROW_LAMBDA * uNC];                                                                  \
     }
 #define PIPE_SOLVE(F, LAM, c)                                                                                          \
     if ((c).base + lane < (c).p1) {                                                                                    \
-        const ContactIds ci = contact_ids(F);                                                                          \
+        float4 X[CROW_LAMBDA];                                                                                         \
+        if (COMPACT) crow_expand(F, X);                                                                                \
+        const float4* E = COMPACT ? X : F;                                                                             \
+        const ContactIds ci = contact_ids(E);                                                                          \
         V3 w0l = mk3(0.f, 0.f, 0.f), w0a = w0l, w1l = w0l, w1a = w0l;                                                  \
         if (ci.dyn0) ld_w(w, ci.id0, w0l, w0a);                                                                        \
         if (ci.dyn1) ld_w(w, ci.id1, w1l, w1a);                                                                        \
-        const float4 out = contact_solve(F, LAM, mu, ci.dyn0, ci.dyn1, w0l, w0a, w1l, w1a);                            \
+        const float4 out = contact_solve(E, LAM, mu, ci.dyn0, ci.dyn1, w0l, w0a, w1l, w1a);                            \
         if (ci.dyn0) st_w(w, ci.id0, w0l, w0a);                                                                        \
         if (ci.dyn1) st_w(w, ci.id1, w1l, w1a);                                                                        \
         rows[(unsigned)((c).base + lane) + (unsigned)CROW_LAMBDA * uNC] = out;                                         \
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
         // run unpipelined
         const int first_end = le.end_of(1, lane);
         const bool single = ncl == 1 && first_end <= 32;
-        float4 FA[CROW_LAMBDA], FB[CROW_LAMBDA], lamA, lamB;
+        float4 FA[NF], FB[NF], lamA, lamB;
         Chunk cur; cur.it = 0; cur.lev = 1; cur.base = 0; cur.p1 = first_end; cur.ok = true;
         if (single) {
             for (int it = 0; it < iters; ++it) {
@@ -136,7 +141,8 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
         } else {
             if (l2pf && ncl > 1) {
                 const int q0 = first_end, q1 = le.end_of(2, lane);
-                if (lane < CROW_FIELDS && q1 > q0) prefetch_l2_bulk(rows + (size_t)lane * uNC + q0, (unsigned)(q1 - q0) * 16u);
+                if (lane < CROW_FIELDS && (!COMPACT || lane < CROW_COMPACT_FIELDS || lane == CROW_LAMBDA) && q1 > q0)
+                    prefetch_l2_bulk(rows + (size_t)lane * uNC + q0, (unsigned)(q1 - q0) * 16u);
             }
             PIPE_ISSUE(FA, lamA, cur)
             while (true) {
@@ -160,9 +166,18 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
     for (int lev = 1, p0 = 0; lev <= ncl; ++lev) {
         const int p1 = le.end_of(lev, lane);
         for (int p = p0 + lane; p < p1; p += 32) {
-            float4 F[9];
+            float4 F[CROW_LAMBDA];
+            if (COMPACT) {
+                float4 C[CROW_COMPACT_FIELDS];
 #pragma unroll
-            for (int f = 0; f < 9; ++f) F[f] = __ldg(rows + ((unsigned)p + (unsigned)f * uNC));
+                for (int f = 0; f < 5; ++f) C[f] = __ldg(rows + ((unsigned)p + (unsigned)f * uNC));
+#pragma unroll
+                for (int f = 5; f < CROW_COMPACT_FIELDS; ++f) C[f] = make_float4(0.f, 0.f, 0.f, 0.f);     // contact_force reads n t b a0 a1 only
+                crow_expand(C, F);
+            } else {
+#pragma unroll
+                for (int f = 0; f < 9; ++f) F[f] = __ldg(rows + ((unsigned)p + (unsigned)f * uNC));
+            }
             const float4 lam = rows[(unsigned)p + (unsigned)CROW_LAMBDA * uNC];
             const ContactIds c = contact_ids(F);
             V3 fl, fa, wl, wa;
@@ -187,12 +202,24 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
 // padded 32 B accumulators unless they would keep the SM below 9 scenes
 static bool pp_pack24(int NB) { return ((size_t)NB * 32 + 1024) * 9 > 227u * 1024u; }
 
+template <bool W24, bool STREAM, bool COMPACT>
+static void pipe_variant(const View& v, float dt, int iters, float mu, cudaStream_t s, bool launch)
+{
+    if (launch) k_pgs_pipe<W24, STREAM, COMPACT><<<(unsigned)v.B, 32, (size_t)v.NB * (W24 ? 24 : 32), s>>>(v, dt, iters, mu);
+    else cudaFuncSetAttribute(k_pgs_pipe<W24, STREAM, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+}
+static void pipe_dispatch(const View& v, float dt, int iters, float mu, cudaStream_t s, bool launch, bool w24, bool stream, bool compact)
+{
+#define PV(a, b, c) pipe_variant<a, b, c>(v, dt, iters, mu, s, launch)
+    if (w24) { if (stream) { if (compact) PV(true, true, true); else PV(true, true, false); } else { if (compact) PV(true, false, true); else PV(true, false, false); } }
+    else     { if (stream) { if (compact) PV(false, true, true); else PV(false, true, false); } else { if (compact) PV(false, false, true); else PV(false, false, false); } }
+#undef PV
+}
+
 void init_pipe_kernels()
 {
-    cudaFuncSetAttribute(k_pgs_pipe<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_pgs_pipe<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_pgs_pipe<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(k_pgs_pipe<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    View v{};
+    for (int k = 0; k < 8; ++k) pipe_dispatch(v, 0.f, 0, 0.f, nullptr, false, k & 1, k & 2, k & 4);
 }
 
 // contexts without joint capacity whose scenes get one warp each (group 32)
@@ -202,19 +229,18 @@ bool level_pipe_wanted(const View& v, int group)
     const int on = e ? atoi(e) : 1;
     return on && group == 32 && v.NJ == 0 && (size_t)v.NB * 24 <= 200 * 1024;
 }
+// 13-field row records for those contexts (SLRBS_ROWS_COMPACT, read when a context is created)
+bool pipe_rows_compact()
+{
+    const char* e = getenv("SLRBS_ROWS_COMPACT");
+    return e ? atoi(e) != 0 : false;
+}
 
 void launch_pgs_pipe(const View& v, float dt, int iters, float mu, cudaStream_t s)
 {
     static int stream = -1;                                      // SLRBS_PIPE_STREAM=1: evict-first row loads (A/B switch)
     if (stream < 0) { const char* e = getenv("SLRBS_PIPE_STREAM"); stream = e ? atoi(e) : 0; }
-    const bool st = stream && v.B >= 256;
-    if (pp_pack24(v.NB)) {
-        if (st) k_pgs_pipe<true, true><<<(unsigned)v.B, 32, (size_t)v.NB * 24, s>>>(v, dt, iters, mu);
-        else k_pgs_pipe<true, false><<<(unsigned)v.B, 32, (size_t)v.NB * 24, s>>>(v, dt, iters, mu);
-    } else {
-        if (st) k_pgs_pipe<false, true><<<(unsigned)v.B, 32, (size_t)v.NB * 32, s>>>(v, dt, iters, mu);
-        else k_pgs_pipe<false, false><<<(unsigned)v.B, 32, (size_t)v.NB * 32, s>>>(v, dt, iters, mu);
-    }
+    pipe_dispatch(v, dt, iters, mu, s, true, pp_pack24(v.NB), stream && v.B >= 256, v.crow_compact != 0);
 }
 
 }  // namespace slrbs

@@ -13,22 +13,24 @@ pytestmark = pytest.mark.gpu
 DT = 0.01
 
 
-VARIANTS = {"lv": ("0", "0", "k_pgs_lv"), "split": ("1", "0", "k_pgs_sp"), "pipe": ("0", "1", "k_pgs_pipe")}
+# variant -> (SLRBS_PGS_SPLIT, SLRBS_PGS_PIPE, SLRBS_PGS_GACC, kernel name in slrbs_describe)
+VARIANTS = {"lv": ("0", "0", "0", "k_pgs_lv"), "split": ("1", "0", "0", "k_pgs_sp"), "pipe": ("0", "1", "0", "k_pgs_pipe"),
+            "gacc": ("0", "1", "1", "k_pgs_gacc")}
 
 
 def make(mode, oracles, group=None, variant=None, **kw):
     """variant: None = the library's choice; for the wide-scene groups "lv" = one lane per row (k_pgs_lv), "split" = two
     lanes per contact row (k_pgs_sp, groups 32 / 64), "pipe" = one warp per contact-only scene with register prefetch
-    (k_pgs_pipe, group 32)."""
+    (k_pgs_pipe, group 32), "gacc" = one warp per contact-only scene with the accumulators in global memory (k_pgs_gacc)."""
     os.environ["SLRBS_PGS_MODE"] = mode
     if group:
         os.environ["SLRBS_LEVEL_GROUP"] = str(group)
     if variant is not None:
-        os.environ["SLRBS_PGS_SPLIT"], os.environ["SLRBS_PGS_PIPE"] = VARIANTS[variant][:2]
+        os.environ["SLRBS_PGS_SPLIT"], os.environ["SLRBS_PGS_PIPE"], os.environ["SLRBS_PGS_GACC"] = VARIANTS[variant][:3]
     try:
         return context_from_oracles(oracles, **kw)
     finally:
-        for k in ("SLRBS_PGS_MODE", "SLRBS_LEVEL_GROUP", "SLRBS_PGS_SPLIT", "SLRBS_PGS_PIPE"):
+        for k in ("SLRBS_PGS_MODE", "SLRBS_LEVEL_GROUP", "SLRBS_PGS_SPLIT", "SLRBS_PGS_PIPE", "SLRBS_PGS_GACC"):
             os.environ.pop(k, None)
 
 
@@ -49,6 +51,7 @@ def jittered(scene, n, **kw):
     ("marble_box", {}, 5, 60, 8, None), ("marble_box", {}, 3, 25, 4, None), ("marble_box", {}, 3, 25, 16, None),
     ("marble_box", {}, 2, 25, 32, "lv"), ("marble_box", {}, 2, 25, 32, "split"), ("marble_box", {}, 2, 25, 64, "split"),
     ("marble_box", {}, 2, 25, 32, "pipe"), ("sphere_on_box", {}, 2, 120, 32, "pipe"), ("cylinder_on_plane", {}, 2, 80, 32, "pipe"),
+    ("marble_box", {}, 2, 25, 32, "gacc"), ("sphere_on_box", {}, 2, 120, 32, "gacc"), ("cylinder_on_plane", {}, 2, 80, 32, "gacc"),
     ("car", {}, 7, 80, 8, None), ("swinging_boxes", {}, 3, 60, 8, None), ("cylinder_on_plane", {}, 2, 80, 8, None),
     # joints and cylinder-plane contacts through the side-split kernel (its joint rows run on the even lanes)
     ("car", {}, 3, 80, 32, "split"), ("swinging_boxes", {}, 2, 60, 32, "split"), ("cylinder_on_plane", {}, 2, 80, 64, "split"),
@@ -58,7 +61,7 @@ def test_level_mode_is_bit_identical_to_sequential(scene, kw, n_scenes, steps, g
     a = make("thread", oracles, max_contacts=1024)
     b = make("level", oracles, group=group, variant=variant, max_contacts=1024)
     if variant is not None:
-        assert VARIANTS[variant][2] in b.describe(), b.describe()
+        assert VARIANTS[variant][3] in b.describe(), b.describe()
     for k in range(steps):
         a.step(DT); b.step(DT)
         if k in (0, 1, steps // 2, steps - 1):
@@ -111,17 +114,21 @@ def test_krylov_in_level_mode():
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("variant", ["lv", "split", "pipe"])
-def test_big_scene_variant_with_packed_accumulators(variant):
+@pytest.mark.parametrize("compact", ["0", "1"], ids=["rows256", "rows208"])
+@pytest.mark.parametrize("variant", ["lv", "split", "pipe", "gacc"])
+def test_big_scene_variant_with_packed_accumulators(variant, compact, monkeypatch):
     """Thousand-body scenes take the kernel variants with 24 B packed accumulators (9 instead of 7 scenes per SM): one
     lane per row (k_pgs_lv<32>), two lanes per contact row (k_pgs_sp<32>) or the register-pipelined warp (k_pgs_pipe, the
     default for contact-only scenes). All must still give the bits of the sequential kernel."""
+    if compact == "1" and variant in ("lv", "split"):
+        pytest.skip("13-field row records are read by k_pgs_pipe / k_pgs_gacc only")
+    monkeypatch.setenv("SLRBS_ROWS_COMPACT", compact)    # 208 B records: a0d, a1d recomputed from rr0, rr1, bit-identically
     oracles = jittered("marble_box_n", 2, nx=10, nz=10, ny=10)
     for o in oracles:
         o.step(DT, 60)                                   # let contacts with the walls and floor form
     a = make("thread", oracles, max_contacts=4096)
     b = make("level", oracles, group=32, variant=variant, max_contacts=4096)
-    assert VARIANTS[variant][2] in b.describe(), b.describe()
+    assert VARIANTS[variant][3] in b.describe(), b.describe()
     for k in range(12):
         a.step(DT); b.step(DT)
     a.sync(); b.sync()
@@ -134,4 +141,7 @@ def test_big_scene_variant_with_packed_accumulators(variant):
         assert_bit_equal(a.contacts(s)["lam"], b.contacts(s)["lam"], "big scene contact lambda")
         da, db = a.body_dyn(s), b.body_dyn(s)
         assert_bit_equal(da["fc"], db["fc"], "fc"); assert_bit_equal(da["tauc"], db["tauc"], "tauc")
+        ra, rb = a.contact_rows(s), b.contact_rows(s)        # the exported Jacobian blocks, whichever record form is stored
+        for key in ("J0", "J1", "J0Minv", "J1Minv", "A", "rhs"):
+            assert_bit_equal(ra[key], rb[key], f"big scene rows {key}")
     a.close(); b.close()
