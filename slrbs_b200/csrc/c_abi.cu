@@ -187,7 +187,10 @@ int slrbs_describe(slrbs_ctx* c, char* buf, int buf_len)
 {
     if (!c || !buf || buf_len <= 0) return fail(SLRBS_E_ARG, "slrbs_describe: bad argument");
     char tmp[256];
-    if (c->v.level_mode && c->level_variant == 4)
+    if (c->v.level_mode && c->level_variant == 5)
+        std::snprintf(tmp, sizeof tmp, "solver=k_pgs_stage (level-scheduled, 1 warp/scene, next chunk's 208 B rows staged in shared memory by cp.async) detect=%s graph=%d",
+                      detect_variant(c->v, c->broadphase), c->use_graph);
+    else if (c->v.level_mode && c->level_variant == 4)
         std::snprintf(tmp, sizeof tmp, "solver=k_pgs_gacc (level-scheduled, 1 warp/scene, accumulators in L1/L2, 18 warps/SM, %s B rows) detect=%s graph=%d",
                       c->v.crow_compact ? "208" : "256", detect_variant(c->v, c->broadphase), c->use_graph);
     else if (c->v.color_mode)
@@ -251,8 +254,8 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
         else v.level_mode = (n_scenes <= 8192 && fits) ? 1 : 0;
         const char* g = std::getenv("SLRBS_LEVEL_GROUP");
         c->level_group = level_group_size(v, g ? std::atoi(g) : 0);
-        c->level_variant = !v.level_mode ? 0 : (v.color_mode ? 3 : (level_split_wanted(v, c->level_group) ? 1 : (level_gacc_wanted(v, c->level_group) ? 4 : (level_pipe_wanted(v, c->level_group) ? 2 : 0))));
-        v.crow_compact = ((c->level_variant == 2 || c->level_variant == 4) && pipe_rows_compact()) ? 1 : 0;
+        c->level_variant = !v.level_mode ? 0 : (v.color_mode ? 3 : (level_split_wanted(v, c->level_group) ? 1 : (level_gacc_wanted(v, c->level_group) ? 4 : (level_stage_wanted(v, c->level_group) ? 5 : (level_pipe_wanted(v, c->level_group) ? 2 : 0)))));
+        v.crow_compact = (c->level_variant == 5 || ((c->level_variant == 2 || c->level_variant == 4) && pipe_rows_compact())) ? 1 : 0;
         if (v.color_mode) c->use_graph = 0;                     // the solver is one cooperative launch; such scenes are not launch bound
         const char* bp = std::getenv("SLRBS_BROADPHASE");
         if (bp) c->broadphase = std::atoi(bp) ? 1 : 0;

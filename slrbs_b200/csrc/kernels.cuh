@@ -52,7 +52,7 @@ void launch_build_sdf(const float* verts, int nt, const int* tris, int nx, int n
 void launch_joint_levels(const View& v, cudaStream_t s);
 void launch_contact_levels(const View& v, cudaStream_t s);
 size_t contact_levels_smem(int NB, int NC);
-void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, int variant, cudaStream_t s);   // variant: 0 k_pgs_lv, 1 k_pgs_sp, 2 k_pgs_pipe, 4 k_pgs_gacc
+void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, int variant, cudaStream_t s);   // variant: 0 k_pgs_lv, 1 k_pgs_sp, 2 k_pgs_pipe, 4 k_pgs_gacc, 5 k_pgs_stage
 int  level_group_size(const View& v, int requested);
 // pgs_split.cu: the level schedule with two lanes per contact row (one per body side); rows = 32 or 64 rows per level step
 void init_split_kernels();
@@ -63,6 +63,10 @@ void init_pipe_kernels();
 void launch_pgs_pipe(const View& v, float dt, int iters, float mu, cudaStream_t s);
 bool level_pipe_wanted(const View& v, int group);
 bool pipe_rows_compact();
+// pgs_stage.cu: one warp per contact-only scene, next chunk's compact row records copied to shared memory by cp.async
+void init_stage_kernels();
+void launch_pgs_stage(const View& v, float dt, int iters, float mu, cudaStream_t s);
+bool level_stage_wanted(const View& v, int group);
 // pgs_gacc.cu: one warp per contact-only scene, accumulators in global memory (L1 / L2), 18 warps per SM
 void init_gacc_kernels();
 void launch_pgs_gacc(const View& v, float dt, int iters, float mu, cudaStream_t s);

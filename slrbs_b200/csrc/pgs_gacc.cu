@@ -141,19 +141,13 @@ void init_gacc_kernels()
     cudaFuncSetAttribute(k_pgs_gacc<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
 }
 
-// Contact-only contexts (group 32) whose batch is more than the scene-resident kernels hold in one wave (9 scenes per SM):
-// twice the residency pays; smaller batches are all resident either way and keep the faster shared-memory gather.
-// SLRBS_PGS_GACC = 0 / 1 forces (read when a context is created).
+// Contact-only contexts (group 32); SLRBS_PGS_GACC=1 selects it (read when a context is created).
 bool level_gacc_wanted(const View& v, int group)
 {
     if (group != 32 || v.NJ != 0) return false;
+    // opt-in: measured slower than the shared-memory kernels on marble_box_1k x 2664 (5.9 vs 4.7 ms, profiles/README.md)
     const char* e = getenv("SLRBS_PGS_GACC");
-    if (e) return atoi(e) != 0;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int smem_per_sm = (int)((227u * 1024u) / ((size_t)v.NB * 24 + 1024));
-    return (long)v.B > (long)sms * smem_per_sm;
+    return e && atoi(e) != 0;
 }
 
 void launch_pgs_gacc(const View& v, float dt, int iters, float mu, cudaStream_t s)

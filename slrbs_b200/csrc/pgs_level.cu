@@ -441,6 +441,7 @@ void init_level_kernels()
     init_split_kernels();
     init_pipe_kernels();
     init_gacc_kernels();
+    init_stage_kernels();
     cudaFuncSetAttribute(k_contact_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
@@ -471,6 +472,7 @@ void launch_pgs_level(const View& v, float dt, int iters, float mu, int group, i
     if (variant == 1) { launch_pgs_split(v, dt, iters, mu, group, s); return; }
     if (variant == 2) { launch_pgs_pipe(v, dt, iters, mu, s); return; }
     if (variant == 4) { launch_pgs_gacc(v, dt, iters, mu, s); return; }
+    if (variant == 5) { launch_pgs_stage(v, dt, iters, mu, s); return; }
     switch (group) {
     case 4:  launch_lv<4>(v, dt, iters, mu, s); break;
     case 8:  launch_lv<8>(v, dt, iters, mu, s); break;

@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 DT = 0.01
 
 
-# variant -> (SLRBS_PGS_SPLIT, SLRBS_PGS_PIPE, SLRBS_PGS_GACC, kernel name in slrbs_describe)
-VARIANTS = {"lv": ("0", "0", "0", "k_pgs_lv"), "split": ("1", "0", "0", "k_pgs_sp"), "pipe": ("0", "1", "0", "k_pgs_pipe"),
-            "gacc": ("0", "1", "1", "k_pgs_gacc")}
+# variant -> (SLRBS_PGS_SPLIT, SLRBS_PGS_PIPE, SLRBS_PGS_GACC, SLRBS_PGS_STAGE, kernel name in slrbs_describe)
+VARIANTS = {"lv": ("0", "0", "0", "0", "k_pgs_lv"), "split": ("1", "0", "0", "0", "k_pgs_sp"), "pipe": ("0", "1", "0", "0", "k_pgs_pipe"),
+            "gacc": ("0", "1", "1", "0", "k_pgs_gacc"), "stage": ("0", "1", "0", "1", "k_pgs_stage")}
 
 
 def make(mode, oracles, group=None, variant=None, **kw):
@@ -26,11 +26,12 @@ def make(mode, oracles, group=None, variant=None, **kw):
     if group:
         os.environ["SLRBS_LEVEL_GROUP"] = str(group)
     if variant is not None:
-        os.environ["SLRBS_PGS_SPLIT"], os.environ["SLRBS_PGS_PIPE"], os.environ["SLRBS_PGS_GACC"] = VARIANTS[variant][:3]
+        (os.environ["SLRBS_PGS_SPLIT"], os.environ["SLRBS_PGS_PIPE"], os.environ["SLRBS_PGS_GACC"],
+         os.environ["SLRBS_PGS_STAGE"]) = VARIANTS[variant][:4]
     try:
         return context_from_oracles(oracles, **kw)
     finally:
-        for k in ("SLRBS_PGS_MODE", "SLRBS_LEVEL_GROUP", "SLRBS_PGS_SPLIT", "SLRBS_PGS_PIPE", "SLRBS_PGS_GACC"):
+        for k in ("SLRBS_PGS_MODE", "SLRBS_LEVEL_GROUP", "SLRBS_PGS_SPLIT", "SLRBS_PGS_PIPE", "SLRBS_PGS_GACC", "SLRBS_PGS_STAGE"):
             os.environ.pop(k, None)
 
 
@@ -52,6 +53,7 @@ def jittered(scene, n, **kw):
     ("marble_box", {}, 2, 25, 32, "lv"), ("marble_box", {}, 2, 25, 32, "split"), ("marble_box", {}, 2, 25, 64, "split"),
     ("marble_box", {}, 2, 25, 32, "pipe"), ("sphere_on_box", {}, 2, 120, 32, "pipe"), ("cylinder_on_plane", {}, 2, 80, 32, "pipe"),
     ("marble_box", {}, 2, 25, 32, "gacc"), ("sphere_on_box", {}, 2, 120, 32, "gacc"), ("cylinder_on_plane", {}, 2, 80, 32, "gacc"),
+    ("marble_box", {}, 2, 25, 32, "stage"), ("sphere_on_box", {}, 2, 120, 32, "stage"), ("cylinder_on_plane", {}, 2, 80, 32, "stage"),
     ("car", {}, 7, 80, 8, None), ("swinging_boxes", {}, 3, 60, 8, None), ("cylinder_on_plane", {}, 2, 80, 8, None),
     # joints and cylinder-plane contacts through the side-split kernel (its joint rows run on the even lanes)
     ("car", {}, 3, 80, 32, "split"), ("swinging_boxes", {}, 2, 60, 32, "split"), ("cylinder_on_plane", {}, 2, 80, 64, "split"),
@@ -61,7 +63,7 @@ def test_level_mode_is_bit_identical_to_sequential(scene, kw, n_scenes, steps, g
     a = make("thread", oracles, max_contacts=1024)
     b = make("level", oracles, group=group, variant=variant, max_contacts=1024)
     if variant is not None:
-        assert VARIANTS[variant][3] in b.describe(), b.describe()
+        assert VARIANTS[variant][4] in b.describe(), b.describe()
     for k in range(steps):
         a.step(DT); b.step(DT)
         if k in (0, 1, steps // 2, steps - 1):
@@ -115,20 +117,22 @@ def test_krylov_in_level_mode():
 
 
 @pytest.mark.parametrize("compact", ["0", "1"], ids=["rows256", "rows208"])
-@pytest.mark.parametrize("variant", ["lv", "split", "pipe", "gacc"])
+@pytest.mark.parametrize("variant", ["lv", "split", "pipe", "gacc", "stage"])
 def test_big_scene_variant_with_packed_accumulators(variant, compact, monkeypatch):
     """Thousand-body scenes take the kernel variants with 24 B packed accumulators (9 instead of 7 scenes per SM): one
     lane per row (k_pgs_lv<32>), two lanes per contact row (k_pgs_sp<32>) or the register-pipelined warp (k_pgs_pipe, the
     default for contact-only scenes). All must still give the bits of the sequential kernel."""
     if compact == "1" and variant in ("lv", "split"):
-        pytest.skip("13-field row records are read by k_pgs_pipe / k_pgs_gacc only")
+        pytest.skip("13-field row records are read by k_pgs_pipe / k_pgs_gacc / k_pgs_stage only")
+    if compact == "0" and variant == "stage":
+        pytest.skip("k_pgs_stage always reads the 13-field records")
     monkeypatch.setenv("SLRBS_ROWS_COMPACT", compact)    # 208 B records: a0d, a1d recomputed from rr0, rr1, bit-identically
     oracles = jittered("marble_box_n", 2, nx=10, nz=10, ny=10)
     for o in oracles:
         o.step(DT, 60)                                   # let contacts with the walls and floor form
     a = make("thread", oracles, max_contacts=4096)
     b = make("level", oracles, group=32, variant=variant, max_contacts=4096)
-    assert VARIANTS[variant][3] in b.describe(), b.describe()
+    assert VARIANTS[variant][4] in b.describe(), b.describe()
     for k in range(12):
         a.step(DT); b.step(DT)
     a.sync(); b.sync()
