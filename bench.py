@@ -38,7 +38,7 @@ SOLVER_ITERS = 10   # RigidBodySystem.cpp:22
 MU = 0.8            # Contact.cpp:4
 BYTES_PER_CONTACT_VISIT = 464
 BYTES_PER_HINGE_VISIT = 744
-E2E_CHUNKS = int(os.environ.get("SLRBS_E2E_CHUNKS", "8"))                  # contexts the batch is split into for the end-to-end arm (transfer / compute overlap)
+E2E_CHUNKS = int(os.environ.get("SLRBS_E2E_CHUNKS", "4"))                  # contexts the batch is split into for the end-to-end arm (transfer / compute overlap)
 
 # --workload mixed_pile: BASELINE configs[3], 10 002 mixed spheres / boxes / closed meshes in ONE scene (slrbs_b200/scenes.py):
 # extension contact pairs, SDF meshes, pair-parallel detection, graph-coloured solver; handled by build_batch()
