@@ -439,6 +439,18 @@ class DevicePile:
     def _rebuild(self, first=False):
         import time
         torch = self.torch
+        grow = 0
+        if self.ctx is not None and not first:
+            # the steps since the last re-partition are still in flight (nothing synchronises them any more): wait for them
+            # here so that the rebuild's own time is what gets counted below
+            try:
+                self.ctx.sync()
+            except SlrbsError as e:
+                # a block produced more contacts than its scene holds since the last re-partition (they were dropped for
+                # those steps): the states are complete all the same; rebuild into a context with more contact slots
+                if "more contacts" not in str(e):
+                    raise
+                grow = 1
         t0 = time.perf_counter()
         if self.ctx is None:
             self._make_ctx()
@@ -446,15 +458,7 @@ class DevicePile:
             self.table.zero_(); self.vmax2.zero_()
             torch.cuda.synchronize(self.device)
             self.ctx.pile_export(self.table.data_ptr(), self.vmax2.data_ptr())
-            grow = 0
-            try:
-                self.ctx.sync()
-            except SlrbsError as e:
-                # a block produced more contacts than its scene holds since the last re-partition (they were dropped for
-                # those steps): the exported states are complete all the same; rebuild into a context with more contact slots
-                if "more contacts" not in str(e):
-                    raise
-                grow = 1
+            self.ctx.sync()
             if self.world > 1:
                 self.dist.all_reduce(self.table)                                   # disjoint owners: sum = gather
                 self.dist.all_reduce(self.vmax2, op=self.dist.ReduceOp.MAX)        # float bits of v^2 >= 0 order like ints
