@@ -46,6 +46,45 @@ template <> struct Acc<true> {
     }
 };
 
+// The same accumulators addressed in the shared state space (32-bit address, ld.shared / st.shared): through a generic
+// pointer the compiler re-derives the shared window base (S2R SR_CgaCtaId, a ~25-cycle read, + MOV + LEA) in front of
+// every gather and every scatter of the sweep.
+template <bool W24> struct AccSh;
+template <> struct AccSh<true> {
+    static __device__ __forceinline__ void ld(unsigned base, int body, V3& l, V3& a)
+    {
+        const unsigned ad = base + (unsigned)body * 24u;
+        float2 p0, p1, p2;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(p0.x), "=f"(p0.y) : "r"(ad));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+8];" : "=f"(p1.x), "=f"(p1.y) : "r"(ad));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+16];" : "=f"(p2.x), "=f"(p2.y) : "r"(ad));
+        l = mk3(p0.x, p0.y, p1.x); a = mk3(p1.y, p2.x, p2.y);
+    }
+    static __device__ __forceinline__ void st(unsigned base, int body, const V3& l, const V3& a)
+    {
+        const unsigned ad = base + (unsigned)body * 24u;
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ad), "f"(l.x), "f"(l.y) : "memory");
+        asm volatile("st.shared.v2.f32 [%0+8], {%1, %2};" ::"r"(ad), "f"(l.z), "f"(a.x) : "memory");
+        asm volatile("st.shared.v2.f32 [%0+16], {%1, %2};" ::"r"(ad), "f"(a.y), "f"(a.z) : "memory");
+    }
+};
+template <> struct AccSh<false> {
+    static __device__ __forceinline__ void ld(unsigned base, int body, V3& l, V3& a)
+    {
+        const unsigned ad = base + (unsigned)body * 32u;
+        float4 p0, p1;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p0.x), "=f"(p0.y), "=f"(p0.z), "=f"(p0.w) : "r"(ad));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(p1.x), "=f"(p1.y), "=f"(p1.z), "=f"(p1.w) : "r"(ad));
+        l = mk3(p0); a = mk3(p1);
+    }
+    static __device__ __forceinline__ void st(unsigned base, int body, const V3& l, const V3& a)
+    {
+        const unsigned ad = base + (unsigned)body * 32u;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "f"(l.x), "f"(l.y), "f"(l.z), "f"(0.f) : "memory");
+        asm volatile("st.shared.v4.f32 [%0+16], {%1, %2, %3, %4};" ::"r"(ad), "f"(a.x), "f"(a.y), "f"(a.z), "f"(0.f) : "memory");
+    }
+};
+
 // level-ordered row streams ([scene][field][pos], layout.cuh mode 1) addressed without the layout-mode test of at_crow
 __device__ __forceinline__ const float4* crow_scene(const View& v, int scene) { return v.crow + (size_t)scene * CROW_FIELDS * v.NC; }
 

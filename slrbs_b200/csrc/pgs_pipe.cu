@@ -23,8 +23,8 @@
 
 namespace slrbs {
 
-#define ld_w Acc<W24>::ld
-#define st_w Acc<W24>::st
+#define ld_w AccSh<W24>::ld
+#define st_w AccSh<W24>::st
 
 namespace {
 
@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
     if (STREAM) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
     extern __shared__ float4 smem_pp4[];
     float* w = reinterpret_cast<float*>(smem_pp4);
+    unsigned wsh = (unsigned)__cvta_generic_to_shared(w);        // accumulators in the shared state space (pgs_level.cuh: AccSh)
+    asm volatile("" : "+r"(wsh));
     const int scene = blockIdx.x, lane = threadIdx.x;
     const int nb = v.nbodies[scene], nc = v.ncontacts[scene];
     const int ncl = nc > 0 ? v.nclev[scene] : 0;                  // no rows, no levels (stale tables are never walked)
@@ -117,11 +119,11 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
         const float4* E = COMPACT ? X : F;                                                                             \
         const ContactIds ci = contact_ids(E);                                                                          \
         V3 w0l = mk3(0.f, 0.f, 0.f), w0a = w0l, w1l = w0l, w1a = w0l;                                                  \
-        if (ci.dyn0) ld_w(w, ci.id0, w0l, w0a);                                                                        \
-        if (ci.dyn1) ld_w(w, ci.id1, w1l, w1a);                                                                        \
+        if (ci.dyn0) ld_w(wsh, ci.id0, w0l, w0a);                                                                        \
+        if (ci.dyn1) ld_w(wsh, ci.id1, w1l, w1a);                                                                        \
         const float4 out = contact_solve(E, LAM, mu, ci.dyn0, ci.dyn1, w0l, w0a, w1l, w1a);                            \
-        if (ci.dyn0) st_w(w, ci.id0, w0l, w0a);                                                                        \
-        if (ci.dyn1) st_w(w, ci.id1, w1l, w1a);                                                                        \
+        if (ci.dyn0) st_w(wsh, ci.id0, w0l, w0a);                                                                        \
+        if (ci.dyn1) st_w(wsh, ci.id1, w1l, w1a);                                                                        \
         rows[(unsigned)((c).base + lane) + (unsigned)CROW_LAMBDA * uNC] = out;                                         \
     }                                                                                                                  \
     __syncwarp();
@@ -181,15 +183,15 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
             const float4 lam = rows[(unsigned)p + (unsigned)CROW_LAMBDA * uNC];
             const ContactIds c = contact_ids(F);
             V3 fl, fa, wl, wa;
-            if (c.dyn0) { contact_force(F, lam, dt, 0, fl, fa); ld_w(w, c.id0, wl, wa); st_w(w, c.id0, wl + fl, wa + fa); }
-            if (c.dyn1) { contact_force(F, lam, dt, 1, fl, fa); ld_w(w, c.id1, wl, wa); st_w(w, c.id1, wl + fl, wa + fa); }
+            if (c.dyn0) { contact_force(F, lam, dt, 0, fl, fa); ld_w(wsh, c.id0, wl, wa); st_w(wsh, c.id0, wl + fl, wa + fa); }
+            if (c.dyn1) { contact_force(F, lam, dt, 1, fl, fa); ld_w(wsh, c.id1, wl, wa); st_w(wsh, c.id1, wl + fl, wa + fa); }
         }
         p0 = p1;
         __syncwarp();
     }
     for (int i = lane; i < nb; i += 32) {
         V3 fl, fa;
-        ld_w(w, i, fl, fa);
+        ld_w(wsh, i, fl, fa);
         v.wl[at(v, i, scene)] = mk4(fl, 0.f);
         v.wa[at(v, i, scene)] = mk4(fa, 0.f);
     }
