@@ -303,11 +303,33 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
+    # the reference viewer's per-frame traffic (SimViewer.cpp:40-45 reads every body's x and q; a PreStepFunc writes f and tau,
+    # RigidBodySystem.cpp:70-73): forces up (24 B / body), poses down (28 B / body), the state itself stays on the device
+    hf, ht = [torch.zeros((B, nb, 3), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    fptr = [[t.data_ptr() + 4 * 3 * nb * s0 for t in (hf, ht)] for _, s0, _ in chunks]
+
+    def poses_run(nsteps):
+        for _ in range(nsteps):
+            for (c, _, n_sc), pp, fp in zip(chunks, cptr, fptr):
+                c.set_external_forces_raw(n_sc, nb, fp[0], fp[1])      # H2D (waits for the chunk's previous download too)
+                c.step(DT, 1)
+                c.download_state_raw_async(n_sc, nb, pp[0], pp[1], 0, 0)   # D2H: x and q
+        for c, _, _ in chunks:
+            c.sync()
+
+    poses_run(2)
+    barrier()
+    t0 = time.perf_counter()
+    poses_run(e2e_steps)
+    torch.cuda.synchronize()
+    poses_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
     for c, _, _ in chunks:
         if c is not ctx:
             c.close()
 
     from slrbs_b200 import sharding
+    poses_ms = sharding.reduce_over_ranks([poses_ms], "max")[0]
     ms, e2e_ms, h2d_inv, d2h_inv = sharding.reduce_over_ranks([ms, e2e_ms, 1.0 / pcie["h2d"], 1.0 / pcie["d2h"]], "max")   # device time: max over ranks
     agg = [prof["solve_ms"], float(prof["solve_launches"]), float(prof["contact_visits"]), float(prof["joint_visits"]),
            float(prof["total_launches"])]                                    # roofline / launches: rank 0's GPU
@@ -361,7 +383,12 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "body-steps/s", "h2d_bytes_per_step": int(B * nb * 13 * 4),
                 "d2h_bytes_per_step": int(B * nb * 13 * 4), "steps": e2e_steps, "contexts": len(chunks),
                 "payload": "x,q,v,omega of every body up and down every step (13 floats each way)",
-                "host_link_gbs_per_rank_all_ranks_copying": {"h2d": 1.0 / h2d_inv, "d2h": 1.0 / d2h_inv}},
+                "host_link_gbs_per_rank_all_ranks_copying": {"h2d": 1.0 / h2d_inv, "d2h": 1.0 / d2h_inv},
+                # informational second protocol, NOT the headline: what the reference's own viewer loop moves per frame
+                "forces_up_poses_down": {"value": sharding.job_throughput(float(B) * nb * e2e_steps, world, poses_ms), "unit": "body-steps/s",
+                                         "h2d_bytes_per_step": int(B * nb * 6 * 4), "d2h_bytes_per_step": int(B * nb * 7 * 4),
+                                         "payload": "f, tau of every body up (what a PreStepFunc produces), x, q of every body down (what "
+                                                    "SimViewer reads); the state stays on the device"}},
         "gpu_launches": launches_timed,
         "clocks": clocks,
     }

@@ -240,6 +240,11 @@ class Context:
         cast = lambda p: None if not p else C.cast(p, C.POINTER(C.c_float))
         self._ck(self.L.slrbs_download_state_async(self.h, scene0, ns, n, cast(px), cast(pq), cast(pv), cast(pw)))
 
+    def set_external_forces_raw(self, ns, n, pf, pt, scene0=0, absolute=False):
+        """Raw host pointers (ints) to [ns][n][3] force / torque arrays, e.g. pinned torch tensors' data_ptr()."""
+        cast = lambda p: None if not p else C.cast(p, C.POINTER(C.c_float))
+        self._ck(self.L.slrbs_set_external_forces(self.h, scene0, ns, n, cast(pf), cast(pt), int(bool(absolute))))
+
     def download_state(self, scene0=0, n_scenes=None, n_bodies=None):
         ns = n_scenes or (self.n_scenes - scene0)
         n = n_bodies or self.n_bodies
