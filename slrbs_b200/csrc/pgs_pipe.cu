@@ -146,6 +146,25 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
                 if (lane < CROW_FIELDS && (!COMPACT || lane < CROW_COMPACT_FIELDS || lane == CROW_LAMBDA) && q1 > q0)
                     prefetch_l2_bulk(rows + (size_t)lane * uNC + q0, (unsigned)(q1 - q0) * 16u);
             }
+#ifndef SLRBS_PIPE_TWO_BUFFERS
+            // ONE landing buffer FB, copied into FA before the next chunk's loads are issued into it. The copy is the point: ptxas
+            // puts every row load on one scoreboard (a counter), so "wait for chunk k's rows" also waits for chunk k+1's loads
+            // if those have been issued already. With two alternating buffers (the #else branch, round-2's first version) the
+            // solve of chunk k read registers a load had written, and its first instruction carried that wait -- the loads
+            // were early but nothing ran under them (profiles/README.md). Here the wait sits on the copy, BEFORE the next
+            // loads are issued, and the solve reads only registers written by MOVs: nothing in it touches the load scoreboard
+            // (checked in the SASS control bits), so the next chunk's 13 LDG.128 are in flight for the whole solve.
+            PIPE_ISSUE(FB, lamB, cur)
+            while (true) {
+                _Pragma("unroll") for (int f = 0; f < NF; ++f) FA[f] = FB[f];
+                lamA = lamB;
+                Chunk nxt = advance(cur);
+                PIPE_ISSUE(FB, lamB, nxt)
+                PIPE_SOLVE(FA, lamA, cur)
+                if (!nxt.ok) break;
+                cur = nxt;
+            }
+#else
             PIPE_ISSUE(FA, lamA, cur)
             while (true) {
                 Chunk nxt = advance(cur);
@@ -157,6 +176,7 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
                 PIPE_SOLVE(FB, lamB, nxt)
                 if (!cur.ok) break;
             }
+#endif
         }
     }
 #undef PIPE_ISSUE
