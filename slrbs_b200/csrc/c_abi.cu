@@ -274,6 +274,10 @@ int slrbs_create(slrbs_ctx** out, int device, int n_scenes, int max_bodies, int 
     A(v.cids, nc) A(v.cp, nc) A(v.cn, nc) A(v.crow, (size_t)CROW_FIELDS * v.NC * bpad)
     { SdfShape* tab = nullptr; A(tab, MAX_SDF_SHAPES) v.sdf_shapes = tab; }
     if (c->level_variant == 4) { A(v.wacc, 2 * nb) }
+    if (c->level_variant == 2) {                               // chunks of a sweep <= levels + rows / 32 <= NC + NC / 32
+        v.cchunk_cap = v.NC + v.NC / 32 + 2;
+        A(v.cchunk, (size_t)v.cchunk_cap * v.B)
+    }
     if (v.color_mode) {
         A(v.cmask, nb) A(v.cwin, nb) A(v.nclev_max, 1)
         // scenes no single CTA can hold are detected pair-parallel over the whole GPU (detect_pairs.cu), extension pairs or not

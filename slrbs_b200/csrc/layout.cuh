@@ -115,6 +115,9 @@ struct View {
     int     crow_compact;
     unsigned long long *cmask, *cwin;   // [B][NB] colours used by a body's contacts | lowest bid among its uncoloured contacts
     int    *nclev_max;  // [1] largest colour count over the scenes (reset by k_prepare)
+    // chunk table of k_pgs_pipe (pgs_pipe.cu): [B][cchunk_cap] entries `base | count << 16`, written and read by the scene's warp
+    unsigned *cchunk;
+    int     cchunk_cap;
 };
 
 __host__ __device__ __forceinline__ size_t at(const View& v, int slot, int scene) { return (size_t)slot * v.B + scene; }

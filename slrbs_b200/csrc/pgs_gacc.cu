@@ -66,8 +66,7 @@ __global__ void __launch_bounds__(32, 18) k_pgs_gacc(View v, float dt, int iters
                 int q0 = p1, q1 = p1;
                 if (lev < ncl) q1 = lev_end[(size_t)(lev + 1) * B];
                 else if (it + 1 < iters) { q0 = 0; q1 = lev_end[B]; }
-                if (lane < CROW_FIELDS && (!COMPACT || lane < CROW_COMPACT_FIELDS || lane == CROW_LAMBDA) && q1 > q0)
-                    prefetch_l2_bulk(rows + (size_t)lane * uNC + q0, (unsigned)(q1 - q0) * 16u);
+                if (q1 > q0) prefetch_rows_l2(rows, uNC, q0, q1, NF, lane, 32);
             }
             for (int p = p0 + lane; p < p1; p += 32) {
                 float4 S[NF];

@@ -276,15 +276,8 @@ __global__ void __launch_bounds__(LvCfg<G>::THREADS, MINB) k_pgs_lv(View v, floa
                 int q0 = p1, q1 = p1;
                 if (lev < ncl) q1 = v.clev_end[at(v, lev + 1, scene)];
                 else if (it + 1 < iters) { q0 = 0; q1 = v.clev_end[at(v, 1, scene)]; }
-                if (LV_BULK_PREFETCH) {
-                    // the rows of a level are contiguous per field ([scene][field][pos]): one bulk L2 prefetch per field
-                    if (gl < CROW_FIELDS && q1 > q0) prefetch_l2_bulk(&v.crow[at_crow(v, gl, q0, scene)], (unsigned)(q1 - q0) * 16u);
-                } else {
-                    for (int q = q0 + gl; q < q1; q += G) {
-#pragma unroll
-                        for (int f = 0; f < CROW_FIELDS; ++f) prefetch_l2(&v.crow[at_crow(v, f, q, scene)]);
-                    }
-                }
+                // the rows of a level are contiguous per field ([scene][field][pos]): one prefetch per 128 B line
+                if (q1 > q0) prefetch_rows_l2(v.crow + (size_t)scene * CROW_FIELDS * (size_t)v.NC, (unsigned)v.NC, q0, q1, CROW_LAMBDA, gl, G);
             }
             for (int p = p0 + gl; p < p1; p += G) {
                 float4 F[CROW_FIELDS];

@@ -10,9 +10,20 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
 }
-#ifndef LV_BULK_PREFETCH
-#define LV_BULK_PREFETCH 1
-#endif
+// Pull positions [q0, q1) of fields 0 .. nf-1 and of the impulse field of one scene's record stream (`rows`, [field][pos],
+// uNC positions per field) towards L2, the (field, 128 B line) pairs dealt over `width` lanes, one prefetch.global.L2 each.
+// (Round 2 used one cp.async.bulk.prefetch per field here; that instruction takes its address from a uniform register, so
+// with a different address per lane the compiler emits a loop over the lanes -- 100 instructions per level and a third of
+// k_pgs_pipe's stall samples, profiles/README.md.)
+__device__ __forceinline__ void prefetch_rows_l2(const float4* rows, unsigned uNC, int q0, int q1, int nf, int lane, int width)
+{
+    const int nl = ((q1 - q0 + 7) >> 3) + 1;                     // lines a span can touch when q0 is not line aligned
+    for (int idx = lane; idx < (nf + 1) * nl; idx += width) {
+        const int ln = idx / (nf + 1), fi = idx - ln * (nf + 1);
+        const int row = min(q0 + 8 * ln, q1 - 1);
+        prefetch_l2(rows + ((unsigned)(fi < nf ? fi : CROW_LAMBDA) * uNC + (unsigned)row));
+    }
+}
 
 // shared-memory accumulators of one scene, per body (linear xyz, angular xyz): either two padded float4 (32 B, two
 // 16 B accesses: best when shared memory is plentiful) or three float2 (24 B: a 1000-body scene then needs 24 KB and 9

@@ -28,25 +28,30 @@ namespace slrbs {
 
 namespace {
 
-// chunk = up to 32 consecutive positions [base, min(base + 32, p1)) of level `lev` in sweep `it`
-struct Chunk { int it, lev, base, p1; bool ok; };
+// One entry of a scene's chunk table: up to 32 consecutive positions of ONE level, `base | count << 16` (positions are below
+// 65535 in level mode, slrbs_create). A sweep is the table walked front to back; every sweep walks the same table.
+enum : unsigned { CH_FORCE = 0x80000000u };                        // set on the entries of the pass that forms the constraint forces
+__device__ __forceinline__ int ch_base(unsigned e) { return (int)(e & 0xffffu); }
+__device__ __forceinline__ int ch_count(unsigned e) { return (int)((e >> 16) & 0x3fu); }
 
-// level ends, 32 at a time in a register per lane (one strided load per 32 levels instead of one dependent load in
-// front of every level's prefetch)
-struct LevelEnds {
-    const int* lev_end; size_t B; int ncl, blk, ends;
-    __device__ __forceinline__ void init(const int* p, size_t b, int n) { lev_end = p; B = b; ncl = n; blk = -1; ends = 0; }
-    // end position of level L (1-based; L = 0 gives 0)
-    __device__ __forceinline__ int end_of(int L, int lane)
+// cursor over (sweep, chunk) for `sweeps` passes over a table of `nch` entries, 32 entries at a time in a register per lane
+struct ChunkCursor {
+    const unsigned* tab; int nch, sweeps, force_sweep, k, it, blk; unsigned reg;
+    __device__ __forceinline__ void init(const unsigned* t, int n, int sw, int fs) { tab = t; nch = n; sweeps = sw; force_sweep = fs; k = 0; it = 0; blk = -1; reg = 0; }
+    // next entry, 0 when all sweeps have been handed out
+    __device__ __forceinline__ unsigned next(int lane)
     {
-        if (L <= 0) return 0;
-        const int b = (L - 1) >> 5;
-        if (b != blk) {                                           // warp-uniform
-            const int l = (b << 5) + 1 + lane;
-            ends = l <= ncl ? lev_end[(size_t)l * B] : 0;
+        if (it >= sweeps) return 0u;
+        const int b = k >> 5;
+        if (b != blk) {                                           // warp-uniform; the table was written by this warp (plain loads)
+            const int i = (b << 5) + lane;
+            reg = i < nch ? tab[i] : 0u;
             blk = b;
         }
-        return __shfl_sync(0xffffffffu, ends, (L - 1) & 31);
+        unsigned e = __shfl_sync(0xffffffffu, reg, k & 31);
+        if (it == force_sweep) e |= CH_FORCE;
+        if (++k == nch) { k = 0; ++it; }
+        return e;
     }
 };
 
@@ -64,9 +69,10 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p, unsigned long long
 }
 
 template <bool W24, bool STREAM, bool COMPACT>
-__global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters, float mu)
+__global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters, float mu, int l2mode)
 {
     constexpr int NF = COMPACT ? CROW_COMPACT_FIELDS : CROW_LAMBDA;      // read-only fields of a stored record
+    constexpr int NFORCE = COMPACT ? 5 : 9;                       // the fields contact_force needs: n t b rr0 rr1 | n t b a0* a1*
     unsigned long long policy = 0;
     if (STREAM) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
     extern __shared__ float4 smem_pp4[];
@@ -79,136 +85,149 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
     float4* rows = v.crow + (size_t)scene * CROW_FIELDS * (size_t)v.NC;
     asm volatile("" : "+l"(rows));                                // one base register pair; a load's address is one IMAD.WIDE.U32 off it
     const unsigned uNC = (unsigned)v.NC;
-    LevelEnds le;
-    le.init(v.clev_end + scene, (size_t)v.B, ncl);
-    const bool l2pf = v.B >= 256;                                 // the row stream exceeds L2 only in batches
 
     for (int i = lane; i < Acc<W24>::FLOATS * nb; i += 32) w[i] = 0.f;
+
+    // ---- chunk table of the scene: levels in order, each cut into chunks of <= 32 rows ------------------------------
+    // (the sweep loop used to find its next chunk by walking level ends: 140 instructions per chunk and a third of the
+    // kernel's stall samples, profiles/r02_k_pgs_pipe_copy_mb1k_*; with the table it is one shuffle)
+    unsigned* tab = v.cchunk + (size_t)scene * v.cchunk_cap;
+    int nch = 0;
+    for (int l0 = 1, carry_end = 0; l0 <= ncl; l0 += 32) {        // 32 levels per trip, one per lane
+        const int l = l0 + lane;
+        const int e1 = l <= ncl ? v.clev_end[at(v, l, scene)] : 0;
+        int e0 = __shfl_up_sync(0xffffffffu, e1, 1);
+        if (lane == 0) e0 = carry_end;
+        carry_end = __shfl_sync(0xffffffffu, e1, 31);
+        const int n = l <= ncl ? (e1 - e0 + 31) >> 5 : 0;         // chunks of this level
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int off = nch + incl - n;
+        for (int k = 0; k < n; ++k) tab[off + k] = (unsigned)(e0 + 32 * k) | ((unsigned)min(32, e1 - e0 - 32 * k) << 16);
+        nch += __shfl_sync(0xffffffffu, incl, 31);
+    }
     __syncwarp();
 
-    // advance to the chunk after c; entering a level, pull the level after it towards L2 (one bulk prefetch per field, the
-    // rows of a level being contiguous per field), so that the register prefetch below finds its rows in L2
-    auto advance = [&](Chunk c) -> Chunk {
-        c.base += 32;
-        if (c.base >= c.p1) {
-            if (c.lev < ncl) { c.lev += 1; c.base = c.p1; }
-            else { c.it += 1; c.lev = 1; c.base = 0; if (c.it >= iters) { c.ok = false; return c; } }
-            c.p1 = le.end_of(c.lev, lane);
-            if (l2pf) {
-                int q0 = c.p1, q1 = c.p1;
-                if (c.lev < ncl) q1 = le.end_of(c.lev + 1, lane);
-                else if (c.it + 1 < iters) { q0 = 0; q1 = le.end_of(1, lane); }
-                if (lane < CROW_FIELDS && (!COMPACT || lane < CROW_COMPACT_FIELDS || lane == CROW_LAMBDA) && q1 > q0)
-                    prefetch_l2_bulk(rows + (size_t)lane * uNC + q0, (unsigned)(q1 - q0) * 16u);
-            }
-        }
-        return c;
-    };
-
-#define PIPE_ISSUE(F, LAM, c)                                                                                          \
-    if ((c).ok && (c).base + lane < (c).p1) {                                                                          \
-        const unsigned q_ = (unsigned)((c).base + lane);                                                               \
-        _Pragma("unroll") for (int f = 0; f < NF; ++f)                                                                  \
-            F[f] = STREAM ? ldg_stream(rows + (q_ + (unsigned)f * uNC), policy) : __ldg(rows + (q_ + (unsigned)f * uNC)); \
+    // One pipeline over iters sweeps (SolverBoxPGS.cpp:217-248) + one pass that forms the constraint forces from the final
+    // impulses (RigidBodySystem.cpp:202-220; same table, same per-body order: the accumulators are cleared and become fc /
+    // tauc). While chunk g is worked on, the records of chunk g + 1 are in flight into the landing registers FB and chunk
+    // g + 2 is being pulled towards L2.
+#define PIPE_ISSUE(F, LAM, e)                                                                                          \
+    if (lane < ch_count(e)) {                                                                                          \
+        const unsigned q_ = (unsigned)(ch_base(e) + lane);                                                             \
+        if ((e) & CH_FORCE) {                                                                                          \
+            _Pragma("unroll") for (int f = 0; f < NFORCE; ++f) F[f] = __ldg(rows + (q_ + (unsigned)f * uNC));          \
+        } else {                                                                                                       \
+            _Pragma("unroll") for (int f = 0; f < NF; ++f)                                                              \
+                F[f] = STREAM ? ldg_stream(rows + (q_ + (unsigned)f * uNC), policy) : __ldg(rows + (q_ + (unsigned)f * uNC)); \
+        }                                                                                                              \
         LAM = rows[q_ + (unsigned)CROW_LAMBDA * uNC];                                                                  \
     }
-#define PIPE_SOLVE(F, LAM, c)                                                                                          \
-    if ((c).base + lane < (c).p1) {                                                                                    \
+    // Pulling rows towards L2 ahead of the register loads (batches only: one scene's rows fit L2). l2mode 1: a window of 32
+    // positions x every stored field, kept 64 .. 96 positions ahead of the chunk whose loads are being issued; positions only
+    // grow inside a sweep, so the window just slides (two prefetch instructions per lane and window: 13 or 16 fields x four
+    // 128 B lines). l2mode 2 (round 2's first version): one cp.async.bulk.prefetch per field of the chunk after next -- that
+    // instruction takes its address from a uniform register, so the compiler serialises the 13 lanes' prefetches in a loop:
+    // 100 instructions per chunk and 36 % of the kernel's stall samples (profiles/r02_k_pgs_pipe_table_mb1k_*).
+#define PIPE_L2(e)                                                                                                     \
+    if (l2mode == 2 && (e) != 0u) {                                                                                    \
+        const bool mine_ = ((e) & CH_FORCE) ? (lane < NFORCE || lane == CROW_LAMBDA) : (lane < NF || lane == CROW_LAMBDA); \
+        if (mine_) prefetch_l2_bulk(rows + (size_t)lane * uNC + ch_base(e), (unsigned)ch_count(e) * 16u);              \
+    }
+    int psw = 0, ppos = 0;                                        // next window: sweep, first position (multiple of 32)
+    auto l2_window = [&](int isw, int ibase) {
+        const int ncr = (nc + 31) & ~31;
+        if (psw > iters || (psw - isw) * ncr + ppos - ibase >= 96) return;
+#pragma unroll
+        for (int j = 0; j < ((NF + 1) * 4 + 31) / 32; ++j) {
+            const int idx = lane + 32 * j, fi = idx >> 2, row = ppos + (idx & 3) * 8;
+            if (fi <= NF && row < nc) prefetch_l2(rows + ((unsigned)(fi < NF ? fi : CROW_LAMBDA) * uNC + (unsigned)row));
+        }
+        ppos += 32;
+        if (ppos >= nc) { ppos = 0; ++psw; }
+    };
+#define PIPE_SOLVE(F, LAM, e)                                                                                          \
+    if (lane < ch_count(e)) {                                                                                          \
         float4 X[CROW_LAMBDA];                                                                                         \
         if (COMPACT) crow_expand(F, X);                                                                                \
         const float4* E = COMPACT ? X : F;                                                                             \
         const ContactIds ci = contact_ids(E);                                                                          \
-        V3 w0l = mk3(0.f, 0.f, 0.f), w0a = w0l, w1l = w0l, w1a = w0l;                                                  \
-        if (ci.dyn0) ld_w(wsh, ci.id0, w0l, w0a);                                                                        \
-        if (ci.dyn1) ld_w(wsh, ci.id1, w1l, w1a);                                                                        \
-        const float4 out = contact_solve(E, LAM, mu, ci.dyn0, ci.dyn1, w0l, w0a, w1l, w1a);                            \
-        if (ci.dyn0) st_w(wsh, ci.id0, w0l, w0a);                                                                        \
-        if (ci.dyn1) st_w(wsh, ci.id1, w1l, w1a);                                                                        \
-        rows[(unsigned)((c).base + lane) + (unsigned)CROW_LAMBDA * uNC] = out;                                         \
+        if ((e) & CH_FORCE) {                                                                                          \
+            V3 fl, fa, wl, wa;                                                                                         \
+            if (ci.dyn0) { contact_force(E, LAM, dt, 0, fl, fa); ld_w(wsh, ci.id0, wl, wa); st_w(wsh, ci.id0, wl + fl, wa + fa); } \
+            if (ci.dyn1) { contact_force(E, LAM, dt, 1, fl, fa); ld_w(wsh, ci.id1, wl, wa); st_w(wsh, ci.id1, wl + fl, wa + fa); } \
+        } else {                                                                                                       \
+            V3 w0l = mk3(0.f, 0.f, 0.f), w0a = w0l, w1l = w0l, w1a = w0l;                                              \
+            if (ci.dyn0) ld_w(wsh, ci.id0, w0l, w0a);                                                                    \
+            if (ci.dyn1) ld_w(wsh, ci.id1, w1l, w1a);                                                                    \
+            const float4 out = contact_solve(E, LAM, mu, ci.dyn0, ci.dyn1, w0l, w0a, w1l, w1a);                        \
+            if (ci.dyn0) st_w(wsh, ci.id0, w0l, w0a);                                                                    \
+            if (ci.dyn1) st_w(wsh, ci.id1, w1l, w1a);                                                                    \
+            rows[(unsigned)(ch_base(e) + lane) + (unsigned)CROW_LAMBDA * uNC] = out;                                   \
+        }                                                                                                              \
     }                                                                                                                  \
     __syncwarp();
+#define PIPE_CLEAR_FOR_FORCES()                                                                                        \
+    { for (int i = lane; i < Acc<W24>::FLOATS * nb; i += 32) w[i] = 0.f; __syncwarp(); }
 
-    if (ncl > 0 && iters > 0) {                                   // SolverBoxPGS.cpp:217-248
-        // a sweep of a single chunk would prefetch the impulses it is about to write: such scenes (<= 32 rows in one level)
-        // run unpipelined
-        const int first_end = le.end_of(1, lane);
-        const bool single = ncl == 1 && first_end <= 32;
+    if (nch > 0) {
+        ChunkCursor cc;
+        cc.init(tab, nch, iters + 1, iters);
         float4 FA[NF], FB[NF], lamA, lamB;
-        Chunk cur; cur.it = 0; cur.lev = 1; cur.base = 0; cur.p1 = first_end; cur.ok = true;
-        if (single) {
-            for (int it = 0; it < iters; ++it) {
-                PIPE_ISSUE(FA, lamA, cur)
-                PIPE_SOLVE(FA, lamA, cur)
+        bool forces = false;                                      // accumulators already cleared for the force pass
+        if (nch == 1) {
+            // a table of one chunk would prefetch the impulses it is about to write: such scenes (<= 32 rows in one level)
+            // run unpipelined
+            for (int it = 0; it <= iters; ++it) {
+                const unsigned e = cc.next(lane);
+                if (e & CH_FORCE) PIPE_CLEAR_FOR_FORCES()
+                PIPE_ISSUE(FA, lamA, e)
+                PIPE_SOLVE(FA, lamA, e)
             }
         } else {
-            if (l2pf && ncl > 1) {
-                const int q0 = first_end, q1 = le.end_of(2, lane);
-                if (lane < CROW_FIELDS && (!COMPACT || lane < CROW_COMPACT_FIELDS || lane == CROW_LAMBDA) && q1 > q0)
-                    prefetch_l2_bulk(rows + (size_t)lane * uNC + q0, (unsigned)(q1 - q0) * 16u);
-            }
-#ifndef SLRBS_PIPE_TWO_BUFFERS
             // ONE landing buffer FB, copied into FA before the next chunk's loads are issued into it. The copy is the point: ptxas
             // puts every row load on one scoreboard (a counter), so "wait for chunk k's rows" also waits for chunk k+1's loads
-            // if those have been issued already. With two alternating buffers (the #else branch, round-2's first version) the
-            // solve of chunk k read registers a load had written, and its first instruction carried that wait -- the loads
-            // were early but nothing ran under them (profiles/README.md). Here the wait sits on the copy, BEFORE the next
-            // loads are issued, and the solve reads only registers written by MOVs: nothing in it touches the load scoreboard
-            // (checked in the SASS control bits), so the next chunk's 13 LDG.128 are in flight for the whole solve.
-            PIPE_ISSUE(FB, lamB, cur)
+            // if those have been issued already. With two alternating buffers (round 2's first version) the solve of chunk k
+            // read registers a load had written, and its first instruction carried that wait -- the loads were early but
+            // nothing ran under them (profiles/README.md). Here the wait sits on the copy, BEFORE the next loads are issued,
+            // and the solve reads only registers written by MOVs: nothing in it touches the load scoreboard (checked in the
+            // SASS control bits), so the next chunk's LDG.128 are in flight for the whole solve.
+            unsigned eI = cc.next(lane);                          // chunk whose loads are issued next
+            unsigned eP = cc.next(lane);                          // the chunk after it (l2mode 2 prefetches by chunk)
+            int isw = 0;                                          // sweep of eI
+            PIPE_L2(eP)
+            if (l2mode == 1) { l2_window(0, 0); l2_window(0, 0); l2_window(0, 0); }
+            PIPE_ISSUE(FB, lamB, eI)
             while (true) {
+                const unsigned eS = eI;
                 _Pragma("unroll") for (int f = 0; f < NF; ++f) FA[f] = FB[f];
                 lamA = lamB;
-                Chunk nxt = advance(cur);
-                PIPE_ISSUE(FB, lamB, nxt)
-                PIPE_SOLVE(FA, lamA, cur)
-                if (!nxt.ok) break;
-                cur = nxt;
+                eI = eP;
+                eP = cc.next(lane);
+                PIPE_L2(eP)
+                if (l2mode == 1 && eI != 0u) {
+                    if (ch_base(eI) < ch_base(eS)) ++isw;         // positions only grow inside a sweep
+                    l2_window(isw, ch_base(eI));
+                    l2_window(isw, ch_base(eI));
+                }
+                PIPE_ISSUE(FB, lamB, eI)
+                if ((eS & CH_FORCE) && !forces) { PIPE_CLEAR_FOR_FORCES() forces = true; }
+                PIPE_SOLVE(FA, lamA, eS)
+                if (eI == 0u) break;
             }
-#else
-            PIPE_ISSUE(FA, lamA, cur)
-            while (true) {
-                Chunk nxt = advance(cur);
-                PIPE_ISSUE(FB, lamB, nxt)
-                PIPE_SOLVE(FA, lamA, cur)
-                if (!nxt.ok) break;
-                cur = advance(nxt);
-                PIPE_ISSUE(FA, lamA, cur)
-                PIPE_SOLVE(FB, lamB, nxt)
-                if (!cur.ok) break;
-            }
-#endif
         }
-    }
-#undef PIPE_ISSUE
-#undef PIPE_SOLVE
-
-    // constraint forces (RigidBodySystem.cpp:202-220) in the same per-body order: w becomes fc / tauc
-    for (int i = lane; i < Acc<W24>::FLOATS * nb; i += 32) w[i] = 0.f;
-    __syncwarp();
-    for (int lev = 1, p0 = 0; lev <= ncl; ++lev) {
-        const int p1 = le.end_of(lev, lane);
-        for (int p = p0 + lane; p < p1; p += 32) {
-            float4 F[CROW_LAMBDA];
-            if (COMPACT) {
-                float4 C[CROW_COMPACT_FIELDS];
-#pragma unroll
-                for (int f = 0; f < 5; ++f) C[f] = __ldg(rows + ((unsigned)p + (unsigned)f * uNC));
-#pragma unroll
-                for (int f = 5; f < CROW_COMPACT_FIELDS; ++f) C[f] = make_float4(0.f, 0.f, 0.f, 0.f);     // contact_force reads n t b a0 a1 only
-                crow_expand(C, F);
-            } else {
-#pragma unroll
-                for (int f = 0; f < 9; ++f) F[f] = __ldg(rows + ((unsigned)p + (unsigned)f * uNC));
-            }
-            const float4 lam = rows[(unsigned)p + (unsigned)CROW_LAMBDA * uNC];
-            const ContactIds c = contact_ids(F);
-            V3 fl, fa, wl, wa;
-            if (c.dyn0) { contact_force(F, lam, dt, 0, fl, fa); ld_w(wsh, c.id0, wl, wa); st_w(wsh, c.id0, wl + fl, wa + fa); }
-            if (c.dyn1) { contact_force(F, lam, dt, 1, fl, fa); ld_w(wsh, c.id1, wl, wa); st_w(wsh, c.id1, wl + fl, wa + fa); }
-        }
-        p0 = p1;
+    } else {
         __syncwarp();
     }
+#undef PIPE_ISSUE
+#undef PIPE_L2
+#undef PIPE_SOLVE
+#undef PIPE_CLEAR_FOR_FORCES
+
     for (int i = lane; i < nb; i += 32) {
         V3 fl, fa;
         ld_w(wsh, i, fl, fa);
@@ -225,14 +244,14 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
 static bool pp_pack24(int NB) { return ((size_t)NB * 32 + 1024) * 9 > 227u * 1024u; }
 
 template <bool W24, bool STREAM, bool COMPACT>
-static void pipe_variant(const View& v, float dt, int iters, float mu, cudaStream_t s, bool launch)
+static void pipe_variant(const View& v, float dt, int iters, float mu, cudaStream_t s, bool launch, int l2mode)
 {
-    if (launch) k_pgs_pipe<W24, STREAM, COMPACT><<<(unsigned)v.B, 32, (size_t)v.NB * (W24 ? 24 : 32), s>>>(v, dt, iters, mu);
+    if (launch) k_pgs_pipe<W24, STREAM, COMPACT><<<(unsigned)v.B, 32, (size_t)v.NB * (W24 ? 24 : 32), s>>>(v, dt, iters, mu, l2mode);
     else cudaFuncSetAttribute(k_pgs_pipe<W24, STREAM, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
-static void pipe_dispatch(const View& v, float dt, int iters, float mu, cudaStream_t s, bool launch, bool w24, bool stream, bool compact)
+static void pipe_dispatch(const View& v, float dt, int iters, float mu, cudaStream_t s, bool launch, bool w24, bool stream, bool compact, int l2mode)
 {
-#define PV(a, b, c) pipe_variant<a, b, c>(v, dt, iters, mu, s, launch)
+#define PV(a, b, c) pipe_variant<a, b, c>(v, dt, iters, mu, s, launch, l2mode)
     if (w24) { if (stream) { if (compact) PV(true, true, true); else PV(true, true, false); } else { if (compact) PV(true, false, true); else PV(true, false, false); } }
     else     { if (stream) { if (compact) PV(false, true, true); else PV(false, true, false); } else { if (compact) PV(false, false, true); else PV(false, false, false); } }
 #undef PV
@@ -241,7 +260,7 @@ static void pipe_dispatch(const View& v, float dt, int iters, float mu, cudaStre
 void init_pipe_kernels()
 {
     View v{};
-    for (int k = 0; k < 8; ++k) pipe_dispatch(v, 0.f, 0, 0.f, nullptr, false, k & 1, k & 2, k & 4);
+    for (int k = 0; k < 8; ++k) pipe_dispatch(v, 0.f, 0, 0.f, nullptr, false, k & 1, k & 2, k & 4, 0);
 }
 
 // contexts without joint capacity whose scenes get one warp each (group 32)
@@ -262,7 +281,10 @@ void launch_pgs_pipe(const View& v, float dt, int iters, float mu, cudaStream_t 
 {
     static int stream = -1;                                      // SLRBS_PIPE_STREAM=1: evict-first row loads (A/B switch)
     if (stream < 0) { const char* e = getenv("SLRBS_PIPE_STREAM"); stream = e ? atoi(e) : 0; }
-    pipe_dispatch(v, dt, iters, mu, s, true, pp_pack24(v.NB), stream && v.B >= 256, v.crow_compact != 0);
+    static int l2 = -1;                                          // SLRBS_PIPE_L2 = 0 none | 1 sliding window (default) | 2 bulk prefetch per chunk
+    if (l2 < 0) { const char* e = getenv("SLRBS_PIPE_L2"); l2 = e ? atoi(e) : 1; }
+    // the row stream exceeds L2 only in batches
+    pipe_dispatch(v, dt, iters, mu, s, true, pp_pack24(v.NB), stream && v.B >= 256, v.crow_compact != 0, v.B >= 256 ? l2 : 0);
 }
 
 }  // namespace slrbs

@@ -95,11 +95,11 @@ __global__ void __launch_bounds__(2 * ROWS, MINB) k_pgs_sp(View v, float dt, int
             if (v.B >= 256) {
                 // pull the NEXT level's rows (or the first level of the next sweep) towards L2 while this one is solved: the
                 // row stream is far larger than L2, and a level would otherwise start with an HBM round trip. The rows of a
-                // level are contiguous per field: one bulk prefetch per field (SASS UBLKPF.L2).
+                // level are contiguous per field: one prefetch per 128 B line, dealt over the lanes.
                 int q0 = p1, q1 = p1;
                 if (lev < ncl) q1 = lev_end[(size_t)(lev + 1) * B];
                 else if (it + 1 < iters) { q0 = 0; q1 = lev_end[B]; }
-                if (tid < CROW_FIELDS && q1 > q0) prefetch_l2_bulk(rows + (size_t)tid * NC + q0, (unsigned)(q1 - q0) * 16u);
+                if (q1 > q0) prefetch_rows_l2(rows, (unsigned)NC, q0, q1, CROW_LAMBDA, tid, (int)blockDim.x);
             }
             for (int base = p0; base < p1; base += ROWS) {        // every lane runs every trip: the shuffles below are warp-wide
                 const int p = base + r;

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(32, 7) k_pgs_stage(View v, float dt, int iters
     for (int i = lane; i < 6 * nb; i += 32) w[i] = 0.f;
     __syncwarp();
 
-    // next chunk; entering a level, pull the level after it towards L2 (one bulk prefetch per stored field)
+    // next chunk; entering a level, pull the level after it towards L2 (one prefetch per 128 B line of every stored field)
     auto advance = [&](Chunk c) -> Chunk {
         c.base += 32;
         if (c.base >= c.p1) {
@@ -91,8 +91,7 @@ __global__ void __launch_bounds__(32, 7) k_pgs_stage(View v, float dt, int iters
                 int q0 = c.p1, q1 = c.p1;
                 if (c.lev < ncl) q1 = le.end_of(c.lev + 1, lane);
                 else if (c.it + 1 < iters) { q0 = 0; q1 = le.end_of(1, lane); }
-                if ((lane < CROW_COMPACT_FIELDS || lane == CROW_LAMBDA) && q1 > q0)
-                    prefetch_l2_bulk(rows + (size_t)lane * uNC + q0, (unsigned)(q1 - q0) * 16u);
+                if (q1 > q0) prefetch_rows_l2(rows, uNC, q0, q1, CROW_COMPACT_FIELDS, lane, 32);
             }
         }
         return c;
@@ -115,8 +114,7 @@ __global__ void __launch_bounds__(32, 7) k_pgs_stage(View v, float dt, int iters
         Chunk cur; cur.it = 0; cur.lev = 1; cur.base = 0; cur.p1 = first_end; cur.ok = true;
         if (l2pf && ncl > 1) {
             const int q0 = first_end, q1 = le.end_of(2, lane);
-            if ((lane < CROW_COMPACT_FIELDS || lane == CROW_LAMBDA) && q1 > q0)
-                prefetch_l2_bulk(rows + (size_t)lane * uNC + q0, (unsigned)(q1 - q0) * 16u);
+            if (q1 > q0) prefetch_rows_l2(rows, uNC, q0, q1, CROW_COMPACT_FIELDS, lane, 32);
         }
         issue(cur);
         while (cur.ok) {
