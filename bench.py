@@ -67,7 +67,7 @@ PILE_DIMS = {"pile_1m": (100, 100, 100), "pile": (48, 24, 48)}
 
 
 
-SOLVER_SOURCES = ("pgs_split.cu", "pgs_level.cu", "pgs_level.cuh", "pgs_math.cuh", "layout.cuh", "kernels.cu")
+SOLVER_SOURCES = ("pgs_pipe.cu", "pgs_stage.cu", "pgs_gacc.cu", "pgs_color.cu", "pgs_split.cu", "pgs_level.cu", "pgs_level.cuh", "pgs_math.cuh", "layout.cuh", "kernels.cu")
 
 
 def solver_source_hash():

@@ -189,22 +189,17 @@ void init_stage_kernels()
     cudaFuncSetAttribute(k_pgs_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 
-// Contact-only contexts whose scenes get one warp each (group 32). The landing buffer costs residency (7 instead of 9
-// thousand-body scenes per SM) and buys a level step of ~2250 instead of ~3000 cycles (measured, profiles/README.md): a scene
-// finishes in 0.73 of the time, so the staged kernel wins whenever it does not need more WAVES than k_pgs_pipe would --
-// batches of up to one wave (a partitioned pile's slab, the chunk contexts of a host-driven loop) always, 2664 scenes
-// (3 waves against 2) not. SLRBS_PGS_STAGE = 0 / 1 forces (read when a context is created).
+// Opt-in (SLRBS_PGS_STAGE=1, read when a context is created) for contact-only contexts whose scenes get one warp each
+// (group 32). History: the landing buffer costs residency (7 instead of 9 thousand-body scenes per SM) and bought a level step
+// of ~2250 instead of ~3000 cycles against the FIRST register-prefetch kernel, which did not overlap its loads; for batches of
+// up to one wave this kernel was then the default. k_pgs_pipe as it is now overlaps its loads at 9 scenes per SM and is
+// faster everywhere it was measured (2664 scenes: 3.44 against 4.70 ms; the 5832 block scenes of a 10^6-sphere pile: 3.71
+// against 3.97 ms; the 666-scene chunk contexts of the host-driven loop: 4.18 against 4.07 10^8 body-steps/s end to end).
 bool level_stage_wanted(const View& v, int group)
 {
     if (group != 32 || v.NJ != 0 || stage_smem(v.NB) > 200 * 1024) return false;
     const char* e = getenv("SLRBS_PGS_STAGE");
-    if (e) return atoi(e) != 0;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long per_stage = (long)((227u * 1024u) / (stage_smem(v.NB) + 1024)), per_pipe = (long)((227u * 1024u) / ((size_t)v.NB * 24 + 1024));
-    const long w_stage = ((long)v.B + sms * per_stage - 1) / (sms * per_stage), w_pipe = ((long)v.B + sms * per_pipe - 1) / (sms * per_pipe);
-    return 0.73 * (double)w_stage < (double)w_pipe;
+    return e && atoi(e) != 0;
 }
 
 void launch_pgs_stage(const View& v, float dt, int iters, float mu, cudaStream_t s)
