@@ -197,7 +197,7 @@ int slrbs_describe(slrbs_ctx* c, char* buf, int buf_len)
         std::snprintf(tmp, sizeof tmp, "solver=k_pgs_color (graph-coloured, all SMs, accumulators in HBM) detect=%s graph=%d",
                       detect_variant(c->v, c->broadphase), c->use_graph);
     else if (c->v.level_mode && c->level_variant == 2)
-        std::snprintf(tmp, sizeof tmp, "solver=k_pgs_pipe (level-scheduled, 1 warp/scene, next chunk's rows prefetched into registers, %s B rows) detect=%s graph=%d",
+        std::snprintf(tmp, sizeof tmp, "solver=k_pgs_pipe (level-scheduled, 1 warp/scene, chunk table, next chunk loaded under the solve, sliding L2 window, %s B rows) detect=%s graph=%d",
                       c->v.crow_compact ? "208" : "256", detect_variant(c->v, c->broadphase), c->use_graph);
     else if (c->v.level_mode && c->level_variant == 1)
         std::snprintf(tmp, sizeof tmp, "solver=k_pgs_sp<ROWS=%d> (level-scheduled, 2 lanes/contact row, %d threads/scene) detect=%s graph=%d",

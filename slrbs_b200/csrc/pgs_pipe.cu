@@ -127,17 +127,12 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
         }                                                                                                              \
         LAM = rows[q_ + (unsigned)CROW_LAMBDA * uNC];                                                                  \
     }
-    // Pulling rows towards L2 ahead of the register loads (batches only: one scene's rows fit L2). l2mode 1: a window of 32
-    // positions x every stored field, kept 64 .. 96 positions ahead of the chunk whose loads are being issued; positions only
-    // grow inside a sweep, so the window just slides (two prefetch instructions per lane and window: 13 or 16 fields x four
-    // 128 B lines). l2mode 2 (round 2's first version): one cp.async.bulk.prefetch per field of the chunk after next -- that
-    // instruction takes its address from a uniform register, so the compiler serialises the 13 lanes' prefetches in a loop:
+    // Pulling rows towards L2 ahead of the register loads (batches only: one scene's rows fit L2; l2mode 0 = off): a window of
+    // 32 positions x every stored field, kept 64 .. 96 positions ahead of the chunk whose loads are being issued; positions
+    // only grow inside a sweep, so the window just slides (two prefetch instructions per lane and window: 13 or 16 fields x four
+    // 128 B lines). Round 2's first version issued one cp.async.bulk.prefetch per field of the chunk after next: that
+    // instruction takes its address from a uniform register, so the compiler serialises the 13 lanes' prefetches in a loop --
     // 100 instructions per chunk and 36 % of the kernel's stall samples (profiles/r02_k_pgs_pipe_table_mb1k_*).
-#define PIPE_L2(e)                                                                                                     \
-    if (l2mode == 2 && (e) != 0u) {                                                                                    \
-        const bool mine_ = ((e) & CH_FORCE) ? (lane < NFORCE || lane == CROW_LAMBDA) : (lane < NF || lane == CROW_LAMBDA); \
-        if (mine_) prefetch_l2_bulk(rows + (size_t)lane * uNC + ch_base(e), (unsigned)ch_count(e) * 16u);              \
-    }
     int psw = 0, ppos = 0;                                        // next window: sweep, first position (multiple of 32)
     auto l2_window = [&](int isw, int ibase) {
         const int ncr = (nc + 31) & ~31;
@@ -197,22 +192,17 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
             // and the solve reads only registers written by MOVs: nothing in it touches the load scoreboard (checked in the
             // SASS control bits), so the next chunk's LDG.128 are in flight for the whole solve.
             unsigned eI = cc.next(lane);                          // chunk whose loads are issued next
-            unsigned eP = cc.next(lane);                          // the chunk after it (l2mode 2 prefetches by chunk)
             int isw = 0;                                          // sweep of eI
-            PIPE_L2(eP)
-            if (l2mode == 1) { l2_window(0, 0); l2_window(0, 0); l2_window(0, 0); }
+            if (l2mode) { l2_window(0, 0); l2_window(0, 0); l2_window(0, 0); }
             PIPE_ISSUE(FB, lamB, eI)
             while (true) {
                 const unsigned eS = eI;
                 _Pragma("unroll") for (int f = 0; f < NF; ++f) FA[f] = FB[f];
                 lamA = lamB;
-                eI = eP;
-                eP = cc.next(lane);
-                PIPE_L2(eP)
-                if (l2mode == 1 && eI != 0u) {
+                eI = cc.next(lane);
+                if (l2mode && eI != 0u) {
                     if (ch_base(eI) < ch_base(eS)) ++isw;         // positions only grow inside a sweep
-                    l2_window(isw, ch_base(eI));
-                    l2_window(isw, ch_base(eI));
+                    l2_window(isw, ch_base(eI));                  // one window per chunk keeps up: a chunk is at most 32 positions
                 }
                 PIPE_ISSUE(FB, lamB, eI)
                 if ((eS & CH_FORCE) && !forces) { PIPE_CLEAR_FOR_FORCES() forces = true; }
@@ -224,7 +214,6 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
         __syncwarp();
     }
 #undef PIPE_ISSUE
-#undef PIPE_L2
 #undef PIPE_SOLVE
 #undef PIPE_CLEAR_FOR_FORCES
 
@@ -281,8 +270,8 @@ void launch_pgs_pipe(const View& v, float dt, int iters, float mu, cudaStream_t 
 {
     static int stream = -1;                                      // SLRBS_PIPE_STREAM=1: evict-first row loads (A/B switch)
     if (stream < 0) { const char* e = getenv("SLRBS_PIPE_STREAM"); stream = e ? atoi(e) : 0; }
-    static int l2 = -1;                                          // SLRBS_PIPE_L2 = 0 none | 1 sliding window (default) | 2 bulk prefetch per chunk
-    if (l2 < 0) { const char* e = getenv("SLRBS_PIPE_L2"); l2 = e ? atoi(e) : 1; }
+    static int l2 = -1;                                          // SLRBS_PIPE_L2 = 0: no L2 prefetch (A/B switch)
+    if (l2 < 0) { const char* e = getenv("SLRBS_PIPE_L2"); l2 = e ? (atoi(e) != 0) : 1; }
     // the row stream exceeds L2 only in batches
     pipe_dispatch(v, dt, iters, mu, s, true, pp_pack24(v.NB), stream && v.B >= 256, v.crow_compact != 0, v.B >= 256 ? l2 : 0);
 }
