@@ -26,7 +26,7 @@ SYMBOLS = [
     "slrbs_timer_start", "slrbs_timer_stop", "slrbs_halo_set_local", "slrbs_halo_set_remote", "slrbs_halo_sync_local",
     "slrbs_halo_pack", "slrbs_halo_unpack", "slrbs_stream", "slrbs_device", "slrbs_pile_init", "slrbs_pile_export", "slrbs_pile_rebuild",
     "slrbs_pile_requests", "slrbs_pile_set_send", "slrbs_pile_scene_keys", "slrbs_set_extensions",
-    "slrbs_sdf_build", "slrbs_sdf_add_shape",
+    "slrbs_sdf_build", "slrbs_sdf_add_shape", "slrbs_debug_div_rn",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library():
     L.slrbs_stream.argtypes = [vp]
     L.slrbs_stream.restype = C.c_void_p
     L.slrbs_device.argtypes = [vp]
+    L.slrbs_debug_div_rn.argtypes = [fp, fp, fp, C.c_int]
     L.slrbs_halo_unpack.argtypes = [vp, C.c_void_p]
     L.slrbs_pile_init.argtypes = [vp, C.c_int, fp, fp, fp, C.c_float, C.c_float, ip, C.c_int, C.c_int, C.c_int, fp]
     L.slrbs_pile_export.argtypes = [vp, C.c_void_p, C.c_void_p]
@@ -414,6 +415,19 @@ def sdf_build(verts, tris, dims, origin, cell, device=0):
     o = np.ascontiguousarray(origin, np.float32)
     out = np.zeros(int(dims[0]) * int(dims[1]) * int(dims[2]), np.float32)
     rc = L.slrbs_sdf_build(int(device), len(v), _f(v), len(t), _i(t), int(dims[0]), int(dims[1]), int(dims[2]), _f(o), float(cell), _f(out))
+    if rc < 0:
+        raise SlrbsError(L.slrbs_last_error().decode())
+    return out
+
+
+def debug_div_rn(a, b):
+    """Test hook (slrbs_debug_div_rn): a / b evaluated on the device by the row solve's call-free division."""
+    L = load_library()
+    a = np.ascontiguousarray(a, np.float32).ravel(); b = np.ascontiguousarray(b, np.float32).ravel()
+    if a.shape != b.shape:
+        raise ValueError("a and b must have the same number of elements")
+    out = np.zeros_like(a)
+    rc = L.slrbs_debug_div_rn(_f(a), _f(b), _f(out), int(a.size))
     if rc < 0:
         raise SlrbsError(L.slrbs_last_error().decode())
     return out

@@ -3,6 +3,7 @@
 // entry point fails with SLRBS_E_CUDA if the device is not usable.
 #include "../../include/slrbs_b200.h"
 #include "kernels.cuh"
+#include "pgs_math.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -886,6 +887,35 @@ int slrbs_halo_sync_local(slrbs_ctx* c)
     CU(cudaSetDevice(c->device));
     launch_halo_copy(c->v, c->n_halo_local, c->halo_src, c->halo_dst, c->stream);
     return check_launch(c);
+}
+
+namespace slrbs {
+__global__ void k_debug_div(const float* a, const float* b, float* out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = div_rn_nocall(a[i], b[i]);
+}
+}  // namespace slrbs
+
+int slrbs_debug_div_rn(const float* a, const float* b, float* out, int n)
+{
+    if (!a || !b || !out || n < 0) return fail(SLRBS_E_ARG, "slrbs_debug_div_rn: null pointer or negative count");
+    if (n == 0) return 0;
+    float *da = nullptr, *db = nullptr, *dout = nullptr;
+    const size_t bytes = (size_t)n * sizeof(float);
+    cudaError_t e = cudaMalloc(&da, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&db, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        slrbs::k_debug_div<<<(unsigned)((n + 255) / 256), 256>>>(da, db, dout, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    if (e != cudaSuccess) return fail(SLRBS_E_CUDA, std::string("slrbs_debug_div_rn: ") + cudaGetErrorString(e));
+    return 0;
 }
 
 void* slrbs_stream(slrbs_ctx* c) { return c ? (void*)c->stream : nullptr; }
