@@ -68,6 +68,13 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p, unsigned long long
     return r;
 }
 
+__device__ __forceinline__ float copy_f32(float x)
+{
+    float y;
+    asm("add.f32 %0, %1, 0f80000000;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <bool W24, bool STREAM, bool COMPACT>
 __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters, float mu, int l2mode)
 {
@@ -197,7 +204,12 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
             PIPE_ISSUE(FB, lamB, eI)
             while (true) {
                 const unsigned eS = eI;
-                _Pragma("unroll") for (int f = 0; f < NF; ++f) FA[f] = FB[f];
+                _Pragma("unroll") for (int f = 0; f < NF; ++f) {
+                    // through the FP32 pipe (one warp instruction per cycle; a MOV issues every second cycle): x + (-0) is x
+                    // for every float, -0 and denormals included; field 2's w holds the packed body ids (any bit pattern)
+                    FA[f].x = copy_f32(FB[f].x); FA[f].y = copy_f32(FB[f].y); FA[f].z = copy_f32(FB[f].z);
+                    FA[f].w = f == 2 ? FB[f].w : copy_f32(FB[f].w);
+                }
                 lamA = lamB;
                 eI = cc.next(lane);
                 if (l2mode && eI != 0u) {
