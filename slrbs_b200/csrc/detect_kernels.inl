@@ -529,34 +529,18 @@ __global__ void __launch_bounds__(512, 2) k_detect_rows(View v, int H)
             }
             if (over) break;
         }
-        // The non-sphere bodies, 32 at a time: first the cheap cull for all of them (every lane busy), then only the
-        // survivors get the full test, each lane working through its own -- a warp of spheres along a wall runs the box
-        // test once or twice instead of once per wall with three or four lanes in it
-        for (int k0 = 0; k0 < nspecial && !over; k0 += 32) {
-            unsigned pend = 0;
-            const int kn = min(32, nspecial - k0);
-            for (int k = 0; k < kn; ++k) {
-                const int j = sm.special[k0 + k];
-                if (j <= i) continue;
-                const int fj = sm.sf[j];
-                if ((fi & fj) & FLAG_FIXED) continue;
-                if ((fj & FLAG_TYPE_MASK) == GEOM_BOX && !sphere_box_may_touch(ci, sm.sp[j], __ldg(&v.bext[at(v, j, scene)]))) continue;
-                pend |= 1u << k;
-            }
-            while (pend) {
-                const int k = __ffs(pend) - 1;
-                pend &= pend - 1;
-                const int j = sm.special[k0 + k];
-                PairOut o;
-                test_pair<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
-                if (o.cnt == 0) continue;
-                if (nh == ROW_HITS) { over = true; break; }
-                int pos = nh;
-                while (pos > 0 && my[pos - 1] > j) --pos;
-                for (int m = nh; m > pos; --m) my[m] = my[m - 1];
-                my[pos] = (unsigned short)j;
-                ++nh;
-            }
+        for (int k = 0; k < nspecial && !over; ++k) {
+            const int j = sm.special[k];
+            if (j <= i) continue;
+            PairOut o;
+            test_pair<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
+            if (o.cnt == 0) continue;
+            if (nh == ROW_HITS) { over = true; break; }
+            int pos = nh;
+            while (pos > 0 && my[pos - 1] > j) --pos;
+            for (int m = nh; m > pos; --m) my[m] = my[m - 1];
+            my[pos] = (unsigned short)j;
+            ++nh;
         }
         if (over) { nhits[i] = ROW_DENSE; dense_list[atomicAdd(&s_ndense, 1)] = i; }
         else { nhits[i] = (unsigned char)nh; rowoff[i] = nh; }
@@ -598,23 +582,10 @@ __global__ void __launch_bounds__(512, 2) k_detect_rows(View v, int H)
         const float4 ci = sm.sp[i];
         const int fi = sm.sf[i];
         const int base = rowoff[i];
-        // sphere partners front to back, the others back to front: the slot of a contact is base + k whatever the order, and
-        // the few non-sphere partners of a row (walls: the highest indices of the marble box) then meet in the same trips
-        // across the lanes instead of being scattered over trips in which the other lanes test spheres
         for (int k = 0; k < nh; ++k) {
             const int j = hits[(size_t)i * ROW_HITS + k];
-            const int fj = sm.sf[j];
-            if ((fj & FLAG_TYPE_MASK) != GEOM_SPHERE) continue;
             PairOut o;
-            test_pair<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j], fj);
-            write_contacts(v, scene, base + k, o);
-        }
-        for (int k = nh - 1; k >= 0; --k) {
-            const int j = hits[(size_t)i * ROW_HITS + k];
-            const int fj = sm.sf[j];
-            if ((fj & FLAG_TYPE_MASK) == GEOM_SPHERE) continue;
-            PairOut o;
-            test_pair<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j], fj);
+            test_pair<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
             write_contacts(v, scene, base + k, o);
         }
     }

@@ -1,16 +1,15 @@
 // pgs_pipe.cu -- level-scheduled Box-PGS for contact-only scenes, one warp per scene, software-pipelined: while the
 // warp solves one chunk of rows (<= 32 rows of one dependency level, one per lane) the row records of the NEXT chunk
-// are already in flight into a second set of registers.
+// are in flight into landing registers and a window of rows further ahead is being pulled into L2.
 //
-// Why: k_pgs_lv on a thousand-sphere scene walks ~1400 chunk steps per solve (130 levels x 10 sweeps + the force
-// scatter), each a strict sequence  16 row loads -> accumulator gather (shared memory) -> ~250 flop chain -> scatter ->
-// warp barrier.  ncu (profiles/r01_k_pgs_lv_mb1k_ncu_details.txt): ~2500 cycles per step, ~900 of them waiting for the
-// row loads even with the level prefetched into L2; nine such warps per SM (the scene's 24 KB of accumulators are what
-// limits residency) cannot cover each other's waits: 0.49 eligible warps per scheduler, DRAM at 0.60 of peak.  Residency
-// being capped by shared memory, the register file is half empty (9 warps x 160 registers = 45 KB of 256 KB): a second
-// row buffer (64 registers) costs no occupancy and takes the load wait off the chain.  Two lanes per row on the same
-// shared memory was the other candidate (pgs_split.cu): measured slower, the chain shortens by less than the extra
-// barrier costs.
+// Why: a thousand-sphere scene is ~1400 chunk steps per solve (130 levels x 10 sweeps + the force pass), each a strict
+// sequence  13 row loads -> accumulator gather (shared memory) -> ~220 instruction chain -> scatter -> warp barrier, and
+// only nine such warps fit an SM (the scene's 24 KB of accumulators are what limits residency): they cannot cover each
+// other's load waits (round 1: 0.49 eligible warps per scheduler, DRAM at 0.60 of peak). Residency being capped by shared
+// memory, the register file is half empty: a landing buffer costs no occupancy and takes the load wait off the chain.
+// What it took to make the loads really overlap (SASS-level findings, profiles/README.md): a copy of the landing
+// registers in front of the next loads, divisions without the slow-path CALL, a chunk table instead of a walk over the
+// level ends, and per-lane L2 prefetches instead of cp.async.bulk.prefetch (which the compiler serialises over the lanes).
 //
 // Same schedule, same per-row functions (pgs_math.cuh) as k_pgs_lv and k_pgs: impulses, constraint forces and
 // trajectories are bit-identical (tests/test_gpu_level_mode.py).  Row order inside a level is free (rows of a level
@@ -196,8 +195,8 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
             // if those have been issued already. With two alternating buffers (round 2's first version) the solve of chunk k
             // read registers a load had written, and its first instruction carried that wait -- the loads were early but
             // nothing ran under them (profiles/README.md). Here the wait sits on the copy, BEFORE the next loads are issued,
-            // and the solve reads only registers written by MOVs: nothing in it touches the load scoreboard (checked in the
-            // SASS control bits), so the next chunk's LDG.128 are in flight for the whole solve.
+            // and the solve reads only registers written by the copy: nothing in it touches the load scoreboard (checked in the
+            // SASS control bits, tools/sass_ctrl.py), so the next chunk's LDG.128 are in flight for the whole solve.
             unsigned eI = cc.next(lane);                          // chunk whose loads are issued next
             int isw = 0;                                          // sweep of eI
             if (l2mode) { l2_window(0, 0); l2_window(0, 0); l2_window(0, 0); }
