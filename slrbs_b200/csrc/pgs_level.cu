@@ -441,7 +441,7 @@ void init_level_kernels()
 int level_group_size(const View& v, int requested)
 {
     int g = requested;
-    if (g != 4 && g != 8 && g != 16 && g != 32 && g != 64 && g != 128) g = v.NB < 24 ? 4 : (v.NB <= 96 ? 8 : (v.NB <= 512 ? 16 : (v.B <= 296 ? 64 : 32)));   // few wide scenes: 2 warps each
+    if (g != 4 && g != 8 && g != 16 && g != 32 && g != 64 && g != 128) g = v.NB < 24 ? 4 : (v.NB <= 96 ? 8 : (v.NB <= 512 ? 16 : ((v.B <= 296 && v.NJ > 0) ? 64 : 32)));   // few wide scenes with joints: 2 warps each (contact-only scenes: k_pgs_pipe, one warp, is faster at every batch size -- 0.70 / 0.85 against 0.73 / 1.13 ms for 16 / 296 thousand-body scenes)
     // the accumulators of the 32 / g scenes of a warp must fit in shared memory
     while (g < 32 && (size_t)(32 / g) * v.NB * 24 > 200 * 1024) g <<= 1;
     return g;
