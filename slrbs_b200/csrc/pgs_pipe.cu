@@ -29,14 +29,13 @@ namespace {
 
 // One entry of a scene's chunk table: up to 32 consecutive positions of ONE level, `base | count << 16` (positions are below
 // 65535 in level mode, slrbs_create). A sweep is the table walked front to back; every sweep walks the same table.
-enum : unsigned { CH_FORCE = 0x80000000u };                        // set on the entries of the pass that forms the constraint forces
 __device__ __forceinline__ int ch_base(unsigned e) { return (int)(e & 0xffffu); }
 __device__ __forceinline__ int ch_count(unsigned e) { return (int)((e >> 16) & 0x3fu); }
 
 // cursor over (sweep, chunk) for `sweeps` passes over a table of `nch` entries, 32 entries at a time in a register per lane
 struct ChunkCursor {
-    const unsigned* tab; int nch, sweeps, force_sweep, k, it, blk; unsigned reg;
-    __device__ __forceinline__ void init(const unsigned* t, int n, int sw, int fs) { tab = t; nch = n; sweeps = sw; force_sweep = fs; k = 0; it = 0; blk = -1; reg = 0; }
+    const unsigned* tab; int nch, sweeps, k, it, blk; unsigned reg;
+    __device__ __forceinline__ void init(const unsigned* t, int n, int sw) { tab = t; nch = n; sweeps = sw; k = 0; it = 0; blk = -1; reg = 0; }
     // next entry, 0 when all sweeps have been handed out
     __device__ __forceinline__ unsigned next(int lane)
     {
@@ -47,8 +46,7 @@ struct ChunkCursor {
             reg = i < nch ? tab[i] : 0u;
             blk = b;
         }
-        unsigned e = __shfl_sync(0xffffffffu, reg, k & 31);
-        if (it == force_sweep) e |= CH_FORCE;
+        const unsigned e = __shfl_sync(0xffffffffu, reg, k & 31);
         if (++k == nch) { k = 0; ++it; }
         return e;
     }
@@ -118,14 +116,15 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
     }
     __syncwarp();
 
-    // One pipeline over iters sweeps (SolverBoxPGS.cpp:217-248) + one pass that forms the constraint forces from the final
-    // impulses (RigidBodySystem.cpp:202-220; same table, same per-body order: the accumulators are cleared and become fc /
-    // tauc). While chunk g is worked on, the records of chunk g + 1 are in flight into the landing registers FB and chunk
-    // g + 2 is being pulled towards L2.
-#define PIPE_ISSUE(F, LAM, e)                                                                                          \
+    // A pipelined loop over iters sweeps (SolverBoxPGS.cpp:217-248), then one over the pass that forms the constraint forces
+    // from the final impulses (RigidBodySystem.cpp:202-220; same table, same per-body order: the accumulators are cleared and
+    // become fc / tauc). While chunk g is worked on, the records of chunk g + 1 are in flight into the landing registers FB
+    // and a window of rows 64 .. 96 positions further on is being pulled towards L2.
+    // ISF (a literal): the pass that forms the constraint forces -- 5 (9) fields + the impulse, no impulse written back
+#define PIPE_ISSUE(F, LAM, e, ISF)                                                                                     \
     if (lane < ch_count(e)) {                                                                                          \
         const unsigned q_ = (unsigned)(ch_base(e) + lane);                                                             \
-        if ((e) & CH_FORCE) {                                                                                          \
+        if (ISF) {                                                                                                     \
             _Pragma("unroll") for (int f = 0; f < NFORCE; ++f) F[f] = __ldg(rows + (q_ + (unsigned)f * uNC));          \
         } else {                                                                                                       \
             _Pragma("unroll") for (int f = 0; f < NF; ++f)                                                              \
@@ -151,13 +150,13 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
         ppos += 32;
         if (ppos >= nc) { ppos = 0; ++psw; }
     };
-#define PIPE_SOLVE(F, LAM, e)                                                                                          \
+#define PIPE_SOLVE(F, LAM, e, ISF)                                                                                     \
     if (lane < ch_count(e)) {                                                                                          \
         float4 X[CROW_LAMBDA];                                                                                         \
         if (COMPACT) crow_expand(F, X);                                                                                \
         const float4* E = COMPACT ? X : F;                                                                             \
         const ContactIds ci = contact_ids(E);                                                                          \
-        if ((e) & CH_FORCE) {                                                                                          \
+        if (ISF) {                                                                                                     \
             V3 fl, fa, wl, wa;                                                                                         \
             if (ci.dyn0) { contact_force(E, LAM, dt, 0, fl, fa); ld_w(wsh, ci.id0, wl, wa); st_w(wsh, ci.id0, wl + fl, wa + fa); } \
             if (ci.dyn1) { contact_force(E, LAM, dt, 1, fl, fa); ld_w(wsh, ci.id1, wl, wa); st_w(wsh, ci.id1, wl + fl, wa + fa); } \
@@ -174,52 +173,62 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
     __syncwarp();
 #define PIPE_CLEAR_FOR_FORCES()                                                                                        \
     { for (int i = lane; i < Acc<W24>::FLOATS * nb; i += 32) w[i] = 0.f; __syncwarp(); }
+    // ONE landing buffer FB, copied into FA before the next chunk's loads are issued into it. The copy is the point: ptxas puts
+    // every row load on one scoreboard (a counter), so "wait for chunk k's rows" also waits for chunk k+1's loads if those
+    // have been issued already. With two alternating buffers (round 2's first version) the solve of chunk k read registers a
+    // load had written, and its first instruction carried that wait -- the loads were early but nothing ran under them
+    // (profiles/README.md). Here the wait sits on the copy, BEFORE the next loads are issued, and the solve reads only
+    // registers written by the copy: nothing in it touches the load scoreboard (checked in the SASS control bits,
+    // tools/sass_ctrl.py), so the next chunk's LDG.128 are in flight for the whole solve. The copy goes through the FP32 pipe
+    // (one warp instruction per cycle; a MOV issues every second cycle): x + (-0) is x for every float, -0 and denormals
+    // included; field 2's w holds the packed body ids (any bit pattern) and is moved.
+#define PIPE_LOOP(ISF, NSWEEPS, SW0)                                                                                   \
+    {                                                                                                                  \
+        cc.init(tab, nch, NSWEEPS);                                                                                    \
+        unsigned eI = cc.next(lane);                              /* chunk whose loads are issued next */              \
+        int isw = SW0;                                            /* its sweep, for the L2 window */                   \
+        if (l2mode && !(ISF)) { l2_window(0, 0); l2_window(0, 0); l2_window(0, 0); }                                   \
+        PIPE_ISSUE(FB, lamB, eI, ISF)                                                                                  \
+        while (eI != 0u) {                                                                                             \
+            const unsigned eS = eI;                                                                                    \
+            _Pragma("unroll") for (int f = 0; f < ((ISF) ? NFORCE : NF); ++f) {                                         \
+                FA[f].x = copy_f32(FB[f].x); FA[f].y = copy_f32(FB[f].y); FA[f].z = copy_f32(FB[f].z);                 \
+                FA[f].w = f == 2 ? FB[f].w : copy_f32(FB[f].w);                                                        \
+            }                                                                                                          \
+            lamA = lamB;                                                                                               \
+            eI = cc.next(lane);                                                                                        \
+            if (l2mode && eI != 0u) {                                                                                  \
+                if (ch_base(eI) < ch_base(eS)) ++isw;             /* positions only grow inside a sweep */             \
+                l2_window(isw, ch_base(eI));                      /* one window per chunk keeps up: a chunk is <= 32 positions */ \
+            }                                                                                                          \
+            PIPE_ISSUE(FB, lamB, eI, ISF)                         /* no lane is below the count of entry 0 */          \
+            PIPE_SOLVE(FA, lamA, eS, ISF)                                                                              \
+        }                                                                                                              \
+    }
 
     if (nch > 0) {
         ChunkCursor cc;
-        cc.init(tab, nch, iters + 1, iters);
         float4 FA[NF], FB[NF], lamA, lamB;
-        bool forces = false;                                      // accumulators already cleared for the force pass
         if (nch == 1) {
             // a table of one chunk would prefetch the impulses it is about to write: such scenes (<= 32 rows in one level)
             // run unpipelined
-            for (int it = 0; it <= iters; ++it) {
+            cc.init(tab, nch, iters + 1);
+            for (int it = 0; it < iters; ++it) {
                 const unsigned e = cc.next(lane);
-                if (e & CH_FORCE) PIPE_CLEAR_FOR_FORCES()
-                PIPE_ISSUE(FA, lamA, e)
-                PIPE_SOLVE(FA, lamA, e)
+                PIPE_ISSUE(FA, lamA, e, false)
+                PIPE_SOLVE(FA, lamA, e, false)
             }
+            const unsigned e = cc.next(lane);
+            PIPE_CLEAR_FOR_FORCES()
+            PIPE_ISSUE(FA, lamA, e, true)
+            PIPE_SOLVE(FA, lamA, e, true)
         } else {
-            // ONE landing buffer FB, copied into FA before the next chunk's loads are issued into it. The copy is the point: ptxas
-            // puts every row load on one scoreboard (a counter), so "wait for chunk k's rows" also waits for chunk k+1's loads
-            // if those have been issued already. With two alternating buffers (round 2's first version) the solve of chunk k
-            // read registers a load had written, and its first instruction carried that wait -- the loads were early but
-            // nothing ran under them (profiles/README.md). Here the wait sits on the copy, BEFORE the next loads are issued,
-            // and the solve reads only registers written by the copy: nothing in it touches the load scoreboard (checked in the
-            // SASS control bits, tools/sass_ctrl.py), so the next chunk's LDG.128 are in flight for the whole solve.
-            unsigned eI = cc.next(lane);                          // chunk whose loads are issued next
-            int isw = 0;                                          // sweep of eI
-            if (l2mode) { l2_window(0, 0); l2_window(0, 0); l2_window(0, 0); }
-            PIPE_ISSUE(FB, lamB, eI)
-            while (true) {
-                const unsigned eS = eI;
-                _Pragma("unroll") for (int f = 0; f < NF; ++f) {
-                    // through the FP32 pipe (one warp instruction per cycle; a MOV issues every second cycle): x + (-0) is x
-                    // for every float, -0 and denormals included; field 2's w holds the packed body ids (any bit pattern)
-                    FA[f].x = copy_f32(FB[f].x); FA[f].y = copy_f32(FB[f].y); FA[f].z = copy_f32(FB[f].z);
-                    FA[f].w = f == 2 ? FB[f].w : copy_f32(FB[f].w);
-                }
-                lamA = lamB;
-                eI = cc.next(lane);
-                if (l2mode && eI != 0u) {
-                    if (ch_base(eI) < ch_base(eS)) ++isw;         // positions only grow inside a sweep
-                    l2_window(isw, ch_base(eI));                  // one window per chunk keeps up: a chunk is at most 32 positions
-                }
-                PIPE_ISSUE(FB, lamB, eI)
-                if ((eS & CH_FORCE) && !forces) { PIPE_CLEAR_FOR_FORCES() forces = true; }
-                PIPE_SOLVE(FA, lamA, eS)
-                if (eI == 0u) break;
-            }
+            // two loops over the same table: the sweeps, then (accumulators cleared) the pass that forms the constraint forces --
+            // kept apart so that neither carries the other's branches (a predicate costs a branch ~18 cycles on this chain);
+            // the one load wait exposed between them is a microsecond per scene
+            PIPE_LOOP(false, iters, 0)
+            PIPE_CLEAR_FOR_FORCES()
+            PIPE_LOOP(true, 1, iters)
         }
     } else {
         __syncwarp();
@@ -227,6 +236,7 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
 #undef PIPE_ISSUE
 #undef PIPE_SOLVE
 #undef PIPE_CLEAR_FOR_FORCES
+#undef PIPE_LOOP
 
     for (int i = lane; i < nb; i += 32) {
         V3 fl, fa;
