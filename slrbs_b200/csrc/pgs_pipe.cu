@@ -32,22 +32,22 @@ namespace {
 __device__ __forceinline__ int ch_base(unsigned e) { return (int)(e & 0xffffu); }
 __device__ __forceinline__ int ch_count(unsigned e) { return (int)((e >> 16) & 0x3fu); }
 
-// cursor over (sweep, chunk) for `sweeps` passes over a table of `nch` entries, 32 entries at a time in a register per lane
+// cursor over (sweep, chunk) for `sweeps` passes over a table of `nch` entries. The entry after the one handed out is
+// already being loaded (one uniform 4 B load per chunk, issued a whole chunk before it is needed), so next() costs neither a
+// shuffle nor a branch on the chain.
 struct ChunkCursor {
-    const unsigned* tab; int nch, sweeps, k, it, blk; unsigned reg;
-    __device__ __forceinline__ void init(const unsigned* t, int n, int sw) { tab = t; nch = n; sweeps = sw; k = 0; it = 0; blk = -1; reg = 0; }
-    // next entry, 0 when all sweeps have been handed out
-    __device__ __forceinline__ unsigned next(int lane)
+    const unsigned* tab; int nch, sweeps, k, it; unsigned ahead;
+    __device__ __forceinline__ void init(const unsigned* t, int n, int sw)
     {
-        if (it >= sweeps) return 0u;
-        const int b = k >> 5;
-        if (b != blk) {                                           // warp-uniform; the table was written by this warp (plain loads)
-            const int i = (b << 5) + lane;
-            reg = i < nch ? tab[i] : 0u;
-            blk = b;
-        }
-        const unsigned e = __shfl_sync(0xffffffffu, reg, k & 31);
+        tab = t; nch = n; sweeps = sw; k = 0; it = 0;
+        ahead = (sw > 0 && n > 0) ? t[0] : 0u;                    // the table was written by this warp: plain loads
+    }
+    // next entry, 0 when all sweeps have been handed out
+    __device__ __forceinline__ unsigned next()
+    {
+        const unsigned e = ahead;
         if (++k == nch) { k = 0; ++it; }
+        ahead = it < sweeps ? tab[k] : 0u;
         return e;
     }
 };
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
 #define PIPE_LOOP(ISF, NSWEEPS, SW0)                                                                                   \
     {                                                                                                                  \
         cc.init(tab, nch, NSWEEPS);                                                                                    \
-        unsigned eI = cc.next(lane);                              /* chunk whose loads are issued next */              \
+        unsigned eI = cc.next();                              /* chunk whose loads are issued next */              \
         int isw = SW0;                                            /* its sweep, for the L2 window */                   \
         if (l2mode && !(ISF)) { l2_window(0, 0); l2_window(0, 0); l2_window(0, 0); }                                   \
         PIPE_ISSUE(FB, lamB, eI, ISF)                                                                                  \
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
                 FA[f].w = f == 2 ? FB[f].w : copy_f32(FB[f].w);                                                        \
             }                                                                                                          \
             lamA = lamB;                                                                                               \
-            eI = cc.next(lane);                                                                                        \
+            eI = cc.next();                                                                                        \
             if (l2mode && eI != 0u) {                                                                                  \
                 if (ch_base(eI) < ch_base(eS)) ++isw;             /* positions only grow inside a sweep */             \
                 l2_window(isw, ch_base(eI));                      /* one window per chunk keeps up: a chunk is <= 32 positions */ \
@@ -214,11 +214,11 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
             // run unpipelined
             cc.init(tab, nch, iters + 1);
             for (int it = 0; it < iters; ++it) {
-                const unsigned e = cc.next(lane);
+                const unsigned e = cc.next();
                 PIPE_ISSUE(FA, lamA, e, false)
                 PIPE_SOLVE(FA, lamA, e, false)
             }
-            const unsigned e = cc.next(lane);
+            const unsigned e = cc.next();
             PIPE_CLEAR_FOR_FORCES()
             PIPE_ISSUE(FA, lamA, e, true)
             PIPE_SOLVE(FA, lamA, e, true)
