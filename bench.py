@@ -116,12 +116,15 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region. The sampler is started ahead of the warm-up
+    (nvidia-smi needs ~0.1 s before its first line) and only the lines that arrive between begin() and end() count; a timed
+    region shorter than the sampling interval is followed by untimed steps of the same load until two samples exist, and
+    the result says so."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.lines, self.proc = [], None
+        self.lines, self.proc, self.t0, self.t1 = [], None, None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -132,20 +135,43 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
+    def _inside(self):
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        return [ln for t, ln in self.lines if t0 <= t <= t1]
+
+    def stop(self, load=None):
+        """load: callable that keeps the GPU under the timed region's load for a moment (used when the region was too short)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.t1 is None:
+            self.end()
+        note = None
+        if len(self._inside()) < 2 and load is not None:
+            t_end = time.perf_counter() + 2.0
+            while len(self._inside()) < 2 and time.perf_counter() < t_end:
+                load()
+                self.t1 = time.perf_counter()
+            note = "timed region shorter than the sampling interval: sampled under the same load right after it"
+        else:
+            time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        lines = self._inside()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -156,8 +182,11 @@ class ClockSampler:
             for nm, val in zip(names, f[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def build_batch(workload, B, rank):
@@ -211,6 +240,7 @@ def run_ours(args):
         ctx.upload_joints(s["jtype"], s["jb0"], s["jb1"], s["r0"], s["q0"], s["r1"], s["q1"])
     del x
     ctx.step(DT, settle); ctx.sync()                       # untimed: let the scene reach its contact-dense state
+    sampler = ClockSampler(local) if rank == 0 else None   # started ahead of the warm-up; only lines inside the timed region count
     ctx.step(DT, args.warmup); ctx.sync()
 
     def barrier():
@@ -220,15 +250,21 @@ def run_ours(args):
 
     # ---- device-resident timed region (CUDA-graph replay, the path slrbs_step takes for a caller) ------
     ctx.profile_read(True)                                 # zero the launch counter
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
+    if sampler:
+        sampler.begin()
     ctx.timer_start()
     ctx.step(DT, args.steps)
     ms = ctx.timer_stop()
     barrier()
-    clocks = sampler.stop() if sampler else None
-    ctx.sync()
+    if sampler:
+        sampler.end()
     launches_timed = int(ctx.profile_read(True)["total_launches"])       # kernels launched (graph nodes replayed) in the timed region
+
+    def same_load():
+        ctx.step(DT, 10); ctx.sync()
+    clocks = sampler.stop(same_load) if sampler else None
+    ctx.profile_read(True)
     # ---- separate profiled pass: CUDA events around every solver launch + visit counters (profiling replaces the graph by
     # plain launches, so it is kept out of the headline region) -------------------------------------
     psteps = max(3, min(args.steps, 10))
@@ -438,16 +474,25 @@ def run_pile(args):
     pile.ctx.sync()
     r0, s0 = pile.stats["rebuilds"], pile.stats.get("steady_rebuild_s", 0.0)
     sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.2 if sampler else 0.0)                     # nvidia-smi needs ~0.1 s before its first line
     pile.ctx.profile_read(True)
     barrier()
+    if sampler:
+        sampler.begin()
     t0 = time.perf_counter()
     pile.ctx.timer_start()
     pile.step(args.steps)
     ms = pile.ctx.timer_stop()
     wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
-    clocks = sampler.stop() if sampler else None
+    if sampler:
+        sampler.end()
     launches = int(pile.ctx.profile_read(True)["total_launches"])
+
+    def same_load():                                        # one rank only: a step of the pile is collective across ranks
+        pile.step(2); pile.ctx.sync()
+    clocks = sampler.stop(same_load if world == 1 else None) if sampler else None
+    pile.ctx.profile_read(True)
     rebuilds, rebuild_ms = pile.stats["rebuilds"] - r0, (pile.stats.get("steady_rebuild_s", 0.0) - s0) * 1e3
     # profiled pass for the solver share (per-launch events)
     psteps = 5
