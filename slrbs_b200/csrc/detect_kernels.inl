@@ -401,9 +401,9 @@ __global__ void __launch_bounds__(DETECT_CTA_THREADS, 2) k_detect_cta(View v, in
 
 // ------------------------------------------------------------------------------------
 // k_detect_rows  one CTA per scene, one THREAD per sphere row. After the grid is built in shared memory, thread i
-// walks the 27 neighbouring cells of sphere i and the non-sphere bodies itself, keeps the partners j > i that touch
-// in a short ascending list in shared memory (16-bit indices, repeated partners from colliding buckets dropped),
-// and the row's contact count. Rows of non-sphere bodies, and sphere rows with more than ROW_HITS partners, are
+// walks the cell of sphere i and the 13 cells after it (half stencil) and records each touching pair once, in the
+// row of the lower index (short lists of 16-bit indices in shared memory, filled through per-row atomics); the row
+// owners then sort their lists and add the non-sphere bodies they touch. Rows of non-sphere bodies, and sphere rows with more than ROW_HITS partners, are
 // walked by a warp each in the reference's all-pairs order (dense_row). A block scan turns the counts into output
 // offsets, then every thread re-evaluates its few touching pairs and writes them: the list is in the reference's
 // lexicographic (i, j) order with no sorting of candidates, no per-row barriers and all 32 lanes testing pairs.
@@ -491,43 +491,60 @@ __global__ void __launch_bounds__(512, 2) k_detect_rows(View v, int H)
     __syncthreads();
     const int nspecial = s_nspecial;
 
-    // ---- pass 1: one thread per sphere row -------------------------------------------------------------------------
+    // ---- pass 1a: grid walk, one thread per sphere, HALF stencil ------------------------------------------------------
+    // Thread i walks its own cell and the 13 neighbouring cells that follow it in (z, y, x) order; a touching pair is
+    // recorded once, by the sphere whose cell comes first (same cell: by the lower index), in the row of the LOWER index --
+    // which may be another thread's row: the rows' counters are shared-memory atomics (rowoff doubles as the counter array
+    // until the block scan) and the lists are sorted afterwards by their owners. A bucket is hashed, so it also holds
+    // spheres of other cells: a candidate counts only if it really lives in the cell being visited (its pair with i is
+    // found from the cell it does live in), which also makes every pair unique without de-duplication.
+    for (int i = tid; i < n; i += T) rowoff[i] = 0;
+    __syncthreads();
     for (int i = tid; i < n; i += T) {
         const int fi = sm.sf[i];
-        if ((fi & FLAG_TYPE_MASK) != GEOM_SPHERE) { nhits[i] = ROW_DENSE; continue; }
+        if ((fi & FLAG_TYPE_MASK) != GEOM_SPHERE) continue;
         const float4 ci = sm.sp[i];
-        unsigned short* my = hits + (size_t)i * ROW_HITS;
-        int nh = 0;
-        bool over = false;
         const int ix = (int)floorf(ci.x * inv_h), iy = (int)floorf(ci.y * inv_h), iz = (int)floorf(ci.z * inv_h);
-        // cell_hash(ix+dx, iy+dy, iz+dz) from per-axis partial products
-        const unsigned hx0 = (unsigned)(ix - 1) * 73856093u, hx1 = (unsigned)ix * 73856093u, hx2 = (unsigned)(ix + 1) * 73856093u;
 #pragma unroll 1
-        for (int cc = 0; cc < 27; ++cc) {
-            const int dy = (cc / 3) % 3, dz = cc / 9, dx = cc - 3 * (cc / 3);
-            const unsigned hyz = ((unsigned)(iy + dy - 1) * 19349663u) ^ ((unsigned)(iz + dz - 1) * 83492791u);
-            const int h = (int)(((dx == 0 ? hx0 : (dx == 1 ? hx1 : hx2)) ^ hyz) & (unsigned)Hmask);
+        for (int cc = 13; cc < 27; ++cc) {                       // 13 = the sphere's own cell, 14 .. 26 = the cells after it
+            const int cx = ix + cc % 3 - 1, cy = iy + (cc / 3) % 3 - 1, cz = iz + cc / 9 - 1;
+            const int h = cell_hash(cx, cy, cz, Hmask);
             const int beg = sm.cell_start[h + 1], end = sm.cell_start[h + 2];
             for (int k = beg; k < end; ++k) {
                 const int j = sm.cell_items[k];
-                if (j <= i) continue;
+                if (j == i || (cc == 13 && j < i)) continue;
                 // the grid holds spheres only: the touch test of collisionDetectSphereSphere (CollisionDetect.cpp:111-115,
-                // same expressions as sphere_sphere(), so the same decision to the bit) without building the contact
+                // same expressions as sphere_sphere(), so the same decision to the bit -- from either side of the pair)
+                // without building the contact
                 const float4 cj = sm.sp[j];
                 if ((fi & sm.sf[j]) & FLAG_FIXED) continue;
                 const V3 vec = mk3(ci) - mk3(cj);
                 const float sq = sqnorm(vec), lim = (ci.w + cj.w) + 1e-3f;
                 if (sq > 1.0001f * (lim * lim)) continue;        // cannot pass the exact test below
                 if (!(sqrtf(sq) < lim)) continue;
-                int pos = nh;                                    // sorted insert, repeated partner dropped
-                while (pos > 0 && my[pos - 1] > j) --pos;
-                if (pos > 0 && my[pos - 1] == j) continue;
-                if (nh == ROW_HITS) { over = true; break; }
-                for (int m = nh; m > pos; --m) my[m] = my[m - 1];
-                my[pos] = (unsigned short)j;
-                ++nh;
+                if ((int)floorf(cj.x * inv_h) != cx || (int)floorf(cj.y * inv_h) != cy || (int)floorf(cj.z * inv_h) != cz) continue;
+                const int r = min(i, j), p = max(i, j);
+                const int slot = atomicAdd(&rowoff[r], 1);
+                if (slot < ROW_HITS) hits[(size_t)r * ROW_HITS + slot] = (unsigned short)p;
             }
-            if (over) break;
+        }
+    }
+    __syncthreads();
+    // ---- pass 1b: every sphere row sorts its partners and adds the non-sphere bodies -----------------------------------
+    for (int i = tid; i < n; i += T) {
+        const int fi = sm.sf[i];
+        if ((fi & FLAG_TYPE_MASK) != GEOM_SPHERE) { nhits[i] = ROW_DENSE; continue; }
+        const float4 ci = sm.sp[i];
+        unsigned short* my = hits + (size_t)i * ROW_HITS;
+        int nh = rowoff[i];
+        bool over = nh > ROW_HITS;
+        if (!over) {
+            for (int a = 1; a < nh; ++a) {                       // insertion sort, ascending partner index
+                const unsigned short x = my[a];
+                int b = a;
+                while (b > 0 && my[b - 1] > x) { my[b] = my[b - 1]; --b; }
+                my[b] = x;
+            }
         }
         for (int k = 0; k < nspecial && !over; ++k) {
             const int j = sm.special[k];
