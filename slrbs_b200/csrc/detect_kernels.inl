@@ -546,18 +546,32 @@ __global__ void __launch_bounds__(512, 2) k_detect_rows(View v, int H)
                 my[b] = x;
             }
         }
-        for (int k = 0; k < nspecial && !over; ++k) {
-            const int j = sm.special[k];
-            if (j <= i) continue;
-            PairOut o;
-            test_pair<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
-            if (o.cnt == 0) continue;
-            if (nh == ROW_HITS) { over = true; break; }
-            int pos = nh;
-            while (pos > 0 && my[pos - 1] > j) --pos;
-            for (int m = nh; m > pos; --m) my[m] = my[m - 1];
-            my[pos] = (unsigned short)j;
-            ++nh;
+        // The non-sphere bodies, 32 at a time: the cheap cull for all of them first (every lane busy), then each lane works
+        // through its own survivors -- a warp of spheres along two walls runs the box test twice with a dozen lanes in it
+        // instead of once per wall with three or four
+        for (int k0 = 0; k0 < nspecial && !over; k0 += 32) {
+            unsigned pend = 0;
+            const int kn = min(32, nspecial - k0);
+            for (int k = 0; k < kn; ++k) {
+                const int j = sm.special[k0 + k];
+                const int fj = sm.sf[j];
+                bool may = j > i && !((fi & fj) & FLAG_FIXED);
+                if (may && (fj & FLAG_TYPE_MASK) == GEOM_BOX) may = sphere_box_may_touch(ci, sm.sp[j], __ldg(&v.bext[at(v, j, scene)]));
+                if (may) pend |= 1u << k;
+            }
+            while (pend) {
+                const int j = sm.special[k0 + __ffs(pend) - 1];
+                pend &= pend - 1;
+                PairOut o;
+                test_pair<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
+                if (o.cnt == 0) continue;
+                if (nh == ROW_HITS) { over = true; break; }
+                int pos = nh;
+                while (pos > 0 && my[pos - 1] > j) --pos;
+                for (int m = nh; m > pos; --m) my[m] = my[m - 1];
+                my[pos] = (unsigned short)j;
+                ++nh;
+            }
         }
         if (over) { nhits[i] = ROW_DENSE; dense_list[atomicAdd(&s_ndense, 1)] = i; }
         else { nhits[i] = (unsigned char)nh; rowoff[i] = nh; }
@@ -599,7 +613,10 @@ __global__ void __launch_bounds__(512, 2) k_detect_rows(View v, int H)
         const float4 ci = sm.sp[i];
         const int fi = sm.sf[i];
         const int base = rowoff[i];
-        for (int k = 0; k < nh; ++k) {
+        // back to front: the slot of a contact is base + k whatever the order, and a row's non-sphere partners (the walls of
+        // the marble box: the highest indices, i.e. the END of the ascending list) then meet in the first trips across the
+        // lanes instead of in whichever trip each lane's list happens to reach them
+        for (int k = nh - 1; k >= 0; --k) {
             const int j = hits[(size_t)i * ROW_HITS + k];
             PairOut o;
             test_pair<DETECT_EXT>(o, v, scene, i, j, ci, fi, sm.sp[j], sm.sf[j]);
