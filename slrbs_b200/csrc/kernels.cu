@@ -153,6 +153,17 @@ __device__ __forceinline__ float dot6_seq(const float* a, const float* b)
     return acc;
 }
 
+// normalized() with the division spelled out (pgs_math.cuh: div_rn_nocall, same bits): a tangent always has a component
+// that is exactly zero (t = n x e_x), and a zero numerator sends the compiler's division through its out-of-range
+// subroutine -- several calls per contact in this kernel (profiles/r02_k_contact_rows_lv_mb1k_ncu_details.txt)
+__device__ __forceinline__ V3 normalized_nocall(const V3& a)
+{
+    const float z = sqnorm(a);
+    if (!(z > 0.0f)) return a;
+    const float d = sqrtf(z);
+    return mk3(div_rn_nocall(a.x, d), div_rn_nocall(a.y, d), div_rn_nocall(a.z, d));
+}
+
 // one contact: frame, Jacobian blocks, J M^-1, diagonal block, RHS -> its row record at `pos` of the scene's stream
 __device__ __forceinline__ void contact_row(const View& v, float h, int scene, int slot, int pos)
 {
@@ -167,8 +178,8 @@ __device__ __forceinline__ void contact_row(const View& v, float h, int scene, i
     // Contact::computeContactFrame (Contact.cpp:33-53)
     V3 t = cross(n, mk3(1.f, 0.f, 0.f));
     if (norm(t) < 1e-5f) t = cross(n, mk3(0.f, 1.f, 0.f));
-    t = normalized(t);
-    const V3 bb = normalized(cross(n, t));
+    t = normalized_nocall(t);
+    const V3 bb = normalized_nocall(cross(n, t));
 
     // Contact::computeJacobian (Contact.cpp:55-94)
     const V3 rr0 = p - b0.x, rr1 = p - b1.x;
