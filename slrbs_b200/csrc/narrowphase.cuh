@@ -52,7 +52,9 @@ static __device__ __noinline__ void sphere_box(PairOut& o, const float4* __restr
     const float dist = norm(dx);
     if (dist < (r + 1e-3f)) {
         o.b0 = is; o.b1 = ib;
-        o.n = rotate(qb, dx / dist);
+        // dx has two exactly-zero components at a face contact: a zero numerator sends the compiler's division through its
+        // out-of-range subroutine, twice per wall contact
+        o.n = rotate(qb, div_by_length(dx, dist));
         o.add(rotate(qb, q) + xb, fminf(0.0f, dist - r));
     }
 }
