@@ -56,7 +56,7 @@ struct ChunkCursor {
 
 // STREAM: the row records are read once per sweep and the whole stream is far larger than L2 -- demand loads then carry an
 // L2 evict-first policy (and do not allocate in L1), so that a line leaves L2 as soon as it has been consumed and the lines the
-// bulk prefetch brought in for the next level are not the ones pushed out.
+// L2 window brought in for the chunks ahead are not the ones pushed out. (SLRBS_PIPE_STREAM=1; measured neutral, off by default.)
 __device__ __forceinline__ float4 ldg_stream(const float4* p, unsigned long long policy)
 {
     float4 r;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(32, 9) k_pgs_pipe(View v, float dt, int iters,
 
     // ---- chunk table of the scene: levels in order, each cut into chunks of <= 32 rows ------------------------------
     // (the sweep loop used to find its next chunk by walking level ends: 140 instructions per chunk and a third of the
-    // kernel's stall samples, profiles/r02_k_pgs_pipe_copy_mb1k_*; with the table it is one shuffle)
+    // kernel's stall samples, profiles/r02_k_pgs_pipe_copy_mb1k_*; with the table it is one uniform load, issued a chunk ahead)
     unsigned* tab = v.cchunk + (size_t)scene * v.cchunk_cap;
     int nch = 0;
     for (int l0 = 1, carry_end = 0; l0 <= ncl; l0 += 32) {        // 32 levels per trip, one per lane
